@@ -1,0 +1,494 @@
+// C ABI of libbseg.so (declared in include/bseg.h): weight packing, the SegGPT forward schedule and thin
+// wrappers around the kernel launchers.
+#include <new>
+#include <vector>
+
+#include "../../include/bseg.h"
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+using namespace bseg;
+
+namespace {
+
+constexpr int kT = BSEG_T;
+constexpr int kD = BSEG_HIDDEN;
+constexpr int kMlp = 4096;
+constexpr int kDecN = 16384;
+
+struct LayerPack {
+  __nv_bfloat16 *qkv_w, *proj_w, *lin1_w, *lin2_w, *relcat;
+  float *qkv_b, *proj_b, *lin1_b, *lin2_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// reversed + concatenated rel-pos tables (see attention.cu): rows 0..110 = rel_pos_h[110-i], 111 = 0,
+// rows 112..166 = rel_pos_w[54-(i-112)], rest 0
+__global__ void pack_relcat_kernel(const float* __restrict__ rel_h, const float* __restrict__ rel_w,
+                                   __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x, d = threadIdx.x;  // 176 x 64
+  float v = 0.f;
+  if (i < 111) v = rel_h[(110 - i) * 64 + d];
+  else if (i >= 112 && i < 167) v = rel_w[(54 - (i - 112)) * 64 + d];
+  out[i * 64 + d] = __float2bfloat16_rn(v);
+}
+
+// conv weight [out,in,3,3] -> [tap][out][in] bf16
+__global__ void pack_conv_w9_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * 64 * 64) return;
+  const int i = idx & 63, o = (idx >> 6) & 63, t = idx >> 12;
+  out[idx] = __float2bfloat16_rn(w[((o * 64 + i) * 3 + t / 3) * 3 + (t % 3)]);
+}
+
+// Additive table of the patch-embedding GEMM epilogue (modeling_seggpt.py:163-206):
+//   tab[s][t][d] = (s==1 && t in bottom half ? mask_token : conv bias) + segment_token_{input|prompt}
+//                  + bicubic(pos_embed 14x14 -> 56x28, align_corners=False)[t] + type_token
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__global__ void embed_table_kernel(const float* __restrict__ pos /*[197,1024]*/, const float* __restrict__ patch_b,
+                                   const float* __restrict__ mask_token, const float* __restrict__ seg_in,
+                                   const float* __restrict__ seg_pr, const float* __restrict__ type_tok,
+                                   float* __restrict__ tab) {
+  const int t = blockIdx.x;  // 0..1567
+  const int ph = t / 28, pw = t % 28;
+  const float A = -0.75f;
+  const float ry = 0.25f * (ph + 0.5f) - 0.5f, rx = 0.5f * (pw + 0.5f) - 0.5f;
+  const float fy = floorf(ry), fx = floorf(rx);
+  const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+  const float ty = ry - fy, tx = rx - fx;
+  const float cy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+  const float cx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+  for (int d = threadIdx.x; d < 1024; d += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), 13);
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), 13);
+        row += cx[b] * pos[(1 + yy * 14 + xx) * 1024 + d];
+      }
+      acc += cy[a] * row;
+    }
+    const float ty_ = type_tok[d];
+    tab[(0 * 1568 + t) * 1024 + d] = ((patch_b[d] + seg_in[d]) + acc) + ty_;
+    const float base1 = (ph < 28) ? patch_b[d] : mask_token[d];
+    tab[(1 * 1568 + t) * 1024 + d] = ((base1 + seg_pr[d]) + acc) + ty_;
+  }
+}
+
+}  // namespace
+
+struct bseg_handle {
+  int num_layers = 0, merge_index = 0;
+  int inter[4] = {0, 0, 0, 0};
+  float eps = 1e-6f;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  __nv_bfloat16* patch_w = nullptr;
+  float* embed_tab[2] = {nullptr, nullptr};  // instance, semantic
+  std::vector<LayerPack> layers;
+  float *enc_ln_w = nullptr, *enc_ln_b = nullptr;
+  __nv_bfloat16* dec_embed_w = nullptr;
+  float* dec_embed_b = nullptr;
+  __nv_bfloat16* conv_w9 = nullptr;
+  float *conv_b = nullptr, *dec_ln_w = nullptr, *dec_ln_b = nullptr, *head_w = nullptr, *head_b = nullptr;
+};
+
+extern "C" {
+
+const char* bseg_last_error(void) { return last_error_buf(); }
+int bseg_version(void) { return 1; }
+long long bseg_launch_count(void) { return launch_count(); }
+
+int bseg_destroy(bseg_handle* h) {
+  if (!h) return 0;
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+  return 0;
+}
+
+int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BSEG_REQUIRE(w != nullptr && out != nullptr, "bseg_create: null argument");
+  BSEG_REQUIRE(w->num_layers > 0 && w->num_layers <= BSEG_MAX_LAYERS, "bseg_create: num_layers=%d", w->num_layers);
+  BSEG_REQUIRE(w->merge_index >= 0 && w->merge_index < w->num_layers, "bseg_create: merge_index=%d", w->merge_index);
+  for (int j = 0; j < 4; ++j)
+    BSEG_REQUIRE(w->intermediate_indices[j] >= w->merge_index && w->intermediate_indices[j] < w->num_layers,
+                 "bseg_create: intermediate index %d out of range", w->intermediate_indices[j]);
+  bseg_handle* h = new (std::nothrow) bseg_handle();
+  BSEG_REQUIRE(h != nullptr, "bseg_create: out of host memory");
+  h->num_layers = w->num_layers;
+  h->merge_index = w->merge_index;
+  for (int j = 0; j < 4; ++j) h->inter[j] = w->intermediate_indices[j];
+  h->eps = w->layer_norm_eps;
+  h->layers.resize(w->num_layers);
+
+  // ---- carve one arena ----
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_patch = carve(1024ull * 768 * 2);
+  const size_t o_tab0 = carve(2ull * kT * kD * 4), o_tab1 = carve(2ull * kT * kD * 4);
+  struct LOff { size_t qkv_w, proj_w, lin1_w, lin2_w, relcat, qkv_b, proj_b, lin1_b, lin2_b, ln1_w, ln1_b, ln2_w, ln2_b; };
+  std::vector<LOff> lo(w->num_layers);
+  for (int i = 0; i < w->num_layers; ++i) {
+    lo[i].qkv_w = carve(3072ull * 1024 * 2);
+    lo[i].proj_w = carve(1024ull * 1024 * 2);
+    lo[i].lin1_w = carve(4096ull * 1024 * 2);
+    lo[i].lin2_w = carve(1024ull * 4096 * 2);
+    lo[i].relcat = carve(176ull * 64 * 2);
+    lo[i].qkv_b = carve(3072 * 4);
+    lo[i].proj_b = carve(1024 * 4);
+    lo[i].lin1_b = carve(4096 * 4);
+    lo[i].lin2_b = carve(1024 * 4);
+    lo[i].ln1_w = carve(1024 * 4);
+    lo[i].ln1_b = carve(1024 * 4);
+    lo[i].ln2_w = carve(1024 * 4);
+    lo[i].ln2_b = carve(1024 * 4);
+  }
+  const size_t o_eln_w = carve(1024 * 4), o_eln_b = carve(1024 * 4);
+  const size_t o_dew = carve(16384ull * 4096 * 2), o_deb = carve(16384 * 4);
+  const size_t o_w9 = carve(9 * 64 * 64 * 2), o_cb = carve(64 * 4), o_dlw = carve(64 * 4), o_dlb = carve(64 * 4);
+  const size_t o_hw = carve(192 * 4), o_hb = carve(16);
+  h->arena_bytes = off;
+  cudaError_t e = cudaMalloc(&h->arena, off);
+  if (e != cudaSuccess) {
+    set_error("bseg_create: cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(e));
+    delete h;
+    return -static_cast<int>(e);
+  }
+  uint8_t* base = static_cast<uint8_t*>(h->arena);
+  auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
+  auto fp = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+  int rc = 0;
+  auto cvt = [&](const float* src, __nv_bfloat16* dst, long long n) {
+    if (!rc) rc = launch_f32_to_bf16(src, dst, n, stream);
+  };
+  auto cpy = [&](const float* src, float* dst, size_t n) {
+    if (!rc) {
+      cudaError_t ce = cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, stream);
+      if (ce != cudaSuccess) {
+        set_error("bseg_create: copy failed: %s", cudaGetErrorString(ce));
+        rc = -static_cast<int>(ce);
+      }
+    }
+  };
+  h->patch_w = bf(o_patch);
+  cvt(w->patch_w, h->patch_w, 1024ll * 768);
+  h->embed_tab[0] = fp(o_tab0);
+  h->embed_tab[1] = fp(o_tab1);
+  embed_table_kernel<<<kT, 256, 0, stream>>>(w->position_embeddings, w->patch_b, w->mask_token,
+                                             w->segment_token_input, w->segment_token_prompt,
+                                             w->type_token_instance, h->embed_tab[0]);
+  embed_table_kernel<<<kT, 256, 0, stream>>>(w->position_embeddings, w->patch_b, w->mask_token,
+                                             w->segment_token_input, w->segment_token_prompt,
+                                             w->type_token_semantic, h->embed_tab[1]);
+  for (int i = 0; i < w->num_layers; ++i) {
+    const bseg_layer_weights& lw = w->layers[i];
+    LayerPack& lp = h->layers[i];
+    lp.qkv_w = bf(lo[i].qkv_w);   cvt(lw.qkv_w, lp.qkv_w, 3072ll * 1024);
+    lp.proj_w = bf(lo[i].proj_w); cvt(lw.proj_w, lp.proj_w, 1024ll * 1024);
+    lp.lin1_w = bf(lo[i].lin1_w); cvt(lw.lin1_w, lp.lin1_w, 4096ll * 1024);
+    lp.lin2_w = bf(lo[i].lin2_w); cvt(lw.lin2_w, lp.lin2_w, 1024ll * 4096);
+    lp.relcat = bf(lo[i].relcat);
+    pack_relcat_kernel<<<176, 64, 0, stream>>>(lw.rel_pos_h, lw.rel_pos_w, lp.relcat);
+    lp.qkv_b = fp(lo[i].qkv_b);   cpy(lw.qkv_b, lp.qkv_b, 3072);
+    lp.proj_b = fp(lo[i].proj_b); cpy(lw.proj_b, lp.proj_b, 1024);
+    lp.lin1_b = fp(lo[i].lin1_b); cpy(lw.lin1_b, lp.lin1_b, 4096);
+    lp.lin2_b = fp(lo[i].lin2_b); cpy(lw.lin2_b, lp.lin2_b, 1024);
+    lp.ln1_w = fp(lo[i].ln1_w);   cpy(lw.ln1_w, lp.ln1_w, 1024);
+    lp.ln1_b = fp(lo[i].ln1_b);   cpy(lw.ln1_b, lp.ln1_b, 1024);
+    lp.ln2_w = fp(lo[i].ln2_w);   cpy(lw.ln2_w, lp.ln2_w, 1024);
+    lp.ln2_b = fp(lo[i].ln2_b);   cpy(lw.ln2_b, lp.ln2_b, 1024);
+  }
+  h->enc_ln_w = fp(o_eln_w); cpy(w->enc_ln_w, h->enc_ln_w, 1024);
+  h->enc_ln_b = fp(o_eln_b); cpy(w->enc_ln_b, h->enc_ln_b, 1024);
+  h->dec_embed_w = bf(o_dew); cvt(w->dec_embed_w, h->dec_embed_w, 16384ll * 4096);
+  h->dec_embed_b = fp(o_deb); cpy(w->dec_embed_b, h->dec_embed_b, 16384);
+  h->conv_w9 = bf(o_w9);
+  pack_conv_w9_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, stream>>>(w->dec_conv_w, h->conv_w9);
+  h->conv_b = fp(o_cb);   cpy(w->dec_conv_b, h->conv_b, 64);
+  h->dec_ln_w = fp(o_dlw); cpy(w->dec_ln_w, h->dec_ln_w, 64);
+  h->dec_ln_b = fp(o_dlb); cpy(w->dec_ln_b, h->dec_ln_b, 64);
+  h->head_w = fp(o_hw);   cpy(w->dec_head_w, h->head_w, 192);
+  h->head_b = fp(o_hb);   cpy(w->dec_head_b, h->head_b, 3);
+  if (!rc) {
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+      set_error("bseg_create: pack kernels failed: %s", cudaGetErrorString(ce));
+      rc = -static_cast<int>(ce);
+    }
+  }
+  if (rc) {
+    bseg_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+// ---- workspace layout (all offsets 1024-aligned) ----
+namespace {
+struct WsLayout {
+  size_t h, xn, att, q, k, vt, mlp, inter, dec, total;
+};
+WsLayout ws_layout(int B) {
+  WsLayout L;
+  const size_t rows2 = 2ull * B * kT, rows1 = 1ull * B * kT;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  L.h = carve(rows2 * kD * 4);
+  L.xn = carve(rows2 * kD * 2);
+  L.att = carve(rows2 * kD * 2);
+  L.q = carve(rows2 * kD * 2);
+  L.k = carve(rows2 * kD * 2);
+  L.vt = carve(rows2 * kD * 2);
+  L.mlp = carve(rows2 * kMlp * 2);  // also: patch-embedding operand [rows2,768] bf16, ensemble scratch fp32 [rows2,1024]
+  L.inter = carve(rows1 * 4096 * 2);
+  L.dec = carve(rows1 * kDecN * 2);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+size_t bseg_workspace_bytes(const bseg_handle* /*h*/, int batch) {
+  if (batch <= 0) return 0;
+  return ws_layout(batch).total;
+}
+
+int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                 const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
+                 size_t workspace_bytes, float* pred_masks, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BSEG_REQUIRE(h != nullptr, "bseg_forward: null handle");
+  BSEG_REQUIRE(batch > 0, "bseg_forward: batch=%d", batch);
+  BSEG_REQUIRE(embedding_type == 0 || embedding_type == 1,
+               "Embedding type should be either 'semantic' or 'instance', but got code %d", embedding_type);
+  BSEG_REQUIRE(ensemble_prompts >= 0 && (ensemble_prompts == 0 || batch % ensemble_prompts == 0),
+               "bseg_forward: batch=%d is not a multiple of ensemble_prompts=%d", batch, ensemble_prompts);
+  const WsLayout L = ws_layout(batch);
+  BSEG_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, "bseg_forward: workspace too small (%zu < %zu)",
+               workspace_bytes, L.total);
+  BSEG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "bseg_forward: workspace must be 256B aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* hbuf = reinterpret_cast<float*>(ws + L.h);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws + L.xn);
+  __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws + L.att);
+  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(ws + L.q);
+  __nv_bfloat16* k = reinterpret_cast<__nv_bfloat16*>(ws + L.k);
+  __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(ws + L.vt);
+  __nv_bfloat16* mlp = reinterpret_cast<__nv_bfloat16*>(ws + L.mlp);
+  __nv_bfloat16* inter = reinterpret_cast<__nv_bfloat16*>(ws + L.inter);
+  __nv_bfloat16* dec = reinterpret_cast<__nv_bfloat16*>(ws + L.dec);
+  const int B = batch;
+  int rc;
+
+  // ---- embeddings: patchify + GEMM (modeling_seggpt.py:713-737, 163-206) ----
+  __nv_bfloat16* a_patch = mlp;
+  if ((rc = launch_patchify(pixel_values, prompt_pixel_values, prompt_masks, nullptr, a_patch, B, stream))) return rc;
+  {
+    GemmEpiParams ep;
+    ep.out = hbuf;
+    ep.ldc = kD;
+    ep.tab = h->embed_tab[embedding_type == 0 ? 0 : 1];
+    ep.rows_per_stream = B * kT;
+    ep.T = kT;
+    if ((rc = launch_gemm(EPI_EMBED, a_patch, 768, h->patch_w, 2ll * B * kT, kD, 768, ep, stream))) return rc;
+  }
+
+  // ---- encoder (modeling_seggpt.py:453-501) ----
+  const int P = ensemble_prompts;
+  for (int i = 0; i < h->num_layers; ++i) {
+    const LayerPack& lp = h->layers[i];
+    const int nstreams = (i <= h->merge_index) ? 2 : 1;
+    const int nseq = nstreams * B;
+    const long long M = static_cast<long long>(nseq) * kT;
+    if ((rc = launch_layernorm1024(hbuf, kD, lp.ln1_w, lp.ln1_b, xn, kD, M, h->eps, stream))) return rc;
+    {
+      GemmEpiParams ep;
+      ep.bias = lp.qkv_b;
+      ep.q = q; ep.k = k; ep.vt = vt;
+      ep.T = kT; ep.heads = BSEG_HEADS;
+      if ((rc = launch_gemm(EPI_QKV, xn, kD, lp.qkv_w, M, 3 * kD, kD, ep, stream))) return rc;
+    }
+    if ((rc = launch_attention(q, k, vt, lp.relcat, att, nseq, BSEG_HEADS, 56, 28, stream))) return rc;
+    bool ens = false;
+    if (P > 0) ens = (i == h->merge_index) ? true : (P >= 2);
+    if (!ens) {
+      GemmEpiParams ep;
+      ep.out = hbuf; ep.ldc = kD; ep.bias = lp.proj_b; ep.resid = hbuf; ep.ldr = kD;
+      if ((rc = launch_gemm(EPI_RESID_F32, att, kD, lp.proj_w, M, kD, kD, ep, stream))) return rc;
+    } else {
+      float* tmp = reinterpret_cast<float*>(mlp);
+      GemmEpiParams ep;
+      ep.out = tmp; ep.ldc = kD; ep.bias = lp.proj_b;
+      if ((rc = launch_gemm(EPI_F32, att, kD, lp.proj_w, M, kD, kD, ep, stream))) return rc;
+      if ((rc = launch_ensemble_residual(hbuf, tmp, nstreams, B / P, P, i == h->merge_index ? 1 : 0, kT, kD, stream)))
+        return rc;
+    }
+    if ((rc = launch_layernorm1024(hbuf, kD, lp.ln2_w, lp.ln2_b, xn, kD, M, h->eps, stream))) return rc;
+    {
+      GemmEpiParams ep;
+      ep.out = mlp; ep.ldc = kMlp; ep.bias = lp.lin1_b;
+      if ((rc = launch_gemm(EPI_BF16_GELU, xn, kD, lp.lin1_w, M, kMlp, kD, ep, stream))) return rc;
+    }
+    {
+      GemmEpiParams ep;
+      ep.out = hbuf; ep.ldc = kD; ep.bias = lp.lin2_b; ep.resid = hbuf; ep.ldr = kD;
+      if ((rc = launch_gemm(EPI_RESID_F32, mlp, kMlp, lp.lin2_w, M, kD, kMlp, ep, stream))) return rc;
+    }
+    if (i == h->merge_index)
+      if ((rc = launch_merge_streams(hbuf, static_cast<long long>(B) * kT * kD, stream))) return rc;
+    for (int j = 0; j < 4; ++j)
+      if (h->inter[j] == i)
+        if ((rc = launch_layernorm1024(hbuf, kD, h->enc_ln_w, h->enc_ln_b, inter + j * kD, 4 * kD,
+                                       static_cast<long long>(B) * kT, h->eps, stream)))
+          return rc;
+  }
+
+  // ---- decoder (modeling_seggpt.py:555-585) ----
+  {
+    GemmEpiParams ep;
+    ep.out = dec; ep.bias = h->dec_embed_b; ep.T = kT; ep.grid_w = 28;
+    if ((rc = launch_gemm(EPI_PIXSHUF, inter, 4 * kD, h->dec_embed_w, static_cast<long long>(B) * kT, kDecN, 4 * kD,
+                          ep, stream)))
+      return rc;
+  }
+  return launch_decoder_head(dec, h->conv_w9, h->conv_b, h->dec_ln_w, h->dec_ln_b, h->head_w, h->head_b, pred_masks,
+                             B, 896, 448, h->eps, stream);
+}
+
+int bseg_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, uint32_t* scratch,
+                     void* stream) {
+  BSEG_REQUIRE(Hs > 0 && Ws > 0, "scene_stats: empty scene");
+  return launch_scene_stats(scene, nodata, Hs, Ws, stats, scratch, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_ingest_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                      const int32_t* boxes, int n_tiles, int crop, const int32_t* coef, const int32_t* bounds,
+                      int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,
+                      long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, void* stream) {
+  BSEG_REQUIRE(n_tiles >= 0 && crop > 0 && ksize > 0, "ingest: bad arguments");
+  // rows of output per CTA: a full 16-row patch band when the composite rows fit in shared memory
+  const double scale = static_cast<double>(crop) / 448.0;
+  const double support = 2.0 * (scale < 1.0 ? 1.0 : scale);
+  int band = 16;
+  int max_rows = 0;
+  for (;;) {
+    max_rows = static_cast<int>(band * scale + 2 * support + 4);
+    if (3ull * max_rows * (crop + 448) <= 160 * 1024 || band == 1) break;
+    band /= 2;
+  }
+  return launch_ingest(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, band, max_rows, mean,
+                       stdv, out_nchw, static_cast<__nv_bfloat16*>(out_patch), patch_tile_stride, out_u8, out_nodata,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int bseg_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean,
+                       const float* stdv, float* out, int batch, int H, int W, void* stream) {
+  BSEG_REQUIRE(batch > 0 && num_classes > 0, "colorize_norm: bad arguments");
+  return launch_colorize_norm(mask, palette, num_classes, mean, stdv, out, batch, H, W,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int bseg_decode_palette(const float* pred, const float* palette_norm, int num_classes, uint8_t* out_u8,
+                        int64_t* out_i64, const uint8_t* nodata, const int32_t* resize_idx, int batch, int H, int W,
+                        int out_size, void* stream) {
+  BSEG_REQUIRE(batch > 0 && num_classes > 0 && num_classes <= 256, "decode_palette: bad arguments");
+  BSEG_REQUIRE(resize_idx != nullptr || (out_size == H && out_size == W),
+               "decode_palette: out_size=%d needs a resize index table", out_size);
+  return launch_decode_palette(pred, palette_norm, num_classes, out_u8, reinterpret_cast<long long*>(out_i64), nodata,
+                               resize_idx, batch, H, W, out_size, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_mean_over_prompts(const float* pred, float* out, int n_tiles, int prompts, long long elems_per_sample,
+                           void* stream) {
+  BSEG_REQUIRE(n_tiles > 0 && prompts > 0, "mean_over_prompts: bad arguments");
+  return launch_mean_over_group(pred, out, n_tiles, prompts, elems_per_sample, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
+                         const int32_t* boxes, int use_atomics, void* stream) {
+  BSEG_REQUIRE(n_tiles >= 0 && crop >= 0, "vote_accumulate: bad arguments");
+  return launch_vote_accumulate(counter, Hs, Ws, cls, n_tiles, crop, boxes, use_atomics,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int bseg_vote_argmax(const uint32_t* counter, uint8_t* out, long long n_pixels, void* stream) {
+  return launch_vote_argmax(counter, out, n_pixels, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uint8_t* yesdata, float beta,
+                               int per_sample, float* loss_out, float* grad_out, float* scratch, int batch, int H,
+                               int W, void* stream) {
+  BSEG_REQUIRE(batch > 0 && beta > 0.f, "loss: bad arguments");
+  return launch_smooth_l1(pred, labels, yesdata, beta, per_sample, loss_out, grad_out, scratch, batch, H, W,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int N, int K, const float* bias,
+                   void* out, long long ldc, int out_is_bf16, int gelu, void* stream) {
+  GemmEpiParams ep;
+  ep.out = out;
+  ep.ldc = ldc;
+  ep.bias = bias;
+  const int mode = out_is_bf16 ? (gelu ? EPI_BF16_GELU : EPI_BF16) : EPI_F32;
+  return launch_gemm(mode, static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), M, N, K,
+                     ep, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_layernorm1024(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
+                       long long ldo, long long M, float eps, void* stream) {
+  return launch_layernorm1024(x, ldx, gamma, beta, static_cast<__nv_bfloat16*>(out), ldo, M, eps,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int bseg_attention(const void* q, const void* k, const void* vt, const void* relcat, void* out, int nseq,
+                   void* stream) {
+  return launch_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
+                          static_cast<const __nv_bfloat16*>(vt), static_cast<const __nv_bfloat16*>(relcat),
+                          static_cast<__nv_bfloat16*>(out), nseq, BSEG_HEADS, 56, 28,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int bseg_pack_relcat(const float* rel_pos_h, const float* rel_pos_w, void* relcat, void* stream) {
+  pack_relcat_kernel<<<176, 64, 0, static_cast<cudaStream_t>(stream)>>>(rel_pos_h, rel_pos_w,
+                                                                        static_cast<__nv_bfloat16*>(relcat));
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int bseg_decoder_head(const void* x_nhwc, const void* w9, const float* conv_b, const float* ln_w, const float* ln_b,
+                      const float* head_w, const float* head_b, float* pred, int batch, int H, int W, float eps,
+                      void* stream) {
+  return launch_decoder_head(static_cast<const __nv_bfloat16*>(x_nhwc), static_cast<const __nv_bfloat16*>(w9),
+                             conv_b, ln_w, ln_b, head_w, head_b, pred, batch, H, W, eps,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int bseg_pack_conv_w9(const float* conv_w, void* w9, void* stream) {
+  pack_conv_w9_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      conv_w, static_cast<__nv_bfloat16*>(w9));
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int bseg_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  return launch_f32_to_bf16(src, static_cast<__nv_bfloat16*>(dst), n, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+// SegGptDecoderHead (modeling_seggpt.py:531-552): conv3x3(64->64, pad 1) -> LayerNorm over C (channels_first,
+// eps 1e-6) -> erf-GELU -> conv1x1(64->3), fused into one persistent implicit-GEMM kernel.
+//   input  : NHWC bf16 [B, H, W, 64]  (written by the decoder_embed GEMM's pixel-shuffle epilogue)
+//   output : NCHW fp32 [B, 3, H, W]   (== pred_masks)
+// A pixel tile is 2 image rows x 64 columns = 128 GEMM rows; each of the 9 taps is one K=64 block whose A tile
+// is a shifted TMA box (out-of-bounds rows/columns are zero filled by TMA == the conv's zero padding).
+// N = 64 output channels fit one accumulator tile, so LN + GELU + the 1x1 head run in the epilogue registers.
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace bseg {
+
+namespace dconv {
+constexpr int kTileW = 64, kTileH = 2;
+constexpr int kStages = 6;
+constexpr int kABytes = 128 * 128;       // 16384 per tap tile
+constexpr int kWBytes = 9 * 64 * 128;    // 73728: 9 taps x [64 out x 64 in] bf16
+constexpr int kThreads = 192;
+constexpr int kOffW = 0;
+constexpr int kOffA = kOffW + kWBytes;
+constexpr int kOffBar = kOffA + kStages * kABytes;
+constexpr int kOffPar = kOffBar + 256;   // fp32 params: conv_b[64] ln_w[64] ln_b[64] head_w[192] head_b[3]
+constexpr int kSmemBytes = kOffPar + 400 * 4 + 1024;
+constexpr uint32_t kTmemCols = 128;
+}  // namespace dconv
+
+__global__ void __launch_bounds__(dconv::kThreads, 1)
+decoder_head_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const float* __restrict__ conv_b, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                    const float* __restrict__ head_w, const float* __restrict__ head_b, float* __restrict__ pred,
+                    int B, int H, int W, float eps) {
+  using namespace dconv;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem + kOffW;
+  uint8_t* sA = smem + kOffA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* w_full = bars;
+  uint64_t* full_bar = bars + 1;                 // [kStages]
+  uint64_t* empty_bar = bars + 1 + kStages;      // [kStages]
+  uint64_t* tmem_full = bars + 1 + 2 * kStages;  // [2]
+  uint64_t* tmem_empty = bars + 3 + 2 * kStages; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kStages);
+  float* sPar = reinterpret_cast<float*>(smem + kOffPar);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = W / kTileW, tiles_y = H / kTileH;
+  const long long num_tiles = static_cast<long long>(B) * tiles_y * tiles_x;
+
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    sPar[i] = conv_b[i];
+    sPar[64 + i] = ln_w[i];
+    sPar[128 + i] = ln_b[i];
+  }
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) sPar[192 + i] = head_w[i];
+  if (threadIdx.x < 3) sPar[384 + threadIdx.x] = head_b[threadIdx.x];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    mbar_init(w_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, kWBytes);
+      for (int t = 0; t < 9; t += 3) tma_load_2d(sW + t * 8192, &tmap_w, w_full, 0, t * 64);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tx = static_cast<int>(tile % tiles_x);
+        const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+        const int b = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes);
+          tma_load_4d(sA + stage * kABytes, &tmap_x, &full_bar[stage], 0, tx * kTileW + (tap % 3) - 1,
+                      ty * kTileH + (tap / 3) - 1, b);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      const uint32_t w_addr = smem_u32(sW);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + as * 64;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr + k * 32),
+                         umma_desc_sw128_kmajor(w_addr + tap * 8192 + k * 32), idesc, (tap | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (tap == 8) umma_commit(&tmem_full[as]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    const long long plane = static_cast<long long>(H) * W;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tx = static_cast<int>(tile % tiles_x);
+      const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+      const int b = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 64;
+      float v[64];
+      {
+        float t0[32], t1[32];
+        tmem_ld32(taddr, t0);
+        tmem_ld32(taddr + 32, t1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = t0[i] + sPar[i];
+          v[32 + i] = t1[i] + sPar[32 + i];
+        }
+      }
+      // accumulator is in registers: release the TMEM buffer early
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) s += v[i];
+      const float mean = s * (1.0f / 64.0f);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float d = v[i] - mean;
+        ss += d * d;
+      }
+      const float rstd = rsqrtf(ss * (1.0f / 64.0f) + eps);
+      float o0 = sPar[384], o1 = sPar[385], o2 = sPar[386];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float g = gelu_erf((v[i] - mean) * rstd * sPar[64 + i] + sPar[128 + i]);
+        o0 = fmaf(g, sPar[192 + i], o0);
+        o1 = fmaf(g, sPar[256 + i], o1);
+        o2 = fmaf(g, sPar[320 + i], o2);
+      }
+      const int y = ty * kTileH + (r >> 6), x = tx * kTileW + (r & 63);
+      float* dst = pred + static_cast<long long>(b) * 3 * plane + static_cast<long long>(y) * W + x;
+      dst[0] = o0;
+      dst[plane] = o1;
+      dst[2 * plane] = o2;
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<dconv::kTmemCols>(tmem_base);
+  }
+}
+
+int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, const float* conv_b, const float* ln_w,
+                        const float* ln_b, const float* head_w, const float* head_b, float* pred, int B, int H, int W,
+                        float eps, cudaStream_t stream) {
+  using namespace dconv;
+  BSEG_REQUIRE(H % kTileH == 0 && W % kTileW == 0, "decoder_head: H=%d W=%d must be multiples of %d x %d", H, W,
+               kTileH, kTileW);
+  CUtensorMap tx, tw;
+  {
+    uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint64_t strides[3] = {128, static_cast<uint64_t>(W) * 128, static_cast<uint64_t>(H) * W * 128};
+    uint32_t box[4] = {64, kTileW, kTileH, 1};
+    int rc = make_tmap_bf16(&tx, x_nhwc, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    int rc = make_tmap_bf16_2d(&tw, w9, 64, 9 * 64, 64, 64, 192);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    BSEG_CHECK_CUDA(
+        cudaFuncSetAttribute(decoder_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const long long tiles = static_cast<long long>(B) * (H / kTileH) * (W / kTileW);
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  decoder_head_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tx, tw, conv_b, ln_w, ln_b, head_w, head_b, pred, B, H,
+                                                             W, eps);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace bseg

@@ -1,0 +1,442 @@
+// Bandwidth-bound kernels of the SegGPT tile path: LayerNorm, patchify (im2col for the stride-16 patch
+// embedding), two-stream merge, feature-ensemble mean, prompt-mask colourise, palette decode, vote
+// stitching, smooth-L1 loss.  Each kernel cites the reference lines it reproduces.
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace bseg {
+
+static inline int blocks_for(long long n, int per_block, int cap = 148 * 16) {
+  long long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return static_cast<int>(b);
+}
+
+// ----------------------------------------------------------------------------------------------
+// fp32 -> bf16 (weight packing at bseg_create time)
+// ----------------------------------------------------------------------------------------------
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = *reinterpret_cast<const float4*>(src + i);
+    uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (long long j = n & ~3LL; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+  }
+}
+int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t stream) {
+  BSEG_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+               "f32_to_bf16: misaligned");
+  f32_to_bf16_kernel<<<blocks_for(n, 1024), 256, 0, stream>>>(src, dst, n);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm over D=1024, fp32 in -> bf16 out.  nn.LayerNorm(eps=1e-6): modeling_seggpt.py:403-404,450.
+// One warp per row; the row lives in registers (two-pass mean / variance, fp32).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm1024_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long ldo, long long M,
+                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp_global; row < M; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = xr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / 1024.0f);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / 1024.0f) + eps);
+    __nv_bfloat16* orow = out + row * ldo;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = (lane + 32 * i) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+      uint2 o = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y),
+                           pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+      *reinterpret_cast<uint2*>(orow + col) = o;
+    }
+  }
+}
+int launch_layernorm1024(const float* x, long long ldx, const float* gamma, const float* beta, __nv_bfloat16* out,
+                         long long ldo, long long M, float eps, cudaStream_t stream) {
+  BSEG_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "layernorm: leading dims must be multiples of 4");
+  layernorm1024_kernel<<<blocks_for(M, 8, 148 * 8), 256, 0, stream>>>(x, ldx, gamma, beta, out, ldo, M, eps);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// patchify: builds the A operand of the patch-embedding GEMM (Conv2d k16 s16 == GEMM over im2col rows).
+//   stream 0 rows = cat(prompt_pixel_values, pixel_values) on H      (modeling_seggpt.py:713)
+//   stream 1 rows = cat(prompt_masks, prompt_masks|labels) on H      (modeling_seggpt.py:714-718); its bottom
+//   half is replaced by the mask token (bool_masked_pos default, :910-917 and :177-178) so those rows are zero
+//   here and the mask token is folded into the additive table of the GEMM epilogue.
+//   A[(s*B + b)*1568 + ph*28 + pw][c*256 + py*16 + px]  (k order == Conv2d weight [out, c, py, px] flattened)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ px, const float* __restrict__ prompt_px,
+                const float* __restrict__ prompt_mask, __nv_bfloat16* __restrict__ A, int B) {
+  // one thread = 8 consecutive pixels of one image row of one channel
+  const long long total = 2LL * B * 3 * 896 * 56;  // (stream, b, c, y, x8)
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x8 = static_cast<int>(idx % 56);
+    long long r = idx / 56;
+    const int y = static_cast<int>(r % 896);
+    r /= 896;
+    const int c = static_cast<int>(r % 3);
+    r /= 3;
+    const int b = static_cast<int>(r % B);
+    const int s = static_cast<int>(r / B);
+    const int ph = y >> 4, py = y & 15;
+    const int x = x8 * 8;
+    const int pw = x >> 4, pxo = x & 15;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    const bool top = y < 448;
+    if (s == 0 || top) {
+      const float* src = (s == 0) ? (top ? prompt_px : px) : prompt_mask;
+      const float* p = src + (((long long)b * 3 + c) * 448 + (top ? y : y - 448)) * 448 + x;
+      const float4 v0 = *reinterpret_cast<const float4*>(p);
+      const float4 v1 = *reinterpret_cast<const float4*>(p + 4);
+      o = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y),
+                     pack_bf16x2(v1.z, v1.w));
+    }
+    const long long row = ((long long)s * B + b) * 1568 + ph * 28 + pw;
+    *reinterpret_cast<uint4*>(A + row * 768 + c * 256 + py * 16 + pxo) = o;
+  }
+}
+int launch_patchify(const float* px, const float* prompt_px, const float* prompt_mask, const float* /*labels*/,
+                    __nv_bfloat16* A, int B, cudaStream_t stream) {
+  const long long total = 2LL * B * 3 * 896 * 56;
+  patchify_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, prompt_px, prompt_mask, A, B);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// two-stream merge after layer `merge_index`: h[:B] = (h[:B] + h[B:]) * 0.5   (modeling_seggpt.py:476-479)
+// ----------------------------------------------------------------------------------------------
+__global__ void merge_streams_kernel(float4* __restrict__ h, long long n4_half) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4_half;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 a = h[i];
+    const float4 b = h[i + n4_half];
+    a.x = (a.x + b.x) * 0.5f; a.y = (a.y + b.y) * 0.5f; a.z = (a.z + b.z) * 0.5f; a.w = (a.w + b.w) * 0.5f;
+    h[i] = a;
+  }
+}
+int launch_merge_streams(float* h, long long n_half, cudaStream_t stream) {
+  BSEG_REQUIRE(n_half % 4 == 0, "merge_streams: size must be a multiple of 4");
+  merge_streams_kernel<<<blocks_for(n_half / 4, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(h), n_half / 4);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// feature ensemble (modeling_seggpt.py:420-432): attention output (after proj, before the residual) of the
+// query half (bottom 28 token rows) is replaced by its mean over the prompts of the same tile, then added
+// to the residual stream.  nseq = nstreams * G * P sequences, sample index = (s*G + g)*P + p.
+//   cross_stream == 0 : mean over p               (layers != merge_index; per stream for layers < merge_index)
+//   cross_stream == 1 : mean over (s, p)          (layer == merge_index: HF averages dim 0 of the 2B batch)
+// ----------------------------------------------------------------------------------------------
+__global__ void ensemble_residual_kernel(float* __restrict__ h, const float* __restrict__ attn, int nstreams, int G,
+                                         int P, int cross_stream, int T, int D) {
+  const long long per_seq4 = (long long)T * D / 4;
+  const long long half4 = per_seq4 / 2;
+  const long long total = (long long)nstreams * G * per_seq4;  // one thread per (s, g, token-elem4), loops over p
+  float4* h4 = reinterpret_cast<float4*>(h);
+  const float4* a4 = reinterpret_cast<const float4*>(attn);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx % per_seq4;
+    const long long sg = idx / per_seq4;
+    const int g = static_cast<int>(sg % G);
+    const int s = static_cast<int>(sg / G);
+    if (e < half4) {  // prompt half: plain residual
+      for (int p = 0; p < P; ++p) {
+        const long long off = (((long long)s * G + g) * P + p) * per_seq4 + e;
+        float4 r = h4[off];
+        const float4 a = a4[off];
+        r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+        h4[off] = r;
+      }
+    } else {
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int s_lo = cross_stream ? 0 : s, s_hi = cross_stream ? nstreams : s + 1;
+      for (int ss = s_lo; ss < s_hi; ++ss)
+        for (int p = 0; p < P; ++p) {
+          const float4 a = a4[(((long long)ss * G + g) * P + p) * per_seq4 + e];
+          m.x += a.x; m.y += a.y; m.z += a.z; m.w += a.w;
+        }
+      const float inv = 1.0f / static_cast<float>((s_hi - s_lo) * P);
+      m.x *= inv; m.y *= inv; m.z *= inv; m.w *= inv;
+      for (int p = 0; p < P; ++p) {
+        const long long off = (((long long)s * G + g) * P + p) * per_seq4 + e;
+        float4 r = h4[off];
+        r.x += m.x; r.y += m.y; r.z += m.z; r.w += m.w;
+        h4[off] = r;
+      }
+    }
+  }
+}
+int launch_ensemble_residual(float* h, const float* attn, int nstreams, int G, int P, int cross_stream, int T, int D,
+                             cudaStream_t stream) {
+  const long long total = (long long)nstreams * G * T * D / 4;
+  ensemble_residual_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(h, attn, nstreams, G, P, cross_stream, T, D);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// pred_masks.mean(dim=0) over the prompts of one tile (predict_no_prompt.py:298)
+__global__ void mean_over_group_kernel(const float* __restrict__ pred, float* __restrict__ out, int P, long long per,
+                                       long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long g = idx / per, e = idx % per;
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += pred[(g * P + p) * per + e];
+    out[idx] = s / static_cast<float>(P);
+  }
+}
+int launch_mean_over_group(const float* pred, float* out, int ngroups, int group, long long per,
+                           cudaStream_t stream) {
+  const long long total = ngroups * per;
+  mean_over_group_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(pred, out, group, per, total);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// torch_apply_mask_rgb + normalize (src/util/ml_util.py:114-132, src/data.py:226-229,342-343):
+//   out[b,c,y,x] = (palette[b, mask[b,y,x], c] / 255 - mean[c]) / std[c]
+// ----------------------------------------------------------------------------------------------
+__global__ void colorize_norm_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ palette,
+                                     int ncls, float m0, float m1, float m2, float s0, float s1, float s2,
+                                     float* __restrict__ out, int B, int HW) {
+  const long long total = (long long)B * HW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = static_cast<int>(idx / HW);
+    const int p = static_cast<int>(idx % HW);
+    int cls = mask[idx];
+    if (cls >= ncls) cls = ncls - 1;
+    const uint8_t* pal = palette + ((long long)b * ncls + cls) * 3;
+    float* o = out + (long long)b * 3 * HW + p;
+    o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(pal[0]), 255.0f), m0), s0);
+    o[HW] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(pal[1]), 255.0f), m1), s1);
+    o[2 * HW] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(pal[2]), 255.0f), m2), s2);
+  }
+}
+int launch_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean,
+                         const float* stdv, float* out, int B, int H, int W, cudaStream_t stream) {
+  const long long total = (long long)B * H * W;
+  colorize_norm_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(mask, palette, num_classes, mean[0], mean[1],
+                                                                   mean[2], stdv[0], stdv[1], stdv[2], out, B, H * W);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// PromptModel.process_pred_masks (src/model.py:155-175) + cv2.resize(INTER_NEAREST) (src/predict.py:258)
+// + nodata zeroing (src/predict_no_prompt.py:303):
+//   cls[b,y,x] = argmin_k sum_c (pred[b,c,H+sy,sx] - palette_norm[b,k,c])^2,  first minimum wins.
+// pred is [B,3,2H,W] fp32 (bottom half decoded); idx (nullable) maps output row/col -> source row/col.
+// ----------------------------------------------------------------------------------------------
+__global__ void decode_palette_kernel(const float* __restrict__ pred, const float* __restrict__ palette_norm,
+                                      int ncls, uint8_t* __restrict__ out_u8, long long* __restrict__ out_i64,
+                                      const uint8_t* __restrict__ nodata, const int* __restrict__ idx, int B, int H,
+                                      int W, int OS) {
+  const long long total = (long long)B * OS * OS;
+  const long long plane = 2LL * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = static_cast<int>(i % OS);
+    const int oy = static_cast<int>((i / OS) % OS);
+    const int b = static_cast<int>(i / ((long long)OS * OS));
+    const int sy = idx ? idx[oy] : oy;
+    const int sx = idx ? idx[ox] : ox;
+    const float* p = pred + (long long)b * 3 * plane + (long long)(H + sy) * W + sx;
+    const float v0 = p[0], v1 = p[plane], v2 = p[2 * plane];
+    const float* pal = palette_norm + (long long)b * ncls * 3;
+    float best = 0.f;
+    int bi = 0;
+    for (int k = 0; k < ncls; ++k) {
+      const float d0 = __fsub_rn(v0, pal[k * 3 + 0]);
+      const float d1 = __fsub_rn(v1, pal[k * 3 + 1]);
+      const float d2 = __fsub_rn(v2, pal[k * 3 + 2]);
+      // torch.pow(x,2) then sum over the 3 channels in order: ((d0^2 + d1^2) + d2^2), no FMA contraction
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+      if (k == 0 || d < best) { best = d; bi = k; }
+    }
+    if (nodata != nullptr && nodata[i]) bi = 0;
+    if (out_u8) out_u8[i] = static_cast<uint8_t>(bi);
+    if (out_i64) out_i64[i] = bi;
+  }
+}
+int launch_decode_palette(const float* pred, const float* palette_norm, int num_classes, uint8_t* out_u8,
+                          long long* out_i64, const uint8_t* nodata, const int* idx, int B, int H, int W,
+                          int out_size, cudaStream_t stream) {
+  const long long total = (long long)B * out_size * out_size;
+  decode_palette_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(pred, palette_norm, num_classes, out_u8, out_i64,
+                                                                    nodata, idx, B, H, W, out_size);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Accumulator.update (src/predict.py:120-159; src/predict_no_prompt.py:163-186): clip the tile box to the
+// scene and add a one-hot vote per pixel.  The reference counter is uint8 (H,W,4) that wraps at 256; here the
+// four counters of a pixel are one u32 (identical byte layout).  A byte that wraps has its carry removed so
+// the result equals per-byte mod-256 arithmetic.
+// ----------------------------------------------------------------------------------------------
+__global__ void vote_accumulate_kernel(uint32_t* __restrict__ counter, int Hs, int Ws, const uint8_t* __restrict__ cls,
+                                       int n_tiles, int crop, const int* __restrict__ boxes, int use_atomics) {
+  const long long per = (long long)crop * crop;
+  const long long total = per * n_tiles;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = static_cast<int>(i / per);
+    const int sy = static_cast<int>((i % per) / crop);
+    const int sx = static_cast<int>(i % crop);
+    const int xmin = boxes[t * 4 + 0], ymin = boxes[t * 4 + 1];
+    const int dy = ymin + sy, dx = xmin + sx;
+    if (dy < 0 || dy >= Hs || dx < 0 || dx >= Ws) continue;
+    const uint32_t c = cls[i];
+    if (c > 3) continue;
+    uint32_t* w = counter + (long long)dy * Ws + dx;
+    const uint32_t inc = 1u << (8 * c);
+    if (use_atomics) {
+      const uint32_t old = atomicAdd(w, inc);
+      if (((old >> (8 * c)) & 0xFFu) == 0xFFu && c < 3) atomicSub(w, 1u << (8 * (c + 1)));
+    } else {
+      const uint32_t old = *w;
+      const uint32_t byte = ((old >> (8 * c)) + 1u) & 0xFFu;
+      *w = (old & ~(0xFFu << (8 * c))) | (byte << (8 * c));
+    }
+  }
+}
+int launch_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
+                           const int* boxes, int use_atomics, cudaStream_t stream) {
+  const long long total = (long long)crop * crop * n_tiles;
+  if (total == 0) return 0;
+  vote_accumulate_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(counter, Hs, Ws, cls, n_tiles, crop, boxes,
+                                                                     use_atomics);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// np.argmax(counter, axis=2) (src/predict.py:100): first maximum wins, untouched pixels -> 0
+__global__ void vote_argmax_kernel(const uint32_t* __restrict__ counter, uint8_t* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t w = counter[i];
+    uint32_t best = w & 0xFFu;
+    uint8_t bi = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const uint32_t v = (w >> (8 * k)) & 0xFFu;
+      if (v > best) { best = v; bi = static_cast<uint8_t>(k); }
+    }
+    out[i] = bi;
+  }
+}
+int launch_vote_argmax(const uint32_t* counter, uint8_t* out, long long n, cudaStream_t stream) {
+  if (n == 0) return 0;
+  vote_argmax_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(counter, out, n);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// SegGptLoss of the reference (src/model.py:40-64): smooth-L1(beta) between pred_masks and [0 ; labels],
+// masked by [0 ; yesdata], sum / keep.sum().  As written, `keep_mask.unsqueeze(1)` broadcasts to a BxB cross
+// product: loss = sum_px (sum_j l_j[px]) * (sum_i keep_i[px]) / sum(keep).  per_sample=1 gives the intended
+// sum_b l_b*keep_b / sum(keep); both are identical at B=1.  Forward and d(loss)/d(pred) in one pass.
+// scratch: [0] = keep count (float), [1] = loss numerator.
+// ----------------------------------------------------------------------------------------------
+__global__ void keep_count_kernel(const uint8_t* __restrict__ yes, long long n, float* __restrict__ scratch) {
+  float c = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c += yes[i] ? 1.f : 0.f;
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0 && c != 0.f) atomicAdd(&scratch[0], c);
+}
+__global__ void smooth_l1_kernel(const float* __restrict__ pred, const float* __restrict__ labels,
+                                 const uint8_t* __restrict__ yes, float beta, int per_sample,
+                                 float* __restrict__ grad, float* __restrict__ scratch, int B, int HW) {
+  // one thread per (pixel, channel) of the bottom half; loops over the batch
+  const float denom = 3.0f * scratch[0];  // keep.sum(): yesdata expanded to the 3 channels
+  const float inv = 1.0f / denom;
+  const long long total = 3LL * HW;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i / HW);
+    const int p = static_cast<int>(i % HW);
+    float ksum = 0.f;
+    if (!per_sample)
+      for (int b = 0; b < B; ++b) ksum += yes[(long long)b * HW + p] ? 1.f : 0.f;
+    for (int b = 0; b < B; ++b) {
+      const long long off = ((long long)b * 3 + c) * 2 * HW + HW + p;  // bottom half of [B,3,2H,W]
+      const float d = pred[off] - labels[((long long)b * 3 + c) * HW + p];
+      const float ad = fabsf(d);
+      const float l = ad < beta ? 0.5f * d * d / beta : ad - 0.5f * beta;
+      const float g = ad < beta ? d / beta : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+      const float w = per_sample ? (yes[(long long)b * HW + p] ? 1.f : 0.f) : ksum;
+      acc += l * w;
+      if (grad) {
+        grad[off] = g * w * inv;
+        grad[off - HW] = 0.f;  // top half: label = 0, keep = 0
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(&scratch[1], acc);
+}
+__global__ void smooth_l1_finalize_kernel(const float* __restrict__ scratch, float* __restrict__ loss) {
+  loss[0] = scratch[1] / (3.0f * scratch[0]);
+}
+int launch_smooth_l1(const float* pred, const float* labels, const uint8_t* yesdata, float beta, int per_sample,
+                     float* loss_out, float* grad_out, float* scratch, int B, int H, int W, cudaStream_t stream) {
+  const int HW = H * W;
+  BSEG_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(float), stream));
+  keep_count_kernel<<<blocks_for((long long)B * HW, 1024), 256, 0, stream>>>(yesdata, (long long)B * HW, scratch);
+  smooth_l1_kernel<<<blocks_for(3LL * HW, 256), 256, 0, stream>>>(pred, labels, yesdata, beta, per_sample, grad_out,
+                                                                  scratch, B, HW);
+  smooth_l1_finalize_kernel<<<1, 1, 0, stream>>>(scratch, loss_out);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace bseg

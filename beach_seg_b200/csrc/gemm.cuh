@@ -1,0 +1,265 @@
+// Persistent, warp-specialised tcgen05 GEMM:  D[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//   A : bf16 row-major activations (K contiguous)          -> TMA, 128B swizzle
+//   W : bf16 row-major nn.Linear weight [out=N, in=K]      -> TMA, 128B swizzle (already K-major)
+//   D : fp32 accumulators in TMEM (double buffered), drained by 4 epilogue warps.
+// Replaces the reference's CPU addmm calls behind every nn.Linear of HF SegGPT
+// (transformers/models/seggpt/modeling_seggpt.py:224,225,355,356,558) and the patch-embed conv (:108).
+#pragma once
+#include "common.cuh"
+
+namespace bseg {
+
+enum GemmEpiMode : int {
+  EPI_BF16 = 0,       // out_bf16[m, n]  = acc + bias[n]
+  EPI_BF16_GELU = 1,  // out_bf16[m, n]  = gelu_erf(acc + bias[n])
+  EPI_F32 = 2,        // out_f32[m, n]   = acc + bias[n]
+  EPI_RESID_F32 = 3,  // out_f32[m, n]   = resid[m, n] + acc + bias[n]      (out may alias resid)
+  EPI_QKV = 4,        // scatter to q[seq,h,t,64], k[seq,h,t,64], vT[seq,h,64,T]  (+bias)
+  EPI_EMBED = 5,      // out_f32[m, n]   = acc + tab[(m / rows_per_stream) * T + m % T, n]
+  EPI_PIXSHUF = 6,    // decoder pixel shuffle: nhwc[b, ph*16+py, pw*16+px, c] = acc + bias[n], n = (py*16+px)*64+c
+};
+
+struct GemmEpiParams {
+  void* out = nullptr;  // bf16* or float*
+  long long ldc = 0;
+  const float* bias = nullptr;
+  const float* resid = nullptr;
+  long long ldr = 0;
+  // EPI_EMBED
+  const float* tab = nullptr;
+  int rows_per_stream = 0;
+  // EPI_QKV / EPI_EMBED / EPI_PIXSHUF : tokens per sequence and token grid width
+  int T = 1568;
+  int grid_w = 28;
+  // EPI_QKV
+  __nv_bfloat16* q = nullptr;
+  __nv_bfloat16* k = nullptr;
+  __nv_bfloat16* vt = nullptr;
+  int heads = 16;
+};
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;
+constexpr int GEMM_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 512 or 256
+};
+
+template <int MODE>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, float (&v)[32], long long m, int n) {
+  // v: 32 consecutive accumulator columns n..n+31 of row m
+  if constexpr (MODE != EPI_EMBED) {
+    if (ep.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
+  }
+  if constexpr (MODE == EPI_BF16 || MODE == EPI_BF16_GELU) {
+    if constexpr (MODE == EPI_BF16_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + m * ep.ldc + n;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 pk = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                            pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+      *reinterpret_cast<uint4*>(dst + i) = pk;
+    }
+  } else if constexpr (MODE == EPI_F32 || MODE == EPI_RESID_F32 || MODE == EPI_EMBED) {
+    float* dst = reinterpret_cast<float*>(ep.out) + m * ep.ldc + n;
+    const float* add = nullptr;
+    if constexpr (MODE == EPI_RESID_F32) add = ep.resid + m * ep.ldr + n;
+    if constexpr (MODE == EPI_EMBED) {
+      long long stream = m / ep.rows_per_stream;
+      long long t = m % ep.T;
+      add = ep.tab + (stream * ep.T + t) * ep.ldc + n;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      if constexpr (MODE != EPI_F32) {
+        float4 r = *reinterpret_cast<const float4*>(add + i);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      *reinterpret_cast<float4*>(dst + i) = o;
+    }
+  } else if constexpr (MODE == EPI_QKV) {
+    const int D = ep.heads * 64;
+    const int which = n / D;
+    const int head = (n % D) >> 6;
+    const int d0 = n & 63;
+    const long long seq = m / ep.T;
+    const long long t = m % ep.T;
+    if (which < 2) {
+      __nv_bfloat16* base = (which == 0) ? ep.q : ep.k;
+      __nv_bfloat16* dst = base + ((seq * ep.heads + head) * ep.T + t) * 64 + d0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 pk = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                              pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+        *reinterpret_cast<uint4*>(dst + i) = pk;
+      }
+    } else {
+      // V is stored transposed ([d, t]) so that P*V consumes it as a K-major B operand
+      __nv_bfloat16* dst = ep.vt + ((seq * ep.heads + head) * 64 + d0) * (long long)ep.T + t;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[(long long)i * ep.T] = __float2bfloat16_rn(v[i]);
+    }
+  } else if constexpr (MODE == EPI_PIXSHUF) {
+    const long long b = m / ep.T;
+    const int t = static_cast<int>(m % ep.T);
+    const int ph = t / ep.grid_w, pw = t % ep.grid_w;
+    const int py = n >> 10, px = (n >> 6) & 15, c0 = n & 63;
+    const int H = (ep.T / ep.grid_w) * 16, W = ep.grid_w * 16;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.out) +
+                         ((b * H + (ph * 16 + py)) * W + (pw * 16 + px)) * 64 + c0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 pk = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                            pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+      *reinterpret_cast<uint4*>(dst + i) = pk;
+    }
+  }
+}
+
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         long long M, int N, int K, GemmEpiParams ep) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operand tiles need 1024B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;     // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_n_tiles = N / BLOCK_N;
+  const long long num_m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const long long num_tiles = num_m_tiles * num_n_tiles;
+  const int num_k_blocks = K / GEMM_BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = static_cast<int>(tile / num_n_tiles) * GEMM_BLOCK_M;
+        const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom
+            const uint64_t da = umma_desc_sw128_kmajor(a_addr + k * 32);
+            const uint64_t db = umma_desc_sw128_kmajor(b_addr + k * 32);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(&tmem_full[as]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long m0 = (tile / num_n_tiles) * GEMM_BLOCK_M;
+      const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const long long m = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (m < M) gemm_epilogue_chunk<MODE>(ep, v, m, n0 + c);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace bseg

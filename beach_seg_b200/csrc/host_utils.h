@@ -1,0 +1,53 @@
+// Host-side plumbing shared by the C-ABI translation units: error reporting, TMA descriptor
+// encoding through the driver entry point (no link-time libcuda dependency), launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace bseg {
+
+// thread-local last-error string behind bseg_last_error()
+char* last_error_buf();
+void set_error(const char* fmt, ...);
+
+#define BSEG_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::bseg::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -static_cast<int>(_e);                                                             \
+    }                                                                                           \
+  } while (0)
+
+#define BSEG_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::bseg::set_error(__VA_ARGS__);    \
+      return -1000;                      \
+    }                                    \
+  } while (0)
+
+// Encode a tiled TMA descriptor for a bf16 tensor with `rank` dims (dim 0 innermost, contiguous).
+// strides_bytes[i] is the byte stride of dim i+1 (rank-1 entries). 128B swizzle, zero OOB fill.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                             uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {ld_elems * 2};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_bf16(out, base, 2, dims, strides, box);
+}
+
+int num_sms();
+
+// launch accounting behind bseg_launch_count()
+void count_launch(int n = 1);
+long long launch_count();
+
+}  // namespace bseg

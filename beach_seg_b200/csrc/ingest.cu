@@ -1,0 +1,204 @@
+// Tile ingest: uint16 4-band Planet Dove scene -> model-ready 448x448 tiles, bit-faithful to the reference chain
+//   tif_image 4-band branch        src/util/geo_util.py:454-468   (false-colour composite, clip, scale, u8 truncate)
+//   crop_tif / padded_crop         src/util/geo_util.py:297-341   (zero padding; nodata padded with 1)
+//   PIL resize(BICUBIC) + /255     src/data.py:93-124             (two-pass fixed-point 8-bit resampler)
+//   K.Normalize(mean, std)         src/data.py:226-229
+// The scene-global statistics of tif_image (min over valid pixels, per-channel max) are a separate reduction.
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace bseg {
+
+// ----------------------------------------------------------------------------------------------
+// scene statistics.  Composite channels: c0 = band3, c1 = band2, c2 = mean(band0, band1).
+//   stats[0] = min over valid pixels and the 3 channels   (geo_util.py:459)
+//   stats[1..3] = per-channel max over ALL pixels          (geo_util.py:463-464 runs before the nodata zeroing)
+// All values are non-negative floats, so the IEEE bit pattern is order preserving and integer atomics work.
+// ----------------------------------------------------------------------------------------------
+__global__ void scene_stats_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ nodata,
+                                   long long npix, unsigned int* __restrict__ scratch) {
+  float mn = INFINITY, mx0 = 0.f, mx1 = 0.f, mx2 = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float b0 = scene[i], b1 = scene[npix + i], b2 = scene[2 * npix + i], b3 = scene[3 * npix + i];
+    const float c2 = (b0 + b1) * 0.5f;
+    mx0 = fmaxf(mx0, b3);
+    mx1 = fmaxf(mx1, b2);
+    mx2 = fmaxf(mx2, c2);
+    if (!nodata[i]) mn = fminf(mn, fminf(b3, fminf(b2, c2)));
+  }
+  mn = -warp_max(-mn);
+  mx0 = warp_max(mx0);
+  mx1 = warp_max(mx1);
+  mx2 = warp_max(mx2);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&scratch[0], __float_as_uint(mn));
+    atomicMax(&scratch[1], __float_as_uint(mx0));
+    atomicMax(&scratch[2], __float_as_uint(mx1));
+    atomicMax(&scratch[3], __float_as_uint(mx2));
+  }
+}
+__global__ void scene_stats_init_kernel(unsigned int* scratch) {
+  scratch[0] = 0x7F800000u;  // +inf
+  scratch[1] = scratch[2] = scratch[3] = 0u;
+}
+__global__ void scene_stats_final_kernel(const unsigned int* scratch, float* stats) {
+  for (int i = 0; i < 4; ++i) stats[i] = __uint_as_float(scratch[i]);
+}
+int launch_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats,
+                       unsigned int* scratch, cudaStream_t stream) {
+  const long long npix = static_cast<long long>(Hs) * Ws;
+  scene_stats_init_kernel<<<1, 1, 0, stream>>>(scratch);
+  long long blocks = (npix + 2047) / 2048;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scene_stats_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(scene, nodata, npix, scratch);
+  scene_stats_final_kernel<<<1, 1, 0, stream>>>(scratch, stats);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// ingest kernel: one CTA = (tile, band of `band` output rows).
+//   phase 1: composite u8 of the needed crop rows -> smem (planar per channel)
+//   phase 2: horizontal fixed-point pass (PIL ImagingResampleHorizontal_8bpc) -> smem
+//   phase 3: vertical fixed-point pass -> u8 -> /255 -> (x-mean)/std -> outputs
+// coef: [448][ksize] int32 (22-bit fixed point), bounds: [448][2] = (first input index, tap count); the same
+// table serves both axes because the crop and the output are square.
+// ----------------------------------------------------------------------------------------------
+constexpr int kOut = 448;
+constexpr int kPrecisionBits = 22;  // 32 - 8 - 2, PIL Resample.c
+
+__device__ __forceinline__ uint8_t composite_u8(float v, float mn, float denom) {
+  // img.clip(min, min+3000) - min ; img /= max ; np.array(img*255, dtype=uint8)  (float32, truncation)
+  const float hi = __fadd_rn(3000.0f, mn);
+  const float c = fminf(fmaxf(v, mn), hi);
+  const float x = __fmul_rn(__fdiv_rn(__fsub_rn(c, mn), denom), 255.0f);
+  return static_cast<uint8_t>(static_cast<int>(x));
+}
+__device__ __forceinline__ uint8_t clip8(int v) {
+  v >>= kPrecisionBits;
+  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+__global__ void __launch_bounds__(256)
+ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ nodata, int Hs, int Ws,
+              const float* __restrict__ stats, const int* __restrict__ boxes, int crop, const int* __restrict__ coef,
+              const int* __restrict__ bounds, int ksize, int band, int max_rows, float m0, float m1, float m2,
+              float s0, float s1, float s2, float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_patch,
+              long long patch_tile_stride, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_nodata) {
+  extern __shared__ uint8_t sm[];
+  uint8_t* comp = sm;                                   // [3][max_rows][crop]
+  uint8_t* hbuf = sm + 3 * max_rows * crop;             // [3][max_rows][kOut]
+  const int tile = blockIdx.y;
+  const int oy0 = blockIdx.x * band;
+  const int oy1 = min(oy0 + band, kOut);
+  const int xmin = boxes[tile * 4 + 0], ymin = boxes[tile * 4 + 1];
+  const int r0 = bounds[2 * oy0];                                      // first crop row needed
+  const int r1 = bounds[2 * (oy1 - 1)] + bounds[2 * (oy1 - 1) + 1];    // one past the last
+  const int nrows = r1 - r0;
+  const long long npix = static_cast<long long>(Hs) * Ws;
+
+  const float mn = stats[0];
+  const float hi = __fadd_rn(3000.0f, mn);
+  float den[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) den[c] = __fsub_rn(fminf(fmaxf(stats[1 + c], mn), hi), mn);
+
+  // ---- phase 1: composite ----
+  for (int i = threadIdx.x; i < nrows * crop; i += blockDim.x) {
+    const int rr = i / crop, cx = i % crop;
+    const int sy = ymin + r0 + rr, sx = xmin + cx;
+    uint8_t v0 = 0, v1 = 0, v2 = 0, nd = 1;
+    if (sy >= 0 && sy < Hs && sx >= 0 && sx < Ws) {
+      const long long p = static_cast<long long>(sy) * Ws + sx;
+      nd = nodata[p] ? 1 : 0;
+      if (!nd) {
+        const float b0 = scene[p], b1 = scene[npix + p], b2 = scene[2 * npix + p], b3 = scene[3 * npix + p];
+        v0 = composite_u8(b3, mn, den[0]);
+        v1 = composite_u8(b2, mn, den[1]);
+        v2 = composite_u8(__fmul_rn(__fadd_rn(b0, b1), 0.5f), mn, den[2]);
+      }
+    }
+    comp[(0 * max_rows + rr) * crop + cx] = v0;
+    comp[(1 * max_rows + rr) * crop + cx] = v1;
+    comp[(2 * max_rows + rr) * crop + cx] = v2;
+    // optional crop-resolution outputs; each crop row is owned by the band whose first needed row is <= it
+    // (bands overlap, identical values are written, which is benign)
+    if (out_u8) {
+      uint8_t* o = out_u8 + ((static_cast<long long>(tile) * crop + (r0 + rr)) * crop + cx) * 3;
+      o[0] = v0; o[1] = v1; o[2] = v2;
+    }
+    if (out_nodata) out_nodata[(static_cast<long long>(tile) * crop + (r0 + rr)) * crop + cx] = nd;
+  }
+  __syncthreads();
+
+  // ---- phase 2: horizontal pass ----
+  for (int i = threadIdx.x; i < nrows * kOut; i += blockDim.x) {
+    const int rr = i / kOut, ox = i % kOut;
+    const int x0 = bounds[2 * ox], cnt = bounds[2 * ox + 1];
+    const int* k = coef + ox * ksize;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+    const uint8_t* c0 = comp + (0 * max_rows + rr) * crop + x0;
+    const uint8_t* c1 = comp + (1 * max_rows + rr) * crop + x0;
+    const uint8_t* c2 = comp + (2 * max_rows + rr) * crop + x0;
+    for (int t = 0; t < cnt; ++t) {
+      const int w = __ldg(k + t);
+      a0 += c0[t] * w;
+      a1 += c1[t] * w;
+      a2 += c2[t] * w;
+    }
+    hbuf[(0 * max_rows + rr) * kOut + ox] = clip8(a0);
+    hbuf[(1 * max_rows + rr) * kOut + ox] = clip8(a1);
+    hbuf[(2 * max_rows + rr) * kOut + ox] = clip8(a2);
+  }
+  __syncthreads();
+
+  // ---- phase 3: vertical pass + normalise ----
+  const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+  const int nout = (oy1 - oy0) * kOut;
+  for (int i = threadIdx.x; i < 3 * nout; i += blockDim.x) {
+    const int c = i / nout;
+    const int oy = oy0 + (i % nout) / kOut, ox = i % kOut;
+    const int y0 = bounds[2 * oy] - r0, cnt = bounds[2 * oy + 1];
+    const int* k = coef + oy * ksize;
+    int a = 1 << (kPrecisionBits - 1);
+    const uint8_t* h = hbuf + (c * max_rows + y0) * kOut + ox;
+    for (int t = 0; t < cnt; ++t) a += h[t * kOut] * __ldg(k + t);
+    const float u = static_cast<float>(clip8(a));
+    const float val = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), mean[c]), stdv[c]);
+    if (out_nchw) out_nchw[((static_cast<long long>(tile) * 3 + c) * kOut + oy) * kOut + ox] = val;
+    if (out_patch) {
+      // row of the patch-embedding A operand: token (oy/16, ox/16), k = c*256 + (oy%16)*16 + ox%16
+      const long long row = static_cast<long long>(oy >> 4) * 28 + (ox >> 4);
+      out_patch[tile * patch_tile_stride + row * 768 + c * 256 + (oy & 15) * 16 + (ox & 15)] =
+          __float2bfloat16_rn(val);
+    }
+  }
+}
+
+int launch_ingest(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
+                  int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
+                  const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
+                  long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream) {
+  if (n_tiles == 0) return 0;
+  BSEG_REQUIRE(band > 0 && max_rows > 0 && crop > 0, "ingest: bad geometry");
+  const size_t smem = static_cast<size_t>(3) * max_rows * (crop + kOut);
+  BSEG_REQUIRE(smem <= 200 * 1024, "ingest: crop=%d band=%d needs %zu B of shared memory", crop, band, smem);
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    BSEG_CHECK_CUDA(cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    attr_bytes = smem;
+  }
+  dim3 grid((kOut + band - 1) / band, n_tiles);
+  ingest_kernel<<<grid, 256, smem, stream>>>(scene, nodata, Hs, Ws, stats, boxes, crop, coef, bounds, ksize, band,
+                                             max_rows, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], out_nchw,
+                                             out_patch, patch_tile_stride, out_u8, out_nodata);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace bseg

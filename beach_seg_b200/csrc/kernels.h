@@ -1,0 +1,56 @@
+// Internal (C++) launcher declarations. The public C ABI lives in include/bseg.h.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm.cuh"
+
+namespace bseg {
+
+// gemm.cu
+int launch_gemm(int mode, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long M, int N, int K,
+                const GemmEpiParams& ep, cudaStream_t stream);
+
+// attention.cu : fused softmax(q k^T * scale + decomposed rel-pos bias) v, one CTA per (seq, head, 128-query tile)
+//   q, k : [nseq, heads, T, 64] bf16     vt : [nseq, heads, 64, T] bf16
+//   relcat : [176, 64] bf16 = reversed rel_pos_h (111 rows, padded to 112) ; reversed rel_pos_w (55 rows, padded to 64)
+//   out : [nseq, T, heads*64] bf16 (token-major, ready to be the A operand of the proj GEMM)
+int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
+                     const __nv_bfloat16* relcat, __nv_bfloat16* out, int nseq, int heads, int grid_h, int grid_w,
+                     cudaStream_t stream);
+
+// decoder_conv.cu : conv3x3(64->64, pad 1) + LayerNorm(C=64) + erf-GELU + conv1x1(64->3), NHWC bf16 in, NCHW fp32 out
+int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9 /*[9][64 out][64 in]*/,
+                        const float* conv_b, const float* ln_w, const float* ln_b, const float* head_w /*[3][64]*/,
+                        const float* head_b, float* pred /*[B,3,H,W]*/, int B, int H, int W, float eps,
+                        cudaStream_t stream);
+
+// elementwise.cu
+int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t stream);
+int launch_layernorm1024(const float* x, long long ldx, const float* gamma, const float* beta, __nv_bfloat16* out,
+                         long long ldo, long long M, float eps, cudaStream_t stream);
+int launch_patchify(const float* px, const float* prompt_px, const float* prompt_mask, const float* labels,
+                    __nv_bfloat16* A, int B, cudaStream_t stream);
+int launch_merge_streams(float* h, long long n_half, cudaStream_t stream);
+int launch_ensemble_residual(float* h, const float* attn, int nstreams, int G, int P, int cross_stream, int T, int D,
+                             cudaStream_t stream);
+int launch_mean_over_group(const float* pred, float* out, int ngroups, int group, long long per, cudaStream_t stream);
+int launch_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean,
+                         const float* stdv, float* out, int B, int H, int W, cudaStream_t stream);
+int launch_decode_palette(const float* pred, const float* palette_norm, int num_classes, uint8_t* out_u8,
+                          long long* out_i64, const uint8_t* nodata, const int* idx, int B, int H, int W,
+                          int out_size, cudaStream_t stream);
+int launch_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
+                           const int* boxes, int use_atomics, cudaStream_t stream);
+int launch_vote_argmax(const uint32_t* counter, uint8_t* out, long long n, cudaStream_t stream);
+int launch_smooth_l1(const float* pred, const float* labels, const uint8_t* yesdata, float beta, int per_sample,
+                     float* loss_out, float* grad_out, float* scratch, int B, int H, int W, cudaStream_t stream);
+int launch_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats /*[4]*/,
+                       unsigned int* scratch /*[4]*/, cudaStream_t stream);
+int launch_ingest(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
+                  int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
+                  const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch, long long patch_tile_stride,
+                  uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
+
+}  // namespace bseg

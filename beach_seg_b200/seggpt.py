@@ -1,0 +1,187 @@
+"""Drop-in for the object `src/util/ml_util.py:7-13 load_model()` returns: the frozen HuggingFace
+`SegGptForImageSegmentation` in eval mode, with the same call signature and output fields, running on the
+hand-written sm_100a kernels of libbseg.so (HF:modeling_seggpt.py:839-959 for the semantics).
+
+    model = SegGptB200.from_hf(hf_model)            # or load_model(checkpoint)
+    out = model(pixel_values=..., prompt_pixel_values=..., prompt_masks=..., embedding_type="instance")
+    out.pred_masks                                  # float32 [B, 3, 896, 448]; attribute is assignable
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+IMG = 448
+NUM_PATCHES = 1568
+
+
+class SegGptOutput:
+    """Mutable stand-in for HF SegGptImageSegmentationOutput (src/predict_no_prompt.py:298 assigns .pred_masks)."""
+
+    def __init__(self, loss=None, pred_masks=None):
+        self.loss = loss
+        self.pred_masks = pred_masks
+        self.hidden_states = None
+        self.attentions = None
+
+    def __getitem__(self, k):
+        if isinstance(k, str):
+            return getattr(self, k)
+        return tuple(v for v in (self.loss, self.pred_masks) if v is not None)[k]
+
+
+class SegGptB200(torch.nn.Module):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], num_layers: int = 24, merge_index: int = 2,
+                 intermediate=(5, 11, 17, 23), layer_norm_eps: float = 1e-6, beta: float = 0.01,
+                 device: str | torch.device = "cuda:0", max_batch: int = 64):
+        super().__init__()
+        self._device = torch.device(device)
+        if self._device.type != "cuda":
+            raise _lib.BsegError("SegGptB200 runs on a CUDA device only; there is no CPU path")
+        self.num_layers, self.merge_index, self.intermediate = num_layers, merge_index, tuple(intermediate)
+        self.beta = beta
+        self.max_batch = max_batch
+        self._handle = C.c_void_p()
+        self._ws: Optional[torch.Tensor] = None
+        self._scratch = torch.zeros(8, dtype=torch.float32, device=self._device)
+        L = _lib.lib()
+        with torch.cuda.device(self._device):
+            keep = []  # fp32 staging copies, freed after packing
+
+            def dev(name):
+                t = state_dict[name].detach().to(device=self._device, dtype=torch.float32).contiguous()
+                keep.append(t)
+                return C.c_void_p(t.data_ptr())
+
+            layers = (_lib.LayerWeights * num_layers)()
+            for i in range(num_layers):
+                p = f"model.encoder.layers.{i}."
+                lw = layers[i]
+                lw.ln1_w, lw.ln1_b = dev(p + "layernorm_before.weight"), dev(p + "layernorm_before.bias")
+                lw.qkv_w, lw.qkv_b = dev(p + "attention.qkv.weight"), dev(p + "attention.qkv.bias")
+                lw.rel_pos_h, lw.rel_pos_w = dev(p + "attention.rel_pos_h"), dev(p + "attention.rel_pos_w")
+                lw.proj_w, lw.proj_b = dev(p + "attention.proj.weight"), dev(p + "attention.proj.bias")
+                lw.ln2_w, lw.ln2_b = dev(p + "layernorm_after.weight"), dev(p + "layernorm_after.bias")
+                lw.lin1_w, lw.lin1_b = dev(p + "mlp.lin1.weight"), dev(p + "mlp.lin1.bias")
+                lw.lin2_w, lw.lin2_b = dev(p + "mlp.lin2.weight"), dev(p + "mlp.lin2.bias")
+            w = _lib.Weights()
+            w.num_layers, w.merge_index = num_layers, merge_index
+            w.intermediate_indices = (C.c_int * 4)(*self.intermediate)
+            w.layer_norm_eps = layer_norm_eps
+            e = "model.embeddings."
+            w.patch_w, w.patch_b = dev(e + "patch_embeddings.projection.weight"), dev(e + "patch_embeddings.projection.bias")
+            w.mask_token = dev(e + "mask_token")
+            w.segment_token_input, w.segment_token_prompt = dev(e + "segment_token_input"), dev(e + "segment_token_prompt")
+            w.type_token_semantic, w.type_token_instance = dev(e + "type_token_semantic"), dev(e + "type_token_instance")
+            w.position_embeddings = dev(e + "position_embeddings")
+            w.layers = layers
+            w.enc_ln_w, w.enc_ln_b = dev("model.encoder.layernorm.weight"), dev("model.encoder.layernorm.bias")
+            w.dec_embed_w, w.dec_embed_b = dev("decoder.decoder_embed.weight"), dev("decoder.decoder_embed.bias")
+            w.dec_conv_w, w.dec_conv_b = dev("decoder.decoder_pred.conv.weight"), dev("decoder.decoder_pred.conv.bias")
+            w.dec_ln_w, w.dec_ln_b = dev("decoder.decoder_pred.layernorm.weight"), dev("decoder.decoder_pred.layernorm.bias")
+            w.dec_head_w, w.dec_head_b = dev("decoder.decoder_pred.head.weight"), dev("decoder.decoder_pred.head.bias")
+            _lib.check(L.bseg_create(C.byref(w), C.byref(self._handle), _lib.stream_ptr()), "bseg_create")
+            torch.cuda.current_stream().synchronize()
+            del keep
+
+    # ------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_hf(cls, hf_model, device="cuda:0", **kw) -> "SegGptB200":
+        cfg = hf_model.config
+        return cls(hf_model.state_dict(), num_layers=cfg.num_hidden_layers, merge_index=cfg.merge_index,
+                   intermediate=tuple(cfg.intermediate_hidden_state_indices), layer_norm_eps=cfg.layer_norm_eps,
+                   beta=cfg.beta, device=device, **kw)
+
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    def to(self, *args, **kwargs):  # the backbone lives in the library's arena; only cuda is meaningful
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                _lib.lib().bseg_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def _workspace(self, batch: int) -> torch.Tensor:
+        need = int(_lib.lib().bseg_workspace_bytes(self._handle, batch))
+        if self._ws is None or self._ws.numel() < need + 256:
+            self._ws = None
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self._device)
+        return self._ws
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, pixel_values: torch.Tensor, prompt_pixel_values: torch.Tensor, prompt_masks: torch.Tensor,
+                bool_masked_pos: Optional[torch.Tensor] = None, feature_ensemble: Optional[bool] = None,
+                embedding_type: Optional[str] = None, labels: Optional[torch.Tensor] = None,
+                output_attentions: Optional[bool] = None, output_hidden_states: Optional[bool] = None,
+                return_dict: Optional[bool] = None, ensemble_group: Optional[int] = None, **kwargs) -> SegGptOutput:
+        for name, t in (("pixel_values", pixel_values), ("prompt_pixel_values", prompt_pixel_values),
+                        ("prompt_masks", prompt_masks)):
+            if t.ndim != 4 or t.shape[1] != 3:
+                raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in "
+                                 "the configuration.")
+            if t.shape[2] != IMG or t.shape[3] != IMG:
+                # HF checks the stacked image (HF:modeling_seggpt.py:116-119)
+                raise ValueError(f"Input image size ({2 * t.shape[2]}*{t.shape[3]}) doesn't match model (896*448).")
+        embedding_type = embedding_type if embedding_type is not None else "instance"
+        if embedding_type not in ("instance", "semantic"):
+            raise ValueError(f"Embedding type should be either 'semantic' or 'instance', but got {embedding_type}")
+        if bool_masked_pos is not None:
+            default = torch.cat([torch.zeros(NUM_PATCHES // 2, dtype=torch.bool),
+                                 torch.ones(NUM_PATCHES - NUM_PATCHES // 2, dtype=torch.bool)])
+            if not torch.equal(bool_masked_pos.reshape(-1, NUM_PATCHES).cpu().bool(),
+                               default.expand(bool_masked_pos.reshape(-1, NUM_PATCHES).shape[0], -1)):
+                raise NotImplementedError("only the default bool_masked_pos (bottom half masked) is supported; the "
+                                          "reference never passes another one")
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("attention / hidden-state outputs are never requested on the reference path")
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (pixel_values, prompt_pixel_values, prompt_masks)):
+            raise NotImplementedError("backward to the prompt (bseg_backward_to_prompt) is not built yet; call under "
+                                      "torch.no_grad()")
+        B = pixel_values.shape[0]
+        if not (prompt_pixel_values.shape[0] == B and prompt_masks.shape[0] == B):
+            raise ValueError("pixel_values, prompt_pixel_values and prompt_masks must share the batch dimension")
+        P = 0
+        if feature_ensemble:
+            P = B if ensemble_group is None else int(ensemble_group)
+            if P <= 0 or B % P != 0:
+                raise ValueError(f"ensemble_group={P} does not divide the batch {B}")
+
+        def prep(t):
+            return t.detach().to(device=self._device, dtype=torch.float32).contiguous()
+
+        px, ppx, pm = prep(pixel_values), prep(prompt_pixel_values), prep(prompt_masks)
+        pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=self._device)
+        L = _lib.lib()
+        step = self.max_batch if P == 0 else max(P, (self.max_batch // P) * P)
+        with torch.cuda.device(self._device):
+            for s in range(0, B, step):
+                n = min(step, B - s)
+                ws = self._workspace(n)
+                base = (ws.data_ptr() + 255) // 256 * 256
+                _lib.check(L.bseg_forward(self._handle, _lib.ptr(px[s:s + n]), _lib.ptr(ppx[s:s + n]),
+                                          _lib.ptr(pm[s:s + n]), n, 0 if embedding_type == "instance" else 1, P,
+                                          C.c_void_p(base), C.c_size_t(ws.numel() - (base - ws.data_ptr())),
+                                          _lib.ptr(pred[s:s + n]), _lib.stream_ptr()), "bseg_forward")
+        loss = None
+        if labels is not None:
+            # HF SegGptLoss (HF:modeling_seggpt.py:780-819) with the default mask == smooth-L1 over the bottom half.
+            # The reference computes it and throws it away (src/model.py:245-255); kept for interface fidelity.
+            lab = prep(labels)
+            yes = torch.ones((B, IMG, IMG), dtype=torch.uint8, device=self._device)
+            loss_t = torch.empty(1, dtype=torch.float32, device=self._device)
+            with torch.cuda.device(self._device):
+                _lib.check(L.bseg_loss_smoothl1_fwd_bwd(_lib.ptr(pred), _lib.ptr(lab), _lib.ptr(yes), self.beta, 1,
+                                                        _lib.ptr(loss_t), None, _lib.ptr(self._scratch), B, IMG, IMG,
+                                                        _lib.stream_ptr()), "bseg_loss")
+            loss = loss_t[0]
+        return SegGptOutput(loss=loss, pred_masks=pred)

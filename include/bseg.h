@@ -1,0 +1,167 @@
+/* bseg.h — C ABI of libbseg.so, the B200 (sm_100a) implementation of beach_seg's segmentation hot path.
+ *
+ * The reference (kyle-dorman/beach_seg) is pure Python: its "plugin interface" for this path is the duck-typed
+ * HuggingFace call `model(pixel_values=, prompt_pixel_values=, prompt_masks=, embedding_type=, ...) -> .pred_masks`
+ * returned by `src/util/ml_util.py:7-13 load_model()` plus the tensor helpers around it.  Each entry point below
+ * names the reference lines it replaces.  `HF:` = transformers/models/seggpt/ (transformers 5.5.0, the un-vendored
+ * dependency that holds the arithmetic).
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a caller-owned DEVICE pointer unless it says "host";
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no host sync inside;
+ *   - return 0 on success, negative on error (-cudaError_t for CUDA failures, -1000 for argument errors);
+ *     bseg_last_error() returns a thread-local message;
+ *   - tensors are contiguous, row-major, in the layouts the reference uses (NCHW fp32 images, (B,H,W) masks).
+ */
+#ifndef BSEG_H_
+#define BSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSEG_T 1568          /* tokens per stacked 896x448 image (56 x 28 patches of 16 px) */
+#define BSEG_HIDDEN 1024
+#define BSEG_HEADS 16
+#define BSEG_IMG 448
+#define BSEG_MAX_LAYERS 48
+
+typedef struct bseg_handle bseg_handle;
+
+/* fp32 DEVICE pointers to the tensors of HF SegGptForImageSegmentation.state_dict() (names in comments). */
+typedef struct bseg_layer_weights {
+  const float* ln1_w;  const float* ln1_b;      /* layers.i.layernorm_before.{weight,bias}        [1024] */
+  const float* qkv_w;  const float* qkv_b;      /* layers.i.attention.qkv.{weight,bias}   [3072,1024],[3072] */
+  const float* rel_pos_h;                       /* layers.i.attention.rel_pos_h                  [111,64] */
+  const float* rel_pos_w;                       /* layers.i.attention.rel_pos_w                   [55,64] */
+  const float* proj_w; const float* proj_b;     /* layers.i.attention.proj.{weight,bias}  [1024,1024],[1024] */
+  const float* ln2_w;  const float* ln2_b;      /* layers.i.layernorm_after.{weight,bias}         [1024] */
+  const float* lin1_w; const float* lin1_b;     /* layers.i.mlp.lin1.{weight,bias}        [4096,1024],[4096] */
+  const float* lin2_w; const float* lin2_b;     /* layers.i.mlp.lin2.{weight,bias}        [1024,4096],[1024] */
+} bseg_layer_weights;
+
+typedef struct bseg_weights {
+  int num_layers;                 /* SegGptConfig.num_hidden_layers (24) */
+  int merge_index;                /* SegGptConfig.merge_index (2) */
+  int intermediate_indices[4];    /* SegGptConfig.intermediate_hidden_state_indices (5,11,17,23) */
+  float layer_norm_eps;           /* 1e-6 */
+  const float* patch_w;           /* model.embeddings.patch_embeddings.projection.weight  [1024,3,16,16] */
+  const float* patch_b;           /* ...projection.bias [1024] */
+  const float* mask_token;        /* model.embeddings.mask_token            [1024] */
+  const float* segment_token_input;
+  const float* segment_token_prompt;
+  const float* type_token_semantic;
+  const float* type_token_instance;
+  const float* position_embeddings; /* model.embeddings.position_embeddings [1, 14*14+1, 1024] (CLS row included) */
+  const bseg_layer_weights* layers; /* host array [num_layers] */
+  const float* enc_ln_w; const float* enc_ln_b;     /* model.encoder.layernorm */
+  const float* dec_embed_w; const float* dec_embed_b; /* decoder.decoder_embed [16384,4096],[16384] */
+  const float* dec_conv_w; const float* dec_conv_b;   /* decoder.decoder_pred.conv [64,64,3,3],[64] */
+  const float* dec_ln_w; const float* dec_ln_b;       /* decoder.decoder_pred.layernorm [64] */
+  const float* dec_head_w; const float* dec_head_b;   /* decoder.decoder_pred.head [3,64,1,1],[3] */
+} bseg_weights;
+
+const char* bseg_last_error(void);
+int bseg_version(void);
+
+/* Replaces load_model() (src/util/ml_util.py:7-13): packs the frozen backbone once into bf16 kernel layouts
+ * (weights stay [out,in] = K-major; rel-pos tables reversed and concatenated; the additive embedding table
+ * bias+segment+type+bicubic(pos) precomputed, HF:modeling_seggpt.py:145-206). `w` is a host struct. */
+int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream);
+int bseg_destroy(bseg_handle* h);
+
+/* Bytes of scratch a forward over `batch` model samples needs. */
+size_t bseg_workspace_bytes(const bseg_handle* h, int batch);
+
+/* Replaces SegGptForImageSegmentation.forward (HF:modeling_seggpt.py:839-959) in eval mode with the default
+ * bool_masked_pos.  pixel_values / prompt_pixel_values / prompt_masks: fp32 [batch,3,448,448].
+ * embedding_type: 0 = "instance", 1 = "semantic".  ensemble_prompts: 0 = feature_ensemble off; P >= 1 = on, the
+ * batch is batch/P tiles of P prompts each (HF averages the whole batch == one tile).
+ * pred_masks: fp32 [batch,3,896,448]. */
+int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                 const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
+                 size_t workspace_bytes, float* pred_masks, void* stream);
+
+/* tif_image 4-band branch statistics (src/util/geo_util.py:459-464): stats[0] = min over valid pixels of the
+ * composite, stats[1..3] = per-channel max.  scene: uint16 [4,Hs,Ws] band-planar; nodata: uint8 [Hs,Ws].
+ * scratch: 4 x uint32. */
+int bseg_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, uint32_t* scratch,
+                     void* stream);
+
+/* tif_image + crop_tif/padded_crop + PIL BICUBIC resize to 448 + /255 + Normalize
+ * (src/util/geo_util.py:454-468,297-341; src/data.py:93-124,226-229).
+ * boxes: int32 [n_tiles,4] = (xmin,ymin,xmax,ymax); coef/bounds: the PIL resampling table for crop->448
+ * (int32 [448,ksize] and [448,2]), built on the host by beach_seg_b200.ingest.pil_bicubic_table().
+ * mean/stdv: host float[3].  Any of the outputs may be NULL:
+ *   out_nchw  fp32 [n,3,448,448] normalised;  out_patch bf16 rows of the patch-embedding operand (tile stride in
+ *   elements);  out_u8 uint8 [n,crop,crop,3] composite crop;  out_nodata uint8 [n,crop,crop]. */
+int bseg_ingest_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                      const int32_t* boxes, int n_tiles, int crop, const int32_t* coef, const int32_t* bounds,
+                      int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,
+                      long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, void* stream);
+
+/* torch_apply_mask_rgb + normalize (src/util/ml_util.py:114-132; src/model.py:210-211,238-239).
+ * mask uint8 [B,H,W]; palette uint8 [B,num_classes,3]; out fp32 [B,3,H,W]. */
+int bseg_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean,
+                       const float* stdv, float* out, int batch, int H, int W, void* stream);
+
+/* PromptModel.process_pred_masks (src/model.py:155-175) [+ cv2 INTER_NEAREST resize, src/predict.py:258;
+ * + nodata zeroing, src/predict_no_prompt.py:303].  pred fp32 [B,3,2H,W]; palette_norm fp32 [B,num_classes,3];
+ * resize_idx: int32 [out_size] source index per output row/col, or NULL (out_size == H == W);
+ * nodata: uint8 [B,out_size,out_size] or NULL; out_u8 / out_i64: [B,out_size,out_size], either may be NULL. */
+int bseg_decode_palette(const float* pred, const float* palette_norm, int num_classes, uint8_t* out_u8,
+                        int64_t* out_i64, const uint8_t* nodata, const int32_t* resize_idx, int batch, int H, int W,
+                        int out_size, void* stream);
+
+/* pred_masks.mean(dim=0) over the prompts of a tile (src/predict_no_prompt.py:298). */
+int bseg_mean_over_prompts(const float* pred, float* out, int n_tiles, int prompts, long long elems_per_sample,
+                           void* stream);
+
+/* Accumulator.update (src/predict.py:120-159; src/predict_no_prompt.py:163-186).  counter: uint32 [Hs,Ws]
+ * == uint8 [Hs,Ws,4] votes;  cls: uint8 [n_tiles,crop,crop];  boxes: int32 [n_tiles,4].
+ * use_atomics must be 1 when tiles of one call may overlap. */
+int bseg_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
+                         const int32_t* boxes, int use_atomics, void* stream);
+
+/* np.argmax(counter, axis=2) (src/predict.py:100; src/predict_no_prompt.py:141). out: uint8 [Hs,Ws]. */
+int bseg_vote_argmax(const uint32_t* counter, uint8_t* out, long long n_pixels, void* stream);
+
+/* SegGptLoss (src/model.py:40-64), forward and gradient w.r.t. pred in one pass.
+ * pred fp32 [B,3,2H,W]; labels fp32 [B,3,H,W]; yesdata uint8 [B,H,W]; per_sample: 0 = as written in the
+ * reference (BxB broadcast), 1 = per-sample masking; loss_out: fp32 [1]; grad_out: fp32 [B,3,2H,W] or NULL;
+ * scratch: 2 floats. */
+int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uint8_t* yesdata, float beta,
+                               int per_sample, float* loss_out, float* grad_out, float* scratch, int batch, int H,
+                               int W, void* stream);
+
+/* ---- building blocks, exported for unit tests and the benchmark's roofline legs ---- */
+
+/* D = A[M,K] * W[N,K]^T (+bias); A, W bf16; out fp32 (out_is_bf16 == 0) or bf16; gelu applies to bf16 output. */
+int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int N, int K, const float* bias,
+                   void* out, long long ldc, int out_is_bf16, int gelu, void* stream);
+/* LayerNorm over 1024 columns: x fp32 [M,ldx] -> out bf16 [M,ldo]. */
+int bseg_layernorm1024(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
+                       long long ldo, long long M, float eps, void* stream);
+/* Fused rel-pos attention. q,k bf16 [nseq,16,1568,64]; vt bf16 [nseq,16,64,1568]; relcat bf16 [176,64];
+ * out bf16 [nseq,1568,1024]. */
+int bseg_attention(const void* q, const void* k, const void* vt, const void* relcat, void* out, int nseq,
+                   void* stream);
+/* relcat = [reverse(rel_pos_h) (111 rows) ; 0 ; reverse(rel_pos_w) (55 rows) ; 0...] as bf16 [176,64]. */
+int bseg_pack_relcat(const float* rel_pos_h, const float* rel_pos_w, void* relcat, void* stream);
+/* Decoder head: conv3x3 + LN(C) + GELU + conv1x1. x bf16 NHWC [B,H,W,64]; w9 bf16 [9,64,64]; pred fp32 [B,3,H,W]. */
+int bseg_decoder_head(const void* x_nhwc, const void* w9, const float* conv_b, const float* ln_w, const float* ln_b,
+                      const float* head_w, const float* head_b, float* pred, int batch, int H, int W, float eps,
+                      void* stream);
+int bseg_pack_conv_w9(const float* conv_w, void* w9, void* stream);
+int bseg_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+
+/* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
+long long bseg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSEG_H_ */
