@@ -68,6 +68,9 @@ SIGNATURES = {
     "bseg_decoder_head": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "bseg_pack_conv_w9": (_i, [_vp, _vp, _vp]),
     "bseg_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "bseg_profile_enable": (_i, [_i]),
+    "bseg_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double)]),
 }
 
 

@@ -487,6 +487,16 @@ int bseg_pack_conv_w9(const float* conv_w, void* w9, void* stream) {
   return 0;
 }
 
+int bseg_profile_enable(int on) {
+  prof_set_enabled(on != 0);
+  return 0;
+}
+
+int bseg_profile_collect(double* ms, long long* launches, double* work, double* bytes) {
+  prof_collect(ms, launches, work, bytes);
+  return 0;
+}
+
 int bseg_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
   return launch_f32_to_bf16(src, static_cast<__nv_bfloat16*>(dst), n, static_cast<cudaStream_t>(stream));
 }

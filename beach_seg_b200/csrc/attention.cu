@@ -365,6 +365,8 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     attr_set = true;
   }
   dim3 grid((kT + kQTile - 1) / kQTile, heads, nseq);
+  ProfScope prof(CAT_ATTENTION, static_cast<double>(nseq) * heads * (4.0 * kT * kT * 64 + 2.0 * kT * 84 * 64),
+                 static_cast<double>(nseq) * heads * kT * 64 * 2 * 4, stream);
   attention_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tr, out, heads);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -214,6 +214,8 @@ int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, co
   }
   const long long tiles = static_cast<long long>(B) * (H / kTileH) * (W / kTileW);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  ProfScope prof(CAT_DECODER_HEAD, static_cast<double>(B) * H * W * (2.0 * 576 * 64 + 2.0 * 64 * 3),
+                 static_cast<double>(B) * H * W * (64 * 2 + 3 * 4), stream);
   decoder_head_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tx, tw, conv_b, ln_w, ln_b, head_w, head_b, pred, B, H,
                                                              W, eps);
   BSEG_CHECK_CUDA(cudaGetLastError());

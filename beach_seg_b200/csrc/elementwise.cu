@@ -81,6 +81,7 @@ layernorm1024_kernel(const float* __restrict__ x, long long ldx, const float* __
 int launch_layernorm1024(const float* x, long long ldx, const float* gamma, const float* beta, __nv_bfloat16* out,
                          long long ldo, long long M, float eps, cudaStream_t stream) {
   BSEG_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "layernorm: leading dims must be multiples of 4");
+  ProfScope prof(CAT_LAYERNORM, 0, static_cast<double>(M) * 1024 * 6, stream);
   layernorm1024_kernel<<<blocks_for(M, 8, 148 * 8), 256, 0, stream>>>(x, ldx, gamma, beta, out, ldo, M, eps);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -130,6 +131,7 @@ patchify_kernel(const float* __restrict__ px, const float* __restrict__ prompt_p
 int launch_patchify(const float* px, const float* prompt_px, const float* prompt_mask, const float* /*labels*/,
                     __nv_bfloat16* A, int B, cudaStream_t stream) {
   const long long total = 2LL * B * 3 * 896 * 56;
+  ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(total) * 8 * 6, stream);
   patchify_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, prompt_px, prompt_mask, A, B);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -150,6 +152,7 @@ __global__ void merge_streams_kernel(float4* __restrict__ h, long long n4_half) 
 }
 int launch_merge_streams(float* h, long long n_half, cudaStream_t stream) {
   BSEG_REQUIRE(n_half % 4 == 0, "merge_streams: size must be a multiple of 4");
+  ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(n_half) * 12, stream);
   merge_streams_kernel<<<blocks_for(n_half / 4, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(h), n_half / 4);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -206,6 +209,7 @@ __global__ void ensemble_residual_kernel(float* __restrict__ h, const float* __r
 int launch_ensemble_residual(float* h, const float* attn, int nstreams, int G, int P, int cross_stream, int T, int D,
                              cudaStream_t stream) {
   const long long total = (long long)nstreams * G * T * D / 4;
+  ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(total) * P * 48, stream);
   ensemble_residual_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(h, attn, nstreams, G, P, cross_stream, T, D);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -256,6 +260,7 @@ __global__ void colorize_norm_kernel(const uint8_t* __restrict__ mask, const uin
 int launch_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean,
                          const float* stdv, float* out, int B, int H, int W, cudaStream_t stream) {
   const long long total = (long long)B * H * W;
+  ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(total) * 13, stream);
   colorize_norm_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(mask, palette, num_classes, mean[0], mean[1],
                                                                    mean[2], stdv[0], stdv[1], stdv[2], out, B, H * W);
   BSEG_CHECK_CUDA(cudaGetLastError());
@@ -304,6 +309,7 @@ int launch_decode_palette(const float* pred, const float* palette_norm, int num_
                           long long* out_i64, const uint8_t* nodata, const int* idx, int B, int H, int W,
                           int out_size, cudaStream_t stream) {
   const long long total = (long long)B * out_size * out_size;
+  ProfScope prof(CAT_DECODE, 0, static_cast<double>(B) * H * W * 12 + static_cast<double>(total), stream);
   decode_palette_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(pred, palette_norm, num_classes, out_u8, out_i64,
                                                                     nodata, idx, B, H, W, out_size);
   BSEG_CHECK_CUDA(cudaGetLastError());
@@ -347,6 +353,7 @@ int launch_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls
                            const int* boxes, int use_atomics, cudaStream_t stream) {
   const long long total = (long long)crop * crop * n_tiles;
   if (total == 0) return 0;
+  ProfScope prof(CAT_VOTE, 0, static_cast<double>(total) * 9, stream);
   vote_accumulate_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(counter, Hs, Ws, cls, n_tiles, crop, boxes,
                                                                      use_atomics);
   BSEG_CHECK_CUDA(cudaGetLastError());
@@ -371,6 +378,7 @@ __global__ void vote_argmax_kernel(const uint32_t* __restrict__ counter, uint8_t
 }
 int launch_vote_argmax(const uint32_t* counter, uint8_t* out, long long n, cudaStream_t stream) {
   if (n == 0) return 0;
+  ProfScope prof(CAT_VOTE, 0, static_cast<double>(n) * 5, stream);
   vote_argmax_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(counter, out, n);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -429,6 +437,7 @@ __global__ void smooth_l1_finalize_kernel(const float* __restrict__ scratch, flo
 int launch_smooth_l1(const float* pred, const float* labels, const uint8_t* yesdata, float beta, int per_sample,
                      float* loss_out, float* grad_out, float* scratch, int B, int H, int W, cudaStream_t stream) {
   const int HW = H * W;
+  ProfScope prof(CAT_LOSS, 0, static_cast<double>(B) * HW * (3 * 4 * 3 + 1), stream);
   BSEG_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(float), stream));
   keep_count_kernel<<<blocks_for((long long)B * HW, 1024), 256, 0, stream>>>(yesdata, (long long)B * HW, scratch);
   smooth_l1_kernel<<<blocks_for(3LL * HW, 256), 256, 0, stream>>>(pred, labels, yesdata, beta, per_sample, grad_out,

@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace bseg {
 
@@ -58,6 +59,46 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+struct ProfRec { int cat; cudaEvent_t a, b; double work, bytes; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;
+}  // namespace
+bool prof_enabled() { return g_prof_on; }
+void prof_set_enabled(bool on) { g_prof_on = on; }
+ProfScope::ProfScope(int cat, double work, double bytes, cudaStream_t stream) : idx_(-1), stream_(stream) {
+  if (!g_prof_on) return;
+  ProfRec r{cat, nullptr, nullptr, work, bytes};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  idx_ = static_cast<int>(g_prof.size());
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[idx_].b, stream_);
+}
+void prof_collect(double* ms, long long* launches, double* work, double* bytes) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0; launches[i] = 0; work[i] = 0; bytes[i] = 0; }
+  for (auto& r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.cat] += t;
+    launches[r.cat] += 1;
+    work[r.cat] += r.work;
+    bytes[r.cat] += r.bytes;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+}
 
 int num_sms() {
   static int n = 0;

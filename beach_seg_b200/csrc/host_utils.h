@@ -50,4 +50,19 @@ int num_sms();
 void count_launch(int n = 1);
 long long launch_count();
 
+// Optional per-launch CUDA-event timing on the launching stream (bseg_profile_*), grouped by kernel category.
+enum ProfCat : int {
+  CAT_GEMM = 0, CAT_ATTENTION, CAT_LAYERNORM, CAT_DECODER_HEAD, CAT_INGEST, CAT_DECODE, CAT_VOTE, CAT_ELEMENTWISE,
+  CAT_LOSS, CAT_COUNT
+};
+bool prof_enabled();
+void prof_set_enabled(bool on);
+void prof_collect(double* ms, long long* launches, double* work, double* bytes);  // arrays of CAT_COUNT
+struct ProfScope {
+  ProfScope(int cat, double work, double bytes, cudaStream_t stream);
+  ~ProfScope();
+  int idx_;
+  cudaStream_t stream_;
+};
+
 }  // namespace bseg

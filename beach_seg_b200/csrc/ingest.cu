@@ -193,6 +193,7 @@ int launch_ingest(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, 
     attr_bytes = smem;
   }
   dim3 grid((kOut + band - 1) / band, n_tiles);
+  ProfScope prof(CAT_INGEST, 0, static_cast<double>(n_tiles) * (4.0 * crop * crop * 2 + 3.0 * 448 * 448 * 2), stream);
   ingest_kernel<<<grid, 256, smem, stream>>>(scene, nodata, Hs, Ws, stats, boxes, crop, coef, bounds, ksize, band,
                                              max_rows, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], out_nchw,
                                              out_patch, patch_tile_stride, out_u8, out_nodata);

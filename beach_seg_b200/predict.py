@@ -1,0 +1,131 @@
+"""Tiled inference over a scene: the tensor part of src/predict.py:232-262 (prompted) batched over tiles, plus the
+`Accumulator` vote stitcher (src/predict.py:55-159) kept on the device, and the owner-computes tile sharding used
+when several GPUs work on one scene (inference tiles need no communication)."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Any, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .ml_util import build_palette, generate_random_rgb_palette
+from .seggpt import SegGptB200
+
+
+def create_palette(num_classes: int, batch_size: int, train: bool, device) -> tuple[torch.Tensor, torch.Tensor]:
+    """PromptModel.create_palette (src/model.py:215-231): uint8 palette (B,C,3) and its normalised float copy.
+    train=True draws the random palette from the global CPU generator exactly like the reference."""
+    if train:
+        batch_palette = generate_random_rgb_palette(num_classes, batch_size, "cpu")
+    else:
+        palette = torch.tensor(build_palette(num_classes - 1), dtype=torch.uint8)
+        batch_palette = palette[None].repeat(batch_size, 1, 1)
+    mean = torch.tensor(ops.IMAGE_MEAN, dtype=torch.float32)
+    std = torch.tensor(ops.IMAGE_STD, dtype=torch.float32)
+    palette_norm = (batch_palette.to(torch.float32) / 255 - mean) / std  # host logic: B*C*3 numbers
+    return batch_palette.to(device), palette_norm.to(device)
+
+
+def shard_tiles(n_tiles: int, rank: int, world_size: int) -> range:
+    """Owner-computes sharding: rank r owns a contiguous block of the (row-major sorted) tile list, so each GPU
+    stitches a spatial stripe of the scene.  No data-path collective is needed for inference."""
+    per = (n_tiles + world_size - 1) // world_size
+    return range(min(rank * per, n_tiles), min((rank + 1) * per, n_tiles))
+
+
+class TilePredictor:
+    """ingest -> SegGPT forward -> palette decode (+resize to crop size) for batches of tile boxes of one scene."""
+
+    def __init__(self, model: SegGptB200, crop_size: int, num_classes: int = 4, random_palette: bool = True):
+        self.model = model
+        self.crop_size = crop_size
+        self.num_classes = num_classes
+        self.random_palette = random_palette  # the reference's forward passes train=True (src/model.py:134)
+
+    @torch.no_grad()
+    def predict_tiles(self, scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Tensor, boxes: torch.Tensor,
+                      prompt_images: torch.Tensor, prompt_masks: torch.Tensor,
+                      palette: Optional[tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+        """boxes int32 [n,4]; prompt_images float32 [n,3,448,448] (normalised); prompt_masks uint8 [n,448,448] class
+        ids.  Returns uint8 [n,crop,crop] class maps (nodata pixels are NOT zeroed, like src/predict.py)."""
+        dev = self.model.device
+        n = boxes.shape[0]
+        if palette is None:
+            palette = create_palette(self.num_classes, n, self.random_palette, dev)
+        pal_u8, pal_norm = palette
+        tiles = ops.ingest_tiles(scene_u16, nodata, stats, boxes, self.crop_size)
+        prompt_color = ops.colorize_norm(prompt_masks, pal_u8)
+        out = self.model(pixel_values=tiles["image"], prompt_pixel_values=prompt_images, prompt_masks=prompt_color,
+                         embedding_type="instance")
+        return ops.decode_palette(out.pred_masks, pal_norm, out_size=self.crop_size, dtype=torch.uint8)
+
+
+class Accumulator:
+    """Device-resident version of the reference's Accumulator (src/predict.py:55-159): same constructor and
+    `update` / `save_current` / context-manager protocol.  `update` takes either the reference's one-hot uint8
+    (crop,crop,C) array or a class-index map; votes are uint8 counters with the reference's wrap-around."""
+
+    def __init__(self, out_shape: tuple[int, int], save_dir: Optional[Path], out_transform: Any = None,
+                 crs: Any = None, classes: Sequence[str] = ("nodata", "sand", "water", "veg"),
+                 device: str | torch.device = "cuda:0"):
+        self.out_shape = tuple(out_shape)
+        self.num_classes = len(classes)
+        if self.num_classes > 4:
+            raise ValueError("the packed vote counter holds at most 4 classes")
+        self.out_transform, self.crs, self.classes = out_transform, crs, tuple(classes)
+        self.device = torch.device(device)
+        self.mask_dir = None
+        if save_dir is not None:
+            self.mask_dir = Path(save_dir) / "masks"
+            self.mask_dir.mkdir(exist_ok=True, parents=True)
+        self.current_pred_counter: Optional[torch.Tensor] = None
+        self.current_date = None
+
+    def __enter__(self):
+        assert self.current_pred_counter is None and self.current_date is None
+        return self
+
+    def __exit__(self, a, b, c):
+        if self.current_pred_counter is not None:
+            self.save_current()
+
+    def initialize_current(self, date: str):
+        self.current_date = date
+        self.current_pred_counter = torch.zeros(self.out_shape, dtype=torch.int32, device=self.device)
+
+    def counter_u8(self) -> np.ndarray:
+        """The reference's `current_pred_counter` view: uint8 (H, W, 4)."""
+        assert self.current_pred_counter is not None
+        return self.current_pred_counter.cpu().numpy().view(np.uint8).reshape(*self.out_shape, 4)
+
+    def prediction(self) -> torch.Tensor:
+        """np.argmax(counter, axis=2) (src/predict.py:100) as uint8 (H, W) on the device."""
+        assert self.current_pred_counter is not None
+        return ops.vote_argmax(self.current_pred_counter)
+
+    def save_current(self):
+        assert self.current_pred_counter is not None and self.current_date is not None
+        pred = self.prediction().cpu().numpy()
+        if self.mask_dir is not None:  # PNG / GeoTIFF / overlay writers are outside the hot path
+            import cv2
+
+            cv2.imwrite(str(self.mask_dir / f"{self.current_date}.png"), pred)
+        return pred
+
+    def update(self, date: str, crop, one_hot_pred, img_crop=None, label_crop=None):
+        if date != self.current_date:
+            if self.current_pred_counter is not None:
+                self.save_current()
+            self.initialize_current(date)
+        cls = one_hot_pred
+        if isinstance(cls, np.ndarray):
+            cls = torch.from_numpy(cls)
+        if cls.ndim == 3 and cls.shape[-1] == self.num_classes and cls.shape[0] == cls.shape[1]:
+            cls = cls.argmax(dim=-1)  # one-hot (crop,crop,C) -> index map (host/device view op, exact)
+        cls = cls.to(device=self.device, dtype=torch.uint8)
+        if cls.ndim == 2:
+            cls = cls[None]
+        boxes = torch.as_tensor(np.asarray(crop, dtype=np.int32).reshape(-1, 4), device=self.device)
+        ops.vote_accumulate(self.current_pred_counter, cls.contiguous(), boxes)

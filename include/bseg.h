@@ -158,6 +158,14 @@ int bseg_decoder_head(const void* x_nhwc, const void* w9, const float* conv_b, c
 int bseg_pack_conv_w9(const float* conv_w, void* w9, void* stream);
 int bseg_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 
+/* Per-launch CUDA-event timing on the launching stream, summed per kernel category (bench.py's roofline leg).
+ * Categories: 0 gemm, 1 attention, 2 layernorm, 3 decoder_head, 4 ingest, 5 decode, 6 vote, 7 elementwise, 8 loss.
+ * collect() synchronises the recorded events and fills HOST arrays of BSEG_PROFILE_CATEGORIES entries:
+ * milliseconds, launches, algorithmic work (FLOP) and algorithmic bytes. */
+#define BSEG_PROFILE_CATEGORIES 9
+int bseg_profile_enable(int on);
+int bseg_profile_collect(double* ms, long long* launches, double* work, double* bytes);
+
 /* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
 long long bseg_launch_count(void);
 

@@ -1,0 +1,174 @@
+"""GPU: the bandwidth-bound glue kernels (through the C ABI wrappers in beach_seg_b200.ops) against the oracle
+restatement of the reference lines and the committed golden fixtures.  Integer / index work is bit exact."""
+import numpy as np
+import pytest
+import torch
+
+from beach_seg_b200 import _lib, ops, synth
+from oracle import glue_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(golden_dir / "glue_golden.npz")
+
+
+def test_layernorm(dev):
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn((1000, 1024), generator=gen) * 3 + 0.5
+    w = 1 + 0.1 * torch.randn(1024, generator=gen)
+    b = 0.1 * torch.randn(1024, generator=gen)
+    want = torch.nn.functional.layer_norm(x, (1024,), w, b, 1e-6)
+    xd, wd, bd = x.to(dev), w.to(dev), b.to(dev)
+    out = torch.zeros((1000, 4096), dtype=torch.bfloat16, device=dev)
+    view = out[:, 1024:2048]
+    _lib.check(_lib.lib().bseg_layernorm1024(_lib.ptr(xd), 1024, _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(view), 4096,
+                                             1000, 1e-6, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out[:, 1024:2048].float().cpu()
+    assert (got - want).abs().max().item() < 2e-2  # bf16 output rounding of |x| <~ 4
+    assert torch.equal(got, want.to(torch.bfloat16).float()) or (got - want.to(torch.bfloat16).float()).abs().max() < 0.04
+    assert out[:, :1024].abs().max().item() == 0 and out[:, 2048:].abs().max().item() == 0
+
+
+def test_colorize_norm_bit_exact(dev, g):
+    pal = torch.from_numpy(g["random_palette_seed42"])
+    mask = torch.from_numpy(g["apply_mask_in"])
+    want = glue_ref.normalize(torch.from_numpy(g["apply_mask_out"]))  # golden from the real torch_apply_mask_rgb
+    got = ops.colorize_norm(mask.to(dev), pal.to(dev)).cpu()
+    assert torch.equal(got, want)
+    # full-size seeded case against the oracle restatement
+    m = synth.blocky_mask(3, seed=4)
+    torch.manual_seed(7)
+    pal = glue_ref.generate_random_rgb_palette(4, 3)
+    want = glue_ref.normalize(glue_ref.torch_apply_mask_rgb(pal, m))
+    assert torch.equal(ops.colorize_norm(m.to(dev), pal.to(dev)).cpu(), want)
+
+
+def test_decode_palette_bit_exact(dev, g):
+    pred = torch.from_numpy(g["decode_pred"])
+    paln = torch.from_numpy(g["decode_palette_norm"])
+    got = ops.decode_palette(pred.to(dev), paln.to(dev)).cpu()
+    assert got.dtype == torch.int64 and np.array_equal(got.numpy(), g["decode_out"])  # includes the tie case
+    gen = torch.Generator().manual_seed(3)
+    pred = torch.randn((2, 3, 896, 448), generator=gen)
+    _, paln = glue_ref.create_palette(4, 2, train=True, generator=gen)
+    want = glue_ref.process_pred_masks(pred, paln)
+    assert torch.equal(ops.decode_palette(pred.to(dev), paln.to(dev)).cpu(), want)
+    # fused cv2 INTER_NEAREST resize (src/predict.py:258) + nodata zeroing (src/predict_no_prompt.py:303)
+    for crop in (512, 112, 336):
+        nod = torch.from_numpy(np.random.default_rng(crop).random((2, crop, crop)) < 0.1)
+        got = ops.decode_palette(pred.to(dev), paln.to(dev), out_size=crop, nodata=nod.to(dev), dtype=torch.uint8)
+        for b in range(2):
+            pm, _ = glue_ref.predict_tail(want[b].numpy(), crop)
+            pm = pm.copy()
+            pm[nod[b].numpy()] = 0
+            assert np.array_equal(got[b].cpu().numpy(), pm.astype(np.uint8))
+
+
+def test_vote_stitch_bit_exact(dev, g):
+    counter = torch.zeros((30, 44), dtype=torch.int32, device=dev)
+    boxes = torch.from_numpy(g["vote_boxes"]).to(dev)
+    cls = torch.from_numpy(g["vote_cls"]).to(dev)
+    ops.vote_accumulate(counter, cls, boxes, overlapping=True)  # all six tiles (two identical boxes) in ONE launch
+    assert np.array_equal(counter.cpu().numpy().view(np.uint8).reshape(30, 44, 4), g["vote_counter"])
+    assert np.array_equal(ops.vote_argmax(counter).cpu().numpy(), g["vote_argmax"])
+    # tile-at-a-time (non-atomic path) gives the same canvas
+    c2 = torch.zeros((30, 44), dtype=torch.int32, device=dev)
+    for i in range(len(boxes)):
+        ops.vote_accumulate(c2, cls[i:i + 1], boxes[i:i + 1])
+    assert torch.equal(c2, counter)
+
+
+def test_vote_uint8_wraparound(dev):
+    """The reference counter is uint8 and wraps at 256 (src/predict.py:114-118): 300 votes -> 44, no carry."""
+    counter = torch.zeros((8, 8), dtype=torch.int32, device=dev)
+    n = 300
+    cls = torch.full((n, 8, 8), 1, dtype=torch.uint8, device=dev)
+    cls[:, :, 4:] = 3
+    boxes = torch.tensor([[0, 0, 8, 8]] * n, dtype=torch.int32, device=dev)
+    ops.vote_accumulate(counter, cls, boxes, overlapping=True)
+    got = counter.cpu().numpy().view(np.uint8).reshape(8, 8, 4)
+    want = np.zeros((8, 8, 4), dtype=np.uint8)
+    want[:, :4, 1] = n % 256
+    want[:, 4:, 3] = n % 256
+    assert np.array_equal(got, want)
+
+
+def test_full_scene_stitch_properties(dev):
+    """BASELINE config 3 geometry (8000x4000 scene, 512 px tiles, stride 448 -> 18x9 = 162 tiles): the canvas equals
+    the numpy Accumulator restatement, every pixel received between 1 and 4 votes, argmax is idempotent."""
+    Hs, Ws, crop = 4000, 8000, 512
+    boxes_np = synth.sliding_boxes(Hs, Ws, crop, 448)
+    assert len(boxes_np) == 162
+    rng = np.random.default_rng(0)
+    cls_np = rng.integers(0, 4, size=(len(boxes_np), crop, crop)).astype(np.uint8)
+    counter = torch.zeros((Hs, Ws), dtype=torch.int32, device=dev)
+    ops.vote_accumulate(counter, torch.from_numpy(cls_np).to(dev), torch.from_numpy(boxes_np).to(dev))
+    acc = glue_ref.AccumulatorRef((Hs, Ws))
+    for b, c in zip(boxes_np, cls_np):
+        acc.update(tuple(int(v) for v in b), np.eye(4, dtype=np.uint8)[c])
+    got = counter.cpu().numpy().view(np.uint8).reshape(Hs, Ws, 4)
+    assert np.array_equal(got, acc.counter)
+    votes = got.sum(axis=2)
+    assert votes.min() >= 1 and votes.max() <= 4
+    assert np.array_equal(ops.vote_argmax(counter).cpu().numpy(), acc.argmax().astype(np.uint8))
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_loss_golden_and_grad(dev, g, B):
+    pred, lab, yes = (torch.from_numpy(g[f"loss_{k}_B{B}"]) for k in ("pred", "labels", "yes"))
+    got = ops.smooth_l1_loss(pred.to(dev), lab.to(dev), yes.to(dev), 0.01, per_sample=False)
+    np.testing.assert_allclose(got.item(), g[f"loss_out_B{B}"], rtol=2e-6)
+    for per_sample in (False, True):
+        p = pred.clone().requires_grad_(True)
+        want = glue_ref.seggpt_loss(p, lab, yes, 0.01, per_sample=per_sample)
+        want.backward()
+        loss, grad = ops.smooth_l1_loss(pred.to(dev), lab.to(dev), yes.to(dev), 0.01, per_sample=per_sample,
+                                        want_grad=True)
+        np.testing.assert_allclose(loss.item(), want.item(), rtol=2e-6)
+        np.testing.assert_allclose(grad.cpu().numpy(), p.grad.numpy(), rtol=1e-5, atol=1e-9)
+
+
+def test_loss_full_size(dev):
+    gen = torch.Generator().manual_seed(8)
+    pred = torch.randn((2, 3, 896, 448), generator=gen)
+    lab = torch.randn((2, 3, 448, 448), generator=gen)
+    yes = torch.rand((2, 1, 448, 448), generator=gen) > 0.25
+    for per_sample in (False, True):
+        want = glue_ref.seggpt_loss(pred, lab, yes, 0.01, per_sample=per_sample)
+        got = ops.smooth_l1_loss(pred.to(dev), lab.to(dev), yes.to(dev), 0.01, per_sample=per_sample)
+        np.testing.assert_allclose(got.item(), want.item(), rtol=1e-5)
+
+
+def _ingest_oracle(scene, nodata, boxes, crop):
+    u8 = glue_ref.tif_image_4band(scene.astype(np.float32), nodata)
+    imgs, crops, nds = [], [], []
+    for b in boxes:
+        ci, cn, _ = glue_ref.crop_tif(tuple(int(v) for v in b), u8, nodata, None, crop)
+        crops.append(ci)
+        nds.append(cn)
+        imgs.append(glue_ref.normalize(torch.from_numpy(glue_ref.get_crop_image(ci, 448))[None])[0])
+    return np.stack(crops), np.stack(nds), torch.stack(imgs)
+
+
+@pytest.mark.parametrize("crop,Hs,Ws", [(512, 1100, 1300), (112, 300, 420), (448, 900, 1000), (1024, 1500, 2100)])
+def test_ingest_bit_exact(dev, crop, Hs, Ws):
+    scene = synth.scene_u16(Hs, Ws, seed=crop)
+    nodata = synth.nodata_wedge(Hs, Ws)
+    boxes = np.array([[0, 0, crop, crop], [Ws - crop - 3, Hs - crop - 5, Ws - 3, Hs - 5],
+                      [-(crop // 3), -(crop // 4), crop - crop // 3, crop - crop // 4],
+                      [Ws - crop // 2, Hs - crop // 2, Ws + crop - crop // 2, Hs + crop - crop // 2]], dtype=np.int32)
+    want_u8, want_nd, want_img = _ingest_oracle(scene, nodata, boxes, crop)
+    sc = torch.from_numpy(scene.view(np.int16)).to(dev)
+    nd = torch.from_numpy(nodata).to(dev)
+    stats = ops.scene_stats(sc, nd)
+    comp = np.stack([scene[3], scene[2], scene[:2].astype(np.float32).mean(axis=0)]).astype(np.float32)
+    want_stats = np.array([comp[:, ~nodata].min(), comp[0].max(), comp[1].max(), comp[2].max()], dtype=np.float32)
+    assert np.array_equal(stats.cpu().numpy(), want_stats)
+    out = ops.ingest_tiles(sc, nd, stats, torch.from_numpy(boxes).to(dev), crop, want_u8=True, want_nodata=True)
+    assert np.array_equal(out["u8"].cpu().numpy(), want_u8)
+    assert np.array_equal(out["nodata"].cpu().numpy().astype(bool), want_nd.astype(bool))
+    assert torch.equal(out["image"].cpu(), want_img)
