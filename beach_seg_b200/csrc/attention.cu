@@ -1,15 +1,21 @@
-// Fused SegGPT attention for one (sequence, head, 128-query tile) per CTA:
+// Fused SegGPT attention, one CTA per (sequence, head, 256-query tile):
 //     out = softmax( (q*scale) k^T + rel_h[q, kh] + rel_w[q, kw] ) v
 // with the decomposed relative-position bias of modeling_seggpt.py:268-311 computed from the UNSCALED q
 // (modeling_seggpt.py:324-329) and an fp32 softmax (:331).  The reference materialises a
 // (16n,1568,1568) fp32 score tensor; here S tiles live in TMEM and never touch HBM.
 //
-//   warp 0      TMA producer   (Q tile + rel tables once, then 112-key K / V^T blocks through a 3-stage ring)
-//   warp 1      tcgen05 issuer (G = Q*Rel^T once; per key block S = Q*K^T (N=112) and O_part = P*V (N=64))
-//   warps 2-5   softmax        (thread <-> query row == TMEM lane; P goes back through swizzled smem)
+//   warp 0      TMA producer   (two 128-query Q tiles + rel tables once; 112-key K blocks and V^T blocks through
+//                               two independent 2-stage rings, K running one block ahead of V)
+//   warp 1      tcgen05 issuer (G = Q*Rel^T once per query tile; per key block S = Q*K^T (N=112), O += P*V (N=64))
+//   warps 2-3   idle (they complete the control warpgroup, which gives its registers away with setmaxnreg)
+//   warps 4-7   softmax warpgroup 0 (query rows   0..127 of the tile; thread <-> row == TMEM lane)
+//   warps 8-11  softmax warpgroup 1 (query rows 128..255)
 //
-// Key blocks are 112 keys = 4 rows of the 28-wide token grid, so a score column maps to (kh, kw) at compile
-// time and 1568 = 14 * 112 needs no key masking.
+// Per key block a softmax thread copies its S row (112 fp32) from TMEM to registers in one pass and frees the S
+// buffer at once, so the next S = Q*K^T overlaps the exponentials.  O accumulates in TMEM across key blocks; it is
+// only rescaled when the running row max grows by more than 2^8 (exact: a stale max merely changes the common
+// scale of P and O).  Key blocks are 112 keys = 4 rows of the 28-wide token grid, so a score column maps to
+// (kh, kw) at compile time and 1568 = 14 * 112 needs no key masking.
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"
@@ -17,39 +23,44 @@
 namespace bseg {
 
 namespace attn {
-constexpr int kQTile = 128;
-constexpr int kKB = 112;         // keys per block
-constexpr int kGridW = 28;       // token grid width
+constexpr int kWG = 2;
+constexpr int kQTile = 128;            // queries per softmax warpgroup
+constexpr int kCtaQ = kWG * kQTile;    // 256
+constexpr int kKB = 112;               // keys per block
+constexpr int kGridW = 28;
 constexpr int kGridH = 56;
-constexpr int kT = kGridW * kGridH;  // 1568
-constexpr int kNumKB = kT / kKB;     // 14
-constexpr int kStages = 3;
-constexpr int kThreads = 192;
+constexpr int kT = kGridW * kGridH;    // 1568
+constexpr int kNumKB = kT / kKB;       // 14
+constexpr int kStages = 2;
+constexpr int kThreads = 128 + kWG * 128;  // 384
+constexpr int kRegsControl = 40;
+constexpr int kRegsSoftmax = 232;  // 128*40 + 256*232 = 64512 <= 65536
 constexpr int kRelRows = 176;  // 112 (reversed rel_pos_h, 111 used) + 64 (reversed rel_pos_w, 55 used)
 
-constexpr int kQBytes = kQTile * 128;        // 16384
+constexpr int kQBytes = kQTile * 128;        // 16384 per warpgroup
 constexpr int kKBytes = kKB * 128;           // 14336
 constexpr int kVBytes = 2 * 64 * 128;        // 16384 (two 64-key halves)
-constexpr int kPBytes = 2 * kQTile * 128;    // 32768 (two 64-key atoms; second uses 48 keys)
-constexpr int kRelBytes = kRelRows * 128;    // 22528 (lives in the P buffer before the main loop)
+constexpr int kPBytes = 2 * kQTile * 128;    // 32768 per warpgroup (two 64-key atoms; second uses 48 keys)
+constexpr int kRelBytes = kRelRows * 128;    // 22528 (lives in warpgroup 0's P buffer before the main loop)
 constexpr int kBhStride = 57;                // fp32 words per row (odd -> conflict free)
 constexpr int kBhBytes = kQTile * kBhStride * 4;
 
 constexpr int kOffQ = 0;
-constexpr int kOffK = kOffQ + kQBytes;
+constexpr int kOffK = kOffQ + kWG * kQBytes;
 constexpr int kOffV = kOffK + kStages * kKBytes;
 constexpr int kOffP = kOffV + kStages * kVBytes;
-constexpr int kOffBh = kOffP + kPBytes;
-constexpr int kOffBar = kOffBh + kBhBytes;
+constexpr int kOffBh = kOffP + kWG * kPBytes;
+constexpr int kOffBar = kOffBh + kWG * kBhBytes;
 constexpr int kSmemBytes = kOffBar + 256 + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-// TMEM columns
+// TMEM columns: warpgroup w owns [w*192, w*192+192): S at +0 (128), O at +128 (64); G (176) overlays both in the prologue
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0;     // 2 x 128
-constexpr uint32_t kColO = 256;   // 2 x 64
-constexpr uint32_t kColG = 256;   // 176 columns, dead before the first P*V
+constexpr uint32_t kColsPerWG = 192;
+constexpr uint32_t kColO = 128;
 
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
 }  // namespace attn
 
 __global__ void __launch_bounds__(attn::kThreads, 1)
@@ -63,23 +74,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
   uint8_t* sP = smem + kOffP;
-  float* sBh = reinterpret_cast<float*>(smem + kOffBh);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* g_full = bars + 1;
-  uint64_t* p_full = bars + 2;
-  uint64_t* kv_full = bars + 3;             // [3]
-  uint64_t* kv_empty = bars + 6;            // [3]
-  uint64_t* s_full = bars + 9;              // [2]
-  uint64_t* o_full = bars + 11;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* v_full = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;    // [2]
+  uint64_t* s_full = bars + 10;    // [kWG]  MMA -> softmax: S_j is in TMEM
+  uint64_t* s_free = bars + 12;    // [kWG]  softmax -> MMA: the S region may be overwritten
+  uint64_t* p_full = bars + 14;    // [kWG]  softmax -> MMA: P_j is in smem (and O rescaled if it had to be)
+  uint64_t* pv_done = bars + 16;   // [kWG]  MMA -> softmax: O += P_j V_j retired (P buffer free, O stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x;
+  const int q0 = blockIdx.x * kCtaQ;
   const int head = blockIdx.y;
   const int seq = blockIdx.z;
   const int sh = seq * heads + head;
+  const int n_active = (q0 + kQTile < kT) ? 2 : 1;  // the last tile of a sequence has one live warpgroup
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -88,14 +102,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_prefetch_desc(&tmap_rel);
     mbar_init(q_full, 1);
     mbar_init(g_full, 1);
-    mbar_init(p_full, 128);
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kWG; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&o_full[i], 1);
+      mbar_init(&s_free[i], 4);   // one arrive per softmax warp
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
   }
@@ -105,19 +122,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kQBytes + kRelBytes);
-      tma_load_3d(sQ, &tmap_q, q_full, 0, qt * kQTile, sh);
+      mbar_arrive_expect_tx(q_full, n_active * kQBytes + kRelBytes);
+      for (int w = 0; w < n_active; ++w) tma_load_3d(sQ + w * kQBytes, &tmap_q, q_full, 0, q0 + w * kQTile, sh);
       tma_load_2d(sP, &tmap_rel, q_full, 0, 0);
-      for (int kb = 0; kb < kNumKB; ++kb) {
+      auto load_k = [&](int kb) {
         const int st = kb % kStages;
-        if (kb >= kStages) mbar_wait(&kv_empty[st], ((kb / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], kKBytes + kVBytes);
-        tma_load_3d(sK + st * kKBytes, &tmap_k, &kv_full[st], 0, kb * kKB, sh);
-        tma_load_3d(sV + st * kVBytes, &tmap_vt, &kv_full[st], kb * kKB, 0, sh);
-        tma_load_3d(sV + st * kVBytes + 8192, &tmap_vt, &kv_full[st], kb * kKB + 64, 0, sh);
+        if (kb >= kStages) mbar_wait(&k_empty[st], ((kb / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kKBytes);
+        tma_load_3d(sK + st * kKBytes, &tmap_k, &k_full[st], 0, kb * kKB, sh);
+      };
+      auto load_v = [&](int kb) {
+        const int st = kb % kStages;
+        if (kb >= kStages) mbar_wait(&v_empty[st], ((kb / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kVBytes);
+        tma_load_3d(sV + st * kVBytes, &tmap_vt, &v_full[st], kb * kKB, 0, sh);
+        tma_load_3d(sV + st * kVBytes + 8192, &tmap_vt, &v_full[st], kb * kKB + 64, 0, sh);
+      };
+      // K stages free up one block earlier than V stages (S_{j+1} is issued before P_j V_j): keep K one ahead
+      load_k(0);
+      for (int kb = 0; kb < kNumKB; ++kb) {
+        if (kb + 1 < kNumKB) load_k(kb + 1);
+        load_v(kb);
       }
     }
   } else if (warp == 1) {
@@ -129,193 +159,207 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
 
-      auto issue_s = [&](int kb) {
+      auto issue_s = [&](int kb) {  // S_w(kb) for every live warpgroup, then release the K stage
         const int st = kb % kStages;
-        mbar_wait(&kv_full[st], (kb / kStages) & 1);
-        tc_fence_after();
+        mbar_wait(&k_full[st], (kb / kStages) & 1);
         const uint32_t k_addr = smem_u32(sK + st * kKBytes);
-        const uint32_t d = tmem_base + kColS + (kb & 1) * 128;
+        for (int w = 0; w < n_active; ++w) {
+          mbar_wait(&s_free[w], kb & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + w * kColsPerWG;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(d, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s,
-                       k != 0);
-        umma_commit(&s_full[kb & 1]);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d, umma_desc_sw128_kmajor(q_addr + w * kQBytes + k * 32),
+                         umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s, k != 0);
+          umma_commit(&s_full[w]);
+        }
+        umma_commit(&k_empty[st]);
       };
 
       mbar_wait(q_full, 0);
       tc_fence_after();
+      for (int w = 0; w < n_active; ++w) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16_ss(tmem_base + kColG, umma_desc_sw128_kmajor(q_addr + k * 32),
-                     umma_desc_sw128_kmajor(p_addr + k * 32), idesc_g, k != 0);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + w * kColsPerWG, umma_desc_sw128_kmajor(q_addr + w * kQBytes + k * 32),
+                       umma_desc_sw128_kmajor(p_addr + k * 32), idesc_g, k != 0);
+      }
       umma_commit(g_full);
       issue_s(0);
-      issue_s(1);
       for (int kb = 0; kb < kNumKB; ++kb) {
+        if (kb + 1 < kNumKB) issue_s(kb + 1);
         const int st = kb % kStages;
-        mbar_wait(p_full, kb & 1);  // P_kb is in smem, S[kb&1] and O[kb&1] are free
-        tc_fence_after();
+        mbar_wait(&v_full[st], (kb / kStages) & 1);
         const uint32_t v_addr = smem_u32(sV + st * kVBytes);
-        const uint32_t d = tmem_base + kColO + (kb & 1) * 64;
+        for (int w = 0; w < n_active; ++w) {
+          mbar_wait(&p_full[w], kb & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + w * kColsPerWG + kColO;
 #pragma unroll
-        for (int k = 0; k < kKB / 16; ++k) {
-          const uint32_t pa = p_addr + (k >> 2) * (kQTile * 128) + (k & 3) * 32;
-          const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
-          umma_bf16_ss(d, umma_desc_sw128_kmajor(pa), umma_desc_sw128_kmajor(va), idesc_o, k != 0);
+          for (int k = 0; k < kKB / 16; ++k) {
+            const uint32_t pa = p_addr + w * kPBytes + (k >> 2) * (kQTile * 128) + (k & 3) * 32;
+            const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
+            umma_bf16_ss(d, umma_desc_sw128_kmajor(pa), umma_desc_sw128_kmajor(va), idesc_o, (kb | k) != 0);
+          }
+          umma_commit(&pv_done[w]);
         }
-        umma_commit(&o_full[kb & 1]);
-        umma_commit(&kv_empty[st]);
-        if (kb + 2 < kNumKB) issue_s(kb + 2);
+        umma_commit(&v_empty[st]);
       }
     }
+  }
   } else {
-    // ============================ softmax warps ============================
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // query row in tile == TMEM lane
-    const int qi_raw = qt * kQTile + r;
-    const bool valid = qi_raw < kT;
-    const int qi = valid ? qi_raw : kT - 1;
-    const int qh = qi / kGridW, qw = qi % kGridW;
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* bh_row = sBh + r * kBhStride;
-    float* stage = reinterpret_cast<float*>(sP + r * 128);  // this thread's own P row (atom 0)
+    // ============================ softmax warpgroups ============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
+    const int w = (warp - 4) >> 2;
+    if (w < n_active) {
+      const int quarter = warp & 3;
+      const int r = quarter * 32 + lane;  // query row in the warpgroup tile == TMEM lane
+      const int qi_raw = q0 + w * kQTile + r;
+      const bool valid = qi_raw < kT;
+      const int qi = valid ? qi_raw : kT - 1;
+      const int qh = qi / kGridW, qw = qi % kGridW;
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * kColsPerWG;
+      float* bh_row = reinterpret_cast<float*>(smem + kOffBh + w * kBhBytes) + r * kBhStride;
+      uint8_t* sPw = sP + w * kPBytes;
+      float* stage = reinterpret_cast<float*>(sPw + r * 128);  // this thread's own P row (atom 0)
 
-    // ---- prologue: decomposed rel-pos bias for this query, pre-multiplied by log2(e) ----
-    mbar_wait(g_full, 0);
-    tc_fence_after();
-    {
-      const int off_h = 55 - qh;  // bh[kh] = G[off_h + kh]
-#pragma unroll
-      for (int c = 0; c < 112; c += 16) {
-        float v[16];
-        tmem_ld16(lane_base + kColG + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int kh = c + i - off_h;
-          if (kh >= 0 && kh < kGridH) bh_row[kh] = v[i] * kLog2e;
-        }
-      }
-      const int off_w = 27 - qw;  // bw[kw] = G[112 + off_w + kw]
-#pragma unroll
-      for (int c = 0; c < 64; c += 16) {
-        float v[16];
-        tmem_ld16(lane_base + kColG + 112 + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int kw = c + i - off_w;
-          if (kw >= 0 && kw < kGridW) stage[kw] = v[i] * kLog2e;
-        }
-      }
-    }
-    float bw[kGridW];
-#pragma unroll
-    for (int i = 0; i < kGridW; ++i) bw[i] = stage[i];
-
-    float o_acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-    const float sc = 0.125f * kLog2e;  // head_dim^-0.5 * log2(e)
-
-    for (int kb = 0; kb < kNumKB; ++kb) {
-      const uint32_t s_addr = lane_base + kColS + (kb & 1) * 128;
-      mbar_wait(&s_full[kb & 1], (kb >> 1) & 1);
+      // ---- prologue: decomposed rel-pos bias of this query, pre-multiplied by log2(e) ----
+      mbar_wait(g_full, 0);
       tc_fence_after();
-      float bh4[4];
+      {
+        const int off_h = 55 - qh;  // bh[kh] = G[off_h + kh]
 #pragma unroll
-      for (int i = 0; i < 4; ++i) bh4[i] = bh_row[kb * 4 + i];
-
-      // pass 1: block max of y = s*scale*log2e + (bh + bw)*log2e
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < kKB; c += 16) {
-        float v[16];
-        tmem_ld16(s_addr + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = c + i;
-          mx = fmaxf(mx, fmaf(v[i], sc, bh4[col / kGridW] + bw[col % kGridW]));
-        }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f(m_run - m_new);  // first block: exp2(-inf) = 0
-      m_run = m_new;
-
-      // the previous P*V must have finished reading the P buffer before it is overwritten
-      if (kb > 0) {
-        mbar_wait(&o_full[(kb - 1) & 1], ((kb - 1) >> 1) & 1);
-        tc_fence_after();
-      }
-
-      // pass 2: p = exp2(y - m), row sum, bf16 P tile into 128B-swizzled smem
-      float lsum = 0.f;
-#pragma unroll
-      for (int c = 0; c < kKB; c += 16) {
-        float v[16];
-        tmem_ld16(s_addr + c, v);
-        tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const int c0 = c + i, c1 = c + i + 1;
-          const float p0 = exp2f(fmaf(v[i], sc, bh4[c0 / kGridW] + bw[c0 % kGridW]) - m_new);
-          const float p1 = exp2f(fmaf(v[i + 1], sc, bh4[c1 / kGridW] + bw[c1 % kGridW]) - m_new);
-          lsum += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        // columns c..c+15 -> two 16B chunks of this row
-        const int atom = c >> 6;
-        const int ch = (c & 63) >> 3;
-        uint8_t* rowp = sP + atom * (kQTile * 128) + r * 128;
-        *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-      l_run = l_run * alpha + lsum;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
-
-      // fold the previous block's P*V into the running output while the tensor core works on this block
-      if (kb > 0) {
-        const uint32_t o_addr = lane_base + kColO + ((kb - 1) & 1) * 64;
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          float v[32];
-          tmem_ld32(o_addr + c, v);
+        for (int c = 0; c < 112; c += 16) {
+          float v[16];
+          tmem_ld16(lane_base + c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], alpha_prev, v[i]);
+          for (int i = 0; i < 16; ++i) {
+            const int kh = c + i - off_h;
+            if (kh >= 0 && kh < kGridH) bh_row[kh] = v[i] * kLog2e;
+          }
+        }
+        const int off_w = 27 - qw;  // bw[kw] = G[112 + off_w + kw]
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+          float v[16];
+          tmem_ld16(lane_base + 112 + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int kw = c + i - off_w;
+            if (kw >= 0 && kw < kGridW) stage[kw] = v[i] * kLog2e;
+          }
         }
       }
-      alpha_prev = alpha;
-    }
-    {
-      constexpr int last = kNumKB - 1;
-      mbar_wait(&o_full[last & 1], (last >> 1) & 1);
-      tc_fence_after();
-      const uint32_t o_addr = lane_base + kColO + (last & 1) * 64;
+      float bw[kGridW];
 #pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        float v[32];
-        tmem_ld32(o_addr + c, v);
+      for (int i = 0; i < kGridW; ++i) bw[i] = stage[i];
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[w]);  // G consumed: the S region is free for S_0
+
+      float m_run = -INFINITY, l_run = 0.f;
+      const float sc = 0.125f * kLog2e;  // head_dim^-0.5 * log2(e)
+
+      for (int kb = 0; kb < kNumKB; ++kb) {
+        mbar_wait(&s_full[w], kb & 1);
+        tc_fence_after();
+        float s[kKB];
+        float bh4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bh4[i] = bh_row[kb * 4 + i];
+        // t = s*scale*log2e + bw*log2e, streamed chunk by chunk behind the TMEM loads; block max of (t + bh*log2e)
+        float gm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        tmem_ld16(lane_base, *reinterpret_cast<float(*)[16]>(&s[0]));
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], alpha_prev, v[i]);
+        for (int c = 0; c < kKB; c += 16) {
+          if (c + 16 < kKB) tmem_ld16(lane_base + c + 16, *reinterpret_cast<float(*)[16]>(&s[c + 16]));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = c + i;
+            s[col] = fmaf(s[col], sc, bw[col % kGridW]);
+            gm[col / kGridW] = fmaxf(gm[col / kGridW], s[col]);
+          }
+          if (c + 16 < kKB) tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[w]);  // S_kb is in registers: S_{kb+1} may be issued
+        const float mx = fmaxf(fmaxf(gm[0] + bh4[0], gm[1] + bh4[1]), fmaxf(gm[2] + bh4[2], gm[3] + bh4[3]));
+
+        if (kb > 0) {
+          // P buffer and O are ours again once the previous P*V has retired
+          mbar_wait(&pv_done[w], (kb - 1) & 1);
+          tc_fence_after();
+          const bool need = mx > m_run + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? mx : m_run;
+            const float alpha = need ? ex2_approx(m_run - m_new) : 1.0f;
+#pragma unroll
+            for (int c = 0; c < 64; c += 16) {
+              float v[16];
+              tmem_ld16(lane_base + kColO + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= alpha;
+              tmem_st16(lane_base + kColO + c, v);
+            }
+            tmem_st_wait();
+            l_run *= alpha;
+            m_run = m_new;
+          }
+        } else {
+          m_run = mx;
+        }
+
+        // p = 2^(t + bh - m), row sum, bf16 P tile into 128B-swizzled smem
+        float lsum = 0.f;
+        float og[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) og[i] = bh4[i] - m_run;
+#pragma unroll
+        for (int c = 0; c < kKB; c += 8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const int c0 = c + i, c1 = c + i + 1;
+            const float p0 = ex2_approx(s[c0] + og[c0 / kGridW]);
+            const float p1 = ex2_approx(s[c1] + og[c1 / kGridW]);
+            lsum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          const int atom = c >> 6;
+          const int ch = (c & 63) >> 3;
+          *reinterpret_cast<uint4*>(sPw + atom * (kQTile * 128) + r * 128 + ((ch ^ (r & 7)) << 4)) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l_run += lsum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[w]);
       }
-    }
-    if (valid) {
+
+      // ---- epilogue: O / l -> bf16, token-major [seq, t, heads*64] ----
+      mbar_wait(&pv_done[w], (kNumKB - 1) & 1);
+      tc_fence_after();
       const float inv = 1.0f / l_run;
       __nv_bfloat16* dst = out + (static_cast<long long>(seq) * kT + qi) * (heads * 64) + head * 64;
 #pragma unroll
-      for (int i = 0; i < 64; i += 8) {
-        uint4 pk = make_uint4(pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv),
-                              pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv),
-                              pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv),
-                              pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv));
-        *reinterpret_cast<uint4*>(dst + i) = pk;
+      for (int c = 0; c < 64; c += 16) {
+        float v[16];
+        tmem_ld16(lane_base + kColO + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          *reinterpret_cast<uint4*>(dst + c) =
+              make_uint4(pack_bf16x2(v[0] * inv, v[1] * inv), pack_bf16x2(v[2] * inv, v[3] * inv),
+                         pack_bf16x2(v[4] * inv, v[5] * inv), pack_bf16x2(v[6] * inv, v[7] * inv));
+          *reinterpret_cast<uint4*>(dst + c + 8) =
+              make_uint4(pack_bf16x2(v[8] * inv, v[9] * inv), pack_bf16x2(v[10] * inv, v[11] * inv),
+                         pack_bf16x2(v[12] * inv, v[13] * inv), pack_bf16x2(v[14] * inv, v[15] * inv));
+        }
       }
     }
   }
@@ -364,7 +408,7 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
         cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((kT + kQTile - 1) / kQTile, heads, nseq);
+  dim3 grid((kT + kCtaQ - 1) / kCtaQ, heads, nseq);
   ProfScope prof(CAT_ATTENTION, static_cast<double>(nseq) * heads * (4.0 * kT * kT * 64 + 2.0 * kT * 84 * 64),
                  static_cast<double>(nseq) * heads * kT * 64 * 2 * 4, stream);
   attention_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tr, out, heads);
