@@ -2,20 +2,21 @@
 //     out = softmax( (q*scale) k^T + rel_h[q, kh] + rel_w[q, kw] ) v
 // with the decomposed relative-position bias of modeling_seggpt.py:268-311 computed from the UNSCALED q
 // (modeling_seggpt.py:324-329) and an fp32 softmax (:331).  The reference materialises a
-// (16n,1568,1568) fp32 score tensor; here S tiles live in TMEM and never touch HBM.
+// (16n,1568,1568) fp32 score tensor; here S, P and O live in TMEM and never touch HBM.
 //
 //   warp 0      TMA producer   (two 128-query Q tiles + rel tables once; 112-key K blocks and V^T blocks through
-//                               two independent 2-stage rings, K running one block ahead of V)
-//   warp 1      tcgen05 issuer (G = Q*Rel^T once per query tile; per key block S = Q*K^T (N=112), O += P*V (N=64))
+//                               two independent 3-stage rings)
+//   warp 1      tcgen05 issuer (G = Q*Rel^T once per query tile; per key block S = Q*K^T (N=112) and
+//                               O += P*V (N=64, P read from TMEM); event driven: whichever warpgroup is ready)
 //   warps 2-3   idle (they complete the control warpgroup, which gives its registers away with setmaxnreg)
 //   warps 4-7   softmax warpgroup 0 (query rows   0..127 of the tile; thread <-> row == TMEM lane)
 //   warps 8-11  softmax warpgroup 1 (query rows 128..255)
 //
-// Per key block a softmax thread copies its S row (112 fp32) from TMEM to registers in one pass and frees the S
-// buffer at once, so the next S = Q*K^T overlaps the exponentials.  O accumulates in TMEM across key blocks; it is
-// only rescaled when the running row max grows by more than 2^8 (exact: a stale max merely changes the common
-// scale of P and O).  Key blocks are 112 keys = 4 rows of the 28-wide token grid, so a score column maps to
-// (kh, kw) at compile time and 1568 = 14 * 112 needs no key masking.
+// Per key block a softmax thread streams its S row (112 fp32) from TMEM into registers once and frees the S buffer,
+// so the next S = Q*K^T overlaps the exponentials; P goes back to TMEM as packed bf16 (the A operand of P*V).
+// O accumulates in TMEM across key blocks and is only rescaled when the running row max grows by more than 2^8
+// (exact: a stale max merely changes the common scale of P and O).  Key blocks are 112 keys = 4 rows of the
+// 28-wide token grid, so a score column maps to (kh, kw) at compile time and 1568 = 14 * 112 needs no key masking.
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"
@@ -31,7 +32,7 @@ constexpr int kGridW = 28;
 constexpr int kGridH = 56;
 constexpr int kT = kGridW * kGridH;    // 1568
 constexpr int kNumKB = kT / kKB;       // 14
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 constexpr int kThreads = 128 + kWG * 128;  // 384
 constexpr int kRegsControl = 40;
 constexpr int kRegsSoftmax = 232;  // 128*40 + 256*232 = 64512 <= 65536
@@ -40,24 +41,28 @@ constexpr int kRelRows = 176;  // 112 (reversed rel_pos_h, 111 used) + 64 (rever
 constexpr int kQBytes = kQTile * 128;        // 16384 per warpgroup
 constexpr int kKBytes = kKB * 128;           // 14336
 constexpr int kVBytes = 2 * 64 * 128;        // 16384 (two 64-key halves)
-constexpr int kPBytes = 2 * kQTile * 128;    // 32768 per warpgroup (two 64-key atoms; second uses 48 keys)
-constexpr int kRelBytes = kRelRows * 128;    // 22528 (lives in warpgroup 0's P buffer before the main loop)
+constexpr int kRelBytes = kRelRows * 128;    // 22528
 constexpr int kBhStride = 57;                // fp32 words per row (odd -> conflict free)
 constexpr int kBhBytes = kQTile * kBhStride * 4;
+constexpr int kBwStride = 29;
+constexpr int kBwBytes = kQTile * kBwStride * 4;   // staging of the per-query width bias (then kept in registers)
 
 constexpr int kOffQ = 0;
 constexpr int kOffK = kOffQ + kWG * kQBytes;
 constexpr int kOffV = kOffK + kStages * kKBytes;
-constexpr int kOffP = kOffV + kStages * kVBytes;
-constexpr int kOffBh = kOffP + kWG * kPBytes;
-constexpr int kOffBar = kOffBh + kWG * kBhBytes;
+constexpr int kOffBh = kOffV + kStages * kVBytes;
+constexpr int kOffRel = (kOffBh + kWG * kBhBytes + 1023) / 1024 * 1024;  // rel tables, then reused as bw staging
+constexpr int kRelRegion = (kWG * kBwBytes > kRelBytes) ? kWG * kBwBytes : kRelBytes;
+constexpr int kOffBar = kOffRel + kRelRegion;
 constexpr int kSmemBytes = kOffBar + 256 + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-// TMEM columns: warpgroup w owns [w*192, w*192+192): S at +0 (128), O at +128 (64); G (176) overlays both in the prologue
+// TMEM columns: warpgroup w owns [w*256, w*256+256): S at +0 (112 of 128), P at +128 (56 of 64, packed bf16 pairs),
+// O at +192 (64); G (176) overlays S and P in the prologue
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColsPerWG = 192;
-constexpr uint32_t kColO = 128;
+constexpr uint32_t kColsPerWG = 256;
+constexpr uint32_t kColP = 128;
+constexpr uint32_t kColO = 192;
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
@@ -73,19 +78,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint8_t* sQ = smem + kOffQ;
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
-  uint8_t* sP = smem + kOffP;
+  uint8_t* sRel = smem + kOffRel;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* g_full = bars + 1;
-  uint64_t* k_full = bars + 2;     // [2]
-  uint64_t* k_empty = bars + 4;    // [2]
-  uint64_t* v_full = bars + 6;     // [2]
-  uint64_t* v_empty = bars + 8;    // [2]
-  uint64_t* s_full = bars + 10;    // [kWG]  MMA -> softmax: S_j is in TMEM
-  uint64_t* s_free = bars + 12;    // [kWG]  softmax -> MMA: the S region may be overwritten
-  uint64_t* p_full = bars + 14;    // [kWG]  softmax -> MMA: P_j is in smem (and O rescaled if it had to be)
-  uint64_t* pv_done = bars + 16;   // [kWG]  MMA -> softmax: O += P_j V_j retired (P buffer free, O stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* k_full = bars + 2;     // [3]
+  uint64_t* k_empty = bars + 5;    // [3]
+  uint64_t* v_full = bars + 8;     // [3]
+  uint64_t* v_empty = bars + 11;   // [3]
+  uint64_t* s_full = bars + 14;    // [kWG]  MMA -> softmax: S_j is in TMEM
+  uint64_t* s_free = bars + 16;    // [kWG]  softmax -> MMA: the S region may be overwritten
+  uint64_t* p_full = bars + 18;    // [kWG]  softmax -> MMA: P_j is in TMEM (and O rescaled if it had to be)
+  uint64_t* pv_done = bars + 20;   // [kWG]  MMA -> softmax: O += P_j V_j retired (P region free, O stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,89 +129,92 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
-  if (warp == 0) {
-    // ============================ TMA producer ============================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, n_active * kQBytes + kRelBytes);
-      for (int w = 0; w < n_active; ++w) tma_load_3d(sQ + w * kQBytes, &tmap_q, q_full, 0, q0 + w * kQTile, sh);
-      tma_load_2d(sP, &tmap_rel, q_full, 0, 0);
-      auto load_k = [&](int kb) {
-        const int st = kb % kStages;
-        if (kb >= kStages) mbar_wait(&k_empty[st], ((kb / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], kKBytes);
-        tma_load_3d(sK + st * kKBytes, &tmap_k, &k_full[st], 0, kb * kKB, sh);
-      };
-      auto load_v = [&](int kb) {
-        const int st = kb % kStages;
-        if (kb >= kStages) mbar_wait(&v_empty[st], ((kb / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], kVBytes);
-        tma_load_3d(sV + st * kVBytes, &tmap_vt, &v_full[st], kb * kKB, 0, sh);
-        tma_load_3d(sV + st * kVBytes + 8192, &tmap_vt, &v_full[st], kb * kKB + 64, 0, sh);
-      };
-      // K stages free up one block earlier than V stages (S_{j+1} is issued before P_j V_j): keep K one ahead
-      load_k(0);
-      for (int kb = 0; kb < kNumKB; ++kb) {
-        if (kb + 1 < kNumKB) load_k(kb + 1);
-        load_v(kb);
+    if (warp == 0) {
+      // ============================ TMA producer ============================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, n_active * kQBytes + kRelBytes);
+        for (int w = 0; w < n_active; ++w) tma_load_3d(sQ + w * kQBytes, &tmap_q, q_full, 0, q0 + w * kQTile, sh);
+        tma_load_2d(sRel, &tmap_rel, q_full, 0, 0);
+        for (int kb = 0; kb < kNumKB; ++kb) {
+          const int st = kb % kStages;
+          if (kb >= kStages) mbar_wait(&k_empty[st], ((kb / kStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], kKBytes);
+          tma_load_3d(sK + st * kKBytes, &tmap_k, &k_full[st], 0, kb * kKB, sh);
+          if (kb >= kStages) mbar_wait(&v_empty[st], ((kb / kStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], kVBytes);
+          tma_load_3d(sV + st * kVBytes, &tmap_vt, &v_full[st], kb * kKB, 0, sh);
+          tma_load_3d(sV + st * kVBytes + 8192, &tmap_vt, &v_full[st], kb * kKB + 64, 0, sh);
+        }
       }
-    }
-  } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
+    } else if (warp == 1) {
+      // ============================ MMA issuer ============================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
+        constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+        const uint32_t q_addr = smem_u32(sQ);
+        const uint32_t rel_addr = smem_u32(sRel);
 
-      auto issue_s = [&](int kb) {  // S_w(kb) for every live warpgroup, then release the K stage
-        const int st = kb % kStages;
-        mbar_wait(&k_full[st], (kb / kStages) & 1);
-        const uint32_t k_addr = smem_u32(sK + st * kKBytes);
+        mbar_wait(q_full, 0);
+        tc_fence_after();
         for (int w = 0; w < n_active; ++w) {
-          mbar_wait(&s_free[w], kb & 1);
-          tc_fence_after();
-          const uint32_t d = tmem_base + w * kColsPerWG;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(d, umma_desc_sw128_kmajor(q_addr + w * kQBytes + k * 32),
-                         umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s, k != 0);
-          umma_commit(&s_full[w]);
+            umma_bf16_ss(tmem_base + w * kColsPerWG, umma_desc_sw128_kmajor(q_addr + w * kQBytes + k * 32),
+                         umma_desc_sw128_kmajor(rel_addr + k * 32), idesc_g, k != 0);
         }
-        umma_commit(&k_empty[st]);
-      };
+        umma_commit(g_full);
 
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      for (int w = 0; w < n_active; ++w) {
+        // Event-driven issue: per warpgroup the next S (needs the K block and a free S region) and the next P*V
+        // (needs the V block and P in TMEM) are issued as soon as their inputs are there, in whatever order the
+        // two warpgroups produce them.
+        int s_next[kWG] = {0, 0}, pv_next[kWG] = {0, 0};
+        if (n_active == 1) { s_next[1] = kNumKB; pv_next[1] = kNumKB; }
+        while (pv_next[0] < kNumKB || pv_next[1] < kNumKB) {
+          bool progressed = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_base + w * kColsPerWG, umma_desc_sw128_kmajor(q_addr + w * kQBytes + k * 32),
-                       umma_desc_sw128_kmajor(p_addr + k * 32), idesc_g, k != 0);
-      }
-      umma_commit(g_full);
-      issue_s(0);
-      for (int kb = 0; kb < kNumKB; ++kb) {
-        if (kb + 1 < kNumKB) issue_s(kb + 1);
-        const int st = kb % kStages;
-        mbar_wait(&v_full[st], (kb / kStages) & 1);
-        const uint32_t v_addr = smem_u32(sV + st * kVBytes);
-        for (int w = 0; w < n_active; ++w) {
-          mbar_wait(&p_full[w], kb & 1);
-          tc_fence_after();
-          const uint32_t d = tmem_base + w * kColsPerWG + kColO;
+          for (int w = 0; w < kWG; ++w) {
+            int kb = s_next[w];
+            if (kb < kNumKB) {
+              const int st = kb % kStages;
+              if (mbar_test(&k_full[st], (kb / kStages) & 1) && mbar_test(&s_free[w], kb & 1)) {
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sK + st * kKBytes);
+                const uint32_t d = tmem_base + w * kColsPerWG;
 #pragma unroll
-          for (int k = 0; k < kKB / 16; ++k) {
-            const uint32_t pa = p_addr + w * kPBytes + (k >> 2) * (kQTile * 128) + (k & 3) * 32;
-            const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
-            umma_bf16_ss(d, umma_desc_sw128_kmajor(pa), umma_desc_sw128_kmajor(va), idesc_o, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ss(d, umma_desc_sw128_kmajor(q_addr + w * kQBytes + k * 32),
+                               umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s, k != 0);
+                umma_commit(&s_full[w]);
+                s_next[w] = kb + 1;
+                progressed = true;
+                if (s_next[w ^ 1] > kb) umma_commit(&k_empty[st]);  // both warpgroups are past this K block
+              }
+            }
+            kb = pv_next[w];
+            if (kb < kNumKB) {
+              const int st = kb % kStages;
+              if (mbar_test(&v_full[st], (kb / kStages) & 1) && mbar_test(&p_full[w], kb & 1)) {
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sV + st * kVBytes);
+                const uint32_t d = tmem_base + w * kColsPerWG + kColO;
+                const uint32_t a = tmem_base + w * kColsPerWG + kColP;
+#pragma unroll
+                for (int k = 0; k < kKB / 16; ++k) {
+                  const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
+                  umma_bf16_ts(d, a + k * 8, umma_desc_sw128_kmajor(va), idesc_o, (kb | k) != 0);
+                }
+                umma_commit(&pv_done[w]);
+                pv_next[w] = kb + 1;
+                progressed = true;
+                if (pv_next[w ^ 1] > kb) umma_commit(&v_empty[st]);
+              }
+            }
           }
-          umma_commit(&pv_done[w]);
+          if (!progressed) __nanosleep(40);  // do not steal issue slots from the softmax warps on this scheduler
         }
-        umma_commit(&v_empty[st]);
       }
     }
-  }
   } else {
     // ============================ softmax warpgroups ============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
@@ -220,11 +228,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int qh = qi / kGridW, qw = qi % kGridW;
       const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * kColsPerWG;
       float* bh_row = reinterpret_cast<float*>(smem + kOffBh + w * kBhBytes) + r * kBhStride;
-      uint8_t* sPw = sP + w * kPBytes;
-      float* stage = reinterpret_cast<float*>(sPw + r * 128);  // this thread's own P row (atom 0)
+      float* stage = reinterpret_cast<float*>(sRel + w * kBwBytes) + r * kBwStride;
 
       // ---- prologue: decomposed rel-pos bias of this query, pre-multiplied by log2(e) ----
-      mbar_wait(g_full, 0);
+      mbar_wait(g_full, 0);  // both G MMAs have retired: the rel tables in smem are dead, G is in TMEM
       tc_fence_after();
       {
         const int off_h = 55 - qh;  // bh[kh] = G[off_h + kh]
@@ -263,13 +270,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const float sc = 0.125f * kLog2e;  // head_dim^-0.5 * log2(e)
 
       for (int kb = 0; kb < kNumKB; ++kb) {
-        mbar_wait(&s_full[w], kb & 1);
-        tc_fence_after();
-        float s[kKB];
         float bh4[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) bh4[i] = bh_row[kb * 4 + i];
+        mbar_wait(&s_full[w], kb & 1);
+        tc_fence_after();
         // t = s*scale*log2e + bw*log2e, streamed chunk by chunk behind the TMEM loads; block max of (t + bh*log2e)
+        float s[kKB];
         float gm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         tmem_ld16(lane_base, *reinterpret_cast<float(*)[16]>(&s[0]));
         tmem_ld_wait();
@@ -290,7 +297,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const float mx = fmaxf(fmaxf(gm[0] + bh4[0], gm[1] + bh4[1]), fmaxf(gm[2] + bh4[2], gm[3] + bh4[3]));
 
         if (kb > 0) {
-          // P buffer and O are ours again once the previous P*V has retired
+          // the P region and O are ours again once the previous P*V has retired
           mbar_wait(&pv_done[w], (kb - 1) & 1);
           tc_fence_after();
           const bool need = mx > m_run + kRescaleThreshold;
@@ -306,7 +313,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
               for (int i = 0; i < 16; ++i) v[i] *= alpha;
               tmem_st16(lane_base + kColO + c, v);
             }
-            tmem_st_wait();
             l_run *= alpha;
             m_run = m_new;
           }
@@ -314,29 +320,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           m_run = mx;
         }
 
-        // p = 2^(t + bh - m), row sum, bf16 P tile into 128B-swizzled smem
+        // p = 2^(t + bh - m), row sum, packed bf16 pairs into the P region of TMEM
         float lsum = 0.f;
         float og[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) og[i] = bh4[i] - m_run;
 #pragma unroll
-        for (int c = 0; c < kKB; c += 8) {
-          uint32_t pk[4];
+        for (int c = 0; c < kKB; c += 16) {
+          uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) {
+          for (int i = 0; i < 16; i += 2) {
             const int c0 = c + i, c1 = c + i + 1;
             const float p0 = ex2_approx(s[c0] + og[c0 / kGridW]);
             const float p1 = ex2_approx(s[c1] + og[c1 / kGridW]);
             lsum += p0 + p1;
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
-          const int atom = c >> 6;
-          const int ch = (c & 63) >> 3;
-          *reinterpret_cast<uint4*>(sPw + atom * (kQTile * 128) + r * 128 + ((ch ^ (r & 7)) << 4)) =
-              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          tmem_st8(lane_base + kColP + (c >> 1), pk);
         }
         l_run += lsum;
-        fence_proxy_async_smem();
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[w]);
