@@ -69,6 +69,7 @@ SIGNATURES = {
     "bseg_pack_conv_w9": (_i, [_vp, _vp, _vp]),
     "bseg_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "bseg_profile_enable": (_i, [_i]),
+    "bseg_profile_collect_gemm": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bseg_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(C.c_double),
                                   C.POINTER(C.c_double)]),
 }

@@ -497,6 +497,11 @@ int bseg_profile_collect(double* ms, long long* launches, double* work, double* 
   return 0;
 }
 
+int bseg_profile_collect_gemm(double* ms, double* work) {
+  prof_collect_sub(ms, work);
+  return 0;
+}
+
 int bseg_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
   return launch_f32_to_bf16(src, static_cast<__nv_bfloat16*>(dst), n, static_cast<cudaStream_t>(stream));
 }

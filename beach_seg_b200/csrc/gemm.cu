@@ -24,7 +24,8 @@ static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloa
   const long long tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * (N / BLOCK_N);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   ProfScope prof(CAT_GEMM, 2.0 * static_cast<double>(M) * N * K,
-                 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream);
+                 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream,
+                 MODE + (K > 2048 ? 8 : 0));
   kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -40,7 +40,8 @@ struct GemmEpiParams {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
-constexpr int GEMM_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each draining half of the tile's columns
+constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4.. epilogue
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -170,7 +171,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -231,6 +232,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    constexpr int kColsPerWarp = BLOCK_N / (GEMM_EPI_WARPS / 4);
+    const int col0 = ((warp - 4) >> 2) * kColsPerWarp;
     int as = 0;
     uint32_t aphase = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -241,7 +244,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const long long m = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();

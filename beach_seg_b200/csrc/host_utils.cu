@@ -61,16 +61,17 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 namespace {
-struct ProfRec { int cat; cudaEvent_t a, b; double work, bytes; };
+struct ProfRec { int cat; cudaEvent_t a, b; double work, bytes; int sub; };
+double g_sub_ms[16], g_sub_work[16];
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 std::mutex g_prof_mu;
 }  // namespace
 bool prof_enabled() { return g_prof_on; }
 void prof_set_enabled(bool on) { g_prof_on = on; }
-ProfScope::ProfScope(int cat, double work, double bytes, cudaStream_t stream) : idx_(-1), stream_(stream) {
+ProfScope::ProfScope(int cat, double work, double bytes, cudaStream_t stream, int sub) : idx_(-1), stream_(stream) {
   if (!g_prof_on) return;
-  ProfRec r{cat, nullptr, nullptr, work, bytes};
+  ProfRec r{cat, nullptr, nullptr, work, bytes, sub & 15};
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   cudaEventRecord(r.a, stream);
@@ -86,11 +87,13 @@ ProfScope::~ProfScope() {
 void prof_collect(double* ms, long long* launches, double* work, double* bytes) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0; launches[i] = 0; work[i] = 0; bytes[i] = 0; }
+  for (int i = 0; i < 16; ++i) { g_sub_ms[i] = 0; g_sub_work[i] = 0; }
   for (auto& r : g_prof) {
     cudaEventSynchronize(r.b);
     float t = 0.f;
     cudaEventElapsedTime(&t, r.a, r.b);
     ms[r.cat] += t;
+    if (r.cat == CAT_GEMM) { g_sub_ms[r.sub] += t; g_sub_work[r.sub] += r.work; }
     launches[r.cat] += 1;
     work[r.cat] += r.work;
     bytes[r.cat] += r.bytes;
@@ -98,6 +101,10 @@ void prof_collect(double* ms, long long* launches, double* work, double* bytes) 
     cudaEventDestroy(r.b);
   }
   g_prof.clear();
+}
+
+void prof_collect_sub(double* ms, double* work) {
+  for (int i = 0; i < 16; ++i) { ms[i] = g_sub_ms[i]; work[i] = g_sub_work[i]; }
 }
 
 int num_sms() {

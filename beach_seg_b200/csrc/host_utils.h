@@ -58,8 +58,9 @@ enum ProfCat : int {
 bool prof_enabled();
 void prof_set_enabled(bool on);
 void prof_collect(double* ms, long long* launches, double* work, double* bytes);  // arrays of CAT_COUNT
+void prof_collect_sub(double* ms, double* work);  // arrays of 16: the last collect()'s per-`sub` split (GEMM epilogue modes)
 struct ProfScope {
-  ProfScope(int cat, double work, double bytes, cudaStream_t stream);
+  ProfScope(int cat, double work, double bytes, cudaStream_t stream, int sub = 0);
   ~ProfScope();
   int idx_;
   cudaStream_t stream_;

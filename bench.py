@@ -258,7 +258,16 @@ def main():
     n = len(CATS)
     pms, pl, pw, pb = (C.c_double * n)(), (C.c_longlong * n)(), (C.c_double * n)(), (C.c_double * n)()
     L.bseg_profile_collect(pms, pl, pw, pb)
+    gms, gwk = (C.c_double * 16)(), (C.c_double * 16)()
+    L.bseg_profile_collect_gemm(gms, gwk)
     L.bseg_profile_enable(0)
+    gemm_modes = {}
+    names = {0: "bf16", 1: "lin1_gelu", 2: "proj_f32(ensemble)", 3: "proj_resid", 4: "qkv", 5: "patch_embed",
+             6: "dec_embed_pixshuf", 11: "lin2_resid", 14: "dec_embed_pixshuf"}
+    for i in range(16):
+        if gms[i] > 0:
+            gemm_modes[names.get(i, str(i))] = {"ms_per_step": gms[i] / args.steps,
+                                                "tflops": gwk[i] / (gms[i] * 1e-3) / 1e12}
     peaks = measured_peaks()
     kernels = {}
     tot_ms = sum(pms[i] for i in range(n))
@@ -297,7 +306,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": int(scene_host.numel() * 2),
                     "d2h_bytes_per_step": int(cls_host.numel()), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernels,
+            "kernels": kernels, "gemm_modes": gemm_modes,
             "model_tflops": value / world * FWD_FLOP_PER_TILE / 1e12,
             "model_frac_of_tensor_peak": value / world * FWD_FLOP_PER_TILE / 1e12 / peaks["tensor"],
         }

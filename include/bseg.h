@@ -165,6 +165,8 @@ int bseg_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 #define BSEG_PROFILE_CATEGORIES 9
 int bseg_profile_enable(int on);
 int bseg_profile_collect(double* ms, long long* launches, double* work, double* bytes);
+/* GEMM split of the last collect(): 16 entries indexed by epilogue mode (+8 when K > 2048). */
+int bseg_profile_collect_gemm(double* ms, double* work);
 
 /* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
 long long bseg_launch_count(void);
