@@ -34,9 +34,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// exact-erf GELU (HF ACT2FN["gelu"] == F.gelu(approximate="none"))
+// exact-erf GELU (HF ACT2FN["gelu"] == F.gelu(approximate="none")): x * Phi(x), Phi(x) = 0.5*(1 + erf(x/sqrt2)).
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): 1 - erf(z) = poly5(t) * exp(-z^2), t = 1/(1 + p z), z >= 0.
+// With h = 0.5*poly5(t)*exp(-x^2/2) = Phi(-|x|):  gelu(x) = x >= 0 ? x*(1-h) : x*h   (no cancellation in the tail).
+// 2 MUFU + 12 FMA-pipe instructions per element instead of libm erff.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float t, e;
+  const float ax = fabsf(x);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // exp(-x^2/2)
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(t, p, 0.5f * 1.421413741f);
+  p = fmaf(t, p, 0.5f * -0.284496736f);
+  p = fmaf(t, p, 0.5f * 0.254829592f);
+  const float h = p * t * e;
+  return x * (x >= 0.f ? 1.0f - h : h);
 }
 
 // ----------------------------------------------------------------------------------------------

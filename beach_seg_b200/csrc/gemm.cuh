@@ -49,9 +49,65 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transposing tile per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiStageBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 512 or 256
 };
+
+// ---- fp32-output epilogues (residual stream / embedding table / plain) ---------------------------------------
+// The accumulator arrives with thread <-> row (TMEM lane).  A row-per-thread global access touches 32 different
+// 128-byte lines per warp instruction, which makes the K=1024 GEMMs epilogue-bound on L1 wavefronts; so a 32x32
+// chunk is transposed through a per-warp swizzled smem tile and rows are then read / written by 8 adjacent lanes
+// (128 contiguous bytes per row, 4 rows per instruction).
+struct EpiRows {
+  float4 r[8];  // addend of rows (i*4 + lane/8), columns 4*(lane%8)..+3
+};
+template <int MODE>
+__device__ __forceinline__ void gemm_epi_f32_prefetch(const GemmEpiParams& ep, EpiRows& pr, long long row0, long long M,
+                                                      int n, int lane) {
+  if constexpr (MODE == EPI_RESID_F32 || MODE == EPI_EMBED) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long m = row0 + i * 4 + (lane >> 3);
+      if (m < M) {
+        const float* add;
+        if constexpr (MODE == EPI_RESID_F32) {
+          add = ep.resid + m * ep.ldr;
+        } else {
+          add = ep.tab + ((m / ep.rows_per_stream) * ep.T + m % ep.T) * ep.ldc;
+        }
+        pr.r[i] = *reinterpret_cast<const float4*>(add + n + 4 * (lane & 7));
+      }
+    }
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void gemm_epi_f32_chunk(const GemmEpiParams& ep, const float (&v)[32], const EpiRows& pr,
+                                                   float* stg, long long row0, long long M, int n, int lane) {
+  // 1) accumulator row of this thread -> smem (16-byte chunk index XOR row&7: conflict free both ways)
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  // 2) coalesced read-back, add, store
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (MODE != EPI_EMBED) {
+    if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4 * (lane & 7)));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    const long long m = row0 + rr;
+    float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+    o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+    if constexpr (MODE != EPI_F32) {
+      o.x += pr.r[i].x; o.y += pr.r[i].y; o.z += pr.r[i].z; o.w += pr.r[i].w;
+    }
+    if (m < M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + m * ep.ldc + n + 4 * (lane & 7)) = o;
+  }
+  __syncwarp();
+}
 
 template <int MODE>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, float (&v)[32], long long m, int n) {
@@ -76,24 +132,6 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, flo
       uint4 pk = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
                             pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
       *reinterpret_cast<uint4*>(dst + i) = pk;
-    }
-  } else if constexpr (MODE == EPI_F32 || MODE == EPI_RESID_F32 || MODE == EPI_EMBED) {
-    float* dst = reinterpret_cast<float*>(ep.out) + m * ep.ldc + n;
-    const float* add = nullptr;
-    if constexpr (MODE == EPI_RESID_F32) add = ep.resid + m * ep.ldr + n;
-    if constexpr (MODE == EPI_EMBED) {
-      long long stream = m / ep.rows_per_stream;
-      long long t = m % ep.T;
-      add = ep.tab + (stream * ep.T + t) * ep.ldc + n;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      if constexpr (MODE != EPI_F32) {
-        float4 r = *reinterpret_cast<const float4*>(add + i);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
-      *reinterpret_cast<float4*>(dst + i) = o;
     }
   } else if constexpr (MODE == EPI_QKV) {
     const int D = ep.heads * 64;
@@ -239,16 +277,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long m0 = (tile / num_n_tiles) * GEMM_BLOCK_M;
       const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
       const long long m = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+      if constexpr (MODE == EPI_F32 || MODE == EPI_RESID_F32 || MODE == EPI_EMBED) {
+        float* stg = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 1024;
+        const long long row0 = m0 + q * 32;
+        EpiRows pr, pn;
+        gemm_epi_f32_prefetch<MODE>(ep, pr, row0, M, n0 + col0, lane);  // does not depend on the accumulator
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
-        float v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        if (m < M) gemm_epilogue_chunk<MODE>(ep, v, m, n0 + c);
+        for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          if (c + 32 < col0 + kColsPerWarp) gemm_epi_f32_prefetch<MODE>(ep, pn, row0, M, n0 + c + 32, lane);
+          tmem_ld_wait();
+          gemm_epi_f32_chunk<MODE>(ep, v, pr, stg, row0, M, n0 + c, lane);
+          pr = pn;
+        }
+      } else {
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          if (m < M) gemm_epilogue_chunk<MODE>(ep, v, m, n0 + c);
+        }
       }
       tc_fence_before();
       __syncwarp();
