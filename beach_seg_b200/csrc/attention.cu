@@ -6,17 +6,22 @@
 //
 //   warp 0      TMA producer   (two 128-query Q tiles + rel tables once; 112-key K blocks and V^T blocks through
 //                               two independent 3-stage rings)
-//   warp 1      tcgen05 issuer (G = Q*Rel^T once per query tile; per key block S = Q*K^T (N=112) and
-//                               O += P*V (N=64, P read from TMEM); event driven: whichever warpgroup is ready)
-//   warps 2-3   idle (they complete the control warpgroup, which gives its registers away with setmaxnreg)
+//   warps 1-2   tcgen05 issuers, one per softmax warpgroup (G = Q*Rel^T once; per key block S = Q*K^T in two
+//                               column halves (N=64, N=48) and O += P*V (N=64, P read from TMEM))
+//   warp 3      idle (completes the control warpgroup, which gives its registers away with setmaxnreg)
 //   warps 4-7   softmax warpgroup 0 (query rows   0..127 of the tile; thread <-> row == TMEM lane)
 //   warps 8-11  softmax warpgroup 1 (query rows 128..255)
 //
-// Per key block a softmax thread streams its S row (112 fp32) from TMEM into registers once and frees the S buffer,
-// so the next S = Q*K^T overlaps the exponentials; P goes back to TMEM as packed bf16 (the A operand of P*V).
-// O accumulates in TMEM across key blocks and is only rescaled when the running row max grows by more than 2^8
-// (exact: a stale max merely changes the common scale of P and O).  Key blocks are 112 keys = 4 rows of the
-// 28-wide token grid, so a score column maps to (kh, kw) at compile time and 1568 = 14 * 112 needs no key masking.
+// Streaming softmax: a thread walks its S row in 16-column chunks straight out of TMEM and exponentiates them on the
+// fly against the running reference m (the row max seen in EARLIER blocks), so TMEM loads, FMAs and MUFU.EX2 of one
+// warp interleave instead of running in phases.  That is exact: a stale reference only changes the common scale of
+// P, l and O.  The reference is raised lazily (when a block exceeds it by 2^8) and O in TMEM is rescaled then; if a
+// half block exceeds it by 2^100 the half is redone against the new reference so that P cannot overflow.
+// Each S half is handed back to the tensor core as soon as it has been consumed, so the next block's Q*K^T
+// overlaps the current block's exponentials.  Key blocks are 112 keys = 4 rows of the 28-wide token grid: a score
+// column maps to (kh, kw) at compile time and 1568 = 14 * 112 needs no key masking.
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"
@@ -28,6 +33,7 @@ constexpr int kWG = 2;
 constexpr int kQTile = 128;            // queries per softmax warpgroup
 constexpr int kCtaQ = kWG * kQTile;    // 256
 constexpr int kKB = 112;               // keys per block
+constexpr int kHalfLo = 64;            // S columns [0,64) and [64,112) are produced / released separately
 constexpr int kGridW = 28;
 constexpr int kGridH = 56;
 constexpr int kT = kGridW * kGridH;    // 1568
@@ -65,8 +71,16 @@ constexpr uint32_t kColP = 128;
 constexpr uint32_t kColO = 192;
 
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr float kLazyThreshold = 8.0f;      // raise the reference when a block exceeds it by 2^8
+constexpr float kOverflowGuard = 100.0f;    // redo a half block whose scores exceed the reference by 2^100
 }  // namespace attn
+
+namespace {
+__device__ __forceinline__ uint32_t scale_bf16x2(uint32_t v, float a) {
+  const float lo = __uint_as_float(v << 16) * a, hi = __uint_as_float(v & 0xffff0000u) * a;
+  return pack_bf16x2(lo, hi);
+}
+}  // namespace
 
 __global__ void __launch_bounds__(attn::kThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -86,11 +100,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* k_empty = bars + 5;    // [3]
   uint64_t* v_full = bars + 8;     // [3]
   uint64_t* v_empty = bars + 11;   // [3]
-  uint64_t* s_full = bars + 14;    // [kWG]  MMA -> softmax: S_j is in TMEM
-  uint64_t* s_free = bars + 16;    // [kWG]  softmax -> MMA: the S region may be overwritten
-  uint64_t* p_full = bars + 18;    // [kWG]  softmax -> MMA: P_j is in TMEM (and O rescaled if it had to be)
-  uint64_t* pv_done = bars + 20;   // [kWG]  MMA -> softmax: O += P_j V_j retired (P region free, O stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* s_full = bars + 14;    // [kWG][2]  MMA -> softmax: half h of S_j is in TMEM
+  uint64_t* s_free = bars + 18;    // [kWG][2]  softmax -> MMA: half h of the S region may be overwritten
+  uint64_t* p_full = bars + 22;    // [kWG]     softmax -> MMA: P_j is in TMEM (and O rescaled if it had to be)
+  uint64_t* pv_done = bars + 24;   // [kWG]     MMA -> softmax: O += P_j V_j retired (P region free, O stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,16 +120,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_prefetch_desc(&tmap_vt);
     tma_prefetch_desc(&tmap_rel);
     mbar_init(q_full, 1);
-    mbar_init(g_full, 1);
+    mbar_init(g_full, n_active);         // one commit per MMA issuer
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], n_active);  // a stage is free once every live warpgroup's MMAs on it have retired
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], n_active);
     }
     for (int i = 0; i < kWG; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);   // one arrive per softmax warp
+      mbar_init(&s_full[2 * i], 1);
+      mbar_init(&s_full[2 * i + 1], 1);
+      mbar_init(&s_free[2 * i], 4);   // one arrive per softmax warp
+      mbar_init(&s_free[2 * i + 1], 4);
       mbar_init(&p_full[i], 4);
       mbar_init(&pv_done[i], 1);
     }
@@ -146,72 +162,61 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           tma_load_3d(sV + st * kVBytes + 8192, &tmap_vt, &v_full[st], kb * kKB + 64, 0, sh);
         }
       }
-    } else if (warp == 1) {
-      // ============================ MMA issuer ============================
+    } else if (warp - 1 < n_active) {
+      // ============================ MMA issuers: warp 1 -> warpgroup 0, warp 2 -> warpgroup 1 ============================
+      // One issuing thread per softmax warpgroup, blocking on that warpgroup's barriers in the order in which the
+      // warpgroup arrives on them (S_lo free, S_hi free, P full), so neither warpgroup ever waits for the other's turn.
       if (lane == 0) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
+        const int w = warp - 1;
+        constexpr uint32_t idesc_lo = umma_idesc_bf16(128, kHalfLo);
+        constexpr uint32_t idesc_hi = umma_idesc_bf16(128, kKB - kHalfLo);
         constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
-        const uint32_t q_addr = smem_u32(sQ);
+        const uint32_t q_addr = smem_u32(sQ) + w * kQBytes;
         const uint32_t rel_addr = smem_u32(sRel);
+        const uint32_t tm = tmem_base + w * kColsPerWG;
 
         mbar_wait(q_full, 0);
         tc_fence_after();
-        for (int w = 0; w < n_active; ++w) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + w * kColsPerWG, umma_desc_sw128_kmajor(q_addr + w * kQBytes + k * 32),
-                         umma_desc_sw128_kmajor(rel_addr + k * 32), idesc_g, k != 0);
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tm, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(rel_addr + k * 32),
+                       idesc_g, k != 0);
         umma_commit(g_full);
 
-        // Event-driven issue: per warpgroup the next S (needs the K block and a free S region) and the next P*V
-        // (needs the V block and P in TMEM) are issued as soon as their inputs are there, in whatever order the
-        // two warpgroups produce them.
-        int s_next[kWG] = {0, 0}, pv_next[kWG] = {0, 0};
-        if (n_active == 1) { s_next[1] = kNumKB; pv_next[1] = kNumKB; }
-        while (pv_next[0] < kNumKB || pv_next[1] < kNumKB) {
-          bool progressed = false;
+        auto issue_s = [&](int kb) {
+          const int st = kb % kStages;
+          mbar_wait(&k_full[st], (kb / kStages) & 1);
+          const uint32_t k_addr = smem_u32(sK + st * kKBytes);
 #pragma unroll
-          for (int w = 0; w < kWG; ++w) {
-            int kb = s_next[w];
-            if (kb < kNumKB) {
-              const int st = kb % kStages;
-              if (mbar_test(&k_full[st], (kb / kStages) & 1) && mbar_test(&s_free[w], kb & 1)) {
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(sK + st * kKBytes);
-                const uint32_t d = tmem_base + w * kColsPerWG;
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(&s_free[2 * w + half], kb & 1);
+            tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_ss(d, umma_desc_sw128_kmajor(q_addr + w * kQBytes + k * 32),
-                               umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s, k != 0);
-                umma_commit(&s_full[w]);
-                s_next[w] = kb + 1;
-                progressed = true;
-                if (s_next[w ^ 1] > kb) umma_commit(&k_empty[st]);  // both warpgroups are past this K block
-              }
-            }
-            kb = pv_next[w];
-            if (kb < kNumKB) {
-              const int st = kb % kStages;
-              if (mbar_test(&v_full[st], (kb / kStages) & 1) && mbar_test(&p_full[w], kb & 1)) {
-                tc_fence_after();
-                const uint32_t v_addr = smem_u32(sV + st * kVBytes);
-                const uint32_t d = tmem_base + w * kColsPerWG + kColO;
-                const uint32_t a = tmem_base + w * kColsPerWG + kColP;
-#pragma unroll
-                for (int k = 0; k < kKB / 16; ++k) {
-                  const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
-                  umma_bf16_ts(d, a + k * 8, umma_desc_sw128_kmajor(va), idesc_o, (kb | k) != 0);
-                }
-                umma_commit(&pv_done[w]);
-                pv_next[w] = kb + 1;
-                progressed = true;
-                if (pv_next[w ^ 1] > kb) umma_commit(&v_empty[st]);
-              }
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tm + half * kHalfLo, umma_desc_sw128_kmajor(q_addr + k * 32),
+                           umma_desc_sw128_kmajor(k_addr + half * (kHalfLo * 128) + k * 32),
+                           half ? idesc_hi : idesc_lo, k != 0);
+            umma_commit(&s_full[2 * w + half]);
           }
-          if (!progressed) __nanosleep(40);  // do not steal issue slots from the softmax warps on this scheduler
+          umma_commit(&k_empty[st]);
+        };
+
+        issue_s(0);
+        for (int kb = 0; kb < kNumKB; ++kb) {
+          if (kb + 1 < kNumKB) issue_s(kb + 1);
+          const int st = kb % kStages;
+          mbar_wait(&v_full[st], (kb / kStages) & 1);
+          mbar_wait(&p_full[w], kb & 1);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(sV + st * kVBytes);
+#pragma unroll
+          for (int k = 0; k < kKB / 16; ++k) {
+            const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
+            umma_bf16_ts(tm + kColO, tm + kColP + k * 8, umma_desc_sw128_kmajor(va), idesc_o, (kb | k) != 0);
+          }
+          umma_commit(&pv_done[w]);
+          umma_commit(&v_empty[st]);
         }
       }
     }
@@ -264,91 +269,149 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       for (int i = 0; i < kGridW; ++i) bw[i] = stage[i];
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[w]);  // G consumed: the S region is free for S_0
+      if (lane == 0) {  // G consumed: both halves of the S region are free for S_0
+        mbar_arrive(&s_free[2 * w]);
+        mbar_arrive(&s_free[2 * w + 1]);
+      }
 
-      float m_run = -INFINITY, l_run = 0.f;
       const float sc = 0.125f * kLog2e;  // head_dim^-0.5 * log2(e)
+      float m_run = 0.f, l_run = 0.f;
+      float alpha_pending = 1.0f;  // factor still to be applied to O (after the P*V that is in flight retires)
+      float bh4[4];
+      float og[4];
+      uint32_t pk[kKB / 2];  // P of the current block: bf16 pairs
 
-      for (int kb = 0; kb < kNumKB; ++kb) {
-        float bh4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) bh4[i] = bh_row[kb * 4 + i];
-        mbar_wait(&s_full[w], kb & 1);
-        tc_fence_after();
-        // t = s*scale*log2e + bw*log2e, streamed chunk by chunk behind the TMEM loads; block max of (t + bh*log2e)
-        float s[kKB];
-        float gm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        tmem_ld16(lane_base, *reinterpret_cast<float(*)[16]>(&s[0]));
+      // exponentiate columns [c0, c1) of the S row against the current reference; returns sum and max exponent
+      auto stream = [&](auto c0_tag, auto c1_tag, float& lsum, float& xmax) {
+        constexpr int c0 = decltype(c0_tag)::value, c1 = decltype(c1_tag)::value;
+        float bufa[16], bufb[16];
+        tmem_ld16(lane_base + c0, bufa);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < kKB; c += 16) {
-          if (c + 16 < kKB) tmem_ld16(lane_base + c + 16, *reinterpret_cast<float(*)[16]>(&s[c + 16]));
+        for (int c = c0; c < c1; c += 16) {
+          float(&cur)[16] = (((c - c0) >> 4) & 1) ? bufb : bufa;
+          float(&nxt)[16] = (((c - c0) >> 4) & 1) ? bufa : bufb;
+          if (c + 16 < c1) tmem_ld16(lane_base + c + 16, nxt);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = c + i;
-            s[col] = fmaf(s[col], sc, bw[col % kGridW]);
-            gm[col / kGridW] = fmaxf(gm[col / kGridW], s[col]);
+          for (int i = 0; i < 16; i += 2) {
+            const int col0 = c + i, col1 = c + i + 1;
+            const float x0 = fmaf(cur[i], sc, bw[col0 % kGridW]) + og[col0 / kGridW];
+            const float x1 = fmaf(cur[i + 1], sc, bw[col1 % kGridW]) + og[col1 / kGridW];
+            xmax = fmaxf(xmax, fmaxf(x0, x1));
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            lsum += p0 + p1;
+            pk[col0 >> 1] = pack_bf16x2(p0, p1);
           }
-          if (c + 16 < kKB) tmem_ld_wait();
+          if (c + 16 < c1) tmem_ld_wait();
+        }
+      };
+      using I0 = std::integral_constant<int, 0>;
+      using I64 = std::integral_constant<int, kHalfLo>;
+      using I112 = std::integral_constant<int, kKB>;
+
+      for (int kb = 0; kb < kNumKB; ++kb) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bh4[i] = bh_row[kb * 4 + i];
+
+        // ---------------- lower half: columns 0..63 ----------------
+        mbar_wait(&s_full[2 * w], kb & 1);
+        tc_fence_after();
+        if (kb == 0) {  // initial reference: row max over the first 16 keys
+          float v[16];
+          tmem_ld16(lane_base, v);
+          tmem_ld_wait();
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fmaf(v[i], sc, bw[i]));
+          m_run = mx + bh4[0];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) og[i] = bh4[i] - m_run;
+        float lsum = 0.f, xmax = -INFINITY;
+        stream(I0{}, I64{}, lsum, xmax);
+        if (__any_sync(0xffffffffu, xmax > kOverflowGuard)) {  // (practically never) redo against a safe reference
+          const float up = fmaxf(xmax, 0.f);
+          const float a = ex2_approx(-up);
+          m_run += up;
+          l_run *= a;
+          alpha_pending *= a;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) og[i] = bh4[i] - m_run;
+          lsum = 0.f;
+          xmax = -INFINITY;
+          stream(I0{}, I64{}, lsum, xmax);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[w]);  // S_kb is in registers: S_{kb+1} may be issued
-        const float mx = fmaxf(fmaxf(gm[0] + bh4[0], gm[1] + bh4[1]), fmaxf(gm[2] + bh4[2], gm[3] + bh4[3]));
+        if (lane == 0) mbar_arrive(&s_free[2 * w]);  // the next block's lower S half may be issued
 
+        // ---------------- upper half: columns 64..111 ----------------
+        mbar_wait(&s_full[2 * w + 1], kb & 1);
+        tc_fence_after();
+        float lsum_hi = 0.f, xmax_hi = -INFINITY;
+        stream(I64{}, I112{}, lsum_hi, xmax_hi);
+        if (__any_sync(0xffffffffu, xmax_hi > kOverflowGuard)) {
+          const float up = fmaxf(xmax_hi, 0.f);
+          const float a = ex2_approx(-up);
+          m_run += up;
+          l_run *= a;
+          alpha_pending *= a;
+          lsum *= a;
+          xmax -= up;
+#pragma unroll
+          for (int i = 0; i < kHalfLo / 2; ++i) pk[i] = scale_bf16x2(pk[i], a);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) og[i] = bh4[i] - m_run;
+          lsum_hi = 0.f;
+          xmax_hi = -INFINITY;
+          stream(I64{}, I112{}, lsum_hi, xmax_hi);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[2 * w + 1]);
+        lsum += lsum_hi;
+        xmax = fmaxf(xmax, xmax_hi);
+
+        // ---------------- hand P to the tensor core ----------------
         if (kb > 0) {
           // the P region and O are ours again once the previous P*V has retired
           mbar_wait(&pv_done[w], (kb - 1) & 1);
           tc_fence_after();
-          const bool need = mx > m_run + kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {
-            const float m_new = need ? mx : m_run;
-            const float alpha = need ? ex2_approx(m_run - m_new) : 1.0f;
+          if (__any_sync(0xffffffffu, alpha_pending != 1.0f)) {
 #pragma unroll
             for (int c = 0; c < 64; c += 16) {
               float v[16];
               tmem_ld16(lane_base + kColO + c, v);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= alpha;
+              for (int i = 0; i < 16; ++i) v[i] *= alpha_pending;
               tmem_st16(lane_base + kColO + c, v);
             }
-            l_run *= alpha;
-            m_run = m_new;
           }
-        } else {
-          m_run = mx;
         }
-
-        // p = 2^(t + bh - m), row sum, packed bf16 pairs into the P region of TMEM
-        float lsum = 0.f;
-        float og[4];
+        alpha_pending = 1.0f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) og[i] = bh4[i] - m_run;
-#pragma unroll
-        for (int c = 0; c < kKB; c += 16) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const int c0 = c + i, c1 = c + i + 1;
-            const float p0 = ex2_approx(s[c0] + og[c0 / kGridW]);
-            const float p1 = ex2_approx(s[c1] + og[c1 / kGridW]);
-            lsum += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-          tmem_st8(lane_base + kColP + (c >> 1), pk);
-        }
+        for (int c = 0; c < kKB / 2; c += 8)
+          tmem_st8(lane_base + kColP + c, *reinterpret_cast<uint32_t(*)[8]>(&pk[c]));
         l_run += lsum;
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[w]);
+
+        // lazily raise the reference for the following blocks
+        if (xmax > kLazyThreshold) {
+          const float a = ex2_approx(-xmax);
+          m_run += xmax;
+          l_run *= a;
+          alpha_pending = a;  // applied to O once this block's P*V has retired
+        }
       }
 
       // ---- epilogue: O / l -> bf16, token-major [seq, t, heads*64] ----
       mbar_wait(&pv_done[w], (kNumKB - 1) & 1);
       tc_fence_after();
-      const float inv = 1.0f / l_run;
+      const float inv = alpha_pending / l_run;
       __nv_bfloat16* dst = out + (static_cast<long long>(seq) * kT + qi) * (heads * 64) + head * 64;
 #pragma unroll
       for (int c = 0; c < 64; c += 16) {

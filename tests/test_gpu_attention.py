@@ -52,3 +52,24 @@ def test_attention_matches_oracle(dev, nseq, qscale, relscale):
         print("per-q-tile abs err:", per_tile.flatten()[:12].tolist())
     # P is rounded to bf16 before P*V (8 mantissa bits): ~4e-3 relative per element
     assert rel < 1e-2
+
+
+def test_attention_extreme_dynamic_range(dev):
+    """Scores that grow by far more than 2^100 between key blocks: exercises the lazy reference update, the O rescale
+    in TMEM and the overflow-guard redo of the streaming softmax (the result must stay finite and exact)."""
+    g = torch.Generator().manual_seed(77)
+    q = bf16r(torch.randn((1, 16, T, 64), generator=g) * 4.0)
+    k = bf16r(torch.randn((1, 16, T, 64), generator=g))
+    k[:, :, 500:900] *= 6.0
+    k[:, :, 900:] *= 14.0   # late keys dominate: every row has to raise its reference repeatedly
+    k = bf16r(k)
+    v = bf16r(torch.randn((1, 16, T, 64), generator=g))
+    rel_h = bf16r(torch.randn((111, 64), generator=g) * 0.2)
+    rel_w = bf16r(torch.randn((55, 64), generator=g) * 0.2)
+    want = attention_ref(q.reshape(-1, T, 64), k.reshape(-1, T, 64), v.reshape(-1, T, 64), rel_h, rel_w)
+    want = want.reshape(1, 16, T, 64).permute(0, 2, 1, 3).reshape(1, T, 1024)
+    got = run_attention(q.to(dev), k.to(dev), v.to(dev), rel_h.to(dev), rel_w.to(dev)).float().cpu()
+    assert torch.isfinite(got).all()
+    rel = ((got - want).norm() / want.norm()).item()
+    print(f"[attention extreme range] rel-L2={rel:.3e} max|err|={(got - want).abs().max().item():.3e}")
+    assert rel < 1e-2
