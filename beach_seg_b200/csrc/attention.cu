@@ -15,7 +15,7 @@
 // Streaming softmax: a thread walks its S row in 16-column chunks straight out of TMEM and exponentiates them on the
 // fly against the running reference m (the row max seen in EARLIER blocks), so TMEM loads, FMAs and MUFU.EX2 of one
 // warp interleave instead of running in phases.  That is exact: a stale reference only changes the common scale of
-// P, l and O.  The reference is raised lazily (when a block exceeds it by 2^8) and O in TMEM is rescaled then; if a
+// P, l and O.  The reference is raised lazily (when a block exceeds it by 2^16) and O in TMEM is rescaled then; if a
 // half block exceeds it by 2^100 the half is redone against the new reference so that P cannot overflow.
 // Each S half is handed back to the tensor core as soon as it has been consumed, so the next block's Q*K^T
 // overlaps the current block's exponentials.  Key blocks are 112 keys = 4 rows of the 28-wide token grid: a score
@@ -71,7 +71,7 @@ constexpr uint32_t kColP = 128;
 constexpr uint32_t kColO = 192;
 
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLazyThreshold = 8.0f;      // raise the reference when a block exceeds it by 2^8
+constexpr float kLazyThreshold = 16.0f;     // raise the reference when a block exceeds it by 2^16
 constexpr float kOverflowGuard = 100.0f;    // redo a half block whose scores exceed the reference by 2^100
 }  // namespace attn
 
@@ -316,14 +316,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // ---------------- lower half: columns 0..63 ----------------
         mbar_wait(&s_full[2 * w], kb & 1);
         tc_fence_after();
-        if (kb == 0) {  // initial reference: row max over the first 16 keys
-          float v[16];
-          tmem_ld16(lane_base, v);
-          tmem_ld_wait();
+        if (kb == 0) {  // initial reference: row max over the first 64 keys
           float mx = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fmaf(v[i], sc, bw[i]));
-          m_run = mx + bh4[0];
+          for (int c = 0; c < kHalfLo; c += 16) {
+            float v[16];
+            tmem_ld16(lane_base + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              mx = fmaxf(mx, fmaf(v[i], sc, bw[(c + i) % kGridW]) + bh4[(c + i) / kGridW]);
+          }
+          m_run = mx;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) og[i] = bh4[i] - m_run;
