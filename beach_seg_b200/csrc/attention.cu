@@ -281,19 +281,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       float og[4];
       uint32_t pk[kKB / 2];  // P of the current block: bf16 pairs
 
-      // exponentiate columns [c0, c1) of the S row against the current reference; returns sum and max exponent
-      auto stream = [&](auto c0_tag, auto c1_tag, float& lsum, float& xmax) {
-        constexpr int c0 = decltype(c0_tag)::value, c1 = decltype(c1_tag)::value;
-        float bufa[16], bufb[16];
-        tmem_ld16(lane_base + c0, bufa);
-        tmem_ld_wait();
+      // exponentiate columns [c0, c1) of the S row against the current reference; returns sum and max exponent.
+      // 32-column TMEM loads, the next one in flight while the current chunk is processed.
+      auto process = [&](const float* cur, int c, int n, float& lsum, float& xmax) {
 #pragma unroll
-        for (int c = c0; c < c1; c += 16) {
-          float(&cur)[16] = (((c - c0) >> 4) & 1) ? bufb : bufa;
-          float(&nxt)[16] = (((c - c0) >> 4) & 1) ? bufa : bufb;
-          if (c + 16 < c1) tmem_ld16(lane_base + c + 16, nxt);
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
+        for (int i = 0; i < 32; i += 2) {
+          if (i < n) {
             const int col0 = c + i, col1 = c + i + 1;
             const float x0 = fmaf(cur[i], sc, bw[col0 % kGridW]) + og[col0 / kGridW];
             const float x1 = fmaf(cur[i + 1], sc, bw[col1 % kGridW]) + og[col1 / kGridW];
@@ -302,8 +295,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             lsum += p0 + p1;
             pk[col0 >> 1] = pack_bf16x2(p0, p1);
           }
-          if (c + 16 < c1) tmem_ld_wait();
         }
+      };
+      auto stream = [&](auto c0_tag, auto c1_tag, float& lsum, float& xmax) {
+        constexpr int c0 = decltype(c0_tag)::value, c1 = decltype(c1_tag)::value;
+        static_assert(c1 - c0 == 64 || c1 - c0 == 48, "half sizes");
+        float bufa[32], bufb[32];
+        tmem_ld32(lane_base + c0, bufa);
+        tmem_ld_wait();
+        if constexpr (c1 - c0 == 64) {
+          tmem_ld32(lane_base + c0 + 32, bufb);
+        } else {
+          tmem_ld16(lane_base + c0 + 32, *reinterpret_cast<float(*)[16]>(&bufb[0]));
+        }
+        process(bufa, c0, 32, lsum, xmax);
+        tmem_ld_wait();
+        process(bufb, c0 + 32, c1 - c0 - 32, lsum, xmax);
       };
       using I0 = std::integral_constant<int, 0>;
       using I64 = std::integral_constant<int, kHalfLo>;

@@ -119,3 +119,37 @@ def test_full_model_vs_hf_and_golden(dev, golden_dir):
     assert flips.float().mean().item() < 0.01
     if fm.numel():
         assert fm.max().item() < 0.1  # only pixels whose logit sits on the decision boundary may flip
+
+
+def test_prompt_model_forward_matches_reference_pipeline(dev):
+    """PromptModel.forward (src/model.py:132-147) end to end: random palette from the global RNG, prompt gather,
+    colourise, SegGPT, palette decode -- against the oracle restatement driven by the HF module (default init)."""
+    from beach_seg_b200.config import BeachSegConfig
+    from beach_seg_b200.model import PromptModel
+
+    conf = BeachSegConfig(checkpoint="random-init:0")
+    pm_model = PromptModel(conf, device=dev)
+    prompt_img01 = synth.smooth_image(2, seed=50)            # prompt images in [0,1] (what get_crop returns)
+    prompt_cls = synth.blocky_mask(2, seed=51)
+
+    class DM:
+        prompt_imgs = [{"image": prompt_img01[i], "mask": prompt_cls[i][None], "crop_idx": i} for i in range(2)]
+
+    pm_model.create_trainable_params(DM)
+    px = synth.normalize(synth.smooth_image(1, seed=52))
+    batch = {"image": px.to(dev), "crop_idx": torch.tensor([1])}
+    torch.manual_seed(99)
+    got = pm_model(batch).cpu()
+
+    hf = make_reference_model(seed=0, stress=False)
+    torch.manual_seed(99)
+    pal, paln = glue_ref.create_palette(4, 1, train=True)
+    ppx = glue_ref.normalize(prompt_img01[1:2])
+    pmask = glue_ref.normalize(glue_ref.torch_apply_mask_rgb(pal, prompt_cls[1:2][:, None]))
+    with torch.no_grad():
+        pred = hf(pixel_values=px, prompt_pixel_values=ppx, prompt_masks=pmask, embedding_type="instance").pred_masks
+    want = glue_ref.process_pred_masks(pred, paln)
+    flips = (got != want).float().mean().item()
+    print(f"[PromptModel.forward] class-map flips vs reference pipeline: {flips * 100:.3f} %")
+    assert got.shape == (1, 448, 448) and got.dtype == torch.int64
+    assert flips < 0.02

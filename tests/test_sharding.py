@@ -1,0 +1,95 @@
+"""CPU: host logic of the multi-GPU path (tile sharding, canvas merge) with world_size-2 gloo, and the host mirrors of
+the reference's palette / config helpers."""
+import dataclasses
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from beach_seg_b200 import synth
+from beach_seg_b200.predict import create_palette, shard_tiles
+from oracle import glue_ref
+
+
+def test_shard_tiles_partitions_exactly():
+    for n in (0, 1, 7, 64, 162, 163):
+        for world in (1, 2, 4, 8):
+            parts = [list(shard_tiles(n, r, world)) for r in range(world)]
+            flat = [i for p in parts for i in p]
+            assert flat == list(range(n))                      # contiguous, ordered, no overlap, nothing lost
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= max(1, (n + world - 1) // world)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Hs, Ws, crop = 600, 1000, 256
+    boxes = synth.sliding_boxes(Hs, Ws, crop, 192)
+    rng = np.random.default_rng(0)
+    cls = rng.integers(0, 4, size=(len(boxes), crop, crop)).astype(np.uint8)
+    mine = shard_tiles(len(boxes), rank, world)
+    acc = glue_ref.AccumulatorRef((Hs, Ws))           # stands in for the per-rank device canvas (same byte layout)
+    for i in mine:
+        acc.update(tuple(int(v) for v in boxes[i]), np.eye(4, dtype=np.uint8)[cls[i]])
+    canvas = torch.from_numpy(acc.counter.view(np.uint32).reshape(Hs, Ws).astype(np.int64))
+    dist.reduce(canvas, dst=0, op=dist.ReduceOp.SUM)  # the one collective of a shared scene: add the u32 canvases
+    if rank == 0:
+        np.save(Path(out_dir) / "merged.npy", canvas.numpy().astype(np.uint32))
+    dist.destroy_process_group()
+
+
+def test_two_rank_canvas_merge_equals_single_process(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    merged = np.load(tmp_path / "merged.npy").view(np.uint8).reshape(600, 1000, 4)
+    Hs, Ws, crop = 600, 1000, 256
+    boxes = synth.sliding_boxes(Hs, Ws, crop, 192)
+    cls = np.random.default_rng(0).integers(0, 4, size=(len(boxes), crop, crop)).astype(np.uint8)
+    acc = glue_ref.AccumulatorRef((Hs, Ws))
+    for b, c in zip(boxes, cls):
+        acc.update(tuple(int(v) for v in b), np.eye(4, dtype=np.uint8)[c])
+    assert np.array_equal(merged, acc.counter)
+
+
+def test_create_palette_matches_reference_rng_stream():
+    """Drop-in: same torch.manual_seed -> same random palette as the reference's CPU path (src/model.py:215-231)."""
+    torch.manual_seed(42)
+    pal, paln = create_palette(4, 3, True, "cpu")
+    torch.manual_seed(42)
+    rpal, rpaln = glue_ref.create_palette(4, 3, train=True)
+    assert torch.equal(pal, rpal) and torch.equal(paln, rpaln)
+    pal, paln = create_palette(4, 2, False, "cpu")
+    rpal, rpaln = glue_ref.create_palette(4, 2, train=False)
+    assert torch.equal(pal.float(), rpal.float()) and torch.equal(paln, rpaln)
+
+
+def test_config_mirrors_reference_defaults():
+    ref_root = Path("/root/reference")
+    if not ref_root.exists():
+        pytest.skip("reference tree not present on this box")
+    sys.path.insert(0, str(ref_root))
+    from src.config import BeachSegConfig as RefConfig  # imports cleanly (PIL only)
+
+    from beach_seg_b200.config import BeachSegConfig
+
+    ref = {f.name: f.default for f in dataclasses.fields(RefConfig)}
+    ours = {f.name: f.default for f in dataclasses.fields(BeachSegConfig)}
+    assert set(ref) == set(ours)
+    for k, v in ref.items():
+        if k == "resample":
+            assert ours[k] == v.name
+        else:
+            assert ours[k] == v, k
