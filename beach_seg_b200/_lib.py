@@ -52,6 +52,17 @@ SIGNATURES = {
     "bseg_destroy": (_i, [_vp]),
     "bseg_workspace_bytes": (_sz, [_vp, _i]),
     "bseg_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "bseg_train_prepare": (_i, [_vp, _vp]),
+    "bseg_train_workspace_bytes": (_sz, [_vp, _i]),
+    "bseg_forward_train": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp]),
+    "bseg_backward_to_prompt": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
+    "bseg_attention_fwd_lse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "bseg_attention_bwd_scratch_bytes": (_sz, [_i]),
+    "bseg_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "bseg_layernorm1024_bwd": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _f, _vp]),
+    "bseg_gemm_bf16_dgelu": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp]),
+    "bseg_pack_conv_w9_dgrad": (_i, [_vp, _vp, _vp]),
+    "bseg_decoder_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "bseg_scene_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bseg_ingest_u16x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f3, _f3, _vp, _vp, _ll, _vp, _vp,
                                _vp]),

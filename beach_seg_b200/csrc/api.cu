@@ -20,6 +20,8 @@ constexpr int kDecN = 16384;
 struct LayerPack {
   __nv_bfloat16 *qkv_w, *proj_w, *lin1_w, *lin2_w, *relcat;
   float *qkv_b, *proj_b, *lin1_b, *lin2_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  // transposed copies ([in, out], the B operand of the dgrad GEMMs) and relcat^T; packed by bseg_train_prepare
+  __nv_bfloat16 *qkv_wt = nullptr, *proj_wt = nullptr, *lin1_wt = nullptr, *lin2_wt = nullptr, *relcat_t = nullptr;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -33,6 +35,20 @@ __global__ void pack_relcat_kernel(const float* __restrict__ rel_h, const float*
   if (i < 111) v = rel_h[(110 - i) * 64 + d];
   else if (i >= 112 && i < 167) v = rel_w[(54 - (i - 112)) * 64 + d];
   out[i * 64 + d] = __float2bfloat16_rn(v);
+}
+
+// relcat [176,64] -> relcat^T [64,192] (columns 176..191 zero): K-major B operand of the bias-gradient MMA
+__global__ void pack_relcat_t_kernel(const __nv_bfloat16* __restrict__ relcat, __nv_bfloat16* __restrict__ out) {
+  const int d = blockIdx.x, j = threadIdx.x;  // 64 x 192
+  out[d * 192 + j] = j < 176 ? relcat[j * 64 + d] : __float2bfloat16_rn(0.f);
+}
+
+// conv3x3 dgrad taps: w9b[tap'][ci][co] = w9[8 - tap'][co][ci]   (tap' = (2-ky)*3 + (2-kx): flipped kernel)
+__global__ void pack_conv_w9_dgrad_kernel(const __nv_bfloat16* __restrict__ w9, __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * 64 * 64) return;
+  const int co = idx & 63, ci = (idx >> 6) & 63, t = idx >> 12;
+  out[idx] = w9[((8 - t) * 64 + co) * 64 + ci];
 }
 
 // conv weight [out,in,3,3] -> [tap][out][in] bf16
@@ -97,6 +113,9 @@ struct bseg_handle {
   float* dec_embed_b = nullptr;
   __nv_bfloat16* conv_w9 = nullptr;
   float *conv_b = nullptr, *dec_ln_w = nullptr, *dec_ln_b = nullptr, *head_w = nullptr, *head_b = nullptr;
+  // training-only packs (bseg_train_prepare)
+  void* train_arena = nullptr;
+  __nv_bfloat16 *patch_wt = nullptr, *dec_embed_wt = nullptr, *conv_w9b = nullptr;
 };
 
 extern "C" {
@@ -108,6 +127,7 @@ long long bseg_launch_count(void) { return launch_count(); }
 int bseg_destroy(bseg_handle* h) {
   if (!h) return 0;
   if (h->arena) cudaFree(h->arena);
+  if (h->train_arena) cudaFree(h->train_arena);
   delete h;
   return 0;
 }
@@ -261,46 +281,94 @@ WsLayout ws_layout(int B) {
   L.total = off;
   return L;
 }
-}  // namespace
 
-size_t bseg_workspace_bytes(const bseg_handle* /*h*/, int batch) {
-  if (batch <= 0) return 0;
-  return ws_layout(batch).total;
+// Training workspace: forward transients + everything the backward needs (saved activations) + backward scratch.
+// Saved per layer (rows = 2*B*T for the two-stream layers, B*T afterwards): the fp32 residual stream after the
+// attention block (h_mid) and after the MLP (h_out), q / k / v^T / attention output (bf16), the MLP pre-activation z
+// (bf16) and the softmax log-sum-exp.  DESIGN.md section 3 has the byte counts.
+struct TrainLayer {
+  size_t h_mid, h_out, q, k, vt, att, z, lse;
+};
+struct TrainLayout {
+  // forward transients
+  size_t xn, mlp, inter;
+  // saved
+  size_t h_emb, dec;
+  std::vector<TrainLayer> layers;
+  // backward scratch
+  size_t dh, dhb, dxn, dz, datt, dot, qt, kt, v, dvec, bias, dqkv, dinter, ddec, dconv, dpatch;
+  size_t total;
+};
+TrainLayout train_layout(const bseg_handle* h, int B) {
+  TrainLayout L;
+  const size_t rows2 = 2ull * B * kT, rows1 = 1ull * B * kT;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  L.xn = carve(rows2 * kD * 2);
+  L.mlp = carve(rows2 * kMlp * 2);
+  L.inter = carve(rows1 * 4096 * 2);
+  L.h_emb = carve(rows2 * kD * 4);
+  L.dec = carve(rows1 * kDecN * 2);
+  L.layers.resize(h->num_layers);
+  for (int i = 0; i < h->num_layers; ++i) {
+    const size_t rows = (i <= h->merge_index) ? rows2 : rows1;
+    TrainLayer& t = L.layers[i];
+    t.h_mid = carve(rows * kD * 4);
+    t.h_out = carve(rows * kD * 4);
+    t.q = carve(rows * kD * 2);
+    t.k = carve(rows * kD * 2);
+    t.vt = carve(rows * kD * 2);
+    t.att = carve(rows * kD * 2);
+    t.z = carve(rows * kMlp * 2);
+    t.lse = carve(rows * BSEG_HEADS * 4);
+  }
+  L.dh = carve(rows1 * kD * 4);
+  L.dhb = carve(rows1 * kD * 2);
+  L.dxn = carve(rows1 * kD * 4);
+  L.dz = carve(rows1 * kMlp * 2);
+  L.datt = carve(rows1 * kD * 2);
+  L.dot = carve(rows1 * kD * 2);
+  L.qt = carve(rows1 * kD * 2);
+  L.kt = carve(rows1 * kD * 2);
+  L.v = carve(rows1 * kD * 2);
+  L.dvec = carve(rows1 * BSEG_HEADS * 4);
+  L.bias = carve(rows1 * BSEG_HEADS * 84 * 4);
+  L.dqkv = carve(rows1 * 3 * kD * 2);
+  L.dinter = carve(rows1 * 4096 * 4);
+  L.ddec = carve(rows1 * kDecN * 2);
+  L.dconv = carve(static_cast<size_t>(B) * 448 * 448 * 64 * 2);
+  L.dpatch = carve(rows1 * 768 * 4);
+  L.total = off;
+  return L;
 }
 
-int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
-                 const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
-                 size_t workspace_bytes, float* pred_masks, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BSEG_REQUIRE(h != nullptr, "bseg_forward: null handle");
-  BSEG_REQUIRE(batch > 0, "bseg_forward: batch=%d", batch);
-  BSEG_REQUIRE(embedding_type == 0 || embedding_type == 1,
-               "Embedding type should be either 'semantic' or 'instance', but got code %d", embedding_type);
-  BSEG_REQUIRE(ensemble_prompts >= 0 && (ensemble_prompts == 0 || batch % ensemble_prompts == 0),
-               "bseg_forward: batch=%d is not a multiple of ensemble_prompts=%d", batch, ensemble_prompts);
-  const WsLayout L = ws_layout(batch);
-  BSEG_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, "bseg_forward: workspace too small (%zu < %zu)",
-               workspace_bytes, L.total);
-  BSEG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "bseg_forward: workspace must be 256B aligned");
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  float* hbuf = reinterpret_cast<float*>(ws + L.h);
-  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws + L.xn);
-  __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws + L.att);
-  __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(ws + L.q);
-  __nv_bfloat16* k = reinterpret_cast<__nv_bfloat16*>(ws + L.k);
-  __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(ws + L.vt);
-  __nv_bfloat16* mlp = reinterpret_cast<__nv_bfloat16*>(ws + L.mlp);
-  __nv_bfloat16* inter = reinterpret_cast<__nv_bfloat16*>(ws + L.inter);
-  __nv_bfloat16* dec = reinterpret_cast<__nv_bfloat16*>(ws + L.dec);
-  const int B = batch;
-  int rc;
+// Pointers one forward pass works with.  Inference: one in-place residual stream and per-layer-reused buffers;
+// training: every buffer the backward needs lives in its own slot of the training workspace.
+struct FwdBufs {
+  float* h_emb;                    // embeddings output == input of layer 0
+  __nv_bfloat16 *xn, *mlp, *inter, *dec;
+  struct PerLayer {
+    float *h_mid, *h_out;
+    __nv_bfloat16 *q, *k, *vt, *att, *z;
+    float* lse;
+  };
+  std::vector<PerLayer> layers;
+};
 
+int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                 const float* prompt_masks, int B, int embedding_type, int P, const FwdBufs& fb, float* pred_masks,
+                 cudaStream_t stream) {
+  int rc;
   // ---- embeddings: patchify + GEMM (modeling_seggpt.py:713-737, 163-206) ----
-  __nv_bfloat16* a_patch = mlp;
+  __nv_bfloat16* a_patch = fb.mlp;
   if ((rc = launch_patchify(pixel_values, prompt_pixel_values, prompt_masks, nullptr, a_patch, B, stream))) return rc;
   {
     GemmEpiParams ep;
-    ep.out = hbuf;
+    ep.out = fb.h_emb;
     ep.ldc = kD;
     ep.tab = h->embed_tab[embedding_type == 0 ? 0 : 1];
     ep.rows_per_stream = B * kT;
@@ -309,65 +377,304 @@ int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_
   }
 
   // ---- encoder (modeling_seggpt.py:453-501) ----
-  const int P = ensemble_prompts;
+  float* h_in = fb.h_emb;
   for (int i = 0; i < h->num_layers; ++i) {
     const LayerPack& lp = h->layers[i];
+    const FwdBufs::PerLayer& pl = fb.layers[i];
     const int nstreams = (i <= h->merge_index) ? 2 : 1;
     const int nseq = nstreams * B;
     const long long M = static_cast<long long>(nseq) * kT;
-    if ((rc = launch_layernorm1024(hbuf, kD, lp.ln1_w, lp.ln1_b, xn, kD, M, h->eps, stream))) return rc;
+    if ((rc = launch_layernorm1024(h_in, kD, lp.ln1_w, lp.ln1_b, fb.xn, kD, M, h->eps, stream))) return rc;
     {
       GemmEpiParams ep;
       ep.bias = lp.qkv_b;
-      ep.q = q; ep.k = k; ep.vt = vt;
+      ep.q = pl.q; ep.k = pl.k; ep.vt = pl.vt;
       ep.T = kT; ep.heads = BSEG_HEADS;
-      if ((rc = launch_gemm(EPI_QKV, xn, kD, lp.qkv_w, M, 3 * kD, kD, ep, stream))) return rc;
+      if ((rc = launch_gemm(EPI_QKV, fb.xn, kD, lp.qkv_w, M, 3 * kD, kD, ep, stream))) return rc;
     }
-    if ((rc = launch_attention(q, k, vt, lp.relcat, att, nseq, BSEG_HEADS, 56, 28, stream))) return rc;
+    if ((rc = launch_attention(pl.q, pl.k, pl.vt, lp.relcat, pl.att, pl.lse, nseq, BSEG_HEADS, 56, 28, stream)))
+      return rc;
     bool ens = false;
     if (P > 0) ens = (i == h->merge_index) ? true : (P >= 2);
     if (!ens) {
       GemmEpiParams ep;
-      ep.out = hbuf; ep.ldc = kD; ep.bias = lp.proj_b; ep.resid = hbuf; ep.ldr = kD;
-      if ((rc = launch_gemm(EPI_RESID_F32, att, kD, lp.proj_w, M, kD, kD, ep, stream))) return rc;
+      ep.out = pl.h_mid; ep.ldc = kD; ep.bias = lp.proj_b; ep.resid = h_in; ep.ldr = kD;
+      if ((rc = launch_gemm(EPI_RESID_F32, pl.att, kD, lp.proj_w, M, kD, kD, ep, stream))) return rc;
     } else {
-      float* tmp = reinterpret_cast<float*>(mlp);
+      BSEG_REQUIRE(pl.h_mid == h_in, "feature ensemble is an inference-only path");
+      float* tmp = reinterpret_cast<float*>(fb.mlp);
       GemmEpiParams ep;
       ep.out = tmp; ep.ldc = kD; ep.bias = lp.proj_b;
-      if ((rc = launch_gemm(EPI_F32, att, kD, lp.proj_w, M, kD, kD, ep, stream))) return rc;
-      if ((rc = launch_ensemble_residual(hbuf, tmp, nstreams, B / P, P, i == h->merge_index ? 1 : 0, kT, kD, stream)))
+      if ((rc = launch_gemm(EPI_F32, pl.att, kD, lp.proj_w, M, kD, kD, ep, stream))) return rc;
+      if ((rc = launch_ensemble_residual(h_in, tmp, nstreams, B / P, P, i == h->merge_index ? 1 : 0, kT, kD, stream)))
         return rc;
     }
-    if ((rc = launch_layernorm1024(hbuf, kD, lp.ln2_w, lp.ln2_b, xn, kD, M, h->eps, stream))) return rc;
+    if ((rc = launch_layernorm1024(pl.h_mid, kD, lp.ln2_w, lp.ln2_b, fb.xn, kD, M, h->eps, stream))) return rc;
     {
       GemmEpiParams ep;
-      ep.out = mlp; ep.ldc = kMlp; ep.bias = lp.lin1_b;
-      if ((rc = launch_gemm(EPI_BF16_GELU, xn, kD, lp.lin1_w, M, kMlp, kD, ep, stream))) return rc;
+      ep.out = fb.mlp; ep.ldc = kMlp; ep.bias = lp.lin1_b; ep.aux = pl.z;
+      if ((rc = launch_gemm(EPI_BF16_GELU, fb.xn, kD, lp.lin1_w, M, kMlp, kD, ep, stream))) return rc;
     }
     {
       GemmEpiParams ep;
-      ep.out = hbuf; ep.ldc = kD; ep.bias = lp.lin2_b; ep.resid = hbuf; ep.ldr = kD;
-      if ((rc = launch_gemm(EPI_RESID_F32, mlp, kMlp, lp.lin2_w, M, kD, kMlp, ep, stream))) return rc;
+      ep.out = pl.h_out; ep.ldc = kD; ep.bias = lp.lin2_b; ep.resid = pl.h_mid; ep.ldr = kD;
+      if ((rc = launch_gemm(EPI_RESID_F32, fb.mlp, kMlp, lp.lin2_w, M, kD, kMlp, ep, stream))) return rc;
     }
     if (i == h->merge_index)
-      if ((rc = launch_merge_streams(hbuf, static_cast<long long>(B) * kT * kD, stream))) return rc;
+      if ((rc = launch_merge_streams(pl.h_out, static_cast<long long>(B) * kT * kD, stream))) return rc;
     for (int j = 0; j < 4; ++j)
       if (h->inter[j] == i)
-        if ((rc = launch_layernorm1024(hbuf, kD, h->enc_ln_w, h->enc_ln_b, inter + j * kD, 4 * kD,
+        if ((rc = launch_layernorm1024(pl.h_out, kD, h->enc_ln_w, h->enc_ln_b, fb.inter + j * kD, 4 * kD,
                                        static_cast<long long>(B) * kT, h->eps, stream)))
           return rc;
+    h_in = pl.h_out;
   }
 
   // ---- decoder (modeling_seggpt.py:555-585) ----
   {
     GemmEpiParams ep;
-    ep.out = dec; ep.bias = h->dec_embed_b; ep.T = kT; ep.grid_w = 28;
-    if ((rc = launch_gemm(EPI_PIXSHUF, inter, 4 * kD, h->dec_embed_w, static_cast<long long>(B) * kT, kDecN, 4 * kD,
+    ep.out = fb.dec; ep.bias = h->dec_embed_b; ep.T = kT; ep.grid_w = 28;
+    if ((rc = launch_gemm(EPI_PIXSHUF, fb.inter, 4 * kD, h->dec_embed_w, static_cast<long long>(B) * kT, kDecN, 4 * kD,
                           ep, stream)))
       return rc;
   }
-  return launch_decoder_head(dec, h->conv_w9, h->conv_b, h->dec_ln_w, h->dec_ln_b, h->head_w, h->head_b, pred_masks,
+  return launch_decoder_head(fb.dec, h->conv_w9, h->conv_b, h->dec_ln_w, h->dec_ln_b, h->head_w, h->head_b, pred_masks,
                              B, 896, 448, h->eps, stream);
+}
+
+int check_forward_args(bseg_handle* h, int batch, int embedding_type, const void* workspace, const char* who) {
+  BSEG_REQUIRE(h != nullptr, "%s: null handle", who);
+  BSEG_REQUIRE(batch > 0, "%s: batch=%d", who, batch);
+  BSEG_REQUIRE(embedding_type == 0 || embedding_type == 1,
+               "Embedding type should be either 'semantic' or 'instance', but got code %d", embedding_type);
+  BSEG_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "%s: workspace must be non-null and 256B aligned", who);
+  return 0;
+}
+
+FwdBufs train_bufs(bseg_handle* h, const TrainLayout& L, uint8_t* ws) {
+  FwdBufs fb;
+  auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(ws + o); };
+  auto fp = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
+  fb.h_emb = fp(L.h_emb);
+  fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
+  fb.layers.resize(h->num_layers);
+  for (int i = 0; i < h->num_layers; ++i) {
+    const TrainLayer& t = L.layers[i];
+    fb.layers[i] = {fp(t.h_mid), fp(t.h_out), bf(t.q), bf(t.k), bf(t.vt), bf(t.att), bf(t.z), fp(t.lse)};
+  }
+  return fb;
+}
+}  // namespace
+
+size_t bseg_workspace_bytes(const bseg_handle* /*h*/, int batch) {
+  if (batch <= 0) return 0;
+  return ws_layout(batch).total;
+}
+
+size_t bseg_train_workspace_bytes(const bseg_handle* h, int batch) {
+  if (h == nullptr || batch <= 0) return 0;
+  return train_layout(h, batch).total;
+}
+
+int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                 const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
+                 size_t workspace_bytes, float* pred_masks, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_forward_args(h, batch, embedding_type, workspace, "bseg_forward");
+  if (rc) return rc;
+  BSEG_REQUIRE(ensemble_prompts >= 0 && (ensemble_prompts == 0 || batch % ensemble_prompts == 0),
+               "bseg_forward: batch=%d is not a multiple of ensemble_prompts=%d", batch, ensemble_prompts);
+  const WsLayout L = ws_layout(batch);
+  BSEG_REQUIRE(workspace_bytes >= L.total, "bseg_forward: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(ws + o); };
+  FwdBufs fb;
+  fb.h_emb = reinterpret_cast<float*>(ws + L.h);
+  fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
+  fb.layers.assign(h->num_layers, {fb.h_emb, fb.h_emb, bf(L.q), bf(L.k), bf(L.vt), bf(L.att), nullptr, nullptr});
+  return forward_impl(h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, ensemble_prompts, fb,
+                      pred_masks, stream);
+}
+
+// ---- training: transposed weight packs, forward that keeps what the backward needs, backward to the prompt ----
+int bseg_train_prepare(bseg_handle* h, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BSEG_REQUIRE(h != nullptr, "bseg_train_prepare: null handle");
+  if (h->train_arena != nullptr) return 0;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  struct LOff { size_t qkv, proj, lin1, lin2, rel; };
+  std::vector<LOff> lo(h->num_layers);
+  for (int i = 0; i < h->num_layers; ++i) {
+    lo[i].qkv = carve(3072ull * 1024 * 2);
+    lo[i].proj = carve(1024ull * 1024 * 2);
+    lo[i].lin1 = carve(4096ull * 1024 * 2);
+    lo[i].lin2 = carve(4096ull * 1024 * 2);
+    lo[i].rel = carve(64 * 192 * 2);
+  }
+  const size_t o_patch = carve(768ull * 1024 * 2), o_dec = carve(16384ull * 4096 * 2), o_w9b = carve(9 * 64 * 64 * 2);
+  void* arena = nullptr;
+  BSEG_CHECK_CUDA(cudaMalloc(&arena, off));
+  uint8_t* base = static_cast<uint8_t*>(arena);
+  auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
+  int rc = 0;
+  // W [out, in] -> W^T [in, out]
+  auto tr = [&](const __nv_bfloat16* w, __nv_bfloat16* wt, int out, int in) {
+    if (!rc) rc = launch_transpose_bf16(w, wt, out, in, 1, 0, 0, in, out, stream);
+  };
+  for (int i = 0; i < h->num_layers && !rc; ++i) {
+    LayerPack& lp = h->layers[i];
+    lp.qkv_wt = bf(lo[i].qkv);   tr(lp.qkv_w, lp.qkv_wt, 3072, 1024);
+    lp.proj_wt = bf(lo[i].proj); tr(lp.proj_w, lp.proj_wt, 1024, 1024);
+    lp.lin1_wt = bf(lo[i].lin1); tr(lp.lin1_w, lp.lin1_wt, 4096, 1024);
+    lp.lin2_wt = bf(lo[i].lin2); tr(lp.lin2_w, lp.lin2_wt, 1024, 4096);
+    lp.relcat_t = bf(lo[i].rel);
+    pack_relcat_t_kernel<<<64, 192, 0, stream>>>(lp.relcat, lp.relcat_t);
+  }
+  h->patch_wt = bf(o_patch);   tr(h->patch_w, h->patch_wt, 1024, 768);
+  h->dec_embed_wt = bf(o_dec); tr(h->dec_embed_w, h->dec_embed_wt, 16384, 4096);
+  h->conv_w9b = bf(o_w9b);
+  pack_conv_w9_dgrad_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, stream>>>(h->conv_w9, h->conv_w9b);
+  if (!rc) {
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+      set_error("bseg_train_prepare: pack kernels failed: %s", cudaGetErrorString(ce));
+      rc = -static_cast<int>(ce);
+    }
+  }
+  if (rc) {
+    cudaFree(arena);
+    return rc;
+  }
+  h->train_arena = arena;
+  return 0;
+}
+
+int bseg_forward_train(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                       const float* prompt_masks, int batch, int embedding_type, void* workspace,
+                       size_t workspace_bytes, float* pred_masks, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_forward_args(h, batch, embedding_type, workspace, "bseg_forward_train");
+  if (rc) return rc;
+  const TrainLayout L = train_layout(h, batch);
+  BSEG_REQUIRE(workspace_bytes >= L.total, "bseg_forward_train: workspace too small (%zu < %zu)", workspace_bytes,
+               L.total);
+  const FwdBufs fb = train_bufs(h, L, static_cast<uint8_t*>(workspace));
+  return forward_impl(h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, 0, fb, pred_masks,
+                      stream);
+}
+
+namespace {
+// dq, dk, dv of one layer: operand transposes + the two attention-backward kernels
+int attention_backward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
+                       const __nv_bfloat16* att, const __nv_bfloat16* datt, const float* lse,
+                       const __nv_bfloat16* relcat, const __nv_bfloat16* relcat_t, __nv_bfloat16* dot,
+                       __nv_bfloat16* qt, __nv_bfloat16* kt, __nv_bfloat16* v, float* dvec, float* bias,
+                       __nv_bfloat16* dqkv, int nseq, cudaStream_t stream) {
+  int rc = launch_attn_bwd_prep(datt, att, q, k, vt, dot, dvec, qt, kt, v, nseq, BSEG_HEADS, kT, stream);
+  if (rc) return rc;
+  return launch_attention_bwd(q, k, v, qt, kt, datt, dot, lse, dvec, relcat, relcat_t, bias, dqkv, nseq, BSEG_HEADS,
+                              stream);
+}
+}  // namespace
+
+int bseg_backward_to_prompt(bseg_handle* h, const float* d_pred_masks, int batch, void* workspace,
+                            size_t workspace_bytes, float* d_prompt_pixel_values, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_forward_args(h, batch, 0, workspace, "bseg_backward_to_prompt");
+  if (rc) return rc;
+  BSEG_REQUIRE(h->train_arena != nullptr, "bseg_backward_to_prompt: call bseg_train_prepare first");
+  const TrainLayout L = train_layout(h, batch);
+  BSEG_REQUIRE(workspace_bytes >= L.total, "bseg_backward_to_prompt: workspace too small (%zu < %zu)", workspace_bytes,
+               L.total);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const FwdBufs fb = train_bufs(h, L, ws);
+  auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(ws + o); };
+  auto fp = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
+  float *dh = fp(L.dh), *dxn = fp(L.dxn), *dinter = fp(L.dinter), *dpatch = fp(L.dpatch);
+  __nv_bfloat16 *dhb = bf(L.dhb), *dz = bf(L.dz), *datt = bf(L.datt), *dqkv = bf(L.dqkv), *ddec = bf(L.ddec),
+                *dconv = bf(L.dconv);
+  const int B = batch;
+  const long long M = static_cast<long long>(B) * kT;
+  // the loss only sees the query half (src/model.py:48-57): d(pred_masks) is zero for image rows < 448, so the decoder
+  // backward touches image rows >= 447 only == token rows 27..55 == tokens [756, 1568) of every sample
+  const int kY0 = 448, kYFirst = 432, kTok0 = (kYFirst / 16) * 28, kToks = kT - kTok0;
+
+  // ---- decoder head (modeling_seggpt.py:546-552) and conv3x3 dgrad ----
+  if ((rc = launch_decoder_head_bwd(fb.dec, h->conv_w9, h->conv_b, h->dec_ln_w, h->dec_ln_b, h->head_w, h->head_b,
+                                    d_pred_masks, dconv, B, 896, 448, kY0, h->eps, stream)))
+    return rc;
+  if ((rc = launch_decoder_conv_dgrad(dconv, h->conv_w9b, ddec, B, 896, 448, kY0, kYFirst, stream))) return rc;
+  // ---- decoder_embed dgrad (pixel shuffle is the row layout of ddec) ----
+  {
+    GemmEpiParams ep;
+    ep.out = dinter; ep.ldc = 4 * kD;
+    GemmRows gr{kT, B, kTok0, kToks};
+    if ((rc = launch_gemm_rows(EPI_F32, ddec, kDecN, h->dec_embed_wt, gr, 4 * kD, kDecN, ep, stream))) return rc;
+  }
+  BSEG_CHECK_CUDA(cudaMemsetAsync(dh, 0, static_cast<size_t>(M) * kD * 4, stream));
+  BSEG_CHECK_CUDA(cudaMemsetAsync(dhb, 0, static_cast<size_t>(M) * kD * 2, stream));
+
+  // ---- encoder, last layer first ----
+  for (int i = h->num_layers - 1; i >= 0; --i) {
+    const LayerPack& lp = h->layers[i];
+    const FwdBufs::PerLayer& pl = fb.layers[i];
+    // the four intermediates went through encoder.layernorm (modeling_seggpt.py:481-482)
+    for (int j = 0; j < 4; ++j)
+      if (h->inter[j] == i)
+        if ((rc = launch_layernorm1024_bwd(pl.h_out, dinter + j * kD, 4 * kD, h->enc_ln_w, dh, dh, dhb, kT, B, kTok0,
+                                           kToks, h->eps, stream)))
+          return rc;
+    // merge (modeling_seggpt.py:476-479): the image stream receives half of the merged gradient
+    if (i == h->merge_index)
+      if ((rc = launch_scale_f32_bf16(dh, dh, dhb, 0.5f, M * kD, stream))) return rc;
+    // MLP: h_out = h_mid + lin2(gelu(lin1(LN2(h_mid))))
+    {
+      GemmEpiParams ep;
+      ep.out = dz; ep.ldc = kMlp; ep.aux = pl.z;
+      if ((rc = launch_gemm(EPI_DGELU, dhb, kD, lp.lin2_wt, M, kMlp, kD, ep, stream))) return rc;
+    }
+    {
+      GemmEpiParams ep;
+      ep.out = dxn; ep.ldc = kD;
+      if ((rc = launch_gemm(EPI_F32, dz, kMlp, lp.lin1_wt, M, kD, kMlp, ep, stream))) return rc;
+    }
+    if ((rc = launch_layernorm1024_bwd(pl.h_mid, dxn, kD, lp.ln2_w, dh, dh, dhb, M, 1, 0, static_cast<int>(M), h->eps,
+                                       stream)))
+      return rc;
+    // attention: h_mid = h_in + proj(attn(LN1(h_in)))
+    {
+      GemmEpiParams ep;
+      ep.out = datt; ep.ldc = kD;
+      if ((rc = launch_gemm(EPI_BF16, dhb, kD, lp.proj_wt, M, kD, kD, ep, stream))) return rc;
+    }
+    if ((rc = attention_backward(pl.q, pl.k, pl.vt, pl.att, datt, pl.lse, lp.relcat, lp.relcat_t, bf(L.dot), bf(L.qt),
+                                 bf(L.kt), bf(L.v), fp(L.dvec), fp(L.bias), dqkv, B, stream)))
+      return rc;
+    {
+      GemmEpiParams ep;
+      ep.out = dxn; ep.ldc = kD;
+      if ((rc = launch_gemm(EPI_F32, dqkv, 3 * kD, lp.qkv_wt, M, kD, 3 * kD, ep, stream))) return rc;
+    }
+    const float* h_in = (i == 0) ? fb.h_emb : fb.layers[i - 1].h_out;
+    if ((rc = launch_layernorm1024_bwd(h_in, dxn, kD, lp.ln1_w, dh, dh, dhb, M, 1, 0, static_cast<int>(M), h->eps,
+                                       stream)))
+      return rc;
+  }
+
+  // ---- patch embedding dgrad for the prompt half (token rows 0..27) and un-patchify ----
+  {
+    GemmEpiParams ep;
+    ep.out = dpatch; ep.ldc = 768;
+    GemmRows gr{kT, B, 0, kT / 2};
+    if ((rc = launch_gemm_rows(EPI_F32, dhb, kD, h->patch_wt, gr, 768, kD, ep, stream))) return rc;
+  }
+  return launch_unpatchify_prompt_grad(dpatch, d_prompt_pixel_values, B, stream);
 }
 
 int bseg_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, uint32_t* scratch,
@@ -459,8 +766,93 @@ int bseg_attention(const void* q, const void* k, const void* vt, const void* rel
                    void* stream) {
   return launch_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
                           static_cast<const __nv_bfloat16*>(vt), static_cast<const __nv_bfloat16*>(relcat),
-                          static_cast<__nv_bfloat16*>(out), nseq, BSEG_HEADS, 56, 28,
+                          static_cast<__nv_bfloat16*>(out), nullptr, nseq, BSEG_HEADS, 56, 28,
                           static_cast<cudaStream_t>(stream));
+}
+
+int bseg_attention_fwd_lse(const void* q, const void* k, const void* vt, const void* relcat, void* out, float* lse,
+                           int nseq, void* stream) {
+  return launch_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
+                          static_cast<const __nv_bfloat16*>(vt), static_cast<const __nv_bfloat16*>(relcat),
+                          static_cast<__nv_bfloat16*>(out), lse, nseq, BSEG_HEADS, 56, 28,
+                          static_cast<cudaStream_t>(stream));
+}
+
+size_t bseg_attention_bwd_scratch_bytes(int nseq) {
+  if (nseq <= 0) return 0;
+  const size_t rows = static_cast<size_t>(nseq) * kT;
+  // dOt, qt, kt, v (bf16), Dvec, bias table (fp32), relcat^T
+  return 4 * align_up(rows * kD * 2, 1024) + align_up(rows * BSEG_HEADS * 4, 1024) +
+         align_up(rows * BSEG_HEADS * 84 * 4, 1024) + align_up(64 * 192 * 2, 1024);
+}
+
+int bseg_attention_bwd(const void* q, const void* k, const void* vt, const void* out, const void* d_out,
+                       const float* lse, const void* relcat, void* dqkv, int nseq, void* scratch, size_t scratch_bytes,
+                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BSEG_REQUIRE(nseq > 0, "attention_bwd: nseq=%d", nseq);
+  BSEG_REQUIRE(scratch != nullptr && scratch_bytes >= bseg_attention_bwd_scratch_bytes(nseq) &&
+                   (reinterpret_cast<uintptr_t>(scratch) & 255) == 0,
+               "attention_bwd: scratch too small or misaligned");
+  const size_t rows = static_cast<size_t>(nseq) * kT;
+  uint8_t* p = static_cast<uint8_t*>(scratch);
+  auto take = [&](size_t bytes) {
+    uint8_t* r = p;
+    p += align_up(bytes, 1024);
+    return r;
+  };
+  auto* dot = reinterpret_cast<__nv_bfloat16*>(take(rows * kD * 2));
+  auto* qt = reinterpret_cast<__nv_bfloat16*>(take(rows * kD * 2));
+  auto* kt = reinterpret_cast<__nv_bfloat16*>(take(rows * kD * 2));
+  auto* v = reinterpret_cast<__nv_bfloat16*>(take(rows * kD * 2));
+  auto* dvec = reinterpret_cast<float*>(take(rows * BSEG_HEADS * 4));
+  auto* bias = reinterpret_cast<float*>(take(rows * BSEG_HEADS * 84 * 4));
+  auto* relt = reinterpret_cast<__nv_bfloat16*>(take(64 * 192 * 2));
+  pack_relcat_t_kernel<<<64, 192, 0, stream>>>(static_cast<const __nv_bfloat16*>(relcat), relt);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return attention_backward(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
+                            static_cast<const __nv_bfloat16*>(vt), static_cast<const __nv_bfloat16*>(out),
+                            static_cast<const __nv_bfloat16*>(d_out), lse, static_cast<const __nv_bfloat16*>(relcat),
+                            relt, dot, qt, kt, v, dvec, bias, static_cast<__nv_bfloat16*>(dqkv), nseq, stream);
+}
+
+int bseg_layernorm1024_bwd(const float* x, const float* dy, long long lddy, const float* gamma, const float* dh_in,
+                           float* dh_out, void* dh_bf16, long long M, float eps, void* stream) {
+  BSEG_REQUIRE(M > 0 && M < (1ll << 31), "layernorm_bwd: M=%lld", M);
+  return launch_layernorm1024_bwd(x, dy, lddy, gamma, dh_in, dh_out, static_cast<__nv_bfloat16*>(dh_bf16), M, 1, 0,
+                                  static_cast<int>(M), eps, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_gemm_bf16_dgelu(const void* A, long long lda, const void* W, long long M, int N, int K, const void* z,
+                         void* out, long long ldc, void* stream) {
+  GemmEpiParams ep;
+  ep.out = out;
+  ep.ldc = ldc;
+  ep.aux = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(z));
+  return launch_gemm(EPI_DGELU, static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), M, N,
+                     K, ep, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_pack_conv_w9_dgrad(const void* w9, void* w9b, void* stream) {
+  pack_conv_w9_dgrad_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(w9), static_cast<__nv_bfloat16*>(w9b));
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int bseg_decoder_head_bwd(const void* x_nhwc, const void* w9, const void* w9b, const float* conv_b, const float* ln_w,
+                          const float* ln_b, const float* head_w, const float* head_b, const float* d_pred,
+                          void* d_conv, void* d_dec_rows, int batch, int H, int W, int y0, float eps, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BSEG_REQUIRE(y0 >= 16 && y0 % 16 == 0, "decoder_head_bwd: y0=%d must be a positive multiple of 16", y0);
+  int rc = launch_decoder_head_bwd(static_cast<const __nv_bfloat16*>(x_nhwc), static_cast<const __nv_bfloat16*>(w9),
+                                   conv_b, ln_w, ln_b, head_w, head_b, d_pred, static_cast<__nv_bfloat16*>(d_conv),
+                                   batch, H, W, y0, eps, stream);
+  if (rc) return rc;
+  return launch_decoder_conv_dgrad(static_cast<const __nv_bfloat16*>(d_conv), static_cast<const __nv_bfloat16*>(w9b),
+                                   static_cast<__nv_bfloat16*>(d_dec_rows), batch, H, W, y0, y0 - 16, stream);
 }
 
 int bseg_pack_relcat(const float* rel_pos_h, const float* rel_pos_w, void* relcat, void* stream) {

@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t scale_bf16x2(uint32_t v, float a) {
 __global__ void __launch_bounds__(attn::kThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_vt, const __grid_constant__ CUtensorMap tmap_rel,
-                     __nv_bfloat16* __restrict__ out, int heads) {
+                     __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, int heads) {
   using namespace attn;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -423,6 +423,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_wait(&pv_done[w], (kNumKB - 1) & 1);
       tc_fence_after();
       const float inv = alpha_pending / l_run;
+      // log2-domain log-sum-exp of the row (saved for the backward pass): P = exp2(x - lse)
+      if (lse_out != nullptr && valid) lse_out[static_cast<long long>(sh) * kT + qi] = m_run + log2f(l_run);
       __nv_bfloat16* dst = out + (static_cast<long long>(seq) * kT + qi) * (heads * 64) + head * 64;
 #pragma unroll
       for (int c = 0; c < 64; c += 16) {
@@ -450,8 +452,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
-                     const __nv_bfloat16* relcat, __nv_bfloat16* out, int nseq, int heads, int grid_h, int grid_w,
-                     cudaStream_t stream) {
+                     const __nv_bfloat16* relcat, __nv_bfloat16* out, float* lse_out, int nseq, int heads, int grid_h,
+                     int grid_w, cudaStream_t stream) {
   using namespace attn;
   BSEG_REQUIRE(grid_h == kGridH && grid_w == kGridW, "attention: only the 56x28 token grid is supported (got %dx%d)",
                grid_h, grid_w);
@@ -488,7 +490,7 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
   dim3 grid((kT + kCtaQ - 1) / kCtaQ, heads, nseq);
   ProfScope prof(CAT_ATTENTION, static_cast<double>(nseq) * heads * (4.0 * kT * kT * 64 + 2.0 * kT * 84 * 64),
                  static_cast<double>(nseq) * heads * kT * 64 * 2 * 4, stream);
-  attention_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tr, out, heads);
+  attention_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tr, out, lse_out, heads);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -1,0 +1,737 @@
+// Backward of the fused SegGPT attention (forward: attention.cu; reference: torch autograd through
+// modeling_seggpt.py:268-348).  With S = scale*q.k + q.Rh[qh-kh] + q.Rw[qw-kw], P = softmax(S), O = P v:
+//     dP = dO v^T,   dS = P * (dP - D),  D = rowsum(dO * O),
+//     dv = P^T dO,   dk = scale * dS^T q,
+//     dq = scale * dS k  +  sum_kh dSh[q,kh] Rh[qh-kh]  +  sum_kw dSw[q,kw] Rw[qw-kw]
+// (dSh / dSw = dS summed over the key columns / key rows of the 56x28 token grid; the rel-pos tables are frozen).
+// Nothing of size T x T touches HBM.  Two kernels, both with S, dP and the accumulators in TMEM:
+//
+//   attention_bwd_dq_kernel   one CTA per (seq, head, 128 queries); thread <-> query row (as in the forward), loops
+//                             over 14 key blocks of 112 keys.  Also writes the per-query bias tables for the second
+//                             kernel.
+//   attention_bwd_dkv_kernel  one CTA per (seq, head, 128 keys); thread <-> key row (S^T = k q^T, so that P^T and dS^T
+//                             are TMEM A operands of dv += P^T dO and dk += dS^T q), loops over 25 query blocks of 64.
+//
+// Each CTA: warp 0 TMA producer, warp 1 tcgen05 issuer, warp 2 table loader (dkv) / idle, warp 3 idle, warps 4-11
+// elementwise (two warps per TMEM lane quarter, splitting the columns).  S / dP are double buffered in TMEM so that the
+// tensor core works on block j+1 while the elementwise warps are on block j.
+#include <type_traits>
+
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace bseg {
+
+namespace abwd {
+constexpr int kGridW = 28, kGridH = 56;
+constexpr int kT = kGridW * kGridH;  // 1568
+constexpr int kThreads = 384;
+constexpr int kRegsControl = 40, kRegsWork = 232;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kBiasRows = kGridH + kGridW;  // 84 rows of the per-(seq,head) bias table [84][T]: bh (56) then bw (28)
+
+// ---------------- dq kernel ----------------
+constexpr int kQTile = 128;
+constexpr int kKB = 112, kNumKB = kT / kKB;  // 14
+constexpr int kStagesQ = 3;
+constexpr int kRelRows = 176;
+constexpr int kQBytes = kQTile * 128;      // 16384
+constexpr int kKBytes = kKB * 128;         // 14336
+constexpr int kKtBytes = 2 * 64 * 128;     // 16384
+constexpr int kStageQBytes = 2 * kKBytes + kKtBytes;  // 45056
+constexpr int kRelRegion = 3 * 64 * 128;   // 24576: relcat [176 x 64] for G, then relcat^T [64 x 192] for the bias gradient
+constexpr int kDshStride = 57;
+constexpr int kDshBytes = kQTile * kDshStride * 4;
+constexpr int kQOffQ = 0;
+constexpr int kQOffdO = kQOffQ + kQBytes;
+constexpr int kQOffRel = kQOffdO + kQBytes;
+constexpr int kQOffRing = kQOffRel + kRelRegion;
+constexpr int kQOffDsh = kQOffRing + kStagesQ * kStageQBytes;
+constexpr int kQOffBar = kQOffDsh + kDshBytes;
+constexpr int kQSmemBytes = kQOffBar + 256 + 1024;
+static_assert(kQOffRing % 1024 == 0 && kStageQBytes % 1024 == 0 && kKBytes % 1024 == 0, "swizzle alignment");
+static_assert(kQSmemBytes <= 227 * 1024, "dq kernel shared memory");
+constexpr int kDswStride = 29;  // staging of the dSw partials in the (dead) ring after the loop
+// TMEM columns: S0 [0,112) dP0 [112,224) S1 [224,336) dP1 [336,448) dQ [448,512); G (176) and dG (88) overlay S0/dP0
+constexpr uint32_t kQColBuf = 224, kQColdP = 112, kQColdQ = 448;
+
+// ---------------- dkv kernel ----------------
+constexpr int kKTile = 128;
+constexpr int kQB = 64, kNumQB = (kT + kQB - 1) / kQB;  // 25 (the last block has 32 live queries)
+constexpr int kStagesK = 3;
+constexpr int kTileBytes = 64 * 128;       // 8192: [64 x 64] bf16
+constexpr int kTabStride = 68;             // floats per table row (64 + 4: LDS.128 rows land on distinct banks)
+constexpr int kBhRows = 6;                 // token rows a 128-key tile can touch
+constexpr int kTabBytes = (kBhRows + kGridW) * kTabStride * 4 + 2 * kQB * 4;  // bh, bw, lse, D
+constexpr int kStageKBytes = 4 * kTileBytes + ((kTabBytes + 1023) / 1024) * 1024;
+constexpr int kKOffK = 0;
+constexpr int kKOffV = kKOffK + kKTile * 128;
+constexpr int kKOffRing = kKOffV + kKTile * 128;
+constexpr int kKOffBar = kKOffRing + kStagesK * kStageKBytes;
+constexpr int kKSmemBytes = kKOffBar + 256 + 1024;
+static_assert(kKSmemBytes <= 227 * 1024, "dkv kernel shared memory");
+// TMEM columns: S0 [0,64) dP0 [64,128) S1 [128,192) dP1 [192,256) dV [256,320) dK [320,384)
+constexpr uint32_t kKColBuf = 128, kKColdP = 64, kKColdV = 256, kKColdK = 320;
+}  // namespace abwd
+
+namespace {
+__device__ __forceinline__ uint32_t tmem_lane_base(uint32_t tmem_base, int quarter) {
+  return tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+}
+}  // namespace
+
+// =====================================================================================================
+// dq
+// =====================================================================================================
+__global__ void __launch_bounds__(abwd::kThreads, 1)
+attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                        const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                        const __grid_constant__ CUtensorMap tmap_kt, const __grid_constant__ CUtensorMap tmap_rel,
+                        const __grid_constant__ CUtensorMap tmap_relt, const float* __restrict__ lse,
+                        const float* __restrict__ Dvec, float* bias_tab, __nv_bfloat16* __restrict__ dqkv, int heads) {
+  using namespace abwd;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + kQOffQ;
+  uint8_t* sdO = smem + kQOffdO;
+  uint8_t* sRel = smem + kQOffRel;
+  uint8_t* sRing = smem + kQOffRing;
+  float* sDsh = reinterpret_cast<float*>(smem + kQOffDsh);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kQOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* g_full = bars + 1;     // MMA -> all: G = Q rel^T is in TMEM, the rel region of smem is dead
+  uint64_t* g_free = bars + 2;     // elementwise -> MMA: G consumed, S/dP buffers may be written
+  uint64_t* relt_full = bars + 3;
+  uint64_t* k_full = bars + 4;     // [3]
+  uint64_t* kv_empty = bars + 7;   // [3]
+  uint64_t* sdp_full = bars + 10;  // [2]
+  uint64_t* ds_full = bars + 12;   // [2]
+  uint64_t* dq_done = bars + 14;   // all scale*dS*K MMAs retired
+  uint64_t* dg_full = bars + 15;   // elementwise -> MMA: dG is in TMEM
+  uint64_t* dq_final = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQTile;
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int sh = seq * heads + head;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_kt);
+    tma_prefetch_desc(&tmap_rel);
+    tma_prefetch_desc(&tmap_relt);
+    mbar_init(q_full, 1);
+    mbar_init(g_full, 1);
+    mbar_init(g_free, 8);
+    mbar_init(relt_full, 1);
+    for (int i = 0; i < kStagesQ; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&ds_full[i], 8);
+    }
+    mbar_init(dq_done, 1);
+    mbar_init(dg_full, 8);
+    mbar_init(dq_final, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
+    if (warp == 0) {
+      // ============================ TMA producer ============================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * kQBytes + kRelRows * 128);
+        tma_load_3d(sQ, &tmap_q, q_full, 0, q0, sh);
+        tma_load_4d(sdO, &tmap_do, q_full, 0, q0, head, seq);
+        tma_load_2d(sRel, &tmap_rel, q_full, 0, 0);
+        for (int kb = 0; kb < kNumKB; ++kb) {
+          const int st = kb % kStagesQ;
+          if (kb >= kStagesQ) mbar_wait(&kv_empty[st], ((kb / kStagesQ) & 1) ^ 1);
+          uint8_t* base = sRing + st * kStageQBytes;
+          mbar_arrive_expect_tx(&k_full[st], kStageQBytes);
+          tma_load_3d(base, &tmap_k, &k_full[st], 0, kb * kKB, sh);
+          tma_load_3d(base + kKBytes, &tmap_v, &k_full[st], 0, kb * kKB, sh);
+          tma_load_3d(base + 2 * kKBytes, &tmap_kt, &k_full[st], kb * kKB, 0, sh);
+          tma_load_3d(base + 2 * kKBytes + 8192, &tmap_kt, &k_full[st], kb * kKB + 64, 0, sh);
+          if (kb == kStagesQ - 1) {
+            // the rel region is free once G has been computed: bring in relcat^T for the bias-gradient MMA
+            mbar_wait(g_full, 0);
+            mbar_arrive_expect_tx(relt_full, kRelRegion);
+            for (int a = 0; a < 3; ++a) tma_load_2d(sRel + a * 8192, &tmap_relt, relt_full, a * 64, 0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ============================ MMA issuer ============================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
+        constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+        const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), rel_addr = smem_u32(sRel);
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(rel_addr + k * 32),
+                       idesc_g, k != 0);
+        umma_commit(g_full);
+
+        auto issue_sdp = [&](int kb) {
+          const int st = kb % kStagesQ;
+          mbar_wait(&k_full[st], (kb / kStagesQ) & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sRing + st * kStageQBytes), v_addr = k_addr + kKBytes;
+          const uint32_t d = tmem_base + (kb & 1) * kQColBuf;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s,
+                         k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d + kQColdP, umma_desc_sw128_kmajor(do_addr + k * 32),
+                         umma_desc_sw128_kmajor(v_addr + k * 32), idesc_s, k != 0);
+          umma_commit(&sdp_full[kb & 1]);
+        };
+
+        mbar_wait(g_free, 0);
+        tc_fence_after();
+        issue_sdp(0);
+        issue_sdp(1);
+        for (int kb = 0; kb < kNumKB; ++kb) {
+          const int st = kb % kStagesQ, buf = kb & 1;
+          mbar_wait(&ds_full[buf], (kb >> 1) & 1);
+          tc_fence_after();
+          const uint32_t kt_addr = smem_u32(sRing + st * kStageQBytes + 2 * kKBytes);
+          const uint32_t a_base = tmem_base + buf * kQColBuf;
+#pragma unroll
+          for (int k = 0; k < kKB / 16; ++k) {
+            // dS (bf16 pairs) of columns [0,64) sits at S columns [0,32), of columns [64,112) at S columns [64,88)
+            const uint32_t a = a_base + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
+            umma_bf16_ts(tmem_base + kQColdQ, a, umma_desc_sw128_kmajor(kt_addr + (k >> 2) * 8192 + (k & 3) * 32),
+                         idesc_o, (kb | k) != 0);
+          }
+          umma_commit(&kv_empty[st]);
+          if (kb + 2 < kNumKB) issue_sdp(kb + 2);
+        }
+        umma_commit(dq_done);
+        // bias gradient: dQ_acc += (8 * dG) relcat   (8 = 1/scale, exact in bf16)
+        mbar_wait(relt_full, 0);
+        mbar_wait(dg_full, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kRelRows / 16; ++k)
+          umma_bf16_ts(tmem_base + kQColdQ, tmem_base + k * 8,
+                       umma_desc_sw128_kmajor(rel_addr + (k >> 2) * 8192 + (k & 3) * 32), idesc_o, 1u);
+        umma_commit(dq_final);
+      }
+    }
+  } else {
+    // ============================ elementwise warps ============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsWork));
+    const int quarter = warp & 3;
+    const int g = (warp - 4) >> 2;  // column group: 0 -> key columns [0,64), 1 -> [64,112)
+    const int r = quarter * 32 + lane;
+    const int qi_raw = q0 + r;
+    const bool valid = qi_raw < kT;
+    const int qi = valid ? qi_raw : kT - 1;
+    const int qh = qi / kGridW, qw = qi % kGridW;
+    const uint32_t lane_base = tmem_lane_base(tmem_base, quarter);
+    float* tab = bias_tab + static_cast<long long>(sh) * kBiasRows * kT;
+    float* dsh_row = sDsh + r * kDshStride;
+
+    // ---- prologue: bias rows of this query (x log2 e); bw stays in registers, bh goes through the global table ----
+    mbar_wait(g_full, 0);
+    tc_fence_after();
+    float bw[kGridW];
+    {
+      const int off_h = 55 - qh;  // bh[kh] = G[off_h + kh]
+#pragma unroll
+      for (int c = 0; c < 112; c += 16) {
+        float v[16];
+        tmem_ld16(lane_base + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int kh = c + i - off_h;
+          if (kh >= 0 && kh < kGridH && valid) tab[kh * kT + qi] = v[i] * kLog2e;
+        }
+      }
+      const int off_w = 27 - qw;  // bw[kw] = G[112 + off_w + kw]
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) {
+        float v[16];
+        tmem_ld16(lane_base + 112 + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int kw = c + i - off_w;
+          if (kw >= 0 && kw < kGridW && valid) tab[(kGridH + kw) * kT + qi] = v[i] * kLog2e;
+        }
+      }
+      // both column groups of a row write the same values; every thread reads back what it wrote itself
+#pragma unroll
+      for (int kw = 0; kw < kGridW; ++kw) bw[kw] = valid ? tab[(kGridH + kw) * kT + qi] : 0.f;
+    }
+    if (g == 0)
+      for (int i = 0; i < kGridH; ++i) dsh_row[i] = 0.f;
+    const float lse_q = valid ? lse[static_cast<long long>(sh) * kT + qi] : 0.f;
+    const float d_q = valid ? Dvec[static_cast<long long>(sh) * kT + qi] : 0.f;
+    tc_fence_before();
+    named_bar_sync(1, 256);  // dsh rows zeroed, both groups' table rows written (each thread re-reads what it wrote)
+    if (lane == 0) mbar_arrive(g_free);
+
+    const float sc = 0.125f * kLog2e;
+    float dsw[kGridW];
+#pragma unroll
+    for (int i = 0; i < kGridW; ++i) dsw[i] = 0.f;
+
+    // one chunk of N columns starting at compile-time column C0: P = exp2(S*sc + bias - lse), dS = P * (dP - D)
+    auto chunk = [&](auto c0_tag, auto n_tag, uint32_t sbase, const float (&boff)[4], float (&acc4)[4]) {
+      constexpr int C0 = decltype(c0_tag)::value, N = decltype(n_tag)::value;
+      float s[32], dp[32];
+      if constexpr (N == 32) {
+        tmem_ld32(sbase + C0, s);
+        tmem_ld32(sbase + kQColdP + C0, dp);
+      } else {
+        tmem_ld16(sbase + C0, *reinterpret_cast<float(*)[16]>(&s[0]));
+        tmem_ld16(sbase + kQColdP + C0, *reinterpret_cast<float(*)[16]>(&dp[0]));
+      }
+      tmem_ld_wait();
+      uint32_t pk[N / 2];
+#pragma unroll
+      for (int i = 0; i < N; i += 2) {
+        const int c0 = C0 + i, c1 = C0 + i + 1;
+        const float x0 = fmaf(s[i], sc, bw[c0 % kGridW]) + boff[c0 / kGridW];
+        const float x1 = fmaf(s[i + 1], sc, bw[c1 % kGridW]) + boff[c1 / kGridW];
+        const float ds0 = ex2_approx(x0) * (dp[i] - d_q);
+        const float ds1 = ex2_approx(x1) * (dp[i + 1] - d_q);
+        dsw[c0 % kGridW] += ds0;
+        dsw[c1 % kGridW] += ds1;
+        acc4[c0 / kGridW] += ds0;
+        acc4[c1 / kGridW] += ds1;
+        pk[i >> 1] = pack_bf16x2(ds0, ds1);
+      }
+      // dS (bf16 pairs) in place over the S columns this thread has just consumed
+      if constexpr (N == 32) {
+        tmem_st16u(sbase + (C0 < 64 ? C0 / 2 : 64 + (C0 - 64) / 2), pk);
+      } else {
+        tmem_st8u(sbase + 64 + (C0 - 64) / 2, pk);
+      }
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I16 = std::integral_constant<int, 16>;
+    using I32 = std::integral_constant<int, 32>;
+    using I64 = std::integral_constant<int, 64>;
+    using I96 = std::integral_constant<int, 96>;
+
+    for (int kb = 0; kb < kNumKB; ++kb) {
+      const int buf = kb & 1;
+      float boff[4], acc4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) boff[i] = (valid ? tab[(kb * 4 + i) * kT + qi] : 0.f) - lse_q;
+      mbar_wait(&sdp_full[buf], (kb >> 1) & 1);
+      tc_fence_after();
+      const uint32_t sbase = lane_base + buf * kQColBuf;
+      if (g == 0) {
+        chunk(I0{}, I32{}, sbase, boff, acc4);
+        chunk(I32{}, I32{}, sbase, boff, acc4);
+        atomicAdd(&dsh_row[kb * 4 + 0], acc4[0]);
+        atomicAdd(&dsh_row[kb * 4 + 1], acc4[1]);
+        atomicAdd(&dsh_row[kb * 4 + 2], acc4[2]);
+      } else {
+        chunk(I64{}, I32{}, sbase, boff, acc4);
+        chunk(I96{}, I16{}, sbase, boff, acc4);
+        atomicAdd(&dsh_row[kb * 4 + 2], acc4[2]);
+        atomicAdd(&dsh_row[kb * 4 + 3], acc4[3]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[buf]);
+    }
+
+    // ---- bias gradient: dG[q, :] (176 columns) = dSh scattered at off_h + kh, dSw scattered at 112 + off_w + kw ----
+    mbar_wait(dq_done, 0);  // every MMA that read the S buffers / the ring has retired
+    tc_fence_after();
+    float* stage = reinterpret_cast<float*>(sRing) + (g * kQTile + r) * kDswStride;
+#pragma unroll
+    for (int i = 0; i < kGridW; ++i) stage[i] = dsw[i];
+    named_bar_sync(1, 256);
+    if (g == 0) {
+      // columns 0..111 -> packed words 0..55
+      const int off_h = 55 - qh;
+#pragma unroll 1
+      for (int w0 = 0; w0 < 56; w0 += 8) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ka = 2 * (w0 + j) - off_h, kb2 = ka + 1;
+          const float a = (ka >= 0 && ka < kGridH) ? dsh_row[ka] * 8.0f : 0.f;
+          const float b = (kb2 >= 0 && kb2 < kGridH) ? dsh_row[kb2] * 8.0f : 0.f;
+          pk[j] = pack_bf16x2(a, b);
+        }
+        tmem_st8u(lane_base + w0, pk);
+      }
+    } else {
+      // columns 112..175 -> packed words 56..87
+      const int off_w = 27 - qw;
+      const float* other = reinterpret_cast<const float*>(sRing) + r * kDswStride;  // group 0's partials
+#pragma unroll 1
+      for (int w0 = 0; w0 < 32; w0 += 8) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ka = 2 * (w0 + j) - off_w, kb2 = ka + 1;
+          const float a = (ka >= 0 && ka < kGridW) ? (stage[ka] + other[ka]) * 8.0f : 0.f;
+          const float b = (kb2 >= 0 && kb2 < kGridW) ? (stage[kb2] + other[kb2]) * 8.0f : 0.f;
+          pk[j] = pack_bf16x2(a, b);
+        }
+        tmem_st8u(lane_base + 56 + w0, pk);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(dg_full);
+
+    // ---- epilogue: dq = scale * accumulator -> bf16, token-major [seq*T + t][0*D + head*64 + d] ----
+    mbar_wait(dq_final, 0);
+    tc_fence_after();
+    {
+      float v[32];
+      tmem_ld32(lane_base + kQColdQ + g * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+        __nv_bfloat16* dst = dqkv + (static_cast<long long>(seq) * kT + qi) * (3 * heads * 64) + head * 64 + g * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(
+              pack_bf16x2(v[i] * 0.125f, v[i + 1] * 0.125f), pack_bf16x2(v[i + 2] * 0.125f, v[i + 3] * 0.125f),
+              pack_bf16x2(v[i + 4] * 0.125f, v[i + 5] * 0.125f), pack_bf16x2(v[i + 6] * 0.125f, v[i + 7] * 0.125f));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// =====================================================================================================
+// dk, dv
+// =====================================================================================================
+__global__ void __launch_bounds__(abwd::kThreads, 1)
+attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                         const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                         const __grid_constant__ CUtensorMap tmap_qt, const __grid_constant__ CUtensorMap tmap_dot,
+                         const float* __restrict__ lse, const float* __restrict__ Dvec,
+                         const float* __restrict__ bias_tab, __nv_bfloat16* __restrict__ dqkv, int heads) {
+  using namespace abwd;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem + kKOffK;
+  uint8_t* sV = smem + kKOffV;
+  uint8_t* sRing = smem + kKOffRing;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKOffBar);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* full = bars + 1;        // [3]  TMA bytes + 32 table-loader lanes
+  uint64_t* empty = bars + 4;       // [3]
+  uint64_t* sdp_full = bars + 7;    // [2]
+  uint64_t* pds_full = bars + 9;    // [2]
+  uint64_t* dkv_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * kKTile;
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int sh = seq * heads + head;
+  const int kh_lo = k0 / kGridW;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_qt);
+    tma_prefetch_desc(&tmap_dot);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < kStagesK; ++i) {
+      mbar_init(&full[i], 1 + 32);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&pds_full[i], 8);
+    }
+    mbar_init(dkv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    if (warp == 0) {
+      // ============================ TMA producer ============================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(kv_full, 2 * kKTile * 128);
+        tma_load_3d(sK, &tmap_k, kv_full, 0, k0, sh);
+        tma_load_3d(sV, &tmap_v, kv_full, 0, k0, sh);
+        for (int j = 0; j < kNumQB; ++j) {
+          const int st = j % kStagesK;
+          if (j >= kStagesK) mbar_wait(&empty[st], ((j / kStagesK) & 1) ^ 1);
+          uint8_t* base = sRing + st * kStageKBytes;
+          mbar_arrive_expect_tx(&full[st], 4 * kTileBytes);
+          tma_load_3d(base, &tmap_q, &full[st], 0, j * kQB, sh);
+          tma_load_4d(base + kTileBytes, &tmap_do, &full[st], 0, j * kQB, head, seq);
+          tma_load_3d(base + 2 * kTileBytes, &tmap_qt, &full[st], j * kQB, 0, sh);
+          tma_load_3d(base + 3 * kTileBytes, &tmap_dot, &full[st], j * kQB, 0, sh);
+        }
+      }
+    } else if (warp == 1) {
+      // ============================ MMA issuer ============================
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+        const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+        mbar_wait(kv_full, 0);
+        tc_fence_after();
+        auto issue_sdp = [&](int j) {
+          const int st = j % kStagesK;
+          mbar_wait(&full[st], (j / kStagesK) & 1);
+          tc_fence_after();
+          const uint32_t q_addr = smem_u32(sRing + st * kStageKBytes), do_addr = q_addr + kTileBytes;
+          const uint32_t d = tmem_base + (j & 1) * kKColBuf;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // S^T = K Q_blk^T
+            umma_bf16_ss(d, umma_desc_sw128_kmajor(k_addr + k * 32), umma_desc_sw128_kmajor(q_addr + k * 32), idesc,
+                         k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // dP^T = V dO_blk^T
+            umma_bf16_ss(d + kKColdP, umma_desc_sw128_kmajor(v_addr + k * 32),
+                         umma_desc_sw128_kmajor(do_addr + k * 32), idesc, k != 0);
+          umma_commit(&sdp_full[j & 1]);
+        };
+        issue_sdp(0);
+        issue_sdp(1);
+        for (int j = 0; j < kNumQB; ++j) {
+          const int st = j % kStagesK, buf = j & 1;
+          mbar_wait(&pds_full[buf], (j >> 1) & 1);
+          tc_fence_after();
+          const uint32_t qt_addr = smem_u32(sRing + st * kStageKBytes + 2 * kTileBytes);
+          const uint32_t dot_addr = qt_addr + kTileBytes;
+          const uint32_t a_base = tmem_base + buf * kKColBuf;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // P^T (bf16 pairs) of queries [0,32) at S columns [0,16), of queries [32,64) at S columns [32,48)
+            const uint32_t a_off = (k < 2 ? k * 8 : 32 + (k - 2) * 8);
+            umma_bf16_ts(tmem_base + kKColdV, a_base + a_off, umma_desc_sw128_kmajor(dot_addr + k * 32), idesc,
+                         (j | k) != 0);
+            umma_bf16_ts(tmem_base + kKColdK, a_base + kKColdP + a_off, umma_desc_sw128_kmajor(qt_addr + k * 32), idesc,
+                         (j | k) != 0);
+          }
+          umma_commit(&empty[st]);
+          if (j + 2 < kNumQB) issue_sdp(j + 2);
+        }
+        umma_commit(dkv_done);
+      }
+    } else if (warp == 2) {
+      // ============================ table loader ============================
+      // per query block: 6 bh rows + 28 bw rows of the bias table (x log2 e), lse and D of the 64 queries
+      const float* tab = bias_tab + static_cast<long long>(sh) * kBiasRows * kT;
+      for (int j = 0; j < kNumQB; ++j) {
+        const int st = j % kStagesK;
+        if (j >= kStagesK) mbar_wait(&empty[st], ((j / kStagesK) & 1) ^ 1);
+        float* dst = reinterpret_cast<float*>(sRing + st * kStageKBytes + 4 * kTileBytes);
+        const int q = j * kQB + 2 * lane;
+        const bool ok = q < kT;  // T is even: q and q+1 are valid together
+#pragma unroll 2
+        for (int row = 0; row < kBhRows + kGridW; ++row) {
+          int src_row = row < kBhRows ? kh_lo + row : kGridH + (row - kBhRows);
+          if (row < kBhRows && src_row >= kGridH) src_row = kGridH - 1;
+          float2 v = make_float2(0.f, 0.f);
+          if (ok) v = *reinterpret_cast<const float2*>(tab + src_row * kT + q);
+          *reinterpret_cast<float2*>(dst + row * kTabStride + 2 * lane) = v;
+        }
+        float2 l = make_float2(INFINITY, INFINITY), dd = make_float2(0.f, 0.f);
+        if (ok) {
+          l = *reinterpret_cast<const float2*>(lse + static_cast<long long>(sh) * kT + q);
+          dd = *reinterpret_cast<const float2*>(Dvec + static_cast<long long>(sh) * kT + q);
+        }
+        float* tail = dst + (kBhRows + kGridW) * kTabStride;
+        *reinterpret_cast<float2*>(tail + 2 * lane) = l;
+        *reinterpret_cast<float2*>(tail + kQB + 2 * lane) = dd;
+        mbar_arrive(&full[st]);
+      }
+    }
+  } else {
+    // ============================ elementwise warps ============================
+    const int quarter = warp & 3;
+    const int g = (warp - 4) >> 2;  // query columns [32g, 32g + 32) of the block
+    const int r = quarter * 32 + lane;
+    const int ki_raw = k0 + r;
+    const bool valid = ki_raw < kT;
+    const int ki = valid ? ki_raw : kT - 1;
+    const int khi = ki / kGridW - kh_lo, kw = ki % kGridW;
+    const uint32_t lane_base = tmem_lane_base(tmem_base, quarter);
+    const float sc = 0.125f * kLog2e;
+
+    for (int j = 0; j < kNumQB; ++j) {
+      const int st = j % kStagesK, buf = j & 1;
+      const float* tabs = reinterpret_cast<const float*>(sRing + st * kStageKBytes + 4 * kTileBytes);
+      const float* bh_row = tabs + khi * kTabStride + g * 32;
+      const float* bw_row = tabs + (kBhRows + kw) * kTabStride + g * 32;
+      const float* lse_s = tabs + (kBhRows + kGridW) * kTabStride + g * 32;
+      const float* d_s = lse_s + kQB;
+      mbar_wait(&full[st], (j / kStagesK) & 1);
+      mbar_wait(&sdp_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t sbase = lane_base + buf * kKColBuf;
+      float s[32], dp[32];
+      tmem_ld32(sbase + g * 32, s);
+      tmem_ld32(sbase + kKColdP + g * 32, dp);
+      tmem_ld_wait();
+      uint32_t pp[16], pd[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 bh4 = *reinterpret_cast<const float4*>(bh_row + i);
+        const float4 bw4 = *reinterpret_cast<const float4*>(bw_row + i);
+        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + i);
+        const float4 d4 = *reinterpret_cast<const float4*>(d_s + i);
+        const float p0 = ex2_approx(fmaf(s[i], sc, bw4.x) + (bh4.x - l4.x));
+        const float p1 = ex2_approx(fmaf(s[i + 1], sc, bw4.y) + (bh4.y - l4.y));
+        const float p2 = ex2_approx(fmaf(s[i + 2], sc, bw4.z) + (bh4.z - l4.z));
+        const float p3 = ex2_approx(fmaf(s[i + 3], sc, bw4.w) + (bh4.w - l4.w));
+        pp[i >> 1] = pack_bf16x2(p0, p1);
+        pp[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+        pd[i >> 1] = pack_bf16x2(p0 * (dp[i] - d4.x), p1 * (dp[i + 1] - d4.y));
+        pd[(i >> 1) + 1] = pack_bf16x2(p2 * (dp[i + 2] - d4.z), p3 * (dp[i + 3] - d4.w));
+      }
+      tmem_st16u(sbase + g * 32, pp);
+      tmem_st16u(sbase + kKColdP + g * 32, pd);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[buf]);
+    }
+
+    // ---- epilogue: dv -> columns [2D, 3D), dk * scale -> columns [D, 2D) of the token-major dqkv rows ----
+    mbar_wait(dkv_done, 0);
+    tc_fence_after();
+    const int D = heads * 64;
+    __nv_bfloat16* row = dqkv + (static_cast<long long>(seq) * kT + ki) * (3 * D) + head * 64 + g * 32;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      float v[32];
+      tmem_ld32(lane_base + (which == 0 ? kKColdV : kKColdK) + g * 32, v);
+      tmem_ld_wait();
+      const float a = which == 0 ? 1.0f : 0.125f;
+      if (valid) {
+        __nv_bfloat16* dst = row + (which == 0 ? 2 * D : D);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(dst + i) =
+              make_uint4(pack_bf16x2(v[i] * a, v[i + 1] * a), pack_bf16x2(v[i + 2] * a, v[i + 3] * a),
+                         pack_bf16x2(v[i + 4] * a, v[i + 5] * a), pack_bf16x2(v[i + 6] * a, v[i + 7] * a));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// =====================================================================================================
+// launcher
+// =====================================================================================================
+int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                         const __nv_bfloat16* qt, const __nv_bfloat16* kt, const __nv_bfloat16* dO,
+                         const __nv_bfloat16* dOt, const float* lse, const float* Dvec, const __nv_bfloat16* relcat,
+                         const __nv_bfloat16* relcat_t, float* bias_tab, __nv_bfloat16* dqkv, int nseq, int heads,
+                         cudaStream_t stream) {
+  using namespace abwd;
+  BSEG_REQUIRE(nseq > 0 && heads > 0, "attention_bwd: empty problem");
+  const uint64_t nsh = static_cast<uint64_t>(nseq) * heads;
+  const uint64_t D = static_cast<uint64_t>(heads) * 64;
+  CUtensorMap tq128, tq64, tk128, tk112, tv128, tv112, tkt, tqt, tdot, tdo128, tdo64, trel, trelt;
+  int rc;
+  {
+    uint64_t dims[3] = {64, static_cast<uint64_t>(kT), nsh};
+    uint64_t strides[2] = {128, static_cast<uint64_t>(kT) * 128};
+    uint32_t b128[3] = {64, 128, 1}, b112[3] = {64, kKB, 1}, b64[3] = {64, 64, 1};
+    if ((rc = make_tmap_bf16(&tq128, q, 3, dims, strides, b128))) return rc;
+    if ((rc = make_tmap_bf16(&tq64, q, 3, dims, strides, b64))) return rc;
+    if ((rc = make_tmap_bf16(&tk128, k, 3, dims, strides, b128))) return rc;
+    if ((rc = make_tmap_bf16(&tk112, k, 3, dims, strides, b112))) return rc;
+    if ((rc = make_tmap_bf16(&tv128, v, 3, dims, strides, b128))) return rc;
+    if ((rc = make_tmap_bf16(&tv112, v, 3, dims, strides, b112))) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(kT), 64, nsh};
+    uint64_t strides[2] = {static_cast<uint64_t>(kT) * 2, static_cast<uint64_t>(kT) * 128};
+    uint32_t box[3] = {64, 64, 1};
+    if ((rc = make_tmap_bf16(&tkt, kt, 3, dims, strides, box))) return rc;
+    if ((rc = make_tmap_bf16(&tqt, qt, 3, dims, strides, box))) return rc;
+    if ((rc = make_tmap_bf16(&tdot, dOt, 3, dims, strides, box))) return rc;
+  }
+  {
+    // dO is token-major [nseq*T, heads*64]: dims (d, t, head, seq)
+    uint64_t dims[4] = {64, static_cast<uint64_t>(kT), static_cast<uint64_t>(heads), static_cast<uint64_t>(nseq)};
+    uint64_t strides[3] = {D * 2, 128, static_cast<uint64_t>(kT) * D * 2};
+    uint32_t b128[4] = {64, 128, 1, 1}, b64[4] = {64, 64, 1, 1};
+    if ((rc = make_tmap_bf16(&tdo128, dO, 4, dims, strides, b128))) return rc;
+    if ((rc = make_tmap_bf16(&tdo64, dO, 4, dims, strides, b64))) return rc;
+  }
+  if ((rc = make_tmap_bf16_2d(&trel, relcat, 64, kRelRows, 64, 64, kRelRows))) return rc;
+  if ((rc = make_tmap_bf16_2d(&trelt, relcat_t, 192, 64, 192, 64, 64))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BSEG_CHECK_CUDA(
+        cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmemBytes));
+    BSEG_CHECK_CUDA(
+        cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKSmemBytes));
+    attr_set = true;
+  }
+  const double pair = static_cast<double>(nseq) * heads * kT * kT;
+  {
+    dim3 grid((kT + kQTile - 1) / kQTile, heads, nseq);
+    ProfScope prof(CAT_ATTENTION, pair * 64 * 2 * 3 + static_cast<double>(nseq) * heads * kT * 2.0 * 176 * 64 * 2,
+                   static_cast<double>(nseq) * heads * kT * (64 * 2 * 5 + kBiasRows * 4), stream);
+    attention_bwd_dq_kernel<<<grid, kThreads, kQSmemBytes, stream>>>(tq128, tdo128, tk112, tv112, tkt, trel, trelt, lse,
+                                                                     Dvec, bias_tab, dqkv, heads);
+    BSEG_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  {
+    dim3 grid((kT + kKTile - 1) / kKTile, heads, nseq);
+    ProfScope prof(CAT_ATTENTION, pair * 64 * 2 * 4, static_cast<double>(nseq) * heads * kT * (64 * 2 * 8), stream);
+    attention_bwd_dkv_kernel<<<grid, kThreads, kKSmemBytes, stream>>>(tk128, tv128, tq64, tdo64, tqt, tdot, lse, Dvec,
+                                                                      bias_tab, dqkv, heads);
+    BSEG_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return 0;
+}
+
+}  // namespace bseg

@@ -51,6 +51,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * (x >= 0.f ? 1.0f - h : h);
 }
 
+// d/dx of the exact-erf GELU: Phi(x) + x * phi(x), with the same erf approximation as gelu_erf
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  float t, e;
+  const float ax = fabsf(x);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // exp(-x^2/2)
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(t, p, 0.5f * 1.421413741f);
+  p = fmaf(t, p, 0.5f * -0.284496736f);
+  p = fmaf(t, p, 0.5f * 0.254829592f);
+  const float h = p * t * e;                       // Phi(-|x|)
+  const float cdf = x >= 0.f ? 1.0f - h : h;
+  return fmaf(x * 0.39894228040143267794f, e, cdf);  // Phi(x) + x * exp(-x^2/2) / sqrt(2 pi)
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
@@ -103,9 +118,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+    // ~2 s at 2 GHz for worker warps, twice that for the control warps 0-3 so that the workers report first
+    if (clock64() - t0 > (threadIdx.x < 128 ? 8000000000LL : 4000000000LL)) {
       printf("bseg: mbarrier watchdog block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+#ifdef BSEG_WATCHDOG_HOOK
+      BSEG_WATCHDOG_HOOK
+#endif
       __trap();
     }
   }
@@ -142,6 +161,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
         "r"(c2), "r"(c3)
       : "memory");
+}
+
+// named barrier among a subset of the CTA's warps (id 1..15; `count` threads, a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -233,6 +257,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                :
                : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])

@@ -12,6 +12,27 @@
 namespace bseg {
 
 namespace dconv {
+// epilogue variants of the same implicit-GEMM main loop
+enum : int {
+  kModeHead = 0,     // forward: + conv bias -> LN(C) -> GELU -> 1x1 head -> pred fp32 NCHW
+  kModeHeadBwd = 1,  // backward through head / GELU / LN (conv output recomputed): d(conv out) -> bf16 NHWC
+  kModeDgrad = 2,    // conv3x3 dgrad (flipped, transposed taps): d(conv in) -> bf16 rows of the decoder_embed dgrad operand
+};
+struct Params {
+  const float* conv_b;
+  const float* ln_w;
+  const float* ln_b;
+  const float* head_w;
+  const float* head_b;
+  float* pred;             // kModeHead: out [B,3,H,W]
+  const float* d_pred;     // kModeHeadBwd: in  [B,3,H,W]
+  __nv_bfloat16* out_bf16; // kModeHeadBwd: [B, H - y_out0, W, 64];  kModeDgrad: [B*T, 16384] (pixel-unshuffled)
+  int B, H, W;
+  int ty_begin;            // first tile row (in units of kTileH image rows) this launch computes
+  int y_in0;               // image row that coordinate 0 of the input tensor map corresponds to (rows above read as 0)
+  int y_out0;              // kModeHeadBwd: image row stored at row 0 of out_bf16
+  float eps;
+};
 constexpr int kTileW = 64, kTileH = 2;
 constexpr int kStages = 6;
 constexpr int kABytes = 128 * 128;       // 16384 per tap tile
@@ -25,12 +46,13 @@ constexpr int kSmemBytes = kOffPar + 400 * 4 + 1024;
 constexpr uint32_t kTmemCols = 128;
 }  // namespace dconv
 
+template <int MODE>
 __global__ void __launch_bounds__(dconv::kThreads, 1)
-decoder_head_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                    const float* __restrict__ conv_b, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                    const float* __restrict__ head_w, const float* __restrict__ head_b, float* __restrict__ pred,
-                    int B, int H, int W, float eps) {
+decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const dconv::Params prm) {
   using namespace dconv;
+  const int B = prm.B, H = prm.H, W = prm.W;
+  const float eps = prm.eps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem + kOffW;
@@ -45,16 +67,18 @@ decoder_head_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   float* sPar = reinterpret_cast<float*>(smem + kOffPar);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_x = W / kTileW, tiles_y = H / kTileH;
+  const int tiles_x = W / kTileW, tiles_y = H / kTileH - prm.ty_begin;
   const long long num_tiles = static_cast<long long>(B) * tiles_y * tiles_x;
 
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-    sPar[i] = conv_b[i];
-    sPar[64 + i] = ln_w[i];
-    sPar[128 + i] = ln_b[i];
+  if constexpr (MODE != kModeDgrad) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+      sPar[i] = prm.conv_b[i];
+      sPar[64 + i] = prm.ln_w[i];
+      sPar[128 + i] = prm.ln_b[i];
+    }
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) sPar[192 + i] = prm.head_w[i];
+    if (threadIdx.x < 3) sPar[384 + threadIdx.x] = prm.head_b[threadIdx.x];
   }
-  for (int i = threadIdx.x; i < 192; i += blockDim.x) sPar[192 + i] = head_w[i];
-  if (threadIdx.x < 3) sPar[384 + threadIdx.x] = head_b[threadIdx.x];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -84,13 +108,13 @@ decoder_head_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tx = static_cast<int>(tile % tiles_x);
-        const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+        const int ty = static_cast<int>((tile / tiles_x) % tiles_y) + prm.ty_begin;
         const int b = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], kABytes);
           tma_load_4d(sA + stage * kABytes, &tmap_x, &full_bar[stage], 0, tx * kTileW + (tap % 3) - 1,
-                      ty * kTileH + (tap / 3) - 1, b);
+                      ty * kTileH + (tap / 3) - 1 - prm.y_in0, b);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -130,8 +154,16 @@ decoder_head_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const long long plane = static_cast<long long>(H) * W;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tx = static_cast<int>(tile % tiles_x);
-      const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+      const int ty = static_cast<int>((tile / tiles_x) % tiles_y) + prm.ty_begin;
       const int b = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
+      const int y = ty * kTileH + (r >> 6), x = tx * kTileW + (r & 63);
+      float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+      if constexpr (MODE == kModeHeadBwd) {  // does not depend on the accumulator: issue before the wait
+        const float* src = prm.d_pred + static_cast<long long>(b) * 3 * plane + static_cast<long long>(y) * W + x;
+        dp0 = src[0];
+        dp1 = src[plane];
+        dp2 = src[2 * plane];
+      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 64;
@@ -143,8 +175,8 @@ decoder_head_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          v[i] = t0[i] + sPar[i];
-          v[32 + i] = t1[i] + sPar[32 + i];
+          v[i] = t0[i] + (MODE == kModeDgrad ? 0.f : sPar[i]);
+          v[32 + i] = t1[i] + (MODE == kModeDgrad ? 0.f : sPar[32 + i]);
         }
       }
       // accumulator is in registers: release the TMEM buffer early
@@ -152,30 +184,70 @@ decoder_head_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
 
-      float s = 0.f;
+      if constexpr (MODE == kModeDgrad) {
+        // rows of the decoder_embed dgrad operand: token (y/16, x/16), column ((y%16)*16 + x%16)*64 + c
+        __nv_bfloat16* dst = prm.out_bf16 +
+                             (static_cast<long long>(b) * ((H >> 4) * (W >> 4)) + (y >> 4) * (W >> 4) + (x >> 4)) * 16384 +
+                             (((y & 15) << 4) + (x & 15)) * 64;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) s += v[i];
-      const float mean = s * (1.0f / 64.0f);
-      float ss = 0.f;
+        for (int i = 0; i < 64; i += 8)
+          *reinterpret_cast<uint4*>(dst + i) =
+              make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]), pack_bf16x2(v[i + 4], v[i + 5]),
+                         pack_bf16x2(v[i + 6], v[i + 7]));
+      } else {
+        float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float d = v[i] - mean;
-        ss += d * d;
+        for (int i = 0; i < 64; ++i) s += v[i];
+        const float mean = s * (1.0f / 64.0f);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float d = v[i] - mean;
+          ss += d * d;
+        }
+        const float rstd = rsqrtf(ss * (1.0f / 64.0f) + eps);
+        if constexpr (MODE == kModeHead) {
+          float o0 = sPar[384], o1 = sPar[385], o2 = sPar[386];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float g = gelu_erf((v[i] - mean) * rstd * sPar[64 + i] + sPar[128 + i]);
+            o0 = fmaf(g, sPar[192 + i], o0);
+            o1 = fmaf(g, sPar[256 + i], o1);
+            o2 = fmaf(g, sPar[320 + i], o2);
+          }
+          float* dst = prm.pred + static_cast<long long>(b) * 3 * plane + static_cast<long long>(y) * W + x;
+          dst[0] = o0;
+          dst[plane] = o1;
+          dst[2 * plane] = o2;
+        } else {
+          // pred = head(gelu(LN(v))):  dg = head_w^T dpred;  dyl = dg * gelu'(yl);  LN backward over the 64 channels
+          float m1 = 0.f, m2 = 0.f;
+          float gyv[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float xh = (v[i] - mean) * rstd;
+            const float yl = fmaf(xh, sPar[64 + i], sPar[128 + i]);
+            const float dg = fmaf(dp0, sPar[192 + i], fmaf(dp1, sPar[256 + i], dp2 * sPar[320 + i]));
+            const float gy = dg * gelu_erf_grad(yl) * sPar[64 + i];
+            m1 += gy;
+            m2 = fmaf(gy, xh, m2);
+            v[i] = xh;
+            gyv[i] = gy;
+          }
+          m1 *= (1.0f / 64.0f);
+          m2 *= (1.0f / 64.0f);
+          __nv_bfloat16* dst = prm.out_bf16 +
+                               ((static_cast<long long>(b) * (H - prm.y_out0) + (y - prm.y_out0)) * W + x) * 64;
+#pragma unroll
+          for (int i = 0; i < 64; i += 8) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = rstd * (gyv[i + j] - m1 - v[i + j] * m2);
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                            pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          }
+        }
       }
-      const float rstd = rsqrtf(ss * (1.0f / 64.0f) + eps);
-      float o0 = sPar[384], o1 = sPar[385], o2 = sPar[386];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float g = gelu_erf((v[i] - mean) * rstd * sPar[64 + i] + sPar[128 + i]);
-        o0 = fmaf(g, sPar[192 + i], o0);
-        o1 = fmaf(g, sPar[256 + i], o1);
-        o2 = fmaf(g, sPar[320 + i], o2);
-      }
-      const int y = ty * kTileH + (r >> 6), x = tx * kTileW + (r & 63);
-      float* dst = pred + static_cast<long long>(b) * 3 * plane + static_cast<long long>(y) * W + x;
-      dst[0] = o0;
-      dst[plane] = o1;
-      dst[2 * plane] = o2;
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -188,16 +260,19 @@ decoder_head_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   }
 }
 
-int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, const float* conv_b, const float* ln_w,
-                        const float* ln_b, const float* head_w, const float* head_b, float* pred, int B, int H, int W,
-                        float eps, cudaStream_t stream) {
+namespace {
+// x: NHWC bf16 tensor whose row 0 is image row `y_in0` and which holds `rows_in` rows per batch entry
+template <int MODE>
+int launch_decoder_conv_t(const __nv_bfloat16* x_nhwc, int rows_in, const __nv_bfloat16* w9, dconv::Params prm,
+                          double flop, double bytes, cudaStream_t stream) {
   using namespace dconv;
-  BSEG_REQUIRE(H % kTileH == 0 && W % kTileW == 0, "decoder_head: H=%d W=%d must be multiples of %d x %d", H, W,
-               kTileH, kTileW);
+  BSEG_REQUIRE(prm.H % kTileH == 0 && prm.W % kTileW == 0, "decoder_conv: H=%d W=%d must be multiples of %d x %d",
+               prm.H, prm.W, kTileH, kTileW);
+  BSEG_REQUIRE(prm.ty_begin >= 0 && prm.ty_begin * kTileH < prm.H, "decoder_conv: tile range");
   CUtensorMap tx, tw;
   {
-    uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
-    uint64_t strides[3] = {128, static_cast<uint64_t>(W) * 128, static_cast<uint64_t>(H) * W * 128};
+    uint64_t dims[4] = {64, static_cast<uint64_t>(prm.W), static_cast<uint64_t>(rows_in), static_cast<uint64_t>(prm.B)};
+    uint64_t strides[3] = {128, static_cast<uint64_t>(prm.W) * 128, static_cast<uint64_t>(rows_in) * prm.W * 128};
     uint32_t box[4] = {64, kTileW, kTileH, 1};
     int rc = make_tmap_bf16(&tx, x_nhwc, 4, dims, strides, box);
     if (rc) return rc;
@@ -206,21 +281,66 @@ int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, co
     int rc = make_tmap_bf16_2d(&tw, w9, 64, 9 * 64, 64, 64, 192);
     if (rc) return rc;
   }
+  auto kern = decoder_conv_kernel<MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    BSEG_CHECK_CUDA(
-        cudaFuncSetAttribute(decoder_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  const long long tiles = static_cast<long long>(B) * (H / kTileH) * (W / kTileW);
+  const long long tiles = static_cast<long long>(prm.B) * (prm.H / kTileH - prm.ty_begin) * (prm.W / kTileW);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  ProfScope prof(CAT_DECODER_HEAD, static_cast<double>(B) * H * W * (2.0 * 576 * 64 + 2.0 * 64 * 3),
-                 static_cast<double>(B) * H * W * (64 * 2 + 3 * 4), stream);
-  decoder_head_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tx, tw, conv_b, ln_w, ln_b, head_w, head_b, pred, B, H,
-                                                             W, eps);
+  ProfScope prof(CAT_DECODER_HEAD, flop, bytes, stream);
+  kern<<<grid, kThreads, kSmemBytes, stream>>>(tx, tw, prm);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+}  // namespace
+
+int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, const float* conv_b, const float* ln_w,
+                        const float* ln_b, const float* head_w, const float* head_b, float* pred, int B, int H, int W,
+                        float eps, cudaStream_t stream) {
+  dconv::Params prm{};
+  prm.conv_b = conv_b; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.head_w = head_w; prm.head_b = head_b;
+  prm.pred = pred;
+  prm.B = B; prm.H = H; prm.W = W; prm.eps = eps;
+  return launch_decoder_conv_t<dconv::kModeHead>(x_nhwc, H, w9, prm,
+                                                 static_cast<double>(B) * H * W * (2.0 * 576 * 64 + 2.0 * 64 * 3),
+                                                 static_cast<double>(B) * H * W * (64 * 2 + 3 * 4), stream);
+}
+
+// Backward through conv1x1 head, GELU and LayerNorm(C) for image rows >= y0 (the loss only touches the query half,
+// src/model.py:48-57): recomputes the conv3x3 output from the saved NHWC input and writes d(conv out) as
+// bf16 NHWC [B, H - y0, W, 64].
+int launch_decoder_head_bwd(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, const float* conv_b,
+                            const float* ln_w, const float* ln_b, const float* head_w, const float* head_b,
+                            const float* d_pred, __nv_bfloat16* d_conv, int B, int H, int W, int y0, float eps,
+                            cudaStream_t stream) {
+  BSEG_REQUIRE(y0 >= 0 && y0 < H && y0 % dconv::kTileH == 0, "decoder_head_bwd: y0=%d", y0);
+  dconv::Params prm{};
+  prm.conv_b = conv_b; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.head_w = head_w; prm.head_b = head_b;
+  prm.d_pred = d_pred;
+  prm.out_bf16 = d_conv;
+  prm.B = B; prm.H = H; prm.W = W; prm.eps = eps;
+  prm.ty_begin = y0 / dconv::kTileH;
+  prm.y_out0 = y0;
+  const double px = static_cast<double>(B) * (H - y0) * W;
+  return launch_decoder_conv_t<dconv::kModeHeadBwd>(x_nhwc, H, w9, prm, px * (2.0 * 576 * 64 + 4.0 * 64 * 3),
+                                                    px * (64 * 2 * 2 + 3 * 4), stream);
+}
+
+// conv3x3 dgrad: d_conv is bf16 NHWC [B, H - y0, W, 64] (rows above y0 are zero); w9b = flipped / transposed taps.
+// Writes rows of the decoder_embed dgrad operand [B*(H/16)*(W/16), 16384] for image rows >= y_first (a multiple of 16).
+int launch_decoder_conv_dgrad(const __nv_bfloat16* d_conv, const __nv_bfloat16* w9b, __nv_bfloat16* d_dec_rows, int B,
+                              int H, int W, int y0, int y_first, cudaStream_t stream) {
+  BSEG_REQUIRE(y_first % 16 == 0 && y_first <= y0 && y_first >= 0, "decoder_conv_dgrad: y_first=%d y0=%d", y_first, y0);
+  dconv::Params prm{};
+  prm.out_bf16 = d_dec_rows;
+  prm.B = B; prm.H = H; prm.W = W;
+  prm.ty_begin = y_first / dconv::kTileH;
+  prm.y_in0 = y0;
+  const double px = static_cast<double>(B) * (H - y_first) * W;
+  return launch_decoder_conv_t<dconv::kModeDgrad>(d_conv, H - y0, w9b, prm, px * 2.0 * 576 * 64, px * 64 * 2 * 2, stream);
 }
 
 }  // namespace bseg

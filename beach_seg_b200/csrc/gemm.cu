@@ -5,13 +5,20 @@
 namespace bseg {
 
 template <int BLOCK_N, int MODE>
-static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long M, int N, int K,
+static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, const GemmRows& gr, int N, int K,
                          const GemmEpiParams& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda),
-                             GEMM_BLOCK_K, GEMM_BLOCK_M);
+  int rc;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(gr.rows_per_batch),
+                        static_cast<uint64_t>(gr.nbatch)};
+    uint64_t strides[2] = {static_cast<uint64_t>(lda) * 2, static_cast<uint64_t>(gr.rows_per_batch) * lda * 2};
+    uint32_t box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
+    rc = make_tmap_bf16(&ta, A, 3, dims, strides, box);
+  }
   if (rc) return rc;
+  const long long M = static_cast<long long>(gr.nbatch) * gr.rows;
   rc = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K),
                          GEMM_BLOCK_K, BLOCK_N);
   if (rc) return rc;
@@ -21,12 +28,12 @@ static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloa
     BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const long long tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * (N / BLOCK_N);
+  const long long tiles = static_cast<long long>(gr.nbatch) * ((gr.rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * (N / BLOCK_N);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   ProfScope prof(CAT_GEMM, 2.0 * static_cast<double>(M) * N * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream,
                  MODE + (K > 2048 ? 8 : 0));
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, gr, N, K, ep);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -34,7 +41,15 @@ static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloa
 
 int launch_gemm(int mode, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long M, int N, int K,
                 const GemmEpiParams& ep, cudaStream_t stream) {
-  BSEG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%lld N=%d K=%d", M, N, K);
+  BSEG_REQUIRE(M > 0 && M < (1ll << 31), "gemm: M=%lld out of range", M);
+  GemmRows gr{M, 1, 0, static_cast<int>(M)};
+  return launch_gemm_rows(mode, A, lda, W, gr, N, K, ep, stream);
+}
+
+int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, const GemmRows& gr, int N,
+                     int K, const GemmEpiParams& ep, cudaStream_t stream) {
+  BSEG_REQUIRE(gr.rows > 0 && gr.nbatch > 0 && N > 0 && K > 0, "gemm: empty problem rows=%d N=%d K=%d", gr.rows, N, K);
+  BSEG_REQUIRE(gr.row_begin >= 0 && gr.row_begin + gr.rows <= gr.rows_per_batch, "gemm: row range outside the batch");
   BSEG_REQUIRE(K % GEMM_BLOCK_K == 0, "gemm: K=%d must be a multiple of %d", K, GEMM_BLOCK_K);
   BSEG_REQUIRE(N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
   BSEG_REQUIRE((lda * 2) % 16 == 0, "gemm: lda=%lld violates TMA 16-byte stride alignment", lda);
@@ -43,8 +58,8 @@ int launch_gemm(int mode, const __nv_bfloat16* A, long long lda, const __nv_bflo
   const bool wide = (N % 256 == 0);
 #define BSEG_GEMM_CASE(MODE_)                                                               \
   case MODE_:                                                                               \
-    return wide ? launch_gemm_t<256, MODE_>(A, lda, W, M, N, K, ep, stream)                 \
-                : launch_gemm_t<128, MODE_>(A, lda, W, M, N, K, ep, stream);
+    return wide ? launch_gemm_t<256, MODE_>(A, lda, W, gr, N, K, ep, stream)                 \
+                : launch_gemm_t<128, MODE_>(A, lda, W, gr, N, K, ep, stream);
   switch (mode) {
     BSEG_GEMM_CASE(EPI_BF16)
     BSEG_GEMM_CASE(EPI_BF16_GELU)
@@ -53,6 +68,7 @@ int launch_gemm(int mode, const __nv_bfloat16* A, long long lda, const __nv_bflo
     BSEG_GEMM_CASE(EPI_QKV)
     BSEG_GEMM_CASE(EPI_EMBED)
     BSEG_GEMM_CASE(EPI_PIXSHUF)
+    BSEG_GEMM_CASE(EPI_DGELU)
     default:
       BSEG_REQUIRE(false, "gemm: unknown epilogue mode %d", mode);
   }

@@ -17,6 +17,7 @@ enum GemmEpiMode : int {
   EPI_QKV = 4,        // scatter to q[seq,h,t,64], k[seq,h,t,64], vT[seq,h,64,T]  (+bias)
   EPI_EMBED = 5,      // out_f32[m, n]   = acc + tab[(m / rows_per_stream) * T + m % T, n]
   EPI_PIXSHUF = 6,    // decoder pixel shuffle: nhwc[b, ph*16+py, pw*16+px, c] = acc + bias[n], n = (py*16+px)*64+c
+  EPI_DGELU = 7,      // backward of lin1's GELU: out_bf16[m, n] = acc * gelu'(aux_bf16[m, n])   (aux = saved pre-activation)
 };
 
 struct GemmEpiParams {
@@ -25,6 +26,8 @@ struct GemmEpiParams {
   const float* bias = nullptr;
   const float* resid = nullptr;
   long long ldr = 0;
+  // EPI_BF16_GELU: optional bf16 copy of the pre-activation (saved for the backward pass); EPI_DGELU: that copy (input)
+  __nv_bfloat16* aux = nullptr;
   // EPI_EMBED
   const float* tab = nullptr;
   int rows_per_stream = 0;
@@ -36,6 +39,16 @@ struct GemmEpiParams {
   __nv_bfloat16* k = nullptr;
   __nv_bfloat16* vt = nullptr;
   int heads = 16;
+};
+
+// Which rows of A (== rows of the output) a launch covers: `nbatch` entries of `rows_per_batch` rows each, of which
+// rows [row_begin, row_begin + rows) are computed.  A plain GEMM is {M, 1, 0, M}; the decoder's query-half slice is
+// {1568, B, 756, 812}.
+struct GemmRows {
+  long long rows_per_batch;
+  int nbatch;
+  int row_begin;
+  int rows;
 };
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -63,13 +76,13 @@ struct EpiRows {
   float4 r[8];  // addend of rows (i*4 + lane/8), columns 4*(lane%8)..+3
 };
 template <int MODE>
-__device__ __forceinline__ void gemm_epi_f32_prefetch(const GemmEpiParams& ep, EpiRows& pr, long long row0, long long M,
+__device__ __forceinline__ void gemm_epi_f32_prefetch(const GemmEpiParams& ep, EpiRows& pr, long long row0, int nvalid,
                                                       int n, int lane) {
   if constexpr (MODE == EPI_RESID_F32 || MODE == EPI_EMBED) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const long long m = row0 + i * 4 + (lane >> 3);
-      if (m < M) {
+      if (i * 4 + (lane >> 3) < nvalid) {
         const float* add;
         if constexpr (MODE == EPI_RESID_F32) {
           add = ep.resid + m * ep.ldr;
@@ -83,7 +96,7 @@ __device__ __forceinline__ void gemm_epi_f32_prefetch(const GemmEpiParams& ep, E
 }
 template <int MODE>
 __device__ __forceinline__ void gemm_epi_f32_chunk(const GemmEpiParams& ep, const float (&v)[32], const EpiRows& pr,
-                                                   float* stg, long long row0, long long M, int n, int lane) {
+                                                   float* stg, long long row0, int nvalid, int n, int lane) {
   // 1) accumulator row of this thread -> smem (16-byte chunk index XOR row&7: conflict free both ways)
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -104,7 +117,7 @@ __device__ __forceinline__ void gemm_epi_f32_chunk(const GemmEpiParams& ep, cons
     if constexpr (MODE != EPI_F32) {
       o.x += pr.r[i].x; o.y += pr.r[i].y; o.z += pr.r[i].z; o.w += pr.r[i].w;
     }
-    if (m < M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + m * ep.ldc + n + 4 * (lane & 7)) = o;
+    if (rr < nvalid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + m * ep.ldc + n + 4 * (lane & 7)) = o;
   }
   __syncwarp();
 }
@@ -121,10 +134,32 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, flo
       }
     }
   }
-  if constexpr (MODE == EPI_BF16 || MODE == EPI_BF16_GELU) {
+  if constexpr (MODE == EPI_BF16 || MODE == EPI_BF16_GELU || MODE == EPI_DGELU) {
     if constexpr (MODE == EPI_BF16_GELU) {
+      if (ep.aux != nullptr) {
+        __nv_bfloat16* z = ep.aux + m * ep.ldc + n;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                                pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+          *reinterpret_cast<uint4*>(z + i) = pk;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if constexpr (MODE == EPI_DGELU) {
+      const __nv_bfloat16* z = ep.aux + m * ep.ldc + n;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(z + i);
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[i + 2 * j] *= gelu_erf_grad(__uint_as_float(w[j] << 16));
+          v[i + 2 * j + 1] *= gelu_erf_grad(__uint_as_float(w[j] & 0xffff0000u));
+        }
+      }
     }
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + m * ep.ldc + n;
 #pragma unroll
@@ -175,7 +210,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, flo
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         long long M, int N, int K, GemmEpiParams ep) {
+                         GemmRows gr, int N, int K, GemmEpiParams ep) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -194,7 +229,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int lane = threadIdx.x & 31;
 
   const int num_n_tiles = N / BLOCK_N;
-  const long long num_m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int tiles_per_batch = (gr.rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const long long num_m_tiles = static_cast<long long>(gr.nbatch) * tiles_per_batch;
   const long long num_tiles = num_m_tiles * num_n_tiles;
   const int num_k_blocks = K / GEMM_BLOCK_K;
 
@@ -225,12 +261,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = static_cast<int>(tile / num_n_tiles) * GEMM_BLOCK_M;
+        const long long mt = tile / num_n_tiles;
+        const int bidx = static_cast<int>(mt / tiles_per_batch);
+        const int m0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * GEMM_BLOCK_M;
         const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+          tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0, bidx);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -275,24 +313,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int as = 0;
     uint32_t aphase = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long m0 = (tile / num_n_tiles) * GEMM_BLOCK_M;
+      const long long mt = tile / num_n_tiles;
+      const int local0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * GEMM_BLOCK_M + q * 32;
+      const long long row0 = (mt / tiles_per_batch) * gr.rows_per_batch + local0;  // first row of this warp
+      const int nvalid = gr.row_begin + gr.rows - local0;                          // rows of this warp inside the range
       const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
-      const long long m = m0 + q * 32 + lane;
+      const long long m = row0 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
       if constexpr (MODE == EPI_F32 || MODE == EPI_RESID_F32 || MODE == EPI_EMBED) {
         float* stg = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 1024;
-        const long long row0 = m0 + q * 32;
         EpiRows pr, pn;
-        gemm_epi_f32_prefetch<MODE>(ep, pr, row0, M, n0 + col0, lane);  // does not depend on the accumulator
+        gemm_epi_f32_prefetch<MODE>(ep, pr, row0, nvalid, n0 + col0, lane);  // does not depend on the accumulator
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
           float v[32];
           tmem_ld32(taddr + c, v);
-          if (c + 32 < col0 + kColsPerWarp) gemm_epi_f32_prefetch<MODE>(ep, pn, row0, M, n0 + c + 32, lane);
+          if (c + 32 < col0 + kColsPerWarp) gemm_epi_f32_prefetch<MODE>(ep, pn, row0, nvalid, n0 + c + 32, lane);
           tmem_ld_wait();
-          gemm_epi_f32_chunk<MODE>(ep, v, pr, stg, row0, M, n0 + c, lane);
+          gemm_epi_f32_chunk<MODE>(ep, v, pr, stg, row0, nvalid, n0 + c, lane);
           pr = pn;
         }
       } else {
@@ -303,7 +343,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           float v[32];
           tmem_ld32(taddr + c, v);
           tmem_ld_wait();
-          if (m < M) gemm_epilogue_chunk<MODE>(ep, v, m, n0 + c);
+          if (lane < nvalid) gemm_epilogue_chunk<MODE>(ep, v, m, n0 + c);
         }
       }
       tc_fence_before();

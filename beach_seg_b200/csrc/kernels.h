@@ -11,20 +11,54 @@ namespace bseg {
 // gemm.cu
 int launch_gemm(int mode, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long M, int N, int K,
                 const GemmEpiParams& ep, cudaStream_t stream);
+int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, const GemmRows& gr, int N,
+                     int K, const GemmEpiParams& ep, cudaStream_t stream);
 
 // attention.cu : fused softmax(q k^T * scale + decomposed rel-pos bias) v, one CTA per (seq, head, 128-query tile)
 //   q, k : [nseq, heads, T, 64] bf16     vt : [nseq, heads, 64, T] bf16
 //   relcat : [176, 64] bf16 = reversed rel_pos_h (111 rows, padded to 112) ; reversed rel_pos_w (55 rows, padded to 64)
 //   out : [nseq, T, heads*64] bf16 (token-major, ready to be the A operand of the proj GEMM)
+//   lse_out (nullable): log2-domain log-sum-exp per (seq, head, query), saved for the backward pass
 int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
-                     const __nv_bfloat16* relcat, __nv_bfloat16* out, int nseq, int heads, int grid_h, int grid_w,
-                     cudaStream_t stream);
+                     const __nv_bfloat16* relcat, __nv_bfloat16* out, float* lse_out, int nseq, int heads, int grid_h,
+                     int grid_w, cudaStream_t stream);
+
+// attention_bwd.cu : dq, dk, dv of the fused attention, written token-major into dqkv [nseq*T, 3*heads*64] bf16
+//   q, k, v : [nseq*heads, T, 64];  qt, kt, dOt : [nseq*heads, 64, T];  dO : token-major [nseq*T, heads*64]
+//   lse, Dvec : [nseq*heads, T] fp32;  relcat [176,64], relcat_t [64,192] bf16;  bias_tab : scratch [nseq*heads, 84, T] fp32
+int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                         const __nv_bfloat16* qt, const __nv_bfloat16* kt, const __nv_bfloat16* dO,
+                         const __nv_bfloat16* dOt, const float* lse, const float* Dvec, const __nv_bfloat16* relcat,
+                         const __nv_bfloat16* relcat_t, float* bias_tab, __nv_bfloat16* dqkv, int nseq, int heads,
+                         cudaStream_t stream);
 
 // decoder_conv.cu : conv3x3(64->64, pad 1) + LayerNorm(C=64) + erf-GELU + conv1x1(64->3), NHWC bf16 in, NCHW fp32 out
 int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9 /*[9][64 out][64 in]*/,
                         const float* conv_b, const float* ln_w, const float* ln_b, const float* head_w /*[3][64]*/,
                         const float* head_b, float* pred /*[B,3,H,W]*/, int B, int H, int W, float eps,
                         cudaStream_t stream);
+
+int launch_decoder_head_bwd(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, const float* conv_b,
+                            const float* ln_w, const float* ln_b, const float* head_w, const float* head_b,
+                            const float* d_pred, __nv_bfloat16* d_conv, int B, int H, int W, int y0, float eps,
+                            cudaStream_t stream);
+int launch_decoder_conv_dgrad(const __nv_bfloat16* d_conv, const __nv_bfloat16* w9b, __nv_bfloat16* d_dec_rows, int B,
+                              int H, int W, int y0, int y_first, cudaStream_t stream);
+
+// backward.cu
+int launch_transpose_bf16(const __nv_bfloat16* src, __nv_bfloat16* dst, int R, int C, int batch,
+                          long long src_batch_stride, long long dst_batch_stride, long long ld_src, long long ld_dst,
+                          cudaStream_t stream);
+int launch_layernorm1024_bwd(const float* x, const float* dy, long long lddy, const float* gamma, const float* dh_in,
+                             float* dh_out, __nv_bfloat16* dh_bf16, long long rows_per_batch, int nbatch,
+                             int row_begin, int rows, float eps, cudaStream_t stream);
+int launch_scale_f32_bf16(const float* src, float* dst, __nv_bfloat16* dst_bf16, float scale, long long n,
+                          cudaStream_t stream);
+int launch_unpatchify_prompt_grad(const float* dA, float* dprompt, int B, cudaStream_t stream);
+int launch_attn_bwd_prep(const __nv_bfloat16* dO, const __nv_bfloat16* O, const __nv_bfloat16* q,
+                         const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* dOt, float* Dvec,
+                         __nv_bfloat16* qt, __nv_bfloat16* kt, __nv_bfloat16* v, int nseq, int heads, int T,
+                         cudaStream_t stream);
 
 // elementwise.cu
 int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t stream);

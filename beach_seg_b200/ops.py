@@ -109,9 +109,10 @@ def ingest_tiles(scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Ten
     out["image"] = torch.empty((n, 3, 448, 448), dtype=torch.float32, device=dev) if want_nchw else None
     out["u8"] = torch.empty((n, crop, crop, 3), dtype=torch.uint8, device=dev) if want_u8 else None
     out["nodata"] = torch.empty((n, crop, crop), dtype=torch.uint8, device=dev) if want_nodata else None
+    boxes_i = boxes.to(torch.int32).contiguous()  # named: must outlive the launch
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().bseg_ingest_u16x4(
-            _lib.ptr(scene_u16), _lib.ptr(nd), Hs, Ws, _lib.ptr(stats), _lib.ptr(boxes.to(torch.int32).contiguous()),
+            _lib.ptr(scene_u16), _lib.ptr(nd), Hs, Ws, _lib.ptr(stats), _lib.ptr(boxes_i),
             n, crop, _lib.ptr(coef), _lib.ptr(bounds), ksize, _lib.f3(IMAGE_MEAN), _lib.f3(IMAGE_STD),
             _lib.ptr(out["image"]), _lib.ptr(out_patch), patch_tile_stride, _lib.ptr(out["u8"]),
             _lib.ptr(out["nodata"]), _lib.stream_ptr()), "bseg_ingest_u16x4")
@@ -161,9 +162,10 @@ def decode_palette(pred_masks: torch.Tensor, palette_norm: torch.Tensor, out_siz
     o8 = torch.empty((B, out_size, out_size), dtype=torch.uint8, device=dev) if dtype == torch.uint8 else None
     o64 = torch.empty((B, out_size, out_size), dtype=torch.int64, device=dev) if dtype == torch.int64 else None
     nd = nodata.to(torch.uint8).contiguous() if nodata is not None else None
+    pred_c, pal_c = pred_masks.contiguous(), palette_norm.to(torch.float32).contiguous()  # must outlive the launch
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().bseg_decode_palette(
-            _lib.ptr(pred_masks.contiguous()), _lib.ptr(palette_norm.to(torch.float32).contiguous()),
+            _lib.ptr(pred_c), _lib.ptr(pal_c),
             palette_norm.shape[1], _lib.ptr(o8), _lib.ptr(o64), _lib.ptr(nd), _lib.ptr(idx), B, H, W, out_size,
             _lib.stream_ptr()), "bseg_decode_palette")
     return o8 if o8 is not None else o64
@@ -176,8 +178,9 @@ def mean_over_prompts(pred_masks: torch.Tensor, prompts: int) -> torch.Tensor:
     n_tiles = B // prompts
     per = pred_masks[0].numel()
     out = torch.empty((n_tiles, *pred_masks.shape[1:]), dtype=torch.float32, device=pred_masks.device)
+    pred_c = pred_masks.contiguous()
     with torch.cuda.device(pred_masks.device):
-        _lib.check(_lib.lib().bseg_mean_over_prompts(_lib.ptr(pred_masks.contiguous()), _lib.ptr(out), n_tiles,
+        _lib.check(_lib.lib().bseg_mean_over_prompts(_lib.ptr(pred_c), _lib.ptr(out), n_tiles,
                                                      prompts, per, _lib.stream_ptr()), "bseg_mean_over_prompts")
     return out
 
@@ -191,9 +194,10 @@ def vote_accumulate(counter: torch.Tensor, cls: torch.Tensor, boxes: torch.Tenso
     _need_cuda(counter, cls, boxes)
     Hs, Ws = counter.shape
     n, crop, _ = cls.shape
+    cls_c, boxes_i = cls.contiguous(), boxes.to(torch.int32).contiguous()  # must outlive the launch
     with torch.cuda.device(counter.device):
-        _lib.check(_lib.lib().bseg_vote_accumulate(_lib.ptr(counter), Hs, Ws, _lib.ptr(cls.contiguous()), n, crop,
-                                                   _lib.ptr(boxes.to(torch.int32).contiguous()),
+        _lib.check(_lib.lib().bseg_vote_accumulate(_lib.ptr(counter), Hs, Ws, _lib.ptr(cls_c), n, crop,
+                                                   _lib.ptr(boxes_i),
                                                    1 if (overlapping and n > 1) else 0, _lib.stream_ptr()),
                    "bseg_vote_accumulate")
 
@@ -223,9 +227,10 @@ def smooth_l1_loss(pred_masks: torch.Tensor, labels: torch.Tensor, yesdata: torc
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     grad = torch.empty_like(pred_masks, dtype=torch.float32) if want_grad else None
     scratch = torch.empty(2, dtype=torch.float32, device=dev)
+    pred_c, lab_c = pred_masks.contiguous(), labels.to(torch.float32).contiguous()  # must outlive the launch
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().bseg_loss_smoothl1_fwd_bwd(
-            _lib.ptr(pred_masks.contiguous()), _lib.ptr(labels.to(torch.float32).contiguous()), _lib.ptr(yes),
+            _lib.ptr(pred_c), _lib.ptr(lab_c), _lib.ptr(yes),
             float(beta), 1 if per_sample else 0, _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(scratch), B, H, W,
             _lib.stream_ptr()), "bseg_loss_smoothl1_fwd_bwd")
     return (loss[0], grad) if want_grad else loss[0]

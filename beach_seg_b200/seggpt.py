@@ -34,6 +34,47 @@ class SegGptOutput:
         return tuple(v for v in (self.loss, self.pred_masks) if v is not None)[k]
 
 
+class _PromptGradFn(torch.autograd.Function):
+    """pred_masks = SegGPT(pixel_values, prompt_pixel_values, prompt_masks) with a gradient path to
+    prompt_pixel_values only: the reference trains nothing else (src/model.py:115-130, src/util/ml_util.py:9-10).
+    Forward = bseg_forward_train (keeps activations in the module's training workspace), backward =
+    bseg_backward_to_prompt.  One forward may be in flight per module (the workspace is reused)."""
+
+    @staticmethod
+    def forward(ctx, prompt_pixel_values, model, pixel_values, prompt_masks, embedding_type):
+        B = pixel_values.shape[0]
+        pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=model.device)
+        ws, base, nbytes = model._train_workspace(B)
+        with torch.cuda.device(model.device):
+            _lib.check(_lib.lib().bseg_forward_train(model._handle, _lib.ptr(pixel_values),
+                                                     _lib.ptr(prompt_pixel_values), _lib.ptr(prompt_masks), B,
+                                                     0 if embedding_type == "instance" else 1, C.c_void_p(base),
+                                                     C.c_size_t(nbytes), _lib.ptr(pred), _lib.stream_ptr()),
+                       "bseg_forward_train")
+        ctx.model, ctx.batch = model, B
+        model._train_token += 1
+        ctx.token = model._train_token
+        return pred
+
+    @staticmethod
+    def backward(ctx, d_pred):
+        model, B = ctx.model, ctx.batch
+        if ctx.token != model._train_token:
+            raise _lib.BsegError("backward() after another training forward of the same module: its saved "
+                                 "activations were overwritten")
+        d_pred = d_pred.to(torch.float32).contiguous()
+        if model.check_grad_support and bool((d_pred[:, :, :IMG] != 0).any()):  # (a device->host sync)
+            raise NotImplementedError("d(pred_masks) must be zero in the prompt half (image rows < 448), as it is for "
+                                      "the reference's SegGptLoss (src/model.py:48-57)")
+        d_prompt = torch.empty((B, 3, IMG, IMG), dtype=torch.float32, device=model.device)
+        ws, base, nbytes = model._train_workspace(B)
+        with torch.cuda.device(model.device):
+            _lib.check(_lib.lib().bseg_backward_to_prompt(model._handle, _lib.ptr(d_pred), B, C.c_void_p(base),
+                                                          C.c_size_t(nbytes), _lib.ptr(d_prompt), _lib.stream_ptr()),
+                       "bseg_backward_to_prompt")
+        return d_prompt, None, None, None, None
+
+
 class SegGptB200(torch.nn.Module):
     def __init__(self, state_dict: Dict[str, torch.Tensor], num_layers: int = 24, merge_index: int = 2,
                  intermediate=(5, 11, 17, 23), layer_norm_eps: float = 1e-6, beta: float = 0.01,
@@ -47,6 +88,10 @@ class SegGptB200(torch.nn.Module):
         self.max_batch = max_batch
         self._handle = C.c_void_p()
         self._ws: Optional[torch.Tensor] = None
+        self._train_ws: Optional[torch.Tensor] = None
+        self._train_token = 0
+        self.check_grad_support = True  # verify in backward() that d(pred_masks) is zero in the prompt half
+        self._train_ready = False
         self._scratch = torch.zeros(8, dtype=torch.float32, device=self._device)
         L = _lib.lib()
         with torch.cuda.device(self._device):
@@ -118,6 +163,21 @@ class SegGptB200(torch.nn.Module):
             self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self._device)
         return self._ws
 
+    def _train_workspace(self, batch: int):
+        """(tensor, 256B-aligned base address, usable bytes) of the training workspace for `batch` samples; the first
+        call also packs the transposed weight copies the dgrad GEMMs need."""
+        L = _lib.lib()
+        if not self._train_ready:
+            with torch.cuda.device(self._device):
+                _lib.check(L.bseg_train_prepare(self._handle, _lib.stream_ptr()), "bseg_train_prepare")
+            self._train_ready = True
+        need = int(L.bseg_train_workspace_bytes(self._handle, batch))
+        if self._train_ws is None or self._train_ws.numel() < need + 256:
+            self._train_ws = None
+            self._train_ws = torch.empty(need + 256, dtype=torch.uint8, device=self._device)
+        base = (self._train_ws.data_ptr() + 255) // 256 * 256
+        return self._train_ws, base, self._train_ws.numel() - (base - self._train_ws.data_ptr())
+
     # ------------------------------------------------------------------------------------------------
     def forward(self, pixel_values: torch.Tensor, prompt_pixel_values: torch.Tensor, prompt_masks: torch.Tensor,
                 bool_masked_pos: Optional[torch.Tensor] = None, feature_ensemble: Optional[bool] = None,
@@ -144,9 +204,10 @@ class SegGptB200(torch.nn.Module):
                                           "reference never passes another one")
         if output_attentions or output_hidden_states:
             raise NotImplementedError("attention / hidden-state outputs are never requested on the reference path")
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (pixel_values, prompt_pixel_values, prompt_masks)):
-            raise NotImplementedError("backward to the prompt (bseg_backward_to_prompt) is not built yet; call under "
-                                      "torch.no_grad()")
+        want_grad = torch.is_grad_enabled() and prompt_pixel_values.requires_grad
+        if torch.is_grad_enabled() and (pixel_values.requires_grad or prompt_masks.requires_grad):
+            raise NotImplementedError("only prompt_pixel_values carries a gradient on the reference path "
+                                      "(src/model.py:115-130); pixel_values / prompt_masks must not require grad")
         B = pixel_values.shape[0]
         if not (prompt_pixel_values.shape[0] == B and prompt_masks.shape[0] == B):
             raise ValueError("pixel_values, prompt_pixel_values and prompt_masks must share the batch dimension")
@@ -159,6 +220,13 @@ class SegGptB200(torch.nn.Module):
         def prep(t):
             return t.detach().to(device=self._device, dtype=torch.float32).contiguous()
 
+        if want_grad:
+            if feature_ensemble:
+                raise NotImplementedError("feature_ensemble is an inference-only path in the reference "
+                                          "(src/predict_no_prompt.py:289-295)")
+            ppx_g = prompt_pixel_values.to(device=self._device, dtype=torch.float32).contiguous()
+            pred = _PromptGradFn.apply(ppx_g, self, prep(pixel_values), prep(prompt_masks), embedding_type)
+            return SegGptOutput(loss=self._hf_loss(pred.detach(), labels, B), pred_masks=pred)
         px, ppx, pm = prep(pixel_values), prep(prompt_pixel_values), prep(prompt_masks)
         pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=self._device)
         L = _lib.lib()
@@ -172,16 +240,19 @@ class SegGptB200(torch.nn.Module):
                                           _lib.ptr(pm[s:s + n]), n, 0 if embedding_type == "instance" else 1, P,
                                           C.c_void_p(base), C.c_size_t(ws.numel() - (base - ws.data_ptr())),
                                           _lib.ptr(pred[s:s + n]), _lib.stream_ptr()), "bseg_forward")
-        loss = None
-        if labels is not None:
-            # HF SegGptLoss (HF:modeling_seggpt.py:780-819) with the default mask == smooth-L1 over the bottom half.
-            # The reference computes it and throws it away (src/model.py:245-255); kept for interface fidelity.
-            lab = prep(labels)
-            yes = torch.ones((B, IMG, IMG), dtype=torch.uint8, device=self._device)
-            loss_t = torch.empty(1, dtype=torch.float32, device=self._device)
-            with torch.cuda.device(self._device):
-                _lib.check(L.bseg_loss_smoothl1_fwd_bwd(_lib.ptr(pred), _lib.ptr(lab), _lib.ptr(yes), self.beta, 1,
-                                                        _lib.ptr(loss_t), None, _lib.ptr(self._scratch), B, IMG, IMG,
-                                                        _lib.stream_ptr()), "bseg_loss")
-            loss = loss_t[0]
-        return SegGptOutput(loss=loss, pred_masks=pred)
+        return SegGptOutput(loss=self._hf_loss(pred, labels, B), pred_masks=pred)
+
+    def _hf_loss(self, pred: torch.Tensor, labels: Optional[torch.Tensor], B: int):
+        """HF SegGptLoss (HF:modeling_seggpt.py:780-819) with the default mask == smooth-L1 over the bottom half.
+        The reference computes it and throws it away (src/model.py:245-255); kept, without a graph, for interface
+        fidelity."""
+        if labels is None:
+            return None
+        lab = labels.detach().to(device=self._device, dtype=torch.float32).contiguous()
+        yes = torch.ones((B, IMG, IMG), dtype=torch.uint8, device=self._device)
+        loss_t = torch.empty(1, dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().bseg_loss_smoothl1_fwd_bwd(_lib.ptr(pred), _lib.ptr(lab), _lib.ptr(yes), self.beta,
+                                                             1, _lib.ptr(loss_t), None, _lib.ptr(self._scratch), B,
+                                                             IMG, IMG, _lib.stream_ptr()), "bseg_loss")
+        return loss_t[0]

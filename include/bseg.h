@@ -85,6 +85,21 @@ int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_
                  const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
                  size_t workspace_bytes, float* pred_masks, void* stream);
 
+/* ---- train step (src/model.py:233-269 + Lightning's loss.backward()): the reference differentiates the frozen HF
+ * module w.r.t. prompt_pixel_values only (all backbone weights have requires_grad=False, src/util/ml_util.py:9-10).
+ * bseg_train_prepare packs the transposed weight copies the dgrad GEMMs need (once, +740 MB).
+ * bseg_forward_train == bseg_forward (no feature ensemble) but keeps, in `workspace`, what the backward needs;
+ * bseg_backward_to_prompt consumes the same workspace:  d_pred_masks fp32 [batch,3,896,448] (must be zero in the
+ * prompt half, image rows < 448, as it is for the reference's loss, src/model.py:48-57) ->
+ * d_prompt_pixel_values fp32 [batch,3,448,448]. */
+int bseg_train_prepare(bseg_handle* h, void* stream);
+size_t bseg_train_workspace_bytes(const bseg_handle* h, int batch);
+int bseg_forward_train(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                       const float* prompt_masks, int batch, int embedding_type, void* workspace,
+                       size_t workspace_bytes, float* pred_masks, void* stream);
+int bseg_backward_to_prompt(bseg_handle* h, const float* d_pred_masks, int batch, void* workspace,
+                            size_t workspace_bytes, float* d_prompt_pixel_values, void* stream);
+
 /* tif_image 4-band branch statistics (src/util/geo_util.py:459-464): stats[0] = min over valid pixels of the
  * composite, stats[1..3] = per-channel max.  scene: uint16 [4,Hs,Ws] band-planar; nodata: uint8 [Hs,Ws].
  * scratch: 4 x uint32. */
@@ -149,6 +164,28 @@ int bseg_layernorm1024(const float* x, long long ldx, const float* gamma, const 
  * out bf16 [nseq,1568,1024]. */
 int bseg_attention(const void* q, const void* k, const void* vt, const void* relcat, void* out, int nseq,
                    void* stream);
+/* The same with the log2-domain log-sum-exp per (seq, head, query) written to lse fp32 [nseq,16,1568]. */
+int bseg_attention_fwd_lse(const void* q, const void* k, const void* vt, const void* relcat, void* out, float* lse,
+                           int nseq, void* stream);
+/* Backward of the fused attention (torch autograd through HF:modeling_seggpt.py:268-348 in the reference).
+ * out / d_out: bf16 token-major [nseq*1568, 1024]; dqkv: bf16 [nseq*1568, 3072] = (dq | dk | dv), head-major inside. */
+size_t bseg_attention_bwd_scratch_bytes(int nseq);
+int bseg_attention_bwd(const void* q, const void* k, const void* vt, const void* out, const void* d_out,
+                       const float* lse, const void* relcat, void* dqkv, int nseq, void* scratch, size_t scratch_bytes,
+                       void* stream);
+/* LayerNorm(1024) backward: dh_out = (dh_in ? dh_in : 0) + dLN(x, gamma; dy); dh_bf16 (nullable) = bf16(dh_out). */
+int bseg_layernorm1024_bwd(const float* x, const float* dy, long long lddy, const float* gamma, const float* dh_in,
+                           float* dh_out, void* dh_bf16, long long M, float eps, void* stream);
+/* out_bf16[M,N] = (A[M,K] * W[N,K]^T) * gelu'(z[M,N])  (backward of lin1's erf-GELU; z = saved pre-activation). */
+int bseg_gemm_bf16_dgelu(const void* A, long long lda, const void* W, long long M, int N, int K, const void* z,
+                         void* out, long long ldc, void* stream);
+/* Decoder-head backward for image rows >= y0: d_pred fp32 [B,3,H,W] -> d_conv bf16 [B,H-y0,W,64] (scratch) ->
+ * d_dec_rows bf16 [B*(H/16)*(W/16), 16384] (rows of the decoder_embed dgrad operand; written for image rows
+ * >= y0-16).  w9b = bseg_pack_conv_w9_dgrad(w9). */
+int bseg_pack_conv_w9_dgrad(const void* w9, void* w9b, void* stream);
+int bseg_decoder_head_bwd(const void* x_nhwc, const void* w9, const void* w9b, const float* conv_b, const float* ln_w,
+                          const float* ln_b, const float* head_w, const float* head_b, const float* d_pred,
+                          void* d_conv, void* d_dec_rows, int batch, int H, int W, int y0, float eps, void* stream);
 /* relcat = [reverse(rel_pos_h) (111 rows) ; 0 ; reverse(rel_pos_w) (55 rows) ; 0...] as bf16 [176,64]. */
 int bseg_pack_relcat(const float* rel_pos_h, const float* rel_pos_w, void* relcat, void* stream);
 /* Decoder head: conv3x3 + LN(C) + GELU + conv1x1. x bf16 NHWC [B,H,W,64]; w9 bf16 [9,64,64]; pred fp32 [B,3,H,W]. */

@@ -1,0 +1,241 @@
+"""GPU: the train step's backward kernels (C ABI) against torch autograd on the same inputs, kernel by kernel, then
+the whole d(loss)/d(prompt_pixel_values) against autograd through the real HF module (fp32, CPU) -- the reference's
+own gradient path (src/model.py:245-255 + Lightning backward; only the prompt carries a gradient).
+
+Tolerances: bf16 operands with fp32 accumulation; north_star states 1e-2 relative for logits and nothing for
+gradients.  The per-kernel bar used here is rel-L2 < 1.5e-2 and 3e-2 for the end-to-end gradient (written at each
+assert)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from beach_seg_b200 import _lib, synth
+from oracle.seggpt_ref import attention_ref, make_reference_model
+
+pytestmark = pytest.mark.gpu
+T = 1568
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_layernorm_backward(dev):
+    g = torch.Generator().manual_seed(3)
+    M = 777
+    x = (torch.randn((M, 1024), generator=g) * 2 + 0.3).to(dev).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(1024, generator=g)).to(dev)
+    beta = torch.randn(1024, generator=g).to(dev)
+    dy = torch.randn((M, 1024), generator=g).to(dev)
+    dh_in = torch.randn((M, 1024), generator=g).to(dev)
+    y = F.layer_norm(x, (1024,), gamma, beta, 1e-6)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    want = dh_in + dx
+    out = torch.empty_like(want)
+    out_bf = torch.empty((M, 1024), dtype=torch.bfloat16, device=dev)
+    _lib.check(_lib.lib().bseg_layernorm1024_bwd(_lib.ptr(x.detach()), _lib.ptr(dy), 1024, _lib.ptr(gamma),
+                                                 _lib.ptr(dh_in), _lib.ptr(out), _lib.ptr(out_bf), M, 1e-6,
+                                                 _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_l2(out, want) < 1e-5
+    assert rel_l2(out_bf.float(), want) < 5e-3
+    # in place, no residual input
+    _lib.check(_lib.lib().bseg_layernorm1024_bwd(_lib.ptr(x.detach()), _lib.ptr(dy), 1024, _lib.ptr(gamma), None,
+                                                 _lib.ptr(out), None, M, 1e-6, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_l2(out, dx) < 1e-5
+
+
+def test_gemm_dgelu(dev):
+    g = torch.Generator().manual_seed(4)
+    M, N, K = 300, 512, 256
+    a = bf16r(torch.randn((M, K), generator=g)).to(dev)
+    w = bf16r(torch.randn((N, K), generator=g) * 0.1).to(dev)
+    z = bf16r(torch.randn((M, N), generator=g) * 1.5).to(dev).requires_grad_(True)
+    (dg,) = torch.autograd.grad(F.gelu(z), z, torch.ones_like(z))
+    want = (a @ w.t()) * dg
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    ab, wb, zb = a.to(torch.bfloat16), w.to(torch.bfloat16), z.detach().to(torch.bfloat16)  # keep alive over the call
+    _lib.check(_lib.lib().bseg_gemm_bf16_dgelu(_lib.ptr(ab), K, _lib.ptr(wb), M, N, K, _lib.ptr(zb), _lib.ptr(out), N,
+                                               _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    r = rel_l2(out.float(), want)
+    print(f"[gemm dgelu] rel-L2={r:.3e}")
+    assert r < 5e-3
+
+
+def _attention_case(dev, nseq, qscale, relscale, seed):
+    g = torch.Generator().manual_seed(seed)
+    q = bf16r(torch.randn((nseq, 16, T, 64), generator=g) * qscale).to(dev)
+    k = bf16r(torch.randn((nseq, 16, T, 64), generator=g)).to(dev)
+    v = bf16r(torch.randn((nseq, 16, T, 64), generator=g)).to(dev)
+    rel_h = bf16r(torch.randn((111, 64), generator=g) * relscale).to(dev)
+    rel_w = bf16r(torch.randn((55, 64), generator=g) * relscale).to(dev)
+    d_out = bf16r(torch.randn((nseq, T, 1024), generator=g)).to(dev)
+    return q, k, v, rel_h, rel_w, d_out
+
+
+@pytest.mark.parametrize("nseq,qscale,relscale", [(1, 1.0, 0.0), (1, 1.0, 0.3), (2, 2.0, 0.4)])
+def test_attention_backward(dev, nseq, qscale, relscale):
+    """dq / dk / dv of the fused attention vs autograd through the oracle's attention (fp32, on the GPU for speed;
+    rel_pos tables on the device too)."""
+    q, k, v, rel_h, rel_w, d_out = _attention_case(dev, nseq, qscale, relscale, seed=11 + nseq)
+    # ---- reference: autograd through attention_ref, one head at a time (the T x T scores are 10 MB each) ----
+    dq_w, dk_w, dv_w, out_w = [torch.empty((nseq, 16, T, 64), device=dev) for _ in range(4)]
+    import oracle.seggpt_ref as ref
+
+    for s in range(nseq):
+        for hd in range(16):
+            qq, kk, vv = (t[s, hd][None].clone().requires_grad_(True) for t in (q, k, v))
+            # attention_ref builds its index tensors on the CPU: move the tables' gather to the device
+            scale = 64 ** -0.5
+            ih = (torch.arange(56)[:, None] - torch.arange(56)[None, :] + 55).to(dev)
+            iw = (torch.arange(28)[:, None] - torch.arange(28)[None, :] + 27).to(dev)
+            rq = qq.reshape(1, 56, 28, 64)
+            bias = (torch.einsum("bhwc,hkc->bhwk", rq, rel_h[ih])[:, :, :, :, None] +
+                    torch.einsum("bhwc,wkc->bhwk", rq, rel_w[iw])[:, :, :, None, :]).reshape(1, T, T)
+            attn = torch.softmax((qq * scale) @ kk.transpose(-2, -1) + bias, dim=-1, dtype=torch.float32)
+            o = attn @ vv
+            do = d_out[s].reshape(T, 16, 64)[:, hd][None]
+            gq, gk, gv = torch.autograd.grad(o, (qq, kk, vv), do)
+            dq_w[s, hd], dk_w[s, hd], dv_w[s, hd], out_w[s, hd] = gq[0], gk[0], gv[0], o[0].detach()
+    assert ref.T == T
+    # ---- ours ----
+    L = _lib.lib()
+    qb, kb = q.to(torch.bfloat16).contiguous(), k.to(torch.bfloat16).contiguous()
+    vt = v.to(torch.bfloat16).transpose(2, 3).contiguous()
+    relcat = torch.empty((176, 64), dtype=torch.bfloat16, device=dev)
+    _lib.check(L.bseg_pack_relcat(_lib.ptr(rel_h), _lib.ptr(rel_w), _lib.ptr(relcat), _lib.stream_ptr()))
+    out = torch.empty((nseq, T, 1024), dtype=torch.bfloat16, device=dev)
+    lse = torch.empty((nseq, 16, T), dtype=torch.float32, device=dev)
+    _lib.check(L.bseg_attention_fwd_lse(_lib.ptr(qb), _lib.ptr(kb), _lib.ptr(vt), _lib.ptr(relcat), _lib.ptr(out),
+                                        _lib.ptr(lse), nseq, _lib.stream_ptr()), "attention_fwd_lse")
+    nbytes = int(L.bseg_attention_bwd_scratch_bytes(nseq))
+    scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    base = (scratch.data_ptr() + 255) // 256 * 256
+    dqkv = torch.zeros((nseq * T, 3072), dtype=torch.bfloat16, device=dev)
+    dob = d_out.to(torch.bfloat16).contiguous()
+    _lib.check(L.bseg_attention_bwd(_lib.ptr(qb), _lib.ptr(kb), _lib.ptr(vt), _lib.ptr(out),
+                                    _lib.ptr(dob), _lib.ptr(lse), _lib.ptr(relcat),
+                                    _lib.ptr(dqkv), nseq, C.c_void_p(base), C.c_size_t(nbytes), _lib.stream_ptr()),
+               "attention_bwd")
+    torch.cuda.synchronize()
+    got = dqkv.float().reshape(nseq, T, 3, 16, 64).permute(2, 0, 3, 1, 4)  # [3, nseq, 16, T, 64]
+    out_got = out.float().reshape(nseq, T, 16, 64).permute(0, 2, 1, 3)
+    r_o = rel_l2(out_got, out_w)
+    r_q, r_k, r_v = rel_l2(got[0], dq_w), rel_l2(got[1], dk_w), rel_l2(got[2], dv_w)
+    print(f"[attention bwd nseq={nseq} q*{qscale} rel*{relscale}] out={r_o:.3e} dq={r_q:.3e} dk={r_k:.3e} dv={r_v:.3e}")
+    if max(r_q, r_k, r_v) > 1.5e-2:
+        for name, a, b in (("dq", got[0], dq_w), ("dk", got[1], dk_w), ("dv", got[2], dv_w)):
+            per_head = (a - b).norm(dim=(2, 3)) / b.norm(dim=(2, 3))
+            tiles = ((a - b)[:, :, :1536].reshape(nseq, 16, 12, 128, 64).norm(dim=(3, 4)) /
+                     b[:, :, :1536].reshape(nseq, 16, 12, 128, 64).norm(dim=(3, 4)))
+            print(name, "per-head:", [f"{x:.2e}" for x in per_head.flatten()[:16].tolist()])
+            print(name, "per-128-row tile (head 0):", [f"{x:.2e}" for x in tiles[0, 0].tolist()])
+    assert r_o < 1e-2
+    assert r_q < 1.5e-2 and r_k < 1.5e-2 and r_v < 1.5e-2  # bf16 P / dS operands, fp32 accumulation
+
+
+def test_decoder_head_backward(dev):
+    """conv1x1 <- GELU <- LN(C) <- conv3x3 backward for the query half vs autograd."""
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 1, 896, 448
+    x = bf16r(torch.randn((B, 64, H, W), generator=g)).to(dev).requires_grad_(True)
+    conv_w = bf16r(torch.randn((64, 64, 3, 3), generator=g) * 0.05).to(dev)
+    conv_b = (torch.randn(64, generator=g) * 0.1).to(dev)
+    ln_w = (1 + 0.2 * torch.randn(64, generator=g)).to(dev)
+    ln_b = (0.1 * torch.randn(64, generator=g)).to(dev)
+    head_w = (torch.randn((3, 64, 1, 1), generator=g) * 0.2).to(dev)
+    head_b = torch.randn(3, generator=g).to(dev)
+    d_pred = torch.zeros((B, 3, H, W), device=dev)
+    d_pred[:, :, 448:] = torch.randn((B, 3, 448, W), generator=g).to(dev)
+    y = F.conv2d(x, conv_w, conv_b, padding=1)
+    y = F.layer_norm(y.permute(0, 2, 3, 1), (64,), ln_w, ln_b, 1e-6).permute(0, 3, 1, 2)
+    y = F.conv2d(F.gelu(y), head_w, head_b)
+    (dx,) = torch.autograd.grad(y, x, d_pred)
+    L = _lib.lib()
+    x_nhwc = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    w9 = torch.empty((9, 64, 64), dtype=torch.bfloat16, device=dev)
+    w9b = torch.empty_like(w9)
+    _lib.check(L.bseg_pack_conv_w9(_lib.ptr(conv_w), _lib.ptr(w9), _lib.stream_ptr()))
+    _lib.check(L.bseg_pack_conv_w9_dgrad(_lib.ptr(w9), _lib.ptr(w9b), _lib.stream_ptr()))
+    d_conv = torch.empty((B, H - 448, W, 64), dtype=torch.bfloat16, device=dev)
+    rows = torch.zeros((B * T, 16384), dtype=torch.bfloat16, device=dev)
+    hw = head_w.reshape(3, 64).contiguous()
+    _lib.check(L.bseg_decoder_head_bwd(_lib.ptr(x_nhwc), _lib.ptr(w9), _lib.ptr(w9b), _lib.ptr(conv_b), _lib.ptr(ln_w),
+                                       _lib.ptr(ln_b), _lib.ptr(hw), _lib.ptr(head_b),
+                                       _lib.ptr(d_pred), _lib.ptr(d_conv), _lib.ptr(rows), B, H, W, 448, 1e-6,
+                                       _lib.stream_ptr()), "decoder_head_bwd")
+    torch.cuda.synchronize()
+    # rows [B*T, (py*16+px)*64 + c] -> NCHW
+    got = rows.float().reshape(B, 56, 28, 16, 16, 64).permute(0, 5, 1, 3, 2, 4).reshape(B, 64, H, W)
+    assert float(dx[:, :, :447].abs().max()) == 0.0  # the gradient lives in image rows >= 447 only
+    r = rel_l2(got[:, :, 432:], dx[:, :, 432:])
+    print(f"[decoder head bwd] rel-L2={r:.3e}")
+    assert float(got[:, :, :432].abs().max()) == 0.0
+    assert r < 1.5e-2
+
+
+SMALL = dict(num_layers=5, merge_index=1, intermediate=(1, 2, 3, 4))
+
+
+def _loss_ref(pred, labels, yes, beta=0.01):
+    """src/model.py:40-64 at B=1 semantics per sample (per-sample variant)."""
+    lab = torch.cat([torch.zeros_like(labels), labels], dim=2)
+    keep = torch.cat([torch.zeros_like(yes), yes], dim=1)[:, None].expand(-1, 3, -1, -1).float()
+    l = F.smooth_l1_loss(pred, lab, reduction="none", beta=beta)
+    return (l * keep).sum() / keep.sum()
+
+
+@pytest.mark.parametrize("batch", [1, 2])
+def test_prompt_gradient_small_model(dev, batch):
+    """d(loss)/d(prompt_pixel_values) through the whole backbone: 5-layer stress-initialised model, HF autograd
+    (fp32, CPU) vs bseg_forward_train + bseg_backward_to_prompt behind the torch.autograd.Function."""
+    from beach_seg_b200 import ops
+    from beach_seg_b200.seggpt import SegGptB200
+
+    hf = make_reference_model(seed=1, stress=True, **SMALL)
+    model = SegGptB200.from_hf(hf, device=dev)
+    px, ppx, pm = synth.model_inputs(batch=batch, seed=31)
+    labels = synth.model_inputs(batch=batch, seed=77)[2]
+    yes = (synth.blocky_mask(batch, seed=78) != 0)
+    # ---- reference ----
+    ppx_ref = ppx.clone().requires_grad_(True)
+    pred_ref = hf(pixel_values=px, prompt_pixel_values=ppx_ref, prompt_masks=pm, embedding_type="instance").pred_masks
+    loss_ref = _loss_ref(pred_ref, labels, yes)
+    (d_pred_ref,) = torch.autograd.grad(loss_ref, pred_ref, retain_graph=True)
+    (g_ref,) = torch.autograd.grad(loss_ref, ppx_ref)
+    # ---- ours: (a) the backward alone, fed with the reference's d(loss)/d(pred_masks) ----
+    ppx_dev = ppx.to(dev).requires_grad_(True)
+    out = model(pixel_values=px.to(dev), prompt_pixel_values=ppx_dev, prompt_masks=pm.to(dev),
+                embedding_type="instance")
+    r_pred = rel_l2(out.pred_masks.detach().cpu(), pred_ref.detach())
+    out.pred_masks.backward(d_pred_ref.to(dev))
+    torch.cuda.synchronize()
+    g = ppx_dev.grad.cpu()
+    r = rel_l2(g, g_ref)
+    cos = F.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
+    # ---- (b) loss + backward end to end (our loss kernel on our pred_masks; smooth-L1 with beta = 0.01 is nearly a
+    # sign function, so a few d(pred) entries flip sign where |pred - label| is within the bf16 error) ----
+    ppx_dev2 = ppx.to(dev).requires_grad_(True)
+    out2 = model(pixel_values=px.to(dev), prompt_pixel_values=ppx_dev2, prompt_masks=pm.to(dev))
+    loss, grad = ops.smooth_l1_loss(out2.pred_masks.detach(), labels.to(dev), yes.to(dev), 0.01, per_sample=True,
+                                    want_grad=True)
+    out2.pred_masks.backward(grad)
+    torch.cuda.synchronize()
+    g2 = ppx_dev2.grad.cpu()
+    r2 = rel_l2(g2, g_ref)
+    cos2 = F.cosine_similarity(g2.flatten(), g_ref.flatten(), dim=0).item()
+    print(f"[prompt grad B={batch}] loss ref={loss_ref.item():.6f} ours={loss.item():.6f} pred rel-L2={r_pred:.3e} "
+          f"grad rel-L2={r:.3e} cos={cos:.6f} | end-to-end grad rel-L2={r2:.3e} cos={cos2:.6f} "
+          f"|g_ref|={g_ref.norm().item():.3e}")
+    assert r_pred < 1e-2
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    assert r < 3e-2 and cos > 0.999    # backward alone: bf16 operands, fp32 accumulation / residual gradient
+    assert r2 < 1e-1 and cos2 > 0.995  # including the sign flips of the near-L1 loss gradient
