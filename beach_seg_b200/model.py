@@ -1,10 +1,11 @@
 """Mirror of the reference's `src/model.py`: `SegGptLoss` and `PromptModel` with the same method names, argument
 meaning and attributes, running on the kernels of libbseg.so.  Lightning is not a dependency here: `PromptModel` is a
 plain `torch.nn.Module` exposing the hooks the reference's scripts call (`post_init`, `create_trainable_params`,
-`forward`, `prepare_prompt`, `create_palette`, `process_pred_masks`, `training_step`, `configure_optimizers`).
-
-Not built yet: the gradient of the backbone w.r.t. the prompt pixels, so `training_step`
-computes the forward loss but the loss does not carry a graph to the prompt parameters (it raises if asked to)."""
+`forward`, `prepare_prompt`, `create_palette`, `process_pred_masks`, `training_step`, `validation_step`,
+`configure_optimizers`).  `training_step` returns a loss whose graph reaches the prompt parameters through the
+CUDA backward (`bseg_backward_to_prompt`); `sync_prompt_grads` is the explicit data-parallel exchange that stands in
+for Lightning's implicit DDP; `fit` is the 30-line loop that stands in for `Trainer.fit`
+(src/train.py:97-115)."""
 from __future__ import annotations
 
 from typing import Any, Optional
@@ -48,6 +49,29 @@ class SegGptLoss(torch.nn.Module):
         return ops.smooth_l1_loss(pred_masks, labels, yesdata, self.beta, per_sample=self.per_sample)
 
 
+def allreduce_prompt_grads(params, group=None) -> None:
+    """Mean all-reduce of the prompt gradients over the data-parallel ranks: ONE collective over a dense
+    [N_prompts, 3*H*W + 1] fp32 buffer (the last column counts the ranks that touched a prompt; 2.4 MB per prompt,
+    NCCL over NVLink on the GPU box, gloo in the CPU tests).  Prompts no rank selected this step keep `grad = None`,
+    so AdamW skips them exactly as it does at world size 1 -- with Lightning's default DDP the reference would instead
+    fail on the unused parameters."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or not params:
+        return
+    per = params[0].numel()
+    buf = torch.zeros((len(params), per + 1), dtype=torch.float32, device=params[0].device)
+    for i, p in enumerate(params):
+        if p.grad is not None:
+            buf[i, :per] = p.grad.reshape(-1)
+            buf[i, per] = 1.0
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    world = dist.get_world_size(group)
+    used = (buf[:, per] > 0).tolist()
+    for i, p in enumerate(params):
+        p.grad = (buf[i, :per] / world).reshape(p.shape).clone() if used[i] else None
+
+
 class InferenceAug:
     """Stand-in for the reference datamodule's `aug` pipeline (src/data.py:226-234): CenterCrop(inpt_size) is the
     identity on inpt_size inputs, Normalize(mean, std) is applied to the image entry; masks pass through."""
@@ -64,12 +88,13 @@ class InferenceAug:
 
 
 class PromptModel(torch.nn.Module):
-    def __init__(self, conf: BeachSegConfig, device: str | torch.device = "cuda:0"):
+    def __init__(self, conf: BeachSegConfig, device: str | torch.device = "cuda:0", model=None):
         super().__init__()
         self.conf = conf
         self.num_classes = len(conf.classes)
         self.nodata_idx = 0
-        self.model = load_model(conf.checkpoint, device=device)
+        # `model`: an already packed backbone to share (the reference always loads its own, src/model.py:77)
+        self.model = model if model is not None else load_model(conf.checkpoint, device=device)
         self._device = torch.device(device)
         self.g = torch.Generator()  # the reference seeds a generator on model.device (cpu there)
         self.g.manual_seed(conf.seed)
@@ -130,7 +155,9 @@ class PromptModel(torch.nn.Module):
         else:
             idx = list(batch_idxes)
         prompt_batch = {k: [v[i] for i in idx] for k, v in self.prompt_batch.items()}
-        prompt_batch["image"] = torch.stack([p.detach() for p in prompt_batch["image"]], dim=0).to(self.device)
+        # training: the stack keeps the graph to the selected prompt parameters (src/model.py:194)
+        prompt_batch["image"] = torch.stack([p if train else p.detach() for p in prompt_batch["image"]],
+                                            dim=0).to(self.device)
         prompt_batch["mask"] = torch.stack([torch.as_tensor(m) for m in prompt_batch["mask"]], dim=0).to(self.device)
         prompt_batch = (self.train_aug if train else self.aug)(prompt_batch)
         prompt_color_mask_norm = ops.colorize_norm(prompt_batch["mask"], batch_palette.to(self.device))
@@ -140,24 +167,72 @@ class PromptModel(torch.nn.Module):
     def create_palette(self, batch_size: int, train: bool):
         return _create_palette(self.num_classes, batch_size, train, self.device)
 
-    # ---- src/model.py:233-269 (forward + loss; the graph to the prompt parameters is not built yet) ----
+    # ---- src/model.py:233-269 ----
     def training_step(self, batch: dict, batch_idx: int = 0) -> torch.Tensor:
         B = batch["mask"].shape[0]
         batch_palette, batch_palette_norm = self.create_palette(B, train=True)
         color_mask_norm = ops.colorize_norm(batch["mask"].to(self.device), batch_palette)
         prompt_idx = torch.randint(0, len(self.prompt_params_list), (B,), generator=self.g)
         prompt_batch, prompt_masks = self.prepare_prompt(prompt_idx, batch_palette, train=True)
-        with torch.no_grad():
-            out = self.model(pixel_values=batch["image"].to(self.device), labels=color_mask_norm,
-                             prompt_pixel_values=prompt_batch["image"], prompt_masks=prompt_masks,
-                             embedding_type="instance")
+        out = self.model(pixel_values=batch["image"].to(self.device), labels=color_mask_norm,
+                         prompt_pixel_values=prompt_batch["image"], prompt_masks=prompt_masks,
+                         embedding_type="instance")
+        self.last_pred = self.process_pred_masks(out.pred_masks.detach(), batch_palette_norm)  # the F1 metric's input
+        self.last_prompt_idx = prompt_idx
         return self.loss_fn(out.pred_masks, color_mask_norm, (batch["mask"] != 0).to(self.device))
 
-    # ---- src/model.py:385-428 (AdamW + cosine per epoch; plain torch, negligible cost) ----
-    def configure_optimizers(self, steps_per_epoch: Optional[int] = None):
-        eff_bs = self.conf.batch_size * self.conf.grad_accum_steps * max(self.conf.world_size, 1)
-        lr = self.conf.lr * (eff_bs / self.conf.base_lr_batch_size) ** 0.5
+    # ---- src/model.py:271-308 ----
+    @torch.no_grad()
+    def validation_step(self, batch: dict, batch_idx: int = 0, dataloader_idx: int = 0) -> torch.Tensor:
+        B = batch["mask"].shape[0]
+        batch_palette, batch_palette_norm = self.create_palette(B, train=True)
+        color_mask_norm = ops.colorize_norm(batch["mask"].to(self.device), batch_palette)
+        prompt_batch, prompt_masks = self.prepare_prompt(batch["crop_idx"], batch_palette, train=False)
+        out = self.model(pixel_values=batch["image"].to(self.device), labels=color_mask_norm,
+                         prompt_pixel_values=prompt_batch["image"], prompt_masks=prompt_masks,
+                         embedding_type="instance")
+        self.last_pred = self.process_pred_masks(out.pred_masks, batch_palette_norm)
+        return self.loss_fn(out.pred_masks, color_mask_norm, (batch["mask"] != 0).to(self.device))
+
+    # ---- data-parallel exchange (Lightning's implicit DDP in the reference, src/train.py:96-107) ----
+    def sync_prompt_grads(self, group=None) -> None:
+        allreduce_prompt_grads(list(self.prompt_params_list), group)
+
+    # ---- src/model.py:385-428 (AdamW, optional linear warm-up, cosine per epoch; plain torch, negligible cost) ----
+    def configure_optimizers(self):
+        from torch.optim.lr_scheduler import CosineAnnealingLR, LambdaLR, SequentialLR
+
+        global_bs = self.conf.batch_size * max(self.conf.world_size, 1) * self.conf.grad_accum_steps
+        ratio = (global_bs / self.conf.base_lr_batch_size) ** 0.5
+        lr, init_lr, min_lr = self.conf.lr * ratio, self.conf.init_lr * ratio, self.conf.min_lr * ratio
+        warmup = self.conf.warmup_epochs
+        if self.conf.optimizer != "adamw":
+            raise RuntimeError(f"Unexpected optimizer {self.conf.optimizer}")
         opt = torch.optim.AdamW(self.parameters(), lr=lr)
-        sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=max(self.conf.epochs, 1),
-                                                           eta_min=self.conf.min_lr)
-        return {"optimizer": opt, "lr_scheduler": sched}
+        scheds, milestones = [], []
+        if warmup:
+            scheds.append(LambdaLR(opt, [lambda epoch: ((lr - init_lr) * (epoch / warmup) + init_lr) / lr]))
+            milestones.append(warmup)
+        if self.conf.scheduler != "cosine":
+            raise RuntimeError(f"Unexpected scheduler {self.conf.scheduler}")
+        scheds.append(CosineAnnealingLR(opt, self.conf.epochs, min_lr))
+        return {"optimizer": opt, "lr_scheduler": {"scheduler": SequentialLR(opt, scheds, milestones),
+                                                   "interval": "epoch", "frequency": 1}}
+
+    # ---- stand-in for Trainer.fit (src/train.py:97-115): step, backward, exchange, AdamW, cosine per epoch ----
+    def fit(self, batches, epochs: Optional[int] = None, on_step=None):
+        cfg = self.configure_optimizers()
+        opt, sched = cfg["optimizer"], cfg["lr_scheduler"]["scheduler"]
+        losses = []
+        for _ in range(self.conf.epochs if epochs is None else epochs):
+            for i, batch in enumerate(batches):
+                loss = self.training_step(batch, i)
+                loss.backward()
+                self.sync_prompt_grads()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+                losses.append(loss.detach())
+                if on_step is not None:
+                    on_step(i, loss)
+            sched.step()
+        return torch.stack(losses).cpu() if losses else torch.empty(0)

@@ -29,6 +29,9 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 TILES_PER_STEP = 64
+TRAIN_BATCH = 32   # BASELINE.json configs[3]: train step, batch 32 of 512^2 tiles per GPU
+TRAIN_PROMPTS = 32
+TRAIN_FLOP_PER_TILE = 3.456e12  # forward + dgrad-only backward (no wgrad: the backbone is frozen)
 CROP = 512
 FWD_FLOP_PER_TILE = 1.5897e12  # BASELINE.md §3 / SURVEY §8(d): algorithmic forward FLOPs per 448-path tile
 CATS = ("gemm", "attention", "layernorm", "decoder_head", "ingest", "decode", "vote", "elementwise", "loss")
@@ -148,6 +151,69 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# train-step leg of our arm
+# ------------------------------------------------------------------------------------------------------------
+def train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrier, timed, L, peaks):
+    from beach_seg_b200 import ops, synth
+    from beach_seg_b200.config import BeachSegConfig
+    from beach_seg_b200.model import PromptModel
+
+    conf = BeachSegConfig(checkpoint="random-init:0", batch_size=TRAIN_BATCH, world_size=world, epochs=1)
+    pmodel = PromptModel(conf, device=dev, model=model)
+    model.check_grad_support = False  # the loss kernel's gradient is zero in the prompt half by construction
+    prompt_img01 = synth.smooth_image(TRAIN_PROMPTS, 5000)
+    prompt_cls = synth.blocky_mask(TRAIN_PROMPTS, 5001)
+
+    class DM:
+        prompt_imgs = [{"image": prompt_img01[i], "mask": prompt_cls[i][None], "crop_idx": i}
+                       for i in range(TRAIN_PROMPTS)]
+
+    pmodel.create_trainable_params(DM)
+    pmodel.g.manual_seed(conf.seed + rank)  # each rank draws its own prompt indices
+    opt = pmodel.configure_optimizers()["optimizer"]
+    labels = synth.blocky_mask(TRAIN_BATCH, 4000 + rank)[:, None].to(dev)
+    tboxes = boxes[:TRAIN_BATCH]
+
+    def step():
+        tiles = ops.ingest_tiles(scene, nodata, stats, tboxes, CROP)          # the step's 32 tiles, 512 -> 448
+        loss = pmodel.training_step({"image": tiles["image"], "mask": labels}, 0)
+        loss.backward()
+        pmodel.sync_prompt_grads()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for _ in range(2):
+        loss = step()
+    ms = timed(step, args.train_steps)
+    # per-category device time of the same steps
+    L.bseg_profile_enable(1)
+    barrier()
+    for _ in range(args.train_steps):
+        loss = step()
+    torch.cuda.synchronize()
+    n = len(CATS)
+    pms, pl, pw, pb = (C.c_double * n)(), (C.c_longlong * n)(), (C.c_double * n)(), (C.c_double * n)()
+    L.bseg_profile_collect(pms, pl, pw, pb)
+    L.bseg_profile_enable(0)
+    tot = sum(pms[i] for i in range(n))
+    kern = {name: {"ms_per_iter": pms[i] / args.train_steps, "launches_per_iter": pl[i] / args.train_steps,
+                   "share": pms[i] / tot if tot else None,
+                   "tflops": pw[i] / (pms[i] * 1e-3) / 1e12 if pw[i] and pms[i] else None}
+            for i, name in enumerate(CATS) if pl[i]}
+    ms_iter = ms / args.train_steps
+    tflops = TRAIN_BATCH * TRAIN_FLOP_PER_TILE / (ms_iter * 1e-3) / 1e12
+    return {"metric": "train step ms/iter", "ms_per_iter": ms_iter, "batch_per_gpu": TRAIN_BATCH, "n_gpus": world,
+            "global_batch": TRAIN_BATCH * world, "tiles_per_s": world * TRAIN_BATCH / (ms_iter * 1e-3),
+            "steps": args.train_steps, "loss": float(loss), "prompts": TRAIN_PROMPTS,
+            "loss_semantics": "SegGptLoss as written in the reference (BxB keep-mask broadcast, src/model.py:40-64)",
+            "includes": "ingest 512->448, colourise, forward (activations kept), palette decode, loss fwd+bwd, "
+                        "backward to the prompts, prompt-grad all-reduce (NCCL, world>1), AdamW step",
+            "model_tflops_per_gpu": tflops, "model_frac_of_tensor_peak": tflops / peaks["tensor"],
+            "grad_allreduce_bytes": TRAIN_PROMPTS * (3 * 448 * 448 + 1) * 4 if world > 1 else 0, "kernels": kern}
+
+
+# ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
 def main():
@@ -158,6 +224,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tiles", type=int, default=2)
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step leg (BASELINE configs[3])")
+    ap.add_argument("--train-steps", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -290,6 +358,18 @@ def main():
                 "frac": gemm_tflops / peaks["tensor"], "peak_source": peaks["source"] + " bf16_tflops_sustained",
                 "traffic": None, "avg_launch_ms": pms[g] / max(pl[g], 1),
                 "flop_per_launch": pw[g] / max(pl[g], 1)}
+    tfile = ROOT / "profiles" / "r01_gemm_traffic.json"
+    if tfile.exists():  # DRAM bytes per launch from the committed `ncu --set full` capture of the layer GEMMs
+        t = json.loads(tfile.read_text())
+        roofline["traffic"] = t["per_launch_avg_dram_bytes"]
+        roofline["traffic_algorithmic_bytes"] = t["per_launch_avg_algorithmic_bytes"]
+        roofline["traffic_source"] = t["source"] + " (4 encoder-layer GEMM launches, M=200704)"
+
+    # ---- train-step leg (BASELINE configs[3]): ingest -> PromptModel.training_step -> backward -> prompt-grad
+    # all-reduce -> AdamW, batch 32 per GPU (weak scaling), ms/iter = max over ranks ----
+    train = None
+    if not args.no_train:
+        train = train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrier, timed, L, peaks)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -311,7 +391,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": int(scene_host.numel() * 2),
                     "d2h_bytes_per_step": int(cls_host.numel()), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernels, "gemm_modes": gemm_modes,
+            "kernels": kernels, "gemm_modes": gemm_modes, "train": train,
             "model_tflops": value / world * FWD_FLOP_PER_TILE / 1e12,
             "model_frac_of_tensor_peak": value / world * FWD_FLOP_PER_TILE / 1e12 / peaks["tensor"],
         }

@@ -292,3 +292,24 @@ class AccumulatorRef:
 
     def argmax(self) -> np.ndarray:
         return np.argmax(self.counter, axis=2)
+
+
+def training_step_ref(hf_model, prompt_params, prompt_masks_cls, batch_image, batch_mask, generator, beta=0.01,
+                      num_classes: int = 4, per_sample: bool = False):
+    """PromptModel.training_step (src/model.py:233-269) with the infer-style augmentation (Normalize only; the kornia
+    train augmentations are stochastic host ops outside the hot path): random palette from the GLOBAL torch RNG,
+    label colourise + normalise, prompt choice from the module's private generator, prompt gather, HF forward, the
+    reference's own SegGptLoss.  `prompt_params`: list of [3,448,448] tensors in [0,1] (requires_grad);
+    `prompt_masks_cls`: list of [1,448,448] class-id tensors; batch_mask: [B,1,448,448].  Returns (loss, prompt_idx)."""
+    B = batch_mask.shape[0]
+    batch_palette, _ = create_palette(num_classes, B, train=True)                       # :235
+    color_mask_norm = normalize(torch_apply_mask_rgb(batch_palette, batch_mask))        # :238-239
+    prompt_idx = torch.randint(0, len(prompt_params), (B,), generator=generator)        # :242
+    idx = prompt_idx.flatten().tolist()
+    prompt_img = normalize(torch.stack([prompt_params[i] for i in idx], dim=0))         # :194 + aug (Normalize)
+    prompt_mask = torch.stack([prompt_masks_cls[i] for i in idx], dim=0)
+    prompt_color = normalize(torch_apply_mask_rgb(batch_palette, prompt_mask))          # :210-211
+    out = hf_model(pixel_values=batch_image, labels=color_mask_norm, prompt_pixel_values=prompt_img,
+                   prompt_masks=prompt_color, embedding_type="instance")                # :245-251
+    loss = seggpt_loss(out.pred_masks, color_mask_norm, batch_mask != 0, beta, per_sample=per_sample)  # :255
+    return loss, prompt_idx

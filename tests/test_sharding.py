@@ -64,6 +64,32 @@ def test_two_rank_canvas_merge_equals_single_process(tmp_path):
     assert np.array_equal(merged, acc.counter)
 
 
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from beach_seg_b200.model import allreduce_prompt_grads
+
+    # 4 prompts; rank 0 touched prompts 0 and 1, rank 1 touched prompts 1 and 3; prompt 2 is unused everywhere
+    params = [torch.nn.Parameter(torch.zeros(3, 8, 8)) for _ in range(4)]
+    touched = [(0, 1), (1, 3)][rank]
+    for i in touched:
+        params[i].grad = torch.full((3, 8, 8), float(10 * rank + i + 1))
+    allreduce_prompt_grads(params)
+    if rank == 0:
+        torch.save([None if p.grad is None else p.grad.clone() for p in params], Path(out_dir) / "grads.pt")
+    dist.destroy_process_group()
+
+
+def test_two_rank_prompt_gradient_allreduce(tmp_path):
+    """The train path's one collective: dense mean all-reduce, untouched prompts keep grad None (AdamW skips them)."""
+    mp.spawn(_grad_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    g = torch.load(tmp_path / "grads.pt")
+    assert g[2] is None
+    assert torch.equal(g[0], torch.full((3, 8, 8), 1.0 / 2))            # rank 0 only: (0*10 + 0 + 1) / world
+    assert torch.equal(g[1], torch.full((3, 8, 8), (2.0 + 12.0) / 2))   # both ranks
+    assert torch.equal(g[3], torch.full((3, 8, 8), 14.0 / 2))           # rank 1 only
+
+
 def test_create_palette_matches_reference_rng_stream():
     """Drop-in: same torch.manual_seed -> same random palette as the reference's CPU path (src/model.py:215-231)."""
     torch.manual_seed(42)
