@@ -63,8 +63,13 @@ constexpr int kStagesK = 3;
 constexpr int kTileBytes = 64 * 128;       // 8192: [64 x 64] bf16
 constexpr int kTabStride = 68;             // floats per table row (64 + 4: LDS.128 rows land on distinct banks)
 constexpr int kBhRows = 6;                 // token rows a 128-key tile can touch
-constexpr int kTabBytes = (kBhRows + kGridW) * kTabStride * 4 + 2 * kQB * 4;  // bh, bw, lse, D
-constexpr int kStageKBytes = 4 * kTileBytes + ((kTabBytes + 1023) / 1024) * 1024;
+// per-stage tables, each a TMA box at a 128-byte aligned offset: bh [6][68], bw [28][68], lse [64], D [64] (fp32)
+constexpr int kTabBhOff = 0;
+constexpr int kTabBwOff = (kBhRows * kTabStride * 4 + 127) / 128 * 128;                 // 1664
+constexpr int kTabLseOff = kTabBwOff + (kGridW * kTabStride * 4 + 127) / 128 * 128;     // 9344
+constexpr int kTabDOff = kTabLseOff + kQB * 4;                                          // 9600
+constexpr int kTabTxBytes = (kBhRows + kGridW) * kTabStride * 4 + 2 * kQB * 4;          // bytes the four boxes carry
+constexpr int kStageKBytes = 4 * kTileBytes + ((kTabDOff + kQB * 4 + 1023) / 1024) * 1024;
 constexpr int kKOffK = 0;
 constexpr int kKOffV = kKOffK + kKTile * 128;
 constexpr int kKOffRing = kKOffV + kKTile * 128;
@@ -440,8 +445,9 @@ __global__ void __launch_bounds__(abwd::kThreads, 1)
 attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                          const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                          const __grid_constant__ CUtensorMap tmap_qt, const __grid_constant__ CUtensorMap tmap_dot,
-                         const float* __restrict__ lse, const float* __restrict__ Dvec,
-                         const float* __restrict__ bias_tab, __nv_bfloat16* __restrict__ dqkv, int heads) {
+                         const __grid_constant__ CUtensorMap tmap_tab6, const __grid_constant__ CUtensorMap tmap_tab28,
+                         const __grid_constant__ CUtensorMap tmap_lse,
+                         const __grid_constant__ CUtensorMap tmap_dvec, __nv_bfloat16* __restrict__ dqkv, int heads) {
   using namespace abwd;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -450,7 +456,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
   uint8_t* sRing = smem + kKOffRing;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKOffBar);
   uint64_t* kv_full = bars + 0;
-  uint64_t* full = bars + 1;        // [3]  TMA bytes + 32 table-loader lanes
+  uint64_t* full = bars + 1;        // [3]
   uint64_t* empty = bars + 4;       // [3]
   uint64_t* sdp_full = bars + 7;    // [2]
   uint64_t* pds_full = bars + 9;    // [2]
@@ -470,9 +476,13 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
     tma_prefetch_desc(&tmap_do);
     tma_prefetch_desc(&tmap_qt);
     tma_prefetch_desc(&tmap_dot);
+    tma_prefetch_desc(&tmap_tab6);
+    tma_prefetch_desc(&tmap_tab28);
+    tma_prefetch_desc(&tmap_lse);
+    tma_prefetch_desc(&tmap_dvec);
     mbar_init(kv_full, 1);
     for (int i = 0; i < kStagesK; ++i) {
-      mbar_init(&full[i], 1 + 32);
+      mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -499,11 +509,19 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
           const int st = j % kStagesK;
           if (j >= kStagesK) mbar_wait(&empty[st], ((j / kStagesK) & 1) ^ 1);
           uint8_t* base = sRing + st * kStageKBytes;
-          mbar_arrive_expect_tx(&full[st], 4 * kTileBytes);
+          mbar_arrive_expect_tx(&full[st], 4 * kTileBytes + kTabTxBytes);
           tma_load_3d(base, &tmap_q, &full[st], 0, j * kQB, sh);
           tma_load_4d(base + kTileBytes, &tmap_do, &full[st], 0, j * kQB, head, seq);
           tma_load_3d(base + 2 * kTileBytes, &tmap_qt, &full[st], j * kQB, 0, sh);
           tma_load_3d(base + 3 * kTileBytes, &tmap_dot, &full[st], j * kQB, 0, sh);
+          // bias rows (x log2 e) of the block's queries: the 6 bh rows from kh_lo (rows past the token grid hold bw
+          // data and are only read by dead key rows) and the 28 bw rows; then lse and D.  Box rows are 68 floats
+          // (4 spill-over columns) so that LDS.128 of neighbouring rows lands on distinct banks.
+          uint8_t* tabs = base + 4 * kTileBytes;
+          tma_load_3d(tabs + kTabBhOff, &tmap_tab6, &full[st], j * kQB, kh_lo, sh);
+          tma_load_3d(tabs + kTabBwOff, &tmap_tab28, &full[st], j * kQB, kGridH, sh);
+          tma_load_2d(tabs + kTabLseOff, &tmap_lse, &full[st], j * kQB, sh);
+          tma_load_2d(tabs + kTabDOff, &tmap_dvec, &full[st], j * kQB, sh);
         }
       }
     } else if (warp == 1) {
@@ -552,34 +570,6 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
         }
         umma_commit(dkv_done);
       }
-    } else if (warp == 2) {
-      // ============================ table loader ============================
-      // per query block: 6 bh rows + 28 bw rows of the bias table (x log2 e), lse and D of the 64 queries
-      const float* tab = bias_tab + static_cast<long long>(sh) * kBiasRows * kT;
-      for (int j = 0; j < kNumQB; ++j) {
-        const int st = j % kStagesK;
-        if (j >= kStagesK) mbar_wait(&empty[st], ((j / kStagesK) & 1) ^ 1);
-        float* dst = reinterpret_cast<float*>(sRing + st * kStageKBytes + 4 * kTileBytes);
-        const int q = j * kQB + 2 * lane;
-        const bool ok = q < kT;  // T is even: q and q+1 are valid together
-#pragma unroll 2
-        for (int row = 0; row < kBhRows + kGridW; ++row) {
-          int src_row = row < kBhRows ? kh_lo + row : kGridH + (row - kBhRows);
-          if (row < kBhRows && src_row >= kGridH) src_row = kGridH - 1;
-          float2 v = make_float2(0.f, 0.f);
-          if (ok) v = *reinterpret_cast<const float2*>(tab + src_row * kT + q);
-          *reinterpret_cast<float2*>(dst + row * kTabStride + 2 * lane) = v;
-        }
-        float2 l = make_float2(INFINITY, INFINITY), dd = make_float2(0.f, 0.f);
-        if (ok) {
-          l = *reinterpret_cast<const float2*>(lse + static_cast<long long>(sh) * kT + q);
-          dd = *reinterpret_cast<const float2*>(Dvec + static_cast<long long>(sh) * kT + q);
-        }
-        float* tail = dst + (kBhRows + kGridW) * kTabStride;
-        *reinterpret_cast<float2*>(tail + 2 * lane) = l;
-        *reinterpret_cast<float2*>(tail + kQB + 2 * lane) = dd;
-        mbar_arrive(&full[st]);
-      }
     }
   } else {
     // ============================ elementwise warps ============================
@@ -596,10 +586,10 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
     for (int j = 0; j < kNumQB; ++j) {
       const int st = j % kStagesK, buf = j & 1;
       const float* tabs = reinterpret_cast<const float*>(sRing + st * kStageKBytes + 4 * kTileBytes);
-      const float* bh_row = tabs + khi * kTabStride + g * 32;
-      const float* bw_row = tabs + (kBhRows + kw) * kTabStride + g * 32;
-      const float* lse_s = tabs + (kBhRows + kGridW) * kTabStride + g * 32;
-      const float* d_s = lse_s + kQB;
+      const float* bh_row = tabs + kTabBhOff / 4 + khi * kTabStride + g * 32;
+      const float* bw_row = tabs + kTabBwOff / 4 + kw * kTabStride + g * 32;
+      const float* lse_s = tabs + kTabLseOff / 4 + g * 32;
+      const float* d_s = tabs + kTabDOff / 4 + g * 32;
       mbar_wait(&full[st], (j / kStagesK) & 1);
       mbar_wait(&sdp_full[buf], (j >> 1) & 1);
       tc_fence_after();
@@ -674,7 +664,8 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
   BSEG_REQUIRE(nseq > 0 && heads > 0, "attention_bwd: empty problem");
   const uint64_t nsh = static_cast<uint64_t>(nseq) * heads;
   const uint64_t D = static_cast<uint64_t>(heads) * 64;
-  CUtensorMap tq128, tq64, tk128, tk112, tv128, tv112, tkt, tqt, tdot, tdo128, tdo64, trel, trelt;
+  CUtensorMap tq128, tq64, tk128, tk112, tv128, tv112, tkt, tqt, tdot, tdo128, tdo64, trel, trelt, ttab6, ttab28, tlse,
+      tdvec;
   int rc;
   {
     uint64_t dims[3] = {64, static_cast<uint64_t>(kT), nsh};
@@ -703,6 +694,19 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
     if ((rc = make_tmap_bf16(&tdo128, dO, 4, dims, strides, b128))) return rc;
     if ((rc = make_tmap_bf16(&tdo64, dO, 4, dims, strides, b64))) return rc;
   }
+  {
+    // bias table [nsh, 84, T] fp32 (written by the dq kernel), lse / D [nsh, T] fp32
+    uint64_t dims[3] = {static_cast<uint64_t>(kT), kBiasRows, nsh};
+    uint64_t strides[2] = {static_cast<uint64_t>(kT) * 4, static_cast<uint64_t>(kT) * kBiasRows * 4};
+    uint32_t b6[3] = {kTabStride, kBhRows, 1}, b28[3] = {kTabStride, kGridW, 1};
+    if ((rc = make_tmap_f32(&ttab6, bias_tab, 3, dims, strides, b6))) return rc;
+    if ((rc = make_tmap_f32(&ttab28, bias_tab, 3, dims, strides, b28))) return rc;
+    uint64_t dims2[2] = {static_cast<uint64_t>(kT), nsh};
+    uint64_t strides2[1] = {static_cast<uint64_t>(kT) * 4};
+    uint32_t b64[2] = {kQB, 1};
+    if ((rc = make_tmap_f32(&tlse, lse, 2, dims2, strides2, b64))) return rc;
+    if ((rc = make_tmap_f32(&tdvec, Dvec, 2, dims2, strides2, b64))) return rc;
+  }
   if ((rc = make_tmap_bf16_2d(&trel, relcat, 64, kRelRows, 64, 64, kRelRows))) return rc;
   if ((rc = make_tmap_bf16_2d(&trelt, relcat_t, 192, 64, 192, 64, 64))) return rc;
   static bool attr_set = false;
@@ -726,8 +730,8 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
   {
     dim3 grid((kT + kKTile - 1) / kKTile, heads, nseq);
     ProfScope prof(CAT_ATTENTION, pair * 64 * 2 * 4, static_cast<double>(nseq) * heads * kT * (64 * 2 * 8), stream);
-    attention_bwd_dkv_kernel<<<grid, kThreads, kKSmemBytes, stream>>>(tk128, tv128, tq64, tdo64, tqt, tdot, lse, Dvec,
-                                                                      bias_tab, dqkv, heads);
+    attention_bwd_dkv_kernel<<<grid, kThreads, kKSmemBytes, stream>>>(tk128, tv128, tq64, tdo64, tqt, tdot, ttab6,
+                                                                      ttab28, tlse, tdvec, dqkv, heads);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }

@@ -56,6 +56,28 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return 0;
 }
 
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  BSEG_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstrides[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
+                  gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BSEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed: CUresult=%d (rank=%d dims0=%llu box0=%u)",
+               static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]), box[0]);
+  return 0;
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }

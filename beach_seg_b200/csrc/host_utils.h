@@ -36,6 +36,10 @@ void set_error(const char* fmt, ...);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
 
+// The same for fp32 tensors, no swizzle (dense rows of box[0] floats in shared memory).
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
 inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                              uint32_t box_inner, uint32_t box_outer) {
   uint64_t dims[2] = {inner, outer};
