@@ -66,6 +66,9 @@ SIGNATURES = {
     "bseg_scene_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bseg_ingest_u16x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f3, _f3, _vp, _vp, _ll, _vp, _vp,
                                _vp]),
+    "bseg_preprocess_u8": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _f3, _f3, _vp, _vp]),
+    "bseg_colorize_resize_norm255": (_i, [_vp, _vp, _i, _f3, _f3, _vp, _vp, _i, _i, _i, _vp]),
+    "bseg_postprocess_semantic": (_i, [_vp, _vp, _i, _f3, _f3, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bseg_colorize_norm": (_i, [_vp, _vp, _i, _f3, _f3, _vp, _i, _i, _i, _vp]),
     "bseg_decode_palette": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bseg_mean_over_prompts": (_i, [_vp, _vp, _i, _i, _ll, _vp]),

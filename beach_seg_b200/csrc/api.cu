@@ -26,6 +26,20 @@ struct LayerPack {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// rows of output per CTA of the ingest / preprocess kernels: a full 16-row patch band when the source rows fit in smem
+void ingest_geometry(int crop, int* band_out, int* max_rows_out) {
+  const double scale = static_cast<double>(crop) / 448.0;
+  const double support = 2.0 * (scale < 1.0 ? 1.0 : scale);
+  int band = 16, max_rows = 0;
+  for (;;) {
+    max_rows = static_cast<int>(band * scale + 2 * support + 4);
+    if (3ull * max_rows * (crop + 448) <= 160 * 1024 || band == 1) break;
+    band /= 2;
+  }
+  *band_out = band;
+  *max_rows_out = max_rows;
+}
+
 // reversed + concatenated rel-pos tables (see attention.cu): rows 0..110 = rel_pos_h[110-i], 111 = 0,
 // rows 112..166 = rel_pos_w[54-(i-112)], rest 0
 __global__ void pack_relcat_kernel(const float* __restrict__ rel_h, const float* __restrict__ rel_w,
@@ -688,19 +702,41 @@ int bseg_ingest_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int 
                       int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,
                       long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, void* stream) {
   BSEG_REQUIRE(n_tiles >= 0 && crop > 0 && ksize > 0, "ingest: bad arguments");
-  // rows of output per CTA: a full 16-row patch band when the composite rows fit in shared memory
-  const double scale = static_cast<double>(crop) / 448.0;
-  const double support = 2.0 * (scale < 1.0 ? 1.0 : scale);
-  int band = 16;
-  int max_rows = 0;
-  for (;;) {
-    max_rows = static_cast<int>(band * scale + 2 * support + 4);
-    if (3ull * max_rows * (crop + 448) <= 160 * 1024 || band == 1) break;
-    band /= 2;
-  }
+  int band, max_rows;
+  ingest_geometry(crop, &band, &max_rows);
   return launch_ingest(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, band, max_rows, mean,
                        stdv, out_nchw, static_cast<__nv_bfloat16*>(out_patch), patch_tile_stride, out_u8, out_nodata,
                        static_cast<cudaStream_t>(stream));
+}
+
+int bseg_preprocess_u8(const uint8_t* images, int layout_chw, int n, int crop, const int32_t* coef,
+                       const int32_t* bounds, int ksize, int precision_bits, const float* mean255, const float* std255,
+                       float* out_nchw, void* stream) {
+  BSEG_REQUIRE(n >= 0 && crop > 0 && ksize > 0 && out_nchw != nullptr, "preprocess_u8: bad arguments");
+  int band, max_rows;
+  ingest_geometry(crop, &band, &max_rows);
+  return launch_preprocess_u8(images, layout_chw, n, crop, coef, bounds, ksize, precision_bits, band, max_rows, mean255,
+                              std255, out_nchw, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_colorize_resize_norm255(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean255,
+                                 const float* std255, const int32_t* resize_idx, float* out, int batch, int in_size,
+                                 int out_size, void* stream) {
+  BSEG_REQUIRE(batch > 0 && num_classes > 0 && in_size > 0 && out_size > 0, "colorize_resize_norm255: bad arguments");
+  BSEG_REQUIRE(resize_idx != nullptr || in_size == out_size, "colorize_resize_norm255: resize needs an index table");
+  return launch_colorize_resize_norm255(mask, palette, num_classes, mean255, std255, resize_idx, out, batch, in_size,
+                                        out_size, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_postprocess_semantic(const float* pred, const float* palette255, int num_classes, const float* mean,
+                              const float* stdv, uint8_t* out_u8, int64_t* out_i64, const uint8_t* nodata,
+                              const int32_t* resize_idx, int batch, int H, int W, int out_size, void* stream) {
+  BSEG_REQUIRE(batch > 0 && num_classes > 0 && num_classes <= 256, "postprocess_semantic: bad arguments");
+  BSEG_REQUIRE(resize_idx != nullptr || (out_size == H && out_size == W),
+               "postprocess_semantic: out_size=%d needs a resize index table", out_size);
+  return launch_postprocess_semantic(pred, palette255, num_classes, mean, stdv, out_u8,
+                                     reinterpret_cast<long long*>(out_i64), nodata, resize_idx, batch, H, W, out_size,
+                                     static_cast<cudaStream_t>(stream));
 }
 
 int bseg_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean,

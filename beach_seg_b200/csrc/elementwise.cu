@@ -269,6 +269,101 @@ int launch_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_cl
 }
 
 // ----------------------------------------------------------------------------------------------
+// SegGptImageProcessor.preprocess for segmentation-map prompts (HF:image_processing_seggpt.py:100-131,175-215):
+// mask_to_rgb with build_palette(num_labels) -> resize NEAREST to 448 (torch interpolate index, passed as a table)
+// -> (rgb - 255 mean) / (255 std).  mask uint8 [B,Hin,Win]; palette uint8 [ncls,3] shared by the batch;
+// idx (nullable when Hin == Win == out) maps an output row/col to its source row/col.
+// ----------------------------------------------------------------------------------------------
+__global__ void colorize_resize_norm255_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ palette,
+                                               int ncls, float m0, float m1, float m2, float s0, float s1, float s2,
+                                               const int* __restrict__ idx, float* __restrict__ out, int B, int Hin,
+                                               int OS) {
+  const long long total = (long long)B * OS * OS;
+  const long long oplane = (long long)OS * OS;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = static_cast<int>(i % OS);
+    const int oy = static_cast<int>((i / OS) % OS);
+    const int b = static_cast<int>(i / oplane);
+    const int sy = idx ? idx[oy] : oy, sx = idx ? idx[ox] : ox;
+    int cls = mask[((long long)b * Hin + sy) * Hin + sx];
+    if (cls >= ncls) cls = ncls - 1;
+    const uint8_t* pal = palette + cls * 3;
+    float* o = out + (long long)b * 3 * oplane + (long long)oy * OS + ox;
+    o[0] = __fdiv_rn(__fsub_rn(static_cast<float>(pal[0]), m0), s0);
+    o[oplane] = __fdiv_rn(__fsub_rn(static_cast<float>(pal[1]), m1), s1);
+    o[2 * oplane] = __fdiv_rn(__fsub_rn(static_cast<float>(pal[2]), m2), s2);
+  }
+}
+int launch_colorize_resize_norm255(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean255,
+                                   const float* std255, const int* idx, float* out, int B, int Hin, int out_size,
+                                   cudaStream_t stream) {
+  const long long total = (long long)B * out_size * out_size;
+  ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(total) * 13, stream);
+  colorize_resize_norm255_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(
+      mask, palette, num_classes, mean255[0], mean255[1], mean255[2], std255[0], std255[1], std255[2], idx, out, B, Hin,
+      out_size);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// SegGptImageProcessor.post_process_semantic_segmentation (HF:image_processing_seggpt.py:254-321), used by
+// src/predict_no_prompt.py:299-303: bottom half of pred_masks -> x*std + mean -> clip(255 x, 0, 255) -> nearest
+// resize to the target size (torch interpolate index table) -> argmin_k sum_c (x_c - palette[k][c])^2 with the
+// palette in 0..255 space -> nodata pixels to class 0.  Same op order as torch (mul, add, mul, clip; pow, sum).
+// ----------------------------------------------------------------------------------------------
+__global__ void postprocess_semantic_kernel(const float* __restrict__ pred, const float* __restrict__ palette255,
+                                            int ncls, float m0, float m1, float m2, float s0, float s1, float s2,
+                                            uint8_t* __restrict__ out_u8, long long* __restrict__ out_i64,
+                                            const uint8_t* __restrict__ nodata, const int* __restrict__ idx, int B,
+                                            int H, int W, int OS) {
+  const long long total = (long long)B * OS * OS;
+  const long long plane = 2LL * H * W;
+  const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = static_cast<int>(i % OS);
+    const int oy = static_cast<int>((i / OS) % OS);
+    const int b = static_cast<int>(i / ((long long)OS * OS));
+    const int sy = idx ? idx[oy] : oy;
+    const int sx = idx ? idx[ox] : ox;
+    const float* p = pred + (long long)b * 3 * plane + (long long)(H + sy) * W + sx;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = __fmul_rn(__fadd_rn(__fmul_rn(p[c * plane], stdv[c]), mean[c]), 255.0f);
+      v[c] = fminf(fmaxf(x, 0.0f), 255.0f);
+    }
+    float best = 0.f;
+    int bi = 0;
+    for (int k = 0; k < ncls; ++k) {
+      const float d0 = __fsub_rn(v[0], palette255[k * 3 + 0]);
+      const float d1 = __fsub_rn(v[1], palette255[k * 3 + 1]);
+      const float d2 = __fsub_rn(v[2], palette255[k * 3 + 2]);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+      if (k == 0 || d < best) { best = d; bi = k; }
+    }
+    if (nodata != nullptr && nodata[i]) bi = 0;
+    if (out_u8) out_u8[i] = static_cast<uint8_t>(bi);
+    if (out_i64) out_i64[i] = bi;
+  }
+}
+int launch_postprocess_semantic(const float* pred, const float* palette255, int num_classes, const float* mean,
+                                const float* stdv, uint8_t* out_u8, long long* out_i64, const uint8_t* nodata,
+                                const int* idx, int B, int H, int W, int out_size, cudaStream_t stream) {
+  const long long total = (long long)B * out_size * out_size;
+  ProfScope prof(CAT_DECODE, 0, static_cast<double>(B) * H * W * 12 + static_cast<double>(total), stream);
+  postprocess_semantic_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(
+      pred, palette255, num_classes, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], out_u8, out_i64, nodata, idx,
+      B, H, W, out_size);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // PromptModel.process_pred_masks (src/model.py:155-175) + cv2.resize(INTER_NEAREST) (src/predict.py:258)
 // + nodata zeroing (src/predict_no_prompt.py:303):
 //   cls[b,y,x] = argmin_k sum_c (pred[b,c,H+sy,sx] - palette_norm[b,k,c])^2,  first minimum wins.

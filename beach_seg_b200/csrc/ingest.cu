@@ -68,7 +68,9 @@ int launch_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int
 // table serves both axes because the crop and the output are square.
 // ----------------------------------------------------------------------------------------------
 constexpr int kOut = 448;
-constexpr int kPrecisionBits = 22;  // 32 - 8 - 2, PIL Resample.c
+// Fixed-point precision of the coefficient table (runtime): 22 = 32 - 8 - 2 for PIL (Resample.c); torchvision's uint8
+// antialias kernel (the HF processor's resize, HF:image_processing_backends.py:200-251 -> ATen
+// upsample_avx_bilinear_bicubic_uint8) uses int16 weights with the largest precision that keeps them below 2^15.
 
 __device__ __forceinline__ uint8_t composite_u8(float v, float mn, float denom) {
   // img.clip(min, min+3000) - min ; img /= max ; np.array(img*255, dtype=uint8)  (float32, truncation)
@@ -77,29 +79,45 @@ __device__ __forceinline__ uint8_t composite_u8(float v, float mn, float denom) 
   const float x = __fmul_rn(__fdiv_rn(__fsub_rn(c, mn), denom), 255.0f);
   return static_cast<uint8_t>(static_cast<int>(x));
 }
-__device__ __forceinline__ uint8_t clip8(int v) {
-  v >>= kPrecisionBits;
+__device__ __forceinline__ uint8_t clip8(int v, int prec) {
+  v >>= prec;
   return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
+// kFromU8 == false: uint16 4-band scene + tile boxes (src/predict.py path, PIL table, (u/255 - mean)/std)
+// kFromU8 == true : uint8 RGB crops [n,crop,crop,3] (HWC) or [n,3,crop,crop] (CHW) (src/predict_no_prompt.py path:
+//                   SegGptImageProcessor.preprocess, torchvision table, (u - 255 mean)/(255 std))
+template <bool kFromU8>
 __global__ void __launch_bounds__(256)
 ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ nodata, int Hs, int Ws,
               const float* __restrict__ stats, const int* __restrict__ boxes, int crop, const int* __restrict__ coef,
               const int* __restrict__ bounds, int ksize, int band, int max_rows, float m0, float m1, float m2,
               float s0, float s1, float s2, float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_patch,
-              long long patch_tile_stride, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_nodata) {
+              long long patch_tile_stride, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_nodata,
+              const uint8_t* __restrict__ src_u8, int src_chw, int prec) {
   extern __shared__ uint8_t sm[];
   uint8_t* comp = sm;                                   // [3][max_rows][crop]
   uint8_t* hbuf = sm + 3 * max_rows * crop;             // [3][max_rows][kOut]
   const int tile = blockIdx.y;
   const int oy0 = blockIdx.x * band;
   const int oy1 = min(oy0 + band, kOut);
-  const int xmin = boxes[tile * 4 + 0], ymin = boxes[tile * 4 + 1];
   const int r0 = bounds[2 * oy0];                                      // first crop row needed
   const int r1 = bounds[2 * (oy1 - 1)] + bounds[2 * (oy1 - 1) + 1];    // one past the last
   const int nrows = r1 - r0;
   const long long npix = static_cast<long long>(Hs) * Ws;
 
+  if constexpr (kFromU8) {
+    // ---- phase 1: copy the needed rows of the uint8 crop ----
+    const long long plane = static_cast<long long>(crop) * crop;
+    const uint8_t* img = src_u8 + static_cast<long long>(tile) * 3 * plane;
+    for (int i = threadIdx.x; i < nrows * crop; i += blockDim.x) {
+      const int rr = i / crop, cx = i % crop;
+      const long long p = static_cast<long long>(r0 + rr) * crop + cx;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) comp[(c * max_rows + rr) * crop + cx] = src_chw ? img[c * plane + p] : img[p * 3 + c];
+    }
+  } else {
+  const int xmin = boxes[tile * 4 + 0], ymin = boxes[tile * 4 + 1];
   const float mn = stats[0];
   const float hi = __fadd_rn(3000.0f, mn);
   float den[3];
@@ -132,6 +150,7 @@ ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ no
     }
     if (out_nodata) out_nodata[(static_cast<long long>(tile) * crop + (r0 + rr)) * crop + cx] = nd;
   }
+  }
   __syncthreads();
 
   // ---- phase 2: horizontal pass ----
@@ -139,7 +158,7 @@ ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ no
     const int rr = i / kOut, ox = i % kOut;
     const int x0 = bounds[2 * ox], cnt = bounds[2 * ox + 1];
     const int* k = coef + ox * ksize;
-    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+    int a0 = 1 << (prec - 1), a1 = a0, a2 = a0;
     const uint8_t* c0 = comp + (0 * max_rows + rr) * crop + x0;
     const uint8_t* c1 = comp + (1 * max_rows + rr) * crop + x0;
     const uint8_t* c2 = comp + (2 * max_rows + rr) * crop + x0;
@@ -149,9 +168,9 @@ ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ no
       a1 += c1[t] * w;
       a2 += c2[t] * w;
     }
-    hbuf[(0 * max_rows + rr) * kOut + ox] = clip8(a0);
-    hbuf[(1 * max_rows + rr) * kOut + ox] = clip8(a1);
-    hbuf[(2 * max_rows + rr) * kOut + ox] = clip8(a2);
+    hbuf[(0 * max_rows + rr) * kOut + ox] = clip8(a0, prec);
+    hbuf[(1 * max_rows + rr) * kOut + ox] = clip8(a1, prec);
+    hbuf[(2 * max_rows + rr) * kOut + ox] = clip8(a2, prec);
   }
   __syncthreads();
 
@@ -163,11 +182,14 @@ ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ no
     const int oy = oy0 + (i % nout) / kOut, ox = i % kOut;
     const int y0 = bounds[2 * oy] - r0, cnt = bounds[2 * oy + 1];
     const int* k = coef + oy * ksize;
-    int a = 1 << (kPrecisionBits - 1);
+    int a = 1 << (prec - 1);
     const uint8_t* h = hbuf + (c * max_rows + y0) * kOut + ox;
     for (int t = 0; t < cnt; ++t) a += h[t * kOut] * __ldg(k + t);
-    const float u = static_cast<float>(clip8(a));
-    const float val = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), mean[c]), stdv[c]);
+    const float u = static_cast<float>(clip8(a, prec));
+    // PIL path: (u/255 - mean)/std (src/data.py:101,226-229); HF processor: (u - 255 mean)/(255 std), mean/std passed
+    // pre-multiplied (HF:image_processing_backends.py:292-331)
+    const float val = kFromU8 ? __fdiv_rn(__fsub_rn(u, mean[c]), stdv[c])
+                              : __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), mean[c]), stdv[c]);
     if (out_nchw) out_nchw[((static_cast<long long>(tile) * 3 + c) * kOut + oy) * kOut + ox] = val;
     if (out_patch) {
       // row of the patch-embedding A operand: token (oy/16, ox/16), k = c*256 + (oy%16)*16 + ox%16
@@ -178,28 +200,51 @@ ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ no
   }
 }
 
+namespace {
+template <bool kFromU8>
+int launch_ingest_t(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
+                    int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
+                    const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
+                    long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, const uint8_t* src_u8,
+                    int src_chw, int prec, cudaStream_t stream) {
+  if (n_tiles == 0) return 0;
+  BSEG_REQUIRE(band > 0 && max_rows > 0 && crop > 0, "ingest: bad geometry");
+  BSEG_REQUIRE(prec >= 1 && prec <= 22, "ingest: coefficient precision %d out of range", prec);
+  const size_t smem = static_cast<size_t>(3) * max_rows * (crop + kOut);
+  BSEG_REQUIRE(smem <= 200 * 1024, "ingest: crop=%d band=%d needs %zu B of shared memory", crop, band, smem);
+  auto kern = ingest_kernel<kFromU8>;
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_bytes = smem;
+  }
+  dim3 grid((kOut + band - 1) / band, n_tiles);
+  ProfScope prof(CAT_INGEST, 0,
+                 static_cast<double>(n_tiles) * ((kFromU8 ? 3.0 : 8.0) * crop * crop + 3.0 * 448 * 448 * (out_nchw ? 4 : 2)),
+                 stream);
+  kern<<<grid, 256, smem, stream>>>(scene, nodata, Hs, Ws, stats, boxes, crop, coef, bounds, ksize, band, max_rows,
+                                    mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], out_nchw, out_patch,
+                                    patch_tile_stride, out_u8, out_nodata, src_u8, src_chw, prec);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+}  // namespace
+
 int launch_ingest(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
                   int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
                   const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
                   long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream) {
-  if (n_tiles == 0) return 0;
-  BSEG_REQUIRE(band > 0 && max_rows > 0 && crop > 0, "ingest: bad geometry");
-  const size_t smem = static_cast<size_t>(3) * max_rows * (crop + kOut);
-  BSEG_REQUIRE(smem <= 200 * 1024, "ingest: crop=%d band=%d needs %zu B of shared memory", crop, band, smem);
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    BSEG_CHECK_CUDA(cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    attr_bytes = smem;
-  }
-  dim3 grid((kOut + band - 1) / band, n_tiles);
-  ProfScope prof(CAT_INGEST, 0, static_cast<double>(n_tiles) * (4.0 * crop * crop * 2 + 3.0 * 448 * 448 * 2), stream);
-  ingest_kernel<<<grid, 256, smem, stream>>>(scene, nodata, Hs, Ws, stats, boxes, crop, coef, bounds, ksize, band,
-                                             max_rows, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], out_nchw,
-                                             out_patch, patch_tile_stride, out_u8, out_nodata);
-  BSEG_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
+  return launch_ingest_t<false>(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, band, max_rows,
+                                mean, stdv, out_nchw, out_patch, patch_tile_stride, out_u8, out_nodata, nullptr, 0, 22,
+                                stream);
+}
+
+int launch_preprocess_u8(const uint8_t* images, int chw, int n, int crop, const int* coef, const int* bounds, int ksize,
+                         int prec, int band, int max_rows, const float* mean255, const float* std255, float* out_nchw,
+                         cudaStream_t stream) {
+  return launch_ingest_t<true>(nullptr, nullptr, 0, 0, nullptr, nullptr, n, crop, coef, bounds, ksize, band, max_rows,
+                               mean255, std255, out_nchw, nullptr, 0, nullptr, nullptr, images, chw, prec, stream);
 }
 
 }  // namespace bseg

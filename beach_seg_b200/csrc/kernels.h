@@ -75,6 +75,15 @@ int launch_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_cl
 int launch_decode_palette(const float* pred, const float* palette_norm, int num_classes, uint8_t* out_u8,
                           long long* out_i64, const uint8_t* nodata, const int* idx, int B, int H, int W,
                           int out_size, cudaStream_t stream);
+int launch_colorize_resize_norm255(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean255,
+                                   const float* std255, const int* idx, float* out, int B, int Hin, int out_size,
+                                   cudaStream_t stream);
+int launch_postprocess_semantic(const float* pred, const float* palette255, int num_classes, const float* mean,
+                                const float* stdv, uint8_t* out_u8, long long* out_i64, const uint8_t* nodata,
+                                const int* idx, int B, int H, int W, int out_size, cudaStream_t stream);
+int launch_preprocess_u8(const uint8_t* images, int chw, int n, int crop, const int* coef, const int* bounds, int ksize,
+                         int prec, int band, int max_rows, const float* mean255, const float* std255, float* out_nchw,
+                         cudaStream_t stream);
 int launch_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
                            const int* boxes, int use_atomics, cudaStream_t stream);
 int launch_vote_argmax(const uint32_t* counter, uint8_t* out, long long n, cudaStream_t stream);

@@ -234,3 +234,145 @@ def smooth_l1_loss(pred_masks: torch.Tensor, labels: torch.Tensor, yesdata: torc
             float(beta), 1 if per_sample else 0, _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(scratch), B, H, W,
             _lib.stream_ptr()), "bseg_loss_smoothl1_fwd_bwd")
     return (loss[0], grad) if want_grad else loss[0]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# HF image-processor path (src/predict_no_prompt.py:235-301; HF:image_processing_seggpt.py)
+# ------------------------------------------------------------------------------------------------------------
+@lru_cache(maxsize=16)
+def tv_bicubic_aa_table(in_size: int, out_size: int = 448):
+    """Coefficient table of torchvision's uint8 bicubic-antialias resize, the kernel the HF processor's
+    `tvF.resize(..., BICUBIC, antialias=True)` runs on CPU (HF:image_processing_backends.py:200-251 -> ATen
+    upsample_avx_bilinear_bicubic_uint8 / _compute_index_ranges_int16_weights): Pillow's windowed bicubic (a = -0.5,
+    support 2*scale) with weights quantised to int16 at the largest precision that keeps them below 2^15.
+    Returns (bounds int32 [out,2], coef int32 [out,ksize], precision_bits).  Bit-exact against torchvision
+    (tests/test_processor.py)."""
+    if in_size == out_size:
+        bounds = np.stack([np.arange(out_size), np.ones(out_size)], axis=1).astype(np.int32)
+        return bounds, np.full((out_size, 1), 1 << 14, dtype=np.int32), 14
+    scale = in_size / out_size
+    support = 2.0 * scale if scale >= 1.0 else 2.0
+    ksize = int(math.ceil(support)) * 2 + 1
+    inv = 1.0 / scale if scale >= 1.0 else 1.0
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    w = np.zeros((out_size, ksize), dtype=np.float64)
+    wmax = 0.0
+    for i in range(out_size):
+        center = scale * (i + 0.5)
+        xmin = max(int(center - support + 0.5), 0)
+        xsize = min(max(min(int(center + support + 0.5), in_size) - xmin, 0), ksize)
+        ws = [_bicubic((j + xmin - center + 0.5) * inv) for j in range(xsize)]
+        tot = sum(ws)
+        if tot != 0.0:
+            ws = [v / tot for v in ws]
+        wmax = max([wmax] + ws)
+        w[i, :xsize] = ws
+        bounds[i] = (xmin, xsize)
+    prec = 0
+    while prec < 22 and int(0.5 + wmax * (1 << (prec + 1))) < (1 << 15):
+        prec += 1
+    v = w * (1 << prec)
+    coef = np.where(v < 0, np.trunc(v - 0.5), np.trunc(v + 0.5)).astype(np.int32)
+    return bounds, coef, prec
+
+
+@lru_cache(maxsize=16)
+def torch_nearest_index(src: int, dst: int) -> np.ndarray:
+    """Source index per destination index of torch `interpolate(mode="nearest")` / torchvision NEAREST resize:
+    min(floor(dst_index * float32(src / dst)), src - 1), evaluated in float32 like ATen."""
+    scale = np.float32(src) / np.float32(dst)
+    idx = np.floor(np.arange(dst, dtype=np.float32) * scale).astype(np.int64)
+    return np.minimum(idx, src - 1).astype(np.int32)
+
+
+@lru_cache(maxsize=16)
+def torch_nearest_exact_index(src: int, dst: int) -> np.ndarray:
+    """The same for `mode="nearest-exact"` (torchvision NEAREST_EXACT, what HF maps PIL NEAREST to,
+    transformers/image_utils.py:56): min(floor((dst_index + 0.5) * float32(src / dst)), src - 1)."""
+    scale = np.float32(src) / np.float32(dst)
+    idx = np.floor((np.arange(dst, dtype=np.float32) + np.float32(0.5)) * scale).astype(np.int64)
+    return np.minimum(idx, src - 1).astype(np.int32)
+
+
+def _hf_mean_std_255():
+    """HF's fused rescale+normalise constants: tensor(mean) * (1.0 / rescale_factor), rescale_factor = 1/255
+    (HF:image_processing_backends.py:292-306), in float32."""
+    f = 1.0 / (1 / 255)
+    return ((torch.tensor(IMAGE_MEAN) * f).tolist(), (torch.tensor(IMAGE_STD) * f).tolist())
+
+
+_tv_cache: dict = {}
+
+
+def preprocess_u8(images_u8: torch.Tensor, channels_first: bool = False) -> torch.Tensor:
+    """SegGptImageProcessor.preprocess for `images` / `prompt_images` (HF:image_processing_seggpt.py:134-252): uint8
+    [n,c,c,3] (or [n,3,c,c]) square crops -> bicubic-antialias resize to 448 -> (x - 255 mean)/(255 std), float32
+    [n,3,448,448]."""
+    _need_cuda(images_u8)
+    if images_u8.dtype != torch.uint8 or images_u8.ndim != 4:
+        raise ValueError("preprocess_u8 expects a uint8 [n,c,c,3] or [n,3,c,c] tensor")
+    n = images_u8.shape[0]
+    crop = images_u8.shape[2]
+    other = images_u8.shape[3] if channels_first else images_u8.shape[1]
+    if other != crop:
+        raise ValueError("preprocess_u8 handles square crops (the reference's crops are squares, src/util/ml_util.py:20-66)")
+    dev = images_u8.device
+    key = (crop, str(dev))
+    if key not in _tv_cache:
+        b, c, p = tv_bicubic_aa_table(crop, 448)
+        _tv_cache[key] = (torch.from_numpy(b).to(dev), torch.from_numpy(c).to(dev), c.shape[1], p)
+    bounds, coef, ksize, prec = _tv_cache[key]
+    m255, s255 = _hf_mean_std_255()
+    src = images_u8.contiguous()
+    out = torch.empty((n, 3, 448, 448), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().bseg_preprocess_u8(_lib.ptr(src), 1 if channels_first else 0, n, crop, _lib.ptr(coef),
+                                                 _lib.ptr(bounds), ksize, prec, _lib.f3(m255), _lib.f3(s255),
+                                                 _lib.ptr(out), _lib.stream_ptr()), "bseg_preprocess_u8")
+    return out
+
+
+def colorize_resize_norm255(mask: torch.Tensor, palette_u8: torch.Tensor, out_size: int = 448) -> torch.Tensor:
+    """SegGptImageProcessor.preprocess for segmentation-map `prompt_masks` (HF:image_processing_seggpt.py:100-131,
+    175-215): class ids uint8 [B,c,c] -> palette colour -> NEAREST resize -> (rgb - 255 mean)/(255 std)."""
+    _need_cuda(mask)
+    if mask.ndim == 4:
+        mask = mask.squeeze(1)
+    B, H, W = mask.shape
+    if H != W:
+        raise ValueError("square masks only")
+    dev = mask.device
+    m8 = mask.to(torch.uint8).contiguous()
+    pal = palette_u8.to(device=dev, dtype=torch.uint8).contiguous()
+    idx = torch.from_numpy(torch_nearest_exact_index(H, out_size)).to(dev) if H != out_size else None
+    m255, s255 = _hf_mean_std_255()
+    out = torch.empty((B, 3, out_size, out_size), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().bseg_colorize_resize_norm255(_lib.ptr(m8), _lib.ptr(pal), pal.shape[0], _lib.f3(m255),
+                                                           _lib.f3(s255), _lib.ptr(idx), _lib.ptr(out), B, H, out_size,
+                                                           _lib.stream_ptr()), "bseg_colorize_resize_norm255")
+    return out
+
+
+def postprocess_semantic(pred_masks: torch.Tensor, palette255: torch.Tensor, out_size: Optional[int] = None,
+                         nodata: Optional[torch.Tensor] = None, dtype=torch.int64) -> torch.Tensor:
+    """SegGptImageProcessor.post_process_semantic_segmentation (HF:image_processing_seggpt.py:254-321) for a batch,
+    optionally with the nodata zeroing of src/predict_no_prompt.py:303.  pred_masks float32 [B,3,2H,W];
+    palette255 float32 [C,3] (0..255).  Returns [B,out,out]."""
+    _need_cuda(pred_masks)
+    B, _, H2, W = pred_masks.shape
+    H = H2 // 2
+    out_size = H if out_size is None else int(out_size)
+    dev = pred_masks.device
+    idx = torch.from_numpy(torch_nearest_index(H, out_size)).to(dev) if (out_size != H or out_size != W) else None
+    o8 = torch.empty((B, out_size, out_size), dtype=torch.uint8, device=dev) if dtype == torch.uint8 else None
+    o64 = torch.empty((B, out_size, out_size), dtype=torch.int64, device=dev) if dtype == torch.int64 else None
+    nd = nodata.to(torch.uint8).contiguous() if nodata is not None else None
+    pred_c = pred_masks.contiguous()
+    pal_c = palette255.to(device=dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().bseg_postprocess_semantic(
+            _lib.ptr(pred_c), _lib.ptr(pal_c), pal_c.shape[0], _lib.f3(IMAGE_MEAN), _lib.f3(IMAGE_STD), _lib.ptr(o8),
+            _lib.ptr(o64), _lib.ptr(nd), _lib.ptr(idx), B, H, W, out_size, _lib.stream_ptr()),
+            "bseg_postprocess_semantic")
+    return o8 if o8 is not None else o64

@@ -62,6 +62,32 @@ class TilePredictor:
         return ops.decode_palette(out.pred_masks, pal_norm, out_size=self.crop_size, dtype=torch.uint8)
 
 
+class NoPromptPredictor:
+    """The tensor part of src/predict_no_prompt.py:270-304, batched over tiles: HF-processor preprocessing of the uint8
+    crops, `n_prompts` prompts per tile with `feature_ensemble=True` (ensemble grouped per tile), mean over the
+    prompts, palette post-processing at crop size, nodata zeroing.  One launch handles `tiles x n_prompts` model
+    samples."""
+
+    def __init__(self, model: SegGptB200, processor, crop_size: int, num_classes: int = 4):
+        self.model, self.processor, self.crop_size, self.num_classes = model, processor, crop_size, num_classes
+        self._pal = torch.tensor(build_palette(num_classes - 1), dtype=torch.float32)
+
+    @torch.no_grad()
+    def predict_tiles(self, crops_u8: torch.Tensor, nodata: Optional[torch.Tensor], prompt_pixel_values: torch.Tensor,
+                      prompt_masks: torch.Tensor) -> torch.Tensor:
+        """crops_u8 uint8 [n,c,c,3]; nodata bool/uint8 [n,c,c] or None; prompt_pixel_values / prompt_masks float32
+        [n*P,3,448,448] (the P prompts of tile i at rows i*P..i*P+P-1, already preprocessed).  Returns uint8 [n,c,c]."""
+        n = crops_u8.shape[0]
+        P = prompt_pixel_values.shape[0] // n
+        px = ops.preprocess_u8(crops_u8.to(self.model.device))                      # :283-288
+        px = px.repeat_interleave(P, dim=0)                                          # images=[crop_img] * len(prompts)
+        out = self.model(pixel_values=px, prompt_pixel_values=prompt_pixel_values, prompt_masks=prompt_masks,
+                         embedding_type="instance", feature_ensemble=True, ensemble_group=P)  # :289-295
+        mean = ops.mean_over_prompts(out.pred_masks, P)                              # :298
+        return ops.postprocess_semantic(mean, self._pal, out_size=self.crop_size, nodata=nodata,
+                                        dtype=torch.uint8)                           # :299-303
+
+
 class Accumulator:
     """Device-resident version of the reference's Accumulator (src/predict.py:55-159): same constructor and
     `update` / `save_current` / context-manager protocol.  `update` takes either the reference's one-hot uint8

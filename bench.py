@@ -205,7 +205,7 @@ def train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrie
     tflops = TRAIN_BATCH * TRAIN_FLOP_PER_TILE / (ms_iter * 1e-3) / 1e12
     return {"metric": "train step ms/iter", "ms_per_iter": ms_iter, "batch_per_gpu": TRAIN_BATCH, "n_gpus": world,
             "global_batch": TRAIN_BATCH * world, "tiles_per_s": world * TRAIN_BATCH / (ms_iter * 1e-3),
-            "steps": args.train_steps, "loss": float(loss), "prompts": TRAIN_PROMPTS,
+            "steps": args.train_steps, "loss": float(loss.detach()), "prompts": TRAIN_PROMPTS,
             "loss_semantics": "SegGptLoss as written in the reference (BxB keep-mask broadcast, src/model.py:40-64)",
             "includes": "ingest 512->448, colourise, forward (activations kept), palette decode, loss fwd+bwd, "
                         "backward to the prompts, prompt-grad all-reduce (NCCL, world>1), AdamW step",

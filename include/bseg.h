@@ -118,6 +118,27 @@ int bseg_ingest_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int 
                       int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,
                       long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, void* stream);
 
+/* ---- src/predict_no_prompt.py path: the HF image processor (HF:image_processing_seggpt.py) on the device ----
+ * SegGptImageProcessor.preprocess for images / prompt images (:134-252): uint8 RGB crops [n,crop,crop,3] (HWC,
+ * layout_chw = 0) or [n,3,crop,crop] -> torchvision bicubic-antialias resize to 448 on uint8 (bit-exact restatement of
+ * ATen's int16-weight kernel; coef/bounds/precision from beach_seg_b200.ops.tv_bicubic_aa_table) ->
+ * (x - 255 mean)/(255 std) (mean255 / std255 host float[3], HF:image_processing_backends.py:292-331) ->
+ * fp32 [n,3,448,448]. */
+int bseg_preprocess_u8(const uint8_t* images, int layout_chw, int n, int crop, const int32_t* coef,
+                       const int32_t* bounds, int ksize, int precision_bits, const float* mean255, const float* std255,
+                       float* out_nchw, void* stream);
+/* preprocess for segmentation-map prompt masks (:100-131,175-215): mask uint8 [B,in,in] -> palette colour (uint8
+ * [num_classes,3] = build_palette(num_labels)) -> NEAREST resize (resize_idx int32 [out] or NULL) ->
+ * (rgb - 255 mean)/(255 std) -> fp32 [B,3,out,out]. */
+int bseg_colorize_resize_norm255(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean255,
+                                 const float* std255, const int32_t* resize_idx, float* out, int batch, int in_size,
+                                 int out_size, void* stream);
+/* post_process_semantic_segmentation (:254-321) [+ nodata zeroing, src/predict_no_prompt.py:303]: pred fp32
+ * [B,3,2H,W] -> bottom half, x*std+mean, clip(255x,0,255), nearest resize, argmin vs palette255 fp32 [num_classes,3]. */
+int bseg_postprocess_semantic(const float* pred, const float* palette255, int num_classes, const float* mean,
+                              const float* stdv, uint8_t* out_u8, int64_t* out_i64, const uint8_t* nodata,
+                              const int32_t* resize_idx, int batch, int H, int W, int out_size, void* stream);
+
 /* torch_apply_mask_rgb + normalize (src/util/ml_util.py:114-132; src/model.py:210-211,238-239).
  * mask uint8 [B,H,W]; palette uint8 [B,num_classes,3]; out fp32 [B,3,H,W]. */
 int bseg_colorize_norm(const uint8_t* mask, const uint8_t* palette, int num_classes, const float* mean,
