@@ -153,3 +153,49 @@ def test_prompt_model_forward_matches_reference_pipeline(dev):
     print(f"[PromptModel.forward] class-map flips vs reference pipeline: {flips * 100:.3f} %")
     assert got.shape == (1, 448, 448) and got.dtype == torch.int64
     assert flips < 0.02
+
+
+def test_full_scene_sliding_window_sharded_equals_single(dev):
+    """BASELINE config 3 at full size: 8000x4000 uint16 scene, 512-px tiles, stride 448 (64-px overlap) = 18 x 9 = 162
+    tiles, random-init 24-layer backbone.  Size-independent properties instead of a CPU oracle run (162 tiles would
+    take ~15 min on the host): (1) every pixel's vote total equals the number of tiles covering it, (2) the canvas
+    stitched from 8 owner-computes shards (no data-path collective, just the sum of the per-rank u32 canvases) is
+    bit-identical to the single-rank canvas, (3) so is the final class map."""
+    from beach_seg_b200.ml_util import load_model
+    from beach_seg_b200.predict import TilePredictor, create_palette, shard_tiles
+
+    Hs, Ws, crop = 4000, 8000, 512
+    model = load_model("random-init:0", device=dev)
+    predictor = TilePredictor(model, crop)
+    scene = torch.from_numpy(synth.scene_u16(Hs, Ws, seed=7).view(np.int16)).to(dev)
+    nodata = torch.from_numpy(synth.nodata_wedge(Hs, Ws, 0.05)).to(dev)
+    boxes_np = synth.sliding_boxes(Hs, Ws, crop, 448)
+    assert len(boxes_np) == 162
+    boxes = torch.from_numpy(boxes_np).to(dev)
+    stats = ops.scene_stats(scene, nodata)
+    n = len(boxes_np)
+    prompts = synth.normalize(synth.smooth_image(1, 2000)).to(dev).expand(n, -1, -1, -1).contiguous()
+    pcls = synth.blocky_mask(1, 3000).to(dev).expand(n, -1, -1).contiguous()
+    torch.manual_seed(42)
+    palette = create_palette(4, n, True, dev)
+
+    def run(ids):
+        canvas = torch.zeros((Hs, Ws), dtype=torch.int32, device=dev)
+        for s in range(0, len(ids), 64):
+            sel = torch.as_tensor(list(ids[s:s + 64]), device=dev)
+            cls = predictor.predict_tiles(scene, nodata, stats, boxes[sel], prompts[sel], pcls[sel],
+                                          (palette[0][sel], palette[1][sel]))
+            ops.vote_accumulate(canvas, cls, boxes[sel], overlapping=True)
+        return canvas
+
+    single = run(range(n))
+    sharded = torch.zeros_like(single)
+    for r in range(8):
+        sharded += run(shard_tiles(n, r, 8))
+    assert torch.equal(single, sharded)
+    votes = single.cpu().numpy().view(np.uint8).reshape(Hs, Ws, 4).sum(axis=2)
+    cover = np.zeros((Hs, Ws), dtype=np.int32)
+    for x0, y0, x1, y1 in boxes_np:
+        cover[max(y0, 0):min(y1, Hs), max(x0, 0):min(x1, Ws)] += 1
+    assert np.array_equal(votes, cover)
+    assert torch.equal(ops.vote_argmax(single), ops.vote_argmax(sharded))
