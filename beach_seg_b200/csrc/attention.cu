@@ -318,7 +318,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
       for (int kb = 0; kb < kNumKB; ++kb) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bh4[i] = bh_row[kb * 4 + i];
+        for (int i = 0; i < 4; ++i) bh4[i] = lds32(bh_row + kb * 4 + i);
 
         // ---------------- lower half: columns 0..63 ----------------
         mbar_wait(&s_full[2 * w], kb & 1);

@@ -353,14 +353,14 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       if (g == 0) {
         chunk(I0{}, I32{}, sbase, boff, acc4);
         chunk(I32{}, I32{}, sbase, boff, acc4);
-        atomicAdd(&dsh_row[kb * 4 + 0], acc4[0]);
-        atomicAdd(&dsh_row[kb * 4 + 1], acc4[1]);
-        atomicAdd(&dsh_row[kb * 4 + 2], acc4[2]);
+        red_shared_add_f32(&dsh_row[kb * 4 + 0], acc4[0]);
+        red_shared_add_f32(&dsh_row[kb * 4 + 1], acc4[1]);
+        red_shared_add_f32(&dsh_row[kb * 4 + 2], acc4[2]);
       } else {
         chunk(I64{}, I32{}, sbase, boff, acc4);
         chunk(I96{}, I16{}, sbase, boff, acc4);
-        atomicAdd(&dsh_row[kb * 4 + 2], acc4[2]);
-        atomicAdd(&dsh_row[kb * 4 + 3], acc4[3]);
+        red_shared_add_f32(&dsh_row[kb * 4 + 2], acc4[2]);
+        red_shared_add_f32(&dsh_row[kb * 4 + 3], acc4[3]);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -601,10 +601,10 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
       uint32_t pp[16], pd[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 bh4 = *reinterpret_cast<const float4*>(bh_row + i);
-        const float4 bw4 = *reinterpret_cast<const float4*>(bw_row + i);
-        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + i);
-        const float4 d4 = *reinterpret_cast<const float4*>(d_s + i);
+        const float4 bh4 = lds128(bh_row + i);
+        const float4 bw4 = lds128(bw_row + i);
+        const float4 l4 = lds128(lse_s + i);
+        const float4 d4 = lds128(d_s + i);
         const float p0 = ex2_approx(fmaf(s[i], sc, bw4.x) + (bh4.x - l4.x));
         const float p1 = ex2_approx(fmaf(s[i + 1], sc, bw4.y) + (bh4.y - l4.y));
         const float p2 = ex2_approx(fmaf(s[i + 2], sc, bw4.z) + (bh4.z - l4.z));

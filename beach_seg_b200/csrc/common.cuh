@@ -86,16 +86,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// Potentially blocking: the thread is suspended until the phase completes or the suspend-time hint (in ns) elapses, so
+// a waiting warp costs (almost) no issue slots.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P1;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -113,19 +115,25 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Blocking wait with a watchdog: a protocol bug traps instead of hanging the GPU box.
+// Blocking wait with a watchdog: a protocol bug traps instead of hanging the GPU box.  The clock is only read every
+// 64th wake-up so that the spin itself stays a two-instruction loop.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    // ~2 s at 2 GHz for worker warps, twice that for the control warps 0-3 so that the workers report first
-    if (clock64() - t0 > (threadIdx.x < 128 ? 8000000000LL : 4000000000LL)) {
-      printf("bseg: mbarrier watchdog block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+    if ((++spins & 63u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      // ~2 s at 2 GHz for worker warps, twice that for the control warps 0-3 so that the workers report first
+      if (now - t0 > (threadIdx.x < 128 ? 8000000000LL : 4000000000LL)) {
+        printf("bseg: mbarrier watchdog block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x, smem_u32(bar), parity);
 #ifdef BSEG_WATCHDOG_HOOK
-      BSEG_WATCHDOG_HOOK
+        BSEG_WATCHDOG_HOOK
 #endif
-      __trap();
+        __trap();
+      }
     }
   }
 }
@@ -161,6 +169,22 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
         "r"(c2), "r"(c3)
       : "memory");
+}
+
+// explicit shared-memory loads (a float* derived from the dynamic smem base otherwise compiles to generic LD)
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float lds32(const float* p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  return v;
+}
+
+__device__ __forceinline__ void red_shared_add_f32(float* p, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
 }
 
 // named barrier among a subset of the CTA's warps (id 1..15; `count` threads, a multiple of 32)
