@@ -40,8 +40,8 @@ constexpr int kT = kGridW * kGridH;    // 1568
 constexpr int kNumKB = kT / kKB;       // 14
 constexpr int kStages = 3;
 constexpr int kThreads = 128 + kWG * 128;  // 384
-constexpr int kRegsControl = 40;
-constexpr int kRegsSoftmax = 232;  // 128*40 + 256*232 = 64512 <= 65536
+constexpr int kRegsControl = 64;
+constexpr int kRegsSoftmax = 216;  // 128*64 + 256*216 = 63488 <= 65536
 constexpr int kRelRows = 176;  // 112 (reversed rel_pos_h, 111 used) + 64 (reversed rel_pos_w, 55 used)
 
 constexpr int kQBytes = kQTile * 128;        // 16384 per warpgroup
@@ -72,8 +72,20 @@ constexpr uint32_t kColO = 192;
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLazyThreshold = 16.0f;     // raise the reference when a block exceeds it by 2^16
+constexpr long long kStaggerCycles = 1300;  // about half of a warpgroup's key-block period
 constexpr float kOverflowGuard = 100.0f;    // redo a half block whose scores exceed the reference by 2^100
 }  // namespace attn
+
+// Optional timeline instrumentation (tools/micro/attn_trace.cu defines BSEG_ATTN_TRACE): clock64 stamps of one CTA.
+#ifdef BSEG_ATTN_TRACE
+__device__ long long g_attn_trace[3][16][16];  // [actor: wg0, wg1, mma0][block][event]
+#define ATTN_TRACE(actor, kb, ev)                                                              \
+  do {                                                                                         \
+    if (trace_cta && lane == 0) g_attn_trace[actor][kb][ev] = clock64();                       \
+  } while (0)
+#else
+#define ATTN_TRACE(actor, kb, ev) do {} while (0)
+#endif
 
 namespace {
 __device__ __forceinline__ uint32_t scale_bf16x2(uint32_t v, float a) {
@@ -106,13 +118,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* pv_done = bars + 24;   // [kWG]     MMA -> softmax: O += P_j V_j retired (P region free, O stable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kCtaQ;
   const int head = blockIdx.y;
   const int seq = blockIdx.z;
   const int sh = seq * heads + head;
   const int n_active = (q0 + kQTile < kT) ? 2 : 1;  // the last tile of a sequence has one live warpgroup
+#ifdef BSEG_ATTN_TRACE
+  const bool trace_cta = blockIdx.x == 2 && blockIdx.y == 5 && blockIdx.z == gridDim.z / 2;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -141,32 +156,41 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
     if (warp == 0) {
-      // ============================ TMA producer ============================
-      if (lane == 0) {
+      // ============================ TMA producer (warp-uniform loop, one elected lane issues) ============================
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(q_full, n_active * kQBytes + kRelBytes);
         for (int w = 0; w < n_active; ++w) tma_load_3d(sQ + w * kQBytes, &tmap_q, q_full, 0, q0 + w * kQTile, sh);
         tma_load_2d(sRel, &tmap_rel, q_full, 0, 0);
-        for (int kb = 0; kb < kNumKB; ++kb) {
-          const int st = kb % kStages;
-          if (kb >= kStages) mbar_wait(&k_empty[st], ((kb / kStages) & 1) ^ 1);
+      }
+      __syncwarp();
+      for (int kb = 0; kb < kNumKB; ++kb) {
+        const int st = kb % kStages;
+        if (kb >= kStages) mbar_wait(&k_empty[st], ((kb / kStages) & 1) ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&k_full[st], kKBytes);
           tma_load_3d(sK + st * kKBytes, &tmap_k, &k_full[st], 0, kb * kKB, sh);
-          if (kb >= kStages) mbar_wait(&v_empty[st], ((kb / kStages) & 1) ^ 1);
+        }
+        __syncwarp();
+        if (kb >= kStages) mbar_wait(&v_empty[st], ((kb / kStages) & 1) ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&v_full[st], kVBytes);
           tma_load_3d(sV + st * kVBytes, &tmap_vt, &v_full[st], kb * kKB, 0, sh);
           tma_load_3d(sV + st * kVBytes + 8192, &tmap_vt, &v_full[st], kb * kKB + 64, 0, sh);
         }
+        __syncwarp();
       }
     } else if (warp - 1 < n_active) {
       // ============================ MMA issuers: warp 1 -> warpgroup 0, warp 2 -> warpgroup 1 ============================
-      // One issuing thread per softmax warpgroup, blocking on that warpgroup's barriers in the order in which the
+      // One issuing warp per softmax warpgroup, blocking on that warpgroup's barriers in the order in which the
       // warpgroup arrives on them (S_lo free, S_hi free, P full), so neither warpgroup ever waits for the other's turn.
-      if (lane == 0) {
+      // The whole warp runs the (warp-uniform) loop and one elected lane issues, which keeps every tcgen05.mma operand
+      // in uniform registers.
+      {
         const int w = warp - 1;
         constexpr uint32_t idesc_lo = umma_idesc_bf16(128, kHalfLo);
         constexpr uint32_t idesc_hi = umma_idesc_bf16(128, kKB - kHalfLo);
@@ -178,28 +202,36 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
         mbar_wait(q_full, 0);
         tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tm, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(rel_addr + k * 32),
-                       idesc_g, k != 0);
-        umma_commit(g_full);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tm, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(rel_addr + k * 32),
+                         idesc_g, k != 0);
+          umma_commit(g_full);
+        }
+        __syncwarp();
 
         auto issue_s = [&](int kb) {
           const int st = kb % kStages;
           mbar_wait(&k_full[st], (kb / kStages) & 1);
+          if (w == 0) ATTN_TRACE(2, kb, 0);  // K block in smem
           const uint32_t k_addr = smem_u32(sK + st * kKBytes);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             mbar_wait(&s_free[2 * w + half], kb & 1);
+            if (w == 0) ATTN_TRACE(2, kb, 1 + half);  // S half free -> issue
             tc_fence_after();
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tm + half * kHalfLo, umma_desc_sw128_kmajor(q_addr + k * 32),
-                           umma_desc_sw128_kmajor(k_addr + half * (kHalfLo * 128) + k * 32),
-                           half ? idesc_hi : idesc_lo, k != 0);
-            umma_commit(&s_full[2 * w + half]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(tm + half * kHalfLo, umma_desc_sw128_kmajor(q_addr + k * 32),
+                             umma_desc_sw128_kmajor(k_addr + half * (kHalfLo * 128) + k * 32),
+                             half ? idesc_hi : idesc_lo, k != 0);
+              umma_commit(&s_full[2 * w + half]);
+              if (half == 1) umma_commit(&k_empty[st]);
+            }
+            __syncwarp();
           }
-          umma_commit(&k_empty[st]);
         };
 
         issue_s(0);
@@ -207,16 +239,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           if (kb + 1 < kNumKB) issue_s(kb + 1);
           const int st = kb % kStages;
           mbar_wait(&v_full[st], (kb / kStages) & 1);
+          if (w == 0) ATTN_TRACE(2, kb, 3);  // V block in smem
           mbar_wait(&p_full[w], kb & 1);
+          if (w == 0) ATTN_TRACE(2, kb, 4);  // P full -> issue PV
           tc_fence_after();
-          const uint32_t v_addr = smem_u32(sV + st * kVBytes);
+          if (elect_one_sync()) {
+            const uint32_t v_addr = smem_u32(sV + st * kVBytes);
 #pragma unroll
-          for (int k = 0; k < kKB / 16; ++k) {
-            const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
-            umma_bf16_ts(tm + kColO, tm + kColP + k * 8, umma_desc_sw128_kmajor(va), idesc_o, (kb | k) != 0);
+            for (int k = 0; k < kKB / 16; ++k) {
+              const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
+              umma_bf16_ts(tm + kColO, tm + kColP + k * 8, umma_desc_sw128_kmajor(va), idesc_o, (kb | k) != 0);
+            }
+            umma_commit(&pv_done[w]);
+            umma_commit(&v_empty[st]);
           }
-          umma_commit(&pv_done[w]);
-          umma_commit(&v_empty[st]);
+          __syncwarp();
         }
       }
     }
@@ -274,6 +311,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_arrive(&s_free[2 * w + 1]);
       }
 
+      // De-phase the two warpgroups by about half a key block: both share the SM's MUFU (16 ex2/clk) and both have the
+      // same compute / hand-off rhythm, so in lock-step they fight over MUFU and then idle together; staggered, one
+      // exponentiates while the other waits for its barriers (the offset is neutrally stable, so it persists).
+      if (w == 1 && n_active == 2) {
+        const long long t_start = clock64();
+        while (clock64() - t_start < kStaggerCycles) {
+        }
+      }
+
       const float sc = 0.125f * kLog2e;  // head_dim^-0.5 * log2(e)
       float m_run = 0.f, l_run = 0.f;
       float alpha_pending = 1.0f;  // factor still to be applied to O (after the P*V that is in flight retires)
@@ -321,7 +367,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int i = 0; i < 4; ++i) bh4[i] = lds32(bh_row + kb * 4 + i);
 
         // ---------------- lower half: columns 0..63 ----------------
+        if (quarter == 0) ATTN_TRACE(w, kb, 0);  // block start
         mbar_wait(&s_full[2 * w], kb & 1);
+        if (quarter == 0) ATTN_TRACE(w, kb, 1);  // S lower half ready
         tc_fence_after();
         if (kb == 0) {  // initial reference: row max over the first 64 keys
           float mx = -INFINITY;
@@ -357,7 +405,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (lane == 0) mbar_arrive(&s_free[2 * w]);  // the next block's lower S half may be issued
 
         // ---------------- upper half: columns 64..111 ----------------
+        if (quarter == 0) ATTN_TRACE(w, kb, 2);  // lower half processed
         mbar_wait(&s_full[2 * w + 1], kb & 1);
+        if (quarter == 0) ATTN_TRACE(w, kb, 3);  // S upper half ready
         tc_fence_after();
         float lsum_hi = 0.f, xmax_hi = -INFINITY;
         stream(I64{}, I112{}, lsum_hi, xmax_hi);
@@ -384,9 +434,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         xmax = fmaxf(xmax, xmax_hi);
 
         // ---------------- hand P to the tensor core ----------------
+        if (quarter == 0) ATTN_TRACE(w, kb, 4);  // upper half processed
         if (kb > 0) {
           // the P region and O are ours again once the previous P*V has retired
           mbar_wait(&pv_done[w], (kb - 1) & 1);
+          if (quarter == 0) ATTN_TRACE(w, kb, 5);  // previous PV retired
           tc_fence_after();
           if (__any_sync(0xffffffffu, alpha_pending != 1.0f)) {
 #pragma unroll
@@ -409,6 +461,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[w]);
+        if (quarter == 0) ATTN_TRACE(w, kb, 6);  // P handed over
 
         // lazily raise the reference for the following blocks
         if (xmax > kLazyThreshold) {

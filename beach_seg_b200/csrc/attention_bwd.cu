@@ -27,7 +27,7 @@ namespace abwd {
 constexpr int kGridW = 28, kGridH = 56;
 constexpr int kT = kGridW * kGridH;  // 1568
 constexpr int kThreads = 384;
-constexpr int kRegsControl = 40, kRegsWork = 232;
+constexpr int kRegsControl = 64, kRegsWork = 216;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kBiasRows = kGridH + kGridW;  // 84 rows of the per-(seq,head) bias table [84][T]: bh (56) then bw (28)
 
@@ -117,7 +117,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint64_t* dq_final = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQTile;
   const int head = blockIdx.y, seq = blockIdx.z;
   const int sh = seq * heads + head;
@@ -151,53 +151,63 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
     if (warp == 0) {
-      // ============================ TMA producer ============================
-      if (lane == 0) {
+      // ============================ TMA producer (warp-uniform loop, one elected lane issues) ============================
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(q_full, 2 * kQBytes + kRelRows * 128);
         tma_load_3d(sQ, &tmap_q, q_full, 0, q0, sh);
         tma_load_4d(sdO, &tmap_do, q_full, 0, q0, head, seq);
         tma_load_2d(sRel, &tmap_rel, q_full, 0, 0);
-        for (int kb = 0; kb < kNumKB; ++kb) {
-          const int st = kb % kStagesQ;
-          if (kb >= kStagesQ) mbar_wait(&kv_empty[st], ((kb / kStagesQ) & 1) ^ 1);
-          uint8_t* base = sRing + st * kStageQBytes;
+      }
+      __syncwarp();
+      for (int kb = 0; kb < kNumKB; ++kb) {
+        const int st = kb % kStagesQ;
+        if (kb >= kStagesQ) mbar_wait(&kv_empty[st], ((kb / kStagesQ) & 1) ^ 1);
+        uint8_t* base = sRing + st * kStageQBytes;
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&k_full[st], kStageQBytes);
           tma_load_3d(base, &tmap_k, &k_full[st], 0, kb * kKB, sh);
           tma_load_3d(base + kKBytes, &tmap_v, &k_full[st], 0, kb * kKB, sh);
           tma_load_3d(base + 2 * kKBytes, &tmap_kt, &k_full[st], kb * kKB, 0, sh);
           tma_load_3d(base + 2 * kKBytes + 8192, &tmap_kt, &k_full[st], kb * kKB + 64, 0, sh);
-          if (kb == kStagesQ - 1) {
-            // the rel region is free once G has been computed: bring in relcat^T for the bias-gradient MMA
-            mbar_wait(g_full, 0);
+        }
+        __syncwarp();
+        if (kb == kStagesQ - 1) {
+          // the rel region is free once G has been computed: bring in relcat^T for the bias-gradient MMA
+          mbar_wait(g_full, 0);
+          if (elect_one_sync()) {
             mbar_arrive_expect_tx(relt_full, kRelRegion);
             for (int a = 0; a < 3; ++a) tma_load_2d(sRel + a * 8192, &tmap_relt, relt_full, a * 64, 0);
           }
+          __syncwarp();
         }
       }
     } else if (warp == 1) {
-      // ============================ MMA issuer ============================
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
-        constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
-        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
-        const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), rel_addr = smem_u32(sRel);
-        mbar_wait(q_full, 0);
-        tc_fence_after();
+      // ============================ MMA issuer (warp-uniform loop, one elected lane issues) ============================
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), rel_addr = smem_u32(sRel);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(rel_addr + k * 32),
                        idesc_g, k != 0);
         umma_commit(g_full);
+      }
+      __syncwarp();
 
-        auto issue_sdp = [&](int kb) {
-          const int st = kb % kStagesQ;
-          mbar_wait(&k_full[st], (kb / kStagesQ) & 1);
-          tc_fence_after();
+      auto issue_sdp = [&](int kb) {
+        const int st = kb % kStagesQ;
+        mbar_wait(&k_full[st], (kb / kStagesQ) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t k_addr = smem_u32(sRing + st * kStageQBytes), v_addr = k_addr + kKBytes;
           const uint32_t d = tmem_base + (kb & 1) * kQColBuf;
 #pragma unroll
@@ -209,16 +219,19 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             umma_bf16_ss(d + kQColdP, umma_desc_sw128_kmajor(do_addr + k * 32),
                          umma_desc_sw128_kmajor(v_addr + k * 32), idesc_s, k != 0);
           umma_commit(&sdp_full[kb & 1]);
-        };
+        }
+        __syncwarp();
+      };
 
-        mbar_wait(g_free, 0);
+      mbar_wait(g_free, 0);
+      tc_fence_after();
+      issue_sdp(0);
+      issue_sdp(1);
+      for (int kb = 0; kb < kNumKB; ++kb) {
+        const int st = kb % kStagesQ, buf = kb & 1;
+        mbar_wait(&ds_full[buf], (kb >> 1) & 1);
         tc_fence_after();
-        issue_sdp(0);
-        issue_sdp(1);
-        for (int kb = 0; kb < kNumKB; ++kb) {
-          const int st = kb % kStagesQ, buf = kb & 1;
-          mbar_wait(&ds_full[buf], (kb >> 1) & 1);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t kt_addr = smem_u32(sRing + st * kStageQBytes + 2 * kKBytes);
           const uint32_t a_base = tmem_base + buf * kQColBuf;
 #pragma unroll
@@ -229,19 +242,23 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                          idesc_o, (kb | k) != 0);
           }
           umma_commit(&kv_empty[st]);
-          if (kb + 2 < kNumKB) issue_sdp(kb + 2);
+          if (kb == kNumKB - 1) umma_commit(dq_done);
         }
-        umma_commit(dq_done);
-        // bias gradient: dQ_acc += (8 * dG) relcat   (8 = 1/scale, exact in bf16)
-        mbar_wait(relt_full, 0);
-        mbar_wait(dg_full, 0);
-        tc_fence_after();
+        __syncwarp();
+        if (kb + 2 < kNumKB) issue_sdp(kb + 2);
+      }
+      // bias gradient: dQ_acc += (8 * dG) relcat   (8 = 1/scale, exact in bf16)
+      mbar_wait(relt_full, 0);
+      mbar_wait(dg_full, 0);
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < kRelRows / 16; ++k)
           umma_bf16_ts(tmem_base + kQColdQ, tmem_base + k * 8,
                        umma_desc_sw128_kmajor(rel_addr + (k >> 2) * 8192 + (k & 3) * 32), idesc_o, 1u);
         umma_commit(dq_final);
       }
+      __syncwarp();
     }
   } else {
     // ============================ elementwise warps ============================
@@ -463,7 +480,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
   uint64_t* dkv_done = bars + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kKTile;
   const int head = blockIdx.y, seq = blockIdx.z;
   const int sh = seq * heads + head;
@@ -496,18 +513,21 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   if (warp < 4) {
     if (warp == 0) {
-      // ============================ TMA producer ============================
-      if (lane == 0) {
+      // ============================ TMA producer (warp-uniform loop, one elected lane issues) ============================
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(kv_full, 2 * kKTile * 128);
         tma_load_3d(sK, &tmap_k, kv_full, 0, k0, sh);
         tma_load_3d(sV, &tmap_v, kv_full, 0, k0, sh);
-        for (int j = 0; j < kNumQB; ++j) {
-          const int st = j % kStagesK;
-          if (j >= kStagesK) mbar_wait(&empty[st], ((j / kStagesK) & 1) ^ 1);
+      }
+      __syncwarp();
+      for (int j = 0; j < kNumQB; ++j) {
+        const int st = j % kStagesK;
+        if (j >= kStagesK) mbar_wait(&empty[st], ((j / kStagesK) & 1) ^ 1);
+        if (elect_one_sync()) {
           uint8_t* base = sRing + st * kStageKBytes;
           mbar_arrive_expect_tx(&full[st], 4 * kTileBytes + kTabTxBytes);
           tma_load_3d(base, &tmap_q, &full[st], 0, j * kQB, sh);
@@ -523,18 +543,19 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
           tma_load_2d(tabs + kTabLseOff, &tmap_lse, &full[st], j * kQB, sh);
           tma_load_2d(tabs + kTabDOff, &tmap_dvec, &full[st], j * kQB, sh);
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
-      // ============================ MMA issuer ============================
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-        const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-        mbar_wait(kv_full, 0);
+      // ============================ MMA issuer (warp-uniform loop, one elected lane issues) ============================
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      auto issue_sdp = [&](int j) {
+        const int st = j % kStagesK;
+        mbar_wait(&full[st], (j / kStagesK) & 1);
         tc_fence_after();
-        auto issue_sdp = [&](int j) {
-          const int st = j % kStagesK;
-          mbar_wait(&full[st], (j / kStagesK) & 1);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t q_addr = smem_u32(sRing + st * kStageKBytes), do_addr = q_addr + kTileBytes;
           const uint32_t d = tmem_base + (j & 1) * kKColBuf;
 #pragma unroll
@@ -546,13 +567,16 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
             umma_bf16_ss(d + kKColdP, umma_desc_sw128_kmajor(v_addr + k * 32),
                          umma_desc_sw128_kmajor(do_addr + k * 32), idesc, k != 0);
           umma_commit(&sdp_full[j & 1]);
-        };
-        issue_sdp(0);
-        issue_sdp(1);
-        for (int j = 0; j < kNumQB; ++j) {
-          const int st = j % kStagesK, buf = j & 1;
-          mbar_wait(&pds_full[buf], (j >> 1) & 1);
-          tc_fence_after();
+        }
+        __syncwarp();
+      };
+      issue_sdp(0);
+      issue_sdp(1);
+      for (int j = 0; j < kNumQB; ++j) {
+        const int st = j % kStagesK, buf = j & 1;
+        mbar_wait(&pds_full[buf], (j >> 1) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t qt_addr = smem_u32(sRing + st * kStageKBytes + 2 * kTileBytes);
           const uint32_t dot_addr = qt_addr + kTileBytes;
           const uint32_t a_base = tmem_base + buf * kKColBuf;
@@ -566,9 +590,10 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
                          (j | k) != 0);
           }
           umma_commit(&empty[st]);
-          if (j + 2 < kNumQB) issue_sdp(j + 2);
+          if (j == kNumQB - 1) umma_commit(dkv_done);
         }
-        umma_commit(dkv_done);
+        __syncwarp();
+        if (j + 2 < kNumQB) issue_sdp(j + 2);
       }
     }
   } else {

@@ -66,7 +66,7 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kStages);
   float* sPar = reinterpret_cast<float*>(smem + kOffPar);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tiles_x = W / kTileW, tiles_y = H / kTileH - prm.ty_begin;
   const long long num_tiles = static_cast<long long>(B) * tiles_y * tiles_x;
 
@@ -98,12 +98,15 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      if (elect_one_sync()) {
       mbar_arrive_expect_tx(w_full, kWBytes);
       for (int t = 0; t < 9; t += 3) tma_load_2d(sW + t * 8192, &tmap_w, w_full, 0, t * 64);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -112,15 +115,18 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int b = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kABytes);
-          tma_load_4d(sA + stage * kABytes, &tmap_x, &full_bar[stage], 0, tx * kTileW + (tap % 3) - 1,
-                      ty * kTileH + (tap / 3) - 1 - prm.y_in0, b);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full_bar[stage], kABytes);
+            tma_load_4d(sA + stage * kABytes, &tmap_x, &full_bar[stage], 0, tx * kTileW + (tap % 3) - 1,
+                        ty * kTileH + (tap / 3) - 1 - prm.y_in0, b);
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       mbar_wait(w_full, 0);
       tc_fence_after();
@@ -134,13 +140,16 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+          if (elect_one_sync()) {
+            const uint32_t a_addr = smem_u32(sA + stage * kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr + k * 32),
-                         umma_desc_sw128_kmajor(w_addr + tap * 8192 + k * 32), idesc, (tap | k) != 0);
-          umma_commit(&empty_bar[stage]);
-          if (tap == 8) umma_commit(&tmem_full[as]);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr + k * 32),
+                           umma_desc_sw128_kmajor(w_addr + tap * 8192 + k * 32), idesc, (tap | k) != 0);
+            umma_commit(&empty_bar[stage]);
+            if (tap == 8) umma_commit(&tmem_full[as]);
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (++as == 2) { as = 0; aphase ^= 1; }

@@ -400,13 +400,53 @@ __global__ void decode_palette_kernel(const float* __restrict__ pred, const floa
     if (out_i64) out_i64[i] = bi;
   }
 }
+// uint8 output, out_size a multiple of 4: 4 consecutive output pixels per thread, one 32-bit store
+__global__ void decode_palette_vec4_kernel(const float* __restrict__ pred, const float* __restrict__ palette_norm,
+                                           int ncls, uint8_t* __restrict__ out_u8, const uint8_t* __restrict__ nodata,
+                                           const int* __restrict__ idx, int B, int H, int W, int OS) {
+  const int ow = OS >> 2;
+  const long long total = (long long)B * OS * ow;
+  const long long plane = 2LL * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = static_cast<int>(i % ow) * 4;
+    const int oy = static_cast<int>((i / ow) % OS);
+    const int b = static_cast<int>(i / ((long long)OS * ow));
+    const int sy = idx ? idx[oy] : oy;
+    const float* row = pred + (long long)b * 3 * plane + (long long)(H + sy) * W;
+    const float* pal = palette_norm + (long long)b * ncls * 3;
+    const long long o = ((long long)b * OS + oy) * OS + ox;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sx = idx ? idx[ox + j] : ox + j;
+      const float v0 = row[sx], v1 = row[plane + sx], v2 = row[2 * plane + sx];
+      float best = 0.f;
+      uint32_t bi = 0;
+      for (int k = 0; k < ncls; ++k) {
+        const float d0 = __fsub_rn(v0, pal[k * 3 + 0]);
+        const float d1 = __fsub_rn(v1, pal[k * 3 + 1]);
+        const float d2 = __fsub_rn(v2, pal[k * 3 + 2]);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+        if (k == 0 || d < best) { best = d; bi = k; }
+      }
+      if (nodata != nullptr && nodata[o + j]) bi = 0;
+      packed |= bi << (8 * j);
+    }
+    *reinterpret_cast<uint32_t*>(out_u8 + o) = packed;
+  }
+}
 int launch_decode_palette(const float* pred, const float* palette_norm, int num_classes, uint8_t* out_u8,
                           long long* out_i64, const uint8_t* nodata, const int* idx, int B, int H, int W,
                           int out_size, cudaStream_t stream) {
   const long long total = (long long)B * out_size * out_size;
   ProfScope prof(CAT_DECODE, 0, static_cast<double>(B) * H * W * 12 + static_cast<double>(total), stream);
-  decode_palette_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(pred, palette_norm, num_classes, out_u8, out_i64,
-                                                                    nodata, idx, B, H, W, out_size);
+  if (out_u8 != nullptr && out_i64 == nullptr && out_size % 4 == 0 && reinterpret_cast<uintptr_t>(out_u8) % 4 == 0)
+    decode_palette_vec4_kernel<<<blocks_for(total / 4, 256), 256, 0, stream>>>(pred, palette_norm, num_classes, out_u8,
+                                                                              nodata, idx, B, H, W, out_size);
+  else
+    decode_palette_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(pred, palette_norm, num_classes, out_u8, out_i64,
+                                                                      nodata, idx, B, H, W, out_size);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -444,37 +484,98 @@ __global__ void vote_accumulate_kernel(uint32_t* __restrict__ counter, int Hs, i
     }
   }
 }
+// Tiles that do not overlap one another (no atomics needed), crop and scene width multiples of 4: 4 pixels per thread
+// -- one u32 of class ids in, one uint4 of counters read-modify-written -- so the kernel moves full sectors instead of
+// single bytes.  A tile whose xmin is not a multiple of 4 takes the scalar path for its pixels.
+__global__ void vote_accumulate_vec4_kernel(uint32_t* __restrict__ counter, int Hs, int Ws,
+                                            const uint8_t* __restrict__ cls, int n_tiles, int crop,
+                                            const int* __restrict__ boxes) {
+  const int cw = crop >> 2;
+  const long long per = (long long)crop * cw;
+  const long long total = per * n_tiles;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = static_cast<int>(i / per);
+    const int sy = static_cast<int>((i % per) / cw);
+    const int sx = static_cast<int>(i % cw) * 4;
+    const int dy = boxes[t * 4 + 1] + sy, dx = boxes[t * 4 + 0] + sx;
+    if (dy < 0 || dy >= Hs || dx + 3 < 0 || dx >= Ws) continue;
+    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(cls + ((long long)t * crop + sy) * crop + sx);
+    uint32_t* w = counter + (long long)dy * Ws + dx;
+    if (dx >= 0 && dx + 3 < Ws && (dx & 3) == 0) {
+      uint4 v = *reinterpret_cast<uint4*>(w);
+      uint32_t pv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t c = (c4 >> (8 * j)) & 0xFFu;
+        if (c <= 3) {
+          const uint32_t byte = ((pv[j] >> (8 * c)) + 1u) & 0xFFu;
+          pv[j] = (pv[j] & ~(0xFFu << (8 * c))) | (byte << (8 * c));
+        }
+      }
+      *reinterpret_cast<uint4*>(w) = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+    } else {
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t c = (c4 >> (8 * j)) & 0xFFu;
+        if (dx + j < 0 || dx + j >= Ws || c > 3) continue;
+        const uint32_t old = w[j];
+        const uint32_t byte = ((old >> (8 * c)) + 1u) & 0xFFu;
+        w[j] = (old & ~(0xFFu << (8 * c))) | (byte << (8 * c));
+      }
+    }
+  }
+}
 int launch_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
                            const int* boxes, int use_atomics, cudaStream_t stream) {
   const long long total = (long long)crop * crop * n_tiles;
   if (total == 0) return 0;
   ProfScope prof(CAT_VOTE, 0, static_cast<double>(total) * 9, stream);
-  vote_accumulate_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(counter, Hs, Ws, cls, n_tiles, crop, boxes,
-                                                                     use_atomics);
+  const bool vec = !use_atomics && (crop % 4 == 0) && (Ws % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(counter) % 16 == 0) && (reinterpret_cast<uintptr_t>(cls) % 4 == 0);
+  if (vec)
+    vote_accumulate_vec4_kernel<<<blocks_for(total / 4, 256), 256, 0, stream>>>(counter, Hs, Ws, cls, n_tiles, crop,
+                                                                               boxes);
+  else
+    vote_accumulate_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(counter, Hs, Ws, cls, n_tiles, crop, boxes,
+                                                                       use_atomics);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
 // np.argmax(counter, axis=2) (src/predict.py:100): first maximum wins, untouched pixels -> 0
-__global__ void vote_argmax_kernel(const uint32_t* __restrict__ counter, uint8_t* __restrict__ out, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const uint32_t w = counter[i];
-    uint32_t best = w & 0xFFu;
-    uint8_t bi = 0;
+__device__ __forceinline__ uint32_t vote_argmax1(uint32_t w) {
+  uint32_t best = w & 0xFFu, bi = 0;
 #pragma unroll
-    for (int k = 1; k < 4; ++k) {
-      const uint32_t v = (w >> (8 * k)) & 0xFFu;
-      if (v > best) { best = v; bi = static_cast<uint8_t>(k); }
-    }
-    out[i] = bi;
+  for (uint32_t k = 1; k < 4; ++k) {
+    const uint32_t v = (w >> (8 * k)) & 0xFFu;
+    if (v > best) { best = v; bi = k; }
   }
+  return bi;
+}
+__global__ void vote_argmax_kernel(const uint32_t* __restrict__ counter, uint8_t* __restrict__ out, long long n) {
+  // 4 pixels per thread: uint4 in, u32 out (the tail is handled by the first threads)
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 w = reinterpret_cast<const uint4*>(counter)[i];
+    reinterpret_cast<uint32_t*>(out)[i] = vote_argmax1(w.x) | (vote_argmax1(w.y) << 8) | (vote_argmax1(w.z) << 16) |
+                                          (vote_argmax1(w.w) << 24);
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = static_cast<uint8_t>(vote_argmax1(counter[i]));
+}
+__global__ void vote_argmax_scalar_kernel(const uint32_t* __restrict__ counter, uint8_t* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = static_cast<uint8_t>(vote_argmax1(counter[i]));
 }
 int launch_vote_argmax(const uint32_t* counter, uint8_t* out, long long n, cudaStream_t stream) {
   if (n == 0) return 0;
   ProfScope prof(CAT_VOTE, 0, static_cast<double>(n) * 5, stream);
-  vote_argmax_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(counter, out, n);
+  if (reinterpret_cast<uintptr_t>(counter) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0)
+    vote_argmax_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, stream>>>(counter, out, n);
+  else
+    vote_argmax_scalar_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(counter, out, n);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

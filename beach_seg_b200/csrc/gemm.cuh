@@ -225,7 +225,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   const int num_n_tiles = N / BLOCK_N;
@@ -253,42 +253,43 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const long long mt = tile / num_n_tiles;
-        const int bidx = static_cast<int>(mt / tiles_per_batch);
-        const int m0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * GEMM_BLOCK_M;
-        const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long mt = tile / num_n_tiles;
+      const int bidx = static_cast<int>(mt / tiles_per_batch);
+      const int m0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * GEMM_BLOCK_M;
+      const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0, bidx);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
@@ -300,10 +301,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (kb == num_k_blocks - 1) umma_commit(&tmem_full[as]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================

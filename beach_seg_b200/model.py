@@ -124,11 +124,15 @@ class PromptModel(torch.nn.Module):
         return x * std + mean
 
     def create_trainable_params(self, datamodule: Any):
-        prompt_imgs = datamodule.prompt_imgs  # list of dicts like BeachSegDataset.get_crop returns
-        self.prompt_batch = {k: [torch.as_tensor(p[k]) for p in prompt_imgs] for k in prompt_imgs[0]
-                             if k in ("image", "mask", "nodata", "crop_idx")}
-        params = [torch.nn.Parameter(img.to(self.device, torch.float32), requires_grad=True)
-                  for img in self.prompt_batch["image"]]
+        """src/model.py:115-130: default-collate the prompt items (tensors stacked, strings listed), then replace
+        "image" by the list of trainable Parameters."""
+        from torch.utils.data import default_collate
+
+        prompt_imgs = [{k: (torch.as_tensor(v) if not isinstance(v, (str, int, float)) else v) for k, v in p.items()}
+                       for p in datamodule.prompt_imgs]
+        self.prompt_batch = default_collate(prompt_imgs)
+        params = [torch.nn.Parameter(self.prompt_batch["image"][i].to(self.device, torch.float32).clone(),
+                                     requires_grad=True) for i in range(len(prompt_imgs))]
         self.prompt_params_list = torch.nn.ParameterList(params)
         self.prompt_batch["image"] = params
 
@@ -156,8 +160,8 @@ class PromptModel(torch.nn.Module):
             idx = list(batch_idxes)
         prompt_batch = {k: [v[i] for i in idx] for k, v in self.prompt_batch.items()}
         # training: the stack keeps the graph to the selected prompt parameters (src/model.py:194)
-        prompt_batch["image"] = torch.stack([p if train else p.detach() for p in prompt_batch["image"]],
-                                            dim=0).to(self.device)
+        prompt_batch["image"] = torch.stack([p.to(self.device) if train else p.detach().to(self.device)
+                                             for p in prompt_batch["image"]], dim=0)
         prompt_batch["mask"] = torch.stack([torch.as_tensor(m) for m in prompt_batch["mask"]], dim=0).to(self.device)
         prompt_batch = (self.train_aug if train else self.aug)(prompt_batch)
         prompt_color_mask_norm = ops.colorize_norm(prompt_batch["mask"], batch_palette.to(self.device))
