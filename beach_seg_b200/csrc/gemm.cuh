@@ -122,6 +122,65 @@ __device__ __forceinline__ void gemm_epi_f32_chunk(const GemmEpiParams& ep, cons
   __syncwarp();
 }
 
+// ---- bf16-output epilogues with a row-major destination (bias / GELU / GELU') ---------------------------------------
+// Same problem as above: thread <-> row means one 16-byte store per lane hits 32 different lines per instruction, and
+// for the K = 1024 GEMMs (8192 MMA cycles per tile) those L1 wavefronts do not hide behind the MMA.  The 32x32 chunk is
+// packed to bf16, transposed through the per-warp swizzled smem tile and written 8 rows x 64 contiguous bytes per
+// instruction (4 lanes per row).
+__device__ __forceinline__ void gemm_epi_bf16_store(__nv_bfloat16* out, long long ldc, const float (&v)[32],
+                                                    uint32_t* stg, long long row0, int nvalid, int n, int lane) {
+  // 1) this thread's row (32 bf16 = 4 x 16 B) -> smem, 16-byte chunk index XOR ((row >> 1) & 3)
+  const int swz = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ swz) << 2)) =
+        make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+  __syncwarp();
+  // 2) read back 8 rows per instruction, 4 lanes per row, and store
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2);
+    const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((c ^ ((rr >> 1) & 3)) << 2));
+    if (rr < nvalid) *reinterpret_cast<uint4*>(out + (row0 + rr) * ldc + n + c * 8) = o;
+  }
+  __syncwarp();
+}
+template <int MODE>
+__device__ __forceinline__ void gemm_epi_bf16_chunk(const GemmEpiParams& ep, float (&v)[32], uint32_t* stg,
+                                                    long long row0, int nvalid, int n, int lane) {
+  const long long m = row0 + lane;
+  if (ep.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + i));
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  if constexpr (MODE == EPI_BF16_GELU) {
+    if (ep.aux != nullptr) gemm_epi_bf16_store(ep.aux, ep.ldc, v, stg, row0, nvalid, n, lane);  // saved pre-activation
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if constexpr (MODE == EPI_DGELU) {
+    if (lane < nvalid) {
+      const __nv_bfloat16* z = ep.aux + m * ep.ldc + n;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(z + i);
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[i + 2 * j] *= gelu_erf_grad(__uint_as_float(w[j] << 16));
+          v[i + 2 * j + 1] *= gelu_erf_grad(__uint_as_float(w[j] & 0xffff0000u));
+        }
+      }
+    }
+  }
+  gemm_epi_bf16_store(reinterpret_cast<__nv_bfloat16*>(ep.out), ep.ldc, v, stg, row0, nvalid, n, lane);
+}
+
 template <int MODE>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, float (&v)[32], long long m, int n) {
   // v: 32 consecutive accumulator columns n..n+31 of row m
@@ -336,6 +395,50 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tmem_ld_wait();
           gemm_epi_f32_chunk<MODE>(ep, v, pr, stg, row0, nvalid, n0 + c, lane);
           pr = pn;
+        }
+      } else if constexpr (MODE == EPI_BF16 || MODE == EPI_BF16_GELU || MODE == EPI_DGELU) {
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 1024;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          gemm_epi_bf16_chunk<MODE>(ep, v, stg, row0, nvalid, n0 + c, lane);
+        }
+      } else if constexpr (MODE == EPI_QKV) {
+        // q / k: the 32 rows of a warp are 32 consecutive tokens of one sequence (T is a multiple of 32), i.e. 32
+        // consecutive 128-byte rows of [seq, head, t, 64]: same coalesced store as the row-major epilogues.
+        // v^T keeps the per-thread transposed scatter (one 64-byte run along t per instruction).
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 1024;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const int D = ep.heads * 64;
+        const long long seq = row0 / ep.T;
+        const long long t0 = row0 % ep.T;
+        const bool rows_in_seq = (ep.T % 32) == 0;
+#pragma unroll 1
+        for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          const int n = n0 + c;
+          const int which = n / D;
+          if (which < 2 && rows_in_seq) {
+            if (ep.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
+            }
+            const int head = (n % D) >> 6;
+            __nv_bfloat16* base = (which == 0 ? ep.q : ep.k) + ((seq * ep.heads + head) * ep.T + t0) * 64;
+            gemm_epi_bf16_store(base, 64, v, stg, 0, nvalid, n & 63, lane);
+          } else if (lane < nvalid) {
+            gemm_epilogue_chunk<MODE>(ep, v, m, n);
+          }
         }
       } else {
         mbar_wait(&tmem_full[as], aphase);
