@@ -27,6 +27,17 @@ int main(int argc, char** argv) {
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("sync: %s\n", cudaGetErrorString(e));
+  {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    for (int it = 0; it < 5; ++it) launch_attention(q, k, vt, rel, out, nullptr, nseq, heads, 56, 28, 0);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    printf("attention nseq=%d: %.3f ms per launch (S k-steps %d, PV k-steps %d, skip exp %d)\n", nseq, ms / 5,
+           (int)BSEG_ATTN_S_KSTEPS, (int)([] { using namespace bseg::attn; return BSEG_ATTN_PV_KSTEPS; }()), (int)BSEG_ATTN_SKIP_EXP);
+  }
   long long tr[3][16][16];
   cudaMemcpyFromSymbol(tr, g_attn_trace, sizeof(tr));
   const long long t0 = tr[0][0][0];

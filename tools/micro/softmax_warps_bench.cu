@@ -44,6 +44,15 @@ __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.055170976f, 0.24260971f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992818f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 #define LDWAIT() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 #define STWAIT() asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory")
 
@@ -86,7 +95,8 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) bench(int iters, long long* c
         float x0 = fmaf(s[i], sc, bw[(col0) % 28]) + og[(col0 / 28) & 3];
         float x1 = fmaf(s[i + 1], sc, bw[(col0 + 1) % 28]) + og[((col0 + 1) / 28) & 3];
         xmax = fmaxf(xmax, fmaxf(x0, x1));
-        float p0 = MODE == 1 ? x0 * 0.5f : ex2(x0), p1 = MODE == 1 ? x1 * 0.5f : ex2(x1);
+        float p0 = MODE == 1 ? x0 * 0.5f : ex2(x0);
+        float p1 = MODE == 1 ? x1 * 0.5f : ((MODE == 3 && ((i >> 1) & 1)) || MODE == 4) ? ex2_poly(x1) : ex2(x1);
         lsum += p0 + p1;
         pk[i >> 1] = pack(p0, p1);
       }
@@ -146,6 +156,9 @@ int main() {
   run<4, 0>("softmax step, 4 threads per row (32x3+16)", cyc, sink);
   run<2, 1>("no MUFU, 2 threads per row", cyc, sink);
   run<4, 1>("no MUFU, 4 threads per row", cyc, sink);
+  run<2, 3>("25% polynomial exp2, 2 threads per row", cyc, sink);
+  run<2, 4>("50% polynomial exp2, 2 threads per row", cyc, sink);
+  run<4, 3>("25% polynomial exp2, 4 threads per row", cyc, sink);
   run<2, 2>("no TMEM store, 2 threads per row", cyc, sink);
   run<4, 2>("no TMEM store, 4 threads per row", cyc, sink);
   return 0;
