@@ -359,11 +359,19 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     using I64 = std::integral_constant<int, 64>;
     using I96 = std::integral_constant<int, 96>;
 
+    // bias rows of the block (global table, L2 latency): fetched one key block ahead
+    float bnext[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bnext[i] = valid ? tab[i * kT + qi] : 0.f;
     for (int kb = 0; kb < kNumKB; ++kb) {
       const int buf = kb & 1;
       float boff[4], acc4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) boff[i] = (valid ? tab[(kb * 4 + i) * kT + qi] : 0.f) - lse_q;
+      for (int i = 0; i < 4; ++i) boff[i] = bnext[i] - lse_q;
+      if (kb + 1 < kNumKB) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bnext[i] = valid ? tab[((kb + 1) * 4 + i) * kT + qi] : 0.f;
+      }
       mbar_wait(&sdp_full[buf], (kb >> 1) & 1);
       tc_fence_after();
       const uint32_t sbase = lane_base + buf * kQColBuf;

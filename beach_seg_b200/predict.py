@@ -62,6 +62,48 @@ class TilePredictor:
         return ops.decode_palette(out.pred_masks, pal_norm, out_size=self.crop_size, dtype=torch.uint8)
 
 
+class HostScenePipeline:
+    """Host-buffer front end of `TilePredictor` for callers that hold the scene in (pinned) host memory, like the
+    reference's numpy pipeline does: every `step()` copies the uint16 scene host->device, predicts its tiles, votes
+    into the device canvas and copies the class maps back to a pinned host buffer.  The copies run on a side stream
+    with two device / host buffers, so step i+1's upload and step i-1's download overlap step i's compute."""
+
+    def __init__(self, predictor: TilePredictor, scene_shape, n_tiles: int, crop_size: int):
+        dev = predictor.model.device
+        self.predictor, self.dev = predictor, dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.scene_dev = [torch.empty(scene_shape, dtype=torch.int16, device=dev) for _ in range(2)]
+        self.cls_host = [torch.empty((n_tiles, crop_size, crop_size), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.buf_free = [torch.cuda.Event() for _ in range(2)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+
+    def step(self, scene_host: torch.Tensor, nodata, stats, boxes, prompt_images, prompt_cls, palette, canvas):
+        """scene_host: pinned int16/uint16 [4,Hs,Ws].  Returns the pinned host tensor that will hold this step's class
+        maps once `d2h_done[slot]` (also returned) has completed."""
+        b = self.i % 2
+        self.i += 1
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.buf_free[b])      # the compute that last read this device buffer
+            self.scene_dev[b].copy_(scene_host, non_blocking=True)
+            self.h2d_done[b].record(self.copy_stream)
+        cur.wait_event(self.h2d_done[b])
+        cls = self.predictor.predict_tiles(self.scene_dev[b], nodata, stats, boxes, prompt_images, prompt_cls, palette)
+        ops.vote_accumulate(canvas, cls, boxes, overlapping=False)
+        self.buf_free[b].record(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.buf_free[b])
+            cls.record_stream(self.copy_stream)
+            self.cls_host[b].copy_(cls, non_blocking=True)
+            self.d2h_done[b].record(self.copy_stream)
+        return self.cls_host[b], self.d2h_done[b]
+
+    def drain(self):
+        self.copy_stream.synchronize()
+
+
 class NoPromptPredictor:
     """The tensor part of src/predict_no_prompt.py:270-304, batched over tiles: HF-processor preprocessing of the uint8
     crops, `n_prompts` prompts per tile with `feature_ensemble=True` (ensemble grouped per tile), mean over the
