@@ -66,6 +66,10 @@ SIGNATURES = {
     "bseg_scene_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bseg_ingest_u16x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f3, _f3, _vp, _vp, _ll, _vp, _vp,
                                _vp]),
+    "bseg_scene_stats_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "bseg_ingest_f32x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f3, _f3, _vp, _vp, _ll, _vp, _vp,
+                               _vp]),
+    "bseg_merge_mosaic": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "bseg_preprocess_u8": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _f3, _f3, _vp, _vp]),
     "bseg_colorize_resize_norm255": (_i, [_vp, _vp, _i, _f3, _f3, _vp, _vp, _i, _i, _i, _vp]),
     "bseg_postprocess_semantic": (_i, [_vp, _vp, _i, _f3, _f3, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -74,6 +78,8 @@ SIGNATURES = {
     "bseg_mean_over_prompts": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "bseg_vote_accumulate": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
     "bseg_vote_argmax": (_i, [_vp, _vp, _ll, _vp]),
+    "bseg_paste_tiles_u8": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "bseg_overlay_prediction": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _vp]),
     "bseg_loss_smoothl1_fwd_bwd": (_i, [_vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "bseg_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp]),
     "bseg_layernorm1024": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _ll, _f, _vp]),

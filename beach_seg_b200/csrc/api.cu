@@ -709,6 +709,32 @@ int bseg_ingest_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int 
                        static_cast<cudaStream_t>(stream));
 }
 
+int bseg_scene_stats_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, uint32_t* scratch,
+                         void* stream) {
+  BSEG_REQUIRE(Hs > 0 && Ws > 0, "scene_stats_f32: empty scene");
+  return launch_scene_stats_f32(scene, nodata, Hs, Ws, stats, scratch, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_ingest_f32x4(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                      const int32_t* boxes, int n_tiles, int crop, const int32_t* coef, const int32_t* bounds,
+                      int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,
+                      long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, void* stream) {
+  BSEG_REQUIRE(n_tiles >= 0 && crop > 0 && ksize > 0, "ingest_f32: bad arguments");
+  int band, max_rows;
+  ingest_geometry(crop, &band, &max_rows);
+  return launch_ingest_f32(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, band, max_rows,
+                           mean, stdv, out_nchw, static_cast<__nv_bfloat16*>(out_patch), patch_tile_stride, out_u8,
+                           out_nodata, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_merge_mosaic(const float* data, const uint8_t* yesdata, int n_rasters, int channels, int Hs, int Ws,
+                      float* mean, uint8_t* nodata, void* stream) {
+  BSEG_REQUIRE(n_rasters > 0 && channels > 0 && Hs > 0 && Ws > 0 && mean != nullptr && nodata != nullptr,
+               "merge_mosaic: bad arguments");
+  return launch_merge_mosaic(data, yesdata, n_rasters, channels, Hs, Ws, mean, nodata,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int bseg_preprocess_u8(const uint8_t* images, int layout_chw, int n, int crop, const int32_t* coef,
                        const int32_t* bounds, int ksize, int precision_bits, const float* mean255, const float* std255,
                        float* out_nchw, void* stream) {
@@ -771,6 +797,19 @@ int bseg_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, 
 
 int bseg_vote_argmax(const uint32_t* counter, uint8_t* out, long long n_pixels, void* stream) {
   return launch_vote_argmax(counter, out, n_pixels, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_paste_tiles_u8(uint8_t* canvas, int Hs, int Ws, const uint8_t* crops, int n_tiles, int crop,
+                        const int32_t* boxes, void* stream) {
+  BSEG_REQUIRE(Hs > 0 && Ws > 0 && n_tiles >= 0 && crop > 0, "paste_tiles: bad arguments");
+  return launch_paste_tiles(canvas, Hs, Ws, crops, n_tiles, crop, boxes, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_overlay_prediction(const uint8_t* img, const uint8_t* pred, const uint8_t* class_rgba, int n_classes,
+                            long long n_pixels, uint8_t* out, void* stream) {
+  BSEG_REQUIRE(n_classes > 0 && n_classes <= 256 && n_pixels >= 0, "overlay_prediction: bad arguments");
+  return launch_overlay_prediction(img, pred, class_rgba, n_classes, n_pixels, out,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uint8_t* yesdata, float beta,

@@ -582,6 +582,120 @@ int launch_vote_argmax(const uint32_t* counter, uint8_t* out, long long n, cudaS
 }
 
 // ----------------------------------------------------------------------------------------------
+// Accumulator.update's image paste (src/predict.py:157): canvas[dy0:dy1, dx0:dx1] = img_crop[sy0:sy1, sx0:sx1] for a
+// batch of tiles.  Overlapping tiles of one scene carry identical pixels (both are crops of the same composite), so
+// the write order does not matter.
+// ----------------------------------------------------------------------------------------------
+__global__ void paste_tiles_kernel(uint8_t* __restrict__ canvas, int Hs, int Ws, const uint8_t* __restrict__ crops,
+                                   int n_tiles, int crop, const int* __restrict__ boxes) {
+  const long long per = (long long)crop * crop;
+  const long long total = per * n_tiles;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = static_cast<int>(i / per);
+    const int sy = static_cast<int>((i % per) / crop);
+    const int sx = static_cast<int>(i % crop);
+    const int dy = boxes[t * 4 + 1] + sy, dx = boxes[t * 4 + 0] + sx;
+    if (dy < 0 || dy >= Hs || dx < 0 || dx >= Ws) continue;
+    const uint8_t* src = crops + i * 3;
+    uint8_t* dst = canvas + ((long long)dy * Ws + dx) * 3;
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+  }
+}
+int launch_paste_tiles(uint8_t* canvas, int Hs, int Ws, const uint8_t* crops, int n_tiles, int crop, const int* boxes,
+                       cudaStream_t stream) {
+  const long long total = (long long)crop * crop * n_tiles;
+  if (total == 0) return 0;
+  ProfScope prof(CAT_VOTE, 0, static_cast<double>(total) * 6, stream);
+  paste_tiles_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(canvas, Hs, Ws, crops, n_tiles, crop, boxes);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// overlay_prediction (src/util/img_util.py:98-116): Image.alpha_composite(RGB->RGBA base, class-colour layer).convert
+// ("RGB").  Pillow's integer compositing (libImaging/AlphaComposite.c) for an opaque destination reduces to
+//   coef1 = a * 128, coef2 = 255 * 128 - coef1, t = src * coef1 + dst * coef2 + (0x80 << 7),
+//   out = (((t >> 8) + t) >> 8) >> 7
+// and a == 0 (class without a colour, or class id outside the table) copies the base pixel.
+// rgba: uint8 [n_classes][4] = (r, g, b, alpha) per class id.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t pil_blend(uint32_t src, uint32_t dst, uint32_t a) {
+  const uint32_t coef1 = a << 7, coef2 = (255u << 7) - coef1;
+  const uint32_t t = src * coef1 + dst * coef2 + (0x80u << 7);
+  return static_cast<uint8_t>((((t >> 8) + t) >> 8) >> 7);
+}
+__global__ void overlay_prediction_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ pred,
+                                          const uint8_t* __restrict__ rgba, int n_classes, long long npix,
+                                          uint8_t* __restrict__ out) {
+  __shared__ uint32_t table[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    table[i] = i < n_classes ? reinterpret_cast<const uint32_t*>(rgba)[i] : 0u;
+  __syncthreads();
+  // 4 pixels (12 bytes) per thread: one u32 of class ids in, three u32 of RGB in and out
+  const long long n4 = npix >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t c4 = reinterpret_cast<const uint32_t*>(pred)[i];
+    uint32_t w[3] = {reinterpret_cast<const uint32_t*>(img)[3 * i], reinterpret_cast<const uint32_t*>(img)[3 * i + 1],
+                     reinterpret_cast<const uint32_t*>(img)[3 * i + 2]};
+    uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t e = table[(c4 >> (8 * j)) & 0xFFu];
+      const uint32_t a = e >> 24;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int byte = 3 * j + c;
+        const uint32_t d = (w[byte >> 2] >> (8 * (byte & 3))) & 0xFFu;
+        const uint32_t v = a ? pil_blend((e >> (8 * c)) & 0xFFu, d, a) : d;
+        o[byte >> 2] |= v << (8 * (byte & 3));
+      }
+    }
+    reinterpret_cast<uint32_t*>(out)[3 * i] = o[0];
+    reinterpret_cast<uint32_t*>(out)[3 * i + 1] = o[1];
+    reinterpret_cast<uint32_t*>(out)[3 * i + 2] = o[2];
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t e = table[pred[i]];
+    const uint32_t a = e >> 24;
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t d = img[3 * i + c];
+      out[3 * i + c] = a ? pil_blend((e >> (8 * c)) & 0xFFu, d, a) : static_cast<uint8_t>(d);
+    }
+  }
+}
+__global__ void overlay_prediction_scalar_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ pred,
+                                                 const uint8_t* __restrict__ rgba, int n_classes, long long npix,
+                                                 uint8_t* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cls = pred[i];
+    const uint32_t a = cls < n_classes ? rgba[cls * 4 + 3] : 0u;
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t d = img[3 * i + c];
+      out[3 * i + c] = a ? pil_blend(rgba[cls * 4 + c], d, a) : static_cast<uint8_t>(d);
+    }
+  }
+}
+int launch_overlay_prediction(const uint8_t* img, const uint8_t* pred, const uint8_t* rgba, int n_classes,
+                              long long npix, uint8_t* out, cudaStream_t stream) {
+  if (npix == 0) return 0;
+  ProfScope prof(CAT_VOTE, 0, static_cast<double>(npix) * 7, stream);
+  const bool vec = ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(pred) |
+                     reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(rgba)) % 4 == 0);
+  if (vec)
+    overlay_prediction_kernel<<<blocks_for((npix + 3) / 4, 256), 256, 0, stream>>>(img, pred, rgba, n_classes, npix,
+                                                                                    out);
+  else
+    overlay_prediction_scalar_kernel<<<blocks_for(npix, 256), 256, 0, stream>>>(img, pred, rgba, n_classes, npix, out);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // SegGptLoss of the reference (src/model.py:40-64): smooth-L1(beta) between pred_masks and [0 ; labels],
 // masked by [0 ; yesdata], sum / keep.sum().  As written, `keep_mask.unsqueeze(1)` broadcasts to a BxB cross
 // product: loss = sum_px (sum_j l_j[px]) * (sum_i keep_i[px]) / sum(keep).  per_sample=1 gives the intended

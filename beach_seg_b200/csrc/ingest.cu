@@ -4,6 +4,8 @@
 //   PIL resize(BICUBIC) + /255     src/data.py:93-124             (two-pass fixed-point 8-bit resampler)
 //   K.Normalize(mean, std)         src/data.py:226-229
 // The scene-global statistics of tif_image (min over valid pixels, per-channel max) are a separate reduction.
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"
@@ -14,15 +16,24 @@ namespace bseg {
 // scene statistics.  Composite channels: c0 = band3, c1 = band2, c2 = mean(band0, band1).
 //   stats[0] = min over valid pixels and the 3 channels   (geo_util.py:459)
 //   stats[1..3] = per-channel max over ALL pixels          (geo_util.py:463-464 runs before the nodata zeroing)
-// All values are non-negative floats, so the IEEE bit pattern is order preserving and integer atomics work.
+// Scene type T: uint16 (raw Planet Dove counts) or float32 (the reference's reprojected / averaged mosaic, which may
+// contain negative values after cubic resampling).  Floats are mapped to order-preserving unsigned keys for the atomics.
 // ----------------------------------------------------------------------------------------------
-__global__ void scene_stats_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ nodata,
-                                   long long npix, unsigned int* __restrict__ scratch) {
-  float mn = INFINITY, mx0 = 0.f, mx1 = 0.f, mx2 = 0.f;
+__device__ __forceinline__ unsigned int float_key(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+template <typename T>
+__global__ void scene_stats_kernel(const T* __restrict__ scene, const uint8_t* __restrict__ nodata, long long npix,
+                                   unsigned int* __restrict__ scratch) {
+  float mn = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
        i += (long long)gridDim.x * blockDim.x) {
     const float b0 = scene[i], b1 = scene[npix + i], b2 = scene[2 * npix + i], b3 = scene[3 * npix + i];
-    const float c2 = (b0 + b1) * 0.5f;
+    const float c2 = __fmul_rn(__fadd_rn(b0, b1), 0.5f);
     mx0 = fmaxf(mx0, b3);
     mx1 = fmaxf(mx1, b2);
     mx2 = fmaxf(mx2, c2);
@@ -33,27 +44,76 @@ __global__ void scene_stats_kernel(const uint16_t* __restrict__ scene, const uin
   mx1 = warp_max(mx1);
   mx2 = warp_max(mx2);
   if ((threadIdx.x & 31) == 0) {
-    atomicMin(&scratch[0], __float_as_uint(mn));
-    atomicMax(&scratch[1], __float_as_uint(mx0));
-    atomicMax(&scratch[2], __float_as_uint(mx1));
-    atomicMax(&scratch[3], __float_as_uint(mx2));
+    atomicMin(&scratch[0], float_key(mn));
+    atomicMax(&scratch[1], float_key(mx0));
+    atomicMax(&scratch[2], float_key(mx1));
+    atomicMax(&scratch[3], float_key(mx2));
   }
 }
 __global__ void scene_stats_init_kernel(unsigned int* scratch) {
-  scratch[0] = 0x7F800000u;  // +inf
-  scratch[1] = scratch[2] = scratch[3] = 0u;
+  scratch[0] = 0xFFFFFFFFu;                    // key of the largest float
+  scratch[1] = scratch[2] = scratch[3] = 0u;   // key of the smallest
 }
 __global__ void scene_stats_final_kernel(const unsigned int* scratch, float* stats) {
-  for (int i = 0; i < 4; ++i) stats[i] = __uint_as_float(scratch[i]);
+  for (int i = 0; i < 4; ++i) stats[i] = key_float(scratch[i]);
 }
-int launch_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats,
-                       unsigned int* scratch, cudaStream_t stream) {
+namespace {
+template <typename T>
+int launch_scene_stats_t(const T* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, unsigned int* scratch,
+                         cudaStream_t stream) {
   const long long npix = static_cast<long long>(Hs) * Ws;
   scene_stats_init_kernel<<<1, 1, 0, stream>>>(scratch);
   long long blocks = (npix + 2047) / 2048;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  scene_stats_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(scene, nodata, npix, scratch);
+  scene_stats_kernel<T><<<static_cast<int>(blocks), 256, 0, stream>>>(scene, nodata, npix, scratch);
   scene_stats_final_kernel<<<1, 1, 0, stream>>>(scratch, stats);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+}  // namespace
+int launch_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats,
+                       unsigned int* scratch, cudaStream_t stream) {
+  return launch_scene_stats_t(scene, nodata, Hs, Ws, stats, scratch, stream);
+}
+int launch_scene_stats_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, float* stats,
+                           unsigned int* scratch, cudaStream_t stream) {
+  return launch_scene_stats_t(scene, nodata, Hs, Ws, stats, scratch, stream);
+}
+
+// ----------------------------------------------------------------------------------------------
+// merge_tifs accumulation (src/util/geo_util.py:410-422): N rasters already reprojected onto the output grid
+// (data fp32 [N,C,H,W], yesdata uint8 [N,H,W]) -> nodata-weighted mean fp32 [C,H,W] (0 where no raster has data) and
+// the merged nodata mask uint8 [H,W] (= ~any(yesdata)).  The sum runs over n = 0..N-1 in float32 like numpy's
+// axis-0 reduction, so the result is bit-identical.
+// ----------------------------------------------------------------------------------------------
+__global__ void merge_mosaic_kernel(const float* __restrict__ data, const uint8_t* __restrict__ yes, int N, int C,
+                                    long long npix, float* __restrict__ mean, uint8_t* __restrict__ nodata) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    float wsum = 0.f;
+    bool any = false;
+    for (int n = 0; n < N; ++n) {
+      const uint8_t y = yes[n * npix + i];
+      wsum = __fadd_rn(wsum, static_cast<float>(y));
+      any |= (y != 0);
+    }
+    for (int c = 0; c < C; ++c) {
+      float acc = 0.f;
+      for (int n = 0; n < N; ++n)
+        acc = __fadd_rn(acc, __fmul_rn(data[((long long)n * C + c) * npix + i], static_cast<float>(yes[n * npix + i])));
+      mean[c * npix + i] = wsum != 0.f ? __fdiv_rn(acc, wsum) : 0.f;
+    }
+    nodata[i] = any ? 0 : 1;
+  }
+}
+int launch_merge_mosaic(const float* data, const uint8_t* yesdata, int N, int C, int Hs, int Ws, float* mean,
+                        uint8_t* nodata, cudaStream_t stream) {
+  const long long npix = static_cast<long long>(Hs) * Ws;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope prof(CAT_INGEST, 0, static_cast<double>(npix) * (N * (C * 4 + 1) + C * 4 + 1), stream);
+  merge_mosaic_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(data, yesdata, N, C, npix, mean, nodata);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -84,17 +144,21 @@ __device__ __forceinline__ uint8_t clip8(int v, int prec) {
   return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// kFromU8 == false: uint16 4-band scene + tile boxes (src/predict.py path, PIL table, (u/255 - mean)/std)
-// kFromU8 == true : uint8 RGB crops [n,crop,crop,3] (HWC) or [n,3,crop,crop] (CHW) (src/predict_no_prompt.py path:
-//                   SegGptImageProcessor.preprocess, torchvision table, (u - 255 mean)/(255 std))
-template <bool kFromU8>
+// SRC 0 / 2: uint16 / float32 4-band scene + tile boxes (src/predict.py path, PIL table, (u/255 - mean)/std)
+// SRC 1     : uint8 RGB crops [n,crop,crop,3] (HWC) or [n,3,crop,crop] (CHW) (src/predict_no_prompt.py path:
+//             SegGptImageProcessor.preprocess, torchvision table, (u - 255 mean)/(255 std))
+enum : int { kSrcU16 = 0, kSrcU8 = 1, kSrcF32 = 2 };
+template <int SRC>
 __global__ void __launch_bounds__(256)
-ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ nodata, int Hs, int Ws,
+ingest_kernel(const void* __restrict__ scene_v, const uint8_t* __restrict__ nodata, int Hs, int Ws,
               const float* __restrict__ stats, const int* __restrict__ boxes, int crop, const int* __restrict__ coef,
               const int* __restrict__ bounds, int ksize, int band, int max_rows, float m0, float m1, float m2,
               float s0, float s1, float s2, float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_patch,
               long long patch_tile_stride, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_nodata,
               const uint8_t* __restrict__ src_u8, int src_chw, int prec) {
+  constexpr bool kFromU8 = (SRC == kSrcU8);
+  using SceneT = typename std::conditional<SRC == kSrcF32, float, uint16_t>::type;
+  const SceneT* __restrict__ scene = static_cast<const SceneT*>(scene_v);
   extern __shared__ uint8_t sm[];
   uint8_t* comp = sm;                                   // [3][max_rows][crop]
   uint8_t* hbuf = sm + 3 * max_rows * crop;             // [3][max_rows][kOut]
@@ -201,8 +265,8 @@ ingest_kernel(const uint16_t* __restrict__ scene, const uint8_t* __restrict__ no
 }
 
 namespace {
-template <bool kFromU8>
-int launch_ingest_t(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
+template <int SRC>
+int launch_ingest_t(const void* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
                     int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
                     const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
                     long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, const uint8_t* src_u8,
@@ -212,7 +276,8 @@ int launch_ingest_t(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws
   BSEG_REQUIRE(prec >= 1 && prec <= 22, "ingest: coefficient precision %d out of range", prec);
   const size_t smem = static_cast<size_t>(3) * max_rows * (crop + kOut);
   BSEG_REQUIRE(smem <= 200 * 1024, "ingest: crop=%d band=%d needs %zu B of shared memory", crop, band, smem);
-  auto kern = ingest_kernel<kFromU8>;
+  constexpr bool kFromU8 = (SRC == kSrcU8);
+  auto kern = ingest_kernel<SRC>;
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
     BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -235,15 +300,24 @@ int launch_ingest(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, 
                   int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
                   const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
                   long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream) {
-  return launch_ingest_t<false>(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, band, max_rows,
-                                mean, stdv, out_nchw, out_patch, patch_tile_stride, out_u8, out_nodata, nullptr, 0, 22,
-                                stream);
+  return launch_ingest_t<kSrcU16>(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, band,
+                                  max_rows, mean, stdv, out_nchw, out_patch, patch_tile_stride, out_u8, out_nodata,
+                                  nullptr, 0, 22, stream);
+}
+
+int launch_ingest_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
+                      int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
+                      const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
+                      long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream) {
+  return launch_ingest_t<kSrcF32>(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, band,
+                                  max_rows, mean, stdv, out_nchw, out_patch, patch_tile_stride, out_u8, out_nodata,
+                                  nullptr, 0, 22, stream);
 }
 
 int launch_preprocess_u8(const uint8_t* images, int chw, int n, int crop, const int* coef, const int* bounds, int ksize,
                          int prec, int band, int max_rows, const float* mean255, const float* std255, float* out_nchw,
                          cudaStream_t stream) {
-  return launch_ingest_t<true>(nullptr, nullptr, 0, 0, nullptr, nullptr, n, crop, coef, bounds, ksize, band, max_rows,
+  return launch_ingest_t<kSrcU8>(nullptr, nullptr, 0, 0, nullptr, nullptr, n, crop, coef, bounds, ksize, band, max_rows,
                                mean255, std255, out_nchw, nullptr, 0, nullptr, nullptr, images, chw, prec, stream);
 }
 

@@ -87,6 +87,10 @@ int launch_preprocess_u8(const uint8_t* images, int chw, int n, int crop, const 
 int launch_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
                            const int* boxes, int use_atomics, cudaStream_t stream);
 int launch_vote_argmax(const uint32_t* counter, uint8_t* out, long long n, cudaStream_t stream);
+int launch_paste_tiles(uint8_t* canvas, int Hs, int Ws, const uint8_t* crops, int n_tiles, int crop, const int* boxes,
+                       cudaStream_t stream);
+int launch_overlay_prediction(const uint8_t* img, const uint8_t* pred, const uint8_t* rgba, int n_classes,
+                              long long npix, uint8_t* out, cudaStream_t stream);
 int launch_smooth_l1(const float* pred, const float* labels, const uint8_t* yesdata, float beta, int per_sample,
                      float* loss_out, float* grad_out, float* scratch, int B, int H, int W, cudaStream_t stream);
 int launch_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats /*[4]*/,
@@ -95,5 +99,13 @@ int launch_ingest(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, 
                   int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
                   const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch, long long patch_tile_stride,
                   uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
+int launch_scene_stats_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, float* stats /*[4]*/,
+                           unsigned int* scratch /*[4]*/, cudaStream_t stream);
+int launch_ingest_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
+                      int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
+                      const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
+                      long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
+int launch_merge_mosaic(const float* data, const uint8_t* yesdata, int N, int C, int Hs, int Ws, float* mean,
+                        uint8_t* nodata, cudaStream_t stream);
 
 }  // namespace bseg

@@ -79,17 +79,49 @@ def _device_table(in_size: int, device):
 
 def scene_stats(scene_u16: torch.Tensor, nodata: torch.Tensor) -> torch.Tensor:
     """Scene-global statistics of tif_image's 4-band branch (src/util/geo_util.py:459-464).
-    scene_u16: uint16 [4,Hs,Ws] (torch.uint16 or int16 storage); nodata: bool/uint8 [Hs,Ws].
+    scene_u16: uint16 [4,Hs,Ws] (torch.uint16 or int16 storage) or float32 [4,Hs,Ws] (the merge_tifs mosaic,
+    src/util/geo_util.py:385,417); nodata: bool/uint8 [Hs,Ws].
     Returns float32 [4] = (min over valid composite pixels, max of channel 0, 1, 2)."""
     _need_cuda(scene_u16, nodata)
+    scene_u16, is_f32 = _scene_kind(scene_u16)
     _, Hs, Ws = scene_u16.shape
     nd = nodata.to(torch.uint8).contiguous()
     stats = torch.empty(4, dtype=torch.float32, device=scene_u16.device)
     scratch = torch.empty(4, dtype=torch.int32, device=scene_u16.device)
     with torch.cuda.device(scene_u16.device):
-        _lib.check(_lib.lib().bseg_scene_stats(_lib.ptr(scene_u16), _lib.ptr(nd), Hs, Ws, _lib.ptr(stats),
-                                               _lib.ptr(scratch), _lib.stream_ptr()), "bseg_scene_stats")
+        fn = _lib.lib().bseg_scene_stats_f32 if is_f32 else _lib.lib().bseg_scene_stats
+        _lib.check(fn(_lib.ptr(scene_u16), _lib.ptr(nd), Hs, Ws, _lib.ptr(stats), _lib.ptr(scratch),
+                      _lib.stream_ptr()), "bseg_scene_stats")
     return stats
+
+
+def _scene_kind(scene: torch.Tensor):
+    """(contiguous scene, is_float32).  uint16 / int16 storage -> the u16 entry points, float32 -> the f32 ones."""
+    if scene.dtype == torch.float32:
+        return scene.contiguous(), True
+    if scene.dtype in (torch.uint16, torch.int16):
+        return scene.contiguous(), False
+    raise _lib.BsegError(f"scene must be uint16 or float32 [4,Hs,Ws], got {scene.dtype}")
+
+
+def merge_mosaic(data: torch.Tensor, yesdata: torch.Tensor):
+    """The accumulation of merge_tifs (src/util/geo_util.py:410-419) for rasters already on the output grid.
+    data: float32 [N,C,H,W]; yesdata: uint8 [N,H,W] (rasterio masks: 0 / 255, used as weights like the reference).
+    Returns (mean float32 [C,H,W], nodata bool [H,W])."""
+    _need_cuda(data, yesdata)
+    if data.dtype != torch.float32 or yesdata.dtype != torch.uint8:
+        raise _lib.BsegError("merge_mosaic: data must be float32 and yesdata uint8")
+    N, C, H, W = data.shape
+    if tuple(yesdata.shape) != (N, H, W):
+        raise _lib.BsegError(f"merge_mosaic: yesdata shape {tuple(yesdata.shape)} != {(N, H, W)}")
+    d = data.contiguous()
+    y = yesdata.contiguous()
+    mean = torch.empty((C, H, W), dtype=torch.float32, device=data.device)
+    nodata = torch.empty((H, W), dtype=torch.uint8, device=data.device)
+    with torch.cuda.device(data.device):
+        _lib.check(_lib.lib().bseg_merge_mosaic(_lib.ptr(d), _lib.ptr(y), N, C, H, W, _lib.ptr(mean),
+                                                _lib.ptr(nodata), _lib.stream_ptr()), "bseg_merge_mosaic")
+    return mean, nodata.bool()
 
 
 def ingest_tiles(scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Tensor, boxes: torch.Tensor,
@@ -100,6 +132,7 @@ def ingest_tiles(scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Ten
     boxes: int32 [n,4] (xmin,ymin,xmax,ymax) on the device.  Returns dict with the requested outputs:
     image float32 [n,3,448,448], u8 uint8 [n,crop,crop,3], nodata uint8 [n,crop,crop]."""
     _need_cuda(scene_u16, nodata, stats, boxes)
+    scene_u16, is_f32 = _scene_kind(scene_u16)
     dev = scene_u16.device
     _, Hs, Ws = scene_u16.shape
     n = boxes.shape[0]
@@ -111,7 +144,8 @@ def ingest_tiles(scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Ten
     out["nodata"] = torch.empty((n, crop, crop), dtype=torch.uint8, device=dev) if want_nodata else None
     boxes_i = boxes.to(torch.int32).contiguous()  # named: must outlive the launch
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().bseg_ingest_u16x4(
+        fn = _lib.lib().bseg_ingest_f32x4 if is_f32 else _lib.lib().bseg_ingest_u16x4
+        _lib.check(fn(
             _lib.ptr(scene_u16), _lib.ptr(nd), Hs, Ws, _lib.ptr(stats), _lib.ptr(boxes_i),
             n, crop, _lib.ptr(coef), _lib.ptr(bounds), ksize, _lib.f3(IMAGE_MEAN), _lib.f3(IMAGE_STD),
             _lib.ptr(out["image"]), _lib.ptr(out_patch), patch_tile_stride, _lib.ptr(out["u8"]),
@@ -209,6 +243,53 @@ def vote_argmax(counter: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(counter.device):
         _lib.check(_lib.lib().bseg_vote_argmax(_lib.ptr(counter), _lib.ptr(out), counter.numel(), _lib.stream_ptr()),
                    "bseg_vote_argmax")
+    return out
+
+
+CLASS_COLORS = {"nodata": None, "water": "yellow", "veg": "blue", "sand": "hotpink"}
+"""src/util/img_util.py:12."""
+_COLOR_RGB = {"yellow": (255, 255, 0), "blue": (0, 0, 255), "hotpink": (255, 105, 180)}  # ImageColor.getrgb values
+
+
+def class_rgba_table(classes: Sequence[str], alpha: int = int(255 * 0.3)) -> np.ndarray:
+    """uint8 [n_classes,4] overlay table of overlay_prediction (src/util/img_util.py:105-111): (r,g,b,alpha) per class
+    id, alpha 0 for classes whose CLASS_COLORS entry is None."""
+    table = np.zeros((len(classes), 4), dtype=np.uint8)
+    for i, c in enumerate(classes):
+        name = CLASS_COLORS[c]
+        if name is not None:
+            table[i] = (*_COLOR_RGB[name], alpha)
+    return table
+
+
+def paste_tiles(canvas: torch.Tensor, crops_u8: torch.Tensor, boxes: torch.Tensor) -> None:
+    """Accumulator.update's `current_img[dy0:dy1, dx0:dx1] = img_crop[sy0:sy1, sx0:sx1]` (src/predict.py:157) for a batch
+    of tiles.  canvas: uint8 [Hs,Ws,3] (modified in place); crops_u8: uint8 [n,crop,crop,3]; boxes: int32 [n,4]."""
+    _need_cuda(canvas, crops_u8, boxes)
+    if canvas.dtype != torch.uint8 or crops_u8.dtype != torch.uint8 or not canvas.is_contiguous():
+        raise _lib.BsegError("paste_tiles: canvas and crops must be uint8, canvas contiguous")
+    Hs, Ws, _ = canvas.shape
+    n, crop = crops_u8.shape[0], crops_u8.shape[1]
+    cr = crops_u8.contiguous()
+    bx = boxes.to(torch.int32).contiguous()
+    with torch.cuda.device(canvas.device):
+        _lib.check(_lib.lib().bseg_paste_tiles_u8(_lib.ptr(canvas), Hs, Ws, _lib.ptr(cr), n, crop, _lib.ptr(bx),
+                                                  _lib.stream_ptr()), "bseg_paste_tiles_u8")
+
+
+def overlay_prediction(img: torch.Tensor, pred: torch.Tensor, classes: Sequence[str]) -> torch.Tensor:
+    """overlay_prediction (src/util/img_util.py:98-116) on the device, bit-exact with Pillow's alpha_composite.
+    img: uint8 [H,W,3]; pred: uint8 [H,W] class ids.  Returns uint8 [H,W,3]."""
+    _need_cuda(img, pred)
+    H, W, _ = img.shape
+    im = img.to(torch.uint8).contiguous()
+    pr = pred.to(torch.uint8).contiguous()
+    table = torch.from_numpy(class_rgba_table(classes)).to(img.device)
+    out = torch.empty_like(im)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().bseg_overlay_prediction(_lib.ptr(im), _lib.ptr(pr), _lib.ptr(table), len(classes),
+                                                      H * W, _lib.ptr(out), _lib.stream_ptr()),
+                   "bseg_overlay_prediction")
     return out
 
 

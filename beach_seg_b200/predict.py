@@ -130,6 +130,22 @@ class NoPromptPredictor:
                                         dtype=torch.uint8)                           # :299-303
 
 
+def write_mask_tif(mask: np.ndarray, transform: Any, crs: Any, path: Path) -> bool:
+    """src/util/img_util.py:67-95: single-band LZW GeoTIFF of the class map.  rasterio (GDAL) does the encoding; it is not
+    part of this image, so without it (or without georeferencing) nothing is written and False is returned."""
+    if transform is None or crs is None:
+        return False
+    try:
+        import rasterio
+    except ImportError:
+        return False
+    h, w = mask.shape
+    with rasterio.open(path, "w", driver="GTiff", height=h, width=w, count=1, dtype=mask.dtype, transform=transform,
+                       crs=crs, compress="lzw") as dst:
+        dst.write(mask, 1)
+    return True
+
+
 class Accumulator:
     """Device-resident version of the reference's Accumulator (src/predict.py:55-159): same constructor and
     `update` / `save_current` / context-manager protocol.  `update` takes either the reference's one-hot uint8
@@ -144,11 +160,15 @@ class Accumulator:
             raise ValueError("the packed vote counter holds at most 4 classes")
         self.out_transform, self.crs, self.classes = out_transform, crs, tuple(classes)
         self.device = torch.device(device)
-        self.mask_dir = None
-        if save_dir is not None:
+        self.mask_dir = self.img_dir = self.tif_dir = None
+        if save_dir is not None:  # the reference's three output folders (src/predict.py:68-75)
+            self.img_dir = Path(save_dir) / "pred"
             self.mask_dir = Path(save_dir) / "masks"
-            self.mask_dir.mkdir(exist_ok=True, parents=True)
+            self.tif_dir = Path(save_dir) / "tifs"
+            for d in (self.img_dir, self.mask_dir, self.tif_dir):
+                d.mkdir(exist_ok=True, parents=True)
         self.current_pred_counter: Optional[torch.Tensor] = None
+        self.current_img: Optional[torch.Tensor] = None
         self.current_date = None
 
     def __enter__(self):
@@ -162,6 +182,13 @@ class Accumulator:
     def initialize_current(self, date: str):
         self.current_date = date
         self.current_pred_counter = torch.zeros(self.out_shape, dtype=torch.int32, device=self.device)
+        self.current_img = torch.zeros((*self.out_shape, 3), dtype=torch.uint8, device=self.device)
+
+    def overlay(self) -> torch.Tensor:
+        """overlay_prediction(current_img, argmax(counter), classes) (src/predict.py:100-102) as uint8 (H, W, 3) on the
+        device."""
+        assert self.current_img is not None
+        return ops.overlay_prediction(self.current_img, self.prediction(), self.classes)
 
     def counter_u8(self) -> np.ndarray:
         """The reference's `current_pred_counter` view: uint8 (H, W, 4)."""
@@ -175,11 +202,16 @@ class Accumulator:
 
     def save_current(self):
         assert self.current_pred_counter is not None and self.current_date is not None
-        pred = self.prediction().cpu().numpy()
-        if self.mask_dir is not None:  # PNG / GeoTIFF / overlay writers are outside the hot path
+        pred_dev = self.prediction()
+        pred = pred_dev.cpu().numpy()
+        if self.mask_dir is not None:  # file encoders stay on the host; pixels come from the GPU
             import cv2
+            from PIL import Image
 
+            blended = ops.overlay_prediction(self.current_img, pred_dev, self.classes).cpu().numpy()
+            Image.fromarray(blended).save(self.img_dir / f"{self.current_date}.png")
             cv2.imwrite(str(self.mask_dir / f"{self.current_date}.png"), pred)
+            write_mask_tif(pred, self.out_transform, self.crs, self.tif_dir / f"{self.current_date}.tif")
         return pred
 
     def update(self, date: str, crop, one_hot_pred, img_crop=None, label_crop=None):
@@ -197,3 +229,7 @@ class Accumulator:
             cls = cls[None]
         boxes = torch.as_tensor(np.asarray(crop, dtype=np.int32).reshape(-1, 4), device=self.device)
         ops.vote_accumulate(self.current_pred_counter, cls.contiguous(), boxes)
+        if img_crop is not None:
+            img = torch.from_numpy(img_crop) if isinstance(img_crop, np.ndarray) else img_crop
+            img = img.to(device=self.device, dtype=torch.uint8)
+            ops.paste_tiles(self.current_img, img[None] if img.ndim == 3 else img, boxes)

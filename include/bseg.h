@@ -118,6 +118,24 @@ int bseg_ingest_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int 
                       int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,
                       long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, void* stream);
 
+/* The same two calls for a float32 scene [4,Hs,Ws] — what merge_tifs hands to tif_image (src/util/geo_util.py:385,
+ * 417-420: rasters are read with out_dtype=float32 and averaged).  Values may be negative (cubic reprojection
+ * overshoot); the statistics use order-preserving keys in `scratch`. */
+int bseg_scene_stats_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, uint32_t* scratch,
+                         void* stream);
+int bseg_ingest_f32x4(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                      const int32_t* boxes, int n_tiles, int crop, const int32_t* coef, const int32_t* bounds,
+                      int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,
+                      long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, void* stream);
+
+/* merge_tifs accumulation (src/util/geo_util.py:410-418): rasters already on the common grid,
+ * data fp32 [n_rasters,channels,Hs,Ws], yesdata uint8 [n_rasters,Hs,Ws] (0 / nonzero) ->
+ * mean fp32 [channels,Hs,Ws] = sum_n(data*yes) / sum_n(yes) (0 where the weight is 0; float32 sums in raster order,
+ * bit-identical to numpy) and nodata uint8 [Hs,Ws] = !any_n(yes).  yesdata is used as the weight exactly as the
+ * reference does (mask values promoted to float32), so pass 0/1 masks for a plain mean. */
+int bseg_merge_mosaic(const float* data, const uint8_t* yesdata, int n_rasters, int channels, int Hs, int Ws,
+                      float* mean, uint8_t* nodata, void* stream);
+
 /* ---- src/predict_no_prompt.py path: the HF image processor (HF:image_processing_seggpt.py) on the device ----
  * SegGptImageProcessor.preprocess for images / prompt images (:134-252): uint8 RGB crops [n,crop,crop,3] (HWC,
  * layout_chw = 0) or [n,3,crop,crop] -> torchvision bicubic-antialias resize to 448 on uint8 (bit-exact restatement of
@@ -164,6 +182,17 @@ int bseg_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, 
 
 /* np.argmax(counter, axis=2) (src/predict.py:100; src/predict_no_prompt.py:141). out: uint8 [Hs,Ws]. */
 int bseg_vote_argmax(const uint32_t* counter, uint8_t* out, long long n_pixels, void* stream);
+
+/* Accumulator.update's image paste (src/predict.py:157): canvas uint8 [Hs,Ws,3]; crops uint8 [n_tiles,crop,crop,3];
+ * boxes int32 [n_tiles,4]; the part of each crop inside the scene overwrites the canvas. */
+int bseg_paste_tiles_u8(uint8_t* canvas, int Hs, int Ws, const uint8_t* crops, int n_tiles, int crop,
+                        const int32_t* boxes, void* stream);
+
+/* overlay_prediction (src/util/img_util.py:98-116): Pillow's Image.alpha_composite of the class-colour layer over the
+ * RGB image, bit-exact.  img, out: uint8 [n_pixels,3]; pred: uint8 [n_pixels] class ids;
+ * class_rgba: uint8 [n_classes,4] = (r,g,b,alpha), alpha 0 = class without a colour (CLASS_COLORS[c] is None). */
+int bseg_overlay_prediction(const uint8_t* img, const uint8_t* pred, const uint8_t* class_rgba, int n_classes,
+                            long long n_pixels, uint8_t* out, void* stream);
 
 /* SegGptLoss (src/model.py:40-64), forward and gradient w.r.t. pred in one pass.
  * pred fp32 [B,3,2H,W]; labels fp32 [B,3,H,W]; yesdata uint8 [B,H,W]; per_sample: 0 = as written in the

@@ -40,6 +40,42 @@ def tif_image_4band(data: np.ndarray, nodata: np.ndarray) -> np.ndarray:
     return np.array(img * 255, dtype=np.uint8)
 
 
+def merge_mosaic(dst_data: np.ndarray, dst_yesdata: np.ndarray):
+    """src/util/geo_util.py:410-419 — the accumulation of merge_tifs once every raster is on the output grid.
+    dst_data: (N,C,H,W) float32; dst_yesdata: (N,H,W) uint8 (rasterio masks, 0/255) -> (mean (C,H,W) float32, nodata (H,W) bool)."""
+    mask_f = dst_yesdata.astype(dst_data.dtype)
+    w = mask_f[:, None, :, :]
+    weighted_sum = (dst_data * w).sum(axis=0)
+    weights = w.sum(axis=0)
+    mean = np.divide(weighted_sum, weights, out=np.full_like(weighted_sum, 0.0), where=weights != 0)
+    mask = ~np.any(dst_yesdata, axis=0)
+    return mean, mask
+
+
+CLASS_COLORS_RGB = {"nodata": None, "water": (255, 255, 0), "veg": (0, 0, 255), "sand": (255, 105, 180)}
+"""src/util/img_util.py:12 with ImageColor.getrgb applied (yellow, blue, hotpink)."""
+
+
+def overlay_prediction(img: np.ndarray, pred: np.ndarray, classes) -> np.ndarray:
+    """src/util/img_util.py:98-116 in integer numpy.  Pillow 12.2 (libImaging/AlphaComposite.c) composites with
+    7 precision bits; for an opaque destination: coef1 = a*128, coef2 = 255*128 - coef1,
+    out = div255(src*coef1 + dst*coef2 + (0x80 << 7)) >> 7 with div255(t) = ((t >> 8) + t) >> 8; a == 0 copies dst.
+    Pinned against PIL.Image.alpha_composite in tests/test_oracle_glue.py.  img (H,W,3) uint8, pred (H,W) -> (H,W,3)."""
+    alpha = int(255 * 0.3)
+    out = img.copy()
+    for cls_idx, name in enumerate(classes):
+        rgb = CLASS_COLORS_RGB[name]
+        if rgb is None:
+            continue
+        m = pred == cls_idx
+        dst = img[m].astype(np.uint32)
+        coef1 = np.uint32(alpha << 7)
+        coef2 = np.uint32((255 << 7) - (alpha << 7))
+        t = np.array(rgb, dtype=np.uint32)[None, :] * coef1 + dst * coef2 + np.uint32(0x80 << 7)
+        out[m] = ((((t >> 8) + t) >> 8) >> 7).astype(np.uint8)
+    return out
+
+
 def padded_crop(arr: np.ndarray, xmin: int, ymin: int, xmax: int, ymax: int, crop_size: int, value=0) -> np.ndarray:
     """src/util/geo_util.py:316-341."""
     if arr.ndim == 3:

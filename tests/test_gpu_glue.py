@@ -172,3 +172,102 @@ def test_ingest_bit_exact(dev, crop, Hs, Ws):
     assert np.array_equal(out["u8"].cpu().numpy(), want_u8)
     assert np.array_equal(out["nodata"].cpu().numpy().astype(bool), want_nd.astype(bool))
     assert torch.equal(out["image"].cpu(), want_img)
+
+
+def _mosaic_inputs(N, H, W, seed):
+    rng = np.random.default_rng(seed)
+    data = (rng.random((N, 4, H, W), dtype=np.float32) * 4000.0 - 150.0).astype(np.float32)   # negative overshoot too
+    yes = (rng.random((N, H, W)) > 0.35).astype(np.uint8) * 255                               # rasterio read_masks
+    yes[:, : H // 7, : W // 5] = 0                                                           # a region no raster covers
+    return data, yes
+
+
+@pytest.mark.parametrize("N,H,W", [(1, 64, 80), (3, 301, 517), (5, 700, 900)])
+def test_merge_mosaic_bit_exact(dev, N, H, W):
+    """bseg_merge_mosaic vs the numpy restatement of merge_tifs' accumulation (src/util/geo_util.py:410-419)."""
+    data, yes = _mosaic_inputs(N, H, W, seed=N)
+    want_mean, want_mask = glue_ref.merge_mosaic(data, yes)
+    mean, mask = ops.merge_mosaic(torch.from_numpy(data).to(dev), torch.from_numpy(yes).to(dev))
+    assert np.array_equal(mask.cpu().numpy(), want_mask)
+    assert np.array_equal(mean.cpu().numpy(), want_mean)
+    # 0/1 weights give the same mean up to rounding of the *255 products; nodata is identical
+    mean01, mask01 = ops.merge_mosaic(torch.from_numpy(data).to(dev), torch.from_numpy(yes // 255).to(dev))
+    assert torch.equal(mask01, mask)
+    np.testing.assert_allclose(mean01.cpu().numpy(), want_mean, rtol=2e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("crop,Hs,Ws", [(512, 1100, 1300), (160, 300, 420)])
+def test_ingest_f32_mosaic_bit_exact(dev, crop, Hs, Ws):
+    """merge -> tif_image -> crop -> resize -> normalise on a float32 mosaic with negative values
+    (src/util/geo_util.py:410-420,454-468; src/data.py:93-124)."""
+    data, yes = _mosaic_inputs(3, Hs, Ws, seed=crop)
+    scene, nodata = glue_ref.merge_mosaic(data, yes)
+    assert scene[:, ~nodata].min() < 0
+    boxes = np.array([[0, 0, crop, crop], [Ws - crop - 3, Hs - crop - 5, Ws - 3, Hs - 5],
+                      [-(crop // 3), -(crop // 4), crop - crop // 3, crop - crop // 4]], dtype=np.int32)
+    want_u8, want_nd, want_img = _ingest_oracle(scene, nodata, boxes, crop)
+    sc, nd = ops.merge_mosaic(torch.from_numpy(data).to(dev), torch.from_numpy(yes).to(dev))
+    stats = ops.scene_stats(sc, nd)
+    comp = np.stack([scene[3], scene[2], scene[:2].mean(axis=0)])
+    want_stats = np.array([comp[:, ~nodata].min(), comp[0].max(), comp[1].max(), comp[2].max()], dtype=np.float32)
+    assert np.array_equal(stats.cpu().numpy(), want_stats)
+    out = ops.ingest_tiles(sc, nd, stats, torch.from_numpy(boxes).to(dev), crop, want_u8=True, want_nodata=True)
+    assert np.array_equal(out["u8"].cpu().numpy(), want_u8)
+    assert np.array_equal(out["nodata"].cpu().numpy().astype(bool), want_nd.astype(bool))
+    assert torch.equal(out["image"].cpu(), want_img)
+
+
+@pytest.mark.parametrize("H,W", [(4, 256), (97, 131), (1000, 2001)])
+def test_overlay_prediction_bit_exact(dev, H, W):
+    """bseg_overlay_prediction vs the Pillow-pinned restatement (src/util/img_util.py:98-116); odd pixel counts
+    exercise the scalar tail, class id 200 (outside the table) must copy the base pixel."""
+    classes = ("nodata", "sand", "water", "veg")
+    rng = np.random.default_rng(H)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    pred = rng.integers(0, 4, (H, W), dtype=np.uint8)
+    if H == 4:  # every (grey level, class) pair
+        img = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 4, axis=0).repeat(3, axis=2).copy()
+        pred = np.repeat(np.arange(4, dtype=np.uint8)[:, None], 256, axis=1).copy()
+    want = glue_ref.overlay_prediction(img, pred, classes)
+    got = ops.overlay_prediction(torch.from_numpy(img).to(dev), torch.from_numpy(pred).to(dev), classes)
+    assert np.array_equal(got.cpu().numpy(), want)
+    pred[0, :7] = 200
+    want = glue_ref.overlay_prediction(img, pred, classes)
+    got = ops.overlay_prediction(torch.from_numpy(img).to(dev), torch.from_numpy(pred).to(dev), classes)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # a different class order, as conf.classes allows
+    other = ("nodata", "water", "veg", "sand")
+    got = ops.overlay_prediction(torch.from_numpy(img).to(dev), torch.from_numpy(pred).to(dev), other)
+    assert np.array_equal(got.cpu().numpy(), glue_ref.overlay_prediction(img, pred, other))
+
+
+def test_accumulator_image_paste_and_outputs(dev, tmp_path):
+    """Accumulator.update with img_crop + save_current (src/predict.py:96-112,157): pasted canvas, overlay PNG and mask
+    PNG equal the numpy/Pillow restatement."""
+    from PIL import Image
+    from beach_seg_b200.predict import Accumulator
+
+    Hs, Ws, crop = 300, 420, 128
+    classes = ("nodata", "sand", "water", "veg")
+    rng = np.random.default_rng(3)
+    scene_img = rng.integers(0, 256, (Hs, Ws, 3), dtype=np.uint8)
+    boxes = synth.sliding_boxes(Hs, Ws, crop, 96)
+    canvas = np.zeros((Hs, Ws, 3), dtype=np.uint8)
+    ref = glue_ref.AccumulatorRef((Hs, Ws))
+    with Accumulator((Hs, Ws), tmp_path, classes=classes, device=dev) as acc:
+        for b in boxes:
+            b = tuple(int(v) for v in b)
+            ci = glue_ref.padded_crop(scene_img, *b, crop)
+            cls = rng.integers(0, 4, (crop, crop)).astype(np.uint8)
+            one_hot = np.eye(4, dtype=np.uint8)[cls]
+            acc.update("20240101", b, one_hot, ci, None)
+            ref.update(b, one_hot)
+            x0, y0, x1, y1 = max(b[0], 0), max(b[1], 0), min(b[2], Ws), min(b[3], Hs)
+            canvas[y0:y1, x0:x1] = ci[y0 - b[1]:y1 - b[1], x0 - b[0]:x1 - b[0]]
+        assert np.array_equal(acc.current_img.cpu().numpy(), canvas)
+        want_pred = ref.argmax().astype(np.uint8)
+        assert np.array_equal(acc.overlay().cpu().numpy(), glue_ref.overlay_prediction(canvas, want_pred, classes))
+    png = np.array(Image.open(tmp_path / "pred" / "20240101.png"))
+    assert np.array_equal(png, glue_ref.overlay_prediction(canvas, want_pred, classes))
+    mask_png = np.array(Image.open(tmp_path / "masks" / "20240101.png"))
+    assert np.array_equal(mask_png, want_pred)

@@ -92,3 +92,43 @@ def test_host_tables_match_oracle():
         want = cv2.resize(ramp, (dst, dst), interpolation=cv2.INTER_NEAREST)[0]
         assert np.array_equal(ops.cv2_nearest_index(src, dst), want)
         assert np.array_equal(glue_ref.cv2_nearest_index(src, dst), want)
+
+
+def test_merge_mosaic_hand_case():
+    """merge_tifs accumulation (src/util/geo_util.py:410-419) on a case small enough to check by hand.
+    rasterio is not in this image, so the reprojection step cannot be run; the accumulation is plain numpy."""
+    data = np.zeros((2, 4, 1, 3), dtype=np.float32)
+    data[0, :, 0, :] = [[10, 20, 30]] * 4
+    data[1, :, 0, :] = [[30, 99, -7]] * 4
+    yes = np.array([[[255, 255, 0]], [[255, 0, 0]]], dtype=np.uint8)
+    mean, mask = glue_ref.merge_mosaic(data, yes)
+    assert mean.dtype == np.float32 and mean.shape == (4, 1, 3)
+    assert np.array_equal(mean[0, 0], np.array([20, 20, 0], dtype=np.float32))
+    assert np.array_equal(mask, np.array([[False, False, True]]))
+
+
+def _pil_overlay(img, pred, classes):
+    """overlay_prediction exactly as the reference writes it (src/util/img_util.py:98-116), on the real Pillow."""
+    from PIL import Image, ImageColor
+
+    colors = {"nodata": None, "water": "yellow", "veg": "blue", "sand": "hotpink"}
+    h, w, _ = img.shape
+    layer = np.zeros((h, w, 4), dtype=np.uint8)
+    for idx, name in enumerate(colors[c] for c in classes):
+        if name is None:
+            continue
+        layer[pred == idx] = (*ImageColor.getrgb(name), int(255 * 0.3))
+    blended = Image.alpha_composite(Image.fromarray(img).convert("RGBA"), Image.fromarray(layer, mode="RGBA"))
+    return np.array(blended.convert("RGB"))
+
+
+def test_overlay_prediction_matches_pillow():
+    """Every (base value, class) pair: 256 grey levels x 4 classes, plus a random RGB image."""
+    classes = ("nodata", "sand", "water", "veg")
+    rng = np.random.default_rng(5)
+    grey = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 4, axis=0).repeat(3, axis=2)
+    pred = np.repeat(np.arange(4, dtype=np.uint8)[:, None], 256, axis=1)
+    assert np.array_equal(glue_ref.overlay_prediction(grey, pred, classes), _pil_overlay(grey, pred, classes))
+    img = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    pred = rng.integers(0, 4, (97, 131), dtype=np.uint8)
+    assert np.array_equal(glue_ref.overlay_prediction(img, pred, classes), _pil_overlay(img, pred, classes))
