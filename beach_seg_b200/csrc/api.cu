@@ -130,6 +130,10 @@ struct bseg_handle {
   // training-only packs (bseg_train_prepare)
   void* train_arena = nullptr;
   __nv_bfloat16 *patch_wt = nullptr, *dec_embed_wt = nullptr, *conv_w9b = nullptr;
+  // fp32 accuracy mode (bseg_enable_fp32): the handle's own fp32 copy of the matrices
+  void* f32_arena = nullptr;
+  std::vector<F32Layer> f32_layers;
+  F32Weights f32;
 };
 
 extern "C" {
@@ -142,6 +146,7 @@ int bseg_destroy(bseg_handle* h) {
   if (!h) return 0;
   if (h->arena) cudaFree(h->arena);
   if (h->train_arena) cudaFree(h->train_arena);
+  if (h->f32_arena) cudaFree(h->f32_arena);
   delete h;
   return 0;
 }
@@ -509,6 +514,90 @@ int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_
   fb.layers.assign(h->num_layers, {fb.h_emb, fb.h_emb, bf(L.q), bf(L.k), bf(L.vt), bf(L.att), nullptr, nullptr});
   return forward_impl(h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, ensemble_prompts, fb,
                       pred_masks, stream);
+}
+
+// ---- fp32 accuracy mode (precise.cu) ----
+int bseg_enable_fp32(bseg_handle* h, const bseg_weights* w, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BSEG_REQUIRE(h != nullptr && w != nullptr, "bseg_enable_fp32: null argument");
+  BSEG_REQUIRE(w->num_layers == h->num_layers, "bseg_enable_fp32: weights have %d layers, the handle %d", w->num_layers,
+               h->num_layers);
+  if (h->f32_arena != nullptr) return 0;
+  size_t off = 0;
+  auto carve = [&](size_t floats) {
+    size_t o = off;
+    off = align_up(off + floats * 4, 256);
+    return o;
+  };
+  struct LOff { size_t qkv, proj, lin1, lin2, rh, rw; };
+  std::vector<LOff> lo(h->num_layers);
+  for (int i = 0; i < h->num_layers; ++i)
+    lo[i] = {carve(3072ull * 1024), carve(1024ull * 1024), carve(4096ull * 1024), carve(4096ull * 1024),
+             carve(111 * 64), carve(55 * 64)};
+  const size_t o_patch = carve(1024ull * 768), o_dec = carve(16384ull * 4096), o_conv = carve(64 * 64 * 9);
+  void* arena = nullptr;
+  BSEG_CHECK_CUDA(cudaMalloc(&arena, off));
+  uint8_t* base = static_cast<uint8_t*>(arena);
+  cudaError_t ce = cudaSuccess;
+  auto cpy = [&](const float* src, size_t o, size_t floats) -> const float* {
+    float* dst = reinterpret_cast<float*>(base + o);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, floats * 4, cudaMemcpyDeviceToDevice, stream);
+    return dst;
+  };
+  h->f32_layers.resize(h->num_layers);
+  for (int i = 0; i < h->num_layers; ++i) {
+    const bseg_layer_weights& lw = w->layers[i];
+    const LayerPack& lp = h->layers[i];
+    F32Layer& f = h->f32_layers[i];
+    f.qkv_w = cpy(lw.qkv_w, lo[i].qkv, 3072ull * 1024);
+    f.proj_w = cpy(lw.proj_w, lo[i].proj, 1024ull * 1024);
+    f.lin1_w = cpy(lw.lin1_w, lo[i].lin1, 4096ull * 1024);
+    f.lin2_w = cpy(lw.lin2_w, lo[i].lin2, 4096ull * 1024);
+    f.rel_pos_h = cpy(lw.rel_pos_h, lo[i].rh, 111 * 64);
+    f.rel_pos_w = cpy(lw.rel_pos_w, lo[i].rw, 55 * 64);
+    f.ln1_w = lp.ln1_w; f.ln1_b = lp.ln1_b; f.ln2_w = lp.ln2_w; f.ln2_b = lp.ln2_b;   // already fp32 in the arena
+    f.qkv_b = lp.qkv_b; f.proj_b = lp.proj_b; f.lin1_b = lp.lin1_b; f.lin2_b = lp.lin2_b;
+  }
+  F32Weights& f = h->f32;
+  f.num_layers = h->num_layers;
+  f.merge_index = h->merge_index;
+  for (int j = 0; j < 4; ++j) f.inter[j] = h->inter[j];
+  f.eps = h->eps;
+  f.patch_w = cpy(w->patch_w, o_patch, 1024ull * 768);
+  f.embed_tab[0] = h->embed_tab[0];
+  f.embed_tab[1] = h->embed_tab[1];
+  f.layers = h->f32_layers.data();
+  f.enc_ln_w = h->enc_ln_w; f.enc_ln_b = h->enc_ln_b;
+  f.dec_embed_w = cpy(w->dec_embed_w, o_dec, 16384ull * 4096);
+  f.dec_embed_b = h->dec_embed_b;
+  f.dec_conv_w = cpy(w->dec_conv_w, o_conv, 64 * 64 * 9);
+  f.dec_conv_b = h->conv_b; f.dec_ln_w = h->dec_ln_w; f.dec_ln_b = h->dec_ln_b;
+  f.dec_head_w = h->head_w; f.dec_head_b = h->head_b;
+  if (ce != cudaSuccess) {
+    set_error("bseg_enable_fp32: copy failed: %s", cudaGetErrorString(ce));
+    cudaFree(arena);
+    return -static_cast<int>(ce);
+  }
+  h->f32_arena = arena;
+  return 0;
+}
+
+size_t bseg_workspace_bytes_f32(const bseg_handle* /*h*/, int batch) {
+  return batch > 0 ? f32_workspace_bytes(batch) : 0;
+}
+
+int bseg_forward_f32(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                     const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
+                     size_t workspace_bytes, float* pred_masks, void* stream_) {
+  int rc = check_forward_args(h, batch, embedding_type, workspace, "bseg_forward_f32");
+  if (rc) return rc;
+  BSEG_REQUIRE(h->f32_arena != nullptr, "bseg_forward_f32: call bseg_enable_fp32 first");
+  BSEG_REQUIRE(ensemble_prompts >= 0 && (ensemble_prompts == 0 || batch % ensemble_prompts == 0),
+               "bseg_forward_f32: batch=%d is not a multiple of ensemble_prompts=%d", batch, ensemble_prompts);
+  BSEG_REQUIRE(workspace_bytes >= f32_workspace_bytes(batch), "bseg_forward_f32: workspace too small (%zu < %zu)",
+               workspace_bytes, f32_workspace_bytes(batch));
+  return forward_f32_impl(h->f32, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type,
+                          ensemble_prompts, workspace, pred_masks, static_cast<cudaStream_t>(stream_));
 }
 
 // ---- training: transposed weight packs, forward that keeps what the backward needs, backward to the prompt ----

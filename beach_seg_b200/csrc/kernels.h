@@ -105,6 +105,26 @@ int launch_ingest_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws,
                       int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
                       const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
                       long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
+// precise.cu : the fp32 accuracy mode (bseg_forward_f32).  Pointers into the handle's own fp32 copy of the weights.
+struct F32Layer {
+  const float *ln1_w, *ln1_b, *qkv_w, *qkv_b, *rel_pos_h, *rel_pos_w, *proj_w, *proj_b, *ln2_w, *ln2_b, *lin1_w, *lin1_b,
+      *lin2_w, *lin2_b;
+};
+struct F32Weights {
+  int num_layers = 0, merge_index = 0;
+  int inter[4] = {0, 0, 0, 0};
+  float eps = 1e-6f;
+  const float* patch_w = nullptr;               // [1024, 768]
+  const float* embed_tab[2] = {nullptr, nullptr};
+  const F32Layer* layers = nullptr;             // host array
+  const float *enc_ln_w = nullptr, *enc_ln_b = nullptr, *dec_embed_w = nullptr, *dec_embed_b = nullptr,
+              *dec_conv_w = nullptr, *dec_conv_b = nullptr, *dec_ln_w = nullptr, *dec_ln_b = nullptr,
+              *dec_head_w = nullptr, *dec_head_b = nullptr;
+};
+size_t f32_workspace_bytes(int B);
+int forward_f32_impl(const F32Weights& w, const float* pixel_values, const float* prompt_pixel_values,
+                     const float* prompt_masks, int B, int embedding_type, int P, void* workspace, float* pred_masks,
+                     cudaStream_t stream);
 int launch_merge_mosaic(const float* data, const uint8_t* yesdata, int N, int C, int Hs, int Ws, float* mean,
                         uint8_t* nodata, cudaStream_t stream);
 

@@ -78,8 +78,14 @@ class _PromptGradFn(torch.autograd.Function):
 class SegGptB200(torch.nn.Module):
     def __init__(self, state_dict: Dict[str, torch.Tensor], num_layers: int = 24, merge_index: int = 2,
                  intermediate=(5, 11, 17, 23), layer_norm_eps: float = 1e-6, beta: float = 0.01,
-                 device: str | torch.device = "cuda:0", max_batch: int = 64):
+                 device: str | torch.device = "cuda:0", max_batch: int = 64, precision: str = "bf16"):
+        """precision: "bf16" = the tcgen05 path (bf16 operands, fp32 accumulation / residual stream / softmax; logits
+        within 1e-2 of the fp32 reference); "fp32" = the accuracy mode (bseg_forward_f32: everything IEEE fp32 on the
+        CUDA cores, within 1e-4, inference only, ~30x slower)."""
         super().__init__()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
         self._device = torch.device(device)
         if self._device.type != "cuda":
             raise _lib.BsegError("SegGptB200 runs on a CUDA device only; there is no CPU path")
@@ -130,6 +136,8 @@ class SegGptB200(torch.nn.Module):
             w.dec_ln_w, w.dec_ln_b = dev("decoder.decoder_pred.layernorm.weight"), dev("decoder.decoder_pred.layernorm.bias")
             w.dec_head_w, w.dec_head_b = dev("decoder.decoder_pred.head.weight"), dev("decoder.decoder_pred.head.bias")
             _lib.check(L.bseg_create(C.byref(w), C.byref(self._handle), _lib.stream_ptr()), "bseg_create")
+            if precision == "fp32":
+                _lib.check(L.bseg_enable_fp32(self._handle, C.byref(w), _lib.stream_ptr()), "bseg_enable_fp32")
             torch.cuda.current_stream().synchronize()
             del keep
 
@@ -157,7 +165,9 @@ class SegGptB200(torch.nn.Module):
             pass
 
     def _workspace(self, batch: int) -> torch.Tensor:
-        need = int(_lib.lib().bseg_workspace_bytes(self._handle, batch))
+        L = _lib.lib()
+        need = int((L.bseg_workspace_bytes_f32 if self.precision == "fp32" else L.bseg_workspace_bytes)(
+            self._handle, batch))
         if self._ws is None or self._ws.numel() < need + 256:
             self._ws = None
             self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self._device)
@@ -220,6 +230,8 @@ class SegGptB200(torch.nn.Module):
         def prep(t):
             return t.detach().to(device=self._device, dtype=torch.float32).contiguous()
 
+        if want_grad and self.precision == "fp32":
+            raise NotImplementedError("the fp32 accuracy mode is inference-only; train with precision='bf16'")
         if want_grad:
             if feature_ensemble:
                 raise NotImplementedError("feature_ensemble is an inference-only path in the reference "
@@ -231,15 +243,17 @@ class SegGptB200(torch.nn.Module):
         pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=self._device)
         L = _lib.lib()
         step = self.max_batch if P == 0 else max(P, (self.max_batch // P) * P)
+        fwd, fwd_name = (L.bseg_forward_f32, "bseg_forward_f32") if self.precision == "fp32" else \
+            (L.bseg_forward, "bseg_forward")
         with torch.cuda.device(self._device):
             for s in range(0, B, step):
                 n = min(step, B - s)
                 ws = self._workspace(n)
                 base = (ws.data_ptr() + 255) // 256 * 256
-                _lib.check(L.bseg_forward(self._handle, _lib.ptr(px[s:s + n]), _lib.ptr(ppx[s:s + n]),
-                                          _lib.ptr(pm[s:s + n]), n, 0 if embedding_type == "instance" else 1, P,
-                                          C.c_void_p(base), C.c_size_t(ws.numel() - (base - ws.data_ptr())),
-                                          _lib.ptr(pred[s:s + n]), _lib.stream_ptr()), "bseg_forward")
+                _lib.check(fwd(self._handle, _lib.ptr(px[s:s + n]), _lib.ptr(ppx[s:s + n]),
+                               _lib.ptr(pm[s:s + n]), n, 0 if embedding_type == "instance" else 1, P,
+                               C.c_void_p(base), C.c_size_t(ws.numel() - (base - ws.data_ptr())),
+                               _lib.ptr(pred[s:s + n]), _lib.stream_ptr()), fwd_name)
         return SegGptOutput(loss=self._hf_loss(pred, labels, B), pred_masks=pred)
 
     def _hf_loss(self, pred: torch.Tensor, labels: Optional[torch.Tensor], B: int):

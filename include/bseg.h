@@ -85,6 +85,16 @@ int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_
                  const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
                  size_t workspace_bytes, float* pred_masks, void* stream);
 
+/* ---- fp32 accuracy mode: the same forward with every operand, accumulator and activation in IEEE fp32 on the CUDA
+ * cores (no tensor cores, no bf16) -- logits within 1e-4 relative of the reference's fp32 CPU forward, about 30x
+ * slower than bseg_forward.  bseg_enable_fp32 copies the fp32 matrices of `w` (the struct given to bseg_create) into
+ * the handle once (+1.5 GB); arguments of bseg_forward_f32 are those of bseg_forward. */
+int bseg_enable_fp32(bseg_handle* h, const bseg_weights* w, void* stream);
+size_t bseg_workspace_bytes_f32(const bseg_handle* h, int batch);
+int bseg_forward_f32(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                     const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
+                     size_t workspace_bytes, float* pred_masks, void* stream);
+
 /* ---- train step (src/model.py:233-269 + Lightning's loss.backward()): the reference differentiates the frozen HF
  * module w.r.t. prompt_pixel_values only (all backbone weights have requires_grad=False, src/util/ml_util.py:9-10).
  * bseg_train_prepare packs the transposed weight copies the dgrad GEMMs need (once, +740 MB).
