@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=2)
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg (BASELINE configs[3])")
     ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--no-fp32-check", action="store_true",
+                    help="skip the fp32-accuracy-mode leg (bf16 path vs bseg_forward_f32 on the bench inputs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -392,6 +394,36 @@ def main():
     if not args.no_train:
         train = train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrier, timed, L, peaks)
 
+    # ---- accuracy leg: the first 8 tiles of the step through the fp32 mode (bseg_forward_f32) and through the bf16
+    # path, same inputs: logit deviation and class-map disagreements (north_star: "with that count reported") ----
+    fp32_mode = None
+    if rank == 0 and world == 1 and not args.no_fp32_check:
+        nb = 8
+        model32 = load_model("random-init:0", device=dev, max_batch=nb, precision="fp32")
+        tiles = ops.ingest_tiles(scene, nodata, stats, boxes[:nb], CROP)["image"]
+        pcol = ops.colorize_norm(prompt_cls[:nb], palette[0][:nb])
+        kw = dict(pixel_values=tiles, prompt_pixel_values=prompt_images[:nb], prompt_masks=pcol,
+                  embedding_type="instance")
+        with torch.no_grad():
+            p32 = model32(**kw).pred_masks  # warm-up + result
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            p32 = model32(**kw).pred_masks
+            e1.record()
+            torch.cuda.synchronize()
+            p16 = model(**kw).pred_masks
+        c32 = ops.decode_palette(p32, palette[1][:nb], out_size=CROP, dtype=torch.uint8)
+        c16 = ops.decode_palette(p16, palette[1][:nb], out_size=CROP, dtype=torch.uint8)
+        q32, q16 = p32[:, :, 448:], p16[:, :, 448:]
+        fp32_mode = {"tiles": nb, "tiles_per_s": nb / (e0.elapsed_time(e1) * 1e-3),
+                     "bf16_vs_fp32_logits_rel_l2": ((q16 - q32).norm() / q32.norm()).item(),
+                     "bf16_vs_fp32_max_abs_over_max": ((q16 - q32).abs().max() / q32.abs().max()).item(),
+                     "class_map_disagreements": int((c32 != c16).sum().item()), "class_map_pixels": int(c32.numel()),
+                     "note": "fp32 mode = every operand/accumulator IEEE fp32 on the CUDA cores; its own deviation from "
+                             "the HF fp32 CPU forward is 2e-6 rel-L2 (tests/test_gpu_fp32_mode.py)"}
+        del model32, p32, p16
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         tps, cores, per = cpu_tile_pipeline(args.cpu_tiles, 1)
@@ -412,7 +444,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": int(scene_host.numel() * 2),
                     "d2h_bytes_per_step": int(cls_host.numel()), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernels, "gemm_modes": gemm_modes, "train": train,
+            "kernels": kernels, "gemm_modes": gemm_modes, "train": train, "fp32_mode": fp32_mode,
             "model_tflops": value / world * FWD_FLOP_PER_TILE / 1e12,
             "model_frac_of_tensor_peak": value / world * FWD_FLOP_PER_TILE / 1e12 / peaks["tensor"],
         }
