@@ -264,6 +264,236 @@ ingest_kernel(const void* __restrict__ scene_v, const uint8_t* __restrict__ noda
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// ingest kernel v2 (used whenever the resampling table has <= 12 taps): same three phases, restructured so that one
+// shared-memory word feeds four multiply-adds.
+//   * the composite is stored TRANSPOSED AND PACKED: word (ch, x) of a row group holds the bytes of 4 consecutive crop
+//     rows, so a horizontal tap is one LDS.32 + 4 byte extracts + 4 IMADs (thread == output column, its <= KS
+//     coefficients live in registers); row groups stream through a double buffer, one __syncthreads per group;
+//   * the horizontal result is stored planar with x contiguous, so a vertical tap is again one LDS.32 for 4 outputs
+//     (thread == 4 adjacent output columns of one output row and channel);
+//   * u8 -> normalised float goes through a 3 x 256 table built per CTA with the exact IEEE divisions of the
+//     reference ((u/255 - mean)/std resp. (u - 255 mean)/(255 std)), so the epilogue is a lookup.
+// Thread x of the composite phase owns crop column x of all 4 rows of the group: global loads are coalesced along x
+// and the packed word is written with one conflict-free STS.32 per channel.
+// ----------------------------------------------------------------------------------------------
+constexpr int kV2Threads = 512;
+template <int SRC, int KS>
+__global__ void __launch_bounds__(kV2Threads, 2)
+ingest_v2_kernel(const void* __restrict__ scene_v, const uint8_t* __restrict__ nodata, int Hs, int Ws,
+                 const float* __restrict__ stats, const int* __restrict__ boxes, int crop, const int* __restrict__ coef,
+                 const int* __restrict__ bounds, int ksize, int band, int rows_pad, float m0, float m1, float m2,
+                 float s0, float s1, float s2, float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_patch,
+                 long long patch_tile_stride, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_nodata,
+                 const uint8_t* __restrict__ src_u8, int src_chw, int prec) {
+  constexpr bool kFromU8 = (SRC == kSrcU8);
+  using SceneT = typename std::conditional<SRC == kSrcF32, float, uint16_t>::type;
+  const SceneT* __restrict__ scene = static_cast<const SceneT*>(scene_v);
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint32_t* comp = reinterpret_cast<uint32_t*>(sm);                 // [2][3][crop] packed 4-row words
+  uint8_t* hbuf = sm + 2 * 3 * crop * 4;                            // [3][rows_pad][kOut]
+  float* lut = reinterpret_cast<float*>(hbuf + 3 * rows_pad * kOut);  // [3][256]
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.y;
+  const int oy0 = blockIdx.x * band;
+  const int oy1 = min(oy0 + band, kOut);
+  const int r0 = bounds[2 * oy0];
+  const int r1 = bounds[2 * (oy1 - 1)] + bounds[2 * (oy1 - 1) + 1];
+  const int nrows = r1 - r0;
+  const int ngroups = (nrows + 3) >> 2;
+  const long long npix = static_cast<long long>(Hs) * Ws;
+
+  {
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+    for (int i = tid; i < 768; i += kV2Threads) {
+      const int c = i >> 8;
+      const float u = static_cast<float>(i & 255);
+      lut[i] = kFromU8 ? __fdiv_rn(__fsub_rn(u, mean[c]), stdv[c])
+                       : __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), mean[c]), stdv[c]);
+    }
+  }
+  // horizontal pass: this thread's output column and its coefficients
+  int kw[KS];
+  int hx0 = 0;
+  if (tid < kOut) {
+    hx0 = bounds[2 * tid];
+    const int hcnt = bounds[2 * tid + 1];
+#pragma unroll
+    for (int t = 0; t < KS; ++t) kw[t] = (t < hcnt && t < ksize) ? coef[tid * ksize + t] : 0;
+  } else {
+#pragma unroll
+    for (int t = 0; t < KS; ++t) kw[t] = 0;
+  }
+
+  int xmin = 0, ymin = 0;
+  float mn = 0.f, den[3] = {1.f, 1.f, 1.f};
+  if constexpr (!kFromU8) {
+    xmin = boxes[tile * 4 + 0];
+    ymin = boxes[tile * 4 + 1];
+    mn = stats[0];
+    const float hi = __fadd_rn(3000.0f, mn);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) den[c] = __fsub_rn(fminf(fmaxf(stats[1 + c], mn), hi), mn);
+  }
+  const long long plane = static_cast<long long>(crop) * crop;
+
+  auto composite = [&](int g, int buf) {
+    for (int x = tid; x < crop; x += kV2Threads) {
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int rr = 4 * g + r;
+        if (rr >= nrows) break;
+        uint32_t v0 = 0, v1 = 0, v2 = 0;
+        if constexpr (kFromU8) {
+          const uint8_t* img = src_u8 + static_cast<long long>(tile) * 3 * plane;
+          const long long p = static_cast<long long>(r0 + rr) * crop + x;
+          if (src_chw) { v0 = img[p]; v1 = img[plane + p]; v2 = img[2 * plane + p]; }
+          else { v0 = img[p * 3]; v1 = img[p * 3 + 1]; v2 = img[p * 3 + 2]; }
+        } else {
+          const int sy = ymin + r0 + rr, sx = xmin + x;
+          uint8_t nd = 1;
+          if (sy >= 0 && sy < Hs && sx >= 0 && sx < Ws) {
+            const long long p = static_cast<long long>(sy) * Ws + sx;
+            nd = nodata[p] ? 1 : 0;
+            if (!nd) {
+              const float b0 = scene[p], b1 = scene[npix + p], b2 = scene[2 * npix + p], b3 = scene[3 * npix + p];
+              v0 = composite_u8(b3, mn, den[0]);
+              v1 = composite_u8(b2, mn, den[1]);
+              v2 = composite_u8(__fmul_rn(__fadd_rn(b0, b1), 0.5f), mn, den[2]);
+            }
+          }
+          // crop-resolution outputs; neighbouring bands write identical values to the rows they share
+          if (out_u8) {
+            uint8_t* o = out_u8 + ((static_cast<long long>(tile) * crop + (r0 + rr)) * crop + x) * 3;
+            o[0] = static_cast<uint8_t>(v0); o[1] = static_cast<uint8_t>(v1); o[2] = static_cast<uint8_t>(v2);
+          }
+          if (out_nodata) out_nodata[(static_cast<long long>(tile) * crop + (r0 + rr)) * crop + x] = nd;
+        }
+        w0 |= v0 << (8 * r);
+        w1 |= v1 << (8 * r);
+        w2 |= v2 << (8 * r);
+      }
+      comp[(buf * 3 + 0) * crop + x] = w0;
+      comp[(buf * 3 + 1) * crop + x] = w1;
+      comp[(buf * 3 + 2) * crop + x] = w2;
+    }
+  };
+  auto horizontal = [&](int g, int buf) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const uint32_t* cp = comp + (buf * 3 + ch) * crop;
+      int a0 = 1 << (prec - 1), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+      for (int t = 0; t < KS; ++t) {
+        const uint32_t w = cp[min(hx0 + t, crop - 1)];
+        const int k = kw[t];
+        a0 += static_cast<int>(w & 0xFFu) * k;
+        a1 += static_cast<int>((w >> 8) & 0xFFu) * k;
+        a2 += static_cast<int>((w >> 16) & 0xFFu) * k;
+        a3 += static_cast<int>(w >> 24) * k;
+      }
+      uint8_t* hp = hbuf + (ch * rows_pad + 4 * g) * kOut + tid;
+      hp[0] = clip8(a0, prec);
+      hp[kOut] = clip8(a1, prec);
+      hp[2 * kOut] = clip8(a2, prec);
+      hp[3 * kOut] = clip8(a3, prec);
+    }
+  };
+
+  composite(0, 0);
+  for (int g = 0; g < ngroups; ++g) {
+    __syncthreads();
+    if (g + 1 < ngroups) composite(g + 1, (g + 1) & 1);
+    if (tid < kOut) horizontal(g, g & 1);
+  }
+  __syncthreads();
+
+  // ---- vertical pass + normalise: item = (output row, channel, 4 adjacent output columns) ----
+  const int items = (oy1 - oy0) * 3 * (kOut / 4);
+  for (int i = tid; i < items; i += kV2Threads) {
+    const int q = i % (kOut / 4);
+    const int c = (i / (kOut / 4)) % 3;
+    const int oy = oy0 + i / (3 * (kOut / 4));
+    const int y0 = bounds[2 * oy] - r0, cnt = bounds[2 * oy + 1];
+    const int* k = coef + oy * ksize;
+    int a0 = 1 << (prec - 1), a1 = a0, a2 = a0, a3 = a0;
+    const uint8_t* hp = hbuf + (c * rows_pad + y0) * kOut + 4 * q;
+    for (int t = 0; t < cnt; ++t) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(hp + t * kOut);
+      const int kk = __ldg(k + t);
+      a0 += static_cast<int>(w & 0xFFu) * kk;
+      a1 += static_cast<int>((w >> 8) & 0xFFu) * kk;
+      a2 += static_cast<int>((w >> 16) & 0xFFu) * kk;
+      a3 += static_cast<int>(w >> 24) * kk;
+    }
+    const float* lc = lut + c * 256;
+    const float f0 = lc[clip8(a0, prec)], f1 = lc[clip8(a1, prec)], f2 = lc[clip8(a2, prec)], f3 = lc[clip8(a3, prec)];
+    const int ox = 4 * q;
+    if (out_nchw)
+      *reinterpret_cast<float4*>(out_nchw + ((static_cast<long long>(tile) * 3 + c) * kOut + oy) * kOut + ox) =
+          make_float4(f0, f1, f2, f3);
+    if (out_patch) {
+      const long long row = static_cast<long long>(oy >> 4) * 28 + (ox >> 4);
+      *reinterpret_cast<uint2*>(out_patch + tile * patch_tile_stride + row * 768 + c * 256 + (oy & 15) * 16 + (ox & 15)) =
+          make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
+    }
+  }
+}
+
+namespace {
+// rows of output per CTA for the v2 kernel: the largest band whose shared memory lets two CTAs share an SM, else the
+// largest that fits at all
+bool ingest_v2_geometry(int crop, int* band_out, int* rows_pad_out, size_t* smem_out) {
+  const double scale = static_cast<double>(crop) / 448.0;
+  const double support = 2.0 * (scale < 1.0 ? 1.0 : scale);
+  const int bands[] = {28, 16, 8, 4, 2, 1};
+  for (int pass = 0; pass < 2; ++pass) {
+    const size_t limit = pass == 0 ? 110 * 1024 : 200 * 1024;
+    for (int band : bands) {
+      const int rows = (static_cast<int>(band * scale + 2 * support + 4) + 3) / 4 * 4;
+      const size_t smem = 24ull * crop + 3ull * rows * 448 + 3072;
+      if (smem <= limit) {
+        *band_out = band;
+        *rows_pad_out = rows;
+        *smem_out = smem;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+template <int SRC, int KS>
+int launch_ingest_v2(const void* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
+                     int n_tiles, int crop, const int* coef, const int* bounds, int ksize, const float* mean,
+                     const float* stdv, float* out_nchw, __nv_bfloat16* out_patch, long long patch_tile_stride,
+                     uint8_t* out_u8, uint8_t* out_nodata, const uint8_t* src_u8, int src_chw, int prec,
+                     cudaStream_t stream) {
+  int band, rows_pad;
+  size_t smem;
+  BSEG_REQUIRE(ingest_v2_geometry(crop, &band, &rows_pad, &smem), "ingest: crop=%d does not fit in shared memory", crop);
+  auto kern = ingest_v2_kernel<SRC, KS>;
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_bytes = smem;
+  }
+  dim3 grid((kOut + band - 1) / band, n_tiles);
+  constexpr bool kFromU8 = (SRC == kSrcU8);
+  const double in_bytes = kFromU8 ? 3.0 : (SRC == kSrcF32 ? 17.0 : 9.0);  // per crop pixel: bands + nodata
+  ProfScope prof(CAT_INGEST, 0,
+                 static_cast<double>(n_tiles) * (in_bytes * crop * crop + 3.0 * 448 * 448 * ((out_nchw ? 4 : 0) + (out_patch ? 2 : 0))),
+                 stream);
+  kern<<<grid, kV2Threads, smem, stream>>>(scene, nodata, Hs, Ws, stats, boxes, crop, coef, bounds, ksize, band,
+                                           rows_pad, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], out_nchw,
+                                           out_patch, patch_tile_stride, out_u8, out_nodata, src_u8, src_chw, prec);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+}  // namespace
+
 namespace {
 template <int SRC>
 int launch_ingest_t(const void* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
@@ -274,6 +504,14 @@ int launch_ingest_t(const void* scene, const uint8_t* nodata, int Hs, int Ws, co
   if (n_tiles == 0) return 0;
   BSEG_REQUIRE(band > 0 && max_rows > 0 && crop > 0, "ingest: bad geometry");
   BSEG_REQUIRE(prec >= 1 && prec <= 22, "ingest: coefficient precision %d out of range", prec);
+  if (ksize <= 8)
+    return launch_ingest_v2<SRC, 8>(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, mean, stdv,
+                                    out_nchw, out_patch, patch_tile_stride, out_u8, out_nodata, src_u8, src_chw, prec,
+                                    stream);
+  if (ksize <= 12)
+    return launch_ingest_v2<SRC, 12>(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, coef, bounds, ksize, mean,
+                                     stdv, out_nchw, out_patch, patch_tile_stride, out_u8, out_nodata, src_u8, src_chw,
+                                     prec, stream);
   const size_t smem = static_cast<size_t>(3) * max_rows * (crop + kOut);
   BSEG_REQUIRE(smem <= 200 * 1024, "ingest: crop=%d band=%d needs %zu B of shared memory", crop, band, smem);
   constexpr bool kFromU8 = (SRC == kSrcU8);
