@@ -1,4 +1,5 @@
-// Fused SegGPT attention, one CTA per (sequence, head, 256-query tile):
+// Fused SegGPT attention, one CTA per (sequence, head, 128-query tile), two CTAs per SM (BSEG_ATTN_WG=1, the default;
+// the warp map below shows the older BSEG_ATTN_WG=2 shape: one CTA per SM with two softmax warpgroups / 256 queries):
 //     out = softmax( (q*scale) k^T + rel_h[q, kh] + rel_w[q, kw] ) v
 // with the decomposed relative-position bias of modeling_seggpt.py:268-311 computed from the UNSCALED q
 // (modeling_seggpt.py:324-329) and an fp32 softmax (:331).  The reference materialises a
@@ -39,8 +40,17 @@ namespace bseg {
 #define BSEG_ATTN_SKIP_EXP 0
 #endif
 
+// BSEG_ATTN_WG = 2: one CTA per SM, two softmax warpgroups (256 queries) sharing the K/V stages.
+// BSEG_ATTN_WG = 1: two CTAs per SM, one softmax warpgroup (128 queries) each, 2-stage rings, the rel tables overlay the
+//                   V stages: 13 instead of 14 warpgroup tiles per (sequence, head), and one CTA's prologue / epilogue
+//                   overlaps the other's main loop.
+// Measured on B200 (tools/ab_attention_wg.sh, nseq 128): WG=2 2.716 ms (487 TFLOP/s), WG=1 2.522 ms (525 TFLOP/s).
+#ifndef BSEG_ATTN_WG
+#define BSEG_ATTN_WG 1
+#endif
+
 namespace attn {
-constexpr int kWG = 2;
+constexpr int kWG = BSEG_ATTN_WG;
 constexpr int kQTile = 128;            // queries per softmax warpgroup
 constexpr int kCtaQ = kWG * kQTile;    // 256
 constexpr int kKB = 112;               // keys per block
@@ -49,10 +59,11 @@ constexpr int kGridW = 28;
 constexpr int kGridH = 56;
 constexpr int kT = kGridW * kGridH;    // 1568
 constexpr int kNumKB = kT / kKB;       // 14
-constexpr int kStages = 3;
-constexpr int kThreads = 128 + kWG * 128;  // 384
-constexpr int kRegsControl = 64;
-constexpr int kRegsSoftmax = 216;  // 128*64 + 256*216 = 63488 <= 65536
+constexpr int kStages = kWG == 2 ? 3 : 2;
+constexpr int kThreads = 128 + kWG * 128;  // 384 | 256
+constexpr int kCtasPerSm = kWG == 2 ? 1 : 2;
+constexpr int kRegsControl = kWG == 2 ? 64 : 40;
+constexpr int kRegsSoftmax = 216;  // 128*64 + 256*216 = 63488 <= 65536 | 2 * (128*40 + 128*216) = 65536
 constexpr int kRelRows = 176;  // 112 (reversed rel_pos_h, 111 used) + 64 (reversed rel_pos_w, 55 used)
 
 constexpr int kQBytes = kQTile * 128;        // 16384 per warpgroup
@@ -68,15 +79,18 @@ constexpr int kOffQ = 0;
 constexpr int kOffK = kOffQ + kWG * kQBytes;
 constexpr int kOffV = kOffK + kStages * kKBytes;
 constexpr int kOffBh = kOffV + kStages * kVBytes;
-constexpr int kOffRel = (kOffBh + kWG * kBhBytes + 1023) / 1024 * 1024;  // rel tables, then reused as bw staging
+// rel tables, then reused as bw staging; with one warpgroup per CTA the region overlays the (not yet used) V stages
 constexpr int kRelRegion = (kWG * kBwBytes > kRelBytes) ? kWG * kBwBytes : kRelBytes;
-constexpr int kOffBar = kOffRel + kRelRegion;
+constexpr bool kRelOverlaysV = (kWG == 1);
+static_assert(!kRelOverlaysV || kRelRegion <= kStages * kVBytes, "rel overlay does not fit in the V stages");
+constexpr int kOffRel = kRelOverlaysV ? kOffV : (kOffBh + kWG * kBhBytes + 1023) / 1024 * 1024;
+constexpr int kOffBar = kRelOverlaysV ? (kOffBh + kWG * kBhBytes + 1023) / 1024 * 1024 : kOffRel + kRelRegion;
 constexpr int kSmemBytes = kOffBar + 256 + 1024;
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kSmemBytes * kCtasPerSm + 1024 * kCtasPerSm <= 228 * 1024, "shared memory budget");
 
 // TMEM columns: warpgroup w owns [w*256, w*256+256): S at +0 (112 of 128), P at +128 (56 of 64, packed bf16 pairs),
 // O at +192 (64); G (176) overlays S and P in the prologue
-constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemCols = 256 * kWG;
 constexpr uint32_t kColsPerWG = 256;
 constexpr uint32_t kColP = 128;
 constexpr uint32_t kColO = 192;
@@ -105,7 +119,7 @@ __device__ __forceinline__ uint32_t scale_bf16x2(uint32_t v, float a) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(attn::kThreads, 1)
+__global__ void __launch_bounds__(attn::kThreads, attn::kCtasPerSm)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_vt, const __grid_constant__ CUtensorMap tmap_rel,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, int heads) {
@@ -127,7 +141,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* s_free = bars + 18;    // [kWG][2]  softmax -> MMA: half h of the S region may be overwritten
   uint64_t* p_full = bars + 22;    // [kWG]     softmax -> MMA: P_j is in TMEM (and O rescaled if it had to be)
   uint64_t* pv_done = bars + 24;   // [kWG]     MMA -> softmax: O += P_j V_j retired (P region free, O stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* rel_free = bars + 26;  // softmax -> TMA: the rel / bw staging region is dead (it overlays the V stages)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -135,7 +150,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const int head = blockIdx.y;
   const int seq = blockIdx.z;
   const int sh = seq * heads + head;
-  const int n_active = (q0 + kQTile < kT) ? 2 : 1;  // the last tile of a sequence has one live warpgroup
+  const int n_active = (kWG == 2 && q0 + kQTile < kT) ? 2 : 1;  // the last tile of a sequence has one live warpgroup
 #ifdef BSEG_ATTN_TRACE
   const bool trace_cta = blockIdx.x == 2 && blockIdx.y == 5 && blockIdx.z == gridDim.z / 2;
 #endif
@@ -147,6 +162,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_prefetch_desc(&tmap_rel);
     mbar_init(q_full, 1);
     mbar_init(g_full, n_active);         // one commit per MMA issuer
+    mbar_init(rel_free, 4 * n_active);   // one arrive per live softmax warp
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], n_active);  // a stage is free once every live warpgroup's MMAs on it have retired
@@ -188,6 +204,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         __syncwarp();
         if (kb >= kStages) mbar_wait(&v_empty[st], ((kb / kStages) & 1) ^ 1);
+        if (kRelOverlaysV && kb == 0) mbar_wait(rel_free, 0);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&v_full[st], kVBytes);
           tma_load_3d(sV + st * kVBytes, &tmap_vt, &v_full[st], kb * kKB, 0, sh);
@@ -315,11 +332,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       float bw[kGridW];
 #pragma unroll
       for (int i = 0; i < kGridW; ++i) bw[i] = stage[i];
+      // the staging area is about to be overwritten by TMA (it overlays the V stages): order this thread's generic-proxy
+      // stores to it before the async-proxy writes that follow the rel_free hand-off
+      if (kRelOverlaysV) fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {  // G consumed: both halves of the S region are free for S_0
         mbar_arrive(&s_free[2 * w]);
         mbar_arrive(&s_free[2 * w + 1]);
+        if (kRelOverlaysV) mbar_arrive(rel_free);  // ... and the bw staging has been read
       }
 
       // De-phase the two warpgroups by about half a key block: both share the SM's MUFU (16 ex2/clk) and both have the
