@@ -380,7 +380,7 @@ struct FwdBufs {
 
 int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
                  const float* prompt_masks, int B, int embedding_type, int P, const FwdBufs& fb, float* pred_masks,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, bool query_half_only = false) {
   int rc;
   // ---- embeddings: patchify + GEMM (modeling_seggpt.py:713-737, 163-206) ----
   __nv_bfloat16* a_patch = fb.mlp;
@@ -450,15 +450,29 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
   }
 
   // ---- decoder (modeling_seggpt.py:555-585) ----
+  // query_half_only: the reference's predict / loss code reads pred_masks[:, :, 448:] only (src/model.py:158-160,48-57).
+  // The conv3x3 at image row 448 needs row 447, so decoder_embed runs from token row 27 (tokens 756..1567) and the head
+  // from image row 448; pred_masks rows < 448 are zero-filled.
+  const int kTok0 = query_half_only ? 27 * 28 : 0;
   {
     GemmEpiParams ep;
     ep.out = fb.dec; ep.bias = h->dec_embed_b; ep.T = kT; ep.grid_w = 28;
-    if ((rc = launch_gemm(EPI_PIXSHUF, fb.inter, 4 * kD, h->dec_embed_w, static_cast<long long>(B) * kT, kDecN, 4 * kD,
-                          ep, stream)))
-      return rc;
+    GemmRows gr{kT, B, kTok0, kT - kTok0};
+    if ((rc = launch_gemm_rows(EPI_PIXSHUF, fb.inter, 4 * kD, h->dec_embed_w, gr, kDecN, 4 * kD, ep, stream))) return rc;
+  }
+  if (query_half_only) {
+    const size_t plane = 896ull * 448, half = 448ull * 448;
+    for (int b = 0; b < B; ++b)
+      for (int c = 0; c < 3; ++c) {
+        cudaError_t ce = cudaMemsetAsync(pred_masks + (static_cast<size_t>(b) * 3 + c) * plane, 0, half * 4, stream);
+        if (ce != cudaSuccess) {
+          set_error("bseg_forward: memset failed: %s", cudaGetErrorString(ce));
+          return -static_cast<int>(ce);
+        }
+      }
   }
   return launch_decoder_head(fb.dec, h->conv_w9, h->conv_b, h->dec_ln_w, h->dec_ln_b, h->head_w, h->head_b, pred_masks,
-                             B, 896, 448, h->eps, stream);
+                             B, 896, 448, h->eps, query_half_only ? 448 : 0, stream);
 }
 
 int check_forward_args(bseg_handle* h, int batch, int embedding_type, const void* workspace, const char* who) {
@@ -496,7 +510,7 @@ size_t bseg_train_workspace_bytes(const bseg_handle* h, int batch) {
   return train_layout(h, batch).total;
 }
 
-int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+static int forward_entry(bool query_half_only, bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
                  const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
                  size_t workspace_bytes, float* pred_masks, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -513,7 +527,21 @@ int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_
   fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
   fb.layers.assign(h->num_layers, {fb.h_emb, fb.h_emb, bf(L.q), bf(L.k), bf(L.vt), bf(L.att), nullptr, nullptr});
   return forward_impl(h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, ensemble_prompts, fb,
-                      pred_masks, stream);
+                      pred_masks, stream, query_half_only);
+}
+
+int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                 const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
+                 size_t workspace_bytes, float* pred_masks, void* stream) {
+  return forward_entry(false, h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type,
+                       ensemble_prompts, workspace, workspace_bytes, pred_masks, stream);
+}
+
+int bseg_forward_query_half(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                            const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts,
+                            void* workspace, size_t workspace_bytes, float* pred_masks, void* stream) {
+  return forward_entry(true, h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type,
+                       ensemble_prompts, workspace, workspace_bytes, pred_masks, stream);
 }
 
 // ---- fp32 accuracy mode (precise.cu) ----
@@ -1031,7 +1059,7 @@ int bseg_decoder_head(const void* x_nhwc, const void* w9, const float* conv_b, c
                       const float* head_w, const float* head_b, float* pred, int batch, int H, int W, float eps,
                       void* stream) {
   return launch_decoder_head(static_cast<const __nv_bfloat16*>(x_nhwc), static_cast<const __nv_bfloat16*>(w9),
-                             conv_b, ln_w, ln_b, head_w, head_b, pred, batch, H, W, eps,
+                             conv_b, ln_w, ln_b, head_w, head_b, pred, batch, H, W, eps, 0,
                              static_cast<cudaStream_t>(stream));
 }
 

@@ -308,14 +308,17 @@ int launch_decoder_conv_t(const __nv_bfloat16* x_nhwc, int rows_in, const __nv_b
 
 int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, const float* conv_b, const float* ln_w,
                         const float* ln_b, const float* head_w, const float* head_b, float* pred, int B, int H, int W,
-                        float eps, cudaStream_t stream) {
+                        float eps, int y_begin, cudaStream_t stream) {
+  BSEG_REQUIRE(y_begin >= 0 && y_begin < H && y_begin % dconv::kTileH == 0, "decoder_head: y_begin=%d", y_begin);
   dconv::Params prm{};
   prm.conv_b = conv_b; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.head_w = head_w; prm.head_b = head_b;
   prm.pred = pred;
   prm.B = B; prm.H = H; prm.W = W; prm.eps = eps;
+  prm.ty_begin = y_begin / dconv::kTileH;  // image rows < y_begin are not computed (pred is left untouched there)
+  const double rows = H - y_begin;
   return launch_decoder_conv_t<dconv::kModeHead>(x_nhwc, H, w9, prm,
-                                                 static_cast<double>(B) * H * W * (2.0 * 576 * 64 + 2.0 * 64 * 3),
-                                                 static_cast<double>(B) * H * W * (64 * 2 + 3 * 4), stream);
+                                                 static_cast<double>(B) * rows * W * (2.0 * 576 * 64 + 2.0 * 64 * 3),
+                                                 static_cast<double>(B) * rows * W * (64 * 2 + 3 * 4), stream);
 }
 
 // Backward through conv1x1 head, GELU and LayerNorm(C) for image rows >= y0 (the loss only touches the query half,

@@ -36,7 +36,7 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
 int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9 /*[9][64 out][64 in]*/,
                         const float* conv_b, const float* ln_w, const float* ln_b, const float* head_w /*[3][64]*/,
                         const float* head_b, float* pred /*[B,3,H,W]*/, int B, int H, int W, float eps,
-                        cudaStream_t stream);
+                        int y_begin /*first image row computed*/, cudaStream_t stream);
 
 int launch_decoder_head_bwd(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9, const float* conv_b,
                             const float* ln_w, const float* ln_b, const float* head_w, const float* head_b,

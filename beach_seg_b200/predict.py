@@ -38,8 +38,12 @@ def shard_tiles(n_tiles: int, rank: int, world_size: int) -> range:
 class TilePredictor:
     """ingest -> SegGPT forward -> palette decode (+resize to crop size) for batches of tile boxes of one scene."""
 
-    def __init__(self, model: SegGptB200, crop_size: int, num_classes: int = 4, random_palette: bool = True):
+    def __init__(self, model: SegGptB200, crop_size: int, num_classes: int = 4, random_palette: bool = True,
+                 query_half_only: bool = False):
+        """query_half_only: run the decoder for the query half only (`bseg_forward_query_half`); class maps are
+        bit-identical because `process_pred_masks` reads pred_masks[:, :, 448:] only (src/model.py:158-160)."""
         self.model = model
+        self.query_half_only = query_half_only
         self.crop_size = crop_size
         self.num_classes = num_classes
         self.random_palette = random_palette  # the reference's forward passes train=True (src/model.py:134)
@@ -58,7 +62,7 @@ class TilePredictor:
         tiles = ops.ingest_tiles(scene_u16, nodata, stats, boxes, self.crop_size)
         prompt_color = ops.colorize_norm(prompt_masks, pal_u8)
         out = self.model(pixel_values=tiles["image"], prompt_pixel_values=prompt_images, prompt_masks=prompt_color,
-                         embedding_type="instance")
+                         embedding_type="instance", query_half_only=self.query_half_only)
         return ops.decode_palette(out.pred_masks, pal_norm, out_size=self.crop_size, dtype=torch.uint8)
 
 

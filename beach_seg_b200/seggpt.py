@@ -193,7 +193,11 @@ class SegGptB200(torch.nn.Module):
                 bool_masked_pos: Optional[torch.Tensor] = None, feature_ensemble: Optional[bool] = None,
                 embedding_type: Optional[str] = None, labels: Optional[torch.Tensor] = None,
                 output_attentions: Optional[bool] = None, output_hidden_states: Optional[bool] = None,
-                return_dict: Optional[bool] = None, ensemble_group: Optional[int] = None, **kwargs) -> SegGptOutput:
+                return_dict: Optional[bool] = None, ensemble_group: Optional[int] = None,
+                query_half_only: bool = False, **kwargs) -> SegGptOutput:
+        """HF forward signature (HF:modeling_seggpt.py:839-959) plus two extensions: `ensemble_group` (several tiles of P
+        prompts per launch) and `query_half_only` (skip the decoder for the prompt half: pred_masks[:, :, :448] is zero,
+        the bottom half -- the only part the reference ever reads -- is bit-identical)."""
         for name, t in (("pixel_values", pixel_values), ("prompt_pixel_values", prompt_pixel_values),
                         ("prompt_masks", prompt_masks)):
             if t.ndim != 4 or t.shape[1] != 3:
@@ -243,8 +247,12 @@ class SegGptB200(torch.nn.Module):
         pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=self._device)
         L = _lib.lib()
         step = self.max_batch if P == 0 else max(P, (self.max_batch // P) * P)
-        fwd, fwd_name = (L.bseg_forward_f32, "bseg_forward_f32") if self.precision == "fp32" else \
-            (L.bseg_forward, "bseg_forward")
+        if self.precision == "fp32":
+            fwd, fwd_name = L.bseg_forward_f32, "bseg_forward_f32"
+        elif query_half_only:
+            fwd, fwd_name = L.bseg_forward_query_half, "bseg_forward_query_half"
+        else:
+            fwd, fwd_name = L.bseg_forward, "bseg_forward"
         with torch.cuda.device(self._device):
             for s in range(0, B, step):
                 n = min(step, B - s)

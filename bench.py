@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=2)
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg (BASELINE configs[3])")
     ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--no-fast-path", action="store_true", help="skip the query-half-only decoder leg")
     ap.add_argument("--no-fp32-check", action="store_true",
                     help="skip the fp32-accuracy-mode leg (bf16 path vs bseg_forward_f32 on the bench inputs)")
     args = ap.parse_args()
@@ -394,6 +395,41 @@ def main():
     if not args.no_train:
         train = train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrier, timed, L, peaks)
 
+    # ---- optional fast path: decoder on the query half only (bseg_forward_query_half); class maps are bit-identical
+    # (checked below).  Reported beside the headline, which keeps the full forward. ----
+    fast = None
+    if not args.no_fast_path:
+        fast_pred = TilePredictor(model, CROP, query_half_only=True)
+        fast_pipe = HostScenePipeline(fast_pred, scene_host.shape, TILES_PER_STEP, CROP)
+        canvas2 = torch.zeros_like(canvas)
+
+        def step_fast():
+            cls = fast_pred.predict_tiles(scene, nodata, stats, boxes, prompt_images, prompt_cls, palette)
+            ops.vote_accumulate(canvas2, cls, boxes, overlapping=False)
+            return cls
+
+        same = bool(torch.equal(step_fast(), step_device()))
+        ms_fast = timed(step_fast, args.steps)
+        fast_pipe.step(scene_host, nodata, stats, boxes, prompt_images, prompt_cls, palette, canvas2)
+        fast_pipe.drain()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fast_pipe.step(scene_host, nodata, stats, boxes, prompt_images, prompt_cls, palette, canvas2)
+        torch.cuda.current_stream().wait_stream(fast_pipe.copy_stream)  # the last download is inside the timed region
+        e1.record()
+        torch.cuda.synchronize()
+        ms_fast_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms_fast_e2e, op=dist.ReduceOp.MAX)
+        barrier()
+        fast = {"what": "decoder_embed + conv head on the query half only (bseg_forward_query_half); the reference's "
+                        "predict path never reads pred_masks[:, :, :448] (src/model.py:158-160)",
+                "value": world * TILES_PER_STEP * args.steps / (ms_fast * 1e-3),
+                "e2e": world * TILES_PER_STEP * args.steps / (ms_fast_e2e.item() * 1e-3), "unit": "tiles/s",
+                "class_maps_identical_to_full_forward": same}
+
     # ---- accuracy leg: the first 8 tiles of the step through the fp32 mode (bseg_forward_f32) and through the bf16
     # path, same inputs: logit deviation and class-map disagreements (north_star: "with that count reported") ----
     fp32_mode = None
@@ -445,6 +481,7 @@ def main():
                     "d2h_bytes_per_step": int(cls_host.numel()), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels": kernels, "gemm_modes": gemm_modes, "train": train, "fp32_mode": fp32_mode,
+            "query_half_fast_path": fast,
             "model_tflops": value / world * FWD_FLOP_PER_TILE / 1e12,
             "model_frac_of_tensor_peak": value / world * FWD_FLOP_PER_TILE / 1e12 / peaks["tensor"],
         }

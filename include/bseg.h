@@ -85,6 +85,15 @@ int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_
                  const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
                  size_t workspace_bytes, float* pred_masks, void* stream);
 
+/* bseg_forward for callers that only read the query half: pred_masks[:, :, 448:, :] is bit-identical to bseg_forward's,
+ * pred_masks[:, :, :448, :] is zero.  Every consumer of pred_masks in the reference reads the bottom half only
+ * (process_pred_masks src/model.py:158-160, SegGptLoss src/model.py:48-57, post_process_semantic_segmentation
+ * HF:image_processing_seggpt.py:284-286), so the decoder skips the prompt half: decoder_embed runs on token rows
+ * 27..55, the conv head on image rows 448..895 (-7.6 ms of a 125 ms step at batch 64). */
+int bseg_forward_query_half(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                            const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts,
+                            void* workspace, size_t workspace_bytes, float* pred_masks, void* stream);
+
 /* ---- fp32 accuracy mode: the same forward with every operand, accumulator and activation in IEEE fp32 on the CUDA
  * cores (no tensor cores, no bf16) -- logits within 1e-4 relative of the reference's fp32 CPU forward, about 30x
  * slower than bseg_forward.  bseg_enable_fp32 copies the fp32 matrices of `w` (the struct given to bseg_create) into

@@ -74,6 +74,22 @@ def test_small_model_feature_ensemble(dev, small):
     assert rel_l2(got4[:2], want) < REL_TOL and rel_l2(got4[2:], want_b) < REL_TOL
 
 
+def test_query_half_only_is_bit_identical(dev, small):
+    """bseg_forward_query_half: the bottom half of pred_masks (the only part the reference reads, src/model.py:158-160)
+    is bit-identical to the full forward, the top half is zero; also with the feature ensemble."""
+    _, model = small
+    px, ppx, pm = synth.model_inputs(batch=3, seed=33)
+    kw = dict(pixel_values=px.to(dev), prompt_pixel_values=ppx.to(dev), prompt_masks=pm.to(dev))
+    with torch.no_grad():
+        full = model(**kw).pred_masks
+        half = model(**kw, query_half_only=True).pred_masks
+        assert torch.equal(half[:, :, 448:], full[:, :, 448:])
+        assert not half[:, :, :448].any()
+        full_e = model(**kw, feature_ensemble=True).pred_masks
+        half_e = model(**kw, feature_ensemble=True, query_half_only=True).pred_masks
+        assert torch.equal(half_e[:, :, 448:], full_e[:, :, 448:])
+
+
 def test_interface_errors(dev, small):
     _, model = small
     z = torch.zeros((1, 3, 448, 448), device=dev)
