@@ -142,8 +142,10 @@ class PromptModel(torch.nn.Module):
         B = batch_dict["image"].shape[0]
         batch_palette, batch_palette_norm = self.create_palette(B, train=True)
         prompt_batch, prompt_masks = self.prepare_prompt(batch_dict["crop_idx"], batch_palette, train=False)
+        # opt-in: skip the decoder for the prompt half, whose pred_masks this method never reads (class maps identical)
+        fast = {"query_half_only": True} if getattr(self, "query_half_only", False) else {}
         out = self.model(pixel_values=batch_dict["image"].to(self.device), prompt_pixel_values=prompt_batch["image"],
-                         prompt_masks=prompt_masks, embedding_type="instance")
+                         prompt_masks=prompt_masks, embedding_type="instance", **fast)
         return self.process_pred_masks(out.pred_masks, batch_palette_norm)
 
     # ---- src/model.py:155-175 ----
