@@ -2,8 +2,10 @@
 // eps 1e-6) -> erf-GELU -> conv1x1(64->3), fused into one persistent implicit-GEMM kernel.
 //   input  : NHWC bf16 [B, H, W, 64]  (written by the decoder_embed GEMM's pixel-shuffle epilogue)
 //   output : NCHW fp32 [B, 3, H, W]   (== pred_masks)
-// A pixel tile is 2 image rows x 64 columns = 128 GEMM rows; each of the 9 taps is one K=64 block whose A tile
-// is a shifted TMA box (out-of-bounds rows/columns are zero filled by TMA == the conv's zero padding).
+// A pixel tile is 2 image rows x 64 columns = 128 GEMM rows; each of the 9 taps is one K=64 block.  Per column shift
+// dx one TMA box brings the 4 input rows y-1 .. y+2 (4 x 8 KB row segments, out-of-bounds rows/columns zero filled ==
+// the conv's zero padding); the A tile of tap (dy, dx) is the 16 KB window starting at segment dy, so a tile costs
+// 3 x 32 KB of L2->smem traffic instead of 9 x 16 KB (the kernel was bound by that traffic, not by MMA or epilogue).
 // N = 64 output channels fit one accumulator tile, so LN + GELU + the 1x1 head run in the epilogue registers.
 #include "common.cuh"
 #include "host_utils.h"
@@ -34,15 +36,18 @@ struct Params {
   float eps;
 };
 constexpr int kTileW = 64, kTileH = 2;
-constexpr int kStages = 6;
-constexpr int kABytes = 128 * 128;       // 16384 per tap tile
+constexpr int kStages = 3;
+constexpr int kSegBytes = kTileW * 128;  // 8192: one image row segment of the tile (64 pixels x 64 channels bf16)
+constexpr int kABytes = 4 * kSegBytes;   // 32768 per column shift dx: the 4 input rows y-1 .. y+2; the A tile of tap
+                                         // (dy, dx) is the 16 KB window starting at segment dy
 constexpr int kWBytes = 9 * 64 * 128;    // 73728: 9 taps x [64 out x 64 in] bf16
-constexpr int kThreads = 192;
+constexpr int kThreads = 64 + 256;      // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kOffW = 0;
 constexpr int kOffA = kOffW + kWBytes;
 constexpr int kOffBar = kOffA + kStages * kABytes;
 constexpr int kOffPar = kOffBar + 256;   // fp32 params: conv_b[64] ln_w[64] ln_b[64] head_w[192] head_b[3]
-constexpr int kSmemBytes = kOffPar + 400 * 4 + 1024;
+constexpr int kOffXch = kOffPar + 400 * 4;  // epilogue exchange between the two channel halves: 2*128*2 + 2*128*4 floats
+constexpr int kSmemBytes = kOffXch + (2 * 128 * 2 + 2 * 128 * 4) * 4 + 1024;
 constexpr uint32_t kTmemCols = 128;
 }  // namespace dconv
 
@@ -90,7 +95,7 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -113,12 +118,12 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int tx = static_cast<int>(tile % tiles_x);
         const int ty = static_cast<int>((tile / tiles_x) % tiles_y) + prm.ty_begin;
         const int b = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int dx = 0; dx < 3; ++dx) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full_bar[stage], kABytes);
-            tma_load_4d(sA + stage * kABytes, &tmap_x, &full_bar[stage], 0, tx * kTileW + (tap % 3) - 1,
-                        ty * kTileH + (tap / 3) - 1 - prm.y_in0, b);
+            tma_load_4d(sA + stage * kABytes, &tmap_x, &full_bar[stage], 0, tx * kTileW + dx - 1,
+                        ty * kTileH - 1 - prm.y_in0, b);
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -137,17 +142,19 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + as * 64;
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int dx = 0; dx < 3; ++dx) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t a_addr = smem_u32(sA + stage * kABytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr + k * 32),
-                           umma_desc_sw128_kmajor(w_addr + tap * 8192 + k * 32), idesc, (tap | k) != 0);
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr + dy * kSegBytes + k * 32),
+                             umma_desc_sw128_kmajor(w_addr + (dy * 3 + dx) * 8192 + k * 32), idesc, (dx | dy | k) != 0);
             umma_commit(&empty_bar[stage]);
-            if (tap == 8) umma_commit(&tmem_full[as]);
+            if (dx == 2) umma_commit(&tmem_full[as]);
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -156,8 +163,14 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       }
     }
   } else {
+    // ---- epilogue: 8 warps; a pixel's 64 channels are split between two threads (warps w and w + 4 share a TMEM lane
+    // quarter).  LayerNorm statistics and the head / LN-backward sums are combined through shared memory. ----
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;  // channels [32 * half, 32 * half + 32)
     const int r = quarter * 32 + lane;
+    const int c0 = half * 32;
+    float* xchA = reinterpret_cast<float*>(smem + kOffXch);   // [2 halves][128][2]  (mean, M2) of the half
+    float* xchB = xchA + 2 * 128 * 2;                         // [2 halves][128][4]  head partials / LN-backward sums
     int as = 0;
     uint32_t aphase = 0;
     const long long plane = static_cast<long long>(H) * W;
@@ -175,20 +188,11 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 64;
-      float v[64];
-      {
-        float t0[32], t1[32];
-        tmem_ld32(taddr, t0);
-        tmem_ld32(taddr + 32, t1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = t0[i] + (MODE == kModeDgrad ? 0.f : sPar[i]);
-          v[32 + i] = t1[i] + (MODE == kModeDgrad ? 0.f : sPar[32 + i]);
-        }
-      }
-      // accumulator is in registers: release the TMEM buffer early
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 64 + c0;
+      float v[32];
+      tmem_ld32(taddr, v);
+      tmem_ld_wait();
+      // accumulator half is in registers: release the TMEM buffer early
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -197,58 +201,76 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         // rows of the decoder_embed dgrad operand: token (y/16, x/16), column ((y%16)*16 + x%16)*64 + c
         __nv_bfloat16* dst = prm.out_bf16 +
                              (static_cast<long long>(b) * ((H >> 4) * (W >> 4)) + (y >> 4) * (W >> 4) + (x >> 4)) * 16384 +
-                             (((y & 15) << 4) + (x & 15)) * 64;
+                             (((y & 15) << 4) + (x & 15)) * 64 + c0;
 #pragma unroll
-        for (int i = 0; i < 64; i += 8)
+        for (int i = 0; i < 32; i += 8)
           *reinterpret_cast<uint4*>(dst + i) =
               make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]), pack_bf16x2(v[i + 4], v[i + 5]),
                          pack_bf16x2(v[i + 6], v[i + 7]));
       } else {
+        // two-pass statistics of this half, then Chan's combination with the other half (exact, no cancellation)
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) s += v[i];
-        const float mean = s * (1.0f / 64.0f);
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const float d = v[i] - mean;
-          ss += d * d;
+        for (int i = 0; i < 32; ++i) {
+          v[i] += sPar[c0 + i];
+          s += v[i];
         }
-        const float rstd = rsqrtf(ss * (1.0f / 64.0f) + eps);
-        if constexpr (MODE == kModeHead) {
-          float o0 = sPar[384], o1 = sPar[385], o2 = sPar[386];
+        const float mean_h = s * (1.0f / 32.0f);
+        float m2_h = 0.f;
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float g = gelu_erf((v[i] - mean) * rstd * sPar[64 + i] + sPar[128 + i]);
-            o0 = fmaf(g, sPar[192 + i], o0);
-            o1 = fmaf(g, sPar[256 + i], o1);
-            o2 = fmaf(g, sPar[320 + i], o2);
+        for (int i = 0; i < 32; ++i) {
+          const float d = v[i] - mean_h;
+          m2_h = fmaf(d, d, m2_h);
+        }
+        *reinterpret_cast<float2*>(xchA + (half * 128 + r) * 2) = make_float2(mean_h, m2_h);
+        named_bar_sync(1, 256);
+        const float2 oth = *reinterpret_cast<const float2*>(xchA + ((half ^ 1) * 128 + r) * 2);
+        const float mean = 0.5f * (mean_h + oth.x);
+        const float dm = mean_h - oth.x;
+        const float var = (m2_h + oth.y + 16.0f * dm * dm) * (1.0f / 64.0f);
+        const float rstd = rsqrtf(var + eps);
+        if constexpr (MODE == kModeHead) {
+          float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float g = gelu_erf((v[i] - mean) * rstd * sPar[64 + c0 + i] + sPar[128 + c0 + i]);
+            o0 = fmaf(g, sPar[192 + c0 + i], o0);
+            o1 = fmaf(g, sPar[256 + c0 + i], o1);
+            o2 = fmaf(g, sPar[320 + c0 + i], o2);
           }
-          float* dst = prm.pred + static_cast<long long>(b) * 3 * plane + static_cast<long long>(y) * W + x;
-          dst[0] = o0;
-          dst[plane] = o1;
-          dst[2 * plane] = o2;
+          if (half == 1) *reinterpret_cast<float4*>(xchB + (128 + r) * 4) = make_float4(o0, o1, o2, 0.f);
+          named_bar_sync(2, 256);
+          if (half == 0) {
+            const float4 ob = *reinterpret_cast<const float4*>(xchB + (128 + r) * 4);
+            float* dst = prm.pred + static_cast<long long>(b) * 3 * plane + static_cast<long long>(y) * W + x;
+            dst[0] = (o0 + ob.x) + sPar[384];
+            dst[plane] = (o1 + ob.y) + sPar[385];
+            dst[2 * plane] = (o2 + ob.z) + sPar[386];
+          }
         } else {
           // pred = head(gelu(LN(v))):  dg = head_w^T dpred;  dyl = dg * gelu'(yl);  LN backward over the 64 channels
           float m1 = 0.f, m2 = 0.f;
-          float gyv[64];
+          float gyv[32];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
+          for (int i = 0; i < 32; ++i) {
             const float xh = (v[i] - mean) * rstd;
-            const float yl = fmaf(xh, sPar[64 + i], sPar[128 + i]);
-            const float dg = fmaf(dp0, sPar[192 + i], fmaf(dp1, sPar[256 + i], dp2 * sPar[320 + i]));
-            const float gy = dg * gelu_erf_grad(yl) * sPar[64 + i];
+            const float yl = fmaf(xh, sPar[64 + c0 + i], sPar[128 + c0 + i]);
+            const float dg = fmaf(dp0, sPar[192 + c0 + i], fmaf(dp1, sPar[256 + c0 + i], dp2 * sPar[320 + c0 + i]));
+            const float gy = dg * gelu_erf_grad(yl) * sPar[64 + c0 + i];
             m1 += gy;
             m2 = fmaf(gy, xh, m2);
             v[i] = xh;
             gyv[i] = gy;
           }
-          m1 *= (1.0f / 64.0f);
-          m2 *= (1.0f / 64.0f);
+          *reinterpret_cast<float2*>(xchB + (half * 128 + r) * 4) = make_float2(m1, m2);
+          named_bar_sync(2, 256);
+          const float2 om = *reinterpret_cast<const float2*>(xchB + ((half ^ 1) * 128 + r) * 4);
+          m1 = (m1 + om.x) * (1.0f / 64.0f);
+          m2 = (m2 + om.y) * (1.0f / 64.0f);
           __nv_bfloat16* dst = prm.out_bf16 +
-                               ((static_cast<long long>(b) * (H - prm.y_out0) + (y - prm.y_out0)) * W + x) * 64;
+                               ((static_cast<long long>(b) * (H - prm.y_out0) + (y - prm.y_out0)) * W + x) * 64 + c0;
 #pragma unroll
-          for (int i = 0; i < 64; i += 8) {
+          for (int i = 0; i < 32; i += 8) {
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = rstd * (gyv[i + j] - m1 - v[i + j] * m2);
@@ -282,7 +304,7 @@ int launch_decoder_conv_t(const __nv_bfloat16* x_nhwc, int rows_in, const __nv_b
   {
     uint64_t dims[4] = {64, static_cast<uint64_t>(prm.W), static_cast<uint64_t>(rows_in), static_cast<uint64_t>(prm.B)};
     uint64_t strides[3] = {128, static_cast<uint64_t>(prm.W) * 128, static_cast<uint64_t>(rows_in) * prm.W * 128};
-    uint32_t box[4] = {64, kTileW, kTileH, 1};
+    uint32_t box[4] = {64, kTileW, kTileH + 2, 1};  // the tile's rows plus one halo row above and below
     int rc = make_tmap_bf16(&tx, x_nhwc, 4, dims, strides, box);
     if (rc) return rc;
   }
