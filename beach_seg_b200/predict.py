@@ -114,8 +114,10 @@ class NoPromptPredictor:
     prompts, palette post-processing at crop size, nodata zeroing.  One launch handles `tiles x n_prompts` model
     samples."""
 
-    def __init__(self, model: SegGptB200, processor, crop_size: int, num_classes: int = 4):
+    def __init__(self, model: SegGptB200, processor, crop_size: int, num_classes: int = 4,
+                 query_half_only: bool = False):
         self.model, self.processor, self.crop_size, self.num_classes = model, processor, crop_size, num_classes
+        self.query_half_only = query_half_only  # post-processing reads pred_masks[:, :, 448:] only (HF:284-286)
         self._pal = torch.tensor(build_palette(num_classes - 1), dtype=torch.float32)
 
     @torch.no_grad()
@@ -128,7 +130,8 @@ class NoPromptPredictor:
         px = ops.preprocess_u8(crops_u8.to(self.model.device))                      # :283-288
         px = px.repeat_interleave(P, dim=0)                                          # images=[crop_img] * len(prompts)
         out = self.model(pixel_values=px, prompt_pixel_values=prompt_pixel_values, prompt_masks=prompt_masks,
-                         embedding_type="instance", feature_ensemble=True, ensemble_group=P)  # :289-295
+                         embedding_type="instance", feature_ensemble=True, ensemble_group=P,
+                         query_half_only=self.query_half_only)                       # :289-295
         mean = ops.mean_over_prompts(out.pred_masks, P)                              # :298
         return ops.postprocess_semantic(mean, self._pal, out_size=self.crop_size, nodata=nodata,
                                         dtype=torch.uint8)                           # :299-303

@@ -134,3 +134,6 @@ def test_no_prompt_tile_body_matches_reference_pipeline(dev):
     print(f"[no-prompt tile body] class-map flips vs reference pipeline: {flips * 100:.3f} %")
     assert got.shape == (2, crop, crop) and np.all(got[nodata] == 0)
     assert flips < 0.01  # bf16 backbone: only pixels on a palette decision boundary may flip
+    fast = NoPromptPredictor(model, ours, crop, query_half_only=True).predict_tiles(
+        torch.from_numpy(tiles).to(dev), torch.from_numpy(nodata).to(dev), ppx, pm).cpu().numpy()
+    assert np.array_equal(fast, got)  # the decoder's prompt half is never read by the post-processing
