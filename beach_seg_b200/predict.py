@@ -56,6 +56,8 @@ class TilePredictor:
         ids.  Returns uint8 [n,crop,crop] class maps (nodata pixels are NOT zeroed, like src/predict.py)."""
         dev = self.model.device
         n = boxes.shape[0]
+        if n == 0:  # e.g. a shard that owns no tile of a small scene
+            return torch.empty((0, self.crop_size, self.crop_size), dtype=torch.uint8, device=dev)
         if palette is None:
             palette = create_palette(self.num_classes, n, self.random_palette, dev)
         pal_u8, pal_norm = palette
