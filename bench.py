@@ -131,6 +131,10 @@ def cpu_tile_pipeline(n_tiles: int, warmup: int):
     return 1.0 / per, cores, per
 
 
+WORKLOAD = ("batched tile inference, 512x512x4 uint16 tiles -> 448 SegGPT ViT-L (random init seed 0), batch 64 per GPU "
+            "per step: ingest+colourise+forward+decode+vote")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -140,8 +144,10 @@ def run_reference(args):
         "impl": "reference", "metric": "tiles/sec (512^2 4-band) predict", "value": tps, "unit": "tiles/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "tile inference 512x512x4 u16 -> 448 SegGPT ViT-L random-init, batch 1 per step "
-                               "(reference CPU path, src/predict.py loop)", "tiles_per_step": 1},
+        # our arm's workload; a reference step is a bounded sample of it: one tile (the reference's own batch size,
+        # src/predict.py runs batch 1) of the same synthetic 512x512x4 shape through the same model
+        "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": TILES_PER_STEP, "crop": CROP,
+                   "sample": "1 tile per step, batch 1 (reference CPU path, src/predict.py loop)", "tiles_per_step": 1},
         "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "reference",
                          "sample": f"{args.steps} tiles, 1 tile/step, HF transformers SegGPT fp32 eager (the "
                                    "reference's own dependency; torch.compile unavailable) + restated glue, median"},
@@ -473,8 +479,7 @@ def main():
             "metric": "tiles/sec (512^2 4-band) predict", "value": value, "unit": "tiles/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "batched tile inference, 512x512x4 uint16 tiles -> 448 SegGPT ViT-L (random init "
-                                   "seed 0), batch 64 per GPU per step: ingest+colourise+forward+decode+vote",
+            "config": {"workload": WORKLOAD,
                        "tiles_per_step_per_gpu": TILES_PER_STEP, "crop": CROP, "parallelism": f"dp{world} (tile shards, "
                        "no data-path collective)", "l2": "per-step activations (>8 GB) exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": int(scene_host.numel() * 2),
