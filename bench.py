@@ -395,6 +395,21 @@ def main():
         roofline["traffic_algorithmic_bytes"] = t["per_launch_avg_algorithmic_bytes"]
         roofline["traffic_source"] = t["source"] + " (4 encoder-layer GEMM launches, M=200704)"
 
+    # ---- the other kernels against their own bounds (same profiled pass; per-step times) ----
+    other = {}
+    if "attention" in kernels and clocks and clocks.get("sm_mhz"):
+        # one exponential per score element: 16 heads x 1568^2 per sequence and layer; MUFU.EX2 = 16 /clk/SM x 148 SMs
+        seqs = TILES_PER_STEP * (2 * (model.merge_index + 1) + (model.num_layers - model.merge_index - 1))
+        exps = seqs * 16 * 1568.0 * 1568.0
+        peak = 16 * 148 * clocks["sm_mhz"] * 1e6
+        ach = exps / (kernels["attention"]["ms_per_step"] * 1e-3)
+        other["attention"] = {"bound": "mufu (ex2 at the sampled SM clock)", "achieved": ach / 1e12, "peak": peak / 1e12,
+                              "unit": "T exp/s", "frac": ach / peak}
+    for name in ("layernorm", "ingest", "decode", "vote"):
+        if name in kernels and kernels[name]["gbs"]:
+            other[name] = {"bound": "hbm", "achieved": kernels[name]["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                           "frac": kernels[name]["gbs"] / peaks["hbm"]}
+
     # ---- train-step leg (BASELINE configs[3]): ingest -> PromptModel.training_step -> backward -> prompt-grad
     # all-reduce -> AdamW, batch 32 per GPU (weak scaling), ms/iter = max over ranks ----
     train = None
@@ -484,7 +499,8 @@ def main():
                        "no data-path collective)", "l2": "per-step activations (>8 GB) exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": int(scene_host.numel() * 2),
                     "d2h_bytes_per_step": int(cls_host.numel()), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other_kernels": other,
+            "cpu_baseline": cpu_baseline,
             "kernels": kernels, "gemm_modes": gemm_modes, "train": train, "fp32_mode": fp32_mode,
             "query_half_fast_path": fast,
             "model_tflops": value / world * FWD_FLOP_PER_TILE / 1e12,
