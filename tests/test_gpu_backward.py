@@ -291,3 +291,49 @@ def test_prompt_model_training_step_matches_reference(dev, batch):
     opt.step()
     moved = [not torch.equal(b, p.detach()) for b, p in zip(before, model.prompt_params_list)]
     assert moved == [i in chosen for i in range(3)]
+
+
+def test_training_step_full_batch_properties(dev):
+    """BASELINE config 4 at full size (batch 32, 24 layers, 8 prompts): no CPU oracle run is affordable (~7 min), so
+    size-independent properties instead: (1) the step is reproducible: same seeds -> bitwise the same gradients (the
+    scalar loss is a float-atomic reduction, equal to 1e-5),
+    (2) only the drawn prompts receive a gradient and it is finite and non-zero, (3) the gradient is linear in the loss
+    scale: backward of 2*loss == 2 * backward of loss (exact in floating point: a power of two)."""
+    from beach_seg_b200.config import BeachSegConfig
+    from beach_seg_b200.model import PromptModel
+
+    B, n_prompts = 32, 8
+    conf = BeachSegConfig(checkpoint="random-init:0", seed=42)
+    px = synth.normalize(synth.smooth_image(B, seed=70)).to(dev)
+    mask = synth.blocky_mask(B, seed=71)[:, None].to(dev)
+    prompt_img01 = synth.smooth_image(n_prompts, seed=72)
+    prompt_cls = synth.blocky_mask(n_prompts, seed=73)
+
+    class DM:
+        prompt_imgs = [{"image": prompt_img01[i], "mask": prompt_cls[i][None], "crop_idx": i} for i in range(n_prompts)]
+
+    backbone = None
+    runs = []
+    for scale in (1.0, 1.0, 2.0):
+        model = PromptModel(conf, device=dev, model=backbone)
+        backbone = model.model
+        model.create_trainable_params(DM)
+        torch.manual_seed(11)
+        loss = model.training_step({"image": px, "mask": mask}, 0)
+        (loss * scale).backward()
+        torch.cuda.synchronize()
+        runs.append((loss.detach().clone(), model.last_prompt_idx.clone(),
+                     [None if p.grad is None else p.grad.detach().clone() for p in model.prompt_params_list]))
+    (l0, idx0, g0), (l1, idx1, g1), (l2, idx2, g2) = runs
+    print(f"[train B=32] losses {l0.item():.7f} {l1.item():.7f} {l2.item():.7f}")
+    assert torch.equal(idx0, idx1) and torch.equal(idx0, idx2)
+    assert abs(l0.item() - l1.item()) <= 1e-5 * abs(l0.item())
+    chosen = set(int(i) for i in idx0)
+    for i in range(n_prompts):
+        if i in chosen:
+            assert torch.isfinite(g0[i]).all() and g0[i].abs().sum() > 0
+            assert torch.equal(g0[i], g1[i]), f"prompt {i}: max diff {(g0[i] - g1[i]).abs().max().item():.3e}"
+            assert torch.equal(g2[i], 2.0 * g0[i]), f"prompt {i}: max diff {(g2[i] - 2 * g0[i]).abs().max().item():.3e}"
+        else:
+            assert g0[i] is None and g1[i] is None
+    print(f"[train B=32] loss={l0.item():.6f} prompts drawn: {sorted(chosen)}")

@@ -137,3 +137,34 @@ def test_no_prompt_tile_body_matches_reference_pipeline(dev):
     fast = NoPromptPredictor(model, ours, crop, query_half_only=True).predict_tiles(
         torch.from_numpy(tiles).to(dev), torch.from_numpy(nodata).to(dev), ppx, pm).cpu().numpy()
     assert np.array_equal(fast, got)  # the decoder's prompt half is never read by the post-processing
+
+
+@pytest.mark.gpu
+def test_no_prompt_full_size_batch_properties(dev):
+    """BASELINE config 5 at full size: 16 tiles of 1024x1024 x 2 prompts (32 model samples, 24-layer backbone) in one
+    launch.  Size-independent properties: every tile's class map is bit-identical to running that tile alone (the
+    ensemble couples only the prompts of one tile), nodata pixels are 0, classes stay in range."""
+    from beach_seg_b200.ml_util import load_model
+    from beach_seg_b200.predict import NoPromptPredictor
+    from beach_seg_b200.processor import load_processor
+
+    n, P, crop = 16, 2, 1024
+    model = load_model("random-init:0", device=dev)
+    proc = load_processor(device=dev)
+    rng = np.random.default_rng(9)
+    to_u8 = lambda t: (t.permute(0, 2, 3, 1) * 255).to(torch.uint8)
+    tiles = to_u8(torch.nn.functional.interpolate(synth.smooth_image(n, 80), size=(crop, crop), mode="bilinear")).to(dev)
+    nodata = torch.from_numpy(rng.random((n, crop, crop)) < 0.03).to(dev)
+    prompts = to_u8(torch.nn.functional.interpolate(synth.smooth_image(P, 81), size=(crop, crop))).numpy()
+    pmasks = [np.ascontiguousarray(np.kron(synth.blocky_mask(P, 82)[i, :256, :256].numpy(), np.ones((4, 4), np.uint8)))
+              for i in range(P)]
+    pin = [proc.preprocess(prompt_images=[prompts[i]], prompt_masks=[pmasks[i]], num_labels=3) for i in range(P)]
+    ppx1 = torch.concat([p["prompt_pixel_values"] for p in pin])
+    pm1 = torch.concat([p["prompt_masks"] for p in pin])
+    pred = NoPromptPredictor(model, proc, crop)
+    got = pred.predict_tiles(tiles, nodata, ppx1.repeat(n, 1, 1, 1), pm1.repeat(n, 1, 1, 1))
+    assert got.shape == (n, crop, crop) and got.dtype == torch.uint8
+    assert int(got.max()) <= 3 and not got[nodata].any()
+    for i in (0, 7, 15):
+        one = pred.predict_tiles(tiles[i:i + 1], nodata[i:i + 1], ppx1, pm1)
+        assert torch.equal(one[0], got[i])
