@@ -80,6 +80,9 @@ SIGNATURES = {
     "bseg_colorize_norm": (_i, [_vp, _vp, _i, _f3, _f3, _vp, _i, _i, _i, _vp]),
     "bseg_decode_palette": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bseg_mean_over_prompts": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
+    "bseg_train_aug_fwd": (_i, [_vp, _vp, _vp, C.POINTER(C.c_int32), _vp, _f, _f, _f3, _f3, _vp, _vp, _vp, _i, _i, _i,
+                                _vp]),
+    "bseg_train_aug_bwd": (_i, [_vp, _vp, C.POINTER(C.c_int32), _f3, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "bseg_vote_accumulate": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
     "bseg_vote_argmax": (_i, [_vp, _vp, _ll, _vp]),
     "bseg_paste_tiles_u8": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),

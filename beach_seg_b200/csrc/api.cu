@@ -905,6 +905,28 @@ int bseg_mean_over_prompts(const float* pred, float* out, int n_tiles, int promp
   return launch_mean_over_group(pred, out, n_tiles, prompts, elems_per_sample, static_cast<cudaStream_t>(stream));
 }
 
+int bseg_train_aug_fwd(const float* image, const uint8_t* mask, const float* params, const int32_t* order4,
+                       const float* noise, float noise_mean, float noise_std, const float* mean, const float* stdv,
+                       float* out_image, uint8_t* out_mask, float* colour_out, int batch, int H, int W, void* stream) {
+  BSEG_REQUIRE(batch >= 0 && H > 0 && W > 0, "train_aug_fwd: bad shape %d x %d x %d", batch, H, W);
+  BSEG_REQUIRE(image && params && order4 && mean && stdv && out_image && colour_out, "train_aug_fwd: null argument");
+  BSEG_REQUIRE((mask == nullptr) == (out_mask == nullptr), "train_aug_fwd: mask and out_mask go together");
+  if (batch == 0) return 0;
+  return launch_train_aug_fwd(image, mask, params, order4, noise, noise_mean, noise_std, mean, stdv, out_image,
+                              out_mask, colour_out, batch, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_train_aug_bwd(const float* image, const float* params, const int32_t* order4, const float* stdv,
+                       const float* colour_out, const float* d_out, float* scratch, float* d_image, int batch, int H,
+                       int W, void* stream) {
+  BSEG_REQUIRE(batch >= 0 && H > 0 && W > 0, "train_aug_bwd: bad shape %d x %d x %d", batch, H, W);
+  BSEG_REQUIRE(image && params && order4 && stdv && colour_out && d_out && scratch && d_image,
+               "train_aug_bwd: null argument");
+  if (batch == 0) return 0;
+  return launch_train_aug_bwd(image, params, order4, stdv, colour_out, d_out, scratch, d_image, batch, H, W,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int bseg_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
                          const int32_t* boxes, int use_atomics, void* stream) {
   BSEG_REQUIRE(n_tiles >= 0 && crop >= 0, "vote_accumulate: bad arguments");

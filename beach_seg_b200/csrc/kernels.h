@@ -105,6 +105,13 @@ int launch_ingest_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws,
                       int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
                       const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
                       long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
+// augment.cu : kornia train augmentations (src/data.py:195-224) forward + gradient w.r.t. the image
+int launch_train_aug_fwd(const float* image, const uint8_t* mask, const float* params, const int* order, const float* noise,
+                         float noise_mean, float noise_std, const float* mean, const float* stdv, float* out_image,
+                         uint8_t* out_mask, float* colour, int B, int H, int W, cudaStream_t stream);
+int launch_train_aug_bwd(const float* image, const float* params, const int* order, const float* stdv,
+                         const float* colour, const float* d_out, float* scratch, float* d_image, int B, int H, int W,
+                         cudaStream_t stream);
 // precise.cu : the fp32 accuracy mode (bseg_forward_f32).  Pointers into the handle's own fp32 copy of the weights.
 struct F32Layer {
   const float *ln1_w, *ln1_b, *qkv_w, *qkv_b, *rel_pos_h, *rel_pos_w, *proj_w, *proj_b, *ln2_w, *ln2_b, *lin1_w, *lin1_b,

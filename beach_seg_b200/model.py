@@ -13,6 +13,7 @@ from typing import Any, Optional
 import torch
 
 from . import ops
+from .augment import InferenceAug, TrainAug  # noqa: F401  (re-exported: the datamodule pipelines, src/data.py:195-234)
 from .config import BeachSegConfig
 from .ml_util import load_model
 from .predict import create_palette as _create_palette
@@ -70,21 +71,6 @@ def allreduce_prompt_grads(params, group=None) -> None:
     used = (buf[:, per] > 0).tolist()
     for i, p in enumerate(params):
         p.grad = (buf[i, :per] / world).reshape(p.shape).clone() if used[i] else None
-
-
-class InferenceAug:
-    """Stand-in for the reference datamodule's `aug` pipeline (src/data.py:226-234): CenterCrop(inpt_size) is the
-    identity on inpt_size inputs, Normalize(mean, std) is applied to the image entry; masks pass through."""
-
-    def __call__(self, batch: dict) -> dict:
-        out = dict(batch)
-        mean = torch.tensor(ops.IMAGE_MEAN, dtype=torch.float32, device=batch["image"].device).view(1, 3, 1, 1)
-        std = torch.tensor(ops.IMAGE_STD, dtype=torch.float32, device=batch["image"].device).view(1, 3, 1, 1)
-        out["image"] = (batch["image"] - mean) / std
-        return out
-
-    def __len__(self):
-        return 2
 
 
 class PromptModel(torch.nn.Module):

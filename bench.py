@@ -207,6 +207,43 @@ def train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrie
                    "share": pms[i] / tot if tot else None,
                    "tflops": pw[i] / (pms[i] * 1e-3) / 1e12 if pw[i] and pms[i] else None}
             for i, name in enumerate(CATS) if pl[i]}
+    # ---- the same step with the datamodule's train_aug (kornia chain of src/data.py:195-224) in
+    # the prompt -> loss autograd chain, and the augmentation kernels timed alone at the same batch ----
+    from beach_seg_b200.augment import TrainAug
+
+    aug = TrainAug(conf, generator=torch.Generator().manual_seed(conf.seed + rank))
+    pmodel.train_aug = aug
+    step()
+    ms_aug_step = timed(step, args.train_steps) / args.train_steps
+    pmodel.train_aug = pmodel.aug
+    img = prompt_img01[torch.arange(TRAIN_BATCH) % TRAIN_PROMPTS].to(dev).requires_grad_(True)
+    msk = prompt_cls[torch.arange(TRAIN_BATCH) % TRAIN_PROMPTS].to(dev)
+    busy = BeachSegConfig(sharpness_p=1.0, erasing_p=1.0, gauss_p=1.0)    # every optional op on every sample
+    aug_busy = TrainAug(busy, generator=torch.Generator().manual_seed(1))
+    draw = aug_busy.sample_params(TRAIN_BATCH, 448, 448)
+    noise = torch.randn(img.shape, device=dev)
+    d_out = torch.randn(img.shape, device=dev)
+    outs = {}
+
+    def aug_fwd():
+        outs["o"], _ = aug_busy.apply(img, msk, draw, noise=noise)
+
+    def aug_bwd():
+        torch.autograd.grad(outs["o"], img, d_out, retain_graph=True)
+
+    aug_fwd(); aug_bwd()
+    reps = 20
+    ms_aug_fwd = timed(aug_fwd, reps) / reps
+    ms_aug_bwd = timed(aug_bwd, reps) / reps
+    px = TRAIN_BATCH * 448 * 448
+    train_aug = {"ms_per_iter_with_train_aug": ms_aug_step, "batch": TRAIN_BATCH,
+                 "fwd_ms": ms_aug_fwd, "bwd_ms": ms_aug_bwd,
+                 "fwd_gbs": px * 62 / (ms_aug_fwd * 1e-3) / 1e9, "bwd_gbs": px * 96 / (ms_aug_bwd * 1e-3) / 1e9,
+                 "bytes_per_px": {"fwd": 62, "bwd": 96},
+                 "note": "fwd/bwd timed through TrainAug.apply / autograd (parameter packing + 2 launches each) with "
+                         "sharpen, erase and noise forced on for every sample; bytes = image, colour scratch, noise, "
+                         "mask and output traffic of the two passes; frac of HBM peak = gbs / roofline peak of the "
+                         "bandwidth kernels"}
     ms_iter = ms / args.train_steps
     tflops = TRAIN_BATCH * TRAIN_FLOP_PER_TILE / (ms_iter * 1e-3) / 1e12
     return {"metric": "train step ms/iter", "ms_per_iter": ms_iter, "batch_per_gpu": TRAIN_BATCH, "n_gpus": world,
@@ -216,7 +253,8 @@ def train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrie
             "includes": "ingest 512->448, colourise, forward (activations kept), palette decode, loss fwd+bwd, "
                         "backward to the prompts, prompt-grad all-reduce (NCCL, world>1), AdamW step",
             "model_tflops_per_gpu": tflops, "model_frac_of_tensor_peak": tflops / peaks["tensor"],
-            "grad_allreduce_bytes": TRAIN_PROMPTS * (3 * 448 * 448 + 1) * 4 if world > 1 else 0, "kernels": kern}
+            "grad_allreduce_bytes": TRAIN_PROMPTS * (3 * 448 * 448 + 1) * 4 if world > 1 else 0, "kernels": kern,
+            "train_aug": train_aug}
 
 
 # ------------------------------------------------------------------------------------------------------------

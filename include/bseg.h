@@ -193,6 +193,26 @@ int bseg_decode_palette(const float* pred, const float* palette_norm, int num_cl
 int bseg_mean_over_prompts(const float* pred, float* out, int n_tiles, int prompts, long long elems_per_sample,
                            void* stream);
 
+/* The datamodule's `train_aug` (src/data.py:195-224: kornia RandomVerticalFlip, RandomHorizontalFlip, ColorJiggle,
+ * RandomSharpness, RandomErasing, RandomGaussianNoise, Normalize), applied to the prompt stack inside the autograd
+ * chain (src/model.py:203-207) and to the training batch (src/data.py:295-313).  SURVEY section 8(f) rank 2.
+ * Every random quantity is an input: params fp32 [B,16] per sample =
+ *   {vflip, hflip, brightness_factor-1, contrast_factor, saturation_factor, hue (radians), sharp_on, sharp_factor,
+ *    erase_on, erase_x, erase_y, erase_w, erase_h, erase_value, noise_on, 0};
+ * order4: HOST int32[4], the permutation of (0 brightness, 1 contrast, 2 saturation, 3 hue) ColorJiggle drew;
+ * noise: fp32 [B,3,H,W] standard normal (may be NULL when no sample has noise_on).
+ * image fp32 [B,3,H,W] in [0,1]; mask uint8 [B,H,W] or NULL (flipped, zeroed inside the erase box);
+ * out_image fp32 [B,3,H,W]; out_mask uint8 [B,H,W] or NULL; colour_out fp32 [B,3,H,W]: the image after the colour
+ * ops, which bseg_train_aug_bwd needs again (caller-owned, keep it until the backward ran). */
+int bseg_train_aug_fwd(const float* image, const uint8_t* mask, const float* params, const int32_t* order4,
+                       const float* noise, float noise_mean, float noise_std, const float* mean, const float* stdv,
+                       float* out_image, uint8_t* out_mask, float* colour_out, int batch, int H, int W, void* stream);
+/* d(out_image)/d(image)^T applied to d_out: torch autograd through the kornia chain in the reference.
+ * scratch: fp32 [2,B,3,H,W]; d_image fp32 [B,3,H,W] (every element written). */
+int bseg_train_aug_bwd(const float* image, const float* params, const int32_t* order4, const float* stdv,
+                       const float* colour_out, const float* d_out, float* scratch, float* d_image, int batch, int H,
+                       int W, void* stream);
+
 /* Accumulator.update (src/predict.py:120-159; src/predict_no_prompt.py:163-186).  counter: uint32 [Hs,Ws]
  * == uint8 [Hs,Ws,4] votes;  cls: uint8 [n_tiles,crop,crop];  boxes: int32 [n_tiles,4].
  * use_atomics must be 1 when tiles of one call may overlap. */

@@ -1,0 +1,34 @@
+// TEST INFRASTRUCTURE ONLY.  Runs the per-pixel functions of beach_seg_b200/csrc/augment_math.cuh -- the very code the
+// CUDA kernels of augment.cu call -- in plain loops on the CPU, so that `-m "not gpu"` tests can check the logic
+// (dual-number Jacobians, HSV round trips, blur transpose, flips) against oracle/aug_ref.py without a GPU.
+// Nothing under beach_seg_b200/ loads this; it is built by tests/test_aug_host_emul.py with g++.
+#include "../../beach_seg_b200/csrc/augment_math.cuh"
+
+using namespace bseg::aug;
+
+extern "C" int emul_train_aug_fwd(const float* image, const uint8_t* mask, const float* params, const int32_t* order4,
+                                  const float* noise, float noise_mean, float noise_std, const float* mean,
+                                  const float* stdv, float* out_image, uint8_t* out_mask, float* colour, int B, int H,
+                                  int W) {
+  if (!valid_order(order4)) return -1000;
+  const Order4 ord = {order4[0], order4[1], order4[2], order4[3]};
+  const float m[3] = {mean[0], mean[1], mean[2]}, s[3] = {stdv[0], stdv[1], stdv[2]};
+  const long long px = (long long)B * H * W;
+  for (long long i = 0; i < px; ++i) color_fwd_px(image, mask, params, ord, colour, out_mask, i, H, W);
+  for (long long i = 0; i < px * 3; ++i) finish_fwd_el(colour, params, noise, noise_mean, noise_std, m, s, out_image, i, H, W);
+  return 0;
+}
+
+extern "C" int emul_train_aug_bwd(const float* image, const float* params, const int32_t* order4, const float* stdv,
+                                  const float* colour, const float* d_out, float* scratch, float* d_image, int B, int H,
+                                  int W) {
+  if (!valid_order(order4)) return -1000;
+  const Order4 ord = {order4[0], order4[1], order4[2], order4[3]};
+  const float s[3] = {stdv[0], stdv[1], stdv[2]};
+  const long long px = (long long)B * H * W;
+  float* gd = scratch;
+  float* gq = scratch + px * 3;
+  for (long long i = 0; i < px * 3; ++i) finish_bwd_el(colour, params, d_out, s, gd, gq, i, H, W);
+  for (long long i = 0; i < px; ++i) color_bwd_px(image, params, ord, gd, gq, d_image, i, H, W);
+  return 0;
+}
