@@ -909,6 +909,7 @@ int bseg_train_aug_fwd(const float* image, const uint8_t* mask, const float* par
                        const float* noise, float noise_mean, float noise_std, const float* mean, const float* stdv,
                        float* out_image, uint8_t* out_mask, float* colour_out, int batch, int H, int W, void* stream) {
   BSEG_REQUIRE(batch >= 0 && H > 0 && W > 0, "train_aug_fwd: bad shape %d x %d x %d", batch, H, W);
+  if (batch == 0) return 0;
   BSEG_REQUIRE(image && params && order4 && mean && stdv && out_image && colour_out, "train_aug_fwd: null argument");
   BSEG_REQUIRE((mask == nullptr) == (out_mask == nullptr), "train_aug_fwd: mask and out_mask go together");
   if (batch == 0) return 0;
@@ -920,6 +921,7 @@ int bseg_train_aug_bwd(const float* image, const float* params, const int32_t* o
                        const float* colour_out, const float* d_out, float* scratch, float* d_image, int batch, int H,
                        int W, void* stream) {
   BSEG_REQUIRE(batch >= 0 && H > 0 && W > 0, "train_aug_bwd: bad shape %d x %d x %d", batch, H, W);
+  if (batch == 0) return 0;
   BSEG_REQUIRE(image && params && order4 && stdv && colour_out && d_out && scratch && d_image,
                "train_aug_bwd: null argument");
   if (batch == 0) return 0;

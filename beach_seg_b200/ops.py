@@ -126,11 +126,13 @@ def merge_mosaic(data: torch.Tensor, yesdata: torch.Tensor):
 
 def ingest_tiles(scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Tensor, boxes: torch.Tensor,
                  crop: int, want_nchw: bool = True, want_u8: bool = False, want_nodata: bool = False,
-                 out_patch: Optional[torch.Tensor] = None, patch_tile_stride: int = 0):
+                 out_patch: Optional[torch.Tensor] = None, patch_tile_stride: int = 0, normalize: bool = True):
     """tif_image + crop_tif + PIL BICUBIC resize to 448 + /255 + Normalize for a batch of tile boxes
     (src/util/geo_util.py:454-468,297-341; src/data.py:93-124,226-229).
     boxes: int32 [n,4] (xmin,ymin,xmax,ymax) on the device.  Returns dict with the requested outputs:
-    image float32 [n,3,448,448], u8 uint8 [n,crop,crop,3], nodata uint8 [n,crop,crop]."""
+    image float32 [n,3,448,448], u8 uint8 [n,crop,crop,3], nodata uint8 [n,crop,crop].
+    normalize=False stops after `/255` (the dataset item of src/data.py:93-96, before any augmentation pipeline): the
+    input of `augment.TrainAug` for the training batch (src/data.py:295-313), which ends with Normalize itself."""
     _need_cuda(scene_u16, nodata, stats, boxes)
     scene_u16, is_f32 = _scene_kind(scene_u16)
     dev = scene_u16.device
@@ -147,7 +149,8 @@ def ingest_tiles(scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Ten
         fn = _lib.lib().bseg_ingest_f32x4 if is_f32 else _lib.lib().bseg_ingest_u16x4
         _lib.check(fn(
             _lib.ptr(scene_u16), _lib.ptr(nd), Hs, Ws, _lib.ptr(stats), _lib.ptr(boxes_i),
-            n, crop, _lib.ptr(coef), _lib.ptr(bounds), ksize, _lib.f3(IMAGE_MEAN), _lib.f3(IMAGE_STD),
+            n, crop, _lib.ptr(coef), _lib.ptr(bounds), ksize, _lib.f3(IMAGE_MEAN if normalize else (0.0, 0.0, 0.0)),
+            _lib.f3(IMAGE_STD if normalize else (1.0, 1.0, 1.0)),
             _lib.ptr(out["image"]), _lib.ptr(out_patch), patch_tile_stride, _lib.ptr(out["u8"]),
             _lib.ptr(out["nodata"]), _lib.stream_ptr()), "bseg_ingest_u16x4")
     return out

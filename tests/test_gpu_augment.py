@@ -82,13 +82,13 @@ def test_prompt_gradient_flows_through_train_aug():
     """The reference's chain prompt parameter -> stack -> train_aug -> SegGPT -> pred_masks (src/model.py:194-207,
     245-251): the gradient reaching the prompt parameters through bseg_train_aug_bwd equals the gradient w.r.t. the
     augmented prompt (same CUDA model backward, leaf tensor) pushed through torch autograd of the oracle chain for the
-    same parameter draw.  Small 3-layer backbone."""
+    same parameter draw.  Small 5-layer backbone."""
     from beach_seg_b200 import synth
     from beach_seg_b200.model import PromptModel
     from beach_seg_b200.seggpt import SegGptB200
     from oracle.seggpt_ref import make_reference_model
 
-    hf = make_reference_model(seed=0, stress=True, num_layers=3, merge_index=1, intermediate=(0, 1, 2, 2))
+    hf = make_reference_model(seed=0, stress=True, num_layers=5, merge_index=1, intermediate=(1, 2, 3, 4))
     backbone = SegGptB200.from_hf(hf, device=DEV)
     conf = busy_conf(gauss_p=0.0)  # the noise field is drawn on the device inside TrainAug.apply
     pm = PromptModel(conf, device=DEV, model=backbone)
@@ -127,3 +127,38 @@ def test_prompt_gradient_flows_through_train_aug():
     g_ref = torch.autograd.grad(ref_aug, params_cpu, leaf.grad.cpu())
     for i in range(2):
         compare_grad(g_dev[i], g_ref[i], f"prompt {i}")
+
+
+def test_ingest_raw_output_feeds_the_training_batch_augmentation():
+    """The training-batch path of the reference (src/data.py:93-96 dataset item in [0,1] -> train_aug in
+    on_after_batch_transfer, src/data.py:295-313): `ingest_tiles(normalize=False)` stops after /255, and
+    Normalize((x)) of it is the normalised ingest output bit for bit."""
+    import numpy as np
+
+    from beach_seg_b200 import ops, synth
+
+    crop, Hs, Ws = 512, 700, 900
+    scene = synth.scene_u16(Hs, Ws, seed=3)
+    nodata = synth.nodata_wedge(Hs, Ws)
+    sc = torch.from_numpy(scene.view(np.int16)).to(DEV)
+    nd = torch.from_numpy(nodata).to(DEV)
+    stats = ops.scene_stats(sc, nd)
+    boxes = torch.tensor([[0, 0, crop, crop], [300, 150, 300 + crop, 150 + crop]], dtype=torch.int32, device=DEV)
+    raw = ops.ingest_tiles(sc, nd, stats, boxes, crop, normalize=False)["image"]
+    norm = ops.ingest_tiles(sc, nd, stats, boxes, crop)["image"]
+    q = raw * 255
+    assert raw.min() >= 0 and raw.max() <= 1 and torch.equal(q.round() / 255, raw)   # u8 / 255 exactly
+    mean = torch.tensor(ops.IMAGE_MEAN, device=DEV).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGE_STD, device=DEV).view(1, 3, 1, 1)
+    assert torch.equal((raw - mean) / std, norm)
+    # the reference's default pipeline on this batch: finite, mask moved with the image
+    from beach_seg_b200.config import BeachSegConfig
+
+    aug = augment.TrainAug(BeachSegConfig(), generator=torch.Generator().manual_seed(0))
+    labels = synth.blocky_mask(2, seed=9).to(DEV)
+    out = aug({"image": raw, "mask": labels})
+    d = aug.last_params
+    ref, ref_mask = aug_ref.train_aug(raw.cpu(), labels.cpu(), to_ref_params(d, torch.zeros(raw.shape), BeachSegConfig())) \
+        if not bool(d["noise_apply"].any()) else (None, None)
+    if ref is not None:
+        assert (out["image"].cpu() - ref).abs().max().item() < 2e-5 and torch.equal(out["mask"].cpu(), ref_mask)
