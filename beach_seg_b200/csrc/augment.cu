@@ -25,40 +25,67 @@ struct F3 {
   float v[3];
 };
 
-__global__ void aug_color_fwd_kernel(const float* __restrict__ image, const uint8_t* __restrict__ mask,
-                                     const float* __restrict__ params, Order4 order, float* __restrict__ colour,
-                                     uint8_t* __restrict__ out_mask, int B, int H, int W) {
-  const long long total = (long long)B * H * W;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x)
-    color_fwd_px(image, mask, params, order, colour, out_mask, idx, H, W);
+// Grids: x covers the H*W pixels of one plane (one element per thread, 32-bit index arithmetic), y = sample (pixel
+// kernels) or sample*3 + channel (element kernels), so the parameter row is uniform per block.
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+aug_color_fwd_kernel(const float* __restrict__ image, const uint8_t* __restrict__ mask, const float* __restrict__ params,
+                     Order4 order, float* __restrict__ colour, uint8_t* __restrict__ out_mask, int H, int W) {
+  const int HW = H * W;
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= HW) return;
+  const long long b = blockIdx.y;
+  color_fwd_px(image + b * 3 * HW, mask ? mask + b * HW : nullptr, params + b * kAugParams, order, colour + b * 3 * HW,
+               mask ? out_mask + b * HW : nullptr, p, H, W);
 }
 
-__global__ void aug_finish_fwd_kernel(const float* __restrict__ colour, const float* __restrict__ params,
-                                      const float* __restrict__ noise, float noise_mean, float noise_std, F3 mean,
-                                      F3 stdv, float* __restrict__ out, int B, int H, int W) {
-  const long long total = (long long)B * 3 * H * W;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x)
-    finish_fwd_el(colour, params, noise, noise_mean, noise_std, mean.v, stdv.v, out, idx, H, W);
+__global__ void __launch_bounds__(kThreads)
+aug_finish_fwd_kernel(const float* __restrict__ colour, const float* __restrict__ params, const float* __restrict__ noise,
+                      float noise_mean, float noise_std, F3 mean, F3 stdv, float* __restrict__ out, int H, int W) {
+  const int HW = H * W;
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= HW) return;
+  const long long bc = blockIdx.y;
+  const int b = blockIdx.y / 3, ch = blockIdx.y - b * 3;
+  finish_fwd_el(colour + bc * HW, params + (long long)b * kAugParams, noise ? noise + bc * HW : nullptr, noise_mean,
+                noise_std, mean.v[ch], stdv.v[ch], out + bc * HW, p, H, W);
 }
 
-__global__ void aug_finish_bwd_kernel(const float* __restrict__ colour, const float* __restrict__ params,
-                                      const float* __restrict__ d_out, F3 stdv, float* __restrict__ gd,
-                                      float* __restrict__ gq, int B, int H, int W) {
-  const long long total = (long long)B * 3 * H * W;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x)
-    finish_bwd_el(colour, params, d_out, stdv.v, gd, gq, idx, H, W);
+__global__ void __launch_bounds__(kThreads)
+aug_finish_bwd_kernel(const float* __restrict__ colour, const float* __restrict__ params, const float* __restrict__ d_out,
+                      F3 inv_std, float* __restrict__ gd, float* __restrict__ gq, int H, int W) {
+  const int HW = H * W;
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= HW) return;
+  const long long bc = blockIdx.y;
+  const int b = blockIdx.y / 3, ch = blockIdx.y - b * 3;
+  finish_bwd_el(colour + bc * HW, params + (long long)b * kAugParams, d_out + bc * HW, inv_std.v[ch], gd + bc * HW,
+                gq + bc * HW, p, H, W);
 }
 
-__global__ void aug_color_bwd_kernel(const float* __restrict__ image, const float* __restrict__ params, Order4 order,
-                                     const float* __restrict__ gd, const float* __restrict__ gq,
-                                     float* __restrict__ d_image, int B, int H, int W) {
-  const long long total = (long long)B * H * W;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x)
-    color_bwd_px(image, params, order, gd, gq, d_image, idx, H, W);
+__global__ void __launch_bounds__(kThreads)
+aug_color_bwd_kernel(const float* __restrict__ image, const float* __restrict__ params, Order4 order,
+                     const float* __restrict__ gd, const float* __restrict__ gq, float* __restrict__ d_image, int H,
+                     int W) {
+  const int HW = H * W;
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= HW) return;
+  const long long b = blockIdx.y;
+  color_bwd_px(image + b * 3 * HW, params + b * kAugParams, order, gd + b * 3 * HW, gq + b * 3 * HW,
+               d_image + b * 3 * HW, p, H, W);
+}
+
+int check_shape(const int* order, int B, int H, int W) {
+  if (!valid_order(order)) {
+    set_error("train_aug: order must be a permutation of 0..3");
+    return -1000;
+  }
+  if ((long long)H * W >= (1LL << 30) || (long long)B * 3 > 65535) {
+    set_error("train_aug: plane of %d x %d pixels or batch %d too large for one launch", H, W, B);
+    return -1000;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -66,23 +93,21 @@ __global__ void aug_color_bwd_kernel(const float* __restrict__ image, const floa
 int launch_train_aug_fwd(const float* image, const uint8_t* mask, const float* params, const int* order, const float* noise,
                          float noise_mean, float noise_std, const float* mean, const float* stdv, float* out_image,
                          uint8_t* out_mask, float* colour, int B, int H, int W, cudaStream_t stream) {
-  if (!valid_order(order)) {
-    set_error("train_aug: order must be a permutation of 0..3");
-    return -1000;
-  }
+  if (int rc = check_shape(order, B, H, W)) return rc;
   const long long px = (long long)B * H * W;
+  const unsigned gx = static_cast<unsigned>((H * W + kThreads - 1) / kThreads);
   const Order4 ord = {order[0], order[1], order[2], order[3]};
   const F3 m = {{mean[0], mean[1], mean[2]}}, s = {{stdv[0], stdv[1], stdv[2]}};
   {
     ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(px) * 26, stream);
-    aug_color_fwd_kernel<<<blocks_for_px(px), 256, 0, stream>>>(image, mask, params, ord, colour, out_mask, B, H, W);
+    aug_color_fwd_kernel<<<dim3(gx, B), kThreads, 0, stream>>>(image, mask, params, ord, colour, out_mask, H, W);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
   {
     ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(px) * 36, stream);
-    aug_finish_fwd_kernel<<<blocks_for_px(px * 3), 256, 0, stream>>>(colour, params, noise, noise_mean, noise_std, m, s,
-                                                                    out_image, B, H, W);
+    aug_finish_fwd_kernel<<<dim3(gx, B * 3), kThreads, 0, stream>>>(colour, params, noise, noise_mean, noise_std, m, s,
+                                                                   out_image, H, W);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -92,24 +117,22 @@ int launch_train_aug_fwd(const float* image, const uint8_t* mask, const float* p
 int launch_train_aug_bwd(const float* image, const float* params, const int* order, const float* stdv,
                          const float* colour, const float* d_out, float* scratch, float* d_image, int B, int H, int W,
                          cudaStream_t stream) {
-  if (!valid_order(order)) {
-    set_error("train_aug: order must be a permutation of 0..3");
-    return -1000;
-  }
+  if (int rc = check_shape(order, B, H, W)) return rc;
   const long long px = (long long)B * H * W;
+  const unsigned gx = static_cast<unsigned>((H * W + kThreads - 1) / kThreads);
   const Order4 ord = {order[0], order[1], order[2], order[3]};
-  const F3 s = {{stdv[0], stdv[1], stdv[2]}};
+  const F3 s = {{1.0f / stdv[0], 1.0f / stdv[1], 1.0f / stdv[2]}};
   float* gd = scratch;
   float* gq = scratch + px * 3;
   {
     ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(px) * 48, stream);
-    aug_finish_bwd_kernel<<<blocks_for_px(px * 3), 256, 0, stream>>>(colour, params, d_out, s, gd, gq, B, H, W);
+    aug_finish_bwd_kernel<<<dim3(gx, B * 3), kThreads, 0, stream>>>(colour, params, d_out, s, gd, gq, H, W);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
   {
     ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(px) * 48, stream);
-    aug_color_bwd_kernel<<<blocks_for_px(px), 256, 0, stream>>>(image, params, ord, gd, gq, d_image, B, H, W);
+    aug_color_bwd_kernel<<<dim3(gx, B), kThreads, 0, stream>>>(image, params, ord, gd, gq, d_image, H, W);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }

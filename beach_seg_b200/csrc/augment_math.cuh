@@ -18,12 +18,14 @@
 #define F_MUL(a, b) __fmul_rn((a), (b))
 #define F_DIV(a, b) __fdiv_rn((a), (b))
 #define LDG(p) __ldg(p)
+#define F_RCP(a) __frcp_rn(a)  // tangents only: values keep IEEE division
 #else
 #define F_ADD(a, b) ((a) + (b))
 #define F_SUB(a, b) ((a) - (b))
 #define F_MUL(a, b) ((a) * (b))
 #define F_DIV(a, b) ((a) / (b))
 #define LDG(p) (*(p))
+#define F_RCP(a) (1.0f / (a))
 #endif
 
 namespace bseg {
@@ -37,12 +39,6 @@ enum : int {
   P_VFLIP = 0, P_HFLIP, P_BRIGHT /*additive: factor-1*/, P_CONTRAST, P_SATURATION, P_HUE_RAD, P_SHARP_ON, P_SHARP_F,
   P_ERASE_ON, P_ERASE_X, P_ERASE_Y, P_ERASE_W, P_ERASE_H, P_ERASE_VALUE, P_NOISE_ON, P_RESERVED
 };
-
-static inline int blocks_for_px(long long n) {
-  long long b = (n + 255) / 256;
-  const long long cap = 148LL * 16;
-  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
-}
 
 // ---- forward-mode dual numbers: value + N tangents.  N = 0 is the plain forward pass. ----
 template <int N>
@@ -63,7 +59,7 @@ template <int N> BSEG_HD Dual<N> mul(const Dual<N>& a, const Dual<N>& b) {
 }
 template <int N> BSEG_HD Dual<N> div(const Dual<N>& a, const Dual<N>& b) {
   Dual<N> r; r.v = F_DIV(a.v, b.v);
-  const float inv = 1.f / b.v;
+  const float inv = F_RCP(b.v);
   DUAL_FOR r.d[i_] = (a.d[i_] - r.v * b.d[i_]) * inv;
   return r;
 }
@@ -76,7 +72,7 @@ template <int N> BSEG_HD Dual<N> mulc(const Dual<N>& a, float c) {
   Dual<N> r; r.v = F_MUL(a.v, c); DUAL_FOR r.d[i_] = a.d[i_] * c; return r;
 }
 template <int N> BSEG_HD Dual<N> divc(const Dual<N>& a, float c) {
-  Dual<N> r; r.v = F_DIV(a.v, c); DUAL_FOR r.d[i_] = a.d[i_] / c; return r;
+  Dual<N> r; r.v = F_DIV(a.v, c); const float ic = 1.0f / c; DUAL_FOR r.d[i_] = a.d[i_] * ic; return r;
 }
 // torch.clamp(x, 0, 1): the gradient passes where 0 <= x <= 1
 template <int N> BSEG_HD Dual<N> clamp01(const Dual<N>& a) {
@@ -88,9 +84,18 @@ template <int N> BSEG_HD Dual<N> clamp01(const Dual<N>& a) {
 template <int N> BSEG_HD Dual<N> sel(bool c, const Dual<N>& a, const Dual<N>& b) {
   Dual<N> r; r.v = c ? a.v : b.v; DUAL_FOR r.d[i_] = c ? a.d[i_] : b.d[i_]; return r;
 }
+// fmodf(x, m) for m > 0.  |x| < 2m covers every call of the chain (hues within a turn of [0, 2 pi), sector indices
+// below 12); there the result is x or x -+ m, and that single subtraction is exact (Sterbenz: m <= |x| < 2m), so this
+// equals fmodf bit for bit without libdevice's division loop.
+BSEG_HD float fmod_pos(float x, float m) {
+  const float ax = fabsf(x);
+  if (ax < m) return x;
+  if (ax < 2.f * m) return x < 0.f ? x + m : x - m;
+  return fmodf(x, m);
+}
 // python / torch `%` for a positive modulus (sign of the result follows the divisor); derivative 1
 BSEG_HD float pymodf(float x, float m) {
-  float r = fmodf(x, m);
+  float r = fmod_pos(x, m);
   if (r != 0.f && r < 0.f) r = F_ADD(r, m);
   return r;
 }
@@ -161,7 +166,7 @@ BSEG_HD void color_chain(Dual<N> (&c)[3], const float* prm, Order4 order) {
         s = clamp01(mulc(s, sat));
       } else {
         h = addc(h, hue);
-        h.v = fmodf(h.v, kTwoPi);  // torch.fmod: the sign follows the dividend
+        h.v = fmod_pos(h.v, kTwoPi);  // torch.fmod: the sign follows the dividend
       }
       hsv_to_rgb(h, s, v, c);
     }
@@ -183,13 +188,13 @@ struct SharpEval {
 };
 BSEG_HD SharpEval sharp_eval(const float* plane, int y, int x, int H, int W) {
   SharpEval e;
-  e.T = plane[(long long)y * W + x];
+  e.T = plane[y * W + x];
   e.interior = y > 0 && y < H - 1 && x > 0 && x < W - 1;
   e.conv = 0.f;
   e.D = e.T;
   if (e.interior) {
     const float w1 = 1.0f / 13.0f, w5 = 5.0f / 13.0f;
-    const float* r0 = plane + (long long)(y - 1) * W + x;
+    const float* r0 = plane + (y - 1) * W + x;
     const float* r1 = r0 + W;
     const float* r2 = r1 + W;
     float a = w1 * r0[-1];
@@ -207,43 +212,35 @@ BSEG_HD SharpEval sharp_eval(const float* plane, int y, int x, int H, int W) {
   return e;
 }
 
+// All per-pixel functions below take pointers already offset to sample b (three planes of H*W for images, one for
+// masks), that sample's parameter row `prm`, and the pixel index p = y*W + x inside a plane (H*W < 2^31).
+
 // ---- forward, pass 1 (one pixel, three channels): flips + colour; the mask is flipped and zeroed in the erase box ----
-BSEG_HD void color_fwd_px(const float* image, const uint8_t* mask, const float* params, Order4 order, float* colour,
-                          uint8_t* out_mask, long long idx, int H, int W) {
-  const long long HW = (long long)H * W;
-  const int b = static_cast<int>(idx / HW);
-  const int p = static_cast<int>(idx - (long long)b * HW);
+BSEG_HD void color_fwd_px(const float* image, const uint8_t* mask, const float* prm, Order4 order, float* colour,
+                          uint8_t* out_mask, int p, int H, int W) {
+  const int HW = H * W;
   const int y = p / W, x = p - y * W;
-  const float* prm = params + (long long)b * kAugParams;
   const int ys = LDG(prm + P_VFLIP) != 0.f ? H - 1 - y : y;
   const int xs = LDG(prm + P_HFLIP) != 0.f ? W - 1 - x : x;
-  const float* src = image + (long long)b * 3 * HW + (long long)ys * W + xs;
+  const float* src = image + ys * W + xs;
   Dual<0> c[3];
   c[0].v = LDG(src);
   c[1].v = LDG(src + HW);
   c[2].v = LDG(src + 2 * HW);
   color_chain<0>(c, prm, order);
-  float* dst = colour + (long long)b * 3 * HW + p;
-  dst[0] = c[0].v;
-  dst[HW] = c[1].v;
-  dst[2 * HW] = c[2].v;
-  if (mask != nullptr)
-    out_mask[idx] = in_erase_box(prm, y, x) ? uint8_t(0) : mask[(long long)b * HW + (long long)ys * W + xs];
+  colour[p] = c[0].v;
+  colour[p + HW] = c[1].v;
+  colour[p + 2 * HW] = c[2].v;
+  if (mask != nullptr) out_mask[p] = in_erase_box(prm, y, x) ? uint8_t(0) : mask[ys * W + xs];
 }
 
-// ---- forward, pass 2 (one element): sharpen + erase + noise + normalise ----
-BSEG_HD void finish_fwd_el(const float* colour, const float* params, const float* noise, float noise_mean,
-                           float noise_std, const float (&mean)[3], const float (&stdv)[3], float* out, long long idx,
-                           int H, int W) {
-  const long long HW = (long long)H * W;
-  const int bc = static_cast<int>(idx / HW);
-  const int p = static_cast<int>(idx - (long long)bc * HW);
-  const int b = bc / 3, ch = bc - b * 3;
+// ---- forward, pass 2 (one element of channel plane ch): sharpen + erase + noise + normalise ----
+BSEG_HD void finish_fwd_el(const float* colour_plane, const float* prm, const float* noise_plane, float noise_mean,
+                           float noise_std, float mean, float stdv, float* out_plane, int p, int H, int W) {
   const int y = p / W, x = p - y * W;
-  const float* prm = params + (long long)b * kAugParams;
   float v;
   if (LDG(prm + P_SHARP_ON) != 0.f) {
-    const SharpEval e = sharp_eval(colour + (long long)bc * HW, y, x, H, W);
+    const SharpEval e = sharp_eval(colour_plane, y, x, H, W);
     const float f = LDG(prm + P_SHARP_F);
     if (f == 0.f) {
       v = e.D;
@@ -254,30 +251,22 @@ BSEG_HD void finish_fwd_el(const float* colour, const float* params, const float
       if (!(f > 0.f && f < 1.f)) v = fminf(fmaxf(v, 0.f), 1.f);
     }
   } else {
-    v = colour[idx];
+    v = colour_plane[p];
   }
   if (in_erase_box(prm, y, x)) v = LDG(prm + P_ERASE_VALUE);
-  if (LDG(prm + P_NOISE_ON) != 0.f) v = F_ADD(v, F_ADD(F_MUL(LDG(noise + idx), noise_std), noise_mean));
-  const float m = ch == 0 ? mean[0] : (ch == 1 ? mean[1] : mean[2]);
-  const float s = ch == 0 ? stdv[0] : (ch == 1 ? stdv[1] : stdv[2]);
-  out[idx] = F_DIV(F_SUB(v, m), s);
+  if (LDG(prm + P_NOISE_ON) != 0.f) v = F_ADD(v, F_ADD(F_MUL(LDG(noise_plane + p), noise_std), noise_mean));
+  out_plane[p] = F_DIV(F_SUB(v, mean), stdv);
 }
 
 // ---- backward, pass 1 (one element): d_out -> the gradient that reaches `colour` directly (gd) and the gradient that
 // enters the 3x3 blur (gq; its transpose is applied by the gather in pass 2) ----
-BSEG_HD void finish_bwd_el(const float* colour, const float* params, const float* d_out, const float (&stdv)[3],
-                           float* gd, float* gq, long long idx, int H, int W) {
-  const long long HW = (long long)H * W;
-  const int bc = static_cast<int>(idx / HW);
-  const int p = static_cast<int>(idx - (long long)bc * HW);
-  const int b = bc / 3, ch = bc - b * 3;
+BSEG_HD void finish_bwd_el(const float* colour_plane, const float* prm, const float* d_out_plane, float inv_std,
+                           float* gd_plane, float* gq_plane, int p, int H, int W) {
   const int y = p / W, x = p - y * W;
-  const float* prm = params + (long long)b * kAugParams;
-  const float s = ch == 0 ? stdv[0] : (ch == 1 ? stdv[1] : stdv[2]);
-  float g = in_erase_box(prm, y, x) ? 0.f : d_out[idx] / s;
+  float g = in_erase_box(prm, y, x) ? 0.f : d_out_plane[p] * inv_std;
   float direct = g, q = 0.f;
   if (LDG(prm + P_SHARP_ON) != 0.f) {
-    const SharpEval e = sharp_eval(colour + (long long)bc * HW, y, x, H, W);
+    const SharpEval e = sharp_eval(colour_plane, y, x, H, W);
     const float f = LDG(prm + P_SHARP_F);
     float dD;
     if (f == 0.f) {
@@ -296,25 +285,22 @@ BSEG_HD void finish_bwd_el(const float* colour, const float* params, const float
     if (e.interior) q = (e.conv >= 0.f && e.conv <= 1.f) ? dD : 0.f;
     else direct += dD;  // on the border the "smoothed" image is the input itself
   }
-  gd[idx] = direct;
-  gq[idx] = q;
+  gd_plane[p] = direct;
+  gq_plane[p] = q;
 }
 
 // ---- backward, pass 2 (one pixel): blur^T gather, then J^T of the colour chain (forward-mode duals, three tangents),
 // written back through the flips ----
-BSEG_HD void color_bwd_px(const float* image, const float* params, Order4 order, const float* gd, const float* gq,
-                          float* d_image, long long idx, int H, int W) {
-  const long long HW = (long long)H * W;
-  const int b = static_cast<int>(idx / HW);
-  const int p = static_cast<int>(idx - (long long)b * HW);
+BSEG_HD void color_bwd_px(const float* image, const float* prm, Order4 order, const float* gd, const float* gq,
+                          float* d_image, int p, int H, int W) {
+  const int HW = H * W;
   const int y = p / W, x = p - y * W;
-  const float* prm = params + (long long)b * kAugParams;
   const bool sharp = LDG(prm + P_SHARP_ON) != 0.f;
   float dT[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const long long base = ((long long)b * 3 + k) * HW;
-    float acc = gd[base + p];
+    const float* gqk = gq + k * HW;
+    float acc = gd[k * HW + p];
     if (sharp) {
       const float w1 = 1.0f / 13.0f, w5 = 5.0f / 13.0f;
 #pragma unroll
@@ -325,7 +311,7 @@ BSEG_HD void color_bwd_px(const float* image, const float* params, Order4 order,
         for (int dx = -1; dx <= 1; ++dx) {
           const int xx = x + dx;
           if (xx < 0 || xx >= W) continue;
-          acc = fmaf((dy == 0 && dx == 0) ? w5 : w1, gq[base + (long long)yy * W + xx], acc);
+          acc = fmaf((dy == 0 && dx == 0) ? w5 : w1, gqk[yy * W + xx], acc);
         }
       }
     }
@@ -333,7 +319,7 @@ BSEG_HD void color_bwd_px(const float* image, const float* params, Order4 order,
   }
   const int ys = LDG(prm + P_VFLIP) != 0.f ? H - 1 - y : y;
   const int xs = LDG(prm + P_HFLIP) != 0.f ? W - 1 - x : x;
-  const long long soff = (long long)b * 3 * HW + (long long)ys * W + xs;
+  const int soff = ys * W + xs;
   Dual<3> c[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

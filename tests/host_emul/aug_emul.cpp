@@ -13,9 +13,15 @@ extern "C" int emul_train_aug_fwd(const float* image, const uint8_t* mask, const
   if (!valid_order(order4)) return -1000;
   const Order4 ord = {order4[0], order4[1], order4[2], order4[3]};
   const float m[3] = {mean[0], mean[1], mean[2]}, s[3] = {stdv[0], stdv[1], stdv[2]};
-  const long long px = (long long)B * H * W;
-  for (long long i = 0; i < px; ++i) color_fwd_px(image, mask, params, ord, colour, out_mask, i, H, W);
-  for (long long i = 0; i < px * 3; ++i) finish_fwd_el(colour, params, noise, noise_mean, noise_std, m, s, out_image, i, H, W);
+  const long long HW = (long long)H * W;
+  for (long long b = 0; b < B; ++b)
+    for (int p = 0; p < HW; ++p)
+      color_fwd_px(image + b * 3 * HW, mask ? mask + b * HW : nullptr, params + b * kAugParams, ord, colour + b * 3 * HW,
+                   mask ? out_mask + b * HW : nullptr, p, H, W);
+  for (long long bc = 0; bc < 3LL * B; ++bc)
+    for (int p = 0; p < HW; ++p)
+      finish_fwd_el(colour + bc * HW, params + (bc / 3) * kAugParams, noise ? noise + bc * HW : nullptr, noise_mean,
+                    noise_std, m[bc % 3], s[bc % 3], out_image + bc * HW, p, H, W);
   return 0;
 }
 
@@ -24,11 +30,17 @@ extern "C" int emul_train_aug_bwd(const float* image, const float* params, const
                                   int W) {
   if (!valid_order(order4)) return -1000;
   const Order4 ord = {order4[0], order4[1], order4[2], order4[3]};
-  const float s[3] = {stdv[0], stdv[1], stdv[2]};
-  const long long px = (long long)B * H * W;
+  const float s[3] = {1.0f / stdv[0], 1.0f / stdv[1], 1.0f / stdv[2]};
+  const long long HW = (long long)H * W;
   float* gd = scratch;
-  float* gq = scratch + px * 3;
-  for (long long i = 0; i < px * 3; ++i) finish_bwd_el(colour, params, d_out, s, gd, gq, i, H, W);
-  for (long long i = 0; i < px; ++i) color_bwd_px(image, params, ord, gd, gq, d_image, i, H, W);
+  float* gq = scratch + HW * 3 * B;
+  for (long long bc = 0; bc < 3LL * B; ++bc)
+    for (int p = 0; p < HW; ++p)
+      finish_bwd_el(colour + bc * HW, params + (bc / 3) * kAugParams, d_out + bc * HW, s[bc % 3], gd + bc * HW,
+                    gq + bc * HW, p, H, W);
+  for (long long b = 0; b < B; ++b)
+    for (int p = 0; p < HW; ++p)
+      color_bwd_px(image + b * 3 * HW, params + b * kAugParams, ord, gd + b * 3 * HW, gq + b * 3 * HW,
+                   d_image + b * 3 * HW, p, H, W);
   return 0;
 }

@@ -146,11 +146,13 @@ def test_ingest_raw_output_feeds_the_training_batch_augmentation():
     boxes = torch.tensor([[0, 0, crop, crop], [300, 150, 300 + crop, 150 + crop]], dtype=torch.int32, device=DEV)
     raw = ops.ingest_tiles(sc, nd, stats, boxes, crop, normalize=False)["image"]
     norm = ops.ingest_tiles(sc, nd, stats, boxes, crop)["image"]
-    q = raw * 255
-    assert raw.min() >= 0 and raw.max() <= 1 and torch.equal(q.round() / 255, raw)   # u8 / 255 exactly
-    mean = torch.tensor(ops.IMAGE_MEAN, device=DEV).view(1, 3, 1, 1)
-    std = torch.tensor(ops.IMAGE_STD, device=DEV).view(1, 3, 1, 1)
-    assert torch.equal((raw - mean) / std, norm)
+    # compared on the CPU: torch's CUDA `x / 255` multiplies by a reciprocal, the kernel (like numpy in the reference)
+    # divides
+    raw_c, norm_c = raw.cpu(), norm.cpu()
+    assert raw_c.min() >= 0 and raw_c.max() <= 1 and torch.equal((raw_c * 255).round() / 255, raw_c)   # u8 / 255 exactly
+    mean = torch.tensor(ops.IMAGE_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGE_STD).view(1, 3, 1, 1)
+    assert torch.equal((raw_c - mean) / std, norm_c)
     # the reference's default pipeline on this batch: finite, mask moved with the image
     from beach_seg_b200.config import BeachSegConfig
 
