@@ -961,6 +961,8 @@ int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uin
                           static_cast<cudaStream_t>(stream));
 }
 
+int bseg_gemm_set_cta_pairs(int on) { return gemm_set_cta_pairs(on); }
+
 int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int N, int K, const float* bias,
                    void* out, long long ldc, int out_is_bf16, int gelu, void* stream) {
   GemmEpiParams ep;

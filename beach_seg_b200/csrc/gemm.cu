@@ -2,7 +2,72 @@
 #include "host_utils.h"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace bseg {
+
+// BSEG_GEMM_2CTA=0/1 selects the CTA-pair kernel (cta_group::2, 256-row tiles) for the N % 256 == 0 GEMMs.
+static int g_cta_pairs = -1;  // -1: not decided yet (environment, else the default)
+static bool use_cta_pairs() {
+  if (g_cta_pairs < 0) {
+    const char* e = getenv("BSEG_GEMM_2CTA");
+    g_cta_pairs = e ? (atoi(e) != 0) : 0;
+  }
+  return g_cta_pairs != 0;
+}
+int gemm_set_cta_pairs(int on) {
+  const int prev = use_cta_pairs() ? 1 : 0;
+  if (on >= 0) g_cta_pairs = on != 0;
+  return prev;
+}
+
+// The CTA-pair variant: clusters of two CTAs, each pair owns 256 x BLOCK_N output tiles.
+template <int BLOCK_N, int MODE>
+static int launch_gemm_pair_t(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, const GemmRows& gr, int N,
+                              int K, const GemmEpiParams& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, 2>;
+  CUtensorMap ta, tb;
+  int rc;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(gr.rows_per_batch),
+                        static_cast<uint64_t>(gr.nbatch)};
+    uint64_t strides[2] = {static_cast<uint64_t>(lda) * 2, static_cast<uint64_t>(gr.rows_per_batch) * lda * 2};
+    uint32_t box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
+    rc = make_tmap_bf16(&ta, A, 3, dims, strides, box);
+  }
+  if (rc) return rc;
+  const long long M = static_cast<long long>(gr.nbatch) * gr.rows;
+  rc = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K),
+                         GEMM_BLOCK_K, Cfg::kBRows);
+  if (rc) return rc;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, MODE, 2>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const long long tiles =
+      static_cast<long long>(gr.nbatch) * ((gr.rows + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M)) * (N / BLOCK_N);
+  const long long pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * (tiles < pairs ? tiles : pairs)));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfScope prof(CAT_GEMM, 2.0 * static_cast<double>(M) * N * K,
+                 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream,
+                 MODE + (K > 2048 ? 8 : 0));
+  BSEG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, gr, N, K, ep));
+  count_launch();
+  return 0;
+}
 
 template <int BLOCK_N, int MODE>
 static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, const GemmRows& gr, int N, int K,
@@ -58,6 +123,7 @@ int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv
   const bool wide = (N % 256 == 0);
 #define BSEG_GEMM_CASE(MODE_)                                                               \
   case MODE_:                                                                               \
+    if (wide && use_cta_pairs()) return launch_gemm_pair_t<256, MODE_>(A, lda, W, gr, N, K, ep, stream); \
     return wide ? launch_gemm_t<256, MODE_>(A, lda, W, gr, N, K, ep, stream)                 \
                 : launch_gemm_t<128, MODE_>(A, lda, W, gr, N, K, ep, stream);
   switch (mode) {

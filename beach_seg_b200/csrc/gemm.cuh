@@ -56,11 +56,15 @@ constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each draining half of the tile's columns
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4.. epilogue
 
-template <int BLOCK_N>
+// kCtas = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BLOCK_N tile with one M = 256 MMA; each CTA stages
+// its 128 rows of A and BLOCK_N / 2 rows of W, so a stage is 32 KB per CTA instead of 48 KB (6 stages instead of 4) and
+// every W tile is fetched from L2 once per 256 output rows instead of once per 128.
+template <int BLOCK_N, int kCtas = 1>
 struct GemmCfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = (BLOCK_N == 256 && kCtas == 1) ? 4 : 6;
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int kBRows = BLOCK_N / kCtas;  // rows of W this CTA stages
+  static constexpr int kBBytes = kBRows * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transposing tile per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiStageBytes;
@@ -266,11 +270,13 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, flo
   }
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int kCtas = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          GemmRows gr, int N, int K, GemmEpiParams ep) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, kCtas>;
+  static_assert(kCtas == 1 || kCtas == 2, "one CTA or a CTA pair");
+  constexpr int kTileM = GEMM_BLOCK_M * kCtas;  // output rows per (pair) tile
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operand tiles need 1024B alignment
@@ -287,8 +293,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
+  // launched as clusters of kCtas CTAs: rank 0 is the leader (MMA issuer, owner of the full / tmem_empty barriers)
+  const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
+  const long long tile_first = blockIdx.x / kCtas;
+  const long long tile_step = gridDim.x / kCtas;
   const int num_n_tiles = N / BLOCK_N;
-  const int tiles_per_batch = (gr.rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int tiles_per_batch = (gr.rows + kTileM - 1) / kTileM;
   const long long num_m_tiles = static_cast<long long>(gr.nbatch) * tiles_per_batch;
   const long long num_tiles = num_m_tiles * num_n_tiles;
   const int num_k_blocks = K / GEMM_BLOCK_K;
@@ -304,13 +314,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS * kCtas);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (kCtas == 2) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
@@ -318,30 +332,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
       const long long mt = tile / num_n_tiles;
       const int bidx = static_cast<int>(mt / tiles_per_batch);
-      const int m0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * GEMM_BLOCK_M;
-      const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
+      const int m0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * kTileM + cta_rank * GEMM_BLOCK_M;
+      const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N + cta_rank * Cfg::kBRows;
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0, bidx);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          if constexpr (kCtas == 2) {
+            // both CTAs' bytes are credited to the leader's barrier, which expects the pair's total
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            tma_load_3d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0, bidx);
+            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0, bidx);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && cta_rank == 0) {
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BLOCK_N;
@@ -356,10 +377,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // advance 16 bf16 = 32 B along K inside the 128B swizzle atom
             const uint64_t da = umma_desc_sw128_kmajor(a_addr + k * 32);
             const uint64_t db = umma_desc_sw128_kmajor(b_addr + k * 32);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kCtas == 2) umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == num_k_blocks - 1) umma_commit(&tmem_full[as]);
+          if constexpr (kCtas == 2) {
+            umma_commit_2sm(&empty_bar[stage]);  // frees the smem slot in both CTAs when these MMAs retire
+            if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (kb == num_k_blocks - 1) umma_commit(&tmem_full[as]);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -373,9 +400,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int col0 = ((warp - 4) >> 2) * kColsPerWarp;
     int as = 0;
     uint32_t aphase = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
       const long long mt = tile / num_n_tiles;
-      const int local0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * GEMM_BLOCK_M + q * 32;
+      const int local0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * kTileM + cta_rank * GEMM_BLOCK_M + q * 32;
       const long long row0 = (mt / tiles_per_batch) * gr.rows_per_batch + local0;  // first row of this warp
       const int nvalid = gr.row_begin + gr.rows - local0;                          // rows of this warp inside the range
       const int n0 = static_cast<int>(tile % num_n_tiles) * BLOCK_N;
@@ -453,16 +480,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (kCtas == 2) mbar_arrive_cluster(&tmem_empty[as], 0);  // the leader's barrier counts both CTAs
+        else mbar_arrive(&tmem_empty[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();  // the peer's shared memory / TMEM stay valid until both are done
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (kCtas == 2) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

@@ -14,6 +14,9 @@ int launch_gemm(int mode, const __nv_bfloat16* A, long long lda, const __nv_bflo
 int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, const GemmRows& gr, int N,
                      int K, const GemmEpiParams& ep, cudaStream_t stream);
 
+// selects the CTA-pair GEMM kernel (cta_group::2) for N % 256 == 0; on < 0 only queries.  Returns the previous setting.
+int gemm_set_cta_pairs(int on);
+
 // attention.cu : fused softmax(q k^T * scale + decomposed rel-pos bias) v, one CTA per (seq, head, 128-query tile)
 //   q, k : [nseq, heads, T, 64] bf16     vt : [nseq, heads, 64, T] bf16
 //   relcat : [176, 64] bf16 = reversed rel_pos_h (111 rows, padded to 112) ; reversed rel_pos_w (55 rows, padded to 64)

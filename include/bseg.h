@@ -243,6 +243,12 @@ int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uin
 
 /* ---- building blocks, exported for unit tests and the benchmark's roofline legs ---- */
 
+/* GEMM kernel variant: 1 = CTA pairs (clusters of two CTAs, tcgen05.mma.cta_group::2, 256 x 256 output tiles, W tiles
+ * fetched once per pair) for every GEMM with N % 256 == 0; 0 = one CTA per 128 x 256 tile.  Both accumulate in the same
+ * order, so results are bit-identical.  on < 0 only queries.  Returns the previous setting (initial value: environment
+ * BSEG_GEMM_2CTA, else the library default). */
+int bseg_gemm_set_cta_pairs(int on);
+
 /* D = A[M,K] * W[N,K]^T (+bias); A, W bf16; out fp32 (out_is_bf16 == 0) or bf16; gelu applies to bf16 output. */
 int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int N, int K, const float* bias,
                    void* out, long long ldc, int out_is_bf16, int gelu, void* stream);

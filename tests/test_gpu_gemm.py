@@ -73,3 +73,39 @@ def test_gemm_argument_errors(dev):
     rc = _lib.lib().bseg_gemm_bf16(_lib.ptr(A), 100, _lib.ptr(W), 128, 128, 100, None, _lib.ptr(out), 128, 0, 0,
                                    _lib.stream_ptr())
     assert rc != 0 and b"multiple of 64" in _lib.lib().bseg_last_error()
+
+
+@pytest.fixture
+def cta_pairs():
+    """Runs the body with the CTA-pair GEMM kernel (tcgen05.mma.cta_group::2) selected, then restores the setting."""
+    L = _lib.lib()
+    prev = L.bseg_gemm_set_cta_pairs(1)
+    yield
+    L.bseg_gemm_set_cta_pairs(prev)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (128, 256, 64), (300, 256, 128), (1568, 1024, 1024),
+                                   (4096 + 17, 3072, 768), (1568 * 3, 1024, 4096), (37 * 256, 4096, 1024)])
+def test_gemm_cta_pairs_bit_identical(dev, M, N, K):
+    """The CTA-pair kernel accumulates every output in the same order as the one-CTA kernel (same K blocking, fp32
+    TMEM accumulators), so the two must agree bit for bit -- including ragged M (TMA zero fill, guarded stores in the
+    second CTA of the last pair) -- and both must match the fp32 matmul."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn((M, K), generator=g).to(dev).to(torch.bfloat16)
+    W = torch.randn((N, K), generator=g).to(dev).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g).to(dev)
+    L = _lib.lib()
+    prev = L.bseg_gemm_set_cta_pairs(0)
+    try:
+        one = run_gemm(A, W, bias)
+        one_bf = run_gemm(A, W, bias, out_bf16=True, gelu=True)
+        L.bseg_gemm_set_cta_pairs(1)
+        two = run_gemm(A, W, bias)
+        two_bf = run_gemm(A, W, bias, out_bf16=True, gelu=True)
+    finally:
+        L.bseg_gemm_set_cta_pairs(prev)
+    want = A.float() @ W.float().t() + bias
+    e, s = report(two, want, f"gemm pairs {M}x{N}x{K}")
+    assert e <= 2e-3 * s
+    assert torch.equal(one, two)
+    assert torch.equal(one_bf, two_bf)
