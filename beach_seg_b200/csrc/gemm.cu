@@ -48,9 +48,7 @@ static int launch_gemm_pair_t(const __nv_bfloat16* A, long long lda, const __nv_
   }
   const long long tiles =
       static_cast<long long>(gr.nbatch) * ((gr.rows + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M)) * (N / BLOCK_N);
-  const long long pairs = num_sms() / 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(2 * (tiles < pairs ? tiles : pairs)));
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
@@ -61,6 +59,17 @@ static int launch_gemm_pair_t(const __nv_bfloat16* A, long long lda, const __nv_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // persistent kernel: launch exactly as many pairs as can be co-resident (normally one per TPC = SMs / 2)
+  static int max_pairs = 0;  // per template instantiation
+  if (max_pairs == 0) {
+    cfg.gridDim = dim3(static_cast<unsigned>(num_sms() & ~1));
+    int n = 0;
+    BSEG_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    BSEG_REQUIRE(n > 0, "gemm: no CTA pair of %d B shared memory can be resident", Cfg::kSmemBytes);
+    max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+  }
+  const long long pairs = max_pairs;
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * (tiles < pairs ? tiles : pairs)));
   ProfScope prof(CAT_GEMM, 2.0 * static_cast<double>(M) * N * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream,
                  MODE + (K > 2048 ? 8 : 0));
