@@ -215,3 +215,31 @@ def test_full_scene_sliding_window_sharded_equals_single(dev):
         cover[max(y0, 0):min(y1, Hs), max(x0, 0):min(x1, Ws)] += 1
     assert np.array_equal(votes, cover)
     assert torch.equal(ops.vote_argmax(single), ops.vote_argmax(sharded))
+
+
+def test_forward_and_gradient_bit_identical_with_cta_pair_gemm(dev, small):
+    """Every GEMM epilogue of the forward (embedding table, QKV head split, residual, GELU, pixel shuffle) and of the
+    backward (dgrad, GELU') through the CTA-pair kernel (tcgen05.mma.cta_group::2, 256-row tiles): same accumulation
+    order as the one-CTA kernel, so pred_masks and the prompt gradient must be bit-identical."""
+    from beach_seg_b200 import _lib
+
+    hf, model = small
+    px, ppx, pm = synth.model_inputs(batch=3, seed=33)
+    L = _lib.lib()
+    prev = L.bseg_gemm_set_cta_pairs(0)
+    outs = []
+    try:
+        for pairs in (0, 1):
+            L.bseg_gemm_set_cta_pairs(pairs)
+            p = ppx.to(dev).requires_grad_(True)
+            out = model(pixel_values=px.to(dev), prompt_pixel_values=p, prompt_masks=pm.to(dev),
+                        embedding_type="instance").pred_masks
+            d = torch.zeros_like(out)
+            d[:, :, 448:] = torch.randn((3, 3, 448, 448), generator=torch.Generator().manual_seed(1)).to(dev)
+            out.backward(d)
+            torch.cuda.synchronize()
+            outs.append((out.detach().clone(), p.grad.clone()))
+    finally:
+        L.bseg_gemm_set_cta_pairs(prev)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])

@@ -78,3 +78,34 @@ def test_erase_zeroes_image_and_mask_inside_the_box_only():
         x, y, w, h = d["erase_box"][b].tolist()
         assert (out[b, :, y:y + h, x:x + w] == 0).all() and (m[b, y:y + h, x:x + w] == 0).all()
         assert int((m[b] == 0).sum()) == w * h
+
+
+def test_sample_params_follow_the_documented_distributions():
+    """Host logic of augment.TrainAug.sample_params: ranges, shapes, reproducibility, RandomErasing geometry."""
+    from beach_seg_b200.augment import TrainAug, pack_params
+    from beach_seg_b200.config import BeachSegConfig
+
+    conf = BeachSegConfig()
+    B, H, W = 4096, 448, 448
+    d = TrainAug(conf, generator=torch.Generator().manual_seed(0)).sample_params(B, H, W)
+    d2 = TrainAug(conf, generator=torch.Generator().manual_seed(0)).sample_params(B, H, W)
+    for k in d:
+        assert (d[k] == d2[k]) if isinstance(d[k], tuple) else torch.equal(d[k], d2[k]), k
+    assert sorted(d["order"]) == [0, 1, 2, 3]
+    for key, p in (("vflip", conf.vertical_flip), ("hflip", conf.horizontal_flip), ("sharp_apply", conf.sharpness_p),
+                   ("erase_apply", conf.erasing_p), ("noise_apply", conf.gauss_p)):
+        assert abs(d[key].float().mean().item() - p) < 0.03, key
+    for key, c in (("brightness", conf.brightness), ("contrast", conf.contrast), ("saturation", conf.saturation)):
+        assert d[key].min() >= 1 - c and d[key].max() <= 1 + c and abs(d[key].mean().item() - 1) < 0.01
+    assert d["hue"].min() >= -conf.hue and d["hue"].max() <= conf.hue
+    assert d["sharp_factor"].min() >= 0 and d["sharp_factor"].max() <= conf.sharpness
+    x, y, w, h = d["erase_box"].unbind(1)
+    assert (w >= 1).all() and (h >= 1).all() and (x >= 0).all() and (y >= 0).all()
+    assert (x + w <= W).all() and (y + h <= H).all()
+    frac = (w * h).float() / (H * W)
+    assert frac.min() > 0.8 * conf.erasing_scale[0] and frac.max() < 1.2 * conf.erasing_scale[1]
+    ratio = h.float() / w.float()
+    assert ratio.min() > 0.25 and ratio.max() < 3.6
+    P = pack_params(B, **{k: v for k, v in d.items() if k != "order"})
+    assert P.shape == (B, 16) and P.dtype == torch.float32
+    assert torch.equal(P[:, 2], d["brightness"] - 1) and torch.equal(P[:, 5], d["hue"] * 2 * math.pi)
