@@ -433,6 +433,16 @@ def main():
         roofline["traffic_algorithmic_bytes"] = t["per_launch_avg_algorithmic_bytes"]
         roofline["traffic_source"] = t["source"] + " (4 encoder-layer GEMM launches, M=200704)"
 
+    # ---- A/B of the two GEMM kernel variants on the same device-resident step (results are bit-identical) ----
+    gemm_variants = {"default": "cta_pairs" if L.bseg_gemm_set_cta_pairs(-1) else "one_cta"}
+    cur = L.bseg_gemm_set_cta_pairs(-1)
+    for vname, v in (("one_cta", 0), ("cta_pairs", 1)):
+        L.bseg_gemm_set_cta_pairs(v)
+        step_device()
+        ms_v = timed(step_device, args.steps)
+        gemm_variants[vname + "_tiles_per_s"] = world * TILES_PER_STEP * args.steps / (ms_v * 1e-3)
+    L.bseg_gemm_set_cta_pairs(cur)
+
     # ---- the other kernels against their own bounds (same profiled pass; per-step times) ----
     other = {}
     if "attention" in kernels and clocks and clocks.get("sm_mhz"):
@@ -539,7 +549,7 @@ def main():
                     "d2h_bytes_per_step": int(cls_host.numel()), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other_kernels": other,
             "cpu_baseline": cpu_baseline,
-            "kernels": kernels, "gemm_modes": gemm_modes, "train": train, "fp32_mode": fp32_mode,
+            "kernels": kernels, "gemm_modes": gemm_modes, "gemm_variants": gemm_variants, "train": train, "fp32_mode": fp32_mode,
             "query_half_fast_path": fast,
             "model_tflops": value / world * FWD_FLOP_PER_TILE / 1e12,
             "model_frac_of_tensor_peak": value / world * FWD_FLOP_PER_TILE / 1e12 / peaks["tensor"],
