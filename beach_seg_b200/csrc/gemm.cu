@@ -120,8 +120,15 @@ int launch_gemm(int mode, const __nv_bfloat16* A, long long lda, const __nv_bflo
   return launch_gemm_rows(mode, A, lda, W, gr, N, K, ep, stream);
 }
 
-int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, const GemmRows& gr, int N,
-                     int K, const GemmEpiParams& ep, cudaStream_t stream) {
+int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, const GemmRows& gr_in,
+                     int N, int K, const GemmEpiParams& ep, cudaStream_t stream) {
+  GemmRows gr = gr_in;
+  // a range that covers every batch entry completely is one contiguous block of rows: no per-entry tile padding
+  // (1568 rows = 12.25 tiles of 128) and 256-row pair tiles fit (B * 1568 is a multiple of 256 for even B)
+  if (gr.nbatch > 1 && gr.row_begin == 0 && gr.rows == gr.rows_per_batch &&
+      gr.rows_per_batch * gr.nbatch < (1ll << 31)) {
+    gr = GemmRows{gr.rows_per_batch * gr.nbatch, 1, 0, static_cast<int>(gr.rows_per_batch * gr.nbatch)};
+  }
   BSEG_REQUIRE(gr.rows > 0 && gr.nbatch > 0 && N > 0 && K > 0, "gemm: empty problem rows=%d N=%d K=%d", gr.rows, N, K);
   BSEG_REQUIRE(gr.row_begin >= 0 && gr.row_begin + gr.rows <= gr.rows_per_batch, "gemm: row range outside the batch");
   BSEG_REQUIRE(K % GEMM_BLOCK_K == 0, "gemm: K=%d must be a multiple of %d", K, GEMM_BLOCK_K);
