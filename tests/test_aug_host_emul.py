@@ -85,3 +85,24 @@ def test_bad_order_is_rejected(emul):
     rc, *_ = augment._raw_fwd(emul.emul_train_aug_fwd, image, mask, params, (0, 1, 1, 3), noise, 0.0, 0.1, aug.mean,
                               aug.std, ())
     assert rc != 0
+
+
+def test_emulated_kernel_code_reproduces_the_committed_vector(emul):
+    import numpy as np
+
+    from tests.test_oracle_aug import _load_golden
+
+    z, t, p = _load_golden()
+    B = z["image"].shape[0]
+    params = augment.pack_params(B, vflip=p.vflip, hflip=p.hflip, brightness=p.brightness, contrast=p.contrast,
+                                 saturation=p.saturation, hue=p.hue, sharp_apply=p.sharp_apply,
+                                 sharp_factor=p.sharp_factor, erase_apply=p.erase_apply, erase_box=p.erase_box,
+                                 noise_apply=p.noise_apply)
+    rc, out, out_mask, colour = augment._raw_fwd(emul.emul_train_aug_fwd, t("image"), t("mask"), params, p.order,
+                                                 t("noise"), p.noise_mean, p.noise_std, aug_ref.IMAGE_MEAN,
+                                                 aug_ref.IMAGE_STD, ())
+    assert rc == 0 and torch.equal(out_mask, t("out_mask"))
+    assert (out - t("out")).abs().max().item() < 2e-5
+    rc, g = augment._raw_bwd(emul.emul_train_aug_bwd, t("image"), params, p.order, aug_ref.IMAGE_STD, colour, t("d_out"), ())
+    assert rc == 0
+    compare_grad(g, t("grad"), "golden")

@@ -164,3 +164,25 @@ def test_ingest_raw_output_feeds_the_training_batch_augmentation():
         if not bool(d["noise_apply"].any()) else (None, None)
     if ref is not None:
         assert (out["image"].cpu() - ref).abs().max().item() < 2e-5 and torch.equal(out["mask"].cpu(), ref_mask)
+
+
+def test_train_aug_reproduces_the_committed_vector():
+    """CUDA path vs tests/golden/aug_golden.npz (the restatement's output for a stored parameter draw)."""
+    from tests.test_oracle_aug import _load_golden
+
+    z, t, p = _load_golden()
+    d = {"vflip": p.vflip, "hflip": p.hflip, "brightness": p.brightness, "contrast": p.contrast,
+         "saturation": p.saturation, "hue": p.hue, "order": p.order, "sharp_apply": p.sharp_apply,
+         "sharp_factor": p.sharp_factor, "erase_apply": p.erase_apply, "erase_box": p.erase_box,
+         "noise_apply": p.noise_apply}
+    from beach_seg_b200.config import BeachSegConfig
+
+    conf = BeachSegConfig(gauss_mean=p.noise_mean, gauss_std=p.noise_std)
+    aug = augment.TrainAug(conf)
+    img = t("image").to(DEV).requires_grad_(True)
+    out, out_mask = aug.apply(img, t("mask").to(DEV), d, noise=t("noise").to(DEV))
+    out.backward(t("d_out").to(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(out_mask.cpu(), t("out_mask"))
+    assert (out.detach().cpu() - t("out")).abs().max().item() < 2e-5
+    compare_grad(img.grad.cpu(), t("grad"), "golden")

@@ -109,3 +109,28 @@ def test_sample_params_follow_the_documented_distributions():
     P = pack_params(B, **{k: v for k, v in d.items() if k != "order"})
     assert P.shape == (B, 16) and P.dtype == torch.float32
     assert torch.equal(P[:, 2], d["brightness"] - 1) and torch.equal(P[:, 5], d["hue"] * 2 * math.pi)
+
+
+def _load_golden():
+    import numpy as np
+    from pathlib import Path
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / "aug_golden.npz")
+    t = lambda k: torch.from_numpy(z[k])
+    p = aug_ref.AugParams(
+        vflip=t("vflip"), hflip=t("hflip"), brightness=t("brightness"), contrast=t("contrast"),
+        saturation=t("saturation"), hue=t("hue"), order=tuple(int(v) for v in z["order"]), sharp_apply=t("sharp_apply"),
+        sharp_factor=t("sharp_factor"), erase_apply=t("erase_apply"), erase_box=t("erase_box"), erase_value=0.0,
+        noise_apply=t("noise_apply"), noise=t("noise"), noise_mean=float(z["noise_mean"]), noise_std=float(z["noise_std"]))
+    return z, t, p
+
+
+def test_restatement_reproduces_the_committed_vector():
+    """tests/golden/aug_golden.npz (oracle/make_golden_aug.py): the restatement's own output for a stored parameter
+    draw -- a regression pin, NOT a kornia pin (kornia is not available here)."""
+    z, t, p = _load_golden()
+    img = t("image").clone().requires_grad_(True)
+    out, out_mask = aug_ref.train_aug(img, t("mask"), p)
+    (grad,) = torch.autograd.grad(out, img, t("d_out"))
+    assert torch.allclose(out.detach(), t("out"), atol=1e-6) and torch.equal(out_mask, t("out_mask"))
+    assert torch.allclose(grad, t("grad"), atol=1e-5)
