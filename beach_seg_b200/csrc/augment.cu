@@ -65,6 +65,34 @@ aug_finish_bwd_kernel(const float* __restrict__ colour, const float* __restrict_
 }
 
 __global__ void __launch_bounds__(kThreads)
+aug_finish_fwd_quad_kernel(const float* __restrict__ colour, const float* __restrict__ params,
+                           const float* __restrict__ noise, float noise_mean, float noise_std, F3 mean, F3 stdv,
+                           float* __restrict__ out, int H, int W) {
+  const int HW = H * W;
+  const int quad = blockIdx.x * kThreads + threadIdx.x;
+  if (quad >= (HW >> 2)) return;
+  const long long bc = blockIdx.y;
+  const int b = blockIdx.y / 3, ch = blockIdx.y - b * 3;
+  finish_fwd_quad(colour + bc * HW, params + (long long)b * kAugParams, noise ? noise + bc * HW : nullptr, noise_mean,
+                  noise_std, mean.v[ch], stdv.v[ch], out + bc * HW, quad, H, W);
+}
+
+__global__ void __launch_bounds__(kThreads)
+aug_finish_bwd_quad_kernel(const float* __restrict__ colour, const float* __restrict__ params,
+                           const float* __restrict__ d_out, F3 inv_std, float* __restrict__ gd, float* __restrict__ gq,
+                           int H, int W) {
+  const int HW = H * W;
+  const int quad = blockIdx.x * kThreads + threadIdx.x;
+  if (quad >= (HW >> 2)) return;
+  const long long bc = blockIdx.y;
+  const int b = blockIdx.y / 3, ch = blockIdx.y - b * 3;
+  finish_bwd_quad(colour + bc * HW, params + (long long)b * kAugParams, d_out + bc * HW, inv_std.v[ch], gd + bc * HW,
+                  gq + bc * HW, quad, H, W);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+__global__ void __launch_bounds__(kThreads)
 aug_color_bwd_kernel(const float* __restrict__ image, const float* __restrict__ params, Order4 order,
                      const float* __restrict__ gd, const float* __restrict__ gq, float* __restrict__ d_image, int H,
                      int W) {
@@ -106,8 +134,14 @@ int launch_train_aug_fwd(const float* image, const uint8_t* mask, const float* p
   }
   {
     ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(px) * 36, stream);
-    aug_finish_fwd_kernel<<<dim3(gx, B * 3), kThreads, 0, stream>>>(colour, params, noise, noise_mean, noise_std, m, s,
-                                                                   out_image, H, W);
+    if (W % 4 == 0 && aligned16(colour) && aligned16(out_image) && aligned16(noise)) {
+      const unsigned gq4 = static_cast<unsigned>((H * W / 4 + kThreads - 1) / kThreads);
+      aug_finish_fwd_quad_kernel<<<dim3(gq4, B * 3), kThreads, 0, stream>>>(colour, params, noise, noise_mean, noise_std,
+                                                                          m, s, out_image, H, W);
+    } else {
+      aug_finish_fwd_kernel<<<dim3(gx, B * 3), kThreads, 0, stream>>>(colour, params, noise, noise_mean, noise_std, m, s,
+                                                                     out_image, H, W);
+    }
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -126,7 +160,12 @@ int launch_train_aug_bwd(const float* image, const float* params, const int* ord
   float* gq = scratch + px * 3;
   {
     ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(px) * 48, stream);
-    aug_finish_bwd_kernel<<<dim3(gx, B * 3), kThreads, 0, stream>>>(colour, params, d_out, s, gd, gq, H, W);
+    if (W % 4 == 0 && aligned16(colour) && aligned16(d_out) && aligned16(gd) && aligned16(gq)) {
+      const unsigned gq4 = static_cast<unsigned>((H * W / 4 + kThreads - 1) / kThreads);
+      aug_finish_bwd_quad_kernel<<<dim3(gq4, B * 3), kThreads, 0, stream>>>(colour, params, d_out, s, gd, gq, H, W);
+    } else {
+      aug_finish_bwd_kernel<<<dim3(gx, B * 3), kThreads, 0, stream>>>(colour, params, d_out, s, gd, gq, H, W);
+    }
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }

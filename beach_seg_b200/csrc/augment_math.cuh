@@ -289,6 +289,134 @@ BSEG_HD void finish_bwd_el(const float* colour_plane, const float* prm, const fl
   gq_plane[p] = q;
 }
 
+// ---- the two finish passes for FOUR consecutive pixels of a row (W % 4 == 0, 16-byte aligned planes): one 16-byte
+// access per operand, the 3 x 6 neighbourhood loaded once, index arithmetic / parameter loads / row predicates shared.
+// The per-pixel arithmetic (order of the nine FMAs included) is the scalar functions', so results are bit-identical. ----
+struct alignas(16) F4 {
+  float v[4];
+};
+BSEG_HD void load6(const float* row4, int x0, int W, float (&w)[6]) {
+  const F4 c = *reinterpret_cast<const F4*>(row4);
+  w[0] = x0 > 0 ? row4[-1] : 0.f;
+  w[1] = c.v[0]; w[2] = c.v[1]; w[3] = c.v[2]; w[4] = c.v[3];
+  w[5] = x0 + 4 < W ? row4[4] : 0.f;
+}
+BSEG_HD float conv9(const float (&a0)[6], const float (&a1)[6], const float (&a2)[6], int j) {
+  const float w1 = 1.0f / 13.0f, w5 = 5.0f / 13.0f;
+  float a = w1 * a0[j];
+  a = fmaf(w1, a0[j + 1], a);
+  a = fmaf(w1, a0[j + 2], a);
+  a = fmaf(w1, a1[j], a);
+  a = fmaf(w5, a1[j + 1], a);
+  a = fmaf(w1, a1[j + 2], a);
+  a = fmaf(w1, a2[j], a);
+  a = fmaf(w1, a2[j + 1], a);
+  a = fmaf(w1, a2[j + 2], a);
+  return a;
+}
+// neighbourhood of a quad: T, interior flags and conv for its four pixels
+struct QuadEval {
+  float T[4], conv[4];
+  bool interior[4];
+};
+BSEG_HD QuadEval quad_eval(const float* plane, int y, int x0, int H, int W, bool sharp) {
+  QuadEval e;
+  const float* row = plane + y * W + x0;
+  const bool yin = sharp && y > 0 && y < H - 1;
+  float a1[6];
+  if (yin) {
+    load6(row, x0, W, a1);
+  } else {
+    const F4 c = *reinterpret_cast<const F4*>(row);
+    a1[1] = c.v[0]; a1[2] = c.v[1]; a1[3] = c.v[2]; a1[4] = c.v[3];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    e.T[j] = a1[j + 1];
+    e.conv[j] = 0.f;
+    e.interior[j] = yin && x0 + j > 0 && x0 + j < W - 1;
+  }
+  if (yin) {
+    float a0[6], a2[6];
+    load6(row - W, x0, W, a0);
+    load6(row + W, x0, W, a2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e.conv[j] = conv9(a0, a1, a2, j);
+  }
+  return e;
+}
+
+BSEG_HD void finish_fwd_quad(const float* colour_plane, const float* prm, const float* noise_plane, float noise_mean,
+                             float noise_std, float mean, float stdv, float* out_plane, int quad, int H, int W) {
+  const int W4 = W >> 2;
+  const int y = quad / W4, x0 = (quad - y * W4) << 2;
+  const bool sharp = LDG(prm + P_SHARP_ON) != 0.f;
+  const float f = LDG(prm + P_SHARP_F);
+  const QuadEval e = quad_eval(colour_plane, y, x0, H, W, sharp);
+  F4 o;
+  F4 nz;
+  const bool noisy = LDG(prm + P_NOISE_ON) != 0.f;
+  if (noisy) nz = *reinterpret_cast<const F4*>(noise_plane + y * W + x0);
+  const float ev = LDG(prm + P_ERASE_VALUE);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v = e.T[j];
+    if (sharp) {
+      const float D = e.interior[j] ? fminf(fmaxf(e.conv[j], 0.f), 1.f) : e.T[j];
+      if (f == 0.f) {
+        v = D;
+      } else if (f != 1.f) {
+        v = F_ADD(D, F_MUL(F_SUB(e.T[j], D), f));
+        if (!(f > 0.f && f < 1.f)) v = fminf(fmaxf(v, 0.f), 1.f);
+      }
+    }
+    if (in_erase_box(prm, y, x0 + j)) v = ev;
+    if (noisy) v = F_ADD(v, F_ADD(F_MUL(nz.v[j], noise_std), noise_mean));
+    o.v[j] = F_DIV(F_SUB(v, mean), stdv);
+  }
+  *reinterpret_cast<F4*>(out_plane + y * W + x0) = o;
+}
+
+BSEG_HD void finish_bwd_quad(const float* colour_plane, const float* prm, const float* d_out_plane, float inv_std,
+                             float* gd_plane, float* gq_plane, int quad, int H, int W) {
+  const int W4 = W >> 2;
+  const int y = quad / W4, x0 = (quad - y * W4) << 2;
+  const bool sharp = LDG(prm + P_SHARP_ON) != 0.f;
+  const float f = LDG(prm + P_SHARP_F);
+  const F4 dv = *reinterpret_cast<const F4*>(d_out_plane + y * W + x0);
+  QuadEval e;
+  if (sharp) e = quad_eval(colour_plane, y, x0, H, W, true);
+  F4 od, oq;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float g = in_erase_box(prm, y, x0 + j) ? 0.f : dv.v[j] * inv_std;
+    float direct = g, q = 0.f;
+    if (sharp) {
+      const float D = e.interior[j] ? fminf(fmaxf(e.conv[j], 0.f), 1.f) : e.T[j];
+      float dD;
+      if (f == 0.f) {
+        dD = g;
+        direct = 0.f;
+      } else if (f == 1.f) {
+        dD = 0.f;
+      } else {
+        if (!(f > 0.f && f < 1.f)) {
+          const float blend = F_ADD(D, F_MUL(F_SUB(e.T[j], D), f));
+          if (!(blend >= 0.f && blend <= 1.f)) g = 0.f;
+        }
+        direct = g * f;
+        dD = g - direct;
+      }
+      if (e.interior[j]) q = (e.conv[j] >= 0.f && e.conv[j] <= 1.f) ? dD : 0.f;
+      else direct += dD;
+    }
+    od.v[j] = direct;
+    oq.v[j] = q;
+  }
+  *reinterpret_cast<F4*>(gd_plane + y * W + x0) = od;
+  *reinterpret_cast<F4*>(gq_plane + y * W + x0) = oq;
+}
+
 // ---- backward, pass 2 (one pixel): blur^T gather, then J^T of the colour chain (forward-mode duals, three tangents),
 // written back through the flips ----
 BSEG_HD void color_bwd_px(const float* image, const float* prm, Order4 order, const float* gd, const float* gq,
