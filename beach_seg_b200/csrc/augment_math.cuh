@@ -289,6 +289,20 @@ BSEG_HD void finish_bwd_el(const float* colour_plane, const float* prm, const fl
   gq_plane[p] = q;
 }
 
+// the erase box of a sample, loaded once per thread
+struct EraseBox {
+  int x0, x1;
+  bool row_in;  // the box is on and covers row y
+};
+BSEG_HD EraseBox load_erase_box(const float* prm, int y) {
+  EraseBox e;
+  e.x0 = static_cast<int>(LDG(prm + P_ERASE_X));
+  e.x1 = e.x0 + static_cast<int>(LDG(prm + P_ERASE_W));
+  const int ey = static_cast<int>(LDG(prm + P_ERASE_Y)), eh = static_cast<int>(LDG(prm + P_ERASE_H));
+  e.row_in = LDG(prm + P_ERASE_ON) != 0.f && y >= ey && y < ey + eh;
+  return e;
+}
+
 // ---- the two finish passes for FOUR consecutive pixels of a row (W % 4 == 0, 16-byte aligned planes): one 16-byte
 // access per operand, the 3 x 6 neighbourhood loaded once, index arithmetic / parameter loads / row predicates shared.
 // The per-pixel arithmetic (order of the nine FMAs included) is the scalar functions', so results are bit-identical. ----
@@ -358,6 +372,7 @@ BSEG_HD void finish_fwd_quad(const float* colour_plane, const float* prm, const 
   const bool noisy = LDG(prm + P_NOISE_ON) != 0.f;
   if (noisy) nz = *reinterpret_cast<const F4*>(noise_plane + y * W + x0);
   const float ev = LDG(prm + P_ERASE_VALUE);
+  const EraseBox box = load_erase_box(prm, y);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float v = e.T[j];
@@ -370,7 +385,7 @@ BSEG_HD void finish_fwd_quad(const float* colour_plane, const float* prm, const 
         if (!(f > 0.f && f < 1.f)) v = fminf(fmaxf(v, 0.f), 1.f);
       }
     }
-    if (in_erase_box(prm, y, x0 + j)) v = ev;
+    if (box.row_in && x0 + j >= box.x0 && x0 + j < box.x1) v = ev;
     if (noisy) v = F_ADD(v, F_ADD(F_MUL(nz.v[j], noise_std), noise_mean));
     o.v[j] = F_DIV(F_SUB(v, mean), stdv);
   }
@@ -387,9 +402,10 @@ BSEG_HD void finish_bwd_quad(const float* colour_plane, const float* prm, const 
   QuadEval e;
   if (sharp) e = quad_eval(colour_plane, y, x0, H, W, true);
   F4 od, oq;
+  const EraseBox box = load_erase_box(prm, y);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float g = in_erase_box(prm, y, x0 + j) ? 0.f : dv.v[j] * inv_std;
+    float g = (box.row_in && x0 + j >= box.x0 && x0 + j < box.x1) ? 0.f : dv.v[j] * inv_std;
     float direct = g, q = 0.f;
     if (sharp) {
       const float D = e.interior[j] ? fminf(fmaxf(e.conv[j], 0.f), 1.f) : e.T[j];
