@@ -13,8 +13,9 @@ CLASSES = ("nodata", "sand", "water", "veg")  # src/config.py:7-12
 class BeachSegConfig:
     project: str = "beach_seg"
     seed: int = 42
-    data: Path = Path("/Users/kyledorman/data/BorderField")
-    model_training_root: Path = Path("/Users/kyledorman/data/results")
+    # the reference's defaults are the author's private directories (src/config.py:19-20); neutral ones here
+    data: Path = Path("data")
+    model_training_root: Path = Path("results")
     classes: tuple = CLASSES
     devices: tuple = ("auto",)
     accelerator: str = "auto"

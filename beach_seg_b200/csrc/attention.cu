@@ -567,11 +567,10 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     int rc = make_tmap_bf16_2d(&tr, relcat, 64, kRelRows, 64, 64, kRelRows);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first()) {
     BSEG_CHECK_CUDA(
         cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
   }
   dim3 grid((kT + kCtaQ - 1) / kCtaQ, heads, nseq);
   ProfScope prof(CAT_ATTENTION, static_cast<double>(nseq) * heads * (4.0 * kT * kT * 64 + 2.0 * kT * 84 * 64),

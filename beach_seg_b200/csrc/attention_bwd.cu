@@ -742,13 +742,12 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
   }
   if ((rc = make_tmap_bf16_2d(&trel, relcat, 64, kRelRows, 64, 64, kRelRows))) return rc;
   if ((rc = make_tmap_bf16_2d(&trelt, relcat_t, 192, 64, 192, 64, 64))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first()) {
     BSEG_CHECK_CUDA(
         cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmemBytes));
     BSEG_CHECK_CUDA(
         cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKSmemBytes));
-    attr_set = true;
   }
   const double pair = static_cast<double>(nseq) * heads * kT * kT;
   {

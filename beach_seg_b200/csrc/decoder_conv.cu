@@ -313,10 +313,9 @@ int launch_decoder_conv_t(const __nv_bfloat16* x_nhwc, int rows_in, const __nv_b
     if (rc) return rc;
   }
   auto kern = decoder_conv_kernel<MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first()) {
     BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
   }
   const long long tiles = static_cast<long long>(prm.B) * (prm.H / kTileH - prm.ty_begin) * (prm.W / kTileW);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());

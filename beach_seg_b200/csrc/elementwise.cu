@@ -1,6 +1,7 @@
 // Bandwidth-bound kernels of the SegGPT tile path: LayerNorm, patchify (im2col for the stride-16 patch
 // embedding), two-stream merge, feature-ensemble mean, prompt-mask colourise, palette decode, vote
 // stitching, smooth-L1 loss.  Each kernel cites the reference lines it reproduces.
+#include "../../include/bseg.h"
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"
@@ -700,20 +701,28 @@ int launch_overlay_prediction(const uint8_t* img, const uint8_t* pred, const uin
 // masked by [0 ; yesdata], sum / keep.sum().  As written, `keep_mask.unsqueeze(1)` broadcasts to a BxB cross
 // product: loss = sum_px (sum_j l_j[px]) * (sum_i keep_i[px]) / sum(keep).  per_sample=1 gives the intended
 // sum_b l_b*keep_b / sum(keep); both are identical at B=1.  Forward and d(loss)/d(pred) in one pass.
-// scratch: [0] = keep count (float), [1] = loss numerator.
+// scratch (BSEG_LOSS_SCRATCH_FLOATS words): [0] = keep count (uint32), [1] = finished-block ticket (uint32),
+// [2 + b] = loss numerator of block b.  Deterministic: the count is an integer sum, every block reduces its numerator
+// in a fixed order and the last block to finish adds the per-block partials in block order (no float atomics), so
+// the loss scalar is bit-reproducible run to run like the gradients are.
 // ----------------------------------------------------------------------------------------------
-__global__ void keep_count_kernel(const uint8_t* __restrict__ yes, long long n, float* __restrict__ scratch) {
-  float c = 0.f;
+constexpr int kLossMaxBlocks = 2048;
+static_assert(2 + kLossMaxBlocks <= BSEG_LOSS_SCRATCH_FLOATS, "loss scratch");
+__global__ void keep_count_kernel(const uint8_t* __restrict__ yes, long long n, uint32_t* __restrict__ scratch) {
+  uint32_t c = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    c += yes[i] ? 1.f : 0.f;
-  c = warp_sum(c);
-  if ((threadIdx.x & 31) == 0 && c != 0.f) atomicAdd(&scratch[0], c);
+    c += yes[i] ? 1u : 0u;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c != 0u) atomicAdd(&scratch[0], c);
 }
-__global__ void smooth_l1_kernel(const float* __restrict__ pred, const float* __restrict__ labels,
-                                 const uint8_t* __restrict__ yes, float beta, int per_sample,
-                                 float* __restrict__ grad, float* __restrict__ scratch, int B, int HW) {
+__global__ void __launch_bounds__(256)
+smooth_l1_kernel(const float* __restrict__ pred, const float* __restrict__ labels, const uint8_t* __restrict__ yes,
+                 float beta, int per_sample, float* __restrict__ grad, uint32_t* __restrict__ scratch,
+                 float* __restrict__ loss_out, int B, int HW) {
   // one thread per (pixel, channel) of the bottom half; loops over the batch
-  const float denom = 3.0f * scratch[0];  // keep.sum(): yesdata expanded to the 3 channels
+  __shared__ float warp_part[8];
+  __shared__ bool is_last;
+  const float denom = 3.0f * static_cast<float>(scratch[0]);  // keep.sum(): yesdata expanded to the 3 channels
   const float inv = 1.0f / denom;
   const long long total = 3LL * HW;
   float acc = 0.f;
@@ -739,22 +748,37 @@ __global__ void smooth_l1_kernel(const float* __restrict__ pred, const float* __
     }
   }
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(&scratch[1], acc);
-}
-__global__ void smooth_l1_finalize_kernel(const float* __restrict__ scratch, float* __restrict__ loss) {
-  loss[0] = scratch[1] / (3.0f * scratch[0]);
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  float* partial = reinterpret_cast<float*>(scratch + 2);
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += warp_part[w];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    is_last = atomicAdd(&scratch[1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {  // the last block to finish: partials in block order, one warp
+    __threadfence();
+    float s = 0.f;
+    for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(&partial[b]);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) loss_out[0] = s / denom;
+  }
 }
 int launch_smooth_l1(const float* pred, const float* labels, const uint8_t* yesdata, float beta, int per_sample,
                      float* loss_out, float* grad_out, float* scratch, int B, int H, int W, cudaStream_t stream) {
   const int HW = H * W;
   ProfScope prof(CAT_LOSS, 0, static_cast<double>(B) * HW * (3 * 4 * 3 + 1), stream);
-  BSEG_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(float), stream));
-  keep_count_kernel<<<blocks_for((long long)B * HW, 1024), 256, 0, stream>>>(yesdata, (long long)B * HW, scratch);
-  smooth_l1_kernel<<<blocks_for(3LL * HW, 256), 256, 0, stream>>>(pred, labels, yesdata, beta, per_sample, grad_out,
-                                                                  scratch, B, HW);
-  smooth_l1_finalize_kernel<<<1, 1, 0, stream>>>(scratch, loss_out);
+  uint32_t* sc = reinterpret_cast<uint32_t*>(scratch);
+  BSEG_CHECK_CUDA(cudaMemsetAsync(sc, 0, 2 * sizeof(uint32_t), stream));
+  keep_count_kernel<<<blocks_for((long long)B * HW, 1024), 256, 0, stream>>>(yesdata, (long long)B * HW, sc);
+  smooth_l1_kernel<<<blocks_for(3LL * HW, 256, kLossMaxBlocks), 256, 0, stream>>>(pred, labels, yesdata, beta,
+                                                                                   per_sample, grad_out, sc, loss_out,
+                                                                                   B, HW);
   BSEG_CHECK_CUDA(cudaGetLastError());
-  count_launch();
+  count_launch(2);
   return 0;
 }
 

@@ -41,10 +41,9 @@ static int launch_gemm_pair_t(const __nv_bfloat16* A, long long lda, const __nv_
                          GEMM_BLOCK_K, Cfg::kBRows);
   if (rc) return rc;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, MODE, 2>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;  // per template instantiation
+  if (attr_once.first()) {
     BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   const long long tiles =
       static_cast<long long>(gr.nbatch) * ((gr.rows + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M)) * (N / BLOCK_N);
@@ -60,7 +59,8 @@ static int launch_gemm_pair_t(const __nv_bfloat16* A, long long lda, const __nv_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent kernel: launch exactly as many pairs as can be co-resident (normally one per TPC = SMs / 2)
-  static int max_pairs = 0;  // per template instantiation
+  static PerDeviceInt max_pairs_cache;  // per template instantiation and device
+  int& max_pairs = max_pairs_cache.get();
   if (max_pairs == 0) {
     cfg.gridDim = dim3(static_cast<unsigned>(num_sms() & ~1));
     int n = 0;
@@ -97,10 +97,9 @@ static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloa
                          GEMM_BLOCK_K, BLOCK_N);
   if (rc) return rc;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, MODE>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;  // per template instantiation
+  if (attr_once.first()) {
     BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   const long long tiles = static_cast<long long>(gr.nbatch) * ((gr.rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * (N / BLOCK_N);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());

@@ -129,12 +129,17 @@ void prof_collect_sub(double* ms, double* work) {
   for (int i = 0; i < 16; ++i) { ms[i] = g_sub_ms[i]; work[i] = g_sub_work[i]; }
 }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int num_sms() {
-  static int n = 0;
+  static PerDeviceInt cache;
+  int& n = cache.get();
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
     if (n <= 0) n = 148;
   }
   return n;

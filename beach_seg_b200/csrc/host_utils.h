@@ -48,7 +48,25 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner,
   return make_tmap_bf16(out, base, 2, dims, strides, box);
 }
 
-int num_sms();
+int num_sms();  // of the current device
+
+// Function attributes (opt-in dynamic shared memory), cluster occupancy and SM counts are PER DEVICE, and the Python API
+// accepts any device=: call-site caches are therefore keyed by the current device ordinal.
+constexpr int kMaxDevices = 64;
+int current_device();
+struct PerDeviceFlag {
+  bool done[kMaxDevices] = {};
+  bool first() {  // true the first time this call site runs on the current device
+    const int d = current_device();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+struct PerDeviceInt {
+  int v[kMaxDevices] = {};
+  int& get() { return v[current_device()]; }
+};
 
 // launch accounting behind bseg_launch_count()
 void count_launch(int n = 1);

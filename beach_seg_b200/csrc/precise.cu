@@ -378,11 +378,10 @@ attention_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ re
 int launch_attention_f32(const float* qkv, const float* rel_h, const float* rel_w, float* out, int nseq,
                          cudaStream_t stream) {
   const size_t smem = kAttnSmemFloats * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_once;
+  if (attr_once.first()) {
     BSEG_CHECK_CUDA(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-    attr_set = true;
   }
   dim3 grid((kT + AQ - 1) / AQ, BSEG_HEADS, nseq);
   ProfScope prof(CAT_ATTENTION, 4.0 * nseq * BSEG_HEADS * kT * static_cast<double>(kT) * 64,

@@ -50,12 +50,76 @@ class SegGptLoss(torch.nn.Module):
         return ops.smooth_l1_loss(pred_masks, labels, yesdata, self.beta, per_sample=self.per_sample)
 
 
+class PromptGradExchange:
+    """Data-parallel exchange of the prompt gradients (Lightning's implicit DDP in the reference, src/train.py:96-107)
+    without per-step packing: ONE persistent dense fp32 buffer [N_prompts, 3*H*W] whose rows ARE the `.grad` tensors of
+    the prompt parameters (autograd accumulates into them in place), ONE average all-reduce over it per step (NCCL over
+    NVLink on the GPU box, gloo in the CPU tests), and no device->host synchronisation on the gradient path: which
+    prompts any rank drew this step is known from an all-gather of the (CPU-drawn) prompt indices that is issued on a
+    side stream at the START of the step and has long finished when the backward is done.  Prompts no rank selected
+    keep `grad = None`, so AdamW skips them exactly as it does at world size 1 -- with Lightning's default DDP the
+    reference would instead fail on the unused parameters."""
+
+    def __init__(self, params, group=None):
+        import torch.distributed as dist
+
+        self.params = list(params)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        p0 = self.params[0]
+        self.per = p0.numel()
+        self.buf = torch.zeros((len(self.params), self.per), dtype=torch.float32, device=p0.device)
+        self.views = [self.buf[i].view(p.shape) for i, p in enumerate(self.params)]
+        self.side = torch.cuda.Stream(device=p0.device) if p0.is_cuda else None
+        self.event = torch.cuda.Event() if p0.is_cuda else None
+        self._gathered = None
+        self._host = None
+
+    def begin_step(self, prompt_idx: torch.Tensor) -> None:
+        """Call before the forward: zero the buffer, hang its rows on the parameters, start the index all-gather."""
+        import torch.distributed as dist
+
+        self.buf.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        idx = prompt_idx.to(torch.int64).flatten()
+        n = idx.numel()
+        if self.side is None:  # CPU (gloo) path of the tests
+            out = torch.empty(self.world * n, dtype=torch.int64)
+            dist.all_gather_into_tensor(out, idx.contiguous(), group=self.group)
+            self._host = out
+            return
+        dev = self.buf.device
+        if self._gathered is None or self._gathered.numel() != self.world * n:
+            self._gathered = torch.empty(self.world * n, dtype=torch.int64, device=dev)
+            self._host = torch.empty(self.world * n, dtype=torch.int64).pin_memory()
+        pinned = idx.pin_memory()
+        self.side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.side):
+            idx_dev = pinned.to(dev, non_blocking=True)
+            dist.all_gather_into_tensor(self._gathered, idx_dev, group=self.group)
+            self._host.copy_(self._gathered, non_blocking=True)
+            self.event.record(self.side)
+        self._keep = (pinned, idx_dev)
+
+    def finish_step(self) -> None:
+        """Call after backward(): one average all-reduce over the buffer; untouched prompts get grad = None."""
+        import torch.distributed as dist
+
+        dist.all_reduce(self.buf, op=dist.ReduceOp.AVG if self.buf.is_cuda else dist.ReduceOp.SUM, group=self.group)
+        if not self.buf.is_cuda:  # gloo has no AVG
+            self.buf.div_(self.world)
+        if self.event is not None:
+            self.event.synchronize()  # recorded before the forward was even enqueued: no stall
+        used = set(self._host.tolist())
+        for i, p in enumerate(self.params):
+            p.grad = self.views[i] if i in used else None
+
+
 def allreduce_prompt_grads(params, group=None) -> None:
-    """Mean all-reduce of the prompt gradients over the data-parallel ranks: ONE collective over a dense
-    [N_prompts, 3*H*W + 1] fp32 buffer (the last column counts the ranks that touched a prompt; 2.4 MB per prompt,
-    NCCL over NVLink on the GPU box, gloo in the CPU tests).  Prompts no rank selected this step keep `grad = None`,
-    so AdamW skips them exactly as it does at world size 1 -- with Lightning's default DDP the reference would instead
-    fail on the unused parameters."""
+    """Stateless form of the exchange for callers that did not go through `PromptGradExchange.begin_step` (one
+    collective over a dense [N_prompts, 3*H*W + 1] fp32 buffer; the last column counts the ranks that touched a prompt).
+    Costs a pack / unpack and one host sync per step; `PromptModel.sync_prompt_grads` uses the persistent exchange."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or not params:
@@ -89,6 +153,7 @@ class PromptModel(torch.nn.Module):
         self.train_aug: Any = InferenceAug()
         self.prompt_batch: dict = {}
         self.prompt_params_list = torch.nn.ParameterList()
+        self.dp_group = None  # torch.distributed group of the data-parallel ranks (None = the default group)
 
     @property
     def device(self) -> torch.device:
@@ -165,6 +230,9 @@ class PromptModel(torch.nn.Module):
         batch_palette, batch_palette_norm = self.create_palette(B, train=True)
         color_mask_norm = ops.colorize_norm(batch["mask"].to(self.device), batch_palette)
         prompt_idx = torch.randint(0, len(self.prompt_params_list), (B,), generator=self.g)
+        ex = self._exchange()
+        if ex is not None:
+            ex.begin_step(prompt_idx)
         prompt_batch, prompt_masks = self.prepare_prompt(prompt_idx, batch_palette, train=True)
         out = self.model(pixel_values=batch["image"].to(self.device), labels=color_mask_norm,
                          prompt_pixel_values=prompt_batch["image"], prompt_masks=prompt_masks,
@@ -187,8 +255,27 @@ class PromptModel(torch.nn.Module):
         return self.loss_fn(out.pred_masks, color_mask_norm, (batch["mask"] != 0).to(self.device))
 
     # ---- data-parallel exchange (Lightning's implicit DDP in the reference, src/train.py:96-107) ----
+    def _exchange(self) -> Optional[PromptGradExchange]:
+        """The persistent gradient exchange when a process group with more than one rank is up (else None)."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.dp_group) == 1 \
+                or len(self.prompt_params_list) == 0:
+            return None
+        ex = getattr(self, "_grad_exchange", None)
+        params = list(self.prompt_params_list)
+        if ex is None or len(ex.params) != len(params) or any(a is not b for a, b in zip(ex.params, params)):
+            ex = PromptGradExchange(params, self.dp_group)
+            self._grad_exchange = ex
+        return ex
+
     def sync_prompt_grads(self, group=None) -> None:
-        allreduce_prompt_grads(list(self.prompt_params_list), group)
+        """Mean of the prompt gradients over the data-parallel ranks; call between backward() and the optimiser step."""
+        ex = self._exchange() if group is None or group is self.dp_group else None
+        if ex is not None and ex._host is not None:
+            ex.finish_step()
+        else:
+            allreduce_prompt_grads(list(self.prompt_params_list), group)
 
     # ---- src/model.py:385-428 (AdamW, optional linear warm-up, cosine per epoch; plain torch, negligible cost) ----
     def configure_optimizers(self):
@@ -213,10 +300,15 @@ class PromptModel(torch.nn.Module):
 
     # ---- stand-in for Trainer.fit (src/train.py:97-115): step, backward, exchange, AdamW, cosine per epoch ----
     def fit(self, batches, epochs: Optional[int] = None, on_step=None):
+        """Default length = the reference's `Trainer(max_epochs=conf.epochs * len(prompt_batch))` (src/train.py:98;
+        `prompt_batch` is the saved dict, so `len()` is its number of KEYS), while the cosine schedule keeps
+        `T_max = conf.epochs` exactly as src/model.py:417 has it."""
         cfg = self.configure_optimizers()
         opt, sched = cfg["optimizer"], cfg["lr_scheduler"]["scheduler"]
         losses = []
-        for _ in range(self.conf.epochs if epochs is None else epochs):
+        if epochs is None:
+            epochs = self.conf.epochs * max(len(self.prompt_batch), 1)
+        for _ in range(epochs):
             for i, batch in enumerate(batches):
                 loss = self.training_step(batch, i)
                 loss.backward()

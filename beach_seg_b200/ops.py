@@ -15,6 +15,7 @@ from . import _lib
 
 IMAGE_MEAN = (0.485, 0.456, 0.406)  # SegGptImageProcessor.image_mean (HF:image_processing_seggpt.py:76)
 IMAGE_STD = (0.229, 0.224, 0.225)   # SegGptImageProcessor.image_std  (HF:image_processing_seggpt.py:77)
+LOSS_SCRATCH_FLOATS = 2052            # BSEG_LOSS_SCRATCH_FLOATS (include/bseg.h)
 
 
 def _need_cuda(*ts):
@@ -67,6 +68,19 @@ def pil_bicubic_table(in_size: int, out_size: int = 448):
 
 
 _table_cache: dict = {}
+_index_cache: dict = {}
+
+
+def _device_array(kind: str, key, device, make):
+    """Device copy of a small host array, cached per (kind, key, device): a fresh `torch.from_numpy(...).to(dev)` is a
+    blocking pageable copy that synchronises the stream on every call (and stalls the upload/compute overlap of
+    predict.HostScenePipeline)."""
+    k = (kind, key, str(device))
+    t = _index_cache.get(k)
+    if t is None:
+        t = torch.from_numpy(np.ascontiguousarray(make())).to(device)
+        _index_cache[k] = t
+    return t
 
 
 def _device_table(in_size: int, device):
@@ -195,7 +209,7 @@ def decode_palette(pred_masks: torch.Tensor, palette_norm: torch.Tensor, out_siz
     dev = pred_masks.device
     idx = None
     if out_size != H or out_size != W:
-        idx = torch.from_numpy(cv2_nearest_index(H, out_size)).to(dev)
+        idx = _device_array("cv2_nearest", (H, out_size), dev, lambda: cv2_nearest_index(H, out_size))
     o8 = torch.empty((B, out_size, out_size), dtype=torch.uint8, device=dev) if dtype == torch.uint8 else None
     o64 = torch.empty((B, out_size, out_size), dtype=torch.int64, device=dev) if dtype == torch.int64 else None
     nd = nodata.to(torch.uint8).contiguous() if nodata is not None else None
@@ -287,7 +301,7 @@ def overlay_prediction(img: torch.Tensor, pred: torch.Tensor, classes: Sequence[
     H, W, _ = img.shape
     im = img.to(torch.uint8).contiguous()
     pr = pred.to(torch.uint8).contiguous()
-    table = torch.from_numpy(class_rgba_table(classes)).to(img.device)
+    table = _device_array("class_rgba", tuple(classes), img.device, lambda: class_rgba_table(classes))
     out = torch.empty_like(im)
     with torch.cuda.device(img.device):
         _lib.check(_lib.lib().bseg_overlay_prediction(_lib.ptr(im), _lib.ptr(pr), _lib.ptr(table), len(classes),
@@ -310,7 +324,7 @@ def smooth_l1_loss(pred_masks: torch.Tensor, labels: torch.Tensor, yesdata: torc
     yes = yesdata.reshape(B, H, W).to(torch.uint8).contiguous()
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     grad = torch.empty_like(pred_masks, dtype=torch.float32) if want_grad else None
-    scratch = torch.empty(2, dtype=torch.float32, device=dev)
+    scratch = torch.empty(LOSS_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
     pred_c, lab_c = pred_masks.contiguous(), labels.to(torch.float32).contiguous()  # must outlive the launch
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().bseg_loss_smoothl1_fwd_bwd(
@@ -428,7 +442,8 @@ def colorize_resize_norm255(mask: torch.Tensor, palette_u8: torch.Tensor, out_si
     dev = mask.device
     m8 = mask.to(torch.uint8).contiguous()
     pal = palette_u8.to(device=dev, dtype=torch.uint8).contiguous()
-    idx = torch.from_numpy(torch_nearest_exact_index(H, out_size)).to(dev) if H != out_size else None
+    idx = (_device_array("nearest_exact", (H, out_size), dev, lambda: torch_nearest_exact_index(H, out_size))
+           if H != out_size else None)
     m255, s255 = _hf_mean_std_255()
     out = torch.empty((B, 3, out_size, out_size), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -448,7 +463,8 @@ def postprocess_semantic(pred_masks: torch.Tensor, palette255: torch.Tensor, out
     H = H2 // 2
     out_size = H if out_size is None else int(out_size)
     dev = pred_masks.device
-    idx = torch.from_numpy(torch_nearest_index(H, out_size)).to(dev) if (out_size != H or out_size != W) else None
+    idx = (_device_array("nearest", (H, out_size), dev, lambda: torch_nearest_index(H, out_size))
+           if (out_size != H or out_size != W) else None)
     o8 = torch.empty((B, out_size, out_size), dtype=torch.uint8, device=dev) if dtype == torch.uint8 else None
     o64 = torch.empty((B, out_size, out_size), dtype=torch.int64, device=dev) if dtype == torch.int64 else None
     nd = nodata.to(torch.uint8).contiguous() if nodata is not None else None

@@ -68,6 +68,44 @@ class TilePredictor:
         return ops.decode_palette(out.pred_masks, pal_norm, out_size=self.crop_size, dtype=torch.uint8)
 
 
+def predict_scene(predictor: "TilePredictor", scene_u16: torch.Tensor, nodata: torch.Tensor, boxes: torch.Tensor,
+                  prompt_images: torch.Tensor, prompt_masks: torch.Tensor,
+                  palette: Optional[tuple[torch.Tensor, torch.Tensor]] = None, rank: int = 0, world_size: int = 1,
+                  tiles_per_launch: int = 64, group=None, stats: Optional[torch.Tensor] = None,
+                  canvas: Optional[torch.Tensor] = None, reduce: bool = True):
+    """The tile loop of src/predict.py:232-262 over one scene, batched and sharded: rank r predicts its contiguous block
+    of the tile list (`shard_tiles`) in launches of `tiles_per_launch`, votes into its own packed-u32 canvas
+    (`Accumulator`'s uint8 (H,W,4) counters), then ONE sum-reduce of the canvases to rank 0 (byte counters cannot carry
+    below 256 votes per pixel) and `np.argmax` there (src/predict.py:100).  Tiles themselves need no communication.
+    boxes int32 [n,4] (all tiles of the scene, every rank passes the same list); prompt_images [n,3,448,448];
+    prompt_masks uint8 [n,448,448]; palette = (uint8 [n,C,3], float32 [n,C,3]) indexed by tile so that the result does
+    not depend on the sharding.  Returns (class map uint8 [Hs,Ws] on rank 0 else None, this rank's canvas after the
+    reduce)."""
+    dev = predictor.model.device
+    _, Hs, Ws = scene_u16.shape
+    n = boxes.shape[0]
+    if stats is None:
+        stats = ops.scene_stats(scene_u16, nodata)  # scene-global, once per scene (src/util/geo_util.py:459-464)
+    if canvas is None:
+        canvas = torch.zeros((Hs, Ws), dtype=torch.int32, device=dev)
+    else:
+        canvas.zero_()
+    if palette is None:
+        palette = create_palette(predictor.num_classes, n, predictor.random_palette, dev)
+    ids = shard_tiles(n, rank, world_size)
+    for s in range(ids.start, ids.stop, tiles_per_launch):
+        e = min(s + tiles_per_launch, ids.stop)
+        cls = predictor.predict_tiles(scene_u16, nodata, stats, boxes[s:e], prompt_images[s:e], prompt_masks[s:e],
+                                      (palette[0][s:e], palette[1][s:e]))
+        ops.vote_accumulate(canvas, cls, boxes[s:e], overlapping=True)
+    if world_size > 1 and reduce:
+        import torch.distributed as dist
+
+        dist.reduce(canvas, dst=0, op=dist.ReduceOp.SUM, group=group)
+    pred = ops.vote_argmax(canvas) if rank == 0 else None
+    return pred, canvas
+
+
 class HostScenePipeline:
     """Host-buffer front end of `TilePredictor` for callers that hold the scene in (pinned) host memory, like the
     reference's numpy pipeline does: every `step()` copies the uint16 scene host->device, predicts its tiles, votes
@@ -120,7 +158,7 @@ class NoPromptPredictor:
                  query_half_only: bool = False):
         self.model, self.processor, self.crop_size, self.num_classes = model, processor, crop_size, num_classes
         self.query_half_only = query_half_only  # post-processing reads pred_masks[:, :, 448:] only (HF:284-286)
-        self._pal = torch.tensor(build_palette(num_classes - 1), dtype=torch.float32)
+        self._pal = torch.tensor(build_palette(num_classes - 1), dtype=torch.float32).to(model.device)
 
     @torch.no_grad()
     def predict_tiles(self, crops_u8: torch.Tensor, nodata: Optional[torch.Tensor], prompt_pixel_values: torch.Tensor,
@@ -170,10 +208,10 @@ class Accumulator:
         self.out_transform, self.crs, self.classes = out_transform, crs, tuple(classes)
         self.device = torch.device(device)
         self.mask_dir = self.img_dir = self.tif_dir = None
-        if save_dir is not None:  # the reference's three output folders (src/predict.py:68-75)
-            self.img_dir = Path(save_dir) / "pred"
+        if save_dir is not None:  # the reference's output folders: images / masks / tif (src/predict.py:70-75)
+            self.img_dir = Path(save_dir) / "images"
             self.mask_dir = Path(save_dir) / "masks"
-            self.tif_dir = Path(save_dir) / "tifs"
+            self.tif_dir = Path(save_dir) / "tif"
             for d in (self.img_dir, self.mask_dir, self.tif_dir):
                 d.mkdir(exist_ok=True, parents=True)
         self.current_pred_counter: Optional[torch.Tensor] = None
@@ -185,8 +223,7 @@ class Accumulator:
         return self
 
     def __exit__(self, a, b, c):
-        if self.current_pred_counter is not None:
-            self.save_current()
+        self.save_current()  # like the reference (src/predict.py:90-91): asserts if nothing was accumulated
 
     def initialize_current(self, date: str):
         self.current_date = date

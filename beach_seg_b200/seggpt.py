@@ -19,6 +19,12 @@ IMG = 448
 NUM_PATCHES = 1568
 
 
+def _ops_loss_scratch() -> int:
+    from .ops import LOSS_SCRATCH_FLOATS
+
+    return LOSS_SCRATCH_FLOATS
+
+
 class SegGptOutput:
     """Mutable stand-in for HF SegGptImageSegmentationOutput (src/predict_no_prompt.py:298 assigns .pred_masks)."""
 
@@ -98,7 +104,7 @@ class SegGptB200(torch.nn.Module):
         self._train_token = 0
         self.check_grad_support = True  # verify in backward() that d(pred_masks) is zero in the prompt half
         self._train_ready = False
-        self._scratch = torch.zeros(8, dtype=torch.float32, device=self._device)
+        self._scratch = torch.zeros(_ops_loss_scratch(), dtype=torch.float32, device=self._device)
         L = _lib.lib()
         with torch.cuda.device(self._device):
             keep = []  # fp32 staging copies, freed after packing
@@ -209,13 +215,15 @@ class SegGptB200(torch.nn.Module):
         embedding_type = embedding_type if embedding_type is not None else "instance"
         if embedding_type not in ("instance", "semantic"):
             raise ValueError(f"Embedding type should be either 'semantic' or 'instance', but got {embedding_type}")
+        mask_rows = 1  # HF's default bool_masked_pos has batch dimension 1 (HF:modeling_seggpt.py:910-917)
         if bool_masked_pos is not None:
             default = torch.cat([torch.zeros(NUM_PATCHES // 2, dtype=torch.bool),
                                  torch.ones(NUM_PATCHES - NUM_PATCHES // 2, dtype=torch.bool)])
-            if not torch.equal(bool_masked_pos.reshape(-1, NUM_PATCHES).cpu().bool(),
-                               default.expand(bool_masked_pos.reshape(-1, NUM_PATCHES).shape[0], -1)):
+            rows = bool_masked_pos.reshape(-1, NUM_PATCHES)
+            if not torch.equal(rows.cpu().bool(), default.expand(rows.shape[0], -1)):
                 raise NotImplementedError("only the default bool_masked_pos (bottom half masked) is supported; the "
                                           "reference never passes another one")
+            mask_rows = rows.shape[0]
         if output_attentions or output_hidden_states:
             raise NotImplementedError("attention / hidden-state outputs are never requested on the reference path")
         want_grad = torch.is_grad_enabled() and prompt_pixel_values.requires_grad
@@ -242,7 +250,7 @@ class SegGptB200(torch.nn.Module):
                                           "(src/predict_no_prompt.py:289-295)")
             ppx_g = prompt_pixel_values.to(device=self._device, dtype=torch.float32).contiguous()
             pred = _PromptGradFn.apply(ppx_g, self, prep(pixel_values), prep(prompt_masks), embedding_type)
-            return SegGptOutput(loss=self._hf_loss(pred.detach(), labels, B), pred_masks=pred)
+            return SegGptOutput(loss=self._hf_loss(pred.detach(), labels, B, mask_rows), pred_masks=pred)
         px, ppx, pm = prep(pixel_values), prep(prompt_pixel_values), prep(prompt_masks)
         pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=self._device)
         L = _lib.lib()
@@ -262,12 +270,15 @@ class SegGptB200(torch.nn.Module):
                                _lib.ptr(pm[s:s + n]), n, 0 if embedding_type == "instance" else 1, P,
                                C.c_void_p(base), C.c_size_t(ws.numel() - (base - ws.data_ptr())),
                                _lib.ptr(pred[s:s + n]), _lib.stream_ptr()), fwd_name)
-        return SegGptOutput(loss=self._hf_loss(pred, labels, B), pred_masks=pred)
+        return SegGptOutput(loss=self._hf_loss(pred, labels, B, mask_rows), pred_masks=pred)
 
-    def _hf_loss(self, pred: torch.Tensor, labels: Optional[torch.Tensor], B: int):
-        """HF SegGptLoss (HF:modeling_seggpt.py:780-819) with the default mask == smooth-L1 over the bottom half.
-        The reference computes it and throws it away (src/model.py:245-255); kept, without a graph, for interface
-        fidelity."""
+    def _hf_loss(self, pred: torch.Tensor, labels: Optional[torch.Tensor], B: int, mask_rows: int = 1):
+        """HF SegGptLoss (HF:modeling_seggpt.py:780-819) with the default mask == smooth-L1 over the bottom half:
+        `(loss * mask).sum() / mask.sum()`.  `mask` comes from bool_masked_pos, whose DEFAULT has batch dimension 1
+        (HF:modeling_seggpt.py:910-917): the numerator then runs over all B samples while the denominator counts one
+        sample's 3*448*448 masked values, i.e. B times the per-sample mean -- reproduced here (`mask_rows` = the batch
+        dimension of bool_masked_pos).  The reference computes this value and throws it away (src/model.py:245-255);
+        kept, without a graph, for interface fidelity."""
         if labels is None:
             return None
         lab = labels.detach().to(device=self._device, dtype=torch.float32).contiguous()
@@ -277,4 +288,5 @@ class SegGptB200(torch.nn.Module):
             _lib.check(_lib.lib().bseg_loss_smoothl1_fwd_bwd(_lib.ptr(pred), _lib.ptr(lab), _lib.ptr(yes), self.beta,
                                                              1, _lib.ptr(loss_t), None, _lib.ptr(self._scratch), B,
                                                              IMG, IMG, _lib.stream_ptr()), "bseg_loss")
-        return loss_t[0]
+        # the kernel divides by B * 3*448*448 (all-ones keep mask); HF divides by mask_rows * 3*448*448
+        return loss_t[0] * (float(B) / float(mask_rows)) if mask_rows != B else loss_t[0]

@@ -191,7 +191,23 @@ def train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrie
 
     for _ in range(2):
         loss = step()
-    ms = timed(step, args.train_steps)
+    # ---- on-hardware check of the exchange: after sync_prompt_grads every rank holds bit-identical gradients ----
+    grads_identical = None
+    if world > 1:
+        import torch.distributed as dist
+
+        tiles = ops.ingest_tiles(scene, nodata, stats, tboxes, CROP)
+        pmodel.training_step({"image": tiles["image"], "mask": labels}, 0).backward()
+        pmodel.sync_prompt_grads()
+        h = torch.stack([p.grad.view(torch.int32).to(torch.int64).sum() if p.grad is not None
+                         else torch.full((), -1, dtype=torch.int64, device=dev) for p in pmodel.prompt_params_list])
+        allh = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(allh, h)
+        grads_identical = all(bool(torch.equal(a, allh[0])) for a in allh)
+        if not grads_identical:
+            raise SystemExit("train: prompt gradients differ across ranks after sync_prompt_grads")
+        opt.zero_grad(set_to_none=True)
+    ms, ms_ranks = timed(step, args.train_steps, want_ranks=True)
     # per-category device time of the same steps
     L.bseg_profile_enable(1)
     barrier()
@@ -253,8 +269,175 @@ def train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrie
             "includes": "ingest 512->448, colourise, forward (activations kept), palette decode, loss fwd+bwd, "
                         "backward to the prompts, prompt-grad all-reduce (NCCL, world>1), AdamW step",
             "model_tflops_per_gpu": tflops, "model_frac_of_tensor_peak": tflops / peaks["tensor"],
-            "grad_allreduce_bytes": TRAIN_PROMPTS * (3 * 448 * 448 + 1) * 4 if world > 1 else 0, "kernels": kern,
+            "grad_allreduce_bytes": TRAIN_PROMPTS * 3 * 448 * 448 * 4 if world > 1 else 0,
+            "grads_identical_on_all_ranks_after_sync": grads_identical,
+            "ms_per_iter_per_rank": [m / args.train_steps for m in ms_ranks], "kernels": kern,
             "train_aug": train_aug}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2]: full-scene sliding-window predict, 8000x4000 px, 512-px tiles, stride 448 (64-px overlap) = 162
+# tiles, sharded over the ranks; vote stitch + one canvas reduce + argmax.  Reference loop: src/predict.py:232-262.
+# ------------------------------------------------------------------------------------------------------------
+def scene_leg(args, dev, rank, world, model, barrier, timed):
+    from beach_seg_b200 import ops, synth
+    from beach_seg_b200.predict import TilePredictor, create_palette, predict_scene, shard_tiles
+
+    Hs, Ws, stride = 4000, 8000, 448
+    scene_np = synth.scene_u16(Hs, Ws, seed=7)                       # the same scene on every rank
+    nodata_np = synth.nodata_wedge(Hs, Ws, 0.05)
+    boxes_np = synth.sliding_boxes(Hs, Ws, CROP, stride)
+    n = len(boxes_np)
+    scene_host = torch.from_numpy(scene_np.view(np.int16)).pin_memory()
+    nodata_host = torch.from_numpy(nodata_np).pin_memory()
+    scene, nodata = scene_host.to(dev), nodata_host.to(dev)
+    boxes = torch.from_numpy(boxes_np).to(dev)
+    prompts = synth.normalize(synth.smooth_image(1, 2000)).to(dev).expand(n, -1, -1, -1)
+    pcls = synth.blocky_mask(1, 3000).to(dev).expand(n, -1, -1)
+    torch.manual_seed(42)
+    palette = create_palette(4, n, True, dev)                         # per tile, identical on every rank
+    predictor = TilePredictor(model, CROP)
+    canvas = torch.zeros((Hs, Ws), dtype=torch.int32, device=dev)
+    scene_dev = torch.empty_like(scene)
+    nodata_dev = torch.empty_like(nodata)
+    pred_host = torch.empty((Hs, Ws), dtype=torch.uint8).pin_memory()
+    out = {}
+
+    def run_device():
+        out["pred"], _ = predict_scene(predictor, scene, nodata, boxes, prompts, pcls, palette, rank, world,
+                                       TILES_PER_STEP, canvas=canvas)
+
+    def run_e2e():
+        # host scene -> device (every rank needs the scene-global statistics and its own stripe), predict the shard,
+        # reduce, argmax, class map back to the host on rank 0
+        scene_dev.copy_(scene_host, non_blocking=True)
+        nodata_dev.copy_(nodata_host, non_blocking=True)
+        pred, _ = predict_scene(predictor, scene_dev, nodata_dev, boxes, prompts, pcls, palette, rank, world,
+                                TILES_PER_STEP, canvas=canvas)
+        if pred is not None:
+            pred_host.copy_(pred, non_blocking=True)
+
+    reps = max(args.scene_reps, 1)
+    for _ in range(2):
+        run_device()
+    ms, per_rank = timed(run_device, reps, want_ranks=True)
+    run_e2e()
+    ms_e2e, _ = timed(run_e2e, reps, want_ranks=True)
+    # ---- on-hardware equality: the canvas reduced over `world` ranks == the canvas one rank stitches alone ----
+    same = None
+    run_device()
+    if world > 1:
+        reduced = canvas.clone()
+        if rank == 0:
+            single_pred, single = predict_scene(predictor, scene, nodata, boxes, prompts, pcls, palette, 0, 1,
+                                                TILES_PER_STEP)
+            same = bool(torch.equal(single, reduced)) and bool(torch.equal(single_pred, out["pred"]))
+            if not same:
+                raise SystemExit("config3: the canvas reduced over the ranks differs from the single-rank canvas")
+    votes_ok = None
+    if rank == 0:
+        votes = canvas.cpu().numpy().view(np.uint8).reshape(Hs, Ws, 4).sum(axis=2)
+        cover = np.zeros((Hs, Ws), dtype=np.int32)
+        for x0, y0, x1, y1 in boxes_np:
+            cover[max(y0, 0):min(y1, Hs), max(x0, 0):min(x1, Ws)] += 1
+        votes_ok = bool(np.array_equal(votes, cover))
+        if not votes_ok:
+            raise SystemExit("config3: vote totals differ from the tile coverage")
+    barrier()
+    per_scene, per_scene_e2e = ms / reps, ms_e2e / reps
+    return {"workload": f"{Ws}x{Hs} px uint16 4-band scene, {CROP}-px tiles, stride {stride} (64-px overlap): {n} tiles "
+                        f"sharded over {world} rank(s) (owner-computes blocks of the row-major tile list), launches of "
+                        f"<= {TILES_PER_STEP} tiles, vote stitch, one NCCL sum-reduce of the u32 canvases, argmax",
+            "tiles": n, "tiles_per_rank": len(shard_tiles(n, 0, world)), "n_gpus": world,
+            "scene_ms": per_scene, "value": n / (per_scene * 1e-3), "unit": "tiles/s",
+            "scene_ms_per_rank_min_max": [min(per_rank) / reps, max(per_rank) / reps],
+            "e2e": {"scene_ms": per_scene_e2e, "value": n / (per_scene_e2e * 1e-3), "unit": "tiles/s",
+                    "h2d_bytes_per_scene_per_rank": int(scene_host.numel() * 2 + nodata_host.numel()),
+                    "d2h_bytes_per_scene": int(pred_host.numel())},
+            "canvas_reduce_bytes": int(canvas.numel() * 4) if world > 1 else 0,
+            "canvas_equals_single_rank_canvas": same, "vote_totals_equal_tile_coverage": votes_ok, "reps": reps}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: predict_no_prompt.py path on 1024x1024 uint8 RGB crops, n_prompts = 2 with feature_ensemble
+# ("batch 16" = 8 tiles x 2 prompts per launch; 16 tiles x 2 = 32 samples also reported).  src/predict_no_prompt.py:270-306.
+# ------------------------------------------------------------------------------------------------------------
+def noprompt_leg(args, dev, rank, world, model, barrier, timed):
+    from beach_seg_b200 import ops, synth
+    from beach_seg_b200.ml_util import build_palette
+    from beach_seg_b200.predict import NoPromptPredictor
+
+    crop, P = 1024, 2
+    res = {"workload": f"predict_no_prompt: {crop}x{crop} uint8 RGB crops -> HF-processor resize to 448, {P} prompts per "
+                       "tile with feature_ensemble=True (grouped per tile), mean over prompts, semantic post-process at "
+                       "crop size, nodata zeroing, vote", "crop": crop, "prompts_per_tile": P, "n_gpus": world}
+    predictor = NoPromptPredictor(model, None, crop)
+    pal_u8 = torch.tensor(build_palette(3), dtype=torch.uint8)
+    for n in (8, 16):
+        g = torch.Generator().manual_seed(900 + rank)
+        crops_host = torch.randint(0, 256, (n, crop, crop, 3), generator=g, dtype=torch.uint8).pin_memory()
+        crops = crops_host.to(dev)
+        nodata = torch.from_numpy(synth.nodata_wedge(crop, crop, 0.05)).to(dev)[None].expand(n, -1, -1).contiguous()
+        ppx = synth.normalize(synth.smooth_image(n * P, 7000 + rank)).to(dev)
+        pmask = ops.colorize_resize_norm255(synth.blocky_mask(n * P, 7100 + rank).to(dev), pal_u8, 448)
+        boxes = torch.from_numpy(synth.tile_boxes(n, crop, crop * 4)).to(dev)
+        canvas = torch.zeros((crop * ((n + 3) // 4), crop * 4), dtype=torch.int32, device=dev)
+        crops_dev = torch.empty_like(crops)
+        cls_host = torch.empty((n, crop, crop), dtype=torch.uint8).pin_memory()
+
+        def step_device():
+            cls = predictor.predict_tiles(crops, nodata, ppx, pmask)
+            ops.vote_accumulate(canvas, cls, boxes, overlapping=False)
+
+        def step_e2e():
+            crops_dev.copy_(crops_host, non_blocking=True)
+            cls = predictor.predict_tiles(crops_dev, nodata, ppx, pmask)
+            ops.vote_accumulate(canvas, cls, boxes, overlapping=False)
+            cls_host.copy_(cls, non_blocking=True)
+
+        for _ in range(3):
+            step_device()
+        ms, _ = timed(step_device, args.steps, want_ranks=True)
+        step_e2e()
+        ms_e2e, _ = timed(step_e2e, args.steps, want_ranks=True)
+        tps = world * n * args.steps / (ms * 1e-3)
+        res[f"tiles{n}_x{P}"] = {"samples_per_launch": n * P, "ms_per_launch": ms / args.steps, "value": tps,
+                                 "unit": "tiles/s",
+                                 "e2e": {"value": world * n * args.steps / (ms_e2e * 1e-3), "unit": "tiles/s",
+                                         "h2d_bytes_per_step": int(crops_host.numel()),
+                                         "d2h_bytes_per_step": int(cls_host.numel())},
+                                 "model_tflops_per_gpu": tps / world * P * FWD_FLOP_PER_TILE / 1e12}
+        del crops, crops_dev, canvas, ppx, pmask
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+# small-batch latency: the reference's real call pattern is batch 1 (src/data.py:287-293, src/predict.py:234)
+# ------------------------------------------------------------------------------------------------------------
+def latency_leg(args, dev, model, predictor, scene, nodata, stats, boxes, prompt_images, prompt_cls, palette, timed):
+    out = {"what": "ingest + colourise + forward + decode of ONE launch of B tiles (device-resident inputs), averaged "
+                   "over back-to-back launches; floor = one pass over the 741 MB of bf16 weights per launch at the "
+                   "measured HBM rate, or the launch's FLOPs at the sustained tensor peak, whichever is larger"}
+    peaks = measured_peaks()
+    for B in (1, 4, 16):
+        args_b = (scene, nodata, stats, boxes[:B], prompt_images[:B], prompt_cls[:B], (palette[0][:B], palette[1][:B]))
+
+        def step():
+            predictor.predict_tiles(*args_b)
+
+        for _ in range(3):
+            step()
+        reps = 20
+        ms, _ = timed(step, reps, want_ranks=True)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        host_ms = (time.perf_counter() - t0) * 1e3 / reps   # host enqueue time per launch (no sync inside)
+        torch.cuda.synchronize()
+        floor = max(0.741e9 / (peaks["hbm"] * 1e9), B * FWD_FLOP_PER_TILE / (peaks["tensor"] * 1e12)) * 1e3
+        out[f"batch{B}"] = {"ms_per_launch": ms / reps, "ms_per_tile": ms / reps / B, "host_enqueue_ms": host_ms,
+                            "floor_ms_per_launch": floor, "frac_of_floor": floor / (ms / reps)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -271,6 +454,10 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg (BASELINE configs[3])")
     ap.add_argument("--train-steps", type=int, default=3)
     ap.add_argument("--no-fast-path", action="store_true", help="skip the query-half-only decoder leg")
+    ap.add_argument("--no-scene", action="store_true", help="skip the full-scene leg (BASELINE configs[2])")
+    ap.add_argument("--scene-reps", type=int, default=2)
+    ap.add_argument("--no-noprompt", action="store_true", help="skip the predict_no_prompt leg (BASELINE configs[4])")
+    ap.add_argument("--no-latency", action="store_true", help="skip the batch 1/4/16 latency leg")
     ap.add_argument("--no-fp32-check", action="store_true",
                     help="skip the fp32-accuracy-mode leg (bf16 path vs bseg_forward_f32 on the bench inputs)")
     args = ap.parse_args()
@@ -340,7 +527,9 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, want_ranks=False):
+        """Device time of `steps` calls, barrier + synchronize on both sides, MAX over ranks (and every rank's own
+        time when asked: attributes a straggler to a GPU)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -349,12 +538,15 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        ranks = [ms]
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            t = torch.zeros(world, dtype=torch.float64, device=dev)
+            t[rank] = ms
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ranks = [float(v) for v in t.tolist()]
+            ms = max(ranks)
         barrier()
-        return ms
+        return (ms, ranks) if want_ranks else ms
 
     for _ in range(args.warmup):
         step_device()
@@ -362,7 +554,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = L.bseg_launch_count()
-    ms = timed(step_device, args.steps)
+    ms, ms_ranks = timed(step_device, args.steps, want_ranks=True)
     launches = int(L.bseg_launch_count() - launches0)
     clocks = sampler.stop() if rank == 0 else None
     value = world * TILES_PER_STEP * args.steps / (ms * 1e-3)
@@ -465,6 +657,13 @@ def main():
     if not args.no_train:
         train = train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrier, timed, L, peaks)
 
+    scene3 = None if args.no_scene else scene_leg(args, dev, rank, world, model, barrier, timed)
+    noprompt5 = None if args.no_noprompt else noprompt_leg(args, dev, rank, world, model, barrier, timed)
+    latency = None
+    if not args.no_latency and world == 1:
+        latency = latency_leg(args, dev, model, predictor, scene, nodata, stats, boxes, prompt_images, prompt_cls,
+                              palette, timed)
+
     # ---- optional fast path: decoder on the query half only (bseg_forward_query_half); class maps are bit-identical
     # (checked below).  Reported beside the headline, which keeps the full forward. ----
     fast = None
@@ -552,6 +751,8 @@ def main():
             "cpu_baseline": cpu_baseline,
             "kernels": kernels, "gemm_modes": gemm_modes, "gemm_variants": gemm_variants, "train": train, "fp32_mode": fp32_mode,
             "query_half_fast_path": fast,
+            "config3_scene": scene3, "config5_no_prompt": noprompt5, "small_batch_latency": latency,
+            "ms_per_step_per_rank": [m / args.steps for m in ms_ranks],
             "model_tflops": value / world * FWD_FLOP_PER_TILE / 1e12,
             "model_frac_of_tensor_peak": value / world * FWD_FLOP_PER_TILE / 1e12 / peaks["tensor"],
         }

@@ -236,7 +236,9 @@ int bseg_overlay_prediction(const uint8_t* img, const uint8_t* pred, const uint8
 /* SegGptLoss (src/model.py:40-64), forward and gradient w.r.t. pred in one pass.
  * pred fp32 [B,3,2H,W]; labels fp32 [B,3,H,W]; yesdata uint8 [B,H,W]; per_sample: 0 = as written in the
  * reference (BxB broadcast), 1 = per-sample masking; loss_out: fp32 [1]; grad_out: fp32 [B,3,2H,W] or NULL;
- * scratch: 2 floats. */
+ * scratch: BSEG_LOSS_SCRATCH_FLOATS 32-bit words (keep count, block ticket, per-block partial sums: the reduction is
+ * two-stage in a fixed order with no float atomics, so loss_out is bit-reproducible run to run). */
+#define BSEG_LOSS_SCRATCH_FLOATS 2052
 int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uint8_t* yesdata, float beta,
                                int per_sample, float* loss_out, float* grad_out, float* scratch, int batch, int H,
                                int W, void* stream);

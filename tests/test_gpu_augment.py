@@ -13,6 +13,11 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _needs_cuda(dev):
+    """Skip (instead of failing with 'Found no NVIDIA driver') when a plain `pytest tests` runs on a host without a GPU."""
+
+
 def _gpu_vs_oracle(conf, B, H, W, seed):
     aug, d, image, mask, noise = draw(conf, B, H, W, seed)
     img_dev = image.to(DEV).requires_grad_(True)

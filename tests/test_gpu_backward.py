@@ -283,8 +283,8 @@ def test_prompt_model_training_step_matches_reference(dev, batch):
     cos = F.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
     print(f"[training_step B={batch}] prompts {chosen}: loss ref={loss_ref.item():.6f} ours={loss.item():.6f} "
           f"grad rel-L2={r:.3e} cos={cos:.6f} |g_ref|={g_ref.norm().item():.3e}")
-    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
-    assert r < 1e-1 and cos > 0.995  # 24 layers of bf16 operands + the near-L1 loss gradient's sign flips
+    assert abs(loss.item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item())  # measured 1.3e-5
+    assert r < 3e-2 and cos > 0.999  # measured 8.7e-3 / 0.99998 (24 layers of bf16 operands, fp32 accumulation)
     # AdamW on the prompt parameters: the untouched prompts must not move (grad None => skipped, like torch at world 1)
     before = [p.detach().clone() for p in model.prompt_params_list]
     opt = model.configure_optimizers()["optimizer"]
@@ -295,8 +295,8 @@ def test_prompt_model_training_step_matches_reference(dev, batch):
 
 def test_training_step_full_batch_properties(dev):
     """BASELINE config 4 at full size (batch 32, 24 layers, 8 prompts): no CPU oracle run is affordable (~7 min), so
-    size-independent properties instead: (1) the step is reproducible: same seeds -> bitwise the same gradients (the
-    scalar loss is a float-atomic reduction, equal to 1e-5),
+    size-independent properties instead: (1) the step is reproducible: same seeds -> bitwise the same gradients and
+    the same loss bits (the loss reduction is two-stage in a fixed order, no float atomics),
     (2) only the drawn prompts receive a gradient and it is finite and non-zero, (3) the gradient is linear in the loss
     scale: backward of 2*loss == 2 * backward of loss (exact in floating point: a power of two)."""
     from beach_seg_b200.config import BeachSegConfig
@@ -327,7 +327,7 @@ def test_training_step_full_batch_properties(dev):
     (l0, idx0, g0), (l1, idx1, g1), (l2, idx2, g2) = runs
     print(f"[train B=32] losses {l0.item():.7f} {l1.item():.7f} {l2.item():.7f}")
     assert torch.equal(idx0, idx1) and torch.equal(idx0, idx2)
-    assert abs(l0.item() - l1.item()) <= 1e-5 * abs(l0.item())
+    assert l0.view(torch.int32).item() == l1.view(torch.int32).item()
     chosen = set(int(i) for i in idx0)
     for i in range(n_prompts):
         if i in chosen:

@@ -267,7 +267,7 @@ def test_accumulator_image_paste_and_outputs(dev, tmp_path):
         assert np.array_equal(acc.current_img.cpu().numpy(), canvas)
         want_pred = ref.argmax().astype(np.uint8)
         assert np.array_equal(acc.overlay().cpu().numpy(), glue_ref.overlay_prediction(canvas, want_pred, classes))
-    png = np.array(Image.open(tmp_path / "pred" / "20240101.png"))
+    png = np.array(Image.open(tmp_path / "images" / "20240101.png"))
     assert np.array_equal(png, glue_ref.overlay_prediction(canvas, want_pred, classes))
     mask_png = np.array(Image.open(tmp_path / "masks" / "20240101.png"))
     assert np.array_equal(mask_png, want_pred)

@@ -90,6 +90,44 @@ def test_two_rank_prompt_gradient_allreduce(tmp_path):
     assert torch.equal(g[3], torch.full((3, 8, 8), 14.0 / 2))           # rank 1 only
 
 
+def _exchange_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from beach_seg_b200.model import PromptGradExchange
+
+    # 4 prompts; rank 0 drew prompts (0, 1, 1), rank 1 drew (1, 3, 3); prompt 2 is unused everywhere
+    params = [torch.nn.Parameter(torch.zeros(3, 8, 8)) for _ in range(4)]
+    ex = PromptGradExchange(params)
+    out = []
+    for step in range(2):  # the buffer is reused: the second step must not see the first one's gradients
+        drawn = torch.tensor([(0, 1, 1), (1, 3, 3)][rank])
+        ex.begin_step(drawn)
+        loss = sum(params[int(i)].sum() * float(10 * rank + int(i) + 1 + step) for i in drawn)
+        loss.backward()  # autograd accumulates in place into the rows of the persistent buffer
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, ex.views))
+        ex.finish_step()
+        out.append([None if p.grad is None else p.grad.clone() for p in params])
+        assert all(p.grad is None or p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, ex.views))
+    hashes = [torch.zeros(4, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(hashes, torch.stack([torch.zeros((), dtype=torch.float64) if g is None else g.double().sum()
+                                         for g in out[-1]]))
+    assert all(torch.equal(h, hashes[0]) for h in hashes)  # every rank ends the step with the same gradients
+    if rank == 0:
+        torch.save(out, Path(out_dir) / "grads.pt")
+    dist.destroy_process_group()
+
+
+def test_two_rank_persistent_prompt_gradient_exchange(tmp_path):
+    """PromptGradExchange: p.grad are rows of ONE persistent buffer, one average all-reduce, prompts no rank drew keep
+    grad None, no stale gradient survives into the next step."""
+    mp.spawn(_exchange_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for step, g in enumerate(torch.load(tmp_path / "grads.pt")):
+        assert g[2] is None
+        assert torch.equal(g[0], torch.full((3, 8, 8), (1.0 + step) / 2))                          # rank 0, once
+        assert torch.equal(g[1], torch.full((3, 8, 8), (2 * (2.0 + step) + (12.0 + step)) / 2))    # rank 0 twice, rank 1 once
+        assert torch.equal(g[3], torch.full((3, 8, 8), 2 * (14.0 + step) / 2))                     # rank 1, twice
+
+
 def test_create_palette_matches_reference_rng_stream():
     """Drop-in: same torch.manual_seed -> same random palette as the reference's CPU path (src/model.py:215-231)."""
     torch.manual_seed(42)
@@ -117,5 +155,7 @@ def test_config_mirrors_reference_defaults():
     for k, v in ref.items():
         if k == "resample":
             assert ours[k] == v.name
+        elif k in ("data", "model_training_root"):  # the reference's defaults are the author's private directories
+            assert isinstance(ours[k], Path)
         else:
             assert ours[k] == v, k
