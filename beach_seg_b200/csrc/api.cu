@@ -16,6 +16,7 @@ constexpr int kT = BSEG_T;
 constexpr int kD = BSEG_HIDDEN;
 constexpr int kMlp = 4096;
 constexpr int kDecN = 16384;
+constexpr float kQScale = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e), see attention.cu
 
 struct LayerPack {
   __nv_bfloat16 *qkv_w, *proj_w, *lin1_w, *lin2_w, *relcat;
@@ -40,15 +41,16 @@ void ingest_geometry(int crop, int* band_out, int* max_rows_out) {
   *max_rows_out = max_rows;
 }
 
-// reversed + concatenated rel-pos tables (see attention.cu): rows 0..110 = rel_pos_h[110-i], 111 = 0,
-// rows 112..166 = rel_pos_w[54-(i-112)], rest 0
+// reversed + concatenated rel-pos tables, times 8 (see attention.cu): rows 0..110 = 8 rel_pos_h[110-i], 111 = 0,
+// rows 112..166 = 8 rel_pos_w[54-(i-112)], rest 0.  8 = 1 / head_dim^-0.5 (exact in bf16): the attention kernels take
+// qs = q * head_dim^-0.5 * log2(e), so qs . (8 rel) is the bias q . rel in the log2 domain.
 __global__ void pack_relcat_kernel(const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                                    __nv_bfloat16* __restrict__ out) {
   const int i = blockIdx.x, d = threadIdx.x;  // 176 x 64
   float v = 0.f;
   if (i < 111) v = rel_h[(110 - i) * 64 + d];
   else if (i >= 112 && i < 167) v = rel_w[(54 - (i - 112)) * 64 + d];
-  out[i * 64 + d] = __float2bfloat16_rn(v);
+  out[i * 64 + d] = __float2bfloat16_rn(8.0f * v);
 }
 
 // relcat [176,64] -> relcat^T [64,192] (columns 176..191 zero): K-major B operand of the bias-gradient MMA
@@ -409,6 +411,7 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
       ep.bias = lp.qkv_b;
       ep.q = pl.q; ep.k = pl.k; ep.vt = pl.vt;
       ep.T = kT; ep.heads = BSEG_HEADS;
+      ep.q_scale = kQScale;  // q is kept as bf16(q * head_dim^-0.5 * log2 e): the score lands in the log2 domain
       if ((rc = launch_gemm(EPI_QKV, fb.xn, kD, lp.qkv_w, M, 3 * kD, kD, ep, stream))) return rc;
     }
     if ((rc = launch_attention(pl.q, pl.k, pl.vt, lp.relcat, pl.att, pl.lse, nseq, BSEG_HEADS, 56, 28, stream)))

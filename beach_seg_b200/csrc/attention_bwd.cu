@@ -4,6 +4,9 @@
 //     dv = P^T dO,   dk = scale * dS^T q,
 //     dq = scale * dS k  +  sum_kh dSh[q,kh] Rh[qh-kh]  +  sum_kw dSw[q,kw] Rw[qw-kw]
 // (dSh / dSw = dS summed over the key columns / key rows of the 56x28 token grid; the rel-pos tables are frozen).
+// Operand conventions (shared with the forward, attention.cu): q arrives as qs = bf16(q * scale * log2 e) and the rel-pos
+// tables as relcat8 = 8 * rel (8 = 1 / scale), so qs.k and qs.relcat8 are the score and the bias in the log2 domain;
+// dk = dS^T qs / log2(e) and dq = scale * (dS k + dG relcat8) are the gradients w.r.t. the UNSCALED projections.
 // Nothing of size T x T touches HBM.  Two kernels, both with S, dP and the accumulators in TMEM:
 //
 //   attention_bwd_dq_kernel   one CTA per (seq, head, 128 queries); thread <-> query row (as in the forward), loops
@@ -247,7 +250,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         __syncwarp();
         if (kb + 2 < kNumKB) issue_sdp(kb + 2);
       }
-      // bias gradient: dQ_acc += (8 * dG) relcat   (8 = 1/scale, exact in bf16)
+      // bias gradient: dQ_acc += dG relcat8   (relcat8 = 8 rel = rel / scale)
       mbar_wait(relt_full, 0);
       mbar_wait(dg_full, 0);
       tc_fence_after();
@@ -288,7 +291,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int kh = c + i - off_h;
-          if (kh >= 0 && kh < kGridH && valid) tab[kh * kT + qi] = v[i] * kLog2e;
+          if (kh >= 0 && kh < kGridH && valid) tab[kh * kT + qi] = v[i];  // already in the log2 domain
         }
       }
       const int off_w = 27 - qw;  // bw[kw] = G[112 + off_w + kw]
@@ -300,7 +303,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int kw = c + i - off_w;
-          if (kw >= 0 && kw < kGridW && valid) tab[(kGridH + kw) * kT + qi] = v[i] * kLog2e;
+          if (kw >= 0 && kw < kGridW && valid) tab[(kGridH + kw) * kT + qi] = v[i];
         }
       }
       // both column groups of a row write the same values; every thread reads back what it wrote itself
@@ -315,7 +318,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     named_bar_sync(1, 256);  // dsh rows zeroed, both groups' table rows written (each thread re-reads what it wrote)
     if (lane == 0) mbar_arrive(g_free);
 
-    const float sc = 0.125f * kLog2e;
+    const float sc = 1.0f;  // qs carries scale * log2(e)
     float dsw[kGridW];
 #pragma unroll
     for (int i = 0; i < kGridW; ++i) dsw[i] = 0.f;
@@ -409,8 +412,8 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int ka = 2 * (w0 + j) - off_h, kb2 = ka + 1;
-          const float a = (ka >= 0 && ka < kGridH) ? dsh_row[ka] * 8.0f : 0.f;
-          const float b = (kb2 >= 0 && kb2 < kGridH) ? dsh_row[kb2] * 8.0f : 0.f;
+          const float a = (ka >= 0 && ka < kGridH) ? dsh_row[ka] : 0.f;
+          const float b = (kb2 >= 0 && kb2 < kGridH) ? dsh_row[kb2] : 0.f;
           pk[j] = pack_bf16x2(a, b);
         }
         tmem_st8u(lane_base + w0, pk);
@@ -425,8 +428,8 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int ka = 2 * (w0 + j) - off_w, kb2 = ka + 1;
-          const float a = (ka >= 0 && ka < kGridW) ? (stage[ka] + other[ka]) * 8.0f : 0.f;
-          const float b = (kb2 >= 0 && kb2 < kGridW) ? (stage[kb2] + other[kb2]) * 8.0f : 0.f;
+          const float a = (ka >= 0 && ka < kGridW) ? (stage[ka] + other[ka]) : 0.f;
+          const float b = (kb2 >= 0 && kb2 < kGridW) ? (stage[kb2] + other[kb2]) : 0.f;
           pk[j] = pack_bf16x2(a, b);
         }
         tmem_st8u(lane_base + 56 + w0, pk);
@@ -614,7 +617,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
     const int ki = valid ? ki_raw : kT - 1;
     const int khi = ki / kGridW - kh_lo, kw = ki % kGridW;
     const uint32_t lane_base = tmem_lane_base(tmem_base, quarter);
-    const float sc = 0.125f * kLog2e;
+    const float sc = 1.0f;  // qs carries scale * log2(e)
 
     for (int j = 0; j < kNumQB; ++j) {
       const int st = j % kStagesK, buf = j & 1;
@@ -665,7 +668,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
       float v[32];
       tmem_ld32(lane_base + (which == 0 ? kKColdV : kKColdK) + g * 32, v);
       tmem_ld_wait();
-      const float a = which == 0 ? 1.0f : 0.125f;
+      const float a = which == 0 ? 1.0f : 0.6931471805599453f;  // dk = dS^T qs / log2(e)
       if (valid) {
         __nv_bfloat16* dst = row + (which == 0 ? 2 * D : D);
 #pragma unroll

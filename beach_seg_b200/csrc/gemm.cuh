@@ -39,6 +39,7 @@ struct GemmEpiParams {
   __nv_bfloat16* k = nullptr;
   __nv_bfloat16* vt = nullptr;
   int heads = 16;
+  float q_scale = 1.0f;  // q is stored as bf16((acc + bias) * q_scale): the attention kernels take q * scale * log2(e)
 };
 
 // Which rows of A (== rows of the output) a launch covers: `nbatch` entries of `rows_per_batch` rows each, of which
@@ -241,6 +242,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, flo
     if (which < 2) {
       __nv_bfloat16* base = (which == 0) ? ep.q : ep.k;
       __nv_bfloat16* dst = base + ((seq * ep.heads + head) * ep.T + t) * 64 + d0;
+      if (which == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= ep.q_scale;
+      }
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 pk = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
@@ -461,6 +466,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               }
             }
             const int head = (n % D) >> 6;
+            if (which == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= ep.q_scale;
+            }
             __nv_bfloat16* base = (which == 0 ? ep.q : ep.k) + ((seq * ep.heads + head) * ep.T + t0) * 64;
             gemm_epi_bf16_store(base, 64, v, stg, 0, nvalid, n & 63, lane);
           } else if (lane < nvalid) {

@@ -257,14 +257,17 @@ int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int
 /* LayerNorm over 1024 columns: x fp32 [M,ldx] -> out bf16 [M,ldo]. */
 int bseg_layernorm1024(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
                        long long ldo, long long M, float eps, void* stream);
-/* Fused rel-pos attention. q,k bf16 [nseq,16,1568,64]; vt bf16 [nseq,16,64,1568]; relcat bf16 [176,64];
- * out bf16 [nseq,1568,1024]. */
+/* Fused rel-pos attention (HF:modeling_seggpt.py:268-348).  q bf16 [nseq,16,1568,64] = the query projection TIMES
+ * head_dim^-0.5 * log2(e) (what bseg_forward's QKV epilogue writes: the score then lands in the log2 domain with no
+ * per-element scaling); k bf16 [nseq,16,1568,64]; vt bf16 [nseq,16,64,1568]; relcat bf16 [176,64] from
+ * bseg_pack_relcat; out bf16 [nseq,1568,1024]. */
 int bseg_attention(const void* q, const void* k, const void* vt, const void* relcat, void* out, int nseq,
                    void* stream);
 /* The same with the log2-domain log-sum-exp per (seq, head, query) written to lse fp32 [nseq,16,1568]. */
 int bseg_attention_fwd_lse(const void* q, const void* k, const void* vt, const void* relcat, void* out, float* lse,
                            int nseq, void* stream);
-/* Backward of the fused attention (torch autograd through HF:modeling_seggpt.py:268-348 in the reference).
+/* Backward of the fused attention (torch autograd through HF:modeling_seggpt.py:268-348 in the reference); q as for
+ * bseg_attention (pre-scaled), the gradients are those w.r.t. the UNSCALED q / k / v projections.
  * out / d_out: bf16 token-major [nseq*1568, 1024]; dqkv: bf16 [nseq*1568, 3072] = (dq | dk | dv), head-major inside. */
 size_t bseg_attention_bwd_scratch_bytes(int nseq);
 int bseg_attention_bwd(const void* q, const void* k, const void* vt, const void* out, const void* d_out,
@@ -283,7 +286,8 @@ int bseg_pack_conv_w9_dgrad(const void* w9, void* w9b, void* stream);
 int bseg_decoder_head_bwd(const void* x_nhwc, const void* w9, const void* w9b, const float* conv_b, const float* ln_w,
                           const float* ln_b, const float* head_w, const float* head_b, const float* d_pred,
                           void* d_conv, void* d_dec_rows, int batch, int H, int W, int y0, float eps, void* stream);
-/* relcat = [reverse(rel_pos_h) (111 rows) ; 0 ; reverse(rel_pos_w) (55 rows) ; 0...] as bf16 [176,64]. */
+/* relcat = 8 * [reverse(rel_pos_h) (111 rows) ; 0 ; reverse(rel_pos_w) (55 rows) ; 0...] as bf16 [176,64]
+ * (8 = 1 / head_dim^-0.5: the pre-scaled q times this table is the rel-pos bias in the log2 domain). */
 int bseg_pack_relcat(const float* rel_pos_h, const float* rel_pos_w, void* relcat, void* stream);
 /* Decoder head: conv3x3 + LN(C) + GELU + conv1x1. x bf16 NHWC [B,H,W,64]; w9 bf16 [9,64,64]; pred fp32 [B,3,H,W]. */
 int bseg_decoder_head(const void* x_nhwc, const void* w9, const float* conv_b, const float* ln_w, const float* ln_b,

@@ -7,13 +7,20 @@ from oracle.seggpt_ref import attention_ref
 
 pytestmark = pytest.mark.gpu
 T = 1568
+Q_SCALE = 0.125 * 1.4426950408889634  # the kernels take qs = bf16(q * head_dim^-0.5 * log2 e) (QKV GEMM epilogue)
 
 
-def run_attention(q, k, v, rel_h, rel_w):
-    """q,k,v: [nseq,16,T,64] fp32 (already bf16-representable) on the device."""
-    dev = q.device
-    nseq = q.shape[0]
-    qb, kb = q.to(torch.bfloat16).contiguous(), k.to(torch.bfloat16).contiguous()
+def scaled_q(q):
+    """(qs, q_eff): the bf16 operand the kernel consumes and the fp32 q it stands for (what the oracle gets)."""
+    qs = (q * Q_SCALE).to(torch.bfloat16)
+    return qs, qs.float() / Q_SCALE
+
+
+def run_attention(qs, k, v, rel_h, rel_w):
+    """qs: bf16 [nseq,16,T,64] pre-scaled query (scaled_q); k,v: fp32 (already bf16-representable), on the device."""
+    dev = qs.device
+    nseq = qs.shape[0]
+    qb, kb = qs.to(torch.bfloat16).contiguous(), k.to(torch.bfloat16).contiguous()
     vt = v.to(torch.bfloat16).transpose(2, 3).contiguous()  # [nseq,16,64,T]
     relcat = torch.empty((176, 64), dtype=torch.bfloat16, device=dev)
     L = _lib.lib()
@@ -32,14 +39,14 @@ def bf16r(t):
 @pytest.mark.parametrize("nseq,qscale,relscale", [(1, 1.0, 0.0), (1, 1.0, 0.3), (2, 3.0, 0.5)])
 def test_attention_matches_oracle(dev, nseq, qscale, relscale):
     g = torch.Generator().manual_seed(int(nseq * 100 + qscale * 10 + relscale * 7))
-    q = bf16r(torch.randn((nseq, 16, T, 64), generator=g) * qscale)
+    qs, q = scaled_q(torch.randn((nseq, 16, T, 64), generator=g) * qscale)
     k = bf16r(torch.randn((nseq, 16, T, 64), generator=g))
     v = bf16r(torch.randn((nseq, 16, T, 64), generator=g))
     rel_h = bf16r(torch.randn((111, 64), generator=g) * relscale)
     rel_w = bf16r(torch.randn((55, 64), generator=g) * relscale)
     want = attention_ref(q.reshape(-1, T, 64), k.reshape(-1, T, 64), v.reshape(-1, T, 64), rel_h, rel_w)
     want = want.reshape(nseq, 16, T, 64).permute(0, 2, 1, 3).reshape(nseq, T, 1024)
-    got = run_attention(q.to(dev), k.to(dev), v.to(dev), rel_h.to(dev), rel_w.to(dev)).float().cpu()
+    got = run_attention(qs.to(dev), k.to(dev), v.to(dev), rel_h.to(dev), rel_w.to(dev)).float().cpu()
     err = (got - want).abs()
     scale = want.abs().max().item()
     rel = ((got - want).norm() / want.norm()).item()
@@ -58,7 +65,7 @@ def test_attention_extreme_dynamic_range(dev):
     """Scores that grow by far more than 2^100 between key blocks: exercises the lazy reference update, the O rescale
     in TMEM and the overflow-guard redo of the streaming softmax (the result must stay finite and exact)."""
     g = torch.Generator().manual_seed(77)
-    q = bf16r(torch.randn((1, 16, T, 64), generator=g) * 4.0)
+    qs, q = scaled_q(torch.randn((1, 16, T, 64), generator=g) * 4.0)
     k = bf16r(torch.randn((1, 16, T, 64), generator=g))
     k[:, :, 500:900] *= 6.0
     k[:, :, 900:] *= 14.0   # late keys dominate: every row has to raise its reference repeatedly
@@ -68,7 +75,7 @@ def test_attention_extreme_dynamic_range(dev):
     rel_w = bf16r(torch.randn((55, 64), generator=g) * 0.2)
     want = attention_ref(q.reshape(-1, T, 64), k.reshape(-1, T, 64), v.reshape(-1, T, 64), rel_h, rel_w)
     want = want.reshape(1, 16, T, 64).permute(0, 2, 1, 3).reshape(1, T, 1024)
-    got = run_attention(q.to(dev), k.to(dev), v.to(dev), rel_h.to(dev), rel_w.to(dev)).float().cpu()
+    got = run_attention(qs.to(dev), k.to(dev), v.to(dev), rel_h.to(dev), rel_w.to(dev)).float().cpu()
     assert torch.isfinite(got).all()
     rel = ((got - want).norm() / want.norm()).item()
     print(f"[attention extreme range] rel-L2={rel:.3e} max|err|={(got - want).abs().max().item():.3e}")
@@ -81,7 +88,7 @@ def test_attention_is_deterministic_and_batch_independent(dev):
     that the rel-pos staging and the V stages share.)"""
     g = torch.Generator().manual_seed(5)
     nseq = 40
-    q = (torch.randn((nseq, 16, T, 64), generator=g) * 1.5).to(dev)
+    q = scaled_q(torch.randn((nseq, 16, T, 64), generator=g) * 1.5)[0].to(dev)
     k = (torch.randn((nseq, 16, T, 64), generator=g) * 1.5).to(dev)
     v = torch.randn((nseq, 16, T, 64), generator=g).to(dev)
     rel_h = (torch.randn((111, 64), generator=g) * 0.3).to(dev)

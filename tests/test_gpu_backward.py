@@ -70,9 +70,13 @@ def test_gemm_dgelu(dev):
     assert r < 5e-3
 
 
+Q_SCALE = 0.125 * 1.4426950408889634  # the kernels take qs = bf16(q * head_dim^-0.5 * log2 e) (QKV GEMM epilogue)
+
+
 def _attention_case(dev, nseq, qscale, relscale, seed):
+    """q is the fp32 query the bf16 operand qs = bf16(q * Q_SCALE) stands for (so that the oracle sees the same q)."""
     g = torch.Generator().manual_seed(seed)
-    q = bf16r(torch.randn((nseq, 16, T, 64), generator=g) * qscale).to(dev)
+    q = ((torch.randn((nseq, 16, T, 64), generator=g) * qscale * Q_SCALE).to(torch.bfloat16).float() / Q_SCALE).to(dev)
     k = bf16r(torch.randn((nseq, 16, T, 64), generator=g)).to(dev)
     v = bf16r(torch.randn((nseq, 16, T, 64), generator=g)).to(dev)
     rel_h = bf16r(torch.randn((111, 64), generator=g) * relscale).to(dev)
@@ -108,7 +112,7 @@ def test_attention_backward(dev, nseq, qscale, relscale):
     assert ref.T == T
     # ---- ours ----
     L = _lib.lib()
-    qb, kb = q.to(torch.bfloat16).contiguous(), k.to(torch.bfloat16).contiguous()
+    qb, kb = (q * Q_SCALE).to(torch.bfloat16).contiguous(), k.to(torch.bfloat16).contiguous()  # qb: exact (see above)
     vt = v.to(torch.bfloat16).transpose(2, 3).contiguous()
     relcat = torch.empty((176, 64), dtype=torch.bfloat16, device=dev)
     _lib.check(L.bseg_pack_relcat(_lib.ptr(rel_h), _lib.ptr(rel_w), _lib.ptr(relcat), _lib.stream_ptr()))

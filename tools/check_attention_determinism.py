@@ -11,10 +11,10 @@ from beach_seg_b200 import _lib
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 nseq = 64
-q = (torch.randn((nseq, 16, 1568, 64), generator=g) * 1.5).to(dev).to(torch.bfloat16)
+q = (torch.randn((nseq, 16, 1568, 64), generator=g) * 1.5 * 0.18).to(dev).to(torch.bfloat16)  # pre-scaled
 k = (torch.randn((nseq, 16, 1568, 64), generator=g) * 1.5).to(dev).to(torch.bfloat16)
 vt = torch.randn((nseq, 16, 64, 1568), generator=g).to(dev).to(torch.bfloat16)
-rel = (torch.randn((176, 64), generator=g) * 0.3).to(dev).to(torch.bfloat16)
+rel = (torch.randn((176, 64), generator=g) * 0.3 * 8).to(dev).to(torch.bfloat16)  # relcat8
 L = _lib.lib()
 
 

@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < cnt; ++i) h[i] = __float2bfloat16(s * ((rand() % 2001) / 1000.0f - 1.0f));
     cudaMemcpy(d, h.data(), cnt * 2, cudaMemcpyHostToDevice);
   };
-  fill(q, n, 1.5f); fill(k, n, 1.5f); fill(vt, n, 1.0f); fill(rel, 176 * 64, 0.3f);
+  fill(q, n, 1.5f * 0.18f); fill(k, n, 1.5f); fill(vt, n, 1.0f); fill(rel, 176 * 64, 0.3f * 8.0f);  // q pre-scaled, relcat8
   for (int it = 0; it < 3; ++it) {
     int rc = launch_attention(q, k, vt, rel, out, nullptr, nseq, heads, 56, 28, 0);
     if (rc) { printf("launch failed: %s\n", last_error_buf()); return 1; }
@@ -35,28 +35,36 @@ int main(int argc, char** argv) {
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
-    printf("attention nseq=%d: %.3f ms per launch (S k-steps %d, PV k-steps %d, skip exp %d)\n", nseq, ms / 5,
-           (int)BSEG_ATTN_S_KSTEPS, (int)([] { using namespace bseg::attn; return BSEG_ATTN_PV_KSTEPS; }()), (int)BSEG_ATTN_SKIP_EXP);
+    printf("attention nseq=%d: %.3f ms per launch (warpgroups per CTA %d, skip exp %d)\n", nseq, ms / 5,
+           (int)BSEG_ATTN_WG, (int)BSEG_ATTN_SKIP_EXP);
   }
   long long tr[3][16][16];
   cudaMemcpyFromSymbol(tr, g_attn_trace, sizeof(tr));
   const long long t0 = tr[0][0][0];
   const char* names[3] = {"softmax WG0", "softmax WG1", "MMA issuer 0"};
-  const char* ev_s[7] = {"start", "S_lo ready", "lo done", "S_hi ready", "hi done", "prevPV done", "P handed"};
-  const char* ev_m[5] = {"K ready", "S_lo free", "S_hi free", "V ready", "P full"};
-  for (int a = 0; a < 3; ++a) {
-    printf("== %s (cycles since WG0 block 0 start; deltas in brackets)\n", names[a]);
+  // plain loop (BSEG_ATTN_PIPELINED=0) events in time order
+  const int order[10] = {0, 1, 6, 7, 2, 3, 4, 8, 9, 5};
+  const char* name[10] = {"start", "S full seen", "S row in regs", "Eh stored", "S handed back", "exp done",
+                          "prevPV seen", "P st issued", "P st complete", "P handed"};
+  for (int a = 0; a < 2; ++a) {
+    printf("== softmax WG%d: per-step cycles per key block (BSEG_ATTN_PIPELINED=%d)\n", a, (int)BSEG_ATTN_PIPELINED);
+    printf("%6s", "kb");
+    for (int e = 0; e < 10; ++e) printf(" %14s", name[e]);
+    printf("\n");
     for (int kb = 0; kb < 14; ++kb) {
-      printf(" kb=%2d:", kb);
-      const int ne = a < 2 ? 7 : 5;
-      long long prev = kb == 0 ? tr[a][0][0] : tr[a][kb - 1][a < 2 ? 6 : 4];
-      for (int ev = 0; ev < ne; ++ev) {
-        if (a < 2 && kb == 0 && ev == 5) { printf(" %12s", "-"); continue; }
-        printf(" %s=%lld[%lld]", a < 2 ? ev_s[ev] : ev_m[ev], tr[a][kb][ev] - t0, tr[a][kb][ev] - prev);
-        prev = tr[a][kb][ev];
+      printf("%6d", kb);
+      long long prev = kb == 0 ? tr[a][0][0] : tr[a][kb - 1][5];
+      for (int e = 0; e < 10; ++e) {
+        const long long t = tr[a][kb][order[e]];
+        if (kb == 0 && order[e] == 4) { printf(" %14s", "-"); continue; }
+        printf(" %14lld", t - prev);
+        prev = t;
       }
-      printf("\n");
+      printf("   | block end at %lld\n", tr[a][kb][5] - t0);
     }
   }
+  printf("== MMA issuer 0 (cycles since WG0 block 0 start): K ready, S free seen, V ready, P full seen\n");
+  for (int kb = 0; kb < 14; ++kb)
+    printf("%6d %10lld %10lld %10lld %10lld\n", kb, tr[2][kb][0] - t0, tr[2][kb][1] - t0, tr[2][kb][3] - t0, tr[2][kb][4] - t0);
   return 0;
 }

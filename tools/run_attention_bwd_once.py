@@ -13,10 +13,10 @@ iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 T = 1568
-q = torch.randn((nseq, 16, T, 64), generator=g).to(dev).to(torch.bfloat16)
+q = (torch.randn((nseq, 16, T, 64), generator=g) * 0.18).to(dev).to(torch.bfloat16)  # pre-scaled by 0.125*log2(e)
 k = torch.randn((nseq, 16, T, 64), generator=g).to(dev).to(torch.bfloat16)
 vt = torch.randn((nseq, 16, 64, T), generator=g).to(dev).to(torch.bfloat16)
-rel = (torch.randn((176, 64), generator=g) * 0.3).to(dev).to(torch.bfloat16)
+rel = (torch.randn((176, 64), generator=g) * 0.3 * 8).to(dev).to(torch.bfloat16)  # relcat8
 do = torch.randn((nseq, T, 1024), generator=g).to(dev).to(torch.bfloat16)
 out = torch.empty((nseq, T, 1024), dtype=torch.bfloat16, device=dev)
 lse = torch.empty((nseq, 16, T), dtype=torch.float32, device=dev)

@@ -10,10 +10,10 @@ from beach_seg_b200 import _lib
 nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
-q = torch.randn((nseq, 16, 1568, 64), generator=g).to(dev).to(torch.bfloat16)
+q = (torch.randn((nseq, 16, 1568, 64), generator=g) * 0.18).to(dev).to(torch.bfloat16)  # pre-scaled by 0.125*log2(e)
 k = torch.randn((nseq, 16, 1568, 64), generator=g).to(dev).to(torch.bfloat16)
 vt = torch.randn((nseq, 16, 64, 1568), generator=g).to(dev).to(torch.bfloat16)
-rel = (torch.randn((176, 64), generator=g) * 0.3).to(dev).to(torch.bfloat16)
+rel = (torch.randn((176, 64), generator=g) * 0.3 * 8).to(dev).to(torch.bfloat16)  # relcat8
 out = torch.empty((nseq, 1568, 1024), dtype=torch.bfloat16, device=dev)
 L = _lib.lib()
 for _ in range(2):
