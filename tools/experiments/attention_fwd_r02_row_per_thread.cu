@@ -1,4 +1,5 @@
-// Fused SegGPT attention: one CTA per (sequence, head, 128-query tile), two CTAs per SM.
+// Fused SegGPT attention.  BSEG_ATTN_WG = 1 (default): one CTA per (sequence, head, 128 queries), two CTAs per SM;
+// BSEG_ATTN_WG = 2: one CTA per 256 queries and SM with two softmax warpgroups sharing the K / V stages.
 //     out = softmax( (q*scale) k^T + rel_h[q, kh] + rel_w[q, kw] ) v
 // with the decomposed relative-position bias of modeling_seggpt.py:268-311 computed from the UNSCALED q
 // (modeling_seggpt.py:324-329) and an fp32 softmax (:331).  The reference materialises a (16n,1568,1568) fp32 score
@@ -8,9 +9,9 @@
 // reversed rel-pos tables (8 = 1 / head_dim^-0.5, exact in bf16), so that qs.k and qs.relcat8 are the score and the
 // bias in the log2 domain without any per-element scaling.
 //
-// The score tile arrives from the tensor core COMPLETE -- scaled, biased and relative to the running softmax reference
-// -- so that a softmax thread does one MUFU.EX2, half a pack and half a packed add per element (round 1: 6.7
-// instructions per element):
+// Round-2 structure: the score tile arrives from the tensor core COMPLETE -- scaled, biased and already relative to
+// the running softmax reference -- so that the softmax warps do one MUFU.EX2, half a pack and half a packed add per
+// element (round 1: 6.7 instructions per element, issue-bound at 0.42 of the MUFU rate):
 //     S = Qs K^T                       4 K-steps, bf16 operands from shared memory
 //       + Ew Bw                        2 K-steps, fp16: Ew[q, kw] = width bias of query q (TMEM, A operand),
 //                                                       Bw[kw, key] = [key % 28 == kw]   (constant one-hot, smem)
@@ -20,17 +21,19 @@
 // Key blocks are 112 keys = 4 rows of the 28-wide token grid (1568 = 14 * 112: no key masking).  The bias operands
 // are fp16 (11 significant bits; they are products q.rel of bf16 factors) and the one-hot factors are exact.
 //
-//   warp 0      TMA producer (Q tile + rel tables once; K blocks and V^T blocks through two 2-stage rings)
-//   warp 1      tcgen05 issuer (G = Qs relcat8^T once; per key block S, then O += P V)
-//   warps 2-3   idle (complete the control warpgroup, which gives its registers away with setmaxnreg)
-//   warps 4-7   softmax warpgroup (thread <-> query row == TMEM lane)
+//   warp 0      TMA producer (Q tiles + rel tables once; K blocks and V^T blocks through two rings shared by the tiles)
+//   warps 1-2   tcgen05 issuers, one per softmax warpgroup (G = Qs relcat8^T once; per key block S, then O += P V),
+//               each blocking on its own warpgroup's barriers only
+//   warp 3      idle (completes the control warpgroup, which gives its registers away with setmaxnreg)
+//   warps 4-7   softmax warpgroup 0 (thread <-> query row == TMEM lane), warps 8-11 softmax warpgroup 1 (WG = 2)
 //
-// Hand-offs: a thread copies its whole S row (112 fp32) to registers in one go and hands the S region straight back
-// -- with the next block's bias row and reference already in Eh -- so that the next S MMA runs under ALL of this
-// block's exponentials; a key block has two mbarrier waits (S full, previous P V retired; the second is probed while
-// the exponentials run).  Measured alternatives that lost (profiles/r02_attn_fwd_timeline_exp*.txt, sources under
-// tools/experiments/): strict MUFU turn taking between two warpgroups, a packed-FMA polynomial exp2 for part of the
-// elements, handing S back later to pipeline the stores, two threads per query row (8 softmax warps per CTA).
+// Hand-offs (profiles/r02_attn_fwd_timeline_*): every element costs one MUFU.EX2 (16 /clk/SM), i.e. >= 896 MUFU cycles
+// per warpgroup and key block; round 1 additionally exposed ~750 cycles of hand-off latency per block (five mbarrier
+// waits at >= 100 cycles each, tcgen05.commit -> wake-up, the S MMA behind a half-block of exponentials), during which
+// both co-resident warpgroups tend to wait at the same time (lock-step: 63 % MUFU utilisation).  Now a thread copies its
+// whole S row (112 fp32) to registers in one go and hands the S region straight back -- with the next block's bias row
+// and reference already in Eh -- so the next S MMA runs under ALL of this block's exponentials; a block has two waits
+// (S full, previous P V retired) instead of five.
 //
 // Streaming softmax against a lazily raised reference m: exact, because a stale reference only changes the common
 // scale of P, l and O.  m is folded into the MMA (column 4 of Eh); a block whose MMA was issued before m was raised
@@ -50,7 +53,17 @@ namespace bseg {
 #define BSEG_ATTN_SKIP_EXP 0
 #endif
 
+#ifndef BSEG_ATTN_WG
 #define BSEG_ATTN_WG 1
+#endif
+// of every 4 element pairs of a row, this many take the polynomial exp2 (FMA pipe) instead of MUFU.EX2
+#ifndef BSEG_ATTN_POLY
+#define BSEG_ATTN_POLY 0
+#endif
+// 1: software-pipelined hand-offs (next S row fetched under the P stores, barriers probed early); 0: plain order
+#ifndef BSEG_ATTN_PIPELINED
+#define BSEG_ATTN_PIPELINED 0
+#endif
 
 namespace attn {
 constexpr int kWG = BSEG_ATTN_WG;      // softmax warpgroups (query tiles) per CTA
@@ -131,6 +144,43 @@ __device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float 
   asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(d));
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// 2^x for two elements on the FMA / ALU pipes instead of the MUFU (the MUFU.EX2 rate, 16 /clk/SM, is what bounds this
+// kernel): Cody-Waite split x = j + f, j = round(x) via the 1.5*2^23 trick, f in [-0.5, 0.5], 2^f by a degree-3
+// minimax polynomial (max relative error 7.5e-5, far below the bf16 rounding of P: 3.9e-3), 2^j by adding j to the
+// exponent field.  x is clamped to >= -126 (results below 2^-126 are flushed by the MUFU path as well).
+__device__ __forceinline__ void exp2_poly_x2(float x0, float x1, float& p0, float& p1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+  const uint64_t nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+  const uint64_t x = pack_f32x2(x0, x1);
+  const uint64_t t = fadd2(x, magic);                                   // low mantissa bits = round(x)
+  const uint64_t jf = fadd2(t, nmagic);                                 // round(x) as a float
+  const uint64_t f = fadd2(x, jf ^ 0x8000000080000000ull);              // x - round(x)
+  uint64_t p = ffma2(pack_f32x2(0.0551716685f, 0.0551716685f), f, pack_f32x2(0.242611125f, 0.242611125f));
+  p = ffma2(p, f, pack_f32x2(0.693260968f, 0.693260968f));
+  p = ffma2(p, f, pack_f32x2(0.999928057f, 0.999928057f));
+  float t0, t1, q0, q1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(p));
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 // Instruction descriptor: A = B = fp16, D = fp32, both K-major
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
@@ -412,10 +462,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if constexpr (kAdjust) {
           x0 += delta; x1 += delta; x2 += delta; x3 += delta;
         }
-        const float p0 = BSEG_ATTN_SKIP_EXP ? x0 * 0.001f : ex2_approx(x0);
-        const float p1 = BSEG_ATTN_SKIP_EXP ? x1 * 0.001f : ex2_approx(x1);
-        const float p2 = BSEG_ATTN_SKIP_EXP ? x2 * 0.001f : ex2_approx(x2);
-        const float p3 = BSEG_ATTN_SKIP_EXP ? x3 * 0.001f : ex2_approx(x3);
+        float p0, p1, p2, p3;
+        // pairs (i/2) % 4 < BSEG_ATTN_POLY go to the FMA pipe
+        if (((i >> 1) & 3) < BSEG_ATTN_POLY) {
+          exp2_poly_x2(x0, x1, p0, p1);
+        } else {
+          p0 = BSEG_ATTN_SKIP_EXP ? x0 * 0.001f : ex2_approx(x0);
+          p1 = BSEG_ATTN_SKIP_EXP ? x1 * 0.001f : ex2_approx(x1);
+        }
+        if ((((i >> 1) + 1) & 3) < BSEG_ATTN_POLY) {
+          exp2_poly_x2(x2, x3, p2, p3);
+        } else {
+          p2 = BSEG_ATTN_SKIP_EXP ? x2 * 0.001f : ex2_approx(x2);
+          p3 = BSEG_ATTN_SKIP_EXP ? x3 * 0.001f : ex2_approx(x3);
+        }
         add_f32x2(ls[0], ls[1], p0, p1);
         add_f32x2(ls[2], ls[3], p2, p3);
         pk[i >> 1] = pack_bf16x2(p0, p1);
@@ -444,11 +504,104 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     using Fast = std::false_type;
     using Slow = std::true_type;
     using C0 = std::integral_constant<int, 0>;
-    using C2 = std::integral_constant<int, 64>;   // the barrier of the end of the block is probed after this many
+    using C1 = std::integral_constant<int, 32>;   // the S region is handed back after this many exponentials
+    using C2 = std::integral_constant<int, 80>;   // the barriers of the end of the block are probed here
     using C3 = std::integral_constant<int, kKB>;
 
+#if BSEG_ATTN_PIPELINED
+    // Software pipeline: every hand-off latency (mbarrier probe ~100-200 cycles, tcgen05.ld / st + wait ~100-150 cycles)
+    // runs under exponentials of the same warp instead of in front of them -- the S row of block j+1 is fetched while
+    // P_j is on its way to TMEM, Eh and P stores are waited for one stage later, barriers are probed ahead of time.
     float x[kKB];
-    uint2 gnext = *reinterpret_cast<const uint2*>(bh_row + 2);  // packed height bias of key block 1
+    mbar_wait(&s_full[w], 0);
+    tc_fence_after();
+    load_s_row(x);
+    tmem_ld_wait();
+
+    for (int kb = 0; kb < kNumKB; ++kb) {
+      const float m_in_s = m_in_next;  // the reference that was in Eh when THIS block's S was issued
+      if (quarter == 0) ATTN_TRACE(w, kb, 0);  // block start: S row in registers
+      if (kb == 0) m_run = ceil16(row_max(x));  // initial reference: row max over the first key block
+      // ---------------- next block's bias row and reference into Eh (the store completes under the first exponentials) ----------------
+      if (kb + 1 < kNumKB) {
+        const uint2 gnext = *reinterpret_cast<const uint2*>(bh_row + 2 * (kb + 1));
+        const float m_enc = fminf(fmaxf(m_run, -kMaxEncodedRef), kMaxEncodedRef);
+        tmem_st4u(lane_base + kColEh, gnext.x, gnext.y, pack_f16x2(-m_enc, 0.f), 0u);
+        m_in_next = m_enc;
+      }
+      float delta = m_in_s - m_run;
+      const bool adjust = __any_sync(0xffffffffu, delta != 0.f);
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      if (adjust) exp_cols(Slow{}, C0{}, C1{}, x, delta, ls);
+      else exp_cols(Fast{}, C0{}, C1{}, x, 0.f, ls);
+      // ---------------- S region (with Eh) back to the tensor core: S_{j+1} runs under the rest of this block ----------------
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[w]);
+      if (quarter == 0) ATTN_TRACE(w, kb, 1);  // S handed back
+      if (adjust) exp_cols(Slow{}, C1{}, C2{}, x, delta, ls);
+      else exp_cols(Fast{}, C1{}, C2{}, x, 0.f, ls);
+      // probe the barriers the end of the block needs (results are consumed ~30 exponentials later)
+      const bool pv_ready = kb > 0 ? mbar_test(&pv_done[w], (kb - 1) & 1) : true;
+      if (adjust) exp_cols(Slow{}, C2{}, C3{}, x, delta, ls);
+      else exp_cols(Fast{}, C2{}, C3{}, x, 0.f, ls);
+      float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      if (__any_sync(0xffffffffu, !(lsum < kOverflowGuard))) {  // (practically never) redo against a safe reference
+        raise(fmaxf(ceil16(row_max(x) + delta), 0.f));
+        delta = m_in_s - m_run;
+        ls[0] = ls[1] = ls[2] = ls[3] = 0.f;
+        exp_cols(Slow{}, C0{}, C3{}, x, delta, ls);
+        lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      }
+      if (quarter == 0) ATTN_TRACE(w, kb, 2);  // exponentials done
+
+      // ---------------- hand P to the tensor core ----------------
+      if (kb > 0) {
+        // the P region and O are ours again once the previous P*V has retired
+        if (!__all_sync(0xffffffffu, pv_ready)) mbar_wait(&pv_done[w], (kb - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha_pending != 1.0f)) {
+#pragma unroll
+          for (int c = 0; c < 64; c += 16) {
+            float v[16];
+            tmem_ld16(lane_base + kColO + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= alpha_pending;
+            tmem_st16(lane_base + kColO + c, v);
+          }
+        }
+      }
+      alpha_pending = 1.0f;
+      tmem_st16u(lane_base + kColP, &pk[0]);
+      tmem_st16u(lane_base + kColP + 16, &pk[16]);
+      tmem_st16u(lane_base + kColP + 32, &pk[32]);
+      tmem_st8u(lane_base + kColP + 48, &pk[48]);
+      if (quarter == 0) ATTN_TRACE(w, kb, 3);  // P stores issued
+      // ---------------- fetch the next S row while the P stores complete ----------------
+      if (kb + 1 < kNumKB) {
+        mbar_wait(&s_full[w], (kb + 1) & 1);  // issued ~80 exponentials ago
+        tc_fence_after();
+        load_s_row(x);
+      }
+      if (quarter == 0) ATTN_TRACE(w, kb, 4);  // next S row requested
+      l_run += lsum;
+      // lazily raise the reference for the following blocks: row sum < 2^e and max P >= row sum / 112
+      if (lsum > kRaiseThreshold) {
+        const int e = ((__float_as_int(lsum) >> 23) & 0xff) - 126;
+        raise(static_cast<float>((e + 15) & ~15));  // applied to O once this block's P*V has retired
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[w]);
+      tmem_ld_wait();
+      if (quarter == 0) ATTN_TRACE(w, kb, 5);  // P handed over, next S row in registers
+    }
+
+#else
+    float x[kKB];
     for (int kb = 0; kb < kNumKB; ++kb) {
       const float m_in_s = m_in_next;  // the reference that was in Eh when THIS block's S was issued
 
@@ -459,14 +612,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_fence_after();
       load_s_row(x);
       tmem_ld_wait();
+      if (quarter == 0) ATTN_TRACE(w, kb, 6);  // S row in registers
       if (kb == 0) m_run = ceil16(row_max(x));  // initial reference: row max over the first key block
       if (kb + 1 < kNumKB) {
+        const uint2 gnext = *reinterpret_cast<const uint2*>(bh_row + 2 * (kb + 1));
         const float m_enc = fminf(fmaxf(m_run, -kMaxEncodedRef), kMaxEncodedRef);
         tmem_st4u(lane_base + kColEh, gnext.x, gnext.y, pack_f16x2(-m_enc, 0.f), 0u);
         m_in_next = m_enc;
-        if (kb + 2 < kNumKB) gnext = *reinterpret_cast<const uint2*>(bh_row + 2 * (kb + 2));  // (used one block later)
         tmem_st_wait();
       }
+      if (quarter == 0) ATTN_TRACE(w, kb, 7);  // Eh stored
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[w]);  // the next block's S may be issued: it runs under this block's exponentials
@@ -475,13 +630,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // ---------------- exponentials ----------------
       float delta = m_in_s - m_run;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      const bool adjust = __any_sync(0xffffffffu, delta != 0.f);
-      if (adjust) exp_cols(Slow{}, C0{}, C2{}, x, delta, ls);
-      else exp_cols(Fast{}, C0{}, C2{}, x, 0.f, ls);
-      // probe the barrier the end of the block needs now: the probe's latency runs under the remaining exponentials
-      const bool pv_ready = kb > 0 ? mbar_test(&pv_done[w], (kb - 1) & 1) : true;
-      if (adjust) exp_cols(Slow{}, C2{}, C3{}, x, delta, ls);
-      else exp_cols(Fast{}, C2{}, C3{}, x, 0.f, ls);
+      if (__any_sync(0xffffffffu, delta != 0.f)) exp_cols(Slow{}, C0{}, C3{}, x, delta, ls);
+      else exp_cols(Fast{}, C0{}, C3{}, x, 0.f, ls);
       float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       if (__any_sync(0xffffffffu, !(lsum < kOverflowGuard))) {  // (practically never) redo against a safe reference
         raise(fmaxf(ceil16(row_max(x) + delta), 0.f));
@@ -495,7 +645,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // ---------------- hand P to the tensor core ----------------
       if (kb > 0) {
         // the P region and O are ours again once the previous P*V has retired
-        if (!__all_sync(0xffffffffu, pv_ready)) mbar_wait(&pv_done[w], (kb - 1) & 1);
+        mbar_wait(&pv_done[w], (kb - 1) & 1);
         if (quarter == 0) ATTN_TRACE(w, kb, 4);  // previous PV retired
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha_pending != 1.0f)) {
@@ -516,7 +666,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tmem_st16u(lane_base + kColP + 32, &pk[32]);
       tmem_st8u(lane_base + kColP + 48, &pk[48]);
       l_run += lsum;
+      if (quarter == 0) ATTN_TRACE(w, kb, 8);  // P stores issued
       tmem_st_wait();
+      if (quarter == 0) ATTN_TRACE(w, kb, 9);  // P stores complete
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[w]);
@@ -529,6 +681,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
     }
 
+#endif
     // ---- epilogue: O / l -> bf16, token-major [seq, t, heads*64] ----
     mbar_wait(&pv_done[w], (kNumKB - 1) & 1);
     tc_fence_after();

@@ -35,35 +35,31 @@ int main(int argc, char** argv) {
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
-    printf("attention nseq=%d: %.3f ms per launch (warpgroups per CTA %d, skip exp %d)\n", nseq, ms / 5,
-           (int)BSEG_ATTN_WG, (int)BSEG_ATTN_SKIP_EXP);
+    printf("attention nseq=%d: %.3f ms per launch (skip exp %d)\n", nseq, ms / 5, (int)BSEG_ATTN_SKIP_EXP);
   }
   long long tr[3][16][16];
   cudaMemcpyFromSymbol(tr, g_attn_trace, sizeof(tr));
   const long long t0 = tr[0][0][0];
   const char* names[3] = {"softmax WG0", "softmax WG1", "MMA issuer 0"};
-  // plain loop (BSEG_ATTN_PIPELINED=0) events in time order
-  const int order[10] = {0, 1, 6, 7, 2, 3, 4, 8, 9, 5};
-  const char* name[10] = {"start", "S full seen", "S row in regs", "Eh stored", "S handed back", "exp done",
-                          "prevPV seen", "P st issued", "P st complete", "P handed"};
+  const char* name[6] = {"start", "S full seen", "S handed back", "exp done", "prevPV seen", "P handed"};
   for (int a = 0; a < 2; ++a) {
-    printf("== softmax WG%d: per-step cycles per key block (BSEG_ATTN_PIPELINED=%d)\n", a, (int)BSEG_ATTN_PIPELINED);
+    printf("== softmax thread group %d (score columns [%d,%d)): cycles per step and key block\n", a, 56 * a, 56 * a + 56);
     printf("%6s", "kb");
-    for (int e = 0; e < 10; ++e) printf(" %14s", name[e]);
+    for (int e = 0; e < 6; ++e) printf(" %14s", name[e]);
     printf("\n");
     for (int kb = 0; kb < 14; ++kb) {
       printf("%6d", kb);
       long long prev = kb == 0 ? tr[a][0][0] : tr[a][kb - 1][5];
-      for (int e = 0; e < 10; ++e) {
-        const long long t = tr[a][kb][order[e]];
-        if (kb == 0 && order[e] == 4) { printf(" %14s", "-"); continue; }
+      for (int e = 0; e < 6; ++e) {
+        const long long t = tr[a][kb][e];
+        if (kb == 0 && e == 4) { printf(" %14s", "-"); continue; }
         printf(" %14lld", t - prev);
         prev = t;
       }
       printf("   | block end at %lld\n", tr[a][kb][5] - t0);
     }
   }
-  printf("== MMA issuer 0 (cycles since WG0 block 0 start): K ready, S free seen, V ready, P full seen\n");
+  printf("== MMA issuer (cycles since block 0 start): K ready, S free seen, V ready, P full seen\n");
   for (int kb = 0; kb < 14; ++kb)
     printf("%6d %10lld %10lld %10lld %10lld\n", kb, tr[2][kb][0] - t0, tr[2][kb][1] - t0, tr[2][kb][3] - t0, tr[2][kb][4] - t0);
   return 0;
