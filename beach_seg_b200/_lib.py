@@ -53,6 +53,7 @@ SIGNATURES = {
     "bseg_workspace_bytes": (_sz, [_vp, _i]),
     "bseg_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "bseg_forward_query_half": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "bseg_set_graph_batch_limit": (_i, [_vp, _i]),
     "bseg_enable_fp32": (_i, [_vp, C.POINTER(Weights), _vp]),
     "bseg_workspace_bytes_f32": (_sz, [_vp, _i]),
     "bseg_forward_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),

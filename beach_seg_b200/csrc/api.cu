@@ -1,5 +1,6 @@
 // C ABI of libbseg.so (declared in include/bseg.h): weight packing, the SegGPT forward schedule and thin
 // wrappers around the kernel launchers.
+#include <list>
 #include <new>
 #include <vector>
 
@@ -132,6 +133,24 @@ struct bseg_handle {
   // training-only packs (bseg_train_prepare)
   void* train_arena = nullptr;
   __nv_bfloat16 *patch_wt = nullptr, *dec_embed_wt = nullptr, *conv_w9b = nullptr;
+  // CUDA graphs of whole forwards (bseg_set_graph_batch_limit): a forward is ~190 launches whose CUtensorMaps are
+  // re-encoded on the host every time; at small batch that host work is as long as the device work.  The second call
+  // with the same arguments captures the launch sequence once, later calls replay it.
+  struct GraphKey {
+    const void *px, *ppx, *pm, *ws, *pred;
+    int batch, emb, prompts, query_half, pairs;
+    bool operator==(const GraphKey& o) const {
+      return px == o.px && ppx == o.ppx && pm == o.pm && ws == o.ws && pred == o.pred && batch == o.batch &&
+             emb == o.emb && prompts == o.prompts && query_half == o.query_half && pairs == o.pairs;
+    }
+  };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;  // nullptr: seen once (eagerly), capture on the next call
+    int launches;          // kernels in the graph (bseg_launch_count keeps counting replays)
+  };
+  std::list<GraphEntry> graphs;  // most recently used first
+  int graph_batch_limit = 0;     // 0: never use graphs
   // fp32 accuracy mode (bseg_enable_fp32): the handle's own fp32 copy of the matrices
   void* f32_arena = nullptr;
   std::vector<F32Layer> f32_layers;
@@ -146,6 +165,8 @@ long long bseg_launch_count(void) { return launch_count(); }
 
 int bseg_destroy(bseg_handle* h) {
   if (!h) return 0;
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->arena) cudaFree(h->arena);
   if (h->train_arena) cudaFree(h->train_arena);
   if (h->f32_arena) cudaFree(h->f32_arena);
@@ -513,6 +534,20 @@ size_t bseg_train_workspace_bytes(const bseg_handle* h, int batch) {
   return train_layout(h, batch).total;
 }
 
+static int forward_eager(bool query_half_only, bseg_handle* h, const float* pixel_values,
+                         const float* prompt_pixel_values, const float* prompt_masks, int batch, int embedding_type,
+                         int ensemble_prompts, void* workspace, float* pred_masks, cudaStream_t stream) {
+  const WsLayout L = ws_layout(batch);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(ws + o); };
+  FwdBufs fb;
+  fb.h_emb = reinterpret_cast<float*>(ws + L.h);
+  fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
+  fb.layers.assign(h->num_layers, {fb.h_emb, fb.h_emb, bf(L.q), bf(L.k), bf(L.vt), bf(L.att), nullptr, nullptr});
+  return forward_impl(h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, ensemble_prompts, fb,
+                      pred_masks, stream, query_half_only);
+}
+
 static int forward_entry(bool query_half_only, bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
                  const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
                  size_t workspace_bytes, float* pred_masks, void* stream_) {
@@ -523,14 +558,63 @@ static int forward_entry(bool query_half_only, bseg_handle* h, const float* pixe
                "bseg_forward: batch=%d is not a multiple of ensemble_prompts=%d", batch, ensemble_prompts);
   const WsLayout L = ws_layout(batch);
   BSEG_REQUIRE(workspace_bytes >= L.total, "bseg_forward: workspace too small (%zu < %zu)", workspace_bytes, L.total);
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(ws + o); };
-  FwdBufs fb;
-  fb.h_emb = reinterpret_cast<float*>(ws + L.h);
-  fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
-  fb.layers.assign(h->num_layers, {fb.h_emb, fb.h_emb, bf(L.q), bf(L.k), bf(L.vt), bf(L.att), nullptr, nullptr});
-  return forward_impl(h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, ensemble_prompts, fb,
-                      pred_masks, stream, query_half_only);
+  auto eager = [&]() {
+    return forward_eager(query_half_only, h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type,
+                         ensemble_prompts, workspace, pred_masks, stream);
+  };
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (batch > h->graph_batch_limit || prof_enabled() ||
+      cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+    return eager();  // (per-launch event timing and a caller's own capture both need the plain launch sequence)
+  const bseg_handle::GraphKey key{pixel_values, prompt_pixel_values, prompt_masks, workspace, pred_masks, batch,
+                                  embedding_type, ensemble_prompts, query_half_only ? 1 : 0, gemm_set_cta_pairs(-1)};
+  for (auto it = h->graphs.begin(); it != h->graphs.end(); ++it) {
+    if (!(it->key == key)) continue;
+    h->graphs.splice(h->graphs.begin(), h->graphs, it);  // most recently used first
+    bseg_handle::GraphEntry& e = h->graphs.front();
+    if (e.exec == nullptr) {  // second call with these arguments: capture (one-time attributes were set by the first)
+      const long long launches0 = launch_count();
+      if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return eager();
+      }
+      rc = eager();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+      if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->graphs.pop_front();
+        return rc != 0 ? rc : eager();
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      e.launches = static_cast<int>(launch_count() - launches0);
+      count_launch(-e.launches);  // nothing ran yet: the replay below accounts for the kernels
+      if (ie != cudaSuccess) {
+        cudaGetLastError();
+        h->graphs.pop_front();
+        return eager();
+      }
+    }
+    BSEG_CHECK_CUDA(cudaGraphLaunch(e.exec, stream));
+    count_launch(e.launches);
+    return 0;
+  }
+  // first call with these arguments: run it, remember the key (bounded cache)
+  h->graphs.push_front({key, nullptr, 0});
+  if (h->graphs.size() > 16) {
+    if (h->graphs.back().exec) cudaGraphExecDestroy(h->graphs.back().exec);
+    h->graphs.pop_back();
+  }
+  return eager();
+}
+
+int bseg_set_graph_batch_limit(bseg_handle* h, int max_batch) {
+  BSEG_REQUIRE(h != nullptr && max_batch >= 0, "bseg_set_graph_batch_limit: bad argument");
+  const int prev = h->graph_batch_limit;
+  h->graph_batch_limit = max_batch;
+  return prev;
 }
 
 int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,

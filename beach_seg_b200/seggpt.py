@@ -84,10 +84,14 @@ class _PromptGradFn(torch.autograd.Function):
 class SegGptB200(torch.nn.Module):
     def __init__(self, state_dict: Dict[str, torch.Tensor], num_layers: int = 24, merge_index: int = 2,
                  intermediate=(5, 11, 17, 23), layer_norm_eps: float = 1e-6, beta: float = 0.01,
-                 device: str | torch.device = "cuda:0", max_batch: int = 64, precision: str = "bf16"):
+                 device: str | torch.device = "cuda:0", max_batch: int = 64, precision: str = "bf16",
+                 graph_batch: int = 16):
         """precision: "bf16" = the tcgen05 path (bf16 operands, fp32 accumulation / residual stream / softmax; logits
         within 1e-2 of the fp32 reference); "fp32" = the accuracy mode (bseg_forward_f32: everything IEEE fp32 on the
-        CUDA cores, within 1e-4, inference only, ~30x slower)."""
+        CUDA cores, within 1e-4, inference only, ~30x slower).
+        graph_batch: inference calls with at most this many samples go through persistent staging buffers and a CUDA graph
+        of the whole forward (bseg_set_graph_batch_limit): the reference's own call pattern is batch 1
+        (src/predict.py:234), where the host work of ~190 launches is as long as the device work.  0 disables it."""
         super().__init__()
         if precision not in ("bf16", "fp32"):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
@@ -105,6 +109,8 @@ class SegGptB200(torch.nn.Module):
         self.check_grad_support = True  # verify in backward() that d(pred_masks) is zero in the prompt half
         self._train_ready = False
         self._scratch = torch.zeros(_ops_loss_scratch(), dtype=torch.float32, device=self._device)
+        self.graph_batch = int(graph_batch) if precision == "bf16" else 0
+        self._stage: Dict[int, tuple] = {}  # batch -> (px, ppx, pm, pred, workspace) with fixed addresses
         L = _lib.lib()
         with torch.cuda.device(self._device):
             keep = []  # fp32 staging copies, freed after packing
@@ -144,6 +150,8 @@ class SegGptB200(torch.nn.Module):
             _lib.check(L.bseg_create(C.byref(w), C.byref(self._handle), _lib.stream_ptr()), "bseg_create")
             if precision == "fp32":
                 _lib.check(L.bseg_enable_fp32(self._handle, C.byref(w), _lib.stream_ptr()), "bseg_enable_fp32")
+            if self.graph_batch > 0:
+                _lib.check(L.bseg_set_graph_batch_limit(self._handle, self.graph_batch) < 0, "bseg_set_graph_batch_limit")
             torch.cuda.current_stream().synchronize()
             del keep
 
@@ -251,9 +259,12 @@ class SegGptB200(torch.nn.Module):
             ppx_g = prompt_pixel_values.to(device=self._device, dtype=torch.float32).contiguous()
             pred = _PromptGradFn.apply(ppx_g, self, prep(pixel_values), prep(prompt_masks), embedding_type)
             return SegGptOutput(loss=self._hf_loss(pred.detach(), labels, B, mask_rows), pred_masks=pred)
+        L = _lib.lib()
+        if 0 < B <= min(self.graph_batch, self.max_batch) and self.precision == "bf16":
+            return self._forward_staged(pixel_values, prompt_pixel_values, prompt_masks, B, embedding_type, P,
+                                        query_half_only, labels, mask_rows)
         px, ppx, pm = prep(pixel_values), prep(prompt_pixel_values), prep(prompt_masks)
         pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=self._device)
-        L = _lib.lib()
         step = self.max_batch if P == 0 else max(P, (self.max_batch // P) * P)
         if self.precision == "fp32":
             fwd, fwd_name = L.bseg_forward_f32, "bseg_forward_f32"
@@ -271,6 +282,32 @@ class SegGptB200(torch.nn.Module):
                                C.c_void_p(base), C.c_size_t(ws.numel() - (base - ws.data_ptr())),
                                _lib.ptr(pred[s:s + n]), _lib.stream_ptr()), fwd_name)
         return SegGptOutput(loss=self._hf_loss(pred, labels, B, mask_rows), pred_masks=pred)
+
+    def _forward_staged(self, pixel_values, prompt_pixel_values, prompt_masks, B, embedding_type, P, query_half_only,
+                        labels, mask_rows) -> SegGptOutput:
+        """Small-batch inference: inputs are copied into per-batch-size buffers with fixed addresses, so that the
+        library can replay the whole forward as one CUDA graph (same kernels, same order: bit-identical results)."""
+        st = self._stage.get(B)
+        if st is None:
+            L = _lib.lib()
+            mk = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self._device)  # noqa: E731
+            ws = torch.empty(int(L.bseg_workspace_bytes(self._handle, B)) + 256, dtype=torch.uint8, device=self._device)
+            st = (mk(B, 3, IMG, IMG), mk(B, 3, IMG, IMG), mk(B, 3, IMG, IMG), mk(B, 3, 2 * IMG, IMG), ws)
+            self._stage[B] = st
+        px, ppx, pm, pred, ws = st
+        px.copy_(pixel_values.detach(), non_blocking=True)
+        ppx.copy_(prompt_pixel_values.detach(), non_blocking=True)
+        pm.copy_(prompt_masks.detach(), non_blocking=True)
+        L = _lib.lib()
+        fwd, name = ((L.bseg_forward_query_half, "bseg_forward_query_half") if query_half_only
+                     else (L.bseg_forward, "bseg_forward"))
+        base = (ws.data_ptr() + 255) // 256 * 256
+        with torch.cuda.device(self._device):
+            _lib.check(fwd(self._handle, _lib.ptr(px), _lib.ptr(ppx), _lib.ptr(pm), B,
+                           0 if embedding_type == "instance" else 1, P, C.c_void_p(base),
+                           C.c_size_t(ws.numel() - (base - ws.data_ptr())), _lib.ptr(pred), _lib.stream_ptr()), name)
+        out = pred.clone()  # the staging buffer is overwritten by the next call
+        return SegGptOutput(loss=self._hf_loss(out, labels, B, mask_rows), pred_masks=out)
 
     def _hf_loss(self, pred: torch.Tensor, labels: Optional[torch.Tensor], B: int, mask_rows: int = 1):
         """HF SegGptLoss (HF:modeling_seggpt.py:780-819) with the default mask == smooth-L1 over the bottom half:

@@ -94,6 +94,13 @@ int bseg_forward_query_half(bseg_handle* h, const float* pixel_values, const flo
                             const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts,
                             void* workspace, size_t workspace_bytes, float* pred_masks, void* stream);
 
+/* Small-batch latency: the reference calls the model with batch 1 (src/data.py:287-293, src/predict.py:234), where the
+ * ~190 launches of a forward (each re-encoding its CUtensorMaps on the host) cost as much host time as device time.
+ * With a limit > 0, bseg_forward / bseg_forward_query_half calls with batch <= max_batch are captured into a CUDA graph
+ * the second time the same (pointers, batch, flags) come in and replayed from then on (results are bit-identical: the
+ * same kernels in the same order).  Returns the previous limit; 0 (the initial value) disables graphs. */
+int bseg_set_graph_batch_limit(bseg_handle* h, int max_batch);
+
 /* ---- fp32 accuracy mode: the same forward with every operand, accumulator and activation in IEEE fp32 on the CUDA
  * cores (no tensor cores, no bf16) -- logits within 1e-4 relative of the reference's fp32 CPU forward, about 30x
  * slower than bseg_forward.  bseg_enable_fp32 copies the fp32 matrices of `w` (the struct given to bseg_create) into

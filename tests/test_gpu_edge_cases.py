@@ -103,3 +103,28 @@ def test_c_abi_argument_errors(dev, small_model):
     assert rc == -1000 and b"bseg_enable_fp32" in L.bseg_last_error()
     with pytest.raises(_lib.BsegError):
         ops.scene_stats(torch.zeros((4, 8, 8), dtype=torch.int16), torch.zeros((8, 8), dtype=torch.bool))  # CPU tensors
+
+
+def test_cuda_graph_replay_is_bit_identical_to_plain_launches(dev):
+    """Small batches go through staging buffers and a CUDA graph of the whole forward (bseg_set_graph_batch_limit): the
+    first call runs eagerly, the second captures, later ones replay.  Same kernels in the same order: the results must be
+    bit-identical to a module that never uses graphs -- for both embedding types, the feature ensemble and the
+    query-half-only decoder, and with inputs that change between calls."""
+    from oracle.seggpt_ref import make_reference_model
+
+    hf = make_reference_model(seed=3, stress=True, num_layers=5, merge_index=1, intermediate=(1, 2, 3, 4))
+    plain = SegGptB200.from_hf(hf, device=dev, graph_batch=0)
+    graphed = SegGptB200.from_hf(hf, device=dev, graph_batch=4)
+    cases = [dict(embedding_type="instance"), dict(embedding_type="semantic"),
+             dict(feature_ensemble=True), dict(query_half_only=True)]
+    with torch.no_grad():
+        for kw in cases:
+            for call in range(4):  # eager, capture, replay, replay -- new inputs every time
+                px, ppx, pm = (t.to(dev) for t in synth.model_inputs(batch=2, seed=400 + call))
+                want = plain(pixel_values=px, prompt_pixel_values=ppx, prompt_masks=pm, **kw).pred_masks
+                got = graphed(pixel_values=px, prompt_pixel_values=ppx, prompt_masks=pm, **kw).pred_masks
+                assert torch.equal(got, want), (kw, call)
+        # a batch above the limit takes the plain path
+        px, ppx, pm = (t.to(dev) for t in synth.model_inputs(batch=5, seed=9))
+        assert torch.equal(graphed(pixel_values=px, prompt_pixel_values=ppx, prompt_masks=pm).pred_masks,
+                           plain(pixel_values=px, prompt_pixel_values=ppx, prompt_masks=pm).pred_masks)
