@@ -26,7 +26,7 @@ class LayerWeights(C.Structure):
 
 class Weights(C.Structure):
     _fields_ = [
-        ("num_layers", C.c_int), ("merge_index", C.c_int), ("intermediate_indices", C.c_int * 4),
+        ("image_size", C.c_int), ("num_layers", C.c_int), ("merge_index", C.c_int), ("intermediate_indices", C.c_int * 4),
         ("layer_norm_eps", C.c_float),
         ("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("mask_token", C.c_void_p),
         ("segment_token_input", C.c_void_p), ("segment_token_prompt", C.c_void_p),
@@ -93,6 +93,9 @@ SIGNATURES = {
     "bseg_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp]),
     "bseg_layernorm1024": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _ll, _f, _vp]),
     "bseg_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "bseg_attention_grid": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "bseg_relcat_rows": (_i, [_i, _i]),
+    "bseg_pack_relcat_grid": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "bseg_pack_relcat": (_i, [_vp, _vp, _vp, _vp]),
     "bseg_decoder_head": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "bseg_pack_conv_w9": (_i, [_vp, _vp, _vp]),

@@ -45,12 +45,14 @@ void ingest_geometry(int crop, int* band_out, int* max_rows_out) {
 // reversed + concatenated rel-pos tables, times 8 (see attention.cu): rows 0..110 = 8 rel_pos_h[110-i], 111 = 0,
 // rows 112..166 = 8 rel_pos_w[54-(i-112)], rest 0.  8 = 1 / head_dim^-0.5 (exact in bf16): the attention kernels take
 // qs = q * head_dim^-0.5 * log2(e), so qs . (8 rel) is the bias q . rel in the log2 domain.
+// General token grid gh x gw: rel_pos_h has 2 gh - 1 rows, padded to a multiple of 16 (rh_pad), rel_pos_w 2 gw - 1.
 __global__ void pack_relcat_kernel(const float* __restrict__ rel_h, const float* __restrict__ rel_w,
-                                   __nv_bfloat16* __restrict__ out) {
-  const int i = blockIdx.x, d = threadIdx.x;  // 176 x 64
+                                   __nv_bfloat16* __restrict__ out, int gh, int gw, int rh_pad) {
+  const int i = blockIdx.x, d = threadIdx.x;  // rows x 64
+  const int nh = 2 * gh - 1, nw = 2 * gw - 1;
   float v = 0.f;
-  if (i < 111) v = rel_h[(110 - i) * 64 + d];
-  else if (i >= 112 && i < 167) v = rel_w[(54 - (i - 112)) * 64 + d];
+  if (i < nh) v = rel_h[(nh - 1 - i) * 64 + d];
+  else if (i >= rh_pad && i < rh_pad + nw) v = rel_w[(nw - 1 - (i - rh_pad)) * 64 + d];
   out[i * 64 + d] = __float2bfloat16_rn(8.0f * v);
 }
 
@@ -84,11 +86,15 @@ __device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f
 __global__ void embed_table_kernel(const float* __restrict__ pos /*[197,1024]*/, const float* __restrict__ patch_b,
                                    const float* __restrict__ mask_token, const float* __restrict__ seg_in,
                                    const float* __restrict__ seg_pr, const float* __restrict__ type_tok,
-                                   float* __restrict__ tab) {
-  const int t = blockIdx.x;  // 0..1567
-  const int ph = t / 28, pw = t % 28;
+                                   float* __restrict__ tab, int gh, int gw) {
+  const int t = blockIdx.x;  // 0..T-1
+  const int T = gh * gw;
+  const int ph = t / gw, pw = t % gw;
   const float A = -0.75f;
-  const float ry = 0.25f * (ph + 0.5f) - 0.5f, rx = 0.5f * (pw + 0.5f) - 0.5f;
+  // F.interpolate(..., size=(gh, gw), mode="bicubic", align_corners=False) from the 14 x 14 pre-training grid:
+  // source coordinate = (dst + 0.5) * (14 / size) - 0.5   (0.25 and 0.5 for the 56 x 28 grid)
+  const float sy = 14.0f / static_cast<float>(gh), sx = 14.0f / static_cast<float>(gw);
+  const float ry = sy * (ph + 0.5f) - 0.5f, rx = sx * (pw + 0.5f) - 0.5f;
   const float fy = floorf(ry), fx = floorf(rx);
   const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
   const float ty = ry - fy, tx = rx - fx;
@@ -108,15 +114,17 @@ __global__ void embed_table_kernel(const float* __restrict__ pos /*[197,1024]*/,
       acc += cy[a] * row;
     }
     const float ty_ = type_tok[d];
-    tab[(0 * 1568 + t) * 1024 + d] = ((patch_b[d] + seg_in[d]) + acc) + ty_;
-    const float base1 = (ph < 28) ? patch_b[d] : mask_token[d];
-    tab[(1 * 1568 + t) * 1024 + d] = ((base1 + seg_pr[d]) + acc) + ty_;
+    tab[(0ll * T + t) * 1024 + d] = ((patch_b[d] + seg_in[d]) + acc) + ty_;
+    const float base1 = (ph < gh / 2) ? patch_b[d] : mask_token[d];
+    tab[(1ll * T + t) * 1024 + d] = ((base1 + seg_pr[d]) + acc) + ty_;
   }
 }
 
 }  // namespace
 
 struct bseg_handle {
+  // token grid of the stacked (prompt over query) image: 56 x 28 for the 448-px path, 64 x 32 for native 512-px tiles
+  int img = BSEG_IMG, gh = 56, gw = 28, T = BSEG_T, relcat_rows = 176;
   int num_layers = 0, merge_index = 0;
   int inter[4] = {0, 0, 0, 0};
   float eps = 1e-6f;
@@ -182,8 +190,17 @@ int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream_) {
   for (int j = 0; j < 4; ++j)
     BSEG_REQUIRE(w->intermediate_indices[j] >= w->merge_index && w->intermediate_indices[j] < w->num_layers,
                  "bseg_create: intermediate index %d out of range", w->intermediate_indices[j]);
+  const int img = w->image_size > 0 ? w->image_size : BSEG_IMG;
+  BSEG_REQUIRE(img == 448 || img == 512,
+               "bseg_create: image_size=%d is not built (448 = the resized path, 512 = native 512-px tiles)", img);
   bseg_handle* h = new (std::nothrow) bseg_handle();
   BSEG_REQUIRE(h != nullptr, "bseg_create: out of host memory");
+  h->img = img;
+  h->gw = img / 16;
+  h->gh = 2 * h->gw;
+  h->T = h->gh * h->gw;
+  h->relcat_rows = attention_relcat_rows(h->gh, h->gw);
+  const int kT = h->T;  // (shadows the 448-path constant in this function)
   h->num_layers = w->num_layers;
   h->merge_index = w->merge_index;
   for (int j = 0; j < 4; ++j) h->inter[j] = w->intermediate_indices[j];
@@ -206,7 +223,7 @@ int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream_) {
     lo[i].proj_w = carve(1024ull * 1024 * 2);
     lo[i].lin1_w = carve(4096ull * 1024 * 2);
     lo[i].lin2_w = carve(1024ull * 4096 * 2);
-    lo[i].relcat = carve(176ull * 64 * 2);
+    lo[i].relcat = carve(static_cast<size_t>(h->relcat_rows) * 64 * 2);
     lo[i].qkv_b = carve(3072 * 4);
     lo[i].proj_b = carve(1024 * 4);
     lo[i].lin1_b = carve(4096 * 4);
@@ -249,10 +266,10 @@ int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream_) {
   h->embed_tab[1] = fp(o_tab1);
   embed_table_kernel<<<kT, 256, 0, stream>>>(w->position_embeddings, w->patch_b, w->mask_token,
                                              w->segment_token_input, w->segment_token_prompt,
-                                             w->type_token_instance, h->embed_tab[0]);
+                                             w->type_token_instance, h->embed_tab[0], h->gh, h->gw);
   embed_table_kernel<<<kT, 256, 0, stream>>>(w->position_embeddings, w->patch_b, w->mask_token,
                                              w->segment_token_input, w->segment_token_prompt,
-                                             w->type_token_semantic, h->embed_tab[1]);
+                                             w->type_token_semantic, h->embed_tab[1], h->gh, h->gw);
   for (int i = 0; i < w->num_layers; ++i) {
     const bseg_layer_weights& lw = w->layers[i];
     LayerPack& lp = h->layers[i];
@@ -261,7 +278,8 @@ int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream_) {
     lp.lin1_w = bf(lo[i].lin1_w); cvt(lw.lin1_w, lp.lin1_w, 4096ll * 1024);
     lp.lin2_w = bf(lo[i].lin2_w); cvt(lw.lin2_w, lp.lin2_w, 1024ll * 4096);
     lp.relcat = bf(lo[i].relcat);
-    pack_relcat_kernel<<<176, 64, 0, stream>>>(lw.rel_pos_h, lw.rel_pos_w, lp.relcat);
+    pack_relcat_kernel<<<h->relcat_rows, 64, 0, stream>>>(lw.rel_pos_h, lw.rel_pos_w, lp.relcat, h->gh, h->gw,
+                                                          (2 * h->gh - 1 + 15) / 16 * 16);
     lp.qkv_b = fp(lo[i].qkv_b);   cpy(lw.qkv_b, lp.qkv_b, 3072);
     lp.proj_b = fp(lo[i].proj_b); cpy(lw.proj_b, lp.proj_b, 1024);
     lp.lin1_b = fp(lo[i].lin1_b); cpy(lw.lin1_b, lp.lin1_b, 4096);
@@ -302,9 +320,9 @@ namespace {
 struct WsLayout {
   size_t h, xn, att, q, k, vt, mlp, inter, dec, total;
 };
-WsLayout ws_layout(int B) {
+WsLayout ws_layout(int B, int T = kT) {
   WsLayout L;
-  const size_t rows2 = 2ull * B * kT, rows1 = 1ull * B * kT;
+  const size_t rows2 = 2ull * B * T, rows1 = 1ull * B * T;
   size_t off = 0;
   auto carve = [&](size_t bytes) {
     size_t o = off;
@@ -405,9 +423,11 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
                  const float* prompt_masks, int B, int embedding_type, int P, const FwdBufs& fb, float* pred_masks,
                  cudaStream_t stream, bool query_half_only = false) {
   int rc;
+  const int kT = h->T;  // tokens of the stacked image (shadows the 448-path constant: 1568, or 2048 for native 512-px tiles)
   // ---- embeddings: patchify + GEMM (modeling_seggpt.py:713-737, 163-206) ----
   __nv_bfloat16* a_patch = fb.mlp;
-  if ((rc = launch_patchify(pixel_values, prompt_pixel_values, prompt_masks, nullptr, a_patch, B, stream))) return rc;
+  if ((rc = launch_patchify(pixel_values, prompt_pixel_values, prompt_masks, nullptr, a_patch, B, h->img, stream)))
+    return rc;
   {
     GemmEpiParams ep;
     ep.out = fb.h_emb;
@@ -435,7 +455,7 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
       ep.q_scale = kQScale;  // q is kept as bf16(q * head_dim^-0.5 * log2 e): the score lands in the log2 domain
       if ((rc = launch_gemm(EPI_QKV, fb.xn, kD, lp.qkv_w, M, 3 * kD, kD, ep, stream))) return rc;
     }
-    if ((rc = launch_attention(pl.q, pl.k, pl.vt, lp.relcat, pl.att, pl.lse, nseq, BSEG_HEADS, 56, 28, stream)))
+    if ((rc = launch_attention(pl.q, pl.k, pl.vt, lp.relcat, pl.att, pl.lse, nseq, BSEG_HEADS, h->gh, h->gw, stream)))
       return rc;
     bool ens = false;
     if (P > 0) ens = (i == h->merge_index) ? true : (P >= 2);
@@ -477,15 +497,15 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
   // query_half_only: the reference's predict / loss code reads pred_masks[:, :, 448:] only (src/model.py:158-160,48-57).
   // The conv3x3 at image row 448 needs row 447, so decoder_embed runs from token row 27 (tokens 756..1567) and the head
   // from image row 448; pred_masks rows < 448 are zero-filled.
-  const int kTok0 = query_half_only ? 27 * 28 : 0;
+  const int kTok0 = query_half_only ? (h->gh / 2 - 1) * h->gw : 0;
   {
     GemmEpiParams ep;
-    ep.out = fb.dec; ep.bias = h->dec_embed_b; ep.T = kT; ep.grid_w = 28;
+    ep.out = fb.dec; ep.bias = h->dec_embed_b; ep.T = kT; ep.grid_w = h->gw;
     GemmRows gr{kT, B, kTok0, kT - kTok0};
     if ((rc = launch_gemm_rows(EPI_PIXSHUF, fb.inter, 4 * kD, h->dec_embed_w, gr, kDecN, 4 * kD, ep, stream))) return rc;
   }
   if (query_half_only) {
-    const size_t plane = 896ull * 448, half = 448ull * 448;
+    const size_t plane = 2ull * h->img * h->img, half = static_cast<size_t>(h->img) * h->img;
     for (int b = 0; b < B; ++b)
       for (int c = 0; c < 3; ++c) {
         cudaError_t ce = cudaMemsetAsync(pred_masks + (static_cast<size_t>(b) * 3 + c) * plane, 0, half * 4, stream);
@@ -496,7 +516,7 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
       }
   }
   return launch_decoder_head(fb.dec, h->conv_w9, h->conv_b, h->dec_ln_w, h->dec_ln_b, h->head_w, h->head_b, pred_masks,
-                             B, 896, 448, h->eps, query_half_only ? 448 : 0, stream);
+                             B, 2 * h->img, h->img, h->eps, query_half_only ? h->img : 0, stream);
 }
 
 int check_forward_args(bseg_handle* h, int batch, int embedding_type, const void* workspace, const char* who) {
@@ -524,9 +544,9 @@ FwdBufs train_bufs(bseg_handle* h, const TrainLayout& L, uint8_t* ws) {
 }
 }  // namespace
 
-size_t bseg_workspace_bytes(const bseg_handle* /*h*/, int batch) {
+size_t bseg_workspace_bytes(const bseg_handle* h, int batch) {
   if (batch <= 0) return 0;
-  return ws_layout(batch).total;
+  return ws_layout(batch, h ? h->T : kT).total;
 }
 
 size_t bseg_train_workspace_bytes(const bseg_handle* h, int batch) {
@@ -537,7 +557,7 @@ size_t bseg_train_workspace_bytes(const bseg_handle* h, int batch) {
 static int forward_eager(bool query_half_only, bseg_handle* h, const float* pixel_values,
                          const float* prompt_pixel_values, const float* prompt_masks, int batch, int embedding_type,
                          int ensemble_prompts, void* workspace, float* pred_masks, cudaStream_t stream) {
-  const WsLayout L = ws_layout(batch);
+  const WsLayout L = ws_layout(batch, h->T);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(ws + o); };
   FwdBufs fb;
@@ -556,7 +576,7 @@ static int forward_entry(bool query_half_only, bseg_handle* h, const float* pixe
   if (rc) return rc;
   BSEG_REQUIRE(ensemble_prompts >= 0 && (ensemble_prompts == 0 || batch % ensemble_prompts == 0),
                "bseg_forward: batch=%d is not a multiple of ensemble_prompts=%d", batch, ensemble_prompts);
-  const WsLayout L = ws_layout(batch);
+  const WsLayout L = ws_layout(batch, h->T);
   BSEG_REQUIRE(workspace_bytes >= L.total, "bseg_forward: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   auto eager = [&]() {
     return forward_eager(query_half_only, h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type,
@@ -635,6 +655,7 @@ int bseg_forward_query_half(bseg_handle* h, const float* pixel_values, const flo
 int bseg_enable_fp32(bseg_handle* h, const bseg_weights* w, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BSEG_REQUIRE(h != nullptr && w != nullptr, "bseg_enable_fp32: null argument");
+  BSEG_REQUIRE(h->img == BSEG_IMG, "bseg_enable_fp32: the fp32 accuracy mode is built for the 448-px path only");
   BSEG_REQUIRE(w->num_layers == h->num_layers, "bseg_enable_fp32: weights have %d layers, the handle %d", w->num_layers,
                h->num_layers);
   if (h->f32_arena != nullptr) return 0;
@@ -719,6 +740,8 @@ int bseg_forward_f32(bseg_handle* h, const float* pixel_values, const float* pro
 int bseg_train_prepare(bseg_handle* h, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BSEG_REQUIRE(h != nullptr, "bseg_train_prepare: null handle");
+  BSEG_REQUIRE(h->img == BSEG_IMG, "bseg_train_prepare: the train step is built for the 448-px path only (the native-"
+               "resolution mode is inference-only)");
   if (h->train_arena != nullptr) return 0;
   size_t off = 0;
   auto carve = [&](size_t bytes) {
@@ -1083,6 +1106,14 @@ int bseg_attention_fwd_lse(const void* q, const void* k, const void* vt, const v
                           static_cast<cudaStream_t>(stream));
 }
 
+int bseg_attention_grid(const void* q, const void* k, const void* vt, const void* relcat, void* out, float* lse,
+                        int nseq, int grid_h, int grid_w, void* stream) {
+  return launch_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
+                          static_cast<const __nv_bfloat16*>(vt), static_cast<const __nv_bfloat16*>(relcat),
+                          static_cast<__nv_bfloat16*>(out), lse, nseq, BSEG_HEADS, grid_h, grid_w,
+                          static_cast<cudaStream_t>(stream));
+}
+
 size_t bseg_attention_bwd_scratch_bytes(int nseq) {
   if (nseq <= 0) return 0;
   const size_t rows = static_cast<size_t>(nseq) * kT;
@@ -1161,8 +1192,16 @@ int bseg_decoder_head_bwd(const void* x_nhwc, const void* w9, const void* w9b, c
 }
 
 int bseg_pack_relcat(const float* rel_pos_h, const float* rel_pos_w, void* relcat, void* stream) {
-  pack_relcat_kernel<<<176, 64, 0, static_cast<cudaStream_t>(stream)>>>(rel_pos_h, rel_pos_w,
-                                                                        static_cast<__nv_bfloat16*>(relcat));
+  return bseg_pack_relcat_grid(rel_pos_h, rel_pos_w, relcat, 56, 28, stream);
+}
+
+int bseg_relcat_rows(int grid_h, int grid_w) { return attention_relcat_rows(grid_h, grid_w); }
+
+int bseg_pack_relcat_grid(const float* rel_pos_h, const float* rel_pos_w, void* relcat, int grid_h, int grid_w,
+                          void* stream) {
+  BSEG_REQUIRE(grid_h > 0 && grid_w > 0, "pack_relcat: empty token grid");
+  pack_relcat_kernel<<<attention_relcat_rows(grid_h, grid_w), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      rel_pos_h, rel_pos_w, static_cast<__nv_bfloat16*>(relcat), grid_h, grid_w, (2 * grid_h - 1 + 15) / 16 * 16);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

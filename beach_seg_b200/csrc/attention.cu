@@ -50,59 +50,64 @@ namespace bseg {
 #define BSEG_ATTN_SKIP_EXP 0
 #endif
 
-#define BSEG_ATTN_WG 1
+// Token grid GH x GW of the stacked (prompt over query) image and ROWS token rows per key block:
+//   56 x 28, 4 rows  (896 x 448 px: the resized path, T = 1568, key blocks of 112)
+//   64 x 32, 2 rows  (1024 x 512 px: native 512-px tiles, SURVEY 8(f) rank 4, T = 2048, key blocks of 64)
+template <int GH, int GW, int ROWS>
+struct AttnCfg {
+  static constexpr int kQTile = 128;            // queries per CTA
+  static constexpr int kGridW = GW;
+  static constexpr int kGridH = GH;
+  static constexpr int kRowsPerKB = ROWS;       // token rows per key block
+  static constexpr int kKB = ROWS * GW;         // keys per block: 112 | 64
+  static constexpr int kT = GW * GH;            // 1568 | 2048
+  static constexpr int kNumKB = kT / kKB;       // 14 | 32
+  static constexpr int kStages = 2;
+  static constexpr int kThreads = 256;
+  static constexpr int kCtasPerSm = 2;
+  static constexpr int kRegsControl = 40;
+  static constexpr int kRegsSoftmax = 216;      // 2 * (128*40 + 128*216) = 65536
+  static constexpr int kRelH = (2 * GH - 1 + 15) / 16 * 16;  // rows of the reversed rel_pos_h table: 111 -> 112 | 127 -> 128
+  static constexpr int kRelW = (2 * GW - 1 + 15) / 16 * 16;  // rows of the reversed rel_pos_w table: 55 -> 64 | 63 -> 64
+  static constexpr int kRelRows = kRelH + kRelW;             // 176 | 192
+  static_assert(GW <= 32 && GW % 2 == 0 && ROWS <= 4 && kKB % 16 == 0 && kT % kKB == 0 && kRelRows <= 256, "token grid");
+
+  static constexpr int kQBytes = kQTile * 128;                  // 16384
+  static constexpr int kKBytes = kKB * 128;                     // 14336 | 8192
+  static constexpr int kVHalves = (kKB + 63) / 64;              // V^T arrives in 64-key halves: 2 | 1
+  static constexpr int kVBytes = kVHalves * 64 * 128;           // 16384 | 8192
+  static constexpr int kRelBytes = kRelRows * 128;              // 22528 | 24576
+  static constexpr int kOneHotBytes = kKB * 128;                // one-hot B operand [keys][64 fp16], 48 columns used
+  static constexpr int kBhStride = GH / 2 + 2;                  // 32-bit words per row of the packed height-bias table (30 | 34)
+  static constexpr int kBhBytes = kQTile * kBhStride * 4;
+  static constexpr int kBwStride = GW + 1;
+  static constexpr int kBwBytes = kQTile * kBwStride * 4;       // staging of the per-query width bias in the prologue
+
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = kOffQ + kQBytes;
+  static constexpr int kOffV = kOffK + kStages * kKBytes;
+  static constexpr int kOffOneHot = kOffV + kStages * kVBytes;
+  static constexpr int kOffBh = kOffOneHot + kOneHotBytes;
+  // the rel tables, then the bw staging, overlay the (not yet used) K and V stages
+  static constexpr int kOffRel = kOffK;
+  static_assert(kRelBytes <= kStages * (kKBytes + kVBytes) && kBwBytes <= kStages * (kKBytes + kVBytes),
+                "rel overlay does not fit in the K / V stages");
+  static constexpr int kOffBar = (kOffBh + kBhBytes + 1023) / 1024 * 1024;
+  static constexpr int kSmemBytes = kOffBar + 256 + 1024;
+  static_assert(kOffK % 1024 == 0 && kOffV % 1024 == 0 && kOffOneHot % 1024 == 0 && kKBytes % 1024 == 0, "swizzle alignment");
+  static_assert(kSmemBytes * kCtasPerSm + 1024 * kCtasPerSm <= 228 * 1024, "shared memory budget");
+
+  // TMEM columns (256 per CTA): S [0,KB)  O [KB,KB+64)  P (bf16 pairs, KB/2)  Ew 16  Eh 8 (fp16 pairs);
+  // G = Qs relcat8^T (kRelRows columns) overlays them in the prologue
+  static constexpr uint32_t kTmemCols = 256;
+  static constexpr uint32_t kColO = kKB;
+  static constexpr uint32_t kColP = kColO + 64;
+  static constexpr uint32_t kColEw = kColP + kKB / 2;
+  static constexpr uint32_t kColEh = kColEw + 16;
+  static_assert(kColEh + 8 <= kTmemCols, "TMEM budget");
+};
 
 namespace attn {
-constexpr int kWG = BSEG_ATTN_WG;      // softmax warpgroups (query tiles) per CTA
-constexpr int kQTile = 128;            // queries per softmax warpgroup
-constexpr int kCtaQ = kWG * kQTile;
-constexpr int kGridW = 28;
-constexpr int kGridH = 56;
-constexpr int kRowsPerKB = 4;          // token rows per key block
-constexpr int kKB = kRowsPerKB * kGridW;  // 112 keys per block
-constexpr int kT = kGridW * kGridH;    // 1568
-constexpr int kNumKB = kT / kKB;       // 14
-constexpr int kStages = kWG == 2 ? 3 : 2;
-constexpr int kThreads = 128 + kWG * 128;  // 384 | 256
-constexpr int kCtasPerSm = kWG == 2 ? 1 : 2;
-constexpr int kRegsControl = kWG == 2 ? 56 : 40;
-constexpr int kRegsSoftmax = kWG == 2 ? 224 : 216;  // 128*56 + 256*224 = 64512 | 2 * (128*40 + 128*216) = 65536
-constexpr int kRelRows = 176;  // 112 (reversed rel_pos_h, 111 used) + 64 (reversed rel_pos_w, 55 used)
-
-constexpr int kQBytes = kQTile * 128;        // 16384
-constexpr int kKBytes = kKB * 128;           // 14336
-constexpr int kVBytes = 2 * 64 * 128;        // 16384 (two 64-key halves)
-constexpr int kRelBytes = kRelRows * 128;    // 22528
-constexpr int kOneHotBytes = kKB * 128;      // 14336: one-hot B operand [112 keys][64 fp16], 48 columns used
-constexpr int kBhStride = 30;                // 32-bit words per row of the packed height-bias table (15 x uint2: LDS.64
-                                             // of 16 consecutive rows hits 32 distinct banks)
-constexpr int kBhBytes = kQTile * kBhStride * 4;   // 15360
-constexpr int kBwStride = 29;
-constexpr int kBwBytes = kQTile * kBwStride * 4;   // staging of the per-query width bias in the prologue
-
-constexpr int kOffQ = 0;
-constexpr int kOffK = kOffQ + kWG * kQBytes;
-constexpr int kOffV = kOffK + kStages * kKBytes;
-constexpr int kOffOneHot = kOffV + kStages * kVBytes;
-constexpr int kOffBh = kOffOneHot + kOneHotBytes;
-// the rel tables, then the bw staging, overlay the (not yet used) V stages
-constexpr int kOffRel = kOffV;
-static_assert(kRelBytes <= kStages * kVBytes && kWG * kBwBytes <= kStages * kVBytes,
-              "rel overlay does not fit in the V stages");
-constexpr int kOffBar = (kOffBh + kWG * kBhBytes + 1023) / 1024 * 1024;
-constexpr int kSmemBytes = kOffBar + 256 + 1024;
-static_assert(kOffK % 1024 == 0 && kOffV % 1024 == 0 && kOffOneHot % 1024 == 0 && kKBytes % 1024 == 0, "swizzle alignment");
-static_assert(kSmemBytes * kCtasPerSm + 1024 * kCtasPerSm <= 228 * 1024, "shared memory budget");
-
-// TMEM columns (256 per warpgroup): S [0,112)  O [112,176)  P [176,232) (bf16 pairs)  Ew [232,248)  Eh [248,256) (fp16
-// pairs); G = Qs relcat8^T (176 columns) overlays S and O in the prologue
-constexpr uint32_t kColsPerWG = 256;
-constexpr uint32_t kTmemCols = kColsPerWG * kWG;
-constexpr uint32_t kColO = 112;
-constexpr uint32_t kColP = 176;
-constexpr uint32_t kColEw = 232;
-constexpr uint32_t kColEh = 248;
-
 constexpr float kRaiseThreshold = 65536.0f;     // raise the reference when a block's row sum exceeds 2^16
 constexpr float kOverflowGuard = 1.0e30f;       // redo a half block whose row sum exceeds this (or is inf / nan)
 constexpr float kMaxEncodedRef = 32768.0f;      // |m| that fp16 holds exactly in steps of 16
@@ -143,41 +148,86 @@ __device__ __forceinline__ void tmem_st4u(uint32_t taddr, uint32_t r0, uint32_t 
 }
 // smallest multiple of 16 that is >= x (as a float)
 __device__ __forceinline__ float ceil16(float x) { return 16.0f * ceilf(x * 0.0625f); }
+// exponentiate columns [C0, C1) of a score row (kAdjust adds the -- rare -- reference correction per element): P as
+// bf16 pairs, partial row sums in ls[4]
+template <bool kAdjust, int C0, int C1, int KB>
+__device__ __forceinline__ void exp_cols(const float (&x)[KB], float delta, float (&ls)[4], uint32_t (&pk)[KB / 2]) {
+#pragma unroll
+  for (int i = C0; i < C1; i += 4) {
+    float x0 = x[i], x1 = x[i + 1], x2 = x[i + 2], x3 = x[i + 3];
+    if (kAdjust) {
+      x0 += delta; x1 += delta; x2 += delta; x3 += delta;
+    }
+    const float p0 = BSEG_ATTN_SKIP_EXP ? x0 * 0.001f : ex2_approx(x0);
+    const float p1 = BSEG_ATTN_SKIP_EXP ? x1 * 0.001f : ex2_approx(x1);
+    const float p2 = BSEG_ATTN_SKIP_EXP ? x2 * 0.001f : ex2_approx(x2);
+    const float p3 = BSEG_ATTN_SKIP_EXP ? x3 * 0.001f : ex2_approx(x3);
+    add_f32x2(ls[0], ls[1], p0, p1);
+    add_f32x2(ls[2], ls[3], p2, p3);
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+  }
+}
+template <int KB>
+__device__ __forceinline__ float row_max(const float (&x)[KB]) {
+  float mx = x[0];
+#pragma unroll
+  for (int i = 1; i < KB; ++i) mx = fmaxf(mx, x[i]);
+  return mx;
+}
+// packed fp16 height bias of key block kb from a row of the table: ROWS values (two words for 4 rows, one for 2)
+template <int ROWS>
+__device__ __forceinline__ void bh_block(const uint32_t* bh_row, int kb, uint32_t& w0, uint32_t& w1) {
+  static_assert(ROWS == 4 || ROWS == 2, "token rows per key block");
+  if (ROWS == 4) {
+    const uint2 g = *reinterpret_cast<const uint2*>(bh_row + 2 * kb);
+    w0 = g.x;
+    w1 = g.y;
+  } else {
+    w0 = bh_row[kb];
+    w1 = 0u;
+  }
+}
 }  // namespace
 
-__global__ void __launch_bounds__(attn::kThreads, attn::kCtasPerSm)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kCtasPerSm)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_vt, const __grid_constant__ CUtensorMap tmap_rel,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, int heads) {
   using namespace attn;
+  constexpr int kQTile = Cfg::kQTile, kGridW = Cfg::kGridW, kGridH = Cfg::kGridH, kRows = Cfg::kRowsPerKB;
+  constexpr int kKB = Cfg::kKB, kT = Cfg::kT, kNumKB = Cfg::kNumKB, kStages = Cfg::kStages;
+  constexpr int kRelH = Cfg::kRelH, kRelW = Cfg::kRelW, kRelRows = Cfg::kRelRows;
+  constexpr int kKBytes = Cfg::kKBytes, kVBytes = Cfg::kVBytes;
+  constexpr uint32_t kColO = Cfg::kColO, kColP = Cfg::kColP, kColEw = Cfg::kColEw, kColEh = Cfg::kColEh;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + kOffQ;
-  uint8_t* sK = smem + kOffK;
-  uint8_t* sV = smem + kOffV;
-  uint8_t* sRel = smem + kOffRel;
-  uint8_t* sOneHot = smem + kOffOneHot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint8_t* sQ = smem + Cfg::kOffQ;
+  uint8_t* sK = smem + Cfg::kOffK;
+  uint8_t* sV = smem + Cfg::kOffV;
+  uint8_t* sRel = smem + Cfg::kOffRel;
+  uint8_t* sOneHot = smem + Cfg::kOffOneHot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* g_full = bars + 1;
-  uint64_t* k_full = bars + 2;     // [3]
-  uint64_t* k_empty = bars + 5;    // [3]
-  uint64_t* v_full = bars + 8;     // [3]
-  uint64_t* v_empty = bars + 11;   // [3]
-  uint64_t* s_full = bars + 14;    // [kWG]     MMA -> softmax: S_j is in TMEM
-  uint64_t* s_free = bars + 18;    // [kWG]     softmax -> MMA: the S region may be overwritten (and Eh is set)
-  uint64_t* p_full = bars + 22;    // [kWG]     softmax -> MMA: P_j is in TMEM (and O rescaled if it had to be)
-  uint64_t* pv_done = bars + 24;   // [kWG]     MMA -> softmax: O += P_j V_j retired (P region free, O stable)
-  uint64_t* rel_free = bars + 26;  // softmax -> TMA: the rel / bw staging region is dead (it overlays the V stages)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* v_full = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;    // [2]
+  uint64_t* s_full = bars + 10;    // MMA -> softmax: S_j is in TMEM
+  uint64_t* s_free = bars + 11;    // softmax -> MMA: the S region may be overwritten (and Eh is set)
+  uint64_t* p_full = bars + 12;    // softmax -> MMA: P_j is in TMEM (and O rescaled if it had to be)
+  uint64_t* pv_done = bars + 13;   // MMA -> softmax: O += P_j V_j retired (P region free, O stable)
+  uint64_t* rel_free = bars + 14;  // softmax -> TMA: the rel / bw staging region is dead (it overlays the K / V stages)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kCtaQ;
+  const int q0 = blockIdx.x * kQTile;
   const int head = blockIdx.y;
   const int seq = blockIdx.z;
   const int sh = seq * heads + head;
-  const int n_active = (kWG == 2 && q0 + kQTile < kT) ? 2 : 1;  // the last tile of a sequence has one live warpgroup
 #ifdef BSEG_ATTN_TRACE
   const bool trace_cta = blockIdx.x == 2 && blockIdx.y == 5 && blockIdx.z == gridDim.z / 2;
 #endif
@@ -188,26 +238,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_prefetch_desc(&tmap_vt);
     tma_prefetch_desc(&tmap_rel);
     mbar_init(q_full, 1);
-    mbar_init(g_full, n_active);         // one commit per MMA issuer
-    mbar_init(rel_free, 4 * n_active);   // one arrive per live softmax warp
+    mbar_init(g_full, 1);
+    mbar_init(rel_free, 4);   // one arrive per softmax warp
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], n_active);  // a stage is free once every live warpgroup's MMAs on it have retired
+      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], n_active);
+      mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < kWG; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);   // one arrive per softmax warp
-      mbar_init(&p_full[i], 4);
-      mbar_init(&pv_done[i], 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);     // one arrive per softmax warp
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   // One-hot B operand of the bias MMAs, K-major rows of 128 B with the 128-byte swizzle: row n = key n of a block,
-  // fp16 columns 0..27 = [n % 28 == column], 32..35 = [n / 28 == column - 32], 36 = 1 (the -m column), rest 0.
-  for (int idx = threadIdx.x; idx < kKB * 8; idx += kThreads) {
+  // fp16 columns 0..GW-1 = [n % GW == column], 32..32+ROWS-1 = [n / GW == column - 32], 36 = 1 (the -m column), rest 0.
+  for (int idx = threadIdx.x; idx < kKB * 8; idx += Cfg::kThreads) {
     const int n = idx >> 3, c = idx & 7;
     const int kw = n % kGridW, j = n / kGridW;
     uint32_t w[4];
@@ -217,7 +265,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int col = 8 * c + 2 * e + hf;
-        const bool one = (col < kGridW) ? (col == kw) : (col >= 32 && col < 36) ? (col - 32 == j) : (col == 36);
+        const bool one = (col < 32) ? (col < kGridW && col == kw) : (col < 36) ? (col - 32 == j) : (col == 36);
         if (one) pair |= 0x3C00u << (16 * hf);
       }
       w[e] = pair;
@@ -231,15 +279,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kRegsControl));
     if (warp == 0) {
       // ============================ TMA producer (warp-uniform loop, one elected lane issues) ============================
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(q_full, n_active * kQBytes + kRelBytes);
-        for (int w = 0; w < n_active; ++w) tma_load_3d(sQ + w * kQBytes, &tmap_q, q_full, 0, q0 + w * kQTile, sh);
+        mbar_arrive_expect_tx(q_full, Cfg::kQBytes + Cfg::kRelBytes);
+        tma_load_3d(sQ, &tmap_q, q_full, 0, q0, sh);
         tma_load_2d(sRel, &tmap_rel, q_full, 0, 0);
       }
       __syncwarp();
+      mbar_wait(rel_free, 0);  // the rel tables / bw staging overlay the K and V stages
       for (int kb = 0; kb < kNumKB; ++kb) {
         const int st = kb % kStages;
         if (kb >= kStages) mbar_wait(&k_empty[st], ((kb / kStages) & 1) ^ 1);
@@ -249,28 +298,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         __syncwarp();
         if (kb >= kStages) mbar_wait(&v_empty[st], ((kb / kStages) & 1) ^ 1);
-        if (kb == 0) mbar_wait(rel_free, 0);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&v_full[st], kVBytes);
-          tma_load_3d(sV + st * kVBytes, &tmap_vt, &v_full[st], kb * kKB, 0, sh);
-          tma_load_3d(sV + st * kVBytes + 8192, &tmap_vt, &v_full[st], kb * kKB + 64, 0, sh);
+#pragma unroll
+          for (int hv = 0; hv < Cfg::kVHalves; ++hv)
+            tma_load_3d(sV + st * kVBytes + hv * 8192, &tmap_vt, &v_full[st], kb * kKB + hv * 64, 0, sh);
         }
         __syncwarp();
       }
-    } else if (warp - 1 < n_active) {
-      // ============================ MMA issuers: warp 1 -> warpgroup 0, warp 2 -> warpgroup 1 ============================
-      // One issuing warp per softmax warpgroup, blocking on that warpgroup's barriers in the order in which the
-      // warpgroup arrives on them, so neither warpgroup ever waits for the other's turn.  The whole warp runs the
-      // (warp-uniform) loop and one elected lane issues, which keeps every tcgen05.mma operand in uniform registers.
-      const int w = warp - 1;
+    } else if (warp == 1) {
+      // ============================ MMA issuer ============================
+      // The whole warp runs the (warp-uniform) loop and one elected lane issues, which keeps every tcgen05.mma operand
+      // in uniform registers.
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
       constexpr uint32_t idesc_e = umma_idesc_f16(128, kKB);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
-      const uint32_t q_addr = smem_u32(sQ) + w * kQBytes;
+      const uint32_t q_addr = smem_u32(sQ);
       const uint32_t rel_addr = smem_u32(sRel);
       const uint32_t onehot_addr = smem_u32(sOneHot);
-      const uint32_t tm = tmem_base + w * kColsPerWG;
+      const uint32_t tm = tmem_base;
 
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -286,10 +333,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       auto issue_s = [&](int kb) {
         const int st = kb % kStages;
         mbar_wait(&k_full[st], (kb / kStages) & 1);
-        if (w == 0) ATTN_TRACE(2, kb, 0);  // K block in smem
+        ATTN_TRACE(2, kb, 0);  // K block in smem
         const uint32_t k_addr = smem_u32(sK + st * kKBytes);
-        mbar_wait(&s_free[w], kb & 1);
-        if (w == 0) ATTN_TRACE(2, kb, 1);  // S free -> issue
+        mbar_wait(s_free, kb & 1);
+        ATTN_TRACE(2, kb, 1);  // S free -> issue
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
@@ -300,7 +347,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
           for (int k = 0; k < 3; ++k)
             umma_bf16_ts(tm, tm + kColEw + k * 8, umma_desc_sw128_kmajor(onehot_addr + k * 32), idesc_e, 1u);
-          umma_commit(&s_full[w]);
+          umma_commit(s_full);
           umma_commit(&k_empty[st]);
         }
         __syncwarp();
@@ -311,9 +358,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (kb + 1 < kNumKB) issue_s(kb + 1);
         const int st = kb % kStages;
         mbar_wait(&v_full[st], (kb / kStages) & 1);
-        if (w == 0) ATTN_TRACE(2, kb, 3);  // V block in smem
-        mbar_wait(&p_full[w], kb & 1);
-        if (w == 0) ATTN_TRACE(2, kb, 4);  // P full -> issue PV
+        ATTN_TRACE(2, kb, 3);  // V block in smem
+        mbar_wait(p_full, kb & 1);
+        ATTN_TRACE(2, kb, 4);  // P full -> issue PV
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t v_addr = smem_u32(sV + st * kVBytes);
@@ -322,35 +369,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t va = v_addr + (k >> 2) * 8192 + (k & 3) * 32;
             umma_bf16_ts(tm + kColO, tm + kColP + k * 8, umma_desc_sw128_kmajor(va), idesc_o, (kb | k) != 0);
           }
-          umma_commit(&pv_done[w]);
+          umma_commit(pv_done);
           umma_commit(&v_empty[st]);
         }
         __syncwarp();
       }
     }
   } else {
-    // ============================ softmax warpgroups ============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
-    const int w = (warp - 4) >> 2;
-    if (w < n_active) {
+    // ============================ softmax warpgroup ============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kRegsSoftmax));
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // query row in the warpgroup tile == TMEM lane
-    const int qi_raw = q0 + w * kQTile + r;
+    const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
+    const int qi_raw = q0 + r;
     const bool valid = qi_raw < kT;
     const int qi = valid ? qi_raw : kT - 1;
     const int qh = qi / kGridW, qw = qi % kGridW;
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * kColsPerWG;
-    uint32_t* bh_row = reinterpret_cast<uint32_t*>(smem + kOffBh + w * kBhBytes) + r * kBhStride;
-    float* stage = reinterpret_cast<float*>(sRel + w * kBwBytes) + r * kBwStride;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t* bh_row = reinterpret_cast<uint32_t*>(smem + Cfg::kOffBh) + r * Cfg::kBhStride;
+    float* stage = reinterpret_cast<float*>(sRel) + r * Cfg::kBwStride;
 
     // ---- prologue: decomposed rel-pos bias of this query (log2 domain), as fp16 MMA operands ----
-    mbar_wait(g_full, 0);  // every issuer's G MMAs have retired: the rel tables in smem are dead, G is in TMEM
+    mbar_wait(g_full, 0);  // the G MMAs have retired: the rel tables in smem are dead, G is in TMEM
     tc_fence_after();
     {
-      const int off_h = 55 - qh;  // bh[kh] = G[off_h + kh]
+      const int off_h = (kGridH - 1) - qh;  // bh[kh] = G[off_h + kh]
       __half* bh_half = reinterpret_cast<__half*>(bh_row);
 #pragma unroll
-      for (int c = 0; c < 112; c += 16) {
+      for (int c = 0; c < kRelH; c += 16) {
         float v[16];
         tmem_ld16(lane_base + c, v);
         tmem_ld_wait();
@@ -360,11 +405,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           if (kh >= 0 && kh < kGridH) bh_half[kh] = __float2half_rn(v[i]);
         }
       }
-      const int off_w = 27 - qw;  // bw[kw] = G[112 + off_w + kw]
+      const int off_w = (kGridW - 1) - qw;  // bw[kw] = G[kRelH + off_w + kw]
 #pragma unroll
-      for (int c = 0; c < 64; c += 16) {
+      for (int c = 0; c < kRelW; c += 16) {
         float v[16];
-        tmem_ld16(lane_base + 112 + c, v);
+        tmem_ld16(lane_base + kRelH + c, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -376,22 +421,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     {
       uint32_t ew[16];
 #pragma unroll
-      for (int i = 0; i < kGridW / 2; ++i) ew[i] = pack_f16x2(stage[2 * i], stage[2 * i + 1]);
-      ew[14] = 0u;
-      ew[15] = 0u;
+      for (int i = 0; i < 16; ++i) ew[i] = (2 * i < kGridW) ? pack_f16x2(stage[2 * i], stage[2 * i + 1]) : 0u;
       tmem_st16u(lane_base + kColEw, ew);
-      const uint2 g0 = *reinterpret_cast<const uint2*>(bh_row);
-      tmem_st4u(lane_base + kColEh, g0.x, g0.y, 0u, 0u);       // height bias of key block 0, -m = 0
+      uint32_t g0, g1;
+      bh_block<kRows>(bh_row, 0, g0, g1);
+      tmem_st4u(lane_base + kColEh, g0, g1, 0u, 0u);       // height bias of key block 0, -m = 0
       tmem_st4u(lane_base + kColEh + 4, 0u, 0u, 0u, 0u);
     }
     tmem_st_wait();
-    // the staging area is about to be overwritten by TMA (it overlays the V stages): order this thread's generic-proxy
+    // the staging area is about to be overwritten by TMA (it overlays the K / V stages): order this thread's generic-proxy
     // accesses to it before the async-proxy writes that follow the rel_free hand-off
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {  // G consumed and E written: the S region is free for S_0
-      mbar_arrive(&s_free[w]);
+      mbar_arrive(s_free);
       mbar_arrive(rel_free);
     }
 
@@ -401,33 +445,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     float alpha_pending = 1.0f;  // factor still to be applied to O (after the P*V that is in flight retires)
     uint32_t pk[kKB / 2];        // P of the current block: bf16 pairs
 
-    // exponentiate columns [C0, C1) of the row (kAdjust adds the -- rare -- reference correction per element): P as bf16
-    // pairs, partial row sums in ls[4]
-    auto exp_cols = [&](auto adjust_tag, auto c0_tag, auto c1_tag, const float (&x)[kKB], float delta, float (&ls)[4]) {
-      constexpr bool kAdjust = decltype(adjust_tag)::value;
-      constexpr int C0 = decltype(c0_tag)::value, C1 = decltype(c1_tag)::value;
-#pragma unroll
-      for (int i = C0; i < C1; i += 4) {
-        float x0 = x[i], x1 = x[i + 1], x2 = x[i + 2], x3 = x[i + 3];
-        if constexpr (kAdjust) {
-          x0 += delta; x1 += delta; x2 += delta; x3 += delta;
-        }
-        const float p0 = BSEG_ATTN_SKIP_EXP ? x0 * 0.001f : ex2_approx(x0);
-        const float p1 = BSEG_ATTN_SKIP_EXP ? x1 * 0.001f : ex2_approx(x1);
-        const float p2 = BSEG_ATTN_SKIP_EXP ? x2 * 0.001f : ex2_approx(x2);
-        const float p3 = BSEG_ATTN_SKIP_EXP ? x3 * 0.001f : ex2_approx(x3);
-        add_f32x2(ls[0], ls[1], p0, p1);
-        add_f32x2(ls[2], ls[3], p2, p3);
-        pk[i >> 1] = pack_bf16x2(p0, p1);
-        pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-      }
-    };
-    auto row_max = [&](const float (&x)[kKB]) {
-      float mx = x[0];
-#pragma unroll
-      for (int i = 1; i < kKB; ++i) mx = fmaxf(mx, x[i]);
-      return mx;
-    };
     // raise the reference by `up` (>= 0, a multiple of 16): everything accumulated so far shrinks by 2^-up
     auto raise = [&](float up) {
       const float a = ex2_approx(-up);
@@ -435,68 +452,61 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       l_run *= a;
       alpha_pending *= a;
     };
-    auto load_s_row = [&](float (&x)[kKB]) {  // asynchronous: tmem_ld_wait() before the first use
-      tmem_ld32(lane_base, *reinterpret_cast<float(*)[32]>(&x[0]));
-      tmem_ld32(lane_base + 32, *reinterpret_cast<float(*)[32]>(&x[32]));
-      tmem_ld32(lane_base + 64, *reinterpret_cast<float(*)[32]>(&x[64]));
-      tmem_ld16(lane_base + 96, *reinterpret_cast<float(*)[16]>(&x[96]));
-    };
-    using Fast = std::false_type;
-    using Slow = std::true_type;
-    using C0 = std::integral_constant<int, 0>;
-    using C2 = std::integral_constant<int, 64>;   // the barrier of the end of the block is probed after this many
-    using C3 = std::integral_constant<int, kKB>;
+    constexpr int kProbeAt = (kKB / 2 + 8) / 16 * 16;  // the P*V barrier is probed after this many exponentials
 
     float x[kKB];
-    uint2 gnext = *reinterpret_cast<const uint2*>(bh_row + 2);  // packed height bias of key block 1
+    uint32_t gn0 = 0u, gn1 = 0u;
+    bh_block<kRows>(bh_row, 1, gn0, gn1);  // packed height bias of key block 1
     for (int kb = 0; kb < kNumKB; ++kb) {
       const float m_in_s = m_in_next;  // the reference that was in Eh when THIS block's S was issued
 
       // ---------------- S row -> registers, S region (with the next block's Eh) straight back to the tensor core ----------------
-      if (quarter == 0) ATTN_TRACE(w, kb, 0);  // block start
-      mbar_wait(&s_full[w], kb & 1);
-      if (quarter == 0) ATTN_TRACE(w, kb, 1);  // S ready
+      if (quarter == 0) ATTN_TRACE(0, kb, 0);  // block start
+      mbar_wait(s_full, kb & 1);
+      if (quarter == 0) ATTN_TRACE(0, kb, 1);  // S ready
       tc_fence_after();
-      load_s_row(x);
+#pragma unroll
+      for (int c = 0; c + 32 <= kKB; c += 32) tmem_ld32(lane_base + c, *reinterpret_cast<float(*)[32]>(&x[c]));
+      if constexpr (kKB % 32 == 16) tmem_ld16(lane_base + kKB - 16, *reinterpret_cast<float(*)[16]>(&x[kKB - 16]));
       tmem_ld_wait();
       if (kb == 0) m_run = ceil16(row_max(x));  // initial reference: row max over the first key block
       if (kb + 1 < kNumKB) {
         const float m_enc = fminf(fmaxf(m_run, -kMaxEncodedRef), kMaxEncodedRef);
-        tmem_st4u(lane_base + kColEh, gnext.x, gnext.y, pack_f16x2(-m_enc, 0.f), 0u);
+        tmem_st4u(lane_base + kColEh, gn0, gn1, pack_f16x2(-m_enc, 0.f), 0u);
         m_in_next = m_enc;
-        if (kb + 2 < kNumKB) gnext = *reinterpret_cast<const uint2*>(bh_row + 2 * (kb + 2));  // (used one block later)
+        if (kb + 2 < kNumKB) bh_block<kRows>(bh_row, kb + 2, gn0, gn1);  // (used one block later)
         tmem_st_wait();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[w]);  // the next block's S may be issued: it runs under this block's exponentials
-      if (quarter == 0) ATTN_TRACE(w, kb, 2);  // S handed back
+      if (lane == 0) mbar_arrive(s_free);  // the next block's S may be issued: it runs under this block's exponentials
+      if (quarter == 0) ATTN_TRACE(0, kb, 2);  // S handed back
 
       // ---------------- exponentials ----------------
       float delta = m_in_s - m_run;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
       const bool adjust = __any_sync(0xffffffffu, delta != 0.f);
-      if (adjust) exp_cols(Slow{}, C0{}, C2{}, x, delta, ls);
-      else exp_cols(Fast{}, C0{}, C2{}, x, 0.f, ls);
+      if (adjust) exp_cols<true, 0, kProbeAt>(x, delta, ls, pk);
+      else exp_cols<false, 0, kProbeAt>(x, 0.f, ls, pk);
       // probe the barrier the end of the block needs now: the probe's latency runs under the remaining exponentials
-      const bool pv_ready = kb > 0 ? mbar_test(&pv_done[w], (kb - 1) & 1) : true;
-      if (adjust) exp_cols(Slow{}, C2{}, C3{}, x, delta, ls);
-      else exp_cols(Fast{}, C2{}, C3{}, x, 0.f, ls);
+      const bool pv_ready = kb > 0 ? mbar_test(pv_done, (kb - 1) & 1) : true;
+      if (adjust) exp_cols<true, kProbeAt, kKB>(x, delta, ls, pk);
+      else exp_cols<false, kProbeAt, kKB>(x, 0.f, ls, pk);
       float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       if (__any_sync(0xffffffffu, !(lsum < kOverflowGuard))) {  // (practically never) redo against a safe reference
         raise(fmaxf(ceil16(row_max(x) + delta), 0.f));
         delta = m_in_s - m_run;
         ls[0] = ls[1] = ls[2] = ls[3] = 0.f;
-        exp_cols(Slow{}, C0{}, C3{}, x, delta, ls);
+        exp_cols<true, 0, kKB>(x, delta, ls, pk);
         lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       }
-      if (quarter == 0) ATTN_TRACE(w, kb, 3);  // exponentials done
+      if (quarter == 0) ATTN_TRACE(0, kb, 3);  // exponentials done
 
       // ---------------- hand P to the tensor core ----------------
       if (kb > 0) {
         // the P region and O are ours again once the previous P*V has retired
-        if (!__all_sync(0xffffffffu, pv_ready)) mbar_wait(&pv_done[w], (kb - 1) & 1);
-        if (quarter == 0) ATTN_TRACE(w, kb, 4);  // previous PV retired
+        if (!__all_sync(0xffffffffu, pv_ready)) mbar_wait(pv_done, (kb - 1) & 1);
+        if (quarter == 0) ATTN_TRACE(0, kb, 4);  // previous PV retired
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha_pending != 1.0f)) {
 #pragma unroll
@@ -511,18 +521,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
       }
       alpha_pending = 1.0f;
-      tmem_st16u(lane_base + kColP, &pk[0]);
-      tmem_st16u(lane_base + kColP + 16, &pk[16]);
-      tmem_st16u(lane_base + kColP + 32, &pk[32]);
-      tmem_st8u(lane_base + kColP + 48, &pk[48]);
+#pragma unroll
+      for (int c = 0; c + 16 <= kKB / 2; c += 16) tmem_st16u(lane_base + kColP + c, &pk[c]);
+      if constexpr ((kKB / 2) % 16 == 8) tmem_st8u(lane_base + kColP + kKB / 2 - 8, &pk[kKB / 2 - 8]);
       l_run += lsum;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[w]);
-      if (quarter == 0) ATTN_TRACE(w, kb, 5);  // P handed over
+      if (lane == 0) mbar_arrive(p_full);
+      if (quarter == 0) ATTN_TRACE(0, kb, 5);  // P handed over
 
-      // lazily raise the reference for the following blocks: row sum < 2^e and max P >= row sum / 112
+      // lazily raise the reference for the following blocks: row sum < 2^e and max P >= row sum / KB
       if (lsum > kRaiseThreshold) {
         const int e = ((__float_as_int(lsum) >> 23) & 0xff) - 126;
         raise(static_cast<float>((e + 15) & ~15));  // applied to O once this block's P*V has retired
@@ -530,7 +539,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
 
     // ---- epilogue: O / l -> bf16, token-major [seq, t, heads*64] ----
-    mbar_wait(&pv_done[w], (kNumKB - 1) & 1);
+    mbar_wait(pv_done, (kNumKB - 1) & 1);
     tc_fence_after();
     const float inv = alpha_pending / l_run;
     // log2-domain log-sum-exp of the row (saved for the backward pass): P = exp2(x - lse)
@@ -550,31 +559,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                        pack_bf16x2(v[12] * inv, v[13] * inv), pack_bf16x2(v[14] * inv, v[15] * inv));
       }
     }
-    }  // w < n_active
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<attn::kTmemCols>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
-                     const __nv_bfloat16* relcat, __nv_bfloat16* out, float* lse_out, int nseq, int heads, int grid_h,
-                     int grid_w, cudaStream_t stream) {
-  using namespace attn;
-  BSEG_REQUIRE(grid_h == kGridH && grid_w == kGridW, "attention: only the 56x28 token grid is supported (got %dx%d)",
-               grid_h, grid_w);
-  BSEG_REQUIRE(nseq > 0 && heads > 0, "attention: empty problem");
+template <class Cfg>
+static int launch_attention_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
+                              const __nv_bfloat16* relcat, __nv_bfloat16* out, float* lse_out, int nseq, int heads,
+                              cudaStream_t stream) {
+  constexpr int kT = Cfg::kT;
   CUtensorMap tq, tk, tv, tr;
   const uint64_t nsh = static_cast<uint64_t>(nseq) * heads;
   {
     uint64_t dims[3] = {64, static_cast<uint64_t>(kT), nsh};
     uint64_t strides[2] = {128, static_cast<uint64_t>(kT) * 128};
-    uint32_t boxq[3] = {64, kQTile, 1};
-    uint32_t boxk[3] = {64, kKB, 1};
+    uint32_t boxq[3] = {64, Cfg::kQTile, 1};
+    uint32_t boxk[3] = {64, Cfg::kKB, 1};
     int rc = make_tmap_bf16(&tq, q, 3, dims, strides, boxq);
     if (rc) return rc;
     rc = make_tmap_bf16(&tk, k, 3, dims, strides, boxk);
@@ -588,20 +594,38 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     if (rc) return rc;
   }
   {
-    int rc = make_tmap_bf16_2d(&tr, relcat, 64, kRelRows, 64, 64, kRelRows);
+    int rc = make_tmap_bf16_2d(&tr, relcat, 64, Cfg::kRelRows, 64, 64, Cfg::kRelRows);
     if (rc) return rc;
   }
-  static PerDeviceFlag attr_once;
+  auto kern = attention_fwd_kernel<Cfg>;
+  static PerDeviceFlag attr_once;  // per template instantiation
   if (attr_once.first()) {
-    BSEG_CHECK_CUDA(
-        cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   }
-  dim3 grid((kT + kCtaQ - 1) / kCtaQ, heads, nseq);
-  ProfScope prof(CAT_ATTENTION, static_cast<double>(nseq) * heads * (4.0 * kT * kT * 64 + 2.0 * kT * 84 * 64),
+  dim3 grid((kT + Cfg::kQTile - 1) / Cfg::kQTile, heads, nseq);
+  ProfScope prof(CAT_ATTENTION,
+                 static_cast<double>(nseq) * heads * (4.0 * kT * kT * 64 + 2.0 * kT * (Cfg::kGridH + Cfg::kGridW) * 64),
                  static_cast<double>(nseq) * heads * kT * 64 * 2 * 4, stream);
-  attention_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tr, out, lse_out, heads);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, tr, out, lse_out, heads);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  return 0;
+}
+
+int attention_relcat_rows(int grid_h, int grid_w) {
+  return (2 * grid_h - 1 + 15) / 16 * 16 + (2 * grid_w - 1 + 15) / 16 * 16;
+}
+
+int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
+                     const __nv_bfloat16* relcat, __nv_bfloat16* out, float* lse_out, int nseq, int heads, int grid_h,
+                     int grid_w, cudaStream_t stream) {
+  BSEG_REQUIRE(nseq > 0 && heads > 0, "attention: empty problem");
+  if (grid_h == 56 && grid_w == 28)
+    return launch_attention_t<AttnCfg<56, 28, 4>>(q, k, vt, relcat, out, lse_out, nseq, heads, stream);
+  if (grid_h == 64 && grid_w == 32)
+    return launch_attention_t<AttnCfg<64, 32, 2>>(q, k, vt, relcat, out, lse_out, nseq, heads, stream);
+  BSEG_REQUIRE(false, "attention: token grid %dx%d is not built (56x28 = the 448-px path, 64x32 = native 512-px tiles)",
+               grid_h, grid_w);
   return 0;
 }
 

@@ -99,15 +99,16 @@ int launch_layernorm1024(const float* x, long long ldx, const float* gamma, cons
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ px, const float* __restrict__ prompt_px,
-                const float* __restrict__ prompt_mask, __nv_bfloat16* __restrict__ A, int B) {
-  // one thread = 8 consecutive pixels of one image row of one channel
-  const long long total = 2LL * B * 3 * 896 * 56;  // (stream, b, c, y, x8)
+                const float* __restrict__ prompt_mask, __nv_bfloat16* __restrict__ A, int B, int img) {
+  // one thread = 8 consecutive pixels of one image row of one channel; img = 448 (56 x 28 tokens) or 512 (64 x 32)
+  const int gw = img >> 4, w8 = img >> 3, T = 2 * gw * gw;
+  const long long total = 2LL * B * 3 * (2 * img) * w8;  // (stream, b, c, y, x8)
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int x8 = static_cast<int>(idx % 56);
-    long long r = idx / 56;
-    const int y = static_cast<int>(r % 896);
-    r /= 896;
+    const int x8 = static_cast<int>(idx % w8);
+    long long r = idx / w8;
+    const int y = static_cast<int>(r % (2 * img));
+    r /= 2 * img;
     const int c = static_cast<int>(r % 3);
     r /= 3;
     const int b = static_cast<int>(r % B);
@@ -116,24 +117,24 @@ patchify_kernel(const float* __restrict__ px, const float* __restrict__ prompt_p
     const int x = x8 * 8;
     const int pw = x >> 4, pxo = x & 15;
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    const bool top = y < 448;
+    const bool top = y < img;
     if (s == 0 || top) {
       const float* src = (s == 0) ? (top ? prompt_px : px) : prompt_mask;
-      const float* p = src + (((long long)b * 3 + c) * 448 + (top ? y : y - 448)) * 448 + x;
+      const float* p = src + (((long long)b * 3 + c) * img + (top ? y : y - img)) * img + x;
       const float4 v0 = *reinterpret_cast<const float4*>(p);
       const float4 v1 = *reinterpret_cast<const float4*>(p + 4);
       o = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y),
                      pack_bf16x2(v1.z, v1.w));
     }
-    const long long row = ((long long)s * B + b) * 1568 + ph * 28 + pw;
+    const long long row = ((long long)s * B + b) * T + ph * gw + pw;
     *reinterpret_cast<uint4*>(A + row * 768 + c * 256 + py * 16 + pxo) = o;
   }
 }
 int launch_patchify(const float* px, const float* prompt_px, const float* prompt_mask, const float* /*labels*/,
-                    __nv_bfloat16* A, int B, cudaStream_t stream) {
-  const long long total = 2LL * B * 3 * 896 * 56;
+                    __nv_bfloat16* A, int B, int img, cudaStream_t stream) {
+  const long long total = 2LL * B * 3 * (2 * img) * (img / 8);
   ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(total) * 8 * 6, stream);
-  patchify_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, prompt_px, prompt_mask, A, B);
+  patchify_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, prompt_px, prompt_mask, A, B, img);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

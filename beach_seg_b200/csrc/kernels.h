@@ -25,6 +25,8 @@ int gemm_set_cta_pairs(int on);
 int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
                      const __nv_bfloat16* relcat, __nv_bfloat16* out, float* lse_out, int nseq, int heads, int grid_h,
                      int grid_w, cudaStream_t stream);
+// rows of the relcat table for a token grid: round16(2 gh - 1) + round16(2 gw - 1)  (176 for 56 x 28, 192 for 64 x 32)
+int attention_relcat_rows(int grid_h, int grid_w);
 
 // attention_bwd.cu : dq, dk, dv of the fused attention, written token-major into dqkv [nseq*T, 3*heads*64] bf16
 //   q, k, v : [nseq*heads, T, 64];  qt, kt, dOt : [nseq*heads, 64, T];  dO : token-major [nseq*T, heads*64]
@@ -68,7 +70,7 @@ int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaSt
 int launch_layernorm1024(const float* x, long long ldx, const float* gamma, const float* beta, __nv_bfloat16* out,
                          long long ldo, long long M, float eps, cudaStream_t stream);
 int launch_patchify(const float* px, const float* prompt_px, const float* prompt_mask, const float* labels,
-                    __nv_bfloat16* A, int B, cudaStream_t stream);
+                    __nv_bfloat16* A, int B, int img, cudaStream_t stream);
 int launch_merge_streams(float* h, long long n_half, cudaStream_t stream);
 int launch_ensemble_residual(float* h, const float* attn, int nstreams, int G, int P, int cross_stream, int T, int D,
                              cudaStream_t stream);

@@ -85,10 +85,13 @@ class SegGptB200(torch.nn.Module):
     def __init__(self, state_dict: Dict[str, torch.Tensor], num_layers: int = 24, merge_index: int = 2,
                  intermediate=(5, 11, 17, 23), layer_norm_eps: float = 1e-6, beta: float = 0.01,
                  device: str | torch.device = "cuda:0", max_batch: int = 64, precision: str = "bf16",
-                 graph_batch: int = 16):
+                 graph_batch: int = 16, image_size: int = IMG):
         """precision: "bf16" = the tcgen05 path (bf16 operands, fp32 accumulation / residual stream / softmax; logits
         within 1e-2 of the fp32 reference); "fp32" = the accuracy mode (bseg_forward_f32: everything IEEE fp32 on the
         CUDA cores, within 1e-4, inference only, ~30x slower).
+        image_size: 448 = the reference's path (crops resized to 448, `SegGptConfig()`); 512 = native-resolution mode for
+        512-px tiles (`SegGptConfig(image_size=(1024, 512))`: 64 x 32 tokens, T = 2048, rel-pos tables of 127 / 63 rows;
+        SURVEY section 8(f) rank 4) -- bf16 inference only.
         graph_batch: inference calls with at most this many samples go through persistent staging buffers and a CUDA graph
         of the whole forward (bseg_set_graph_batch_limit): the reference's own call pattern is batch 1
         (src/predict.py:234), where the host work of ~190 launches is as long as the device work.  0 disables it."""
@@ -96,6 +99,12 @@ class SegGptB200(torch.nn.Module):
         if precision not in ("bf16", "fp32"):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         self.precision = precision
+        if image_size not in (448, 512):
+            raise ValueError(f"image_size must be 448 or 512 (native 512-px tiles), got {image_size}")
+        if image_size != IMG and precision != "bf16":
+            raise NotImplementedError("the native-resolution mode runs on the bf16 path only")
+        self.image_size = int(image_size)
+        self.num_patches = 2 * (self.image_size // 16) ** 2
         self._device = torch.device(device)
         if self._device.type != "cuda":
             raise _lib.BsegError("SegGptB200 runs on a CUDA device only; there is no CPU path")
@@ -132,6 +141,7 @@ class SegGptB200(torch.nn.Module):
                 lw.lin1_w, lw.lin1_b = dev(p + "mlp.lin1.weight"), dev(p + "mlp.lin1.bias")
                 lw.lin2_w, lw.lin2_b = dev(p + "mlp.lin2.weight"), dev(p + "mlp.lin2.bias")
             w = _lib.Weights()
+            w.image_size = self.image_size
             w.num_layers, w.merge_index = num_layers, merge_index
             w.intermediate_indices = (C.c_int * 4)(*self.intermediate)
             w.layer_norm_eps = layer_norm_eps
@@ -159,6 +169,11 @@ class SegGptB200(torch.nn.Module):
     @classmethod
     def from_hf(cls, hf_model, device="cuda:0", **kw) -> "SegGptB200":
         cfg = hf_model.config
+        size = cfg.image_size
+        height, width = (size, size) if isinstance(size, int) else (int(size[0]), int(size[1]))
+        if height != 2 * width:
+            raise ValueError(f"SegGptConfig.image_size={size}: the stacked image must be (2 * tile, tile)")
+        kw.setdefault("image_size", width)
         return cls(hf_model.state_dict(), num_layers=cfg.num_hidden_layers, merge_index=cfg.merge_index,
                    intermediate=tuple(cfg.intermediate_hidden_state_indices), layer_norm_eps=cfg.layer_norm_eps,
                    beta=cfg.beta, device=device, **kw)
@@ -212,22 +227,22 @@ class SegGptB200(torch.nn.Module):
         """HF forward signature (HF:modeling_seggpt.py:839-959) plus two extensions: `ensemble_group` (several tiles of P
         prompts per launch) and `query_half_only` (skip the decoder for the prompt half: pred_masks[:, :, :448] is zero,
         the bottom half -- the only part the reference ever reads -- is bit-identical)."""
+        S, NP = self.image_size, self.num_patches
         for name, t in (("pixel_values", pixel_values), ("prompt_pixel_values", prompt_pixel_values),
                         ("prompt_masks", prompt_masks)):
             if t.ndim != 4 or t.shape[1] != 3:
                 raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in "
                                  "the configuration.")
-            if t.shape[2] != IMG or t.shape[3] != IMG:
+            if t.shape[2] != S or t.shape[3] != S:
                 # HF checks the stacked image (HF:modeling_seggpt.py:116-119)
-                raise ValueError(f"Input image size ({2 * t.shape[2]}*{t.shape[3]}) doesn't match model (896*448).")
+                raise ValueError(f"Input image size ({2 * t.shape[2]}*{t.shape[3]}) doesn't match model ({2 * S}*{S}).")
         embedding_type = embedding_type if embedding_type is not None else "instance"
         if embedding_type not in ("instance", "semantic"):
             raise ValueError(f"Embedding type should be either 'semantic' or 'instance', but got {embedding_type}")
         mask_rows = 1  # HF's default bool_masked_pos has batch dimension 1 (HF:modeling_seggpt.py:910-917)
         if bool_masked_pos is not None:
-            default = torch.cat([torch.zeros(NUM_PATCHES // 2, dtype=torch.bool),
-                                 torch.ones(NUM_PATCHES - NUM_PATCHES // 2, dtype=torch.bool)])
-            rows = bool_masked_pos.reshape(-1, NUM_PATCHES)
+            default = torch.cat([torch.zeros(NP // 2, dtype=torch.bool), torch.ones(NP - NP // 2, dtype=torch.bool)])
+            rows = bool_masked_pos.reshape(-1, NP)
             if not torch.equal(rows.cpu().bool(), default.expand(rows.shape[0], -1)):
                 raise NotImplementedError("only the default bool_masked_pos (bottom half masked) is supported; the "
                                           "reference never passes another one")
@@ -252,6 +267,8 @@ class SegGptB200(torch.nn.Module):
 
         if want_grad and self.precision == "fp32":
             raise NotImplementedError("the fp32 accuracy mode is inference-only; train with precision='bf16'")
+        if want_grad and S != IMG:
+            raise NotImplementedError("the native-resolution mode is inference-only; the train step runs at 448")
         if want_grad:
             if feature_ensemble:
                 raise NotImplementedError("feature_ensemble is an inference-only path in the reference "
@@ -264,7 +281,7 @@ class SegGptB200(torch.nn.Module):
             return self._forward_staged(pixel_values, prompt_pixel_values, prompt_masks, B, embedding_type, P,
                                         query_half_only, labels, mask_rows)
         px, ppx, pm = prep(pixel_values), prep(prompt_pixel_values), prep(prompt_masks)
-        pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=self._device)
+        pred = torch.empty((B, 3, 2 * S, S), dtype=torch.float32, device=self._device)
         step = self.max_batch if P == 0 else max(P, (self.max_batch // P) * P)
         if self.precision == "fp32":
             fwd, fwd_name = L.bseg_forward_f32, "bseg_forward_f32"
@@ -292,7 +309,8 @@ class SegGptB200(torch.nn.Module):
             L = _lib.lib()
             mk = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self._device)  # noqa: E731
             ws = torch.empty(int(L.bseg_workspace_bytes(self._handle, B)) + 256, dtype=torch.uint8, device=self._device)
-            st = (mk(B, 3, IMG, IMG), mk(B, 3, IMG, IMG), mk(B, 3, IMG, IMG), mk(B, 3, 2 * IMG, IMG), ws)
+            S = self.image_size
+            st = (mk(B, 3, S, S), mk(B, 3, S, S), mk(B, 3, S, S), mk(B, 3, 2 * S, S), ws)
             self._stage[B] = st
         px, ppx, pm, pred, ws = st
         px.copy_(pixel_values.detach(), non_blocking=True)
@@ -319,11 +337,12 @@ class SegGptB200(torch.nn.Module):
         if labels is None:
             return None
         lab = labels.detach().to(device=self._device, dtype=torch.float32).contiguous()
-        yes = torch.ones((B, IMG, IMG), dtype=torch.uint8, device=self._device)
+        S = self.image_size
+        yes = torch.ones((B, S, S), dtype=torch.uint8, device=self._device)
         loss_t = torch.empty(1, dtype=torch.float32, device=self._device)
         with torch.cuda.device(self._device):
             _lib.check(_lib.lib().bseg_loss_smoothl1_fwd_bwd(_lib.ptr(pred), _lib.ptr(lab), _lib.ptr(yes), self.beta,
                                                              1, _lib.ptr(loss_t), None, _lib.ptr(self._scratch), B,
-                                                             IMG, IMG, _lib.stream_ptr()), "bseg_loss")
+                                                             S, S, _lib.stream_ptr()), "bseg_loss")
         # the kernel divides by B * 3*448*448 (all-ones keep mask); HF divides by mask_rows * 3*448*448
         return loss_t[0] * (float(B) / float(mask_rows)) if mask_rows != B else loss_t[0]

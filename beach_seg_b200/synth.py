@@ -31,19 +31,19 @@ def nodata_wedge(height: int, width: int, frac: float = 0.05) -> np.ndarray:
     return (xx / max(width, 1) + yy / max(height, 1)) < np.sqrt(2 * frac)
 
 
-def smooth_image(batch: int, seed: int) -> torch.Tensor:
-    """float32 [B,3,448,448] in [0,1]: band-limited random field + fine noise (image-like statistics)."""
+def smooth_image(batch: int, seed: int, size: int = 448) -> torch.Tensor:
+    """float32 [B,3,size,size] in [0,1]: band-limited random field + fine noise (image-like statistics)."""
     g = torch.Generator().manual_seed(seed)
     low = torch.rand((batch, 3, 14, 14), generator=g)
-    img = torch.nn.functional.interpolate(low, size=(448, 448), mode="bilinear", align_corners=False)
-    img = img + 0.08 * torch.randn((batch, 3, 448, 448), generator=g)
+    img = torch.nn.functional.interpolate(low, size=(size, size), mode="bilinear", align_corners=False)
+    img = img + 0.08 * torch.randn((batch, 3, size, size), generator=g)
     return img.clamp_(0.0, 1.0)
 
 
-def blocky_mask(batch: int, seed: int, num_classes: int = 4) -> torch.Tensor:
-    """uint8 [B,448,448]: randint(0, num_classes) on a 28x28 grid, upsampled x16."""
+def blocky_mask(batch: int, seed: int, num_classes: int = 4, size: int = 448) -> torch.Tensor:
+    """uint8 [B,size,size]: randint(0, num_classes) on a (size/16)^2 grid, upsampled x16."""
     g = torch.Generator().manual_seed(seed)
-    m = torch.randint(0, num_classes, (batch, 28, 28), generator=g, dtype=torch.uint8)
+    m = torch.randint(0, num_classes, (batch, size // 16, size // 16), generator=g, dtype=torch.uint8)
     return m.repeat_interleave(16, dim=1).repeat_interleave(16, dim=2).contiguous()
 
 
@@ -53,12 +53,12 @@ def normalize(x: torch.Tensor) -> torch.Tensor:
     return (x - mean) / std
 
 
-def model_inputs(batch: int, seed: int = 123):
-    """(pixel_values, prompt_pixel_values, prompt_masks), each float32 [B,3,448,448], normalised like the reference
+def model_inputs(batch: int, seed: int = 123, size: int = 448):
+    """(pixel_values, prompt_pixel_values, prompt_masks), each float32 [B,3,size,size], normalised like the reference
     does (images: /255 + ImageNet mean/std; prompt masks: build_palette(3) colours, same normalisation)."""
-    px = normalize(smooth_image(batch, seed))
-    ppx = normalize(smooth_image(batch, seed + 1))
-    cls = blocky_mask(batch, seed + 2).long()
+    px = normalize(smooth_image(batch, seed, size))
+    ppx = normalize(smooth_image(batch, seed + 1, size))
+    cls = blocky_mask(batch, seed + 2, size=size).long()
     pal = torch.tensor(PALETTE3, dtype=torch.float32) / 255.0
     pm = normalize(pal[cls].permute(0, 3, 1, 2).contiguous())
     return px, ppx, pm

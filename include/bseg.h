@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BSEG_T 1568          /* tokens per stacked 896x448 image (56 x 28 patches of 16 px) */
+#define BSEG_T 1568          /* tokens per stacked 896x448 image (56 x 28 patches of 16 px); native 512-px tiles: 2048 */
 #define BSEG_HIDDEN 1024
 #define BSEG_HEADS 16
 #define BSEG_IMG 448
@@ -44,6 +44,9 @@ typedef struct bseg_layer_weights {
 } bseg_layer_weights;
 
 typedef struct bseg_weights {
+  int image_size;                 /* SegGptConfig.image_size[1]: 448 (or 0) = the reference's resized path, T = 1568;
+                                   * 512 = native-resolution mode for 512-px tiles (SegGptConfig(image_size=(1024,512)),
+                                   * 64 x 32 tokens, T = 2048, rel-pos tables of 127 / 63 rows): bf16 inference only */
   int num_layers;                 /* SegGptConfig.num_hidden_layers (24) */
   int merge_index;                /* SegGptConfig.merge_index (2) */
   int intermediate_indices[4];    /* SegGptConfig.intermediate_hidden_state_indices (5,11,17,23) */
@@ -80,7 +83,8 @@ size_t bseg_workspace_bytes(const bseg_handle* h, int batch);
  * bool_masked_pos.  pixel_values / prompt_pixel_values / prompt_masks: fp32 [batch,3,448,448].
  * embedding_type: 0 = "instance", 1 = "semantic".  ensemble_prompts: 0 = feature_ensemble off; P >= 1 = on, the
  * batch is batch/P tiles of P prompts each (HF averages the whole batch == one tile).
- * pred_masks: fp32 [batch,3,896,448]. */
+ * pred_masks: fp32 [batch,3,896,448].  For a handle created with image_size = 512 every 448 above reads 512
+ * ([batch,3,512,512] in, [batch,3,1024,512] out). */
 int bseg_forward(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
                  const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
                  size_t workspace_bytes, float* pred_masks, void* stream);
@@ -270,6 +274,13 @@ int bseg_layernorm1024(const float* x, long long ldx, const float* gamma, const 
  * bseg_pack_relcat; out bf16 [nseq,1568,1024]. */
 int bseg_attention(const void* q, const void* k, const void* vt, const void* relcat, void* out, int nseq,
                    void* stream);
+/* The same for a token grid grid_h x grid_w (56 x 28, or 64 x 32 = native 512-px tiles, T = grid_h * grid_w), with
+ * relcat from bseg_pack_relcat_grid (bseg_relcat_rows(grid_h, grid_w) x 64 bf16); lse may be NULL. */
+int bseg_attention_grid(const void* q, const void* k, const void* vt, const void* relcat, void* out, float* lse,
+                        int nseq, int grid_h, int grid_w, void* stream);
+int bseg_relcat_rows(int grid_h, int grid_w);
+int bseg_pack_relcat_grid(const float* rel_pos_h, const float* rel_pos_w, void* relcat, int grid_h, int grid_w,
+                          void* stream);
 /* The same with the log2-domain log-sum-exp per (seq, head, query) written to lse fp32 [nseq,16,1568]. */
 int bseg_attention_fwd_lse(const void* q, const void* k, const void* vt, const void* relcat, void* out, float* lse,
                            int nseq, void* stream);

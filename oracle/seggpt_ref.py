@@ -28,19 +28,23 @@ T = GRID_H * GRID_W
 
 
 def make_reference_model(seed: int = 0, stress: bool = False, num_layers: int = 24, merge_index: int = 2,
-                         intermediate=(5, 11, 17, 23)):
+                         intermediate=(5, 11, 17, 23), image_size: int = 448):
     """HF SegGPT ViT-L, seeded random init, frozen, eval (what src/util/ml_util.py:7-13 load_model returns, minus
     from_pretrained / torch.compile).
 
     stress=True additionally randomises every bias / LayerNorm affine / token and enlarges the rel-pos tables and
     qkv weights so that softmax rows are far from uniform: HF's default init has zero biases and std-0.02 weights,
     which would leave bias / affine / rel-pos code paths numerically untested.
+
+    image_size != 448 builds the native-resolution variant `SegGptConfig(image_size=(2 * image_size, image_size))`
+    (verified for 512 -> T = 2048 tokens; the rel-pos tables then have 2*64-1 / 2*32-1 rows).
     """
     from transformers import SegGptConfig, SegGptForImageSegmentation
 
     torch.manual_seed(seed)
+    extra = {} if image_size == 448 else {"image_size": [2 * image_size, image_size]}
     cfg = SegGptConfig(num_hidden_layers=num_layers, merge_index=merge_index,
-                       intermediate_hidden_state_indices=list(intermediate))
+                       intermediate_hidden_state_indices=list(intermediate), **extra)
     model = SegGptForImageSegmentation(cfg)
     if stress:
         g = torch.Generator().manual_seed(seed + 1)
@@ -65,26 +69,28 @@ def _ln(x, w, b, eps):
     return F.layer_norm(x, (x.shape[-1],), w, b, eps)
 
 
-def rel_pos_bias(q: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor) -> torch.Tensor:
-    """add_decomposed_rel_pos (HF:modeling_seggpt.py:268-311) for q_size == k_size == (56, 28), where get_rel_pos
-    (:232-266) is the identity resize.  q: [N, T, 64] (UNSCALED).  Returns [N, T, T]."""
+def rel_pos_bias(q: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, grid_h: int = GRID_H,
+                 grid_w: int = GRID_W) -> torch.Tensor:
+    """add_decomposed_rel_pos (HF:modeling_seggpt.py:268-311) for q_size == k_size == (grid_h, grid_w) with natively
+    sized tables (2*grid-1 rows), where get_rel_pos (:232-266) is the identity resize.  q: [N, T, 64] (UNSCALED).
+    Returns [N, T, T]."""
     n = q.shape[0]
-    ih = torch.arange(GRID_H)[:, None] - torch.arange(GRID_H)[None, :] + (GRID_H - 1)
-    iw = torch.arange(GRID_W)[:, None] - torch.arange(GRID_W)[None, :] + (GRID_W - 1)
-    Rh = rel_pos_h[ih]  # [56, 56, 64]
-    Rw = rel_pos_w[iw]  # [28, 28, 64]
-    rq = q.reshape(n, GRID_H, GRID_W, -1)
+    ih = torch.arange(grid_h)[:, None] - torch.arange(grid_h)[None, :] + (grid_h - 1)
+    iw = torch.arange(grid_w)[:, None] - torch.arange(grid_w)[None, :] + (grid_w - 1)
+    Rh = rel_pos_h[ih]  # [gh, gh, 64]
+    Rw = rel_pos_w[iw]  # [gw, gw, 64]
+    rq = q.reshape(n, grid_h, grid_w, -1)
     rel_h = torch.einsum("bhwc,hkc->bhwk", rq, Rh)
     rel_w = torch.einsum("bhwc,wkc->bhwk", rq, Rw)
     bias = rel_h[:, :, :, :, None] + rel_w[:, :, :, None, :]
-    return bias.reshape(n, T, T)
+    return bias.reshape(n, grid_h * grid_w, grid_h * grid_w)
 
 
-def attention_ref(q, k, v, rel_pos_h, rel_pos_w):
+def attention_ref(q, k, v, rel_pos_h, rel_pos_w, grid_h: int = GRID_H, grid_w: int = GRID_W):
     """SegGptAttention.forward core (HF:modeling_seggpt.py:324-344). q,k,v: [N, T, 64] fp32."""
     scale = q.shape[-1] ** -0.5
     attn = (q * scale) @ k.transpose(-2, -1)
-    attn = attn + rel_pos_bias(q, rel_pos_h, rel_pos_w)
+    attn = attn + rel_pos_bias(q, rel_pos_h, rel_pos_w, grid_h, grid_w)
     attn = torch.softmax(attn, dim=-1, dtype=torch.float32)
     return attn @ v
 

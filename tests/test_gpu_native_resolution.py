@@ -1,0 +1,119 @@
+"""GPU: native-resolution mode: 512-px tiles without the resize to 448, i.e. HF
+`SegGptConfig(image_size=(1024, 512))` -- 64 x 32 tokens, T = 2048, rel-pos tables of 127 / 63 rows, position embeddings
+interpolated 14x14 -> 64x32.  Oracle = that HF module (seeded random init, fp32, CPU); bar = north_star's 1e-2 relative
+for bf16 operands, class maps differing only where the reference's decision margin is < 0.1."""
+import pytest
+import torch
+
+from beach_seg_b200 import _lib, ops, synth
+from beach_seg_b200.seggpt import SegGptB200
+from oracle import glue_ref
+from oracle.seggpt_ref import attention_ref, make_reference_model
+
+pytestmark = pytest.mark.gpu
+GH, GW = 64, 32
+T = GH * GW
+Q_SCALE = 0.125 * 1.4426950408889634
+SMALL = dict(num_layers=5, merge_index=1, intermediate=(1, 2, 3, 4))
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("nseq,qscale,relscale", [(1, 1.0, 0.3), (2, 3.0, 0.5)])
+def test_attention_64x32_matches_oracle(dev, nseq, qscale, relscale):
+    """bseg_attention_grid at the 64 x 32 token grid (key blocks of 64 = 2 token rows) against the oracle's attention."""
+    g = torch.Generator().manual_seed(int(nseq * 100 + qscale * 10 + relscale * 7))
+    qs = (torch.randn((nseq, 16, T, 64), generator=g) * qscale * Q_SCALE).to(torch.bfloat16)
+    q = qs.float() / Q_SCALE
+    k = bf16r(torch.randn((nseq, 16, T, 64), generator=g))
+    v = bf16r(torch.randn((nseq, 16, T, 64), generator=g))
+    rel_h = bf16r(torch.randn((2 * GH - 1, 64), generator=g) * relscale)
+    rel_w = bf16r(torch.randn((2 * GW - 1, 64), generator=g) * relscale)
+    want = attention_ref(q.reshape(-1, T, 64), k.reshape(-1, T, 64), v.reshape(-1, T, 64), rel_h, rel_w, GH, GW)
+    want = want.reshape(nseq, 16, T, 64).permute(0, 2, 1, 3).reshape(nseq, T, 1024)
+    L = _lib.lib()
+    rows = L.bseg_relcat_rows(GH, GW)
+    assert rows == 192
+    relcat = torch.empty((rows, 64), dtype=torch.bfloat16, device=dev)
+    rh, rw = rel_h.to(dev), rel_w.to(dev)
+    _lib.check(L.bseg_pack_relcat_grid(_lib.ptr(rh), _lib.ptr(rw), _lib.ptr(relcat), GH, GW, _lib.stream_ptr()))
+    qb, kb = qs.to(dev).contiguous(), k.to(dev).to(torch.bfloat16).contiguous()
+    vt = v.to(dev).to(torch.bfloat16).transpose(2, 3).contiguous()
+    out = torch.empty((nseq, T, 1024), dtype=torch.bfloat16, device=dev)
+    lse = torch.empty((nseq, 16, T), dtype=torch.float32, device=dev)
+    _lib.check(L.bseg_attention_grid(_lib.ptr(qb), _lib.ptr(kb), _lib.ptr(vt), _lib.ptr(relcat), _lib.ptr(out),
+                                     _lib.ptr(lse), nseq, GH, GW, _lib.stream_ptr()), "bseg_attention_grid")
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    rel = rel_l2(got, want)
+    print(f"[attention 64x32 nseq={nseq} q*{qscale} rel*{relscale}] rel-L2={rel:.3e}")
+    assert rel < 1e-2
+    # the saved log-sum-exp (log2 domain) against the oracle's scores
+    s = (q.reshape(-1, T, 64) * 0.125) @ k.reshape(-1, T, 64).transpose(-2, -1)
+    from oracle.seggpt_ref import rel_pos_bias
+
+    s = s + rel_pos_bias(q.reshape(-1, T, 64), rel_h, rel_w, GH, GW)
+    lse_ref = torch.logsumexp(s, dim=-1) * 1.4426950408889634
+    lse_err = (lse.cpu().reshape(-1, T) - lse_ref).abs().max().item()
+    print(f"[attention 64x32] max |lse error| = {lse_err:.3e} at max |lse| = {lse_ref.abs().max().item():.1f} (log2 units)")
+    assert lse_err < 2e-2 + 1e-3 * lse_ref.abs().max().item()  # bf16 operands: the scores themselves carry ~1e-3 relative
+
+
+def test_unknown_token_grid_is_rejected(dev):
+    L = _lib.lib()
+    z = torch.zeros(16, dtype=torch.bfloat16, device=dev)
+    rc = L.bseg_attention_grid(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), None, 1, 128, 64,
+                               _lib.stream_ptr())
+    assert rc != 0 and b"not built" in L.bseg_last_error()
+
+
+@pytest.mark.parametrize("embedding_type", ["instance", "semantic"])
+def test_native_512_model_vs_hf(dev, embedding_type):
+    """5-layer stress-initialised backbone at image_size 512: pred_masks [B, 3, 1024, 512] against the HF module."""
+    hf = make_reference_model(seed=4, stress=True, image_size=512, **SMALL)
+    model = SegGptB200.from_hf(hf, device=dev)
+    assert model.image_size == 512 and model.num_patches == 2048
+    px, ppx, pm = synth.model_inputs(batch=2, seed=31, size=512)
+    with torch.no_grad():
+        want = hf(pixel_values=px, prompt_pixel_values=ppx, prompt_masks=pm, embedding_type=embedding_type).pred_masks
+        got = model(pixel_values=px.to(dev), prompt_pixel_values=ppx.to(dev), prompt_masks=pm.to(dev),
+                    embedding_type=embedding_type).pred_masks
+        half = model(pixel_values=px.to(dev), prompt_pixel_values=ppx.to(dev), prompt_masks=pm.to(dev),
+                     embedding_type=embedding_type, query_half_only=True).pred_masks
+    assert got.shape == (2, 3, 1024, 512)
+    r = rel_l2(got.cpu(), want)
+    print(f"[native 512 {embedding_type}] pred rel-L2={r:.3e}")
+    assert r < 1e-2
+    assert torch.equal(half[:, :, 512:], got[:, :, 512:]) and not half[:, :, :512].any()
+    # class maps through the palette decode (generic in the tile size)
+    _, paln = glue_ref.create_palette(4, 2, train=False)
+    cls = ops.decode_palette(got, paln.to(dev)).cpu()
+    d = ((want[:, :, 512:].permute(0, 2, 3, 1)[:, :, :, None, :] - paln[:, None, None]) ** 2).sum(-1)
+    cls_ref = d.argmin(-1)
+    top2 = d.topk(2, dim=-1, largest=False).values
+    margin = top2[..., 1] - top2[..., 0]
+    flipped = cls != cls_ref
+    print(f"[native 512 {embedding_type}] class flips {int(flipped.sum())}/{flipped.numel()}")
+    assert cls.shape == (2, 512, 512) and flipped.float().mean().item() < 0.01
+    if flipped.any():
+        assert margin[flipped].max().item() < 0.1
+
+
+def test_native_512_interface(dev):
+    """Wrong tile size raises HF's ValueError; the train step and the fp32 mode are 448-only and say so."""
+    hf = make_reference_model(seed=4, stress=False, image_size=512, **SMALL)
+    model = SegGptB200.from_hf(hf, device=dev)
+    z448 = torch.zeros((1, 3, 448, 448), device=dev)
+    with pytest.raises(ValueError):
+        model(pixel_values=z448, prompt_pixel_values=z448, prompt_masks=z448)
+    z = torch.zeros((1, 3, 512, 512), device=dev)
+    with pytest.raises(NotImplementedError):
+        model(pixel_values=z, prompt_pixel_values=z.clone().requires_grad_(True), prompt_masks=z)
+    with pytest.raises(NotImplementedError):
+        SegGptB200.from_hf(hf, device=dev, precision="fp32")
