@@ -71,6 +71,8 @@ SIGNATURES = {
     "bseg_scene_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bseg_ingest_u16x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f3, _f3, _vp, _vp, _ll, _vp, _vp,
                                _vp]),
+    "bseg_ingest_native_u16x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _f3, _f3, _vp, _vp, _vp, _vp]),
+    "bseg_ingest_native_f32x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _f3, _f3, _vp, _vp, _vp, _vp]),
     "bseg_scene_stats_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bseg_ingest_f32x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f3, _f3, _vp, _vp, _ll, _vp, _vp,
                                _vp]),

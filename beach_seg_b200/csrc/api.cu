@@ -936,6 +936,22 @@ int bseg_ingest_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int 
                        static_cast<cudaStream_t>(stream));
 }
 
+int bseg_ingest_native_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                             const int32_t* boxes, int n_tiles, int crop, const float* mean, const float* stdv,
+                             float* out_nchw, uint8_t* out_u8, uint8_t* out_nodata, void* stream) {
+  BSEG_REQUIRE(n_tiles >= 0 && crop > 0, "ingest_native: bad arguments");
+  return launch_ingest_native(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, mean, stdv, out_nchw, out_u8,
+                              out_nodata, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_ingest_native_f32x4(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                             const int32_t* boxes, int n_tiles, int crop, const float* mean, const float* stdv,
+                             float* out_nchw, uint8_t* out_u8, uint8_t* out_nodata, void* stream) {
+  BSEG_REQUIRE(n_tiles >= 0 && crop > 0, "ingest_native_f32: bad arguments");
+  return launch_ingest_native_f32(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, mean, stdv, out_nchw, out_u8,
+                                  out_nodata, static_cast<cudaStream_t>(stream));
+}
+
 int bseg_scene_stats_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, uint32_t* scratch,
                          void* stream) {
   BSEG_REQUIRE(Hs > 0 && Ws > 0, "scene_stats_f32: empty scene");

@@ -474,10 +474,11 @@ int launch_ingest_v2(const void* scene, const uint8_t* nodata, int Hs, int Ws, c
   size_t smem;
   BSEG_REQUIRE(ingest_v2_geometry(crop, &band, &rows_pad, &smem), "ingest: crop=%d does not fit in shared memory", crop);
   auto kern = ingest_v2_kernel<SRC, KS>;
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
+  static PerDeviceInt attr_cache;  // largest opt-in size set so far, per template instantiation and device
+  int& attr_bytes = attr_cache.get();
+  if (static_cast<int>(smem) > attr_bytes) {
     BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_bytes = smem;
+    attr_bytes = static_cast<int>(smem);
   }
   dim3 grid((kOut + band - 1) / band, n_tiles);
   constexpr bool kFromU8 = (SRC == kSrcU8);
@@ -516,10 +517,11 @@ int launch_ingest_t(const void* scene, const uint8_t* nodata, int Hs, int Ws, co
   BSEG_REQUIRE(smem <= 200 * 1024, "ingest: crop=%d band=%d needs %zu B of shared memory", crop, band, smem);
   constexpr bool kFromU8 = (SRC == kSrcU8);
   auto kern = ingest_kernel<SRC>;
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
+  static PerDeviceInt attr_cache;  // largest opt-in size set so far, per template instantiation and device
+  int& attr_bytes = attr_cache.get();
+  if (static_cast<int>(smem) > attr_bytes) {
     BSEG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_bytes = smem;
+    attr_bytes = static_cast<int>(smem);
   }
   dim3 grid((kOut + band - 1) / band, n_tiles);
   ProfScope prof(CAT_INGEST, 0,
@@ -557,6 +559,167 @@ int launch_preprocess_u8(const uint8_t* images, int chw, int n, int crop, const 
                          cudaStream_t stream) {
   return launch_ingest_t<kSrcU8>(nullptr, nullptr, 0, 0, nullptr, nullptr, n, crop, coef, bounds, ksize, band, max_rows,
                                mean255, std255, out_nchw, nullptr, 0, nullptr, nullptr, images, chw, prec, stream);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Native-resolution ingest: the model runs at the tile size (image_size == crop), so
+// get_crop skips the PIL resize (src/data.py:94, `if inpt_size != crop_size`) and the chain is purely per pixel:
+// composite -> u8 -> /255 -> (x - mean)/std, same arithmetic as above (the normalise goes through a 3 x 256 table of
+// the exact IEEE results).  HBM-bound: 9 B in (4 x u16 + nodata), 12 B out (+3 / +1 for the optional u8 / nodata
+// crops) per pixel; one thread handles four consecutive pixels with 8-byte band loads and 16-byte stores when the box
+// is aligned and inside the scene, else pixel by pixel with the reference's zero / nodata padding.
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024)
+ingest_native_kernel(const T* __restrict__ scene, const uint8_t* __restrict__ nodata, int Hs, int Ws,
+                     const float* __restrict__ stats, const int* __restrict__ boxes, int crop, float m0, float m1,
+                     float m2, float s0, float s1, float s2, float* __restrict__ out_nchw, uint8_t* __restrict__ out_u8,
+                     uint8_t* __restrict__ out_nodata) {
+  __shared__ float lut[3][256];
+  // uint16 scenes: the clipped, min-subtracted composite takes 3001 values (channels 0, 1) / 6001 half-integer values
+  // (channel 2 = mean of two bands), so the three IEEE divisions per pixel become table look-ups of the exact results
+  __shared__ uint8_t clut[3001 + 3001 + 6001 + 1];
+  const float mn = stats[0];
+  const float hi = __fadd_rn(3000.0f, mn);
+  float den[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) den[c] = __fsub_rn(fminf(fmaxf(stats[1 + c], mn), hi), mn);
+  const bool use_clut = sizeof(T) == 2 && mn >= 0.f && mn <= 65535.f && mn == floorf(mn);
+  {
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+      const int c = i >> 8, u = i & 255;
+      lut[c][u] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u), 255.0f), mean[c]), stdv[c]);
+    }
+    if (use_clut) {
+      for (int i = threadIdx.x; i < 3001 + 3001 + 6001; i += blockDim.x) {
+        const int c = i < 3001 ? 0 : (i < 6002 ? 1 : 2);
+        const float v = c == 0 ? mn + static_cast<float>(i) : c == 1 ? mn + static_cast<float>(i - 3001)
+                                                                      : mn + 0.5f * static_cast<float>(i - 6002);
+        clut[i] = composite_u8(v, mn, den[c]);
+      }
+    }
+  }
+  __syncthreads();
+  const int mn_i = static_cast<int>(mn);
+  const int tile = blockIdx.y;
+  const int xmin = boxes[tile * 4 + 0], ymin = boxes[tile * 4 + 1];
+  const long long npix = static_cast<long long>(Hs) * Ws;
+  const long long plane = static_cast<long long>(crop) * crop;
+  float* o_tile = out_nchw + static_cast<long long>(tile) * 3 * plane;
+  const bool fast = sizeof(T) == 2 && (crop & 3) == 0 && (xmin & 3) == 0 && (Ws & 3) == 0 && xmin >= 0 && ymin >= 0 &&
+                    xmin + crop <= Ws && ymin + crop <= Hs;
+  const int quads = crop >> 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < crop * ((crop + 3) >> 2); i += gridDim.x * blockDim.x) {
+    const int row = i / ((crop + 3) >> 2), qx = (i % ((crop + 3) >> 2)) * 4;
+    uint8_t v[4][3], nd[4];
+    if (fast) {
+      const long long p = static_cast<long long>(ymin + row) * Ws + xmin + qx;
+      const uint32_t ndw = *reinterpret_cast<const uint32_t*>(nodata + p);
+      ushort4 b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) b[k] = *reinterpret_cast<const ushort4*>(reinterpret_cast<const uint16_t*>(scene) + k * npix + p);
+      const unsigned short* b0 = &b[0].x; const unsigned short* b1 = &b[1].x;
+      const unsigned short* b2 = &b[2].x; const unsigned short* b3 = &b[3].x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        nd[j] = ((ndw >> (8 * j)) & 0xffu) ? 1 : 0;
+        v[j][0] = v[j][1] = v[j][2] = 0;
+        if (!nd[j]) {
+          if (use_clut) {
+            v[j][0] = clut[min(max(static_cast<int>(b3[j]) - mn_i, 0), 3000)];
+            v[j][1] = clut[3001 + min(max(static_cast<int>(b2[j]) - mn_i, 0), 3000)];
+            v[j][2] = clut[6002 + min(max(static_cast<int>(b0[j]) + static_cast<int>(b1[j]) - 2 * mn_i, 0), 6000)];
+          } else {
+            v[j][0] = composite_u8(static_cast<float>(b3[j]), mn, den[0]);
+            v[j][1] = composite_u8(static_cast<float>(b2[j]), mn, den[1]);
+            v[j][2] = composite_u8(__fmul_rn(__fadd_rn(static_cast<float>(b0[j]), static_cast<float>(b1[j])), 0.5f), mn, den[2]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sy = ymin + row, sx = xmin + qx + j;
+        v[j][0] = v[j][1] = v[j][2] = 0;
+        nd[j] = 1;
+        if (qx + j < crop && sy >= 0 && sy < Hs && sx >= 0 && sx < Ws) {
+          const long long p = static_cast<long long>(sy) * Ws + sx;
+          nd[j] = nodata[p] ? 1 : 0;
+          if (!nd[j]) {
+            const float b0 = scene[p], b1 = scene[npix + p], b2 = scene[2 * npix + p], b3 = scene[3 * npix + p];
+            v[j][0] = composite_u8(b3, mn, den[0]);
+            v[j][1] = composite_u8(b2, mn, den[1]);
+            v[j][2] = composite_u8(__fmul_rn(__fadd_rn(b0, b1), 0.5f), mn, den[2]);
+          }
+        }
+      }
+    }
+    const long long o = static_cast<long long>(row) * crop + qx;
+    if (fast || qx + 3 < crop) {
+      if ((crop & 3) == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          *reinterpret_cast<float4*>(o_tile + c * plane + o) =
+              make_float4(lut[c][v[0][c]], lut[c][v[1][c]], lut[c][v[2][c]], lut[c][v[3][c]]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o_tile[c * plane + o + j] = lut[c][v[j][c]];
+      }
+    } else {
+      for (int j = 0; qx + j < crop; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o_tile[c * plane + o + j] = lut[c][v[j][c]];
+    }
+    for (int j = 0; j < 4 && qx + j < crop; ++j) {
+      if (out_u8) {
+        uint8_t* u = out_u8 + (static_cast<long long>(tile) * plane + o + j) * 3;
+        u[0] = v[j][0]; u[1] = v[j][1]; u[2] = v[j][2];
+      }
+      if (out_nodata) out_nodata[static_cast<long long>(tile) * plane + o + j] = nd[j];
+    }
+  }
+  (void)quads;
+}
+
+template <typename T>
+static int launch_ingest_native_t(const T* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                                  const int* boxes, int n_tiles, int crop, const float* mean, const float* stdv,
+                                  float* out_nchw, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream) {
+  if (n_tiles == 0) return 0;
+  BSEG_REQUIRE(crop > 0 && out_nchw != nullptr, "ingest_native: bad arguments");
+  BSEG_REQUIRE((reinterpret_cast<uintptr_t>(scene) & 7) == 0 && (reinterpret_cast<uintptr_t>(nodata) & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out_nchw) & 15) == 0,
+               "ingest_native: misaligned buffers");
+  // two CTAs of 1024 threads per SM over all tiles: large CTAs amortise the 12 K-entry composite table each one builds
+  const int work = crop * ((crop + 3) / 4);
+  int bx = (work + 1023) / 1024;
+  const int cap = (num_sms() * 2 + n_tiles - 1) / n_tiles;
+  if (bx > cap) bx = cap < 1 ? 1 : cap;
+  ProfScope prof(CAT_INGEST, 0,
+                 static_cast<double>(n_tiles) * crop * crop * ((sizeof(T) == 2 ? 9.0 : 17.0) + 12.0 + (out_u8 ? 3 : 0) +
+                                                               (out_nodata ? 1 : 0)),
+                 stream);
+  ingest_native_kernel<T><<<dim3(bx, n_tiles), 1024, 0, stream>>>(scene, nodata, Hs, Ws, stats, boxes, crop, mean[0], mean[1],
+                                                                 mean[2], stdv[0], stdv[1], stdv[2], out_nchw, out_u8,
+                                                                 out_nodata);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+int launch_ingest_native(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                         const int* boxes, int n_tiles, int crop, const float* mean, const float* stdv, float* out_nchw,
+                         uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream) {
+  return launch_ingest_native_t(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, mean, stdv, out_nchw, out_u8,
+                                out_nodata, stream);
+}
+int launch_ingest_native_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                             const int* boxes, int n_tiles, int crop, const float* mean, const float* stdv,
+                             float* out_nchw, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream) {
+  return launch_ingest_native_t(scene, nodata, Hs, Ws, stats, boxes, n_tiles, crop, mean, stdv, out_nchw, out_u8,
+                                out_nodata, stream);
 }
 
 }  // namespace bseg

@@ -110,6 +110,13 @@ int launch_ingest_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws,
                       int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
                       const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,
                       long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
+// native-resolution ingest (image_size == crop: no resize): composite -> u8 -> /255 -> normalise, [n,3,crop,crop]
+int launch_ingest_native(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                         const int* boxes, int n_tiles, int crop, const float* mean, const float* stdv, float* out_nchw,
+                         uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
+int launch_ingest_native_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                             const int* boxes, int n_tiles, int crop, const float* mean, const float* stdv,
+                             float* out_nchw, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
 // augment.cu : kornia train augmentations (src/data.py:195-224) forward + gradient w.r.t. the image
 int launch_train_aug_fwd(const float* image, const uint8_t* mask, const float* params, const int* order, const float* noise,
                          float noise_mean, float noise_std, const float* mean, const float* stdv, float* out_image,

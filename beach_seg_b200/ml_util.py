@@ -7,16 +7,18 @@ from . import _lib, ops
 from .seggpt import SegGptB200
 
 
-def load_model(checkpoint: str, device: str | torch.device = "cuda:0", **kw) -> SegGptB200:
+def load_model(checkpoint: str, device: str | torch.device = "cuda:0", image_size: int = 448, **kw) -> SegGptB200:
     """src/util/ml_util.py:7-13: `from_pretrained(checkpoint)`, freeze, eval.  The reference then wraps the module in
     torch.compile; here the frozen backbone is packed once into the kernel layouts of libbseg.so instead.
-    `checkpoint="random-init:<seed>"` builds HF's seeded random init (the only option without network access)."""
+    `checkpoint="random-init:<seed>"` builds HF's seeded random init (the only option without network access);
+    with `image_size=512` that is the native-resolution variant `SegGptConfig(image_size=(1024, 512))`."""
     from transformers import SegGptConfig, SegGptForImageSegmentation
 
     if checkpoint.startswith("random-init"):
         seed = int(checkpoint.split(":")[1]) if ":" in checkpoint else 0
         torch.manual_seed(seed)
-        hf = SegGptForImageSegmentation(SegGptConfig())
+        cfg = SegGptConfig() if image_size == 448 else SegGptConfig(image_size=[2 * image_size, image_size])
+        hf = SegGptForImageSegmentation(cfg)
     else:
         hf = SegGptForImageSegmentation.from_pretrained(checkpoint)
     for p in hf.parameters():  # freeze the backbone

@@ -140,19 +140,38 @@ def merge_mosaic(data: torch.Tensor, yesdata: torch.Tensor):
 
 def ingest_tiles(scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Tensor, boxes: torch.Tensor,
                  crop: int, want_nchw: bool = True, want_u8: bool = False, want_nodata: bool = False,
-                 out_patch: Optional[torch.Tensor] = None, patch_tile_stride: int = 0, normalize: bool = True):
+                 out_patch: Optional[torch.Tensor] = None, patch_tile_stride: int = 0, normalize: bool = True,
+                 out_size: int = 448):
     """tif_image + crop_tif + PIL BICUBIC resize to 448 + /255 + Normalize for a batch of tile boxes
     (src/util/geo_util.py:454-468,297-341; src/data.py:93-124,226-229).
     boxes: int32 [n,4] (xmin,ymin,xmax,ymax) on the device.  Returns dict with the requested outputs:
     image float32 [n,3,448,448], u8 uint8 [n,crop,crop,3], nodata uint8 [n,crop,crop].
     normalize=False stops after `/255` (the dataset item of src/data.py:93-96, before any augmentation pipeline): the
-    input of `augment.TrainAug` for the training batch (src/data.py:295-313), which ends with Normalize itself."""
+    input of `augment.TrainAug` for the training batch (src/data.py:295-313), which ends with Normalize itself.
+    out_size: 448 (the reference's inpt_size) or == crop for the native-resolution mode, where get_crop skips the
+    resize (src/data.py:94) and the image is float32 [n,3,crop,crop]."""
     _need_cuda(scene_u16, nodata, stats, boxes)
     scene_u16, is_f32 = _scene_kind(scene_u16)
     dev = scene_u16.device
     _, Hs, Ws = scene_u16.shape
     n = boxes.shape[0]
     nd = nodata.to(torch.uint8).contiguous()
+    if out_size != 448:
+        if out_size != crop:
+            raise _lib.BsegError(f"ingest_tiles: out_size must be 448 or the crop size ({crop}), got {out_size}")
+        if out_patch is not None or not want_nchw:
+            raise _lib.BsegError("ingest_tiles: the native-resolution path writes the NCHW image only")
+        out = {"image": torch.empty((n, 3, crop, crop), dtype=torch.float32, device=dev),
+               "u8": torch.empty((n, crop, crop, 3), dtype=torch.uint8, device=dev) if want_u8 else None,
+               "nodata": torch.empty((n, crop, crop), dtype=torch.uint8, device=dev) if want_nodata else None}
+        boxes_n = boxes.to(torch.int32).contiguous()
+        with torch.cuda.device(dev):
+            fn = _lib.lib().bseg_ingest_native_f32x4 if is_f32 else _lib.lib().bseg_ingest_native_u16x4
+            _lib.check(fn(_lib.ptr(scene_u16), _lib.ptr(nd), Hs, Ws, _lib.ptr(stats), _lib.ptr(boxes_n), n, crop,
+                          _lib.f3(IMAGE_MEAN if normalize else (0.0, 0.0, 0.0)),
+                          _lib.f3(IMAGE_STD if normalize else (1.0, 1.0, 1.0)), _lib.ptr(out["image"]),
+                          _lib.ptr(out["u8"]), _lib.ptr(out["nodata"]), _lib.stream_ptr()), "bseg_ingest_native")
+        return out
     bounds, coef, ksize = _device_table(crop, dev)
     out = {}
     out["image"] = torch.empty((n, 3, 448, 448), dtype=torch.float32, device=dev) if want_nchw else None

@@ -47,6 +47,9 @@ class TilePredictor:
         self.crop_size = crop_size
         self.num_classes = num_classes
         self.random_palette = random_palette  # the reference's forward passes train=True (src/model.py:134)
+        self.image_size = getattr(model, "image_size", 448)
+        if self.image_size != 448 and self.image_size != crop_size:
+            raise ValueError(f"native-resolution model (image_size={self.image_size}) needs crop_size == image_size")
 
     @torch.no_grad()
     def predict_tiles(self, scene_u16: torch.Tensor, nodata: torch.Tensor, stats: torch.Tensor, boxes: torch.Tensor,
@@ -61,7 +64,7 @@ class TilePredictor:
         if palette is None:
             palette = create_palette(self.num_classes, n, self.random_palette, dev)
         pal_u8, pal_norm = palette
-        tiles = ops.ingest_tiles(scene_u16, nodata, stats, boxes, self.crop_size)
+        tiles = ops.ingest_tiles(scene_u16, nodata, stats, boxes, self.crop_size, out_size=self.image_size)
         prompt_color = ops.colorize_norm(prompt_masks, pal_u8)
         out = self.model(pixel_values=tiles["image"], prompt_pixel_values=prompt_images, prompt_masks=prompt_color,
                          embedding_type="instance", query_half_only=self.query_half_only)

@@ -148,6 +148,16 @@ int bseg_ingest_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int 
                       int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,
                       long long patch_tile_stride, uint8_t* out_u8, uint8_t* out_nodata, void* stream);
 
+/* The same chain when the model runs at the tile size (native-resolution mode, image_size == crop): get_crop skips the
+ * resize (src/data.py:94), so this is tif_image + crop_tif + /255 + Normalize only -- a purely HBM-bound pass (9 B in,
+ * 12 B out per pixel).  out_nchw fp32 [n,3,crop,crop] (required); out_u8 / out_nodata as above, nullable. */
+int bseg_ingest_native_u16x4(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                             const int32_t* boxes, int n_tiles, int crop, const float* mean, const float* stdv,
+                             float* out_nchw, uint8_t* out_u8, uint8_t* out_nodata, void* stream);
+int bseg_ingest_native_f32x4(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
+                             const int32_t* boxes, int n_tiles, int crop, const float* mean, const float* stdv,
+                             float* out_nchw, uint8_t* out_u8, uint8_t* out_nodata, void* stream);
+
 /* The same two calls for a float32 scene [4,Hs,Ws] — what merge_tifs hands to tif_image (src/util/geo_util.py:385,
  * 417-420: rasters are read with out_dtype=float32 and averaged).  Values may be negative (cubic reprojection
  * overshoot); the statistics use order-preserving keys in `scratch`. */

@@ -117,3 +117,66 @@ def test_native_512_interface(dev):
         model(pixel_values=z, prompt_pixel_values=z.clone().requires_grad_(True), prompt_masks=z)
     with pytest.raises(NotImplementedError):
         SegGptB200.from_hf(hf, device=dev, precision="fp32")
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_native_ingest_bit_exact(dev, f32):
+    """bseg_ingest_native_*: tif_image + crop_tif + /255 + Normalize with NO resize (src/data.py:94 skips it when
+    inpt_size == crop_size), bit-exact against the oracle glue -- aligned boxes (vector path), unaligned and
+    out-of-scene boxes (scalar path with the reference's zero / nodata padding)."""
+    import numpy as np
+
+    Hs, Ws, crop = 700, 1100, 512
+    scene = synth.scene_u16(Hs, Ws, seed=21)
+    nodata = synth.nodata_wedge(Hs, Ws, 0.05)
+    boxes = np.array([[0, 0, 512, 512], [512, 128, 1024, 640], [301, 77, 813, 589], [-40, -60, 472, 452],
+                      [900, 500, 1412, 1012]], dtype=np.int32)
+    data = scene.astype(np.float32)
+    u8 = glue_ref.tif_image_4band(data.copy(), nodata)
+    sc = torch.from_numpy(data if f32 else scene.view(np.int16)).to(dev)
+    nd = torch.from_numpy(nodata).to(dev)
+    stats = ops.scene_stats(sc, nd)
+    out = ops.ingest_tiles(sc, nd, stats, torch.from_numpy(boxes).to(dev), crop, want_u8=True, want_nodata=True,
+                           out_size=crop)
+    assert out["image"].shape == (len(boxes), 3, crop, crop)
+    for i, b in enumerate(boxes):
+        ci, cn, _ = glue_ref.crop_tif(tuple(int(v) for v in b), u8, nodata, None, crop)
+        want = glue_ref.normalize(torch.from_numpy(glue_ref.get_crop_image(ci, crop))[None])[0]
+        assert np.array_equal(out["u8"][i].cpu().numpy(), ci), i
+        assert np.array_equal(out["nodata"][i].cpu().numpy().astype(bool), cn), i
+        assert torch.equal(out["image"][i].cpu(), want), i
+
+
+def test_native_tile_predictor_end_to_end(dev):
+    """TilePredictor on a native-resolution backbone: ingest (no resize) -> forward at 512 -> palette decode at 512 ->
+    votes, against the oracle pipeline driven by the HF module."""
+    import numpy as np
+
+    from beach_seg_b200.predict import TilePredictor
+
+    hf = make_reference_model(seed=4, stress=True, image_size=512, **SMALL)
+    model = SegGptB200.from_hf(hf, device=dev)
+    with pytest.raises(ValueError):
+        TilePredictor(model, 448)
+    pred = TilePredictor(model, 512, random_palette=False)
+    Hs, Ws = 512, 1024
+    scene = synth.scene_u16(Hs, Ws, seed=22)
+    nodata = np.zeros((Hs, Ws), dtype=bool)
+    boxes = np.array([[0, 0, 512, 512], [512, 0, 1024, 512]], dtype=np.int32)
+    sc, nd = torch.from_numpy(scene.view(np.int16)).to(dev), torch.from_numpy(nodata).to(dev)
+    stats = ops.scene_stats(sc, nd)
+    ppx = synth.normalize(synth.smooth_image(2, 60, size=512))
+    pcls = synth.blocky_mask(2, 61, size=512)
+    cls = pred.predict_tiles(sc, nd, stats, torch.from_numpy(boxes).to(dev), ppx.to(dev), pcls.to(dev)).cpu()
+    assert cls.shape == (2, 512, 512) and cls.dtype == torch.uint8
+    u8 = glue_ref.tif_image_4band(scene.astype(np.float32), nodata)
+    pal, paln = glue_ref.create_palette(4, 2, train=False)
+    px = torch.stack([glue_ref.normalize(torch.from_numpy(glue_ref.get_crop_image(
+        glue_ref.crop_tif(tuple(int(v) for v in b), u8, nodata, None, 512)[0], 512))[None])[0] for b in boxes])
+    pm = glue_ref.normalize(glue_ref.torch_apply_mask_rgb(pal, pcls[:, None]))
+    with torch.no_grad():
+        want = hf(pixel_values=px, prompt_pixel_values=ppx, prompt_masks=pm, embedding_type="instance").pred_masks
+    d = ((want[:, :, 512:].permute(0, 2, 3, 1)[:, :, :, None, :] - paln[:, None, None]) ** 2).sum(-1)
+    flips = (cls.long() != d.argmin(-1)).float().mean().item()
+    print(f"[native TilePredictor] class flips vs oracle pipeline {flips * 100:.3f} %")
+    assert flips < 0.01
