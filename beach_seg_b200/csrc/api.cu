@@ -191,8 +191,8 @@ int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream_) {
     BSEG_REQUIRE(w->intermediate_indices[j] >= w->merge_index && w->intermediate_indices[j] < w->num_layers,
                  "bseg_create: intermediate index %d out of range", w->intermediate_indices[j]);
   const int img = w->image_size > 0 ? w->image_size : BSEG_IMG;
-  BSEG_REQUIRE(img == 448 || img == 512,
-               "bseg_create: image_size=%d is not built (448 = the resized path, 512 = native 512-px tiles)", img);
+  BSEG_REQUIRE(img == 448 || img == 512 || img == 1024,
+               "bseg_create: image_size=%d is not built (448 = the resized path, 512 / 1024 = native tiles)", img);
   bseg_handle* h = new (std::nothrow) bseg_handle();
   BSEG_REQUIRE(h != nullptr, "bseg_create: out of host memory");
   h->img = img;

@@ -53,6 +53,8 @@ namespace bseg {
 // Token grid GH x GW of the stacked (prompt over query) image and ROWS token rows per key block:
 //   56 x 28, 4 rows  (896 x 448 px: the resized path, T = 1568, key blocks of 112)
 //   64 x 32, 2 rows  (1024 x 512 px: native 512-px tiles, SURVEY 8(f) rank 4, T = 2048, key blocks of 64)
+//  128 x 64, 1 row   (2048 x 1024 px: native 1024-px tiles, T = 8192, key blocks of 64; the rel tables (255 + 127 rows) do
+//                     not fit TMEM's 256 columns at once, so G is computed in two passes)
 template <int GH, int GW, int ROWS>
 struct AttnCfg {
   static constexpr int kQTile = 128;            // queries per CTA
@@ -70,17 +72,21 @@ struct AttnCfg {
   static constexpr int kRelH = (2 * GH - 1 + 15) / 16 * 16;  // rows of the reversed rel_pos_h table: 111 -> 112 | 127 -> 128
   static constexpr int kRelW = (2 * GW - 1 + 15) / 16 * 16;  // rows of the reversed rel_pos_w table: 55 -> 64 | 63 -> 64
   static constexpr int kRelRows = kRelH + kRelW;             // 176 | 192
-  static_assert(GW <= 32 && GW % 2 == 0 && ROWS <= 4 && kKB % 16 == 0 && kT % kKB == 0 && kRelRows <= 256, "token grid");
+  static constexpr bool kTwoPassG = kRelRows > 256;          // G = Qs relcat8^T in two passes (height, then width)
+  static constexpr int kEwSteps = (GW + 15) / 16;            // K-steps of the width-bias MMA: 2 | 2 | 4
+  static constexpr int kEhBase = kEwSteps * 16;              // first K-column of the Eh step in the one-hot operand
+  static constexpr int kOneHotAtoms = (kEhBase + 16 + 63) / 64;  // 128-byte-row tiles of the one-hot operand: 1 | 1 | 2
+  static_assert(GW % 2 == 0 && ROWS <= 4 && kKB % 16 == 0 && kT % kKB == 0 && kRelH <= 256 && kRelW <= 256, "token grid");
 
   static constexpr int kQBytes = kQTile * 128;                  // 16384
   static constexpr int kKBytes = kKB * 128;                     // 14336 | 8192
   static constexpr int kVHalves = (kKB + 63) / 64;              // V^T arrives in 64-key halves: 2 | 1
   static constexpr int kVBytes = kVHalves * 64 * 128;           // 16384 | 8192
-  static constexpr int kRelBytes = kRelRows * 128;              // 22528 | 24576
-  static constexpr int kOneHotBytes = kKB * 128;                // one-hot B operand [keys][64 fp16], 48 columns used
+  static constexpr int kRelBytes = (kTwoPassG ? kRelH : kRelRows) * 128;  // 22528 | 24576 | 32768 (height table, then width)
+  static constexpr int kOneHotBytes = kOneHotAtoms * kKB * 128; // one-hot B operand [keys][64 fp16] per atom
   static constexpr int kBhStride = GH / 2 + 2;                  // 32-bit words per row of the packed height-bias table (30 | 34)
   static constexpr int kBhBytes = kQTile * kBhStride * 4;
-  static constexpr int kBwStride = GW + 1;
+  static constexpr int kBwStride = GW % 32 == 0 && GW > 32 ? GW : GW + 1;
   static constexpr int kBwBytes = kQTile * kBwStride * 4;       // staging of the per-query width bias in the prologue
 
   static constexpr int kOffQ = 0;
@@ -103,7 +109,7 @@ struct AttnCfg {
   static constexpr uint32_t kColO = kKB;
   static constexpr uint32_t kColP = kColO + 64;
   static constexpr uint32_t kColEw = kColP + kKB / 2;
-  static constexpr uint32_t kColEh = kColEw + 16;
+  static constexpr uint32_t kColEh = kColEw + kEhBase / 2;
   static_assert(kColEh + 8 <= kTmemCols, "TMEM budget");
 };
 
@@ -178,13 +184,16 @@ __device__ __forceinline__ float row_max(const float (&x)[KB]) {
 // packed fp16 height bias of key block kb from a row of the table: ROWS values (two words for 4 rows, one for 2)
 template <int ROWS>
 __device__ __forceinline__ void bh_block(const uint32_t* bh_row, int kb, uint32_t& w0, uint32_t& w1) {
-  static_assert(ROWS == 4 || ROWS == 2, "token rows per key block");
+  static_assert(ROWS == 4 || ROWS == 2 || ROWS == 1, "token rows per key block");
   if (ROWS == 4) {
     const uint2 g = *reinterpret_cast<const uint2*>(bh_row + 2 * kb);
     w0 = g.x;
     w1 = g.y;
-  } else {
+  } else if (ROWS == 2) {
     w0 = bh_row[kb];
+    w1 = 0u;
+  } else {
+    w0 = reinterpret_cast<const unsigned short*>(bh_row)[kb];  // (upper half zero)
     w1 = 0u;
   }
 }
@@ -220,7 +229,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* p_full = bars + 12;    // softmax -> MMA: P_j is in TMEM (and O rescaled if it had to be)
   uint64_t* pv_done = bars + 13;   // MMA -> softmax: O += P_j V_j retired (P region free, O stable)
   uint64_t* rel_free = bars + 14;  // softmax -> TMA: the rel / bw staging region is dead (it overlays the K / V stages)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* gh_done = bars + 15;   // (two-pass G) softmax -> MMA: the height part of G has been read out of TMEM
+  uint64_t* q2_full = bars + 16;   // (two-pass G) TMA -> MMA: the width rel table is in smem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -250,13 +261,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     mbar_init(s_free, 4);     // one arrive per softmax warp
     mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
+    mbar_init(gh_done, 4);
+    mbar_init(q2_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  // One-hot B operand of the bias MMAs, K-major rows of 128 B with the 128-byte swizzle: row n = key n of a block,
-  // fp16 columns 0..GW-1 = [n % GW == column], 32..32+ROWS-1 = [n / GW == column - 32], 36 = 1 (the -m column), rest 0.
-  for (int idx = threadIdx.x; idx < kKB * 8; idx += Cfg::kThreads) {
-    const int n = idx >> 3, c = idx & 7;
+  // One-hot B operand of the bias MMAs, K-major rows of 128 B with the 128-byte swizzle (one tile of kKB rows per 64
+  // K-columns): row n = key n of a block, fp16 columns 0..GW-1 = [n % GW == column], kEhBase..kEhBase+ROWS-1 =
+  // [n / GW == column - kEhBase], kEhBase + 4 = 1 (the -m column), rest 0.
+  constexpr int kEhBase = Cfg::kEhBase;
+  for (int idx = threadIdx.x; idx < Cfg::kOneHotAtoms * kKB * 8; idx += Cfg::kThreads) {
+    const int atom = idx / (kKB * 8), n = (idx >> 3) % kKB, c = idx & 7;
     const int kw = n % kGridW, j = n / kGridW;
     uint32_t w[4];
 #pragma unroll
@@ -264,13 +279,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       uint32_t pair = 0;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int col = 8 * c + 2 * e + hf;
-        const bool one = (col < 32) ? (col < kGridW && col == kw) : (col < 36) ? (col - 32 == j) : (col == 36);
+        const int col = 64 * atom + 8 * c + 2 * e + hf;
+        const bool one = (col < kEhBase) ? (col < kGridW && col == kw)
+                                         : (col < kEhBase + 4) ? (col - kEhBase == j) : (col == kEhBase + 4);
         if (one) pair |= 0x3C00u << (16 * hf);
       }
       w[e] = pair;
     }
-    *reinterpret_cast<uint4*>(sOneHot + n * 128 + ((c ^ (n & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(sOneHot + atom * (kKB * 128) + n * 128 + ((c ^ (n & 7)) << 4)) =
+        make_uint4(w[0], w[1], w[2], w[3]);
   }
   fence_proxy_async_smem();  // generic-proxy writes above -> visible to the tensor core's async-proxy reads
   tc_fence_before();
@@ -285,9 +302,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(q_full, Cfg::kQBytes + Cfg::kRelBytes);
         tma_load_3d(sQ, &tmap_q, q_full, 0, q0, sh);
-        tma_load_2d(sRel, &tmap_rel, q_full, 0, 0);
+        tma_load_2d(sRel, &tmap_rel, q_full, 0, 0);  // all of relcat8, or its height part (two-pass G)
       }
       __syncwarp();
+      if constexpr (Cfg::kTwoPassG) {
+        mbar_wait(g_full, 0);  // the height MMAs have read their table: the width table may take its place
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(q2_full, Cfg::kRelBytes);  // (a full box: the rows past the table arrive as zeros)
+          tma_load_2d(sRel, &tmap_rel, q2_full, 0, kRelH);
+        }
+        __syncwarp();
+      }
       mbar_wait(rel_free, 0);  // the rel tables / bw staging overlay the K and V stages
       for (int kb = 0; kb < kNumKB; ++kb) {
         const int st = kb % kStages;
@@ -312,7 +337,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // in uniform registers.
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
       constexpr uint32_t idesc_e = umma_idesc_f16(128, kKB);
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, Cfg::kTwoPassG ? kRelH : kRelRows);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t rel_addr = smem_u32(sRel);
@@ -329,6 +354,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         umma_commit(g_full);
       }
       __syncwarp();
+      if constexpr (Cfg::kTwoPassG) {  // second pass: the width part of G into TMEM columns [0, kRelW)
+        constexpr uint32_t idesc_gw = umma_idesc_bf16(128, kRelW);
+        mbar_wait(q2_full, 0);
+        mbar_wait(gh_done, 0);
+        tc_fence_after();
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tm, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(rel_addr + k * 32),
+                         idesc_gw, k != 0);
+          umma_commit(g_full);
+        }
+        __syncwarp();
+      }
 
       auto issue_s = [&](int kb) {
         const int st = kb % kStages;
@@ -345,8 +384,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                          k != 0);
           // + width bias (2 K-steps), + height bias and -m (1 K-step): fp16 A operands from TMEM, one-hot B from smem
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
-            umma_bf16_ts(tm, tm + kColEw + k * 8, umma_desc_sw128_kmajor(onehot_addr + k * 32), idesc_e, 1u);
+          for (int k = 0; k <= Cfg::kEwSteps; ++k)  // (the last step is Eh)
+            umma_bf16_ts(tm, tm + kColEw + k * 8,
+                         umma_desc_sw128_kmajor(onehot_addr + (k >> 2) * (kKB * 128) + (k & 3) * 32), idesc_e, 1u);
           umma_commit(s_full);
           umma_commit(&k_empty[st]);
         }
@@ -405,11 +445,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           if (kh >= 0 && kh < kGridH) bh_half[kh] = __float2half_rn(v[i]);
         }
       }
-      const int off_w = (kGridW - 1) - qw;  // bw[kw] = G[kRelH + off_w + kw]
+      if constexpr (Cfg::kTwoPassG) {  // hand the G columns back: the width pass overwrites them
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gh_done);
+        mbar_wait(g_full, 1);
+        tc_fence_after();
+      }
+      constexpr int kGwCol0 = Cfg::kTwoPassG ? 0 : kRelH;  // first TMEM column of the width part of G
+      const int off_w = (kGridW - 1) - qw;  // bw[kw] = G[kGwCol0 + off_w + kw]
 #pragma unroll
       for (int c = 0; c < kRelW; c += 16) {
         float v[16];
-        tmem_ld16(lane_base + kRelH + c, v);
+        tmem_ld16(lane_base + kGwCol0 + c, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -419,10 +467,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
     }
     {
-      uint32_t ew[16];
+      constexpr int kEwWords = Cfg::kEhBase / 2;  // 16 | 32 packed fp16 pairs
 #pragma unroll
-      for (int i = 0; i < 16; ++i) ew[i] = (2 * i < kGridW) ? pack_f16x2(stage[2 * i], stage[2 * i + 1]) : 0u;
-      tmem_st16u(lane_base + kColEw, ew);
+      for (int w0 = 0; w0 < kEwWords; w0 += 16) {
+        uint32_t ew[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          ew[i] = (2 * (w0 + i) < kGridW) ? pack_f16x2(stage[2 * (w0 + i)], stage[2 * (w0 + i) + 1]) : 0u;
+        tmem_st16u(lane_base + kColEw + w0, ew);
+      }
       uint32_t g0, g1;
       bh_block<kRows>(bh_row, 0, g0, g1);
       tmem_st4u(lane_base + kColEh, g0, g1, 0u, 0u);       // height bias of key block 0, -m = 0
@@ -594,7 +647,8 @@ static int launch_attention_t(const __nv_bfloat16* q, const __nv_bfloat16* k, co
     if (rc) return rc;
   }
   {
-    int rc = make_tmap_bf16_2d(&tr, relcat, 64, Cfg::kRelRows, 64, 64, Cfg::kRelRows);
+    // one box = the whole table, or (two-pass G) its height part; the width part is a second box of kRelW rows
+    int rc = make_tmap_bf16_2d(&tr, relcat, 64, Cfg::kRelRows, 64, 64, Cfg::kTwoPassG ? Cfg::kRelH : Cfg::kRelRows);
     if (rc) return rc;
   }
   auto kern = attention_fwd_kernel<Cfg>;
@@ -624,8 +678,10 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     return launch_attention_t<AttnCfg<56, 28, 4>>(q, k, vt, relcat, out, lse_out, nseq, heads, stream);
   if (grid_h == 64 && grid_w == 32)
     return launch_attention_t<AttnCfg<64, 32, 2>>(q, k, vt, relcat, out, lse_out, nseq, heads, stream);
-  BSEG_REQUIRE(false, "attention: token grid %dx%d is not built (56x28 = the 448-px path, 64x32 = native 512-px tiles)",
-               grid_h, grid_w);
+  if (grid_h == 128 && grid_w == 64)
+    return launch_attention_t<AttnCfg<128, 64, 1>>(q, k, vt, relcat, out, lse_out, nseq, heads, stream);
+  BSEG_REQUIRE(false, "attention: token grid %dx%d is not built (56x28 = the 448-px path, 64x32 / 128x64 = native 512- / "
+               "1024-px tiles)", grid_h, grid_w);
   return 0;
 }
 

@@ -89,9 +89,9 @@ class SegGptB200(torch.nn.Module):
         """precision: "bf16" = the tcgen05 path (bf16 operands, fp32 accumulation / residual stream / softmax; logits
         within 1e-2 of the fp32 reference); "fp32" = the accuracy mode (bseg_forward_f32: everything IEEE fp32 on the
         CUDA cores, within 1e-4, inference only, ~30x slower).
-        image_size: 448 = the reference's path (crops resized to 448, `SegGptConfig()`); 512 = native-resolution mode for
-        512-px tiles (`SegGptConfig(image_size=(1024, 512))`: 64 x 32 tokens, T = 2048, rel-pos tables of 127 / 63 rows;
-        SURVEY section 8(f) rank 4) -- bf16 inference only.
+        image_size: 448 = the reference's path (crops resized to 448, `SegGptConfig()`); 512 / 1024 = native-resolution
+        mode for 512- / 1024-px tiles (`SegGptConfig(image_size=(2 * tile, tile))`: 64 x 32 tokens, T = 2048, rel-pos tables
+        of 127 / 63 rows; 128 x 64 tokens, T = 8192, 255 / 127 rows) -- bf16 inference only.
         graph_batch: inference calls with at most this many samples go through persistent staging buffers and a CUDA graph
         of the whole forward (bseg_set_graph_batch_limit): the reference's own call pattern is batch 1
         (src/predict.py:234), where the host work of ~190 launches is as long as the device work.  0 disables it."""
@@ -99,8 +99,8 @@ class SegGptB200(torch.nn.Module):
         if precision not in ("bf16", "fp32"):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         self.precision = precision
-        if image_size not in (448, 512):
-            raise ValueError(f"image_size must be 448 or 512 (native 512-px tiles), got {image_size}")
+        if image_size not in (448, 512, 1024):
+            raise ValueError(f"image_size must be 448, or 512 / 1024 (native-resolution tiles), got {image_size}")
         if image_size != IMG and precision != "bf16":
             raise NotImplementedError("the native-resolution mode runs on the bf16 path only")
         self.image_size = int(image_size)

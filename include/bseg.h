@@ -45,8 +45,9 @@ typedef struct bseg_layer_weights {
 
 typedef struct bseg_weights {
   int image_size;                 /* SegGptConfig.image_size[1]: 448 (or 0) = the reference's resized path, T = 1568;
-                                   * 512 = native-resolution mode for 512-px tiles (SegGptConfig(image_size=(1024,512)),
-                                   * 64 x 32 tokens, T = 2048, rel-pos tables of 127 / 63 rows): bf16 inference only */
+                                   * 512 / 1024 = native-resolution mode for 512- / 1024-px tiles
+                                   * (SegGptConfig(image_size=(2*tile, tile)): 64 x 32 tokens, T = 2048, rel-pos tables of
+                                   * 127 / 63 rows; 128 x 64 tokens, T = 8192, 255 / 127 rows): bf16 inference only */
   int num_layers;                 /* SegGptConfig.num_hidden_layers (24) */
   int merge_index;                /* SegGptConfig.merge_index (2) */
   int intermediate_indices[4];    /* SegGptConfig.intermediate_hidden_state_indices (5,11,17,23) */
@@ -284,7 +285,7 @@ int bseg_layernorm1024(const float* x, long long ldx, const float* gamma, const 
  * bseg_pack_relcat; out bf16 [nseq,1568,1024]. */
 int bseg_attention(const void* q, const void* k, const void* vt, const void* relcat, void* out, int nseq,
                    void* stream);
-/* The same for a token grid grid_h x grid_w (56 x 28, or 64 x 32 = native 512-px tiles, T = grid_h * grid_w), with
+/* The same for a token grid grid_h x grid_w (56 x 28; 64 x 32 / 128 x 64 = native 512- / 1024-px tiles), with
  * relcat from bseg_pack_relcat_grid (bseg_relcat_rows(grid_h, grid_w) x 64 bf16); lse may be NULL. */
 int bseg_attention_grid(const void* q, const void* k, const void* vt, const void* relcat, void* out, float* lse,
                         int nseq, int grid_h, int grid_w, void* stream);

@@ -68,7 +68,7 @@ def test_attention_64x32_matches_oracle(dev, nseq, qscale, relscale):
 def test_unknown_token_grid_is_rejected(dev):
     L = _lib.lib()
     z = torch.zeros(16, dtype=torch.bfloat16, device=dev)
-    rc = L.bseg_attention_grid(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), None, 1, 128, 64,
+    rc = L.bseg_attention_grid(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), None, 1, 96, 48,
                                _lib.stream_ptr())
     assert rc != 0 and b"not built" in L.bseg_last_error()
 
@@ -180,3 +180,62 @@ def test_native_tile_predictor_end_to_end(dev):
     flips = (cls.long() != d.argmin(-1)).float().mean().item()
     print(f"[native TilePredictor] class flips vs oracle pipeline {flips * 100:.3f} %")
     assert flips < 0.01
+
+
+def test_attention_128x64_matches_oracle(dev):
+    """bseg_attention_grid at the 128 x 64 token grid of native 1024-px tiles (T = 8192, key blocks of one token row, the
+    rel tables of 255 + 127 rows go through TMEM in two passes) against the oracle's attention, evaluated on the GPU one
+    head at a time (the 8192 x 8192 score matrix of a head is 268 MB)."""
+    gh, gw = 128, 64
+    t = gh * gw
+    g = torch.Generator().manual_seed(17)
+    qs = (torch.randn((1, 16, t, 64), generator=g) * 1.5 * Q_SCALE).to(torch.bfloat16).to(dev)
+    q = qs.float() / Q_SCALE
+    k = bf16r(torch.randn((1, 16, t, 64), generator=g)).to(dev)
+    v = bf16r(torch.randn((1, 16, t, 64), generator=g)).to(dev)
+    rel_h = bf16r(torch.randn((2 * gh - 1, 64), generator=g) * 0.4).to(dev)
+    rel_w = bf16r(torch.randn((2 * gw - 1, 64), generator=g) * 0.4).to(dev)
+    L = _lib.lib()
+    rows = L.bseg_relcat_rows(gh, gw)
+    assert rows == 384
+    relcat = torch.empty((rows, 64), dtype=torch.bfloat16, device=dev)
+    _lib.check(L.bseg_pack_relcat_grid(_lib.ptr(rel_h), _lib.ptr(rel_w), _lib.ptr(relcat), gh, gw, _lib.stream_ptr()))
+    kb = k.to(torch.bfloat16).contiguous()
+    vt = v.to(torch.bfloat16).transpose(2, 3).contiguous()
+    out = torch.empty((1, t, 1024), dtype=torch.bfloat16, device=dev)
+    _lib.check(L.bseg_attention_grid(_lib.ptr(qs), _lib.ptr(kb), _lib.ptr(vt), _lib.ptr(relcat), _lib.ptr(out), None, 1,
+                                     gh, gw, _lib.stream_ptr()), "bseg_attention_grid")
+    torch.cuda.synchronize()
+    got = out.float().reshape(t, 16, 64)
+    ih = (torch.arange(gh)[:, None] - torch.arange(gh)[None, :] + gh - 1).to(dev)
+    iw = (torch.arange(gw)[:, None] - torch.arange(gw)[None, :] + gw - 1).to(dev)
+    num = den = 0.0
+    for hd in range(16):
+        rq = q[0, hd].reshape(gh, gw, 64)
+        bias = (torch.einsum("hwc,hkc->hwk", rq, rel_h[ih])[:, :, :, None] +
+                torch.einsum("hwc,wkc->hwk", rq, rel_w[iw])[:, :, None, :]).reshape(t, t)
+        want = torch.softmax((q[0, hd] * 0.125) @ k[0, hd].T + bias, dim=-1) @ v[0, hd]
+        num += (got[:, hd] - want).pow(2).sum().item()
+        den += want.pow(2).sum().item()
+        del bias, want
+    rel = (num / den) ** 0.5
+    print(f"[attention 128x64] rel-L2={rel:.3e}")
+    assert rel < 1e-2
+
+
+def test_native_1024_model_vs_hf(dev):
+    """4-layer stress-initialised backbone at image_size 1024 (T = 8192): pred_masks [1, 3, 2048, 1024] against the HF
+    module (fp32, CPU: about 20 GB of score matrices, one sample)."""
+    # (HF concatenates one hidden state per DISTINCT intermediate index and the decoder needs four: four layers)
+    hf = make_reference_model(seed=6, stress=True, image_size=1024, num_layers=4, merge_index=0, intermediate=(0, 1, 2, 3))
+    model = SegGptB200.from_hf(hf, device=dev)
+    assert model.image_size == 1024 and model.num_patches == 8192
+    px, ppx, pm = synth.model_inputs(batch=1, seed=41, size=1024)
+    with torch.no_grad():
+        want = hf(pixel_values=px, prompt_pixel_values=ppx, prompt_masks=pm, embedding_type="instance").pred_masks
+        got = model(pixel_values=px.to(dev), prompt_pixel_values=ppx.to(dev), prompt_masks=pm.to(dev),
+                    embedding_type="instance").pred_masks
+    assert got.shape == (1, 3, 2048, 1024)
+    r = rel_l2(got.cpu(), want)
+    print(f"[native 1024] pred rel-L2={r:.3e}")
+    assert r < 1e-2
