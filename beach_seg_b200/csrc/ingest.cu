@@ -566,8 +566,8 @@ int launch_preprocess_u8(const uint8_t* images, int chw, int n, int crop, const 
 // get_crop skips the PIL resize (src/data.py:94, `if inpt_size != crop_size`) and the chain is purely per pixel:
 // composite -> u8 -> /255 -> (x - mean)/std, same arithmetic as above (the normalise goes through a 3 x 256 table of
 // the exact IEEE results).  HBM-bound: 9 B in (4 x u16 + nodata), 12 B out (+3 / +1 for the optional u8 / nodata
-// crops) per pixel; one thread handles four consecutive pixels with 8-byte band loads and 16-byte stores when the box
-// is aligned and inside the scene, else pixel by pixel with the reference's zero / nodata padding.
+// crops) per pixel; one thread handles eight consecutive pixels with 16-byte band loads and stores when the box is
+// aligned and inside the scene, else pixel by pixel with the reference's zero / nodata padding.
 // ----------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(1024)
@@ -607,23 +607,28 @@ ingest_native_kernel(const T* __restrict__ scene, const uint8_t* __restrict__ no
   const long long npix = static_cast<long long>(Hs) * Ws;
   const long long plane = static_cast<long long>(crop) * crop;
   float* o_tile = out_nchw + static_cast<long long>(tile) * 3 * plane;
-  const bool fast = sizeof(T) == 2 && (crop & 3) == 0 && (xmin & 3) == 0 && (Ws & 3) == 0 && xmin >= 0 && ymin >= 0 &&
+  // eight consecutive pixels per thread and iteration: 16-byte band loads, 8-byte nodata load, 2 x 16-byte stores per
+  // channel (enough bytes in flight per SM to cover the HBM latency with one 1024-thread CTA)
+  constexpr int PX = 8;
+  const bool fast = sizeof(T) == 2 && (crop % PX) == 0 && (xmin % PX) == 0 && (Ws % PX) == 0 && xmin >= 0 && ymin >= 0 &&
                     xmin + crop <= Ws && ymin + crop <= Hs;
-  const int quads = crop >> 2;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < crop * ((crop + 3) >> 2); i += gridDim.x * blockDim.x) {
-    const int row = i / ((crop + 3) >> 2), qx = (i % ((crop + 3) >> 2)) * 4;
-    uint8_t v[4][3], nd[4];
+  const int groups = (crop + PX - 1) / PX;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < crop * groups; i += gridDim.x * blockDim.x) {
+    const int row = i / groups, qx = (i % groups) * PX;
+    uint8_t v[PX][3], nd[PX];
     if (fast) {
       const long long p = static_cast<long long>(ymin + row) * Ws + xmin + qx;
-      const uint32_t ndw = *reinterpret_cast<const uint32_t*>(nodata + p);
-      ushort4 b[4];
+      const uint2 ndw = *reinterpret_cast<const uint2*>(nodata + p);
+      uint4 b[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) b[k] = *reinterpret_cast<const ushort4*>(reinterpret_cast<const uint16_t*>(scene) + k * npix + p);
-      const unsigned short* b0 = &b[0].x; const unsigned short* b1 = &b[1].x;
-      const unsigned short* b2 = &b[2].x; const unsigned short* b3 = &b[3].x;
+      for (int k = 0; k < 4; ++k) b[k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(scene) + k * npix + p);
+      const unsigned short* b0 = reinterpret_cast<const unsigned short*>(&b[0]);
+      const unsigned short* b1 = reinterpret_cast<const unsigned short*>(&b[1]);
+      const unsigned short* b2 = reinterpret_cast<const unsigned short*>(&b[2]);
+      const unsigned short* b3 = reinterpret_cast<const unsigned short*>(&b[3]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        nd[j] = ((ndw >> (8 * j)) & 0xffu) ? 1 : 0;
+      for (int j = 0; j < PX; ++j) {
+        nd[j] = (((j < 4 ? ndw.x : ndw.y) >> (8 * (j & 3))) & 0xffu) ? 1 : 0;
         v[j][0] = v[j][1] = v[j][2] = 0;
         if (!nd[j]) {
           if (use_clut) {
@@ -639,7 +644,7 @@ ingest_native_kernel(const T* __restrict__ scene, const uint8_t* __restrict__ no
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < PX; ++j) {
         const int sy = ymin + row, sx = xmin + qx + j;
         v[j][0] = v[j][1] = v[j][2] = 0;
         nd[j] = 1;
@@ -656,32 +661,29 @@ ingest_native_kernel(const T* __restrict__ scene, const uint8_t* __restrict__ no
       }
     }
     const long long o = static_cast<long long>(row) * crop + qx;
-    if (fast || qx + 3 < crop) {
-      if ((crop & 3) == 0) {
+    if (qx + PX <= crop && (crop & 3) == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          *reinterpret_cast<float4*>(o_tile + c * plane + o) =
-              make_float4(lut[c][v[0][c]], lut[c][v[1][c]], lut[c][v[2][c]], lut[c][v[3][c]]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o_tile[c * plane + o + j] = lut[c][v[j][c]];
+      for (int c = 0; c < 3; ++c) {
+        *reinterpret_cast<float4*>(o_tile + c * plane + o) =
+            make_float4(lut[c][v[0][c]], lut[c][v[1][c]], lut[c][v[2][c]], lut[c][v[3][c]]);
+        *reinterpret_cast<float4*>(o_tile + c * plane + o + 4) =
+            make_float4(lut[c][v[4][c]], lut[c][v[5][c]], lut[c][v[6][c]], lut[c][v[7][c]]);
       }
     } else {
-      for (int j = 0; qx + j < crop; ++j)
+      for (int j = 0; j < PX && qx + j < crop; ++j)
 #pragma unroll
         for (int c = 0; c < 3; ++c) o_tile[c * plane + o + j] = lut[c][v[j][c]];
     }
-    for (int j = 0; j < 4 && qx + j < crop; ++j) {
-      if (out_u8) {
-        uint8_t* u = out_u8 + (static_cast<long long>(tile) * plane + o + j) * 3;
-        u[0] = v[j][0]; u[1] = v[j][1]; u[2] = v[j][2];
+    if (out_u8 || out_nodata) {
+      for (int j = 0; j < PX && qx + j < crop; ++j) {
+        if (out_u8) {
+          uint8_t* u = out_u8 + (static_cast<long long>(tile) * plane + o + j) * 3;
+          u[0] = v[j][0]; u[1] = v[j][1]; u[2] = v[j][2];
+        }
+        if (out_nodata) out_nodata[static_cast<long long>(tile) * plane + o + j] = nd[j];
       }
-      if (out_nodata) out_nodata[static_cast<long long>(tile) * plane + o + j] = nd[j];
     }
   }
-  (void)quads;
 }
 
 template <typename T>
@@ -690,11 +692,11 @@ static int launch_ingest_native_t(const T* scene, const uint8_t* nodata, int Hs,
                                   float* out_nchw, uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream) {
   if (n_tiles == 0) return 0;
   BSEG_REQUIRE(crop > 0 && out_nchw != nullptr, "ingest_native: bad arguments");
-  BSEG_REQUIRE((reinterpret_cast<uintptr_t>(scene) & 7) == 0 && (reinterpret_cast<uintptr_t>(nodata) & 3) == 0 &&
+  BSEG_REQUIRE((reinterpret_cast<uintptr_t>(scene) & 15) == 0 && (reinterpret_cast<uintptr_t>(nodata) & 7) == 0 &&
                    (reinterpret_cast<uintptr_t>(out_nchw) & 15) == 0,
                "ingest_native: misaligned buffers");
   // two CTAs of 1024 threads per SM over all tiles: large CTAs amortise the 12 K-entry composite table each one builds
-  const int work = crop * ((crop + 3) / 4);
+  const int work = crop * ((crop + 7) / 8);
   int bx = (work + 1023) / 1024;
   const int cap = (num_sms() * 2 + n_tiles - 1) / n_tiles;
   if (bx > cap) bx = cap < 1 ? 1 : cap;

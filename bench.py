@@ -415,61 +415,62 @@ def noprompt_leg(args, dev, rank, world, model, barrier, timed):
 # native-resolution mode: 512-px tiles WITHOUT the resize to 448, i.e. the backbone at
 # SegGptConfig(image_size=(1024, 512)): 64 x 32 tokens, T = 2048; ingest is then a purely HBM-bound per-pixel pass
 # ------------------------------------------------------------------------------------------------------------
-NATIVE_FLOP_PER_TILE = 2.186e12  # forward at native 512^2
-NATIVE_TILES = 32
+NATIVE = {512: (32, 2.186e12), 1024: (8, 14.356e12)}  # tile -> (tiles per step, SURVEY section 8(d) forward FLOPs per tile)
 
 
-def native_leg(args, dev, rank, world, scene, nodata, stats, boxes, barrier, timed, L, peaks):
+def native_leg(args, dev, rank, world, scene, nodata, stats, barrier, timed, L, peaks):
     from beach_seg_b200 import ops, synth
     from beach_seg_b200.ml_util import load_model
     from beach_seg_b200.predict import TilePredictor, create_palette
 
-    model = load_model("random-init:0", device=dev, max_batch=NATIVE_TILES, image_size=512)
-    predictor = TilePredictor(model, CROP)
-    n = NATIVE_TILES
-    prompts = synth.normalize(synth.smooth_image(n, 8000 + rank, size=512)).to(dev)
-    pcls = synth.blocky_mask(n, 8100 + rank, size=512).to(dev)
-    torch.manual_seed(43)
-    palette = create_palette(4, n, True, dev)
-    canvas = torch.zeros(scene.shape[1:], dtype=torch.int32, device=dev)
-    b = boxes[:n]
+    res = {}
+    for tile, (n, flop) in NATIVE.items():
+        model = load_model("random-init:0", device=dev, max_batch=n, image_size=tile)
+        predictor = TilePredictor(model, tile)
+        prompts = synth.normalize(synth.smooth_image(n, 8000 + rank, size=tile)).to(dev)
+        pcls = synth.blocky_mask(n, 8100 + rank, size=tile).to(dev)
+        torch.manual_seed(43)
+        palette = create_palette(4, n, True, dev)
+        canvas = torch.zeros(scene.shape[1:], dtype=torch.int32, device=dev)
+        b = torch.from_numpy(synth.tile_boxes(n, tile, scene.shape[2])).to(dev)
 
-    def step():
-        cls = predictor.predict_tiles(scene, nodata, stats, b, prompts, pcls, palette)
-        ops.vote_accumulate(canvas, cls, b, overlapping=False)
+        def step():
+            cls = predictor.predict_tiles(scene, nodata, stats, b, prompts, pcls, palette)
+            ops.vote_accumulate(canvas, cls, b, overlapping=False)
 
-    for _ in range(3):
-        step()
-    ms, _ = timed(step, args.steps, want_ranks=True)
-    L.bseg_profile_enable(1)
-    barrier()
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    ncat = len(CATS)
-    pms, pl, pw, pb = (C.c_double * ncat)(), (C.c_longlong * ncat)(), (C.c_double * ncat)(), (C.c_double * ncat)()
-    L.bseg_profile_collect(pms, pl, pw, pb)
-    L.bseg_profile_enable(0)
-    tot = sum(pms[i] for i in range(ncat))
-    kern = {name: {"ms_per_step": pms[i] / args.steps, "share": pms[i] / tot if tot else None,
-                   "tflops": pw[i] / (pms[i] * 1e-3) / 1e12 if pw[i] and pms[i] else None,
-                   "gbs": pb[i] / (pms[i] * 1e-3) / 1e9 if pb[i] and pms[i] else None}
-            for i, name in enumerate(CATS) if pl[i]}
-    tps = world * n * args.steps / (ms * 1e-3)
-    ing = kern.get("ingest", {})
-    out = {"workload": f"native-resolution mode: {n} tiles of 512x512x4 uint16 per GPU per step, backbone at "
-                       "image_size 512 (64x32 tokens, T=2048, random init seed 0): ingest (no resize) + colourise + "
-                       "forward + decode + vote", "tiles_per_step_per_gpu": n, "n_gpus": world, "value": tps,
-           "unit": "tiles/s", "ms_per_step": ms / args.steps,
-           "model_tflops_per_gpu": tps / world * NATIVE_FLOP_PER_TILE / 1e12,
-           "model_frac_of_tensor_peak": tps / world * NATIVE_FLOP_PER_TILE / 1e12 / peaks["tensor"], "kernels": kern,
-           "ingest_roofline": ({"bound": "hbm", "achieved": ing["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
-                                "frac": ing["gbs"] / peaks["hbm"],
-                                "bytes_per_pixel": "9 in (4 x u16 + nodata) + 12 out (3 x fp32)"}
-                               if ing.get("gbs") else None)}
-    del model
-    return out
-
+        for _ in range(3):
+            step()
+        ms, _ = timed(step, args.steps, want_ranks=True)
+        L.bseg_profile_enable(1)
+        barrier()
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize()
+        ncat = len(CATS)
+        pms, pl, pw, pb = (C.c_double * ncat)(), (C.c_longlong * ncat)(), (C.c_double * ncat)(), (C.c_double * ncat)()
+        L.bseg_profile_collect(pms, pl, pw, pb)
+        L.bseg_profile_enable(0)
+        tot = sum(pms[i] for i in range(ncat))
+        kern = {name: {"ms_per_step": pms[i] / args.steps, "share": pms[i] / tot if tot else None,
+                       "tflops": pw[i] / (pms[i] * 1e-3) / 1e12 if pw[i] and pms[i] else None,
+                       "gbs": pb[i] / (pms[i] * 1e-3) / 1e9 if pb[i] and pms[i] else None}
+                for i, name in enumerate(CATS) if pl[i]}
+        tps = world * n * args.steps / (ms * 1e-3)
+        ing = kern.get("ingest", {})
+        res[f"tile{tile}"] = {
+            "workload": f"native-resolution mode: {n} tiles of {tile}x{tile}x4 uint16 per GPU per step, backbone at "
+                        f"image_size {tile} ({tile // 8}x{tile // 16} tokens, T={2 * (tile // 16) ** 2}, random init seed 0): "
+                        "ingest (no resize) + colourise + forward + decode + vote",
+            "tiles_per_step_per_gpu": n, "n_gpus": world, "value": tps, "unit": "tiles/s", "ms_per_step": ms / args.steps,
+            "flop_per_tile": flop, "model_tflops_per_gpu": tps / world * flop / 1e12,
+            "model_frac_of_tensor_peak": tps / world * flop / 1e12 / peaks["tensor"], "kernels": kern,
+            "ingest_roofline": ({"bound": "hbm", "achieved": ing["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                                 "frac": ing["gbs"] / peaks["hbm"],
+                                 "bytes_per_pixel": "9 in (4 x u16 + nodata) + 12 out (3 x fp32)"}
+                                if ing.get("gbs") else None)}
+        del model, predictor, prompts, pcls, canvas
+        torch.cuda.empty_cache()
+    return res
 
 # ------------------------------------------------------------------------------------------------------------
 # small-batch latency: the reference's real call pattern is batch 1 (src/data.py:287-293, src/predict.py:234)
@@ -518,7 +519,7 @@ def main():
     ap.add_argument("--scene-reps", type=int, default=2)
     ap.add_argument("--no-noprompt", action="store_true", help="skip the predict_no_prompt leg (BASELINE configs[4])")
     ap.add_argument("--no-latency", action="store_true", help="skip the batch 1/4/16 latency leg")
-    ap.add_argument("--no-native", action="store_true", help="skip the native-resolution (512-px, T=2048) leg")
+    ap.add_argument("--no-native", action="store_true", help="skip the native-resolution legs (512- / 1024-px tiles)")
     ap.add_argument("--no-fp32-check", action="store_true",
                     help="skip the fp32-accuracy-mode leg (bf16 path vs bseg_forward_f32 on the bench inputs)")
     args = ap.parse_args()
@@ -720,8 +721,8 @@ def main():
 
     scene3 = None if args.no_scene else scene_leg(args, dev, rank, world, model, barrier, timed)
     noprompt5 = None if args.no_noprompt else noprompt_leg(args, dev, rank, world, model, barrier, timed)
-    native = None if args.no_native else native_leg(args, dev, rank, world, scene, nodata, stats, boxes, barrier, timed,
-                                                    L, peaks)
+    native = None if args.no_native else native_leg(args, dev, rank, world, scene, nodata, stats, barrier, timed, L,
+                                                    peaks)
     latency = None
     if not args.no_latency and world == 1:
         latency = latency_leg(args, dev, model, predictor, scene, nodata, stats, boxes, prompt_images, prompt_cls,
@@ -815,7 +816,7 @@ def main():
             "kernels": kernels, "gemm_modes": gemm_modes, "gemm_variants": gemm_variants, "train": train, "fp32_mode": fp32_mode,
             "query_half_fast_path": fast,
             "config3_scene": scene3, "config5_no_prompt": noprompt5, "small_batch_latency": latency,
-            "native_resolution_512": native,
+            "native_resolution": native,
             "ms_per_step_per_rank": [m / args.steps for m in ms_ranks],
             "model_tflops": value / world * FWD_FLOP_PER_TILE / 1e12,
             "model_frac_of_tensor_peak": value / world * FWD_FLOP_PER_TILE / 1e12 / peaks["tensor"],
