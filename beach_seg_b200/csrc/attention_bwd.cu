@@ -14,8 +14,13 @@
 //                             kernel.
 //   attention_bwd_dkv_kernel  one CTA per (seq, head, 128 keys); thread <-> key row (S^T = k q^T, so that P^T and dS^T
 //                             are TMEM A operands of dv += P^T dO and dk += dS^T q), loops over 25 query blocks of 64.
+//                             Bias, -lse and -D come out of the tensor core with the scores: S^T = k qs^T + A_h TabH +
+//                             A_w TabW and dP^T - D = v dO^T + A_1 TabD, where A_* are constant one-hot / all-one
+//                             columns per key row (smem) and Tab* the per-query 16-bit tables of the block, TMA-loaded
+//                             and read as MN-major B operands.  Per element the key thread is left with one ex2, half
+//                             a packed multiply and two halves of a bf16 pack.
 //
-// Each CTA: warp 0 TMA producer, warp 1 tcgen05 issuer, warp 2 table loader (dkv) / idle, warp 3 idle, warps 4-11
+// Each CTA: warp 0 TMA producer, warp 1 tcgen05 issuer, warps 2-3 idle, warps 4-11
 // elementwise (two warps per TMEM lane quarter, splitting the columns).  S / dP are double buffered in TMEM so that the
 // tensor core works on block j+1 while the elementwise warps are on block j.
 #include <type_traits>
@@ -64,20 +69,21 @@ constexpr int kKTile = 128;
 constexpr int kQB = 64, kNumQB = (kT + kQB - 1) / kQB;  // 25 (the last block has 32 live queries)
 constexpr int kStagesK = 3;
 constexpr int kTileBytes = 64 * 128;       // 8192: [64 x 64] bf16
-constexpr int kTabStride = 68;             // floats per table row (64 + 4: LDS.128 rows land on distinct banks)
-constexpr int kBhRows = 6;                 // token rows a 128-key tile can touch
-// per-stage tables, each a TMA box at a 128-byte aligned offset: bh [6][68], bw [28][68], lse [64], D [64] (fp32)
-constexpr int kTabBhOff = 0;
-constexpr int kTabBwOff = (kBhRows * kTabStride * 4 + 127) / 128 * 128;                 // 1664
-constexpr int kTabLseOff = kTabBwOff + (kGridW * kTabStride * 4 + 127) / 128 * 128;     // 9344
-constexpr int kTabDOff = kTabLseOff + kQB * 4;                                          // 9600
-constexpr int kTabTxBytes = (kBhRows + kGridW) * kTabStride * 4 + 2 * kQB * 4;          // bytes the four boxes carry
-constexpr int kStageKBytes = 4 * kTileBytes + ((kTabDOff + kQB * 4 + 1023) / 1024) * 1024;
+// Per-query tables, 16-bit, [row][T] per (seq, head), written by the dq kernel and read here as MN-major B operands
+// (K = table row, N = query): fp16 rows 0..55 bh[kh], 56..83 bw[kw], 84 / 85 = -lse split hi / lo, 86 / 87 = 0;
+// bf16 rows 0..2 of a second table = -D split three ways.
+constexpr int kTabRows = 88, kDRows = 3;
+constexpr int kTabHBytes = 16 * 128, kTabWBytes = 32 * 128, kTabDBytes = 16 * 128;  // TMA boxes of 16 / 32 / 16 rows
+constexpr int kTabHOff = 4 * kTileBytes, kTabWOff = kTabHOff + kTabHBytes, kTabDOff = kTabWOff + kTabWBytes;
+constexpr int kStageKBytes = kTabDOff + kTabDBytes;  // 40960
 constexpr int kKOffK = 0;
 constexpr int kKOffV = kKOffK + kKTile * 128;
-constexpr int kKOffRing = kKOffV + kKTile * 128;
+constexpr int kKOffA = kKOffV + kKTile * 128;        // constant A operand of the fold MMAs: [128 keys][64 x 16 bit]
+constexpr int kKOffRing = kKOffA + kKTile * 128;
 constexpr int kKOffBar = kKOffRing + kStagesK * kStageKBytes;
 constexpr int kKSmemBytes = kKOffBar + 256 + 1024;
+static_assert(kStageKBytes % 1024 == 0 && kTabHOff % 1024 == 0 && kTabWOff % 1024 == 0 && kTabDOff % 1024 == 0,
+              "swizzle alignment");
 static_assert(kKSmemBytes <= 227 * 1024, "dkv kernel shared memory");
 // TMEM columns: S0 [0,64) dP0 [64,128) S1 [128,192) dP1 [192,256) dV [256,320) dK [320,384)
 constexpr uint32_t kKColBuf = 128, kKColdP = 64, kKColdV = 256, kKColdK = 320;
@@ -97,7 +103,8 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                         const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                         const __grid_constant__ CUtensorMap tmap_kt, const __grid_constant__ CUtensorMap tmap_rel,
                         const __grid_constant__ CUtensorMap tmap_relt, const float* __restrict__ lse,
-                        const float* __restrict__ Dvec, float* bias_tab, __nv_bfloat16* __restrict__ dqkv, int heads) {
+                        const float* __restrict__ Dvec, __half* tab16, __nv_bfloat16* dtab,
+                        __nv_bfloat16* __restrict__ dqkv, int heads) {
   using namespace abwd;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -274,7 +281,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int qi = valid ? qi_raw : kT - 1;
     const int qh = qi / kGridW, qw = qi % kGridW;
     const uint32_t lane_base = tmem_lane_base(tmem_base, quarter);
-    float* tab = bias_tab + static_cast<long long>(sh) * kBiasRows * kT;
+    __half* tab = tab16 + static_cast<long long>(sh) * kTabRows * kT;
     float* dsh_row = sDsh + r * kDshStride;
 
     // ---- prologue: bias rows of this query (x log2 e); bw stays in registers, bh goes through the global table ----
@@ -291,7 +298,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int kh = c + i - off_h;
-          if (kh >= 0 && kh < kGridH && valid) tab[kh * kT + qi] = v[i];  // already in the log2 domain
+          if (kh >= 0 && kh < kGridH && valid) tab[kh * kT + qi] = __float2half_rn(v[i]);  // log2 domain
         }
       }
       const int off_w = 27 - qw;  // bw[kw] = G[112 + off_w + kw]
@@ -303,17 +310,34 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int kw = c + i - off_w;
-          if (kw >= 0 && kw < kGridW && valid) tab[(kGridH + kw) * kT + qi] = v[i];
+          if (kw >= 0 && kw < kGridW && valid) tab[(kGridH + kw) * kT + qi] = __float2half_rn(v[i]);
         }
       }
       // both column groups of a row write the same values; every thread reads back what it wrote itself
 #pragma unroll
-      for (int kw = 0; kw < kGridW; ++kw) bw[kw] = valid ? tab[(kGridH + kw) * kT + qi] : 0.f;
+      for (int kw = 0; kw < kGridW; ++kw) bw[kw] = valid ? __half2float(tab[(kGridH + kw) * kT + qi]) : 0.f;
     }
     if (g == 0)
       for (int i = 0; i < kGridH; ++i) dsh_row[i] = 0.f;
     const float lse_q = valid ? lse[static_cast<long long>(sh) * kT + qi] : 0.f;
     const float d_q = valid ? Dvec[static_cast<long long>(sh) * kT + qi] : 0.f;
+    if (valid && g == 0) {
+      // rows of the dkv kernel's tables that depend on the query only: -lse as fp16 hi + lo, -D as three bf16 terms
+      const __half l_hi = __float2half_rn(-lse_q);
+      const __half l_lo = __float2half_rn(-lse_q - __half2float(l_hi));
+      tab[(kBiasRows + 0) * kT + qi] = l_hi;
+      tab[(kBiasRows + 1) * kT + qi] = l_lo;
+      tab[(kBiasRows + 2) * kT + qi] = __float2half_rn(0.f);
+      tab[(kBiasRows + 3) * kT + qi] = __float2half_rn(0.f);
+      __nv_bfloat16* drow = dtab + static_cast<long long>(sh) * kDRows * kT + qi;
+      float rest = -d_q;
+#pragma unroll
+      for (int i = 0; i < kDRows; ++i) {
+        const __nv_bfloat16 part = __float2bfloat16_rn(rest);
+        drow[i * kT] = part;
+        rest -= __bfloat162float(part);
+      }
+    }
     tc_fence_before();
     named_bar_sync(1, 256);  // dsh rows zeroed, both groups' table rows written (each thread re-reads what it wrote)
     if (lane == 0) mbar_arrive(g_free);
@@ -365,7 +389,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     // bias rows of the block (global table, L2 latency): fetched one key block ahead
     float bnext[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) bnext[i] = valid ? tab[i * kT + qi] : 0.f;
+    for (int i = 0; i < 4; ++i) bnext[i] = valid ? __half2float(tab[i * kT + qi]) : 0.f;
     for (int kb = 0; kb < kNumKB; ++kb) {
       const int buf = kb & 1;
       float boff[4], acc4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -373,7 +397,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       for (int i = 0; i < 4; ++i) boff[i] = bnext[i] - lse_q;
       if (kb + 1 < kNumKB) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bnext[i] = valid ? tab[((kb + 1) * 4 + i) * kT + qi] : 0.f;
+        for (int i = 0; i < 4; ++i) bnext[i] = valid ? __half2float(tab[((kb + 1) * 4 + i) * kT + qi]) : 0.f;
       }
       mbar_wait(&sdp_full[buf], (kb >> 1) & 1);
       tc_fence_after();
@@ -473,14 +497,14 @@ __global__ void __launch_bounds__(abwd::kThreads, 1)
 attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                          const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                          const __grid_constant__ CUtensorMap tmap_qt, const __grid_constant__ CUtensorMap tmap_dot,
-                         const __grid_constant__ CUtensorMap tmap_tab6, const __grid_constant__ CUtensorMap tmap_tab28,
-                         const __grid_constant__ CUtensorMap tmap_lse,
-                         const __grid_constant__ CUtensorMap tmap_dvec, __nv_bfloat16* __restrict__ dqkv, int heads) {
+                         const __grid_constant__ CUtensorMap tmap_tabh, const __grid_constant__ CUtensorMap tmap_tabw,
+                         const __grid_constant__ CUtensorMap tmap_tabd, __nv_bfloat16* __restrict__ dqkv, int heads) {
   using namespace abwd;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + kKOffK;
   uint8_t* sV = smem + kKOffV;
+  uint8_t* sA = smem + kKOffA;
   uint8_t* sRing = smem + kKOffRing;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKOffBar);
   uint64_t* kv_full = bars + 0;
@@ -504,10 +528,9 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
     tma_prefetch_desc(&tmap_do);
     tma_prefetch_desc(&tmap_qt);
     tma_prefetch_desc(&tmap_dot);
-    tma_prefetch_desc(&tmap_tab6);
-    tma_prefetch_desc(&tmap_tab28);
-    tma_prefetch_desc(&tmap_lse);
-    tma_prefetch_desc(&tmap_dvec);
+    tma_prefetch_desc(&tmap_tabh);
+    tma_prefetch_desc(&tmap_tabw);
+    tma_prefetch_desc(&tmap_tabd);
     mbar_init(kv_full, 1);
     for (int i = 0; i < kStagesK; ++i) {
       mbar_init(&full[i], 1);
@@ -521,6 +544,32 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  // Constant A operand of the fold MMAs, one K-major row of 64 16-bit values per key (128-byte swizzle):
+  //   fp16 [0,16)   one-hot at the key's token row relative to kh_lo          x TabH rows kh_lo ..
+  //   fp16 [16,48)  one-hot at 16 + the key's token column; 1 at 44 and 45     x TabW rows 56 .. 87 (bw, -lse hi, lo)
+  //   bf16 [48,64)  1 at 48, 49, 50                                           x TabD rows 0 .. 2 (-D split)
+  for (int idx = threadIdx.x; idx < kKTile * 8; idx += kThreads) {
+    const int n = idx >> 3, c = idx & 7;
+    const int ki = min(k0 + n, kT - 1);
+    const int khi = ki / kGridW - kh_lo, kw = ki % kGridW;
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint32_t pair = 0;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int col = 8 * c + 2 * e + hf;
+        uint32_t bits = 0;
+        if (col < 16) bits = (col == khi) ? 0x3C00u : 0u;
+        else if (col < 48) bits = (col - 16 == kw || col == 44 || col == 45) ? 0x3C00u : 0u;
+        else bits = (col < 48 + kDRows) ? 0x3F80u : 0u;
+        pair |= bits << (16 * hf);
+      }
+      w[e] = pair;
+    }
+    *reinterpret_cast<uint4*>(sA + n * 128 + ((c ^ (n & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  fence_proxy_async_smem();  // generic-proxy writes above -> visible to the tensor core's async-proxy reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -540,26 +589,25 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
         if (j >= kStagesK) mbar_wait(&empty[st], ((j / kStagesK) & 1) ^ 1);
         if (elect_one_sync()) {
           uint8_t* base = sRing + st * kStageKBytes;
-          mbar_arrive_expect_tx(&full[st], 4 * kTileBytes + kTabTxBytes);
+          mbar_arrive_expect_tx(&full[st], kStageKBytes);  // full boxes: out-of-range rows / queries arrive as zeros
           tma_load_3d(base, &tmap_q, &full[st], 0, j * kQB, sh);
           tma_load_4d(base + kTileBytes, &tmap_do, &full[st], 0, j * kQB, head, seq);
           tma_load_3d(base + 2 * kTileBytes, &tmap_qt, &full[st], j * kQB, 0, sh);
           tma_load_3d(base + 3 * kTileBytes, &tmap_dot, &full[st], j * kQB, 0, sh);
-          // bias rows (x log2 e) of the block's queries: the 6 bh rows from kh_lo (rows past the token grid hold bw
-          // data and are only read by dead key rows) and the 28 bw rows; then lse and D.  Box rows are 68 floats
-          // (4 spill-over columns) so that LDS.128 of neighbouring rows lands on distinct banks.
-          uint8_t* tabs = base + 4 * kTileBytes;
-          tma_load_3d(tabs + kTabBhOff, &tmap_tab6, &full[st], j * kQB, kh_lo, sh);
-          tma_load_3d(tabs + kTabBwOff, &tmap_tab28, &full[st], j * kQB, kGridH, sh);
-          tma_load_2d(tabs + kTabLseOff, &tmap_lse, &full[st], j * kQB, sh);
-          tma_load_2d(tabs + kTabDOff, &tmap_dvec, &full[st], j * kQB, sh);
+          // 16 table rows from kh_lo (the tile touches at most 6; the others meet zero columns of A), the 32 rows
+          // bw / -lse, the 3 (+13 out-of-range = zero) rows of -D
+          tma_load_3d(base + kTabHOff, &tmap_tabh, &full[st], j * kQB, kh_lo, sh);
+          tma_load_3d(base + kTabWOff, &tmap_tabw, &full[st], j * kQB, kGridH, sh);
+          tma_load_3d(base + kTabDOff, &tmap_tabd, &full[st], j * kQB, 0, sh);
         }
         __syncwarp();
       }
     } else if (warp == 1) {
       // ============================ MMA issuer (warp-uniform loop, one elected lane issues) ============================
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      constexpr uint32_t idesc_tab = umma_idesc_16bit(128, 64, 0, 0, 0, 1);   // fp16 x fp16, B MN-major
+      constexpr uint32_t idesc_tabd = umma_idesc_16bit(128, 64, 1, 1, 0, 1);  // bf16 x bf16, B MN-major
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), a_addr = smem_u32(sA);
       mbar_wait(kv_full, 0);
       tc_fence_after();
       auto issue_sdp = [&](int j) {
@@ -573,10 +621,19 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
           for (int k = 0; k < 4; ++k)  // S^T = K Q_blk^T
             umma_bf16_ss(d, umma_desc_sw128_kmajor(k_addr + k * 32), umma_desc_sw128_kmajor(q_addr + k * 32), idesc,
                          k != 0);
+          // ... + bias(key, query) - lse(query)
+          umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr), umma_desc_sw128_mnmajor(q_addr + kTabHOff), idesc_tab, 1u);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr + 32 + k * 32),
+                         umma_desc_sw128_mnmajor(q_addr + kTabWOff + k * 2048), idesc_tab, 1u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dP^T = V dO_blk^T
             umma_bf16_ss(d + kKColdP, umma_desc_sw128_kmajor(v_addr + k * 32),
                          umma_desc_sw128_kmajor(do_addr + k * 32), idesc, k != 0);
+          // ... - D(query)
+          umma_bf16_ss(d + kKColdP, umma_desc_sw128_kmajor(a_addr + 96), umma_desc_sw128_mnmajor(q_addr + kTabDOff),
+                       idesc_tabd, 1u);
           umma_commit(&sdp_full[j & 1]);
         }
         __syncwarp();
@@ -615,40 +672,25 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
     const int ki_raw = k0 + r;
     const bool valid = ki_raw < kT;
     const int ki = valid ? ki_raw : kT - 1;
-    const int khi = ki / kGridW - kh_lo, kw = ki % kGridW;
     const uint32_t lane_base = tmem_lane_base(tmem_base, quarter);
-    const float sc = 1.0f;  // qs carries scale * log2(e)
 
     for (int j = 0; j < kNumQB; ++j) {
-      const int st = j % kStagesK, buf = j & 1;
-      const float* tabs = reinterpret_cast<const float*>(sRing + st * kStageKBytes + 4 * kTileBytes);
-      const float* bh_row = tabs + kTabBhOff / 4 + khi * kTabStride + g * 32;
-      const float* bw_row = tabs + kTabBwOff / 4 + kw * kTabStride + g * 32;
-      const float* lse_s = tabs + kTabLseOff / 4 + g * 32;
-      const float* d_s = tabs + kTabDOff / 4 + g * 32;
-      mbar_wait(&full[st], (j / kStagesK) & 1);
+      const int buf = j & 1;
       mbar_wait(&sdp_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t sbase = lane_base + buf * kKColBuf;
       float s[32], dp[32];
-      tmem_ld32(sbase + g * 32, s);
-      tmem_ld32(sbase + kKColdP + g * 32, dp);
+      tmem_ld32(sbase + g * 32, s);              // S^T + bias - lse  (log2 domain)
+      tmem_ld32(sbase + kKColdP + g * 32, dp);   // dP^T - D
       tmem_ld_wait();
       uint32_t pp[16], pd[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 bh4 = lds128(bh_row + i);
-        const float4 bw4 = lds128(bw_row + i);
-        const float4 l4 = lds128(lse_s + i);
-        const float4 d4 = lds128(d_s + i);
-        const float p0 = ex2_approx(fmaf(s[i], sc, bw4.x) + (bh4.x - l4.x));
-        const float p1 = ex2_approx(fmaf(s[i + 1], sc, bw4.y) + (bh4.y - l4.y));
-        const float p2 = ex2_approx(fmaf(s[i + 2], sc, bw4.z) + (bh4.z - l4.z));
-        const float p3 = ex2_approx(fmaf(s[i + 3], sc, bw4.w) + (bh4.w - l4.w));
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2_approx(s[i]), p1 = ex2_approx(s[i + 1]);
+        float d0, d1;
+        mul_f32x2(d0, d1, p0, p1, dp[i], dp[i + 1]);
         pp[i >> 1] = pack_bf16x2(p0, p1);
-        pp[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-        pd[i >> 1] = pack_bf16x2(p0 * (dp[i] - d4.x), p1 * (dp[i + 1] - d4.y));
-        pd[(i >> 1) + 1] = pack_bf16x2(p2 * (dp[i + 2] - d4.z), p3 * (dp[i + 3] - d4.w));
+        pd[i >> 1] = pack_bf16x2(d0, d1);
       }
       tmem_st16u(sbase + g * 32, pp);
       tmem_st16u(sbase + kKColdP + g * 32, pd);
@@ -700,8 +742,11 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
   BSEG_REQUIRE(nseq > 0 && heads > 0, "attention_bwd: empty problem");
   const uint64_t nsh = static_cast<uint64_t>(nseq) * heads;
   const uint64_t D = static_cast<uint64_t>(heads) * 64;
-  CUtensorMap tq128, tq64, tk128, tk112, tv128, tv112, tkt, tqt, tdot, tdo128, tdo64, trel, trelt, ttab6, ttab28, tlse,
-      tdvec;
+  CUtensorMap tq128, tq64, tk128, tk112, tv128, tv112, tkt, tqt, tdot, tdo128, tdo64, trel, trelt, ttabh, ttabw, ttabd;
+  // the scratch the caller sized for the former fp32 table ([nsh, 84, T] floats) holds both 16-bit tables
+  __half* tab16 = reinterpret_cast<__half*>(bias_tab);
+  __nv_bfloat16* dtab = reinterpret_cast<__nv_bfloat16*>(tab16 + nsh * kTabRows * kT);
+  static_assert((kTabRows + kDRows) * 2 <= kBiasRows * 4, "16-bit tables must fit in the bias scratch");
   int rc;
   {
     uint64_t dims[3] = {64, static_cast<uint64_t>(kT), nsh};
@@ -731,17 +776,15 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
     if ((rc = make_tmap_bf16(&tdo64, dO, 4, dims, strides, b64))) return rc;
   }
   {
-    // bias table [nsh, 84, T] fp32 (written by the dq kernel), lse / D [nsh, T] fp32
-    uint64_t dims[3] = {static_cast<uint64_t>(kT), kBiasRows, nsh};
-    uint64_t strides[2] = {static_cast<uint64_t>(kT) * 4, static_cast<uint64_t>(kT) * kBiasRows * 4};
-    uint32_t b6[3] = {kTabStride, kBhRows, 1}, b28[3] = {kTabStride, kGridW, 1};
-    if ((rc = make_tmap_f32(&ttab6, bias_tab, 3, dims, strides, b6))) return rc;
-    if ((rc = make_tmap_f32(&ttab28, bias_tab, 3, dims, strides, b28))) return rc;
-    uint64_t dims2[2] = {static_cast<uint64_t>(kT), nsh};
-    uint64_t strides2[1] = {static_cast<uint64_t>(kT) * 4};
-    uint32_t b64[2] = {kQB, 1};
-    if ((rc = make_tmap_f32(&tlse, lse, 2, dims2, strides2, b64))) return rc;
-    if ((rc = make_tmap_f32(&tdvec, Dvec, 2, dims2, strides2, b64))) return rc;
+    // per-query tables [nsh, 88, T] fp16 and [nsh, 3, T] bf16 (written by the dq kernel); 16-bit data either way
+    uint64_t dims[3] = {static_cast<uint64_t>(kT), kTabRows, nsh};
+    uint64_t strides[2] = {static_cast<uint64_t>(kT) * 2, static_cast<uint64_t>(kT) * kTabRows * 2};
+    uint32_t b16[3] = {kQB, 16, 1}, b32[3] = {kQB, 32, 1};
+    if ((rc = make_tmap_bf16(&ttabh, tab16, 3, dims, strides, b16))) return rc;
+    if ((rc = make_tmap_bf16(&ttabw, tab16, 3, dims, strides, b32))) return rc;
+    uint64_t ddims[3] = {static_cast<uint64_t>(kT), kDRows, nsh};
+    uint64_t dstrides[2] = {static_cast<uint64_t>(kT) * 2, static_cast<uint64_t>(kT) * kDRows * 2};
+    if ((rc = make_tmap_bf16(&ttabd, dtab, 3, ddims, dstrides, b16))) return rc;
   }
   if ((rc = make_tmap_bf16_2d(&trel, relcat, 64, kRelRows, 64, 64, kRelRows))) return rc;
   if ((rc = make_tmap_bf16_2d(&trelt, relcat_t, 192, 64, 192, 64, 64))) return rc;
@@ -758,15 +801,15 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
     ProfScope prof(CAT_ATTENTION, pair * 64 * 2 * 3 + static_cast<double>(nseq) * heads * kT * 2.0 * 176 * 64 * 2,
                    static_cast<double>(nseq) * heads * kT * (64 * 2 * 5 + kBiasRows * 4), stream);
     attention_bwd_dq_kernel<<<grid, kThreads, kQSmemBytes, stream>>>(tq128, tdo128, tk112, tv112, tkt, trel, trelt, lse,
-                                                                     Dvec, bias_tab, dqkv, heads);
+                                                                     Dvec, tab16, dtab, dqkv, heads);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
   {
     dim3 grid((kT + kKTile - 1) / kKTile, heads, nseq);
     ProfScope prof(CAT_ATTENTION, pair * 64 * 2 * 4, static_cast<double>(nseq) * heads * kT * (64 * 2 * 8), stream);
-    attention_bwd_dkv_kernel<<<grid, kThreads, kKSmemBytes, stream>>>(tk128, tv128, tq64, tdo64, tqt, tdot, ttab6,
-                                                                      ttab28, tlse, tdvec, dqkv, heads);
+    attention_bwd_dkv_kernel<<<grid, kThreads, kKSmemBytes, stream>>>(tk128, tv128, tq64, tdo64, tqt, tdot, ttabh,
+                                                                      ttabw, ttabd, dqkv, heads);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -431,6 +432,49 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
          (1u << 10) |        // b_format = BF16
          ((N >> 3) << 17) |  // n_dim
          ((M >> 4) << 24);   // m_dim
+}
+
+// K-major is the layout of every TMA-loaded [rows][64 x 16-bit] tile used as "rows = M or N, columns = K".  The SAME bytes
+// read as an MN-major operand are "rows = K, columns = M or N" (CUTLASS mma_traits_sm100.hpp, make_umma_desc<Major::MN>,
+// SWIZZLE_128B: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): 64 MN elements per 128-byte row, 8 K rows per
+// 1024-byte swizzle atom, the next 8 K rows at SBO; LBO (the next 64 MN elements) is unused for MN extents of 64.
+// One instruction consumes 16 K rows = 2048 bytes.  The instruction descriptor must carry the matching major bit.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes = 16) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// General 16-bit instruction descriptor (D = fp32): operand formats (0 = fp16, 1 = bf16) and majors (0 = K, 1 = MN).
+__host__ __device__ constexpr uint32_t umma_idesc_16bit(uint32_t M, uint32_t N, uint32_t a_bf16, uint32_t b_bf16,
+                                                        uint32_t a_mn = 0, uint32_t b_mn = 0) {
+  return (1u << 4) | (a_bf16 << 7) | (b_bf16 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// Instruction descriptor: A = B = fp16, D = fp32, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return umma_idesc_16bit(M, N, 0, 0);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// two fp32 adds / multiplies in one instruction (sm_100 packed fp32)
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(d));
+}
+__device__ __forceinline__ void mul_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 
 }  // namespace bseg
