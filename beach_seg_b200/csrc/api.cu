@@ -23,7 +23,7 @@ struct LayerPack {
   __nv_bfloat16 *qkv_w, *proj_w, *lin1_w, *lin2_w, *relcat;
   float *qkv_b, *proj_b, *lin1_b, *lin2_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b;
   // transposed copies ([in, out], the B operand of the dgrad GEMMs) and relcat^T; packed by bseg_train_prepare
-  __nv_bfloat16 *qkv_wt = nullptr, *proj_wt = nullptr, *lin1_wt = nullptr, *lin2_wt = nullptr, *relcat_t = nullptr;
+  __nv_bfloat16 *qkv_wt = nullptr, *proj_wt = nullptr, *lin1_wt = nullptr, *lin2_wt = nullptr;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -54,12 +54,6 @@ __global__ void pack_relcat_kernel(const float* __restrict__ rel_h, const float*
   if (i < nh) v = rel_h[(nh - 1 - i) * 64 + d];
   else if (i >= rh_pad && i < rh_pad + nw) v = rel_w[(nw - 1 - (i - rh_pad)) * 64 + d];
   out[i * 64 + d] = __float2bfloat16_rn(8.0f * v);
-}
-
-// relcat [176,64] -> relcat^T [64,192] (columns 176..191 zero): K-major B operand of the bias-gradient MMA
-__global__ void pack_relcat_t_kernel(const __nv_bfloat16* __restrict__ relcat, __nv_bfloat16* __restrict__ out) {
-  const int d = blockIdx.x, j = threadIdx.x;  // 64 x 192
-  out[d * 192 + j] = j < 176 ? relcat[j * 64 + d] : __float2bfloat16_rn(0.f);
 }
 
 // conv3x3 dgrad taps: w9b[tap'][ci][co] = w9[8 - tap'][co][ci]   (tap' = (2-ky)*3 + (2-kx): flipped kernel)
@@ -356,7 +350,7 @@ struct TrainLayout {
   size_t h_emb, dec;
   std::vector<TrainLayer> layers;
   // backward scratch
-  size_t dh, dhb, dxn, dz, datt, dot, qt, kt, v, dvec, bias, dqkv, dinter, ddec, dconv, dpatch;
+  size_t dh, dhb, dxn, dz, datt, v, dvec, bias, dqkv, dinter, ddec, dconv, dpatch;
   size_t total;
 };
 TrainLayout train_layout(const bseg_handle* h, int B) {
@@ -391,9 +385,6 @@ TrainLayout train_layout(const bseg_handle* h, int B) {
   L.dxn = carve(rows1 * kD * 4);
   L.dz = carve(rows1 * kMlp * 2);
   L.datt = carve(rows1 * kD * 2);
-  L.dot = carve(rows1 * kD * 2);
-  L.qt = carve(rows1 * kD * 2);
-  L.kt = carve(rows1 * kD * 2);
   L.v = carve(rows1 * kD * 2);
   L.dvec = carve(rows1 * BSEG_HEADS * 4);
   L.bias = carve(rows1 * BSEG_HEADS * 84 * 4);
@@ -756,7 +747,6 @@ int bseg_train_prepare(bseg_handle* h, void* stream_) {
     lo[i].proj = carve(1024ull * 1024 * 2);
     lo[i].lin1 = carve(4096ull * 1024 * 2);
     lo[i].lin2 = carve(4096ull * 1024 * 2);
-    lo[i].rel = carve(64 * 192 * 2);
   }
   const size_t o_patch = carve(768ull * 1024 * 2), o_dec = carve(16384ull * 4096 * 2), o_w9b = carve(9 * 64 * 64 * 2);
   void* arena = nullptr;
@@ -774,8 +764,6 @@ int bseg_train_prepare(bseg_handle* h, void* stream_) {
     lp.proj_wt = bf(lo[i].proj); tr(lp.proj_w, lp.proj_wt, 1024, 1024);
     lp.lin1_wt = bf(lo[i].lin1); tr(lp.lin1_w, lp.lin1_wt, 4096, 1024);
     lp.lin2_wt = bf(lo[i].lin2); tr(lp.lin2_w, lp.lin2_wt, 1024, 4096);
-    lp.relcat_t = bf(lo[i].rel);
-    pack_relcat_t_kernel<<<64, 192, 0, stream>>>(lp.relcat, lp.relcat_t);
   }
   h->patch_wt = bf(o_patch);   tr(h->patch_w, h->patch_wt, 1024, 768);
   h->dec_embed_wt = bf(o_dec); tr(h->dec_embed_w, h->dec_embed_wt, 16384, 4096);
@@ -811,16 +799,14 @@ int bseg_forward_train(bseg_handle* h, const float* pixel_values, const float* p
 }
 
 namespace {
-// dq, dk, dv of one layer: operand transposes + the two attention-backward kernels
+// dq, dk, dv of one layer: D = rowsum(dO * O) and v = vt^T, then the two attention-backward kernels
 int attention_backward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt,
                        const __nv_bfloat16* att, const __nv_bfloat16* datt, const float* lse,
-                       const __nv_bfloat16* relcat, const __nv_bfloat16* relcat_t, __nv_bfloat16* dot,
-                       __nv_bfloat16* qt, __nv_bfloat16* kt, __nv_bfloat16* v, float* dvec, float* bias,
-                       __nv_bfloat16* dqkv, int nseq, cudaStream_t stream) {
-  int rc = launch_attn_bwd_prep(datt, att, q, k, vt, dot, dvec, qt, kt, v, nseq, BSEG_HEADS, kT, stream);
+                       const __nv_bfloat16* relcat, __nv_bfloat16* v, float* dvec, float* bias, __nv_bfloat16* dqkv,
+                       int nseq, cudaStream_t stream) {
+  int rc = launch_attn_bwd_prep(datt, att, vt, dvec, v, nseq, BSEG_HEADS, kT, stream);
   if (rc) return rc;
-  return launch_attention_bwd(q, k, v, qt, kt, datt, dot, lse, dvec, relcat, relcat_t, bias, dqkv, nseq, BSEG_HEADS,
-                              stream);
+  return launch_attention_bwd(q, k, v, datt, lse, dvec, relcat, bias, dqkv, nseq, BSEG_HEADS, stream);
 }
 }  // namespace
 
@@ -894,8 +880,8 @@ int bseg_backward_to_prompt(bseg_handle* h, const float* d_pred_masks, int batch
       ep.out = datt; ep.ldc = kD;
       if ((rc = launch_gemm(EPI_BF16, dhb, kD, lp.proj_wt, M, kD, kD, ep, stream))) return rc;
     }
-    if ((rc = attention_backward(pl.q, pl.k, pl.vt, pl.att, datt, pl.lse, lp.relcat, lp.relcat_t, bf(L.dot), bf(L.qt),
-                                 bf(L.kt), bf(L.v), fp(L.dvec), fp(L.bias), dqkv, B, stream)))
+    if ((rc = attention_backward(pl.q, pl.k, pl.vt, pl.att, datt, pl.lse, lp.relcat, bf(L.v), fp(L.dvec), fp(L.bias),
+                                 dqkv, B, stream)))
       return rc;
     {
       GemmEpiParams ep;
@@ -1133,9 +1119,9 @@ int bseg_attention_grid(const void* q, const void* k, const void* vt, const void
 size_t bseg_attention_bwd_scratch_bytes(int nseq) {
   if (nseq <= 0) return 0;
   const size_t rows = static_cast<size_t>(nseq) * kT;
-  // dOt, qt, kt, v (bf16), Dvec, bias table (fp32), relcat^T
-  return 4 * align_up(rows * kD * 2, 1024) + align_up(rows * BSEG_HEADS * 4, 1024) +
-         align_up(rows * BSEG_HEADS * 84 * 4, 1024) + align_up(64 * 192 * 2, 1024);
+  // v (bf16), Dvec (fp32), the per-query 16-bit tables (sized as 84 floats per query and head)
+  return align_up(rows * kD * 2, 1024) + align_up(rows * BSEG_HEADS * 4, 1024) +
+         align_up(rows * BSEG_HEADS * 84 * 4, 1024);
 }
 
 int bseg_attention_bwd(const void* q, const void* k, const void* vt, const void* out, const void* d_out,
@@ -1153,20 +1139,13 @@ int bseg_attention_bwd(const void* q, const void* k, const void* vt, const void*
     p += align_up(bytes, 1024);
     return r;
   };
-  auto* dot = reinterpret_cast<__nv_bfloat16*>(take(rows * kD * 2));
-  auto* qt = reinterpret_cast<__nv_bfloat16*>(take(rows * kD * 2));
-  auto* kt = reinterpret_cast<__nv_bfloat16*>(take(rows * kD * 2));
   auto* v = reinterpret_cast<__nv_bfloat16*>(take(rows * kD * 2));
   auto* dvec = reinterpret_cast<float*>(take(rows * BSEG_HEADS * 4));
   auto* bias = reinterpret_cast<float*>(take(rows * BSEG_HEADS * 84 * 4));
-  auto* relt = reinterpret_cast<__nv_bfloat16*>(take(64 * 192 * 2));
-  pack_relcat_t_kernel<<<64, 192, 0, stream>>>(static_cast<const __nv_bfloat16*>(relcat), relt);
-  BSEG_CHECK_CUDA(cudaGetLastError());
-  count_launch();
   return attention_backward(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
                             static_cast<const __nv_bfloat16*>(vt), static_cast<const __nv_bfloat16*>(out),
                             static_cast<const __nv_bfloat16*>(d_out), lse, static_cast<const __nv_bfloat16*>(relcat),
-                            relt, dot, qt, kt, v, dvec, bias, static_cast<__nv_bfloat16*>(dqkv), nseq, stream);
+                            v, dvec, bias, static_cast<__nv_bfloat16*>(dqkv), nseq, stream);
 }
 
 int bseg_layernorm1024_bwd(const float* x, const float* dy, long long lddy, const float* gamma, const float* dh_in,

@@ -42,20 +42,25 @@ constexpr int kBiasRows = kGridH + kGridW;  // 84 rows of the per-(seq,head) bia
 // ---------------- dq kernel ----------------
 constexpr int kQTile = 128;
 constexpr int kKB = 112, kNumKB = kT / kKB;  // 14
-constexpr int kStagesQ = 3;
+constexpr int kStagesQ = 4;
 constexpr int kRelRows = 176;
 constexpr int kQBytes = kQTile * 128;      // 16384
 constexpr int kKBytes = kKB * 128;         // 14336
-constexpr int kKtBytes = 2 * 64 * 128;     // 16384
-constexpr int kStageQBytes = 2 * kKBytes + kKtBytes;  // 45056
-constexpr int kRelRegion = 3 * 64 * 128;   // 24576: relcat [176 x 64] for G, then relcat^T [64 x 192] for the bias gradient
+constexpr int kStageQBytes = 2 * kKBytes;  // 28672: K block, V block
+constexpr int kRelRegion = 3 * 64 * 128;   // 24576: relcat8 [176 x 64]: K-major B of G = Q rel^T, MN-major B of dQ += dG rel
+// Per-query tables, 16-bit, [row][T] per (seq, head), written here and read by the dkv kernel as MN-major B operands
+// (K = table row, N = query): fp16 rows 0..55 bh[kh], 56..83 bw[kw], 84 / 85 = -lse split hi / lo, 86 / 87 = 0;
+// bf16 rows 0..2 of a second table = -D split three ways.
+constexpr int kTabRows = 88, kDRows = 3;
+constexpr int kBiasTileBytes = kTabRows * kQTile * 2;  // 22528: the CTA's [88][128 queries] slice of the fp16 table
 constexpr int kDshStride = 57;
 constexpr int kDshBytes = kQTile * kDshStride * 4;
 constexpr int kQOffQ = 0;
 constexpr int kQOffdO = kQOffQ + kQBytes;
 constexpr int kQOffRel = kQOffdO + kQBytes;
 constexpr int kQOffRing = kQOffRel + kRelRegion;
-constexpr int kQOffDsh = kQOffRing + kStagesQ * kStageQBytes;
+constexpr int kQOffBias = kQOffRing + kStagesQ * kStageQBytes;
+constexpr int kQOffDsh = kQOffBias + kBiasTileBytes;
 constexpr int kQOffBar = kQOffDsh + kDshBytes;
 constexpr int kQSmemBytes = kQOffBar + 256 + 1024;
 static_assert(kQOffRing % 1024 == 0 && kStageQBytes % 1024 == 0 && kKBytes % 1024 == 0, "swizzle alignment");
@@ -67,15 +72,12 @@ constexpr uint32_t kQColBuf = 224, kQColdP = 112, kQColdQ = 448;
 // ---------------- dkv kernel ----------------
 constexpr int kKTile = 128;
 constexpr int kQB = 64, kNumQB = (kT + kQB - 1) / kQB;  // 25 (the last block has 32 live queries)
-constexpr int kStagesK = 3;
+constexpr int kStagesK = 4;
 constexpr int kTileBytes = 64 * 128;       // 8192: [64 x 64] bf16
-// Per-query tables, 16-bit, [row][T] per (seq, head), written by the dq kernel and read here as MN-major B operands
-// (K = table row, N = query): fp16 rows 0..55 bh[kh], 56..83 bw[kw], 84 / 85 = -lse split hi / lo, 86 / 87 = 0;
-// bf16 rows 0..2 of a second table = -D split three ways.
-constexpr int kTabRows = 88, kDRows = 3;
 constexpr int kTabHBytes = 16 * 128, kTabWBytes = 32 * 128, kTabDBytes = 16 * 128;  // TMA boxes of 16 / 32 / 16 rows
-constexpr int kTabHOff = 4 * kTileBytes, kTabWOff = kTabHOff + kTabHBytes, kTabDOff = kTabWOff + kTabWBytes;
-constexpr int kStageKBytes = kTabDOff + kTabDBytes;  // 40960
+// a stage: Q block, dO block (each both the K-major B of the score MMAs and the MN-major B of the gradient MMAs), tables
+constexpr int kTabHOff = 2 * kTileBytes, kTabWOff = kTabHOff + kTabHBytes, kTabDOff = kTabWOff + kTabWBytes;
+constexpr int kStageKBytes = kTabDOff + kTabDBytes;  // 24576
 constexpr int kKOffK = 0;
 constexpr int kKOffV = kKOffK + kKTile * 128;
 constexpr int kKOffA = kKOffV + kKTile * 128;        // constant A operand of the fold MMAs: [128 keys][64 x 16 bit]
@@ -101,8 +103,7 @@ __device__ __forceinline__ uint32_t tmem_lane_base(uint32_t tmem_base, int quart
 __global__ void __launch_bounds__(abwd::kThreads, 1)
 attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                         const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-                        const __grid_constant__ CUtensorMap tmap_kt, const __grid_constant__ CUtensorMap tmap_rel,
-                        const __grid_constant__ CUtensorMap tmap_relt, const float* __restrict__ lse,
+                        const __grid_constant__ CUtensorMap tmap_rel, const float* __restrict__ lse,
                         const float* __restrict__ Dvec, __half* tab16, __nv_bfloat16* dtab,
                         __nv_bfloat16* __restrict__ dqkv, int heads) {
   using namespace abwd;
@@ -112,20 +113,20 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint8_t* sdO = smem + kQOffdO;
   uint8_t* sRel = smem + kQOffRel;
   uint8_t* sRing = smem + kQOffRing;
+  __half* sBias = reinterpret_cast<__half*>(smem + kQOffBias);
   float* sDsh = reinterpret_cast<float*>(smem + kQOffDsh);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kQOffBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* g_full = bars + 1;     // MMA -> all: G = Q rel^T is in TMEM, the rel region of smem is dead
+  uint64_t* g_full = bars + 1;     // MMA -> all: G = Q rel^T is in TMEM
   uint64_t* g_free = bars + 2;     // elementwise -> MMA: G consumed, S/dP buffers may be written
-  uint64_t* relt_full = bars + 3;
-  uint64_t* k_full = bars + 4;     // [3]
-  uint64_t* kv_empty = bars + 7;   // [3]
-  uint64_t* sdp_full = bars + 10;  // [2]
-  uint64_t* ds_full = bars + 12;   // [2]
-  uint64_t* dq_done = bars + 14;   // all scale*dS*K MMAs retired
-  uint64_t* dg_full = bars + 15;   // elementwise -> MMA: dG is in TMEM
-  uint64_t* dq_final = bars + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* k_full = bars + 3;     // [4]
+  uint64_t* kv_empty = bars + 7;   // [4]
+  uint64_t* sdp_full = bars + 11;  // [2]
+  uint64_t* ds_full = bars + 13;   // [2]
+  uint64_t* dq_done = bars + 15;   // all scale*dS*K MMAs retired
+  uint64_t* dg_full = bars + 16;   // elementwise -> MMA: dG is in TMEM
+  uint64_t* dq_final = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQTile;
@@ -137,20 +138,17 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     tma_prefetch_desc(&tmap_do);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    tma_prefetch_desc(&tmap_kt);
     tma_prefetch_desc(&tmap_rel);
-    tma_prefetch_desc(&tmap_relt);
     mbar_init(q_full, 1);
     mbar_init(g_full, 1);
     mbar_init(g_free, 8);
-    mbar_init(relt_full, 1);
     for (int i = 0; i < kStagesQ; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&ds_full[i], 8);
+      mbar_init(&ds_full[i], 4);   // the four warps of the warpgroup that owns the buffer
     }
     mbar_init(dq_done, 1);
     mbar_init(dg_full, 8);
@@ -182,25 +180,16 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           mbar_arrive_expect_tx(&k_full[st], kStageQBytes);
           tma_load_3d(base, &tmap_k, &k_full[st], 0, kb * kKB, sh);
           tma_load_3d(base + kKBytes, &tmap_v, &k_full[st], 0, kb * kKB, sh);
-          tma_load_3d(base + 2 * kKBytes, &tmap_kt, &k_full[st], kb * kKB, 0, sh);
-          tma_load_3d(base + 2 * kKBytes + 8192, &tmap_kt, &k_full[st], kb * kKB + 64, 0, sh);
         }
         __syncwarp();
-        if (kb == kStagesQ - 1) {
-          // the rel region is free once G has been computed: bring in relcat^T for the bias-gradient MMA
-          mbar_wait(g_full, 0);
-          if (elect_one_sync()) {
-            mbar_arrive_expect_tx(relt_full, kRelRegion);
-            for (int a = 0; a < 3; ++a) tma_load_2d(sRel + a * 8192, &tmap_relt, relt_full, a * 64, 0);
-          }
-          __syncwarp();
-        }
       }
     } else if (warp == 1) {
       // ============================ MMA issuer (warp-uniform loop, one elected lane issues) ============================
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKB);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, kRelRows);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+      // B operands whose K dimension is the ROW index of a [rows][64 x bf16] tile (keys of the K block, rows of relcat8)
+      // are read straight from the tile the K-major MMAs use, as MN-major operands: no transposed copies
+      constexpr uint32_t idesc_o = umma_idesc_16bit(128, 64, 1, 1, 0, 1);
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), rel_addr = smem_u32(sRel);
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -242,14 +231,13 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_wait(&ds_full[buf], (kb >> 1) & 1);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t kt_addr = smem_u32(sRing + st * kStageQBytes + 2 * kKBytes);
+          const uint32_t k_addr = smem_u32(sRing + st * kStageQBytes);
           const uint32_t a_base = tmem_base + buf * kQColBuf;
 #pragma unroll
           for (int k = 0; k < kKB / 16; ++k) {
             // dS (bf16 pairs) of columns [0,64) sits at S columns [0,32), of columns [64,112) at S columns [64,88)
             const uint32_t a = a_base + (k < 4 ? k * 8 : 64 + (k - 4) * 8);
-            umma_bf16_ts(tmem_base + kQColdQ, a, umma_desc_sw128_kmajor(kt_addr + (k >> 2) * 8192 + (k & 3) * 32),
-                         idesc_o, (kb | k) != 0);
+            umma_bf16_ts(tmem_base + kQColdQ, a, umma_desc_sw128_mnmajor(k_addr + k * 2048), idesc_o, (kb | k) != 0);
           }
           umma_commit(&kv_empty[st]);
           if (kb == kNumKB - 1) umma_commit(dq_done);
@@ -258,14 +246,13 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (kb + 2 < kNumKB) issue_sdp(kb + 2);
       }
       // bias gradient: dQ_acc += dG relcat8   (relcat8 = 8 rel = rel / scale)
-      mbar_wait(relt_full, 0);
       mbar_wait(dg_full, 0);
       tc_fence_after();
       if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < kRelRows / 16; ++k)
-          umma_bf16_ts(tmem_base + kQColdQ, tmem_base + k * 8,
-                       umma_desc_sw128_kmajor(rel_addr + (k >> 2) * 8192 + (k & 3) * 32), idesc_o, 1u);
+          umma_bf16_ts(tmem_base + kQColdQ, tmem_base + k * 8, umma_desc_sw128_mnmajor(rel_addr + k * 2048), idesc_o,
+                       1u);
         umma_commit(dq_final);
       }
       __syncwarp();
@@ -274,7 +261,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     // ============================ elementwise warps ============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsWork));
     const int quarter = warp & 3;
-    const int g = (warp - 4) >> 2;  // column group: 0 -> key columns [0,64), 1 -> [64,112)
+    const int g = (warp - 4) >> 2;  // warpgroup: owns the key blocks kb with (kb & 1) == g (and S / dP buffer g)
     const int r = quarter * 32 + lane;
     const int qi_raw = q0 + r;
     const bool valid = qi_raw < kT;
@@ -284,12 +271,15 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     __half* tab = tab16 + static_cast<long long>(sh) * kTabRows * kT;
     float* dsh_row = sDsh + r * kDshStride;
 
-    // ---- prologue: bias rows of this query (x log2 e); bw stays in registers, bh goes through the global table ----
+    // ---- prologue: the CTA's [88 rows][128 queries] slice of the fp16 bias table goes to shared memory (warpgroup 0:
+    //      the 56 token-row biases bh, warpgroup 1: the 28 token-column biases bw and the -lse rows), is copied from there
+    //      to the global table with 16-byte stores, and stays resident for this kernel's own bias lookups ----
     mbar_wait(g_full, 0);
     tc_fence_after();
-    float bw[kGridW];
-    {
-      const int off_h = 55 - qh;  // bh[kh] = G[off_h + kh]
+    const float lse_q = valid ? lse[static_cast<long long>(sh) * kT + qi] : 0.f;
+    const float d_q = valid ? Dvec[static_cast<long long>(sh) * kT + qi] : 0.f;
+    if (g == 0) {
+      const int off_h = 55 - qh;  // bh[kh] = G[off_h + kh]  (already in the log2 domain)
 #pragma unroll
       for (int c = 0; c < 112; c += 16) {
         float v[16];
@@ -298,9 +288,10 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int kh = c + i - off_h;
-          if (kh >= 0 && kh < kGridH && valid) tab[kh * kT + qi] = __float2half_rn(v[i]);  // log2 domain
+          if (kh >= 0 && kh < kGridH) sBias[kh * kQTile + r] = __float2half_rn(v[i]);
         }
       }
+    } else {
       const int off_w = 27 - qw;  // bw[kw] = G[112 + off_w + kw]
 #pragma unroll
       for (int c = 0; c < 64; c += 16) {
@@ -310,45 +301,49 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int kw = c + i - off_w;
-          if (kw >= 0 && kw < kGridW && valid) tab[(kGridH + kw) * kT + qi] = __float2half_rn(v[i]);
+          if (kw >= 0 && kw < kGridW) sBias[(kGridH + kw) * kQTile + r] = __float2half_rn(v[i]);
         }
       }
-      // both column groups of a row write the same values; every thread reads back what it wrote itself
-#pragma unroll
-      for (int kw = 0; kw < kGridW; ++kw) bw[kw] = valid ? __half2float(tab[(kGridH + kw) * kT + qi]) : 0.f;
-    }
-    if (g == 0)
-      for (int i = 0; i < kGridH; ++i) dsh_row[i] = 0.f;
-    const float lse_q = valid ? lse[static_cast<long long>(sh) * kT + qi] : 0.f;
-    const float d_q = valid ? Dvec[static_cast<long long>(sh) * kT + qi] : 0.f;
-    if (valid && g == 0) {
-      // rows of the dkv kernel's tables that depend on the query only: -lse as fp16 hi + lo, -D as three bf16 terms
+      // rows that depend on the query only: -lse as fp16 hi + lo (rows 84, 85; 86, 87 = 0), -D as three bf16 terms
       const __half l_hi = __float2half_rn(-lse_q);
-      const __half l_lo = __float2half_rn(-lse_q - __half2float(l_hi));
-      tab[(kBiasRows + 0) * kT + qi] = l_hi;
-      tab[(kBiasRows + 1) * kT + qi] = l_lo;
-      tab[(kBiasRows + 2) * kT + qi] = __float2half_rn(0.f);
-      tab[(kBiasRows + 3) * kT + qi] = __float2half_rn(0.f);
-      __nv_bfloat16* drow = dtab + static_cast<long long>(sh) * kDRows * kT + qi;
-      float rest = -d_q;
+      sBias[(kBiasRows + 0) * kQTile + r] = l_hi;
+      sBias[(kBiasRows + 1) * kQTile + r] = __float2half_rn(-lse_q - __half2float(l_hi));
+      sBias[(kBiasRows + 2) * kQTile + r] = __float2half_rn(0.f);
+      sBias[(kBiasRows + 3) * kQTile + r] = __float2half_rn(0.f);
+      if (valid) {
+        __nv_bfloat16* drow = dtab + static_cast<long long>(sh) * kDRows * kT + qi;
+        float rest = -d_q;
 #pragma unroll
-      for (int i = 0; i < kDRows; ++i) {
-        const __nv_bfloat16 part = __float2bfloat16_rn(rest);
-        drow[i * kT] = part;
-        rest -= __bfloat162float(part);
+        for (int i = 0; i < kDRows; ++i) {
+          const __nv_bfloat16 part = __float2bfloat16_rn(rest);
+          drow[i * kT] = part;
+          rest -= __bfloat162float(part);
+        }
       }
     }
     tc_fence_before();
-    named_bar_sync(1, 256);  // dsh rows zeroed, both groups' table rows written (each thread re-reads what it wrote)
+    named_bar_sync(1, 256);  // the table slice is complete; every G column has been read
     if (lane == 0) mbar_arrive(g_free);
+    {
+      // 88 rows x 16 chunks of 8 queries; T - q0 is a multiple of 8, so a chunk is all valid or all out of range
+      const int t = threadIdx.x - 128;
+      for (int idx = t; idx < kTabRows * (kQTile / 8); idx += 256) {
+        const int row = idx >> 4, c8 = (idx & 15) * 8;
+        if (q0 + c8 < kT)
+          *reinterpret_cast<uint4*>(tab + row * kT + q0 + c8) = *reinterpret_cast<const uint4*>(sBias + row * kQTile + c8);
+      }
+    }
+    float bw[kGridW];
+#pragma unroll
+    for (int kw = 0; kw < kGridW; ++kw) bw[kw] = __half2float(sBias[(kGridH + kw) * kQTile + r]);
 
-    const float sc = 1.0f;  // qs carries scale * log2(e)
     float dsw[kGridW];
 #pragma unroll
     for (int i = 0; i < kGridW; ++i) dsw[i] = 0.f;
 
-    // one chunk of N columns starting at compile-time column C0: P = exp2(S*sc + bias - lse), dS = P * (dP - D)
-    auto chunk = [&](auto c0_tag, auto n_tag, uint32_t sbase, const float (&boff)[4], float (&acc4)[4]) {
+    // One chunk of N columns starting at compile-time column C0: P = exp2(S + bias - lse), dS = P * (dP - D); pairs of
+    // columns go through the packed fp32 pipe (a pair never straddles a token row: 28 is even).
+    auto chunk = [&](auto c0_tag, auto n_tag, uint32_t sbase, const float (&boff)[4], float (&acc)[8]) {
       constexpr int C0 = decltype(c0_tag)::value, N = decltype(n_tag)::value;
       float s[32], dp[32];
       if constexpr (N == 32) {
@@ -362,15 +357,18 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       uint32_t pk[N / 2];
 #pragma unroll
       for (int i = 0; i < N; i += 2) {
-        const int c0 = C0 + i, c1 = C0 + i + 1;
-        const float x0 = fmaf(s[i], sc, bw[c0 % kGridW]) + boff[c0 / kGridW];
-        const float x1 = fmaf(s[i + 1], sc, bw[c1 % kGridW]) + boff[c1 / kGridW];
-        const float ds0 = ex2_approx(x0) * (dp[i] - d_q);
-        const float ds1 = ex2_approx(x1) * (dp[i + 1] - d_q);
-        dsw[c0 % kGridW] += ds0;
-        dsw[c1 % kGridW] += ds1;
-        acc4[c0 / kGridW] += ds0;
-        acc4[c1 / kGridW] += ds1;
+        const int c0 = C0 + i;
+        const int wi = c0 % kGridW, hi = c0 / kGridW;
+        float x0 = s[i], x1 = s[i + 1];
+        add_f32x2(x0, x1, bw[wi], bw[wi + 1]);
+        add_f32x2(x0, x1, boff[hi], boff[hi]);
+        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        float t0 = dp[i], t1 = dp[i + 1];
+        add_f32x2(t0, t1, -d_q, -d_q);
+        float ds0, ds1;
+        mul_f32x2(ds0, ds1, p0, p1, t0, t1);
+        add_f32x2(dsw[wi], dsw[wi + 1], ds0, ds1);
+        add_f32x2(acc[2 * hi], acc[2 * hi + 1], ds0, ds1);
         pk[i >> 1] = pack_bf16x2(ds0, ds1);
       }
       // dS (bf16 pairs) in place over the S columns this thread has just consumed
@@ -386,38 +384,26 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     using I64 = std::integral_constant<int, 64>;
     using I96 = std::integral_constant<int, 96>;
 
-    // bias rows of the block (global table, L2 latency): fetched one key block ahead
-    float bnext[4];
+    // The two warpgroups take alternate key blocks (warpgroup g <-> S / dP buffer g), each thread a whole row of 112
+    // columns, so that one warpgroup's hand-off latencies (barrier wait, tcgen05.ld / st round trips) sit under the
+    // other's exponentials.
+    for (int kb = g; kb < kNumKB; kb += 2) {
+      float boff[4], acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) bnext[i] = valid ? __half2float(tab[i * kT + qi]) : 0.f;
-    for (int kb = 0; kb < kNumKB; ++kb) {
-      const int buf = kb & 1;
-      float boff[4], acc4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) boff[i] = bnext[i] - lse_q;
-      if (kb + 1 < kNumKB) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) bnext[i] = valid ? __half2float(tab[((kb + 1) * 4 + i) * kT + qi]) : 0.f;
-      }
-      mbar_wait(&sdp_full[buf], (kb >> 1) & 1);
+      for (int i = 0; i < 4; ++i) boff[i] = __half2float(sBias[(kb * 4 + i) * kQTile + r]) - lse_q;
+      mbar_wait(&sdp_full[g], (kb >> 1) & 1);
       tc_fence_after();
-      const uint32_t sbase = lane_base + buf * kQColBuf;
-      if (g == 0) {
-        chunk(I0{}, I32{}, sbase, boff, acc4);
-        chunk(I32{}, I32{}, sbase, boff, acc4);
-        red_shared_add_f32(&dsh_row[kb * 4 + 0], acc4[0]);
-        red_shared_add_f32(&dsh_row[kb * 4 + 1], acc4[1]);
-        red_shared_add_f32(&dsh_row[kb * 4 + 2], acc4[2]);
-      } else {
-        chunk(I64{}, I32{}, sbase, boff, acc4);
-        chunk(I96{}, I16{}, sbase, boff, acc4);
-        red_shared_add_f32(&dsh_row[kb * 4 + 2], acc4[2]);
-        red_shared_add_f32(&dsh_row[kb * 4 + 3], acc4[3]);
-      }
+      const uint32_t sbase = lane_base + g * kQColBuf;
+      chunk(I0{}, I32{}, sbase, boff, acc);
+      chunk(I32{}, I32{}, sbase, boff, acc);
+      chunk(I64{}, I32{}, sbase, boff, acc);
+      chunk(I96{}, I16{}, sbase, boff, acc);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ds_full[buf]);
+      if (lane == 0) mbar_arrive(&ds_full[g]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dsh_row[kb * 4 + i] = acc[2 * i] + acc[2 * i + 1];
     }
 
     // ---- bias gradient: dG[q, :] (176 columns) = dSh scattered at off_h + kh, dSw scattered at 112 + off_w + kw ----
@@ -496,7 +482,6 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 __global__ void __launch_bounds__(abwd::kThreads, 1)
 attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                          const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
-                         const __grid_constant__ CUtensorMap tmap_qt, const __grid_constant__ CUtensorMap tmap_dot,
                          const __grid_constant__ CUtensorMap tmap_tabh, const __grid_constant__ CUtensorMap tmap_tabw,
                          const __grid_constant__ CUtensorMap tmap_tabd, __nv_bfloat16* __restrict__ dqkv, int heads) {
   using namespace abwd;
@@ -508,12 +493,12 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
   uint8_t* sRing = smem + kKOffRing;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKOffBar);
   uint64_t* kv_full = bars + 0;
-  uint64_t* full = bars + 1;        // [3]
-  uint64_t* empty = bars + 4;       // [3]
-  uint64_t* sdp_full = bars + 7;    // [2]
-  uint64_t* pds_full = bars + 9;    // [2]
-  uint64_t* dkv_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* full = bars + 1;        // [4]
+  uint64_t* empty = bars + 5;       // [4]
+  uint64_t* sdp_full = bars + 9;    // [2]
+  uint64_t* pds_full = bars + 11;   // [2]
+  uint64_t* dkv_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kKTile;
@@ -526,8 +511,6 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_do);
-    tma_prefetch_desc(&tmap_qt);
-    tma_prefetch_desc(&tmap_dot);
     tma_prefetch_desc(&tmap_tabh);
     tma_prefetch_desc(&tmap_tabw);
     tma_prefetch_desc(&tmap_tabd);
@@ -538,7 +521,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&pds_full[i], 8);
+      mbar_init(&pds_full[i], 4);   // the four warps of the warpgroup that owns the buffer
     }
     mbar_init(dkv_done, 1);
     fence_barrier_init();
@@ -592,8 +575,6 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
           mbar_arrive_expect_tx(&full[st], kStageKBytes);  // full boxes: out-of-range rows / queries arrive as zeros
           tma_load_3d(base, &tmap_q, &full[st], 0, j * kQB, sh);
           tma_load_4d(base + kTileBytes, &tmap_do, &full[st], 0, j * kQB, head, seq);
-          tma_load_3d(base + 2 * kTileBytes, &tmap_qt, &full[st], j * kQB, 0, sh);
-          tma_load_3d(base + 3 * kTileBytes, &tmap_dot, &full[st], j * kQB, 0, sh);
           // 16 table rows from kh_lo (the tile touches at most 6; the others meet zero columns of A), the 32 rows
           // bw / -lse, the 3 (+13 out-of-range = zero) rows of -D
           tma_load_3d(base + kTabHOff, &tmap_tabh, &full[st], j * kQB, kh_lo, sh);
@@ -607,6 +588,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       constexpr uint32_t idesc_tab = umma_idesc_16bit(128, 64, 0, 0, 0, 1);   // fp16 x fp16, B MN-major
       constexpr uint32_t idesc_tabd = umma_idesc_16bit(128, 64, 1, 1, 0, 1);  // bf16 x bf16, B MN-major
+      constexpr uint32_t idesc_grad = idesc_tabd;  // dV += P^T dO, dK += dS^T Q: K = query = ROW of the dO / Q tile
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), a_addr = smem_u32(sA);
       mbar_wait(kv_full, 0);
       tc_fence_after();
@@ -645,17 +627,17 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
         mbar_wait(&pds_full[buf], (j >> 1) & 1);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t qt_addr = smem_u32(sRing + st * kStageKBytes + 2 * kTileBytes);
-          const uint32_t dot_addr = qt_addr + kTileBytes;
+          const uint32_t q_addr = smem_u32(sRing + st * kStageKBytes), do_addr = q_addr + kTileBytes;
           const uint32_t a_base = tmem_base + buf * kKColBuf;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // P^T (bf16 pairs) of queries [0,32) at S columns [0,16), of queries [32,64) at S columns [32,48)
+            // P^T (bf16 pairs) of queries [0,32) at S columns [0,16), of queries [32,64) at S columns [32,48);
+            // the B operand is the block's dO / Q tile read MN-major: 16 query rows = 2048 bytes per K step
             const uint32_t a_off = (k < 2 ? k * 8 : 32 + (k - 2) * 8);
-            umma_bf16_ts(tmem_base + kKColdV, a_base + a_off, umma_desc_sw128_kmajor(dot_addr + k * 32), idesc,
+            umma_bf16_ts(tmem_base + kKColdV, a_base + a_off, umma_desc_sw128_mnmajor(do_addr + k * 2048), idesc_grad,
                          (j | k) != 0);
-            umma_bf16_ts(tmem_base + kKColdK, a_base + kKColdP + a_off, umma_desc_sw128_kmajor(qt_addr + k * 32), idesc,
-                         (j | k) != 0);
+            umma_bf16_ts(tmem_base + kKColdK, a_base + kKColdP + a_off, umma_desc_sw128_mnmajor(q_addr + k * 2048),
+                         idesc_grad, (j | k) != 0);
           }
           umma_commit(&empty[st]);
           if (j == kNumQB - 1) umma_commit(dkv_done);
@@ -667,37 +649,41 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
   } else {
     // ============================ elementwise warps ============================
     const int quarter = warp & 3;
-    const int g = (warp - 4) >> 2;  // query columns [32g, 32g + 32) of the block
+    const int g = (warp - 4) >> 2;  // warpgroup: owns the query blocks j with (j & 1) == g (and S / dP buffer g)
     const int r = quarter * 32 + lane;
     const int ki_raw = k0 + r;
     const bool valid = ki_raw < kT;
     const int ki = valid ? ki_raw : kT - 1;
     const uint32_t lane_base = tmem_lane_base(tmem_base, quarter);
 
-    for (int j = 0; j < kNumQB; ++j) {
-      const int buf = j & 1;
-      mbar_wait(&sdp_full[buf], (j >> 1) & 1);
+    // The two warpgroups take alternate query blocks, each thread the whole 64-column row of its key, so that one
+    // warpgroup's hand-off latencies sit under the other's exponentials.
+    for (int j = g; j < kNumQB; j += 2) {
+      mbar_wait(&sdp_full[g], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t sbase = lane_base + buf * kKColBuf;
-      float s[32], dp[32];
-      tmem_ld32(sbase + g * 32, s);              // S^T + bias - lse  (log2 domain)
-      tmem_ld32(sbase + kKColdP + g * 32, dp);   // dP^T - D
-      tmem_ld_wait();
-      uint32_t pp[16], pd[16];
+      const uint32_t sbase = lane_base + g * kKColBuf;
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(s[i]), p1 = ex2_approx(s[i + 1]);
-        float d0, d1;
-        mul_f32x2(d0, d1, p0, p1, dp[i], dp[i + 1]);
-        pp[i >> 1] = pack_bf16x2(p0, p1);
-        pd[i >> 1] = pack_bf16x2(d0, d1);
+      for (int h = 0; h < 2; ++h) {
+        float s[32], dp[32];
+        tmem_ld32(sbase + h * 32, s);              // S^T + bias - lse  (log2 domain)
+        tmem_ld32(sbase + kKColdP + h * 32, dp);   // dP^T - D
+        tmem_ld_wait();
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2_approx(s[i]), p1 = ex2_approx(s[i + 1]);
+          float d0, d1;
+          mul_f32x2(d0, d1, p0, p1, dp[i], dp[i + 1]);
+          pp[i >> 1] = pack_bf16x2(p0, p1);
+          pd[i >> 1] = pack_bf16x2(d0, d1);
+        }
+        tmem_st16u(sbase + h * 32, pp);
+        tmem_st16u(sbase + kKColdP + h * 32, pd);
       }
-      tmem_st16u(sbase + g * 32, pp);
-      tmem_st16u(sbase + kKColdP + g * 32, pd);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pds_full[buf]);
+      if (lane == 0) mbar_arrive(&pds_full[g]);
     }
 
     // ---- epilogue: dv -> columns [2D, 3D), dk * scale -> columns [D, 2D) of the token-major dqkv rows ----
@@ -733,17 +719,15 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
 // =====================================================================================================
 // launcher
 // =====================================================================================================
-int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
-                         const __nv_bfloat16* qt, const __nv_bfloat16* kt, const __nv_bfloat16* dO,
-                         const __nv_bfloat16* dOt, const float* lse, const float* Dvec, const __nv_bfloat16* relcat,
-                         const __nv_bfloat16* relcat_t, float* bias_tab, __nv_bfloat16* dqkv, int nseq, int heads,
-                         cudaStream_t stream) {
+int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* dO,
+                         const float* lse, const float* Dvec, const __nv_bfloat16* relcat, float* bias_tab,
+                         __nv_bfloat16* dqkv, int nseq, int heads, cudaStream_t stream) {
   using namespace abwd;
   BSEG_REQUIRE(nseq > 0 && heads > 0, "attention_bwd: empty problem");
   const uint64_t nsh = static_cast<uint64_t>(nseq) * heads;
   const uint64_t D = static_cast<uint64_t>(heads) * 64;
-  CUtensorMap tq128, tq64, tk128, tk112, tv128, tv112, tkt, tqt, tdot, tdo128, tdo64, trel, trelt, ttabh, ttabw, ttabd;
-  // the scratch the caller sized for the former fp32 table ([nsh, 84, T] floats) holds both 16-bit tables
+  CUtensorMap tq128, tq64, tk128, tk112, tv128, tv112, tdo128, tdo64, trel, ttabh, ttabw, ttabd;
+  // the scratch the caller sizes as [nsh, 84, T] floats holds both 16-bit tables
   __half* tab16 = reinterpret_cast<__half*>(bias_tab);
   __nv_bfloat16* dtab = reinterpret_cast<__nv_bfloat16*>(tab16 + nsh * kTabRows * kT);
   static_assert((kTabRows + kDRows) * 2 <= kBiasRows * 4, "16-bit tables must fit in the bias scratch");
@@ -758,14 +742,6 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
     if ((rc = make_tmap_bf16(&tk112, k, 3, dims, strides, b112))) return rc;
     if ((rc = make_tmap_bf16(&tv128, v, 3, dims, strides, b128))) return rc;
     if ((rc = make_tmap_bf16(&tv112, v, 3, dims, strides, b112))) return rc;
-  }
-  {
-    uint64_t dims[3] = {static_cast<uint64_t>(kT), 64, nsh};
-    uint64_t strides[2] = {static_cast<uint64_t>(kT) * 2, static_cast<uint64_t>(kT) * 128};
-    uint32_t box[3] = {64, 64, 1};
-    if ((rc = make_tmap_bf16(&tkt, kt, 3, dims, strides, box))) return rc;
-    if ((rc = make_tmap_bf16(&tqt, qt, 3, dims, strides, box))) return rc;
-    if ((rc = make_tmap_bf16(&tdot, dOt, 3, dims, strides, box))) return rc;
   }
   {
     // dO is token-major [nseq*T, heads*64]: dims (d, t, head, seq)
@@ -787,7 +763,6 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
     if ((rc = make_tmap_bf16(&ttabd, dtab, 3, ddims, dstrides, b16))) return rc;
   }
   if ((rc = make_tmap_bf16_2d(&trel, relcat, 64, kRelRows, 64, 64, kRelRows))) return rc;
-  if ((rc = make_tmap_bf16_2d(&trelt, relcat_t, 192, 64, 192, 64, 64))) return rc;
   static PerDeviceFlag attr_once;
   if (attr_once.first()) {
     BSEG_CHECK_CUDA(
@@ -799,17 +774,17 @@ int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const _
   {
     dim3 grid((kT + kQTile - 1) / kQTile, heads, nseq);
     ProfScope prof(CAT_ATTENTION, pair * 64 * 2 * 3 + static_cast<double>(nseq) * heads * kT * 2.0 * 176 * 64 * 2,
-                   static_cast<double>(nseq) * heads * kT * (64 * 2 * 5 + kBiasRows * 4), stream);
-    attention_bwd_dq_kernel<<<grid, kThreads, kQSmemBytes, stream>>>(tq128, tdo128, tk112, tv112, tkt, trel, trelt, lse,
-                                                                     Dvec, tab16, dtab, dqkv, heads);
+                   static_cast<double>(nseq) * heads * kT * (64 * 2 * 5 + (kTabRows + kDRows) * 2), stream);
+    attention_bwd_dq_kernel<<<grid, kThreads, kQSmemBytes, stream>>>(tq128, tdo128, tk112, tv112, trel, lse, Dvec, tab16,
+                                                                     dtab, dqkv, heads);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
   {
     dim3 grid((kT + kKTile - 1) / kKTile, heads, nseq);
-    ProfScope prof(CAT_ATTENTION, pair * 64 * 2 * 4, static_cast<double>(nseq) * heads * kT * (64 * 2 * 8), stream);
-    attention_bwd_dkv_kernel<<<grid, kThreads, kKSmemBytes, stream>>>(tk128, tv128, tq64, tdo64, tqt, tdot, ttabh,
-                                                                      ttabw, ttabd, dqkv, heads);
+    ProfScope prof(CAT_ATTENTION, pair * 64 * 2 * 4, static_cast<double>(nseq) * heads * kT * (64 * 2 * 6), stream);
+    attention_bwd_dkv_kernel<<<grid, kThreads, kKSmemBytes, stream>>>(tk128, tv128, tq64, tdo64, ttabh, ttabw, ttabd, dqkv,
+                                                                      heads);
     BSEG_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }

@@ -190,17 +190,15 @@ int launch_unpatchify_prompt_grad(const float* dA, float* dprompt, int B, cudaSt
 
 // ----------------------------------------------------------------------------------------------
 // Attention-backward operand preparation for one layer (all per (sequence, head)):
-//   dOt[sh][d][t] = dO[seq*T + t][head*64 + d]            (K-major B operand of dV += P^T dO)
-//   Dvec[sh][t]   = sum_d dO[.][d] * O[.][d]              (softmax backward row term)
-//   qt[sh][d][t]  = q[sh][t][d],  kt[sh][d][t] = k[sh][t][d],  v[sh][t][d] = vt[sh][d][t]
-// dO and O are token-major [nseq*T, heads*64] bf16; q, k are [nseq*heads, T, 64]; vt is [nseq*heads, 64, T].
-// One block handles 64 tokens of one (seq, head) for all five products.
+//   Dvec[sh][t] = sum_d dO[.][d] * O[.][d]      (softmax backward row term)
+//   v[sh][t][d] = vt[sh][d][t]                  (K-major operand of dP = dO v^T)
+// dO and O are token-major [nseq*T, heads*64] bf16; vt is [nseq*heads, 64, T].  One block handles 64 tokens of one
+// (seq, head).  (The other transposed operands the backward once needed -- q^T, k^T, dO^T -- are gone: the kernels
+// read the row-major tiles as MN-major MMA operands.)
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
-                     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                     const __nv_bfloat16* __restrict__ vt, __nv_bfloat16* __restrict__ dOt, float* __restrict__ Dvec,
-                     __nv_bfloat16* __restrict__ qt, __nv_bfloat16* __restrict__ kt, __nv_bfloat16* __restrict__ v,
+                     const __nv_bfloat16* __restrict__ vt, float* __restrict__ Dvec, __nv_bfloat16* __restrict__ v,
                      int heads, int T) {
   __shared__ __nv_bfloat16 tile[64][66];
   const int t0 = blockIdx.x * 64;
@@ -208,9 +206,8 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* 
   const int seq = sh / heads, head = sh % heads;
   const int D = heads * 64;
   const int tid = threadIdx.x;
-  // ---- dO -> dOt and Dvec ----
+  // ---- Dvec: thread (row = tid/4, 16 columns at (tid%4)*16) ----
   {
-    // thread (row = tid/4, 16 columns at (tid%4)*16)
     const int r = tid >> 2, c0 = (tid & 3) * 16;
     float part = 0.f;
     if (t0 + r < T) {
@@ -220,54 +217,15 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* 
       const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; ++j)
         part += __uint_as_float(aw[j] << 16) * __uint_as_float(bw[j] << 16) +
                 __uint_as_float(aw[j] & 0xffff0000u) * __uint_as_float(bw[j] & 0xffff0000u);
-        *reinterpret_cast<uint32_t*>(&tile[r][c0 + 2 * j]) = aw[j];
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(&tile[r][c0 + 2 * j]) = 0u;
     }
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     if ((tid & 3) == 0 && t0 + r < T) Dvec[(long long)sh * T + t0 + r] = part;
   }
-  __syncthreads();
-  {
-    const int tl = tid & 63, dg = (tid >> 6) * 16;  // a warp writes 32 consecutive tokens of one d row
-    if (t0 + tl < T) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) dOt[((long long)sh * 64 + dg + j) * T + t0 + tl] = tile[tl][dg + j];
-    }
-  }
-  // ---- q -> qt, k -> kt ----
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    const __nv_bfloat16* src = which == 0 ? q : k;
-    __nv_bfloat16* dst = which == 0 ? qt : kt;
-    __syncthreads();
-    {
-      const int r = tid >> 2, c0 = (tid & 3) * 16;
-      if (t0 + r < T) {
-        const long long off = ((long long)sh * T + t0 + r) * 64 + c0;
-        const uint4 a0 = *reinterpret_cast<const uint4*>(src + off), a1 = *reinterpret_cast<const uint4*>(src + off + 8);
-        const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(&tile[r][c0 + 2 * j]) = aw[j];
-      }
-    }
-    __syncthreads();
-    {
-      const int tl = tid & 63, dg = (tid >> 6) * 16;
-      if (t0 + tl < T) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dst[((long long)sh * 64 + dg + j) * T + t0 + tl] = tile[tl][dg + j];
-      }
-    }
-  }
   // ---- vt -> v ----
-  __syncthreads();
   {
     const int tl = tid & 63, dg = (tid >> 6) * 16;
 #pragma unroll
@@ -291,14 +249,12 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* 
     }
   }
 }
-int launch_attn_bwd_prep(const __nv_bfloat16* dO, const __nv_bfloat16* O, const __nv_bfloat16* q,
-                         const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* dOt, float* Dvec,
-                         __nv_bfloat16* qt, __nv_bfloat16* kt, __nv_bfloat16* v, int nseq, int heads, int T,
-                         cudaStream_t stream) {
+int launch_attn_bwd_prep(const __nv_bfloat16* dO, const __nv_bfloat16* O, const __nv_bfloat16* vt, float* Dvec,
+                         __nv_bfloat16* v, int nseq, int heads, int T, cudaStream_t stream) {
   BSEG_REQUIRE(nseq > 0 && heads > 0 && nseq * heads <= 65535, "attn_bwd_prep: bad shape");
   dim3 grid((T + 63) / 64, nseq * heads);
-  ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(nseq) * heads * T * 64 * 2 * 9, stream);
-  attn_bwd_prep_kernel<<<grid, 256, 0, stream>>>(dO, O, q, k, vt, dOt, Dvec, qt, kt, v, heads, T);
+  ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(nseq) * heads * T * (64 * 2 * 4 + 4), stream);
+  attn_bwd_prep_kernel<<<grid, 256, 0, stream>>>(dO, O, vt, Dvec, v, heads, T);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -29,13 +29,12 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
 int attention_relcat_rows(int grid_h, int grid_w);
 
 // attention_bwd.cu : dq, dk, dv of the fused attention, written token-major into dqkv [nseq*T, 3*heads*64] bf16
-//   q, k, v : [nseq*heads, T, 64];  qt, kt, dOt : [nseq*heads, 64, T];  dO : token-major [nseq*T, heads*64]
-//   lse, Dvec : [nseq*heads, T] fp32;  relcat [176,64], relcat_t [64,192] bf16;  bias_tab : scratch [nseq*heads, 84, T] fp32
-int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
-                         const __nv_bfloat16* qt, const __nv_bfloat16* kt, const __nv_bfloat16* dO,
-                         const __nv_bfloat16* dOt, const float* lse, const float* Dvec, const __nv_bfloat16* relcat,
-                         const __nv_bfloat16* relcat_t, float* bias_tab, __nv_bfloat16* dqkv, int nseq, int heads,
-                         cudaStream_t stream);
+//   q, k, v : [nseq*heads, T, 64] (qs pre-scaled like the forward's);  dO : token-major [nseq*T, heads*64]
+//   lse, Dvec : [nseq*heads, T] fp32;  relcat8 [176,64] bf16;  bias_tab : scratch of nseq*heads*84*T floats (holds the
+//   16-bit per-query tables the dq kernel hands to the dk/dv kernel)
+int launch_attention_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* dO,
+                         const float* lse, const float* Dvec, const __nv_bfloat16* relcat, float* bias_tab,
+                         __nv_bfloat16* dqkv, int nseq, int heads, cudaStream_t stream);
 
 // decoder_conv.cu : conv3x3(64->64, pad 1) + LayerNorm(C=64) + erf-GELU + conv1x1(64->3), NHWC bf16 in, NCHW fp32 out
 int launch_decoder_head(const __nv_bfloat16* x_nhwc, const __nv_bfloat16* w9 /*[9][64 out][64 in]*/,
@@ -60,10 +59,8 @@ int launch_layernorm1024_bwd(const float* x, const float* dy, long long lddy, co
 int launch_scale_f32_bf16(const float* src, float* dst, __nv_bfloat16* dst_bf16, float scale, long long n,
                           cudaStream_t stream);
 int launch_unpatchify_prompt_grad(const float* dA, float* dprompt, int B, cudaStream_t stream);
-int launch_attn_bwd_prep(const __nv_bfloat16* dO, const __nv_bfloat16* O, const __nv_bfloat16* q,
-                         const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* dOt, float* Dvec,
-                         __nv_bfloat16* qt, __nv_bfloat16* kt, __nv_bfloat16* v, int nseq, int heads, int T,
-                         cudaStream_t stream);
+int launch_attn_bwd_prep(const __nv_bfloat16* dO, const __nv_bfloat16* O, const __nv_bfloat16* vt, float* Dvec,
+                         __nv_bfloat16* v, int nseq, int heads, int T, cudaStream_t stream);
 
 // elementwise.cu
 int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t stream);
