@@ -72,7 +72,8 @@ constexpr uint32_t kQColBuf = 224, kQColdP = 112, kQColdQ = 448;
 // ---------------- dkv kernel ----------------
 constexpr int kKTile = 128;
 constexpr int kQB = 64, kNumQB = (kT + kQB - 1) / kQB;  // 25 (the last block has 32 live queries)
-constexpr int kStagesK = 4;
+constexpr int kStagesK = 5;
+constexpr int kBufsK = 3;                  // S^T / dP^T buffers in TMEM = query blocks in flight
 constexpr int kTileBytes = 64 * 128;       // 8192: [64 x 64] bf16
 constexpr int kTabHBytes = 16 * 128, kTabWBytes = 32 * 128, kTabDBytes = 16 * 128;  // TMA boxes of 16 / 32 / 16 rows
 // a stage: Q block, dO block (each both the K-major B of the score MMAs and the MN-major B of the gradient MMAs), tables
@@ -87,9 +88,20 @@ constexpr int kKSmemBytes = kKOffBar + 256 + 1024;
 static_assert(kStageKBytes % 1024 == 0 && kTabHOff % 1024 == 0 && kTabWOff % 1024 == 0 && kTabDOff % 1024 == 0,
               "swizzle alignment");
 static_assert(kKSmemBytes <= 227 * 1024, "dkv kernel shared memory");
-// TMEM columns: S0 [0,64) dP0 [64,128) S1 [128,192) dP1 [192,256) dV [256,320) dK [320,384)
-constexpr uint32_t kKColBuf = 128, kKColdP = 64, kKColdV = 256, kKColdK = 320;
+// TMEM columns: three S^T / dP^T buffers [b * 128, +64) / [b * 128 + 64, +64), dV [384,448), dK [448,512)
+constexpr uint32_t kKColBuf = 128, kKColdP = 64, kKColdV = 384, kKColdK = 448;
 }  // namespace abwd
+
+// Optional timeline instrumentation (tools/micro/abwd_trace.cu defines BSEG_ABWD_TRACE): clock64 stamps of CTA (0,0,0).
+#ifdef BSEG_ABWD_TRACE
+__device__ long long g_abwd_trace[2][4][32][8];  // [kernel: dq, dkv][actor: tma, mma, wg0, wg1][block][event]
+#define ABWD_TRACE(kern, actor, blk, ev)                                                              \
+  do {                                                                                                \
+    if (trace_cta && lane == 0) g_abwd_trace[kern][actor][blk][ev] = clock64();                       \
+  } while (0)
+#else
+#define ABWD_TRACE(kern, actor, blk, ev) do {} while (0)
+#endif
 
 namespace {
 __device__ __forceinline__ uint32_t tmem_lane_base(uint32_t tmem_base, int quarter) {
@@ -132,6 +144,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const int q0 = blockIdx.x * kQTile;
   const int head = blockIdx.y, seq = blockIdx.z;
   const int sh = seq * heads + head;
+#ifdef BSEG_ABWD_TRACE
+  const bool trace_cta = blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -174,7 +189,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       __syncwarp();
       for (int kb = 0; kb < kNumKB; ++kb) {
         const int st = kb % kStagesQ;
+        ABWD_TRACE(0, 0, kb, 0);
         if (kb >= kStagesQ) mbar_wait(&kv_empty[st], ((kb / kStagesQ) & 1) ^ 1);
+        ABWD_TRACE(0, 0, kb, 1);
         uint8_t* base = sRing + st * kStageQBytes;
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&k_full[st], kStageQBytes);
@@ -204,7 +221,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
       auto issue_sdp = [&](int kb) {
         const int st = kb % kStagesQ;
+        ABWD_TRACE(0, 1, kb, 0);
         mbar_wait(&k_full[st], (kb / kStagesQ) & 1);
+        ABWD_TRACE(0, 1, kb, 1);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t k_addr = smem_u32(sRing + st * kStageQBytes), v_addr = k_addr + kKBytes;
@@ -220,6 +239,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           umma_commit(&sdp_full[kb & 1]);
         }
         __syncwarp();
+        ABWD_TRACE(0, 1, kb, 2);
       };
 
       mbar_wait(g_free, 0);
@@ -228,7 +248,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       issue_sdp(1);
       for (int kb = 0; kb < kNumKB; ++kb) {
         const int st = kb % kStagesQ, buf = kb & 1;
+        ABWD_TRACE(0, 1, kb, 3);
         mbar_wait(&ds_full[buf], (kb >> 1) & 1);
+        ABWD_TRACE(0, 1, kb, 4);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t k_addr = smem_u32(sRing + st * kStageQBytes);
@@ -243,6 +265,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           if (kb == kNumKB - 1) umma_commit(dq_done);
         }
         __syncwarp();
+        ABWD_TRACE(0, 1, kb, 5);
         if (kb + 2 < kNumKB) issue_sdp(kb + 2);
       }
       // bias gradient: dQ_acc += dG relcat8   (relcat8 = 8 rel = rel / scale)
@@ -391,17 +414,23 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       float boff[4], acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 4; ++i) boff[i] = __half2float(sBias[(kb * 4 + i) * kQTile + r]) - lse_q;
+      if (quarter == 0) ABWD_TRACE(0, 2 + g, kb, 0);
       mbar_wait(&sdp_full[g], (kb >> 1) & 1);
+      if (quarter == 0) ABWD_TRACE(0, 2 + g, kb, 1);
       tc_fence_after();
       const uint32_t sbase = lane_base + g * kQColBuf;
       chunk(I0{}, I32{}, sbase, boff, acc);
       chunk(I32{}, I32{}, sbase, boff, acc);
+      if (quarter == 0) ABWD_TRACE(0, 2 + g, kb, 2);
       chunk(I64{}, I32{}, sbase, boff, acc);
       chunk(I96{}, I16{}, sbase, boff, acc);
+      if (quarter == 0) ABWD_TRACE(0, 2 + g, kb, 3);
       tmem_st_wait();
+      if (quarter == 0) ABWD_TRACE(0, 2 + g, kb, 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[g]);
+      if (quarter == 0) ABWD_TRACE(0, 2 + g, kb, 5);
 #pragma unroll
       for (int i = 0; i < 4; ++i) dsh_row[kb * 4 + i] = acc[2 * i] + acc[2 * i + 1];
     }
@@ -493,18 +522,22 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
   uint8_t* sRing = smem + kKOffRing;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKOffBar);
   uint64_t* kv_full = bars + 0;
-  uint64_t* full = bars + 1;        // [4]
-  uint64_t* empty = bars + 5;       // [4]
-  uint64_t* sdp_full = bars + 9;    // [2]
-  uint64_t* pds_full = bars + 11;   // [2]
-  uint64_t* dkv_done = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* full = bars + 1;        // [5]
+  uint64_t* empty = bars + 6;       // [5]
+  uint64_t* sdp_full = bars + 11;   // [3]
+  uint64_t* pds_full = bars + 14;   // [3]
+  uint64_t* dkv_done = bars + 17;
+  uint64_t* buf_free = bars + 18;   // [3] gradient MMAs of the block that used the buffer have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kKTile;
   const int head = blockIdx.y, seq = blockIdx.z;
   const int sh = seq * heads + head;
   const int kh_lo = k0 / kGridW;
+#ifdef BSEG_ABWD_TRACE
+  const bool trace_cta = blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_k);
@@ -519,9 +552,10 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&sdp_full[i], 1);
-      mbar_init(&pds_full[i], 4);   // the four warps of the warpgroup that owns the buffer
+    for (int i = 0; i < kBufsK; ++i) {
+      mbar_init(&sdp_full[i], 2);   // one commit from the S^T issuer, one from the dP^T issuer
+      mbar_init(&pds_full[i], 4);   // the four warps of the warpgroup that works on the block
+      mbar_init(&buf_free[i], 1);
     }
     mbar_init(dkv_done, 1);
     fence_barrier_init();
@@ -569,7 +603,9 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
       __syncwarp();
       for (int j = 0; j < kNumQB; ++j) {
         const int st = j % kStagesK;
+        ABWD_TRACE(1, 0, j, 0);
         if (j >= kStagesK) mbar_wait(&empty[st], ((j / kStagesK) & 1) ^ 1);
+        ABWD_TRACE(1, 0, j, 1);
         if (elect_one_sync()) {
           uint8_t* base = sRing + st * kStageKBytes;
           mbar_arrive_expect_tx(&full[st], kStageKBytes);  // full boxes: out-of-range rows / queries arrive as zeros
@@ -583,48 +619,60 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
         }
         __syncwarp();
       }
-    } else if (warp == 1) {
-      // ============================ MMA issuer (warp-uniform loop, one elected lane issues) ============================
+    } else if (warp == 1 || warp == 3) {
+      // ============================ score-MMA issuers (warp-uniform loops, one elected lane issues) ============================
+      // Three issuing warps (S^T in warp 1, dP^T in warp 3, the gradients in warp 2): a tcgen05.mma of N = 64 costs its
+      // issuer ~57 cycles and an mbarrier wait ~170 even when the phase is long complete, so one warp doing all of it
+      // was the kernel's critical path.
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       constexpr uint32_t idesc_tab = umma_idesc_16bit(128, 64, 0, 0, 0, 1);   // fp16 x fp16, B MN-major
       constexpr uint32_t idesc_tabd = umma_idesc_16bit(128, 64, 1, 1, 0, 1);  // bf16 x bf16, B MN-major
-      constexpr uint32_t idesc_grad = idesc_tabd;  // dV += P^T dO, dK += dS^T Q: K = query = ROW of the dO / Q tile
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), a_addr = smem_u32(sA);
       mbar_wait(kv_full, 0);
-      tc_fence_after();
-      auto issue_sdp = [&](int j) {
-        const int st = j % kStagesK;
+      for (int j = 0; j < kNumQB; ++j) {
+        const int st = j % kStagesK, buf = j % kBufsK;
+        if (warp == 1) ABWD_TRACE(1, 1, j, 0);
         mbar_wait(&full[st], (j / kStagesK) & 1);
+        if (j >= kBufsK) mbar_wait(&buf_free[buf], (j / kBufsK - 1) & 1);  // P^T / dS^T of block j - 3 consumed
+        if (warp == 1) ABWD_TRACE(1, 1, j, 1);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t q_addr = smem_u32(sRing + st * kStageKBytes), do_addr = q_addr + kTileBytes;
-          const uint32_t d = tmem_base + (j & 1) * kKColBuf;
+          const uint32_t d = tmem_base + buf * kKColBuf;
+          if (warp == 1) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // S^T = K Q_blk^T
-            umma_bf16_ss(d, umma_desc_sw128_kmajor(k_addr + k * 32), umma_desc_sw128_kmajor(q_addr + k * 32), idesc,
-                         k != 0);
-          // ... + bias(key, query) - lse(query)
-          umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr), umma_desc_sw128_mnmajor(q_addr + kTabHOff), idesc_tab, 1u);
+            for (int k = 0; k < 4; ++k)  // S^T = K Q_blk^T
+              umma_bf16_ss(d, umma_desc_sw128_kmajor(k_addr + k * 32), umma_desc_sw128_kmajor(q_addr + k * 32), idesc,
+                           k != 0);
+            // ... + bias(key, query) - lse(query)
+            umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr), umma_desc_sw128_mnmajor(q_addr + kTabHOff), idesc_tab, 1u);
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr + 32 + k * 32),
-                         umma_desc_sw128_mnmajor(q_addr + kTabWOff + k * 2048), idesc_tab, 1u);
+            for (int k = 0; k < 2; ++k)
+              umma_bf16_ss(d, umma_desc_sw128_kmajor(a_addr + 32 + k * 32),
+                           umma_desc_sw128_mnmajor(q_addr + kTabWOff + k * 2048), idesc_tab, 1u);
+          } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // dP^T = V dO_blk^T
-            umma_bf16_ss(d + kKColdP, umma_desc_sw128_kmajor(v_addr + k * 32),
-                         umma_desc_sw128_kmajor(do_addr + k * 32), idesc, k != 0);
-          // ... - D(query)
-          umma_bf16_ss(d + kKColdP, umma_desc_sw128_kmajor(a_addr + 96), umma_desc_sw128_mnmajor(q_addr + kTabDOff),
-                       idesc_tabd, 1u);
-          umma_commit(&sdp_full[j & 1]);
+            for (int k = 0; k < 4; ++k)  // dP^T = V dO_blk^T
+              umma_bf16_ss(d + kKColdP, umma_desc_sw128_kmajor(v_addr + k * 32),
+                           umma_desc_sw128_kmajor(do_addr + k * 32), idesc, k != 0);
+            // ... - D(query)
+            umma_bf16_ss(d + kKColdP, umma_desc_sw128_kmajor(a_addr + 96), umma_desc_sw128_mnmajor(q_addr + kTabDOff),
+                         idesc_tabd, 1u);
+          }
+          umma_commit(&sdp_full[buf]);
         }
         __syncwarp();
-      };
-      issue_sdp(0);
-      issue_sdp(1);
+        if (warp == 1) ABWD_TRACE(1, 1, j, 2);
+      }
+    } else if (warp == 2) {
+      // ============================ gradient-MMA issuer ============================
+      constexpr uint32_t idesc_grad = umma_idesc_16bit(128, 64, 1, 1, 0, 1);  // K = query = ROW of the dO / Q tile
       for (int j = 0; j < kNumQB; ++j) {
-        const int st = j % kStagesK, buf = j & 1;
-        mbar_wait(&pds_full[buf], (j >> 1) & 1);
+        const int st = j % kStagesK, buf = j % kBufsK;
+        ABWD_TRACE(1, 1, j, 3);
+        mbar_wait(&full[st], (j / kStagesK) & 1);   // complete long ago; observed here for the operand tiles' visibility
+        mbar_wait(&pds_full[buf], (j / kBufsK) & 1);
+        ABWD_TRACE(1, 1, j, 4);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t q_addr = smem_u32(sRing + st * kStageKBytes), do_addr = q_addr + kTileBytes;
@@ -640,28 +688,33 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
                          idesc_grad, (j | k) != 0);
           }
           umma_commit(&empty[st]);
+          umma_commit(&buf_free[buf]);
           if (j == kNumQB - 1) umma_commit(dkv_done);
         }
         __syncwarp();
-        if (j + 2 < kNumQB) issue_sdp(j + 2);
+        ABWD_TRACE(1, 1, j, 5);
       }
     }
   } else {
     // ============================ elementwise warps ============================
     const int quarter = warp & 3;
-    const int g = (warp - 4) >> 2;  // warpgroup: owns the query blocks j with (j & 1) == g (and S / dP buffer g)
+    const int g = (warp - 4) >> 2;  // warpgroup: takes the query blocks j with (j & 1) == g
     const int r = quarter * 32 + lane;
     const int ki_raw = k0 + r;
     const bool valid = ki_raw < kT;
     const int ki = valid ? ki_raw : kT - 1;
     const uint32_t lane_base = tmem_lane_base(tmem_base, quarter);
 
-    // The two warpgroups take alternate query blocks, each thread the whole 64-column row of its key, so that one
-    // warpgroup's hand-off latencies sit under the other's exponentials.
+    // The two warpgroups take alternate query blocks, each thread the whole 64-column row of its key, and three
+    // blocks are in flight (buffer j % 3): while a warpgroup exponentiates block j the tensor core finishes the
+    // gradient MMAs of j - 1 / j - 2 and the score MMAs of j + 1 / j + 2, so neither side waits for a round trip.
     for (int j = g; j < kNumQB; j += 2) {
-      mbar_wait(&sdp_full[g], (j >> 1) & 1);
+      const int buf = j % kBufsK;
+      if (quarter == 0) ABWD_TRACE(1, 2 + g, j, 0);
+      mbar_wait(&sdp_full[buf], (j / kBufsK) & 1);
+      if (quarter == 0) ABWD_TRACE(1, 2 + g, j, 1);
       tc_fence_after();
-      const uint32_t sbase = lane_base + g * kKColBuf;
+      const uint32_t sbase = lane_base + buf * kKColBuf;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float s[32], dp[32];
@@ -679,11 +732,14 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __gri
         }
         tmem_st16u(sbase + h * 32, pp);
         tmem_st16u(sbase + kKColdP + h * 32, pd);
+        if (quarter == 0) ABWD_TRACE(1, 2 + g, j, 2 + h);
       }
       tmem_st_wait();
+      if (quarter == 0) ABWD_TRACE(1, 2 + g, j, 4);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pds_full[g]);
+      if (lane == 0) mbar_arrive(&pds_full[buf]);
+      if (quarter == 0) ABWD_TRACE(1, 2 + g, j, 5);
     }
 
     // ---- epilogue: dv -> columns [2D, 3D), dk * scale -> columns [D, 2D) of the token-major dqkv rows ----
