@@ -66,8 +66,9 @@ constexpr int kQSmemBytes = kQOffBar + 256 + 1024;
 static_assert(kQOffRing % 1024 == 0 && kStageQBytes % 1024 == 0 && kKBytes % 1024 == 0, "swizzle alignment");
 static_assert(kQSmemBytes <= 227 * 1024, "dq kernel shared memory");
 constexpr int kDswStride = 29;  // staging of the dSw partials in the (dead) ring after the loop
-// TMEM columns: S0 [0,112) dP0 [112,224) S1 [224,336) dP1 [336,448) dQ [448,512); G (176) and dG (88) overlay S0/dP0
-constexpr uint32_t kQColBuf = 224, kQColdP = 112, kQColdQ = 448;
+// TMEM columns: S0 [0,112) dP0 [112,224) S1 [224,336) dP1 [336,448) dQ [448,512); G (176) overlays S1/dP1 in the
+// prologue, dG (88) overlays S0 at the end
+constexpr uint32_t kQColBuf = 224, kQColdP = 112, kQColdQ = 448, kQColG = 224;
 
 // ---------------- dkv kernel ----------------
 constexpr int kKTile = 128;
@@ -213,7 +214,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(rel_addr + k * 32),
+          umma_bf16_ss(tmem_base + kQColG, umma_desc_sw128_kmajor(q_addr + k * 32), umma_desc_sw128_kmajor(rel_addr + k * 32),
                        idesc_g, k != 0);
         umma_commit(g_full);
       }
@@ -242,9 +243,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         ABWD_TRACE(0, 1, kb, 2);
       };
 
+      issue_sdp(0);  // buffer 0 does not overlap G: block 0's scores are computed under the bias-table prologue
       mbar_wait(g_free, 0);
       tc_fence_after();
-      issue_sdp(0);
       issue_sdp(1);
       for (int kb = 0; kb < kNumKB; ++kb) {
         const int st = kb % kStagesQ, buf = kb & 1;
@@ -306,7 +307,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
       for (int c = 0; c < 112; c += 16) {
         float v[16];
-        tmem_ld16(lane_base + c, v);
+        tmem_ld16(lane_base + kQColG + c, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -319,7 +320,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
       for (int c = 0; c < 64; c += 16) {
         float v[16];
-        tmem_ld16(lane_base + 112 + c, v);
+        tmem_ld16(lane_base + kQColG + 112 + c, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
