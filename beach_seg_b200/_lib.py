@@ -74,6 +74,8 @@ SIGNATURES = {
     "bseg_ingest_native_u16x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _f3, _f3, _vp, _vp, _vp, _vp]),
     "bseg_ingest_native_f32x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _f3, _f3, _vp, _vp, _vp, _vp]),
     "bseg_scene_stats_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "bseg_scene_stats_rows": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "bseg_scene_stats_finalize": (_i, [_vp, _vp, _vp]),
     "bseg_ingest_f32x4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f3, _f3, _vp, _vp, _ll, _vp, _vp,
                                _vp]),
     "bseg_merge_mosaic": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -944,6 +944,17 @@ int bseg_scene_stats_f32(const float* scene, const uint8_t* nodata, int Hs, int 
   return launch_scene_stats_f32(scene, nodata, Hs, Ws, stats, scratch, static_cast<cudaStream_t>(stream));
 }
 
+int bseg_scene_stats_rows(const void* scene, int is_f32, const uint8_t* nodata, int Hs, int Ws, int row0, int row1,
+                          uint32_t* keys, void* stream) {
+  BSEG_REQUIRE(Hs > 0 && Ws > 0 && row0 >= 0 && row0 <= row1 && row1 <= Hs, "scene_stats_rows: rows [%d,%d) of %d",
+               row0, row1, Hs);
+  return launch_scene_stats_rows(scene, is_f32, nodata, Hs, Ws, row0, row1, keys, static_cast<cudaStream_t>(stream));
+}
+
+int bseg_scene_stats_finalize(const uint32_t* keys, float* stats, void* stream) {
+  return launch_scene_stats_finalize(keys, stats, static_cast<cudaStream_t>(stream));
+}
+
 int bseg_ingest_f32x4(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats,
                       const int32_t* boxes, int n_tiles, int crop, const int32_t* coef, const int32_t* bounds,
                       int ksize, const float* mean, const float* stdv, float* out_nchw, void* out_patch,

@@ -26,11 +26,12 @@ __device__ __forceinline__ unsigned int float_key(float f) {
 __device__ __forceinline__ float key_float(unsigned int k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
+// pixels [first, first + count) of a scene whose bands are npix pixels apart
 template <typename T>
 __global__ void scene_stats_kernel(const T* __restrict__ scene, const uint8_t* __restrict__ nodata, long long npix,
-                                   unsigned int* __restrict__ scratch) {
+                                   long long first, long long count, unsigned int* __restrict__ scratch) {
   float mn = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+  for (long long i = first + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < first + count;
        i += (long long)gridDim.x * blockDim.x) {
     const float b0 = scene[i], b1 = scene[npix + i], b2 = scene[2 * npix + i], b3 = scene[3 * npix + i];
     const float c2 = __fmul_rn(__fadd_rn(b0, b1), 0.5f);
@@ -58,27 +59,44 @@ __global__ void scene_stats_final_kernel(const unsigned int* scratch, float* sta
   for (int i = 0; i < 4; ++i) stats[i] = key_float(scratch[i]);
 }
 namespace {
+// rows [row0, row1) of the scene; stats == nullptr leaves the (order-preserving) keys in scratch for a later merge
 template <typename T>
-int launch_scene_stats_t(const T* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, unsigned int* scratch,
-                         cudaStream_t stream) {
+int launch_scene_stats_t(const T* scene, const uint8_t* nodata, int Hs, int Ws, int row0, int row1, float* stats,
+                         unsigned int* scratch, cudaStream_t stream) {
   const long long npix = static_cast<long long>(Hs) * Ws;
+  const long long first = static_cast<long long>(row0) * Ws, count = static_cast<long long>(row1 - row0) * Ws;
   scene_stats_init_kernel<<<1, 1, 0, stream>>>(scratch);
-  long long blocks = (npix + 2047) / 2048;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  scene_stats_kernel<T><<<static_cast<int>(blocks), 256, 0, stream>>>(scene, nodata, npix, scratch);
-  scene_stats_final_kernel<<<1, 1, 0, stream>>>(scratch, stats);
+  if (count > 0) {
+    long long blocks = (count + 2047) / 2048;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    scene_stats_kernel<T><<<static_cast<int>(blocks), 256, 0, stream>>>(scene, nodata, npix, first, count, scratch);
+  }
+  if (stats != nullptr) scene_stats_final_kernel<<<1, 1, 0, stream>>>(scratch, stats);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 }  // namespace
+int launch_scene_stats_rows(const void* scene, int is_f32, const uint8_t* nodata, int Hs, int Ws, int row0, int row1,
+                            unsigned int* scratch, cudaStream_t stream) {
+  return is_f32 ? launch_scene_stats_t(static_cast<const float*>(scene), nodata, Hs, Ws, row0, row1, nullptr, scratch,
+                                       stream)
+                : launch_scene_stats_t(static_cast<const uint16_t*>(scene), nodata, Hs, Ws, row0, row1, nullptr,
+                                       scratch, stream);
+}
+int launch_scene_stats_finalize(const unsigned int* scratch, float* stats, cudaStream_t stream) {
+  scene_stats_final_kernel<<<1, 1, 0, stream>>>(scratch, stats);
+  BSEG_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
 int launch_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats,
                        unsigned int* scratch, cudaStream_t stream) {
-  return launch_scene_stats_t(scene, nodata, Hs, Ws, stats, scratch, stream);
+  return launch_scene_stats_t(scene, nodata, Hs, Ws, 0, Hs, stats, scratch, stream);
 }
 int launch_scene_stats_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, float* stats,
                            unsigned int* scratch, cudaStream_t stream) {
-  return launch_scene_stats_t(scene, nodata, Hs, Ws, stats, scratch, stream);
+  return launch_scene_stats_t(scene, nodata, Hs, Ws, 0, Hs, stats, scratch, stream);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -103,6 +103,11 @@ int launch_ingest(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, 
                   uint8_t* out_u8, uint8_t* out_nodata, cudaStream_t stream);
 int launch_scene_stats_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, float* stats /*[4]*/,
                            unsigned int* scratch /*[4]*/, cudaStream_t stream);
+// statistics of rows [row0, row1) only, left as order-preserving uint32 keys in scratch[4] (min key, 3 max keys) so that
+// partial results of disjoint row ranges merge exactly with integer min / max; finalize turns merged keys into stats
+int launch_scene_stats_rows(const void* scene, int is_f32, const uint8_t* nodata, int Hs, int Ws, int row0, int row1,
+                            unsigned int* scratch, cudaStream_t stream);
+int launch_scene_stats_finalize(const unsigned int* scratch, float* stats, cudaStream_t stream);
 int launch_ingest_f32(const float* scene, const uint8_t* nodata, int Hs, int Ws, const float* stats, const int* boxes,
                       int n_tiles, int crop, const int* coef, const int* bounds, int ksize, int band, int max_rows,
                       const float* mean, const float* stdv, float* out_nchw, __nv_bfloat16* out_patch,

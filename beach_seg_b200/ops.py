@@ -109,6 +109,35 @@ def scene_stats(scene_u16: torch.Tensor, nodata: torch.Tensor) -> torch.Tensor:
     return stats
 
 
+def scene_stats_sharded(scene_u16: torch.Tensor, nodata: torch.Tensor, row0: int, row1: int, group=None) -> torch.Tensor:
+    """`scene_stats` of a scene whose rows are spread over the ranks of `group`: this rank reduces rows [row0, row1) of
+    its device copy (rows outside are never read, so they need not have been uploaded), the ranks' order-preserving
+    integer keys are merged with one MAX all-reduce (the min key negated), and the merged keys are decoded.  The row
+    ranges of the ranks must cover the scene; the result is bit-identical to `scene_stats` of the whole scene."""
+    _need_cuda(scene_u16, nodata)
+    scene_u16, is_f32 = _scene_kind(scene_u16)
+    _, Hs, Ws = scene_u16.shape
+    nd = nodata.to(torch.uint8).contiguous()
+    dev = scene_u16.device
+    keys = torch.empty(4, dtype=torch.int32, device=dev)
+    stats = torch.empty(4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().bseg_scene_stats_rows(_lib.ptr(scene_u16), int(is_f32), _lib.ptr(nd), Hs, Ws, int(row0),
+                                                    int(row1), _lib.ptr(keys), _lib.stream_ptr()),
+                   "bseg_scene_stats_rows")
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            k = keys.to(torch.int64) & 0xFFFFFFFF            # the uint32 keys
+            k[0] = -k[0]                                       # min -> max
+            dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+            k[0] = -k[0]
+            keys = k.to(torch.int32)                           # keeps the low 32 bits
+        _lib.check(_lib.lib().bseg_scene_stats_finalize(_lib.ptr(keys), _lib.ptr(stats), _lib.stream_ptr()),
+                   "bseg_scene_stats_finalize")
+    return stats
+
+
 def _scene_kind(scene: torch.Tensor):
     """(contiguous scene, is_float32).  uint16 / int16 storage -> the u16 entry points, float32 -> the f32 ones."""
     if scene.dtype == torch.float32:

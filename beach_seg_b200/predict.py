@@ -35,6 +35,35 @@ def shard_tiles(n_tiles: int, rank: int, world_size: int) -> range:
     return range(min(rank * per, n_tiles), min((rank + 1) * per, n_tiles))
 
 
+def shard_rows(boxes, n_rows: int, rank: int, world_size: int) -> tuple[tuple[int, int], tuple[int, int]]:
+    """What rank r has to hold of a scene of `n_rows` rows when the tile list `boxes` ((x0, y0, x1, y1) rows, sorted
+    row-major) is sharded with `shard_tiles`: (rows its tiles read, rows it reduces for the scene-global statistics).
+    The statistics rows are an even split of ALL rows (tiles need not cover the scene); both ranges are half-open and
+    the first may be empty (0, 0) for a rank without tiles."""
+    ids = shard_tiles(len(boxes), rank, world_size)
+    per = (n_rows + world_size - 1) // world_size
+    stat_rows = (min(rank * per, n_rows), min((rank + 1) * per, n_rows))
+    if len(ids) == 0:
+        return (0, 0), stat_rows
+    ys = [(int(boxes[i][1]), int(boxes[i][3])) for i in ids]
+    y0 = max(min(y for y, _ in ys), 0)
+    y1 = min(max(y for _, y in ys), n_rows)
+    return (y0, max(y1, y0)), stat_rows
+
+
+def upload_scene_rows(scene_host: torch.Tensor, nodata_host: torch.Tensor, scene_dev: torch.Tensor,
+                      nodata_dev: torch.Tensor, row_ranges) -> int:
+    """Host -> device copy of the union of the half-open row ranges only (each band's rows are one contiguous chunk of
+    the band-planar [4,Hs,Ws] scene).  Returns the bytes copied.  `scene_host` / `nodata_host` should be pinned."""
+    lo = min(r[0] for r in row_ranges if r[1] > r[0])
+    hi = max(r[1] for r in row_ranges if r[1] > r[0])
+    for band in range(scene_host.shape[0]):   # one contiguous chunk per band: a strided copy_ would be staged on the host
+        scene_dev[band, lo:hi].copy_(scene_host[band, lo:hi], non_blocking=True)
+    nodata_dev[lo:hi].copy_(nodata_host[lo:hi], non_blocking=True)
+    return int(scene_host[:, lo:hi].numel() * scene_host.element_size()
+               + nodata_host[lo:hi].numel() * nodata_host.element_size())
+
+
 class TilePredictor:
     """ingest -> SegGPT forward -> palette decode (+resize to crop size) for batches of tile boxes of one scene."""
 

@@ -281,7 +281,8 @@ def train_leg(args, dev, rank, world, model, scene, nodata, stats, boxes, barrie
 # ------------------------------------------------------------------------------------------------------------
 def scene_leg(args, dev, rank, world, model, barrier, timed):
     from beach_seg_b200 import ops, synth
-    from beach_seg_b200.predict import TilePredictor, create_palette, predict_scene, shard_tiles
+    from beach_seg_b200.predict import (TilePredictor, create_palette, predict_scene, shard_rows, shard_tiles,
+                                        upload_scene_rows)
 
     Hs, Ws, stride = 4000, 8000, 448
     scene_np = synth.scene_u16(Hs, Ws, seed=7)                       # the same scene on every rank
@@ -307,13 +308,17 @@ def scene_leg(args, dev, rank, world, model, barrier, timed):
         out["pred"], _ = predict_scene(predictor, scene, nodata, boxes, prompts, pcls, palette, rank, world,
                                        TILES_PER_STEP, canvas=canvas)
 
+    tile_rows, stat_rows = shard_rows(boxes_np, Hs, rank, world)
+    h2d = {}
+
     def run_e2e():
-        # host scene -> device (every rank needs the scene-global statistics and its own stripe), predict the shard,
-        # reduce, argmax, class map back to the host on rank 0
-        scene_dev.copy_(scene_host, non_blocking=True)
-        nodata_dev.copy_(nodata_host, non_blocking=True)
+        # host scene -> device: only the rows this rank's tiles read plus its share of the rows for the scene-global
+        # statistics (merged over the ranks with one 4-word all-reduce); predict the shard, reduce the canvases,
+        # argmax, class map back to the host on rank 0
+        h2d["bytes"] = upload_scene_rows(scene_host, nodata_host, scene_dev, nodata_dev, (tile_rows, stat_rows))
+        st = ops.scene_stats_sharded(scene_dev, nodata_dev, stat_rows[0], stat_rows[1])
         pred, _ = predict_scene(predictor, scene_dev, nodata_dev, boxes, prompts, pcls, palette, rank, world,
-                                TILES_PER_STEP, canvas=canvas)
+                                TILES_PER_STEP, stats=st, canvas=canvas)
         if pred is not None:
             pred_host.copy_(pred, non_blocking=True)
 
@@ -321,8 +326,17 @@ def scene_leg(args, dev, rank, world, model, barrier, timed):
     for _ in range(2):
         run_device()
     ms, per_rank = timed(run_device, reps, want_ranks=True)
+    scene_dev.fill_(-1)   # rows a rank does not upload must not matter
+    nodata_dev.fill_(1)
     run_e2e()
     ms_e2e, _ = timed(run_e2e, reps, want_ranks=True)
+    torch.cuda.synchronize()
+    e2e_same = None
+    if rank == 0:
+        e2e_same = bool(torch.equal(pred_host, out["pred"].cpu()))
+        if not e2e_same:
+            raise SystemExit("config3: the class map of the host-buffer (row-sharded upload) path differs from the "
+                             "device-resident path")
     # ---- on-hardware equality: the canvas reduced over `world` ranks == the canvas one rank stitches alone ----
     same = None
     run_device()
@@ -352,7 +366,9 @@ def scene_leg(args, dev, rank, world, model, barrier, timed):
             "scene_ms": per_scene, "value": n / (per_scene * 1e-3), "unit": "tiles/s",
             "scene_ms_per_rank_min_max": [min(per_rank) / reps, max(per_rank) / reps],
             "e2e": {"scene_ms": per_scene_e2e, "value": n / (per_scene_e2e * 1e-3), "unit": "tiles/s",
-                    "h2d_bytes_per_scene_per_rank": int(scene_host.numel() * 2 + nodata_host.numel()),
+                    "h2d_bytes_per_scene_per_rank": h2d["bytes"],
+                    "h2d_rows": "rows the rank's tiles read + its 1/N of the rows for the scene statistics",
+                    "class_map_equals_device_resident_path": e2e_same,
                     "d2h_bytes_per_scene": int(pred_host.numel())},
             "canvas_reduce_bytes": int(canvas.numel() * 4) if world > 1 else 0,
             "canvas_equals_single_rank_canvas": same, "vote_totals_equal_tile_coverage": votes_ok, "reps": reps}

@@ -137,6 +137,15 @@ int bseg_backward_to_prompt(bseg_handle* h, const float* d_pred_masks, int batch
 int bseg_scene_stats(const uint16_t* scene, const uint8_t* nodata, int Hs, int Ws, float* stats, uint32_t* scratch,
                      void* stream);
 
+/* The same statistics for a scene whose rows are spread over several GPUs (src/util/geo_util.py:459-464 needs them
+ * scene-global): bseg_scene_stats_rows reduces rows [row0, row1) of the device scene (uint16, or float32 when is_f32)
+ * into keys[4] = order-preserving uint32 encodings of (min, max0, max1, max2); keys of disjoint row ranges merge
+ * exactly with an integer min (keys[0]) / max (keys[1..3]) -- e.g. one all-reduce -- and bseg_scene_stats_finalize
+ * decodes merged keys into stats[4].  Rows outside [row0, row1) are not read. */
+int bseg_scene_stats_rows(const void* scene, int is_f32, const uint8_t* nodata, int Hs, int Ws, int row0, int row1,
+                          uint32_t* keys, void* stream);
+int bseg_scene_stats_finalize(const uint32_t* keys, float* stats, void* stream);
+
 /* tif_image + crop_tif/padded_crop + PIL BICUBIC resize to 448 + /255 + Normalize
  * (src/util/geo_util.py:454-468,297-341; src/data.py:93-124,226-229).
  * boxes: int32 [n_tiles,4] = (xmin,ymin,xmax,ymax); coef/bounds: the PIL resampling table for crop->448

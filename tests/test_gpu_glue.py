@@ -217,6 +217,44 @@ def test_ingest_f32_mosaic_bit_exact(dev, crop, Hs, Ws):
     assert torch.equal(out["image"].cpu(), want_img)
 
 
+@pytest.mark.parametrize("kind", ["u16", "f32"])
+def test_scene_stats_of_row_ranges_merge_exactly(dev, kind):
+    """bseg_scene_stats_rows / _finalize (the scene-global min / max of src/util/geo_util.py:459-464 when the rows of a
+    scene live on several GPUs): keys of disjoint row ranges, merged with integer min / max as the all-reduce of
+    ops.scene_stats_sharded does, decode to exactly the whole-scene statistics; rows outside a range are never read
+    (they hold garbage here); an all-nodata range does not disturb the minimum."""
+    Hs, Ws = 301, 517
+    rng = np.random.default_rng(5)
+    if kind == "u16":
+        scene = synth.scene_u16(Hs, Ws, seed=3)
+        sc_full = torch.from_numpy(scene.view(np.int16)).to(dev)
+    else:
+        scene = (rng.standard_normal((4, Hs, Ws)) * 900 + 300).astype(np.float32)
+        sc_full = torch.from_numpy(scene).to(dev)
+    nodata = rng.random((Hs, Ws)) < 0.2
+    nodata[100:180] = True                                   # the middle range has no valid pixel at all
+    nd = torch.from_numpy(nodata).to(dev)
+    want = ops.scene_stats(sc_full, nd)
+    assert torch.equal(ops.scene_stats_sharded(sc_full, nd, 0, Hs), want)   # world size 1: no merge
+    L = _lib.lib()
+    merged = None
+    for r0, r1 in [(0, 100), (100, 180), (180, Hs), (Hs, Hs)]:
+        part = sc_full.clone()
+        garbage = torch.full_like(part, 30000 if kind == "u16" else 1e30)
+        part[:, :r0], part[:, r1:] = garbage[:, :r0], garbage[:, r1:]
+        keys = torch.empty(4, dtype=torch.int32, device=dev)
+        _lib.check(L.bseg_scene_stats_rows(_lib.ptr(part), int(kind == "f32"), _lib.ptr(nd.to(torch.uint8)), Hs, Ws, r0,
+                                           r1, _lib.ptr(keys), _lib.stream_ptr()))
+        k = keys.to(torch.int64) & 0xFFFFFFFF
+        merged = k if merged is None else torch.cat([torch.minimum(merged[:1], k[:1]), torch.maximum(merged[1:], k[1:])])
+    stats = torch.empty(4, dtype=torch.float32, device=dev)
+    _lib.check(L.bseg_scene_stats_finalize(_lib.ptr(merged.to(torch.int32)), _lib.ptr(stats), _lib.stream_ptr()))
+    assert torch.equal(stats, want)
+    with pytest.raises(_lib.BsegError):
+        _lib.check(L.bseg_scene_stats_rows(_lib.ptr(sc_full), 0, _lib.ptr(nd.to(torch.uint8)), Hs, Ws, 5, Hs + 1,
+                                           _lib.ptr(torch.empty(4, dtype=torch.int32, device=dev)), _lib.stream_ptr()))
+
+
 @pytest.mark.parametrize("H,W", [(4, 256), (97, 131), (1000, 2001)])
 def test_overlay_prediction_bit_exact(dev, H, W):
     """bseg_overlay_prediction vs the Pillow-pinned restatement (src/util/img_util.py:98-116); odd pixel counts

@@ -159,3 +159,26 @@ def test_config_mirrors_reference_defaults():
             assert isinstance(ours[k], Path)
         else:
             assert ours[k] == v, k
+
+
+def test_shard_rows_cover_the_tiles_and_the_scene():
+    """predict.shard_rows: the rows a rank uploads contain every row its tiles read, and the statistics rows of all
+    ranks partition the scene (src/util/geo_util.py:459-464 needs scene-global min / max)."""
+    import numpy as np
+
+    from beach_seg_b200 import synth
+    from beach_seg_b200.predict import shard_rows, shard_tiles
+
+    Hs, Ws = 4000, 8000
+    boxes = synth.sliding_boxes(Hs, Ws, 512, 448)
+    for world in (1, 2, 3, 8, 200):
+        covered = np.zeros(Hs, dtype=np.int32)
+        for r in range(world):
+            (t0, t1), (s0, s1) = shard_rows(boxes, Hs, r, world)
+            covered[s0:s1] += 1
+            for i in shard_tiles(len(boxes), r, world):
+                y0, y1 = max(int(boxes[i][1]), 0), min(int(boxes[i][3]), Hs)
+                assert t0 <= y0 and y1 <= t1
+            if len(shard_tiles(len(boxes), r, world)) == 0:
+                assert (t0, t1) == (0, 0)
+        assert (covered == 1).all()
