@@ -1,21 +1,11 @@
 #!/bin/bash
-# Runs every GPU test file in its own process (a CUDA trap poisons the context) under a timeout, logging to gpurun_out/.
-# usage: tools/gpu_check.sh [test files...]
+# full GPU regression: parity suite, smoke(), default bench
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
-files=("$@")
-if [ ${#files[@]} -eq 0 ]; then
-  files=(tests/test_gpu_gemm.py tests/test_gpu_glue.py tests/test_gpu_attention.py tests/test_gpu_decoder.py tests/test_gpu_model.py)
-fi
-rc_all=0
-for f in "${files[@]}"; do
-  name=$(basename "$f" .py)
-  echo "=== $f" | tee -a gpurun_out/summary.txt
-  timeout 600 python -m pytest "$f" -m gpu -q -s -x --timeout 300 > "gpurun_out/$name.log" 2>&1
-  rc=$?
-  echo "rc=$rc" | tee -a gpurun_out/summary.txt
-  tail -n 25 "gpurun_out/$name.log" | cut -c1-300
-  grep -E "^\[|passed|failed|error" "gpurun_out/$name.log" | cut -c1-300 >> gpurun_out/summary.txt
-  [ $rc -ne 0 ] && rc_all=1
-done
-exit $rc_all
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1
+echo "gpu tests rc=$?"; tail -4 gpurun_out/gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench rc=$?"; tail -2 gpurun_out/bench.err; python tools/show_bench.py gpurun_out/bench.json 2>/dev/null | head -4
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+echo "reference arm rc=$?"; tail -c 600 gpurun_out/bench_ref.json
