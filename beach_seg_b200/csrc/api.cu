@@ -578,7 +578,7 @@ static int forward_entry(bool query_half_only, bseg_handle* h, const float* pixe
       cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
     return eager();  // (per-launch event timing and a caller's own capture both need the plain launch sequence)
   const bseg_handle::GraphKey key{pixel_values, prompt_pixel_values, prompt_masks, workspace, pred_masks, batch,
-                                  embedding_type, ensemble_prompts, query_half_only ? 1 : 0, gemm_set_cta_pairs(-1)};
+                                  embedding_type, ensemble_prompts, query_half_only ? 1 : 0, gemm_set_cta_pairs(-1) | (gemm_set_small_tiles(-1) << 1)};
   for (auto it = h->graphs.begin(); it != h->graphs.end(); ++it) {
     if (!(it->key == key)) continue;
     h->graphs.splice(h->graphs.begin(), h->graphs, it);  // most recently used first
@@ -1085,6 +1085,7 @@ int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uin
 }
 
 int bseg_gemm_set_cta_pairs(int on) { return gemm_set_cta_pairs(on); }
+int bseg_gemm_set_small_tiles(int on) { return gemm_set_small_tiles(on); }
 
 int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int N, int K, const float* bias,
                    void* out, long long ldc, int out_is_bf16, int gelu, void* stream) {

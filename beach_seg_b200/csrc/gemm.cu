@@ -15,6 +15,12 @@ static bool use_cta_pairs() {
   }
   return g_cta_pairs != 0;
 }
+static int g_small_tiles = 1;  // 128 x 128 tiles for launches too small to fill the SMs with 256-wide ones
+int gemm_set_small_tiles(int on) {
+  const int prev = g_small_tiles;
+  if (on >= 0) g_small_tiles = on != 0;
+  return prev;
+}
 int gemm_set_cta_pairs(int on) {
   const int prev = use_cta_pairs() ? 1 : 0;
   if (on >= 0) g_cta_pairs = on != 0;
@@ -135,11 +141,25 @@ int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv
   BSEG_REQUIRE((lda * 2) % 16 == 0, "gemm: lda=%lld violates TMA 16-byte stride alignment", lda);
   BSEG_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                "gemm: operands must be 16-byte aligned");
-  const bool wide = (N % 256 == 0);
+  bool wide = (N % 256 == 0);
   // 256-row tiles pad a ragged row range more than 128-row tiles do (the decoder's 812-row query-half slices: 1024
   // instead of 896 rows computed); pairs only when that costs less than they gain
   const int t128 = (gr.rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, t256 = (gr.rows + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-  const bool pairs = use_cta_pairs() && 2 * t256 * 100 <= t128 * 105;
+  bool pairs = use_cta_pairs() && 2 * t256 * 100 <= t128 * 105;
+  // Small launches (one or a few tiles of a scene: M = 1568 .. 6272 rows) leave most SMs without a tile when the tiles
+  // are 256 wide: 7 x 4 pair tiles for the N = 1024 GEMMs of a single tile.  Estimate each variant as
+  // (waves of tiles over its slots) x (tensor cycles per K step of its tile) and take 128 x 128 one-CTA tiles when
+  // they win clearly; all variants accumulate over K in the same order, so the results are bit-identical.
+  if (wide && g_small_tiles != 0) {
+    const long long sms = num_sms();
+    const long long nb = gr.nbatch;
+    const long long tiles_pair = nb * t256 * (N / 256), tiles_256 = nb * t128 * (N / 256), tiles_128 = nb * t128 * (N / 128);
+    const long long slots_pair = sms / 2 > 0 ? sms / 2 : 1;
+    const long long est_wide = pairs ? ((tiles_pair + slots_pair - 1) / slots_pair) * 128
+                                     : ((tiles_256 + sms - 1) / sms) * 128;
+    const long long est_128 = ((tiles_128 + sms - 1) / sms) * 90;  // measured: a 128 x 128 tile costs ~0.7 of a 256-wide one
+    if (est_128 * 100 <= est_wide * 85) wide = false;
+  }
 #define BSEG_GEMM_CASE(MODE_)                                                               \
   case MODE_:                                                                               \
     if (wide && pairs) return launch_gemm_pair_t<256, MODE_>(A, lda, W, gr, N, K, ep, stream); \

@@ -16,6 +16,8 @@ int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv
 
 // selects the CTA-pair GEMM kernel (cta_group::2) for N % 256 == 0; on < 0 only queries.  Returns the previous setting.
 int gemm_set_cta_pairs(int on);
+// 128 x 128 one-CTA tiles for launches too small to fill the SMs with 256-wide tiles (default on; < 0 queries)
+int gemm_set_small_tiles(int on);
 
 // attention.cu : fused softmax(q k^T * scale + decomposed rel-pos bias) v, one CTA per (seq, head, 128-query tile)
 //   q, k : [nseq, heads, T, 64] bf16     vt : [nseq, heads, 64, T] bf16

@@ -281,6 +281,10 @@ int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uin
  * order, so results are bit-identical.  on < 0 only queries.  Returns the previous setting (initial value: environment
  * BSEG_GEMM_2CTA, else the library default). */
 int bseg_gemm_set_cta_pairs(int on);
+/* Tile shape for small launches (one or a few tiles per call, the reference's own call pattern src/predict.py:234):
+ * 1 (default) lets a GEMM whose 256-wide tiles would leave most SMs idle run on 128 x 128 one-CTA tiles instead;
+ * 0 always uses the 256-wide tiles.  Results are bit-identical.  Returns the previous setting; < 0 only queries. */
+int bseg_gemm_set_small_tiles(int on);
 
 /* D = A[M,K] * W[N,K]^T (+bias); A, W bf16; out fp32 (out_is_bf16 == 0) or bf16; gelu applies to bf16 output. */
 int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int N, int K, const float* bias,

@@ -109,3 +109,30 @@ def test_gemm_cta_pairs_bit_identical(dev, M, N, K):
     assert e <= 2e-3 * s
     assert torch.equal(one, two)
     assert torch.equal(one_bf, two_bf)
+
+
+@pytest.mark.parametrize("M,N,K", [(1568, 1024, 4096), (1568, 1024, 1024), (3136, 3072, 1024), (1568 + 40, 4096, 1024),
+                                   (6272, 1024, 4096)])
+def test_gemm_small_launch_tiles_bit_identical(dev, M, N, K):
+    """bseg_gemm_set_small_tiles: launches of one to four tiles (M = 1568 .. 6272 rows) run on 128 x 128 one-CTA tiles
+    when 256-wide tiles would leave most SMs idle.  Same K order, same fp32 accumulators: the outputs must equal the
+    256-wide variants bit for bit (fp32 and bf16 + GELU epilogues) and match the fp32 matmul."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K + 1)
+    A = torch.randn((M, K), generator=g).to(dev).to(torch.bfloat16)
+    W = torch.randn((N, K), generator=g).to(dev).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g).to(dev)
+    L = _lib.lib()
+    prev = L.bseg_gemm_set_small_tiles(0)
+    try:
+        wide = run_gemm(A, W, bias)
+        wide_bf = run_gemm(A, W, bias, out_bf16=True, gelu=True)
+        assert L.bseg_gemm_set_small_tiles(1) == 0
+        small = run_gemm(A, W, bias)
+        small_bf = run_gemm(A, W, bias, out_bf16=True, gelu=True)
+    finally:
+        L.bseg_gemm_set_small_tiles(prev)
+    want = A.float() @ W.float().t() + bias
+    e, s_ = report(small, want, f"gemm small tiles {M}x{N}x{K}")
+    assert e <= 2e-3 * s_
+    assert torch.equal(wide, small)
+    assert torch.equal(wide_bf, small_bf)
