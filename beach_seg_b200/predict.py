@@ -142,12 +142,15 @@ class HostScenePipeline:
     """Host-buffer front end of `TilePredictor` for callers that hold the scene in (pinned) host memory, like the
     reference's numpy pipeline does: every `step()` copies the uint16 scene host->device, predicts its tiles, votes
     into the device canvas and copies the class maps back to a pinned host buffer.  The copies run on a side stream
-    with two device / host buffers, so step i+1's upload and step i-1's download overlap step i's compute."""
+    with two device / host buffers, so step i+1's upload and step i-1's download overlap step i's compute.  Uploads
+    and downloads have a stream each: on one in-order copy stream the upload of step i+1 would queue behind the
+    download of step i, which waits for step i's compute -- every upload would then be exposed."""
 
     def __init__(self, predictor: TilePredictor, scene_shape, n_tiles: int, crop_size: int):
         dev = predictor.model.device
         self.predictor, self.dev = predictor, dev
-        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.h2d_stream = torch.cuda.Stream(device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)   # downloads (the stream a caller joins at the end)
         self.scene_dev = [torch.empty(scene_shape, dtype=torch.int16, device=dev) for _ in range(2)]
         self.cls_host = [torch.empty((n_tiles, crop_size, crop_size), dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.h2d_done = [torch.cuda.Event() for _ in range(2)]
@@ -161,10 +164,10 @@ class HostScenePipeline:
         b = self.i % 2
         self.i += 1
         cur = torch.cuda.current_stream(self.dev)
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.buf_free[b])      # the compute that last read this device buffer
+        with torch.cuda.stream(self.h2d_stream):
+            self.h2d_stream.wait_event(self.buf_free[b])       # the compute that last read this device buffer
             self.scene_dev[b].copy_(scene_host, non_blocking=True)
-            self.h2d_done[b].record(self.copy_stream)
+            self.h2d_done[b].record(self.h2d_stream)
         cur.wait_event(self.h2d_done[b])
         cls = self.predictor.predict_tiles(self.scene_dev[b], nodata, stats, boxes, prompt_images, prompt_cls, palette)
         ops.vote_accumulate(canvas, cls, boxes, overlapping=False)
@@ -177,6 +180,7 @@ class HostScenePipeline:
         return self.cls_host[b], self.d2h_done[b]
 
     def drain(self):
+        self.h2d_stream.synchronize()
         self.copy_stream.synchronize()
 
 
