@@ -160,13 +160,14 @@ __device__ __forceinline__ void gemm_epi_bf16_chunk(const GemmEpiParams& ep, flo
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + i));
-      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      add_f32x2(v[i], v[i + 1], b.x, b.y);
+      add_f32x2(v[i + 2], v[i + 3], b.z, b.w);
     }
   }
   if constexpr (MODE == EPI_BF16_GELU) {
     if (ep.aux != nullptr) gemm_epi_bf16_store(ep.aux, ep.ldc, v, stg, row0, nvalid, n, lane);  // saved pre-activation
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; i += 2) gelu_erf_x2(v[i], v[i + 1]);
   }
   if constexpr (MODE == EPI_DGELU) {
     if (lane < nvalid) {
@@ -210,7 +211,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, flo
         }
       }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      for (int i = 0; i < 32; i += 2) gelu_erf_x2(v[i], v[i + 1]);
     }
     if constexpr (MODE == EPI_DGELU) {
       const __nv_bfloat16* z = ep.aux + m * ep.ldc + n;
