@@ -78,6 +78,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // Two elements at a time with the polynomial on the packed fp32 pipe (fma.rn.f32x2 rounds each half exactly like the
 // scalar fma, so the results are bit-identical to gelu_erf): 8 issue slots per element instead of 11.5 -- the lin1
 // GEMM's epilogue was 13 % of its time.
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1);
+__device__ __forceinline__ void mul_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1);
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -113,6 +115,31 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // exp(-x^2/2)
   return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
+// two derivatives at a time, polynomial and the exponent's argument on the packed pipe (bit-identical to the scalar form)
+__device__ __forceinline__ void gelu_erf_grad_x2(float x0, float x1, float& g0, float& g1) {
+  const float a0 = fminf(fabsf(x0), 8.0f), a1 = fminf(fabsf(x1), 8.0f);
+  const uint64_t a = pack_f32x2(a0, a1);
+  uint64_t q = fma_f32x2_raw(a, pack_f32x2(2.980947283504065e-05f, 2.980947283504065e-05f),
+                             pack_f32x2(-0.0007226605666801333f, -0.0007226605666801333f));
+  q = fma_f32x2_raw(q, a, pack_f32x2(0.007852795533835888f, 0.007852795533835888f));
+  q = fma_f32x2_raw(q, a, pack_f32x2(-0.052913740277290344f, -0.052913740277290344f));
+  q = fma_f32x2_raw(q, a, pack_f32x2(-0.45927515625953674f, -0.45927515625953674f));
+  q = fma_f32x2_raw(q, a, pack_f32x2(-1.150988221168518f, -1.150988221168518f));
+  q = fma_f32x2_raw(q, a, pack_f32x2(-1.0000197887420654f, -1.0000197887420654f));
+  float q0, q1, h0, h1, e0, e1, s0, s1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(q));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(q1));
+  // exp(-x^2 / 2): the scalar form evaluates (x * x) * c, so do the packed one
+  mul_f32x2(s0, s1, x0, x1, x0, x1);
+  mul_f32x2(s0, s1, s0, s1, -0.72134752044448170368f, -0.72134752044448170368f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+  const float c0 = x0 >= 0.f ? 1.0f - h0 : h0, c1 = x1 >= 0.f ? 1.0f - h1 : h1;
+  g0 = fmaf(x0 * 0.39894228040143267794f, e0, c0);
+  g1 = fmaf(x1 * 0.39894228040143267794f, e1, c1);
 }
 
 // ----------------------------------------------------------------------------------------------

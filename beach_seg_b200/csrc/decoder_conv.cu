@@ -208,20 +208,25 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
               make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]), pack_bf16x2(v[i + 4], v[i + 5]),
                          pack_bf16x2(v[i + 6], v[i + 7]));
       } else {
-        // two-pass statistics of this half, then Chan's combination with the other half (exact, no cancellation)
-        float s = 0.f;
+        // two-pass statistics of this half, then Chan's combination with the other half (exact, no cancellation).
+        // All per-channel arithmetic runs on pairs of channels (packed fp32 pipe), parameters come as float2 pairs.
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] += sPar[c0 + i];
-          s += v[i];
+        for (int i = 0; i < 32; i += 2) {
+          const float2 cb = *reinterpret_cast<const float2*>(sPar + c0 + i);
+          add_f32x2(v[i], v[i + 1], cb.x, cb.y);
+          add_f32x2(s0, s1, v[i], v[i + 1]);
         }
-        const float mean_h = s * (1.0f / 32.0f);
-        float m2_h = 0.f;
+        const float mean_h = (s0 + s1) * (1.0f / 32.0f);
+        float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float d = v[i] - mean_h;
-          m2_h = fmaf(d, d, m2_h);
+        for (int i = 0; i < 32; i += 2) {
+          float d0 = v[i], d1 = v[i + 1];
+          add_f32x2(d0, d1, -mean_h, -mean_h);
+          uint64_t q = fma_f32x2_raw(pack_f32x2(d0, d1), pack_f32x2(d0, d1), pack_f32x2(q0, q1));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(q));
         }
+        const float m2_h = q0 + q1;
         *reinterpret_cast<float2*>(xchA + (half * 128 + r) * 2) = make_float2(mean_h, m2_h);
         named_bar_sync(1, 256);
         const float2 oth = *reinterpret_cast<const float2*>(xchA + ((half ^ 1) * 128 + r) * 2);
@@ -230,14 +235,31 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const float var = (m2_h + oth.y + 16.0f * dm * dm) * (1.0f / 64.0f);
         const float rstd = rsqrtf(var + eps);
         if constexpr (MODE == kModeHead) {
-          float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+          uint64_t p0 = 0, p1 = 0, p2 = 0;  // (even, odd) channel partial sums of the three head outputs
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float g = gelu_erf((v[i] - mean) * rstd * sPar[64 + c0 + i] + sPar[128 + c0 + i]);
-            o0 = fmaf(g, sPar[192 + c0 + i], o0);
-            o1 = fmaf(g, sPar[256 + c0 + i], o1);
-            o2 = fmaf(g, sPar[320 + c0 + i], o2);
+          for (int i = 0; i < 32; i += 2) {
+            const float2 ga = *reinterpret_cast<const float2*>(sPar + 64 + c0 + i);
+            const float2 be = *reinterpret_cast<const float2*>(sPar + 128 + c0 + i);
+            float t0 = v[i], t1 = v[i + 1];
+            add_f32x2(t0, t1, -mean, -mean);
+            mul_f32x2(t0, t1, t0, t1, rstd, rstd);
+            uint64_t y = fma_f32x2_raw(pack_f32x2(t0, t1), pack_f32x2(ga.x, ga.y), pack_f32x2(be.x, be.y));
+            float g0, g1;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(g0), "=f"(g1) : "l"(y));
+            gelu_erf_x2(g0, g1);
+            const uint64_t g = pack_f32x2(g0, g1);
+            const float2 w0 = *reinterpret_cast<const float2*>(sPar + 192 + c0 + i);
+            const float2 w1 = *reinterpret_cast<const float2*>(sPar + 256 + c0 + i);
+            const float2 w2 = *reinterpret_cast<const float2*>(sPar + 320 + c0 + i);
+            p0 = fma_f32x2_raw(g, pack_f32x2(w0.x, w0.y), p0);
+            p1 = fma_f32x2_raw(g, pack_f32x2(w1.x, w1.y), p1);
+            p2 = fma_f32x2_raw(g, pack_f32x2(w2.x, w2.y), p2);
           }
+          float o0a, o0b, o1a, o1b, o2a, o2b;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(o0a), "=f"(o0b) : "l"(p0));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(o1a), "=f"(o1b) : "l"(p1));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(o2a), "=f"(o2b) : "l"(p2));
+          const float o0 = o0a + o0b, o1 = o1a + o1b, o2 = o2a + o2b;
           if (half == 1) *reinterpret_cast<float4*>(xchB + (128 + r) * 4) = make_float4(o0, o1, o2, 0.f);
           named_bar_sync(2, 256);
           if (half == 0) {

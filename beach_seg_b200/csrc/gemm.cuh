@@ -178,8 +178,9 @@ __device__ __forceinline__ void gemm_epi_bf16_chunk(const GemmEpiParams& ep, flo
         const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          v[i + 2 * j] *= gelu_erf_grad(__uint_as_float(w[j] << 16));
-          v[i + 2 * j + 1] *= gelu_erf_grad(__uint_as_float(w[j] & 0xffff0000u));
+          float g0, g1;
+          gelu_erf_grad_x2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u), g0, g1);
+          mul_f32x2(v[i + 2 * j], v[i + 2 * j + 1], v[i + 2 * j], v[i + 2 * j + 1], g0, g1);
         }
       }
     }
@@ -221,8 +222,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpiParams& ep, flo
         const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          v[i + 2 * j] *= gelu_erf_grad(__uint_as_float(w[j] << 16));
-          v[i + 2 * j + 1] *= gelu_erf_grad(__uint_as_float(w[j] & 0xffff0000u));
+          float g0, g1;
+          gelu_erf_grad_x2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u), g0, g1);
+          mul_f32x2(v[i + 2 * j], v[i + 2 * j + 1], v[i + 2 * j], v[i + 2 * j + 1], g0, g1);
         }
       }
     }
