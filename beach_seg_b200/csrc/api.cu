@@ -312,8 +312,14 @@ int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream_) {
 // ---- workspace layout (all offsets 1024-aligned) ----
 namespace {
 struct WsLayout {
-  size_t h, xn, att, q, k, vt, mlp, inter, dec, total;
+  size_t h, xn, att, q, k, vt, mlp, inter, dec, ln_stats, ln_ready, total;
 };
+// Exchange buffers of the residual+LayerNorm GEMM epilogue (EPI_RESID_LN): eight (mean, M2) partials per row, and one
+// arrival counter per 32 rows for each of the (at most) 2 * kMaxLayers fused launches of a forward pass.
+constexpr int kMaxLayers = 64;
+size_t ln_stats_bytes(size_t rows) { return rows * 8 * sizeof(float2); }
+size_t ln_ready_stride(size_t rows) { return (rows + 31) / 32; }  // counters per launch
+size_t ln_ready_bytes(size_t rows) { return 2 * kMaxLayers * ln_ready_stride(rows) * sizeof(unsigned int); }
 WsLayout ws_layout(int B, int T = kT) {
   WsLayout L;
   const size_t rows2 = 2ull * B * T, rows1 = 1ull * B * T;
@@ -332,6 +338,8 @@ WsLayout ws_layout(int B, int T = kT) {
   L.mlp = carve(rows2 * kMlp * 2);  // also: patch-embedding operand [rows2,768] bf16, ensemble scratch fp32 [rows2,1024]
   L.inter = carve(rows1 * 4096 * 2);
   L.dec = carve(rows1 * kDecN * 2);
+  L.ln_stats = carve(ln_stats_bytes(rows2));
+  L.ln_ready = carve(ln_ready_bytes(rows2));
   L.total = off;
   return L;
 }
@@ -345,7 +353,7 @@ struct TrainLayer {
 };
 struct TrainLayout {
   // forward transients
-  size_t xn, mlp, inter;
+  size_t xn, mlp, inter, ln_stats, ln_ready;
   // saved
   size_t h_emb, dec;
   std::vector<TrainLayer> layers;
@@ -365,6 +373,8 @@ TrainLayout train_layout(const bseg_handle* h, int B) {
   L.xn = carve(rows2 * kD * 2);
   L.mlp = carve(rows2 * kMlp * 2);
   L.inter = carve(rows1 * 4096 * 2);
+  L.ln_stats = carve(ln_stats_bytes(rows2));
+  L.ln_ready = carve(ln_ready_bytes(rows2));
   L.h_emb = carve(rows2 * kD * 4);
   L.dec = carve(rows1 * kDecN * 2);
   L.layers.resize(h->num_layers);
@@ -402,6 +412,8 @@ TrainLayout train_layout(const bseg_handle* h, int B) {
 struct FwdBufs {
   float* h_emb;                    // embeddings output == input of layer 0
   __nv_bfloat16 *xn, *mlp, *inter, *dec;
+  float2* ln_stats = nullptr;          // EPI_RESID_LN exchange (see ws_layout)
+  unsigned int* ln_ready = nullptr;
   struct PerLayer {
     float *h_mid, *h_out;
     __nv_bfloat16 *q, *k, *vt, *att, *z;
@@ -430,14 +442,34 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
   }
 
   // ---- encoder (modeling_seggpt.py:453-501) ----
+  // Fused residual + LayerNorm (gemm_set_fused_ln, default on): the proj GEMM also emits norm2 of its rows and the lin2
+  // GEMM emits the NEXT layer's norm1 (when the stream is not merged / ensembled in between), so 46 of the 52
+  // layernorm1024 launches of a 24-layer forward and their fp32 re-read of the residual stream disappear.
+  const bool fused_ln = gemm_set_fused_ln(-1) != 0 && fb.ln_stats != nullptr && h->num_layers <= kMaxLayers;
+  const size_t ready_stride = ln_ready_stride(2ull * B * kT);
+  if (fused_ln) {
+    cudaError_t ce = cudaMemsetAsync(fb.ln_ready, 0, ln_ready_bytes(2ull * B * kT), stream);
+    if (ce != cudaSuccess) {
+      set_error("bseg_forward: memset failed: %s", cudaGetErrorString(ce));
+      return -static_cast<int>(ce);
+    }
+  }
+  auto fuse_ln = [&](GemmEpiParams& ep, const float* gamma, const float* beta, int launch_idx) {
+    ep.ln_gamma = gamma; ep.ln_beta = beta; ep.ln_out = fb.xn; ep.ld_ln = kD; ep.ln_eps = h->eps;
+    ep.ln_stats = fb.ln_stats;
+    ep.ln_ready = fb.ln_ready + static_cast<size_t>(launch_idx) * ready_stride;
+  };
   float* h_in = fb.h_emb;
+  bool ln1_done = false;  // norm1 of this layer was written by the previous layer's lin2 epilogue
   for (int i = 0; i < h->num_layers; ++i) {
     const LayerPack& lp = h->layers[i];
     const FwdBufs::PerLayer& pl = fb.layers[i];
     const int nstreams = (i <= h->merge_index) ? 2 : 1;
     const int nseq = nstreams * B;
     const long long M = static_cast<long long>(nseq) * kT;
-    if ((rc = launch_layernorm1024(h_in, kD, lp.ln1_w, lp.ln1_b, fb.xn, kD, M, h->eps, stream))) return rc;
+    if (!ln1_done)
+      if ((rc = launch_layernorm1024(h_in, kD, lp.ln1_w, lp.ln1_b, fb.xn, kD, M, h->eps, stream))) return rc;
+    ln1_done = false;
     {
       GemmEpiParams ep;
       ep.bias = lp.qkv_b;
@@ -450,10 +482,14 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
       return rc;
     bool ens = false;
     if (P > 0) ens = (i == h->merge_index) ? true : (P >= 2);
+    bool ln2_done = false;
     if (!ens) {
       GemmEpiParams ep;
       ep.out = pl.h_mid; ep.ldc = kD; ep.bias = lp.proj_b; ep.resid = h_in; ep.ldr = kD;
-      if ((rc = launch_gemm(EPI_RESID_F32, pl.att, kD, lp.proj_w, M, kD, kD, ep, stream))) return rc;
+      if (fused_ln) fuse_ln(ep, lp.ln2_w, lp.ln2_b, 2 * i);
+      if ((rc = launch_gemm(fused_ln ? EPI_RESID_LN : EPI_RESID_F32, pl.att, kD, lp.proj_w, M, kD, kD, ep, stream)))
+        return rc;
+      ln2_done = fused_ln;
     } else {
       BSEG_REQUIRE(pl.h_mid == h_in, "feature ensemble is an inference-only path");
       float* tmp = reinterpret_cast<float*>(fb.mlp);
@@ -463,7 +499,8 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
       if ((rc = launch_ensemble_residual(h_in, tmp, nstreams, B / P, P, i == h->merge_index ? 1 : 0, kT, kD, stream)))
         return rc;
     }
-    if ((rc = launch_layernorm1024(pl.h_mid, kD, lp.ln2_w, lp.ln2_b, fb.xn, kD, M, h->eps, stream))) return rc;
+    if (!ln2_done)
+      if ((rc = launch_layernorm1024(pl.h_mid, kD, lp.ln2_w, lp.ln2_b, fb.xn, kD, M, h->eps, stream))) return rc;
     {
       GemmEpiParams ep;
       ep.out = fb.mlp; ep.ldc = kMlp; ep.bias = lp.lin1_b; ep.aux = pl.z;
@@ -472,7 +509,12 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
     {
       GemmEpiParams ep;
       ep.out = pl.h_out; ep.ldc = kD; ep.bias = lp.lin2_b; ep.resid = pl.h_mid; ep.ldr = kD;
-      if ((rc = launch_gemm(EPI_RESID_F32, fb.mlp, kMlp, lp.lin2_w, M, kD, kMlp, ep, stream))) return rc;
+      // the next layer's norm1 reads exactly these rows unless the two streams are merged first
+      const bool fuse_next = fused_ln && i + 1 < h->num_layers && i != h->merge_index;
+      if (fuse_next) fuse_ln(ep, h->layers[i + 1].ln1_w, h->layers[i + 1].ln1_b, 2 * i + 1);
+      if ((rc = launch_gemm(fuse_next ? EPI_RESID_LN : EPI_RESID_F32, fb.mlp, kMlp, lp.lin2_w, M, kD, kMlp, ep, stream)))
+        return rc;
+      ln1_done = fuse_next;
     }
     if (i == h->merge_index)
       if ((rc = launch_merge_streams(pl.h_out, static_cast<long long>(B) * kT * kD, stream))) return rc;
@@ -526,6 +568,8 @@ FwdBufs train_bufs(bseg_handle* h, const TrainLayout& L, uint8_t* ws) {
   auto fp = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
   fb.h_emb = fp(L.h_emb);
   fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
+  fb.ln_stats = reinterpret_cast<float2*>(ws + L.ln_stats);
+  fb.ln_ready = reinterpret_cast<unsigned int*>(ws + L.ln_ready);
   fb.layers.resize(h->num_layers);
   for (int i = 0; i < h->num_layers; ++i) {
     const TrainLayer& t = L.layers[i];
@@ -554,6 +598,8 @@ static int forward_eager(bool query_half_only, bseg_handle* h, const float* pixe
   FwdBufs fb;
   fb.h_emb = reinterpret_cast<float*>(ws + L.h);
   fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
+  fb.ln_stats = reinterpret_cast<float2*>(ws + L.ln_stats);
+  fb.ln_ready = reinterpret_cast<unsigned int*>(ws + L.ln_ready);
   fb.layers.assign(h->num_layers, {fb.h_emb, fb.h_emb, bf(L.q), bf(L.k), bf(L.vt), bf(L.att), nullptr, nullptr});
   return forward_impl(h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, ensemble_prompts, fb,
                       pred_masks, stream, query_half_only);
@@ -578,7 +624,7 @@ static int forward_entry(bool query_half_only, bseg_handle* h, const float* pixe
       cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
     return eager();  // (per-launch event timing and a caller's own capture both need the plain launch sequence)
   const bseg_handle::GraphKey key{pixel_values, prompt_pixel_values, prompt_masks, workspace, pred_masks, batch,
-                                  embedding_type, ensemble_prompts, query_half_only ? 1 : 0, gemm_set_cta_pairs(-1) | (gemm_set_small_tiles(-1) << 1)};
+                                  embedding_type, ensemble_prompts, query_half_only ? 1 : 0, gemm_set_cta_pairs(-1) | (gemm_set_small_tiles(-1) << 1) | (gemm_set_fused_ln(-1) << 2)};
   for (auto it = h->graphs.begin(); it != h->graphs.end(); ++it) {
     if (!(it->key == key)) continue;
     h->graphs.splice(h->graphs.begin(), h->graphs, it);  // most recently used first
@@ -1086,6 +1132,29 @@ int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uin
 
 int bseg_gemm_set_cta_pairs(int on) { return gemm_set_cta_pairs(on); }
 int bseg_gemm_set_small_tiles(int on) { return gemm_set_small_tiles(on); }
+int bseg_gemm_set_fused_ln(int on) { return gemm_set_fused_ln(on); }
+
+size_t bseg_gemm_resid_ln_scratch_bytes(long long M) {
+  if (M <= 0) return 0;
+  return align_up(ln_stats_bytes(static_cast<size_t>(M)), 1024) + ln_ready_stride(static_cast<size_t>(M)) * sizeof(unsigned int);
+}
+int bseg_gemm_bf16_resid_ln(const void* A, long long lda, const void* W, long long M, int K, const float* bias,
+                            float* hres, const float* gamma, const float* beta, void* ln_out, float eps, void* scratch,
+                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BSEG_REQUIRE(A && W && hres && gamma && beta && ln_out && scratch && M > 0, "bseg_gemm_bf16_resid_ln: bad argument");
+  uint8_t* sc = static_cast<uint8_t*>(scratch);
+  const size_t off = align_up(ln_stats_bytes(static_cast<size_t>(M)), 1024);
+  BSEG_CHECK_CUDA(cudaMemsetAsync(sc + off, 0, ln_ready_stride(static_cast<size_t>(M)) * sizeof(unsigned int), stream));
+  GemmEpiParams ep;
+  ep.out = hres; ep.ldc = 1024; ep.bias = bias; ep.resid = hres; ep.ldr = 1024;
+  ep.ln_gamma = gamma; ep.ln_beta = beta; ep.ln_out = static_cast<__nv_bfloat16*>(ln_out); ep.ld_ln = 1024;
+  ep.ln_eps = eps;
+  ep.ln_stats = reinterpret_cast<float2*>(sc);
+  ep.ln_ready = reinterpret_cast<unsigned int*>(sc + off);
+  return launch_gemm(EPI_RESID_LN, static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), M,
+                     1024, K, ep, stream);
+}
 
 int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int N, int K, const float* bias,
                    void* out, long long ldc, int out_is_bf16, int gelu, void* stream) {

@@ -21,6 +21,12 @@ int gemm_set_small_tiles(int on) {
   if (on >= 0) g_small_tiles = on != 0;
   return prev;
 }
+static int g_fused_ln = 1;  // residual GEMMs also emit the LayerNorm that follows (EPI_RESID_LN)
+int gemm_set_fused_ln(int on) {
+  const int prev = g_fused_ln;
+  if (on >= 0) g_fused_ln = on != 0;
+  return prev;
+}
 int gemm_set_cta_pairs(int on) {
   const int prev = use_cta_pairs() ? 1 : 0;
   if (on >= 0) g_cta_pairs = on != 0;
@@ -78,7 +84,7 @@ static int launch_gemm_pair_t(const __nv_bfloat16* A, long long lda, const __nv_
   cfg.gridDim = dim3(static_cast<unsigned>(2 * (tiles < pairs ? tiles : pairs)));
   ProfScope prof(CAT_GEMM, 2.0 * static_cast<double>(M) * N * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream,
-                 MODE + (K > 2048 ? 8 : 0));
+                 MODE == EPI_RESID_LN ? (K > 2048 ? 13 : 12) : MODE + (K > 2048 ? 8 : 0));
   BSEG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, gr, N, K, ep));
   count_launch();
   return 0;
@@ -111,7 +117,7 @@ static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloa
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   ProfScope prof(CAT_GEMM, 2.0 * static_cast<double>(M) * N * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream,
-                 MODE + (K > 2048 ? 8 : 0));
+                 MODE == EPI_RESID_LN ? (K > 2048 ? 13 : 12) : MODE + (K > 2048 ? 8 : 0));
   kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, gr, N, K, ep);
   BSEG_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -159,6 +165,16 @@ int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv
                                      : ((tiles_256 + sms - 1) / sms) * 128;
     const long long est_128 = ((tiles_128 + sms - 1) / sms) * 90;  // measured: a 128 x 128 tile costs ~0.7 of a 256-wide one
     if (est_128 * 100 <= est_wide * 85) wide = false;
+  }
+  if (mode == EPI_RESID_LN) {
+    // residual + LayerNorm: the four N tiles of a row block exchange row statistics, eight 128-column slices per row
+    BSEG_REQUIRE(N == 1024 && gr.nbatch == 1 && gr.row_begin == 0,
+                 "gemm: the residual+LayerNorm epilogue needs N == 1024 and one contiguous row range");
+    BSEG_REQUIRE(ep.ln_gamma && ep.ln_beta && ep.ln_out && ep.ln_stats && ep.ln_ready && ep.resid && ep.out,
+                 "gemm: residual+LayerNorm epilogue with a null pointer");
+    BSEG_REQUIRE(ep.ld_ln % 4 == 0 && ep.ldc % 4 == 0 && ep.ldr % 4 == 0, "gemm: residual+LayerNorm leading dims");
+    if (pairs) return launch_gemm_pair_t<256, EPI_RESID_LN>(A, lda, W, gr, N, K, ep, stream);
+    return launch_gemm_t<256, EPI_RESID_LN>(A, lda, W, gr, N, K, ep, stream);
   }
 #define BSEG_GEMM_CASE(MODE_)                                                               \
   case MODE_:                                                                               \

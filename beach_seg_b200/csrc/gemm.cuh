@@ -18,6 +18,10 @@ enum GemmEpiMode : int {
   EPI_EMBED = 5,      // out_f32[m, n]   = acc + tab[(m / rows_per_stream) * T + m % T, n]
   EPI_PIXSHUF = 6,    // decoder pixel shuffle: nhwc[b, ph*16+py, pw*16+px, c] = acc + bias[n], n = (py*16+px)*64+c
   EPI_DGELU = 7,      // backward of lin1's GELU: out_bf16[m, n] = acc * gelu'(aux_bf16[m, n])   (aux = saved pre-activation)
+  // EPI_RESID_F32 + the LayerNorm that reads the updated residual stream next (N == 1024 == the whole row, BLOCK_N = 256):
+  //   out_f32[m, :] = resid[m, :] + acc + bias ;  ln_out_bf16[m, :] = LN(out_f32[m, :]) * gamma + beta
+  // The fp32 row is normalised while it is still in L2 instead of being read back from HBM by layernorm1024_kernel.
+  EPI_RESID_LN = 8,
 };
 
 struct GemmEpiParams {
@@ -40,6 +44,14 @@ struct GemmEpiParams {
   __nv_bfloat16* vt = nullptr;
   int heads = 16;
   float q_scale = 1.0f;  // q is stored as bf16((acc + bias) * q_scale): the attention kernels take q * scale * log2(e)
+  // EPI_RESID_LN: LayerNorm parameters / output, and the cross-CTA exchange of the row statistics
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  __nv_bfloat16* ln_out = nullptr;
+  long long ld_ln = 0;
+  float ln_eps = 1e-6f;
+  float2* ln_stats = nullptr;     // [M][8] (mean, M2) of the eight 128-column slices of a row
+  unsigned int* ln_ready = nullptr;  // [ceil(M / 32)] arrival counters, ZERO before the launch (8 arrivals per 32 rows)
 };
 
 // Which rows of A (== rows of the output) a launch covers: `nbatch` entries of `rows_per_batch` rows each, of which
@@ -125,6 +137,149 @@ __device__ __forceinline__ void gemm_epi_f32_chunk(const GemmEpiParams& ep, cons
     if (rr < nvalid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + m * ep.ldc + n + 4 * (lane & 7)) = o;
   }
   __syncwarp();
+}
+
+// ---- EPI_RESID_LN: residual epilogue + LayerNorm of the finished row ---------------------------------------------
+// A 256-column tile sees a quarter of a row, so the row statistics are exchanged between the four CTAs (pairs) that own
+// the N tiles of the same rows: every epilogue warp publishes (mean, M2) of its 32 rows x 128 columns, bumps the
+// arrival counter of its 32-row group (release), hands its TMEM buffer back to the MMA warp, waits for the eight
+// arrivals of the group (acquire; the other seven warps belong to CTAs that are resident by construction: the kernel is
+// persistent with at most one wave of CTAs), merges the eight partials and normalises ITS OWN 32 x 128 slice, which it
+// wrote microseconds ago and now reads back from L2 with the same thread <-> element mapping.
+// Statistics are carried as (mean, M2 = sum of squared deviations) and merged pairwise between equal counts (Chan et
+// al.): no E[x^2] - mean^2 cancellation, and the merge is bitwise symmetric, so every warp that merges the same eight
+// partials in the same tree gets the same bits (one row is normalised consistently by four different CTAs).
+__device__ __forceinline__ void ln_merge_equal(float& mean, float& m2, float mean_b, float m2_b, float half_count) {
+  const float d = mean_b - mean;
+  m2 = __fmaf_rn(d * d, half_count, m2 + m2_b);
+  mean = 0.5f * (mean + mean_b);
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u32(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// lane 0 of the warp spins (with the same kind of watchdog as mbar_wait), the warp re-converges behind it
+__device__ __forceinline__ void ln_wait_ready(const unsigned int* ctr, unsigned int target, int lane) {
+  if (lane == 0) {
+    long long t0 = 0;
+    uint32_t spins = 0;
+    while (ld_acquire_gpu_u32(ctr) < target) {
+      __nanosleep(40);
+      if ((++spins & 63u) == 0u) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000LL) {
+          printf("bseg: LayerNorm statistics watchdog block=%d thread=%d counter=%u target=%u\n", blockIdx.x,
+                 threadIdx.x, ld_acquire_gpu_u32(ctr), target);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncwarp();
+  __threadfence();
+}
+// pass 1 for one 32 x 32 chunk: gemm_epi_f32_chunk<EPI_RESID_F32> + running statistics of rows (i*4 + lane/8) over
+// this thread's four columns per chunk.  `ci` = number of chunks already merged (the running side holds 4*ci values).
+__device__ __forceinline__ void gemm_epi_resid_ln_chunk(const GemmEpiParams& ep, const float (&v)[32], const EpiRows& pr,
+                                                        float* stg, long long row0, int nvalid, int n, int lane, int ci,
+                                                        float (&rmean)[8], float (&rm2)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4 * (lane & 7)));
+  // merging 4 new values into 4*ci: mean += delta / (ci + 1), M2 += M2_new + delta^2 * 4 ci / (ci + 1)
+  const float w_mean = ci == 0 ? 1.0f : (ci == 1 ? 0.5f : (ci == 2 ? (1.0f / 3.0f) : 0.25f));
+  const float w_m2 = ci == 0 ? 0.0f : (ci == 1 ? 2.0f : (ci == 2 ? (8.0f / 3.0f) : 3.0f));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    const long long m = row0 + rr;
+    float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+    o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+    o.x += pr.r[i].x; o.y += pr.r[i].y; o.z += pr.r[i].z; o.w += pr.r[i].w;
+    if (rr < nvalid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + m * ep.ldc + n + 4 * (lane & 7)) = o;
+    const float m4 = 0.25f * ((o.x + o.y) + (o.z + o.w));
+    const float da = o.x - m4, db = o.y - m4, dc = o.z - m4, dd = o.w - m4;
+    const float q4 = (da * da + db * db) + (dc * dc + dd * dd);
+    const float delta = m4 - rmean[i];
+    rmean[i] = __fmaf_rn(delta, w_mean, rmean[i]);
+    rm2[i] += __fmaf_rn(delta * delta, w_m2, q4);
+  }
+  __syncwarp();
+}
+// Everything after the last chunk of pass 1 (the caller has already released its TMEM buffer): publish, wait, merge,
+// normalise.  `slot` = 2 * (N tile) + (column half of the warp); the warp covers columns [ncol0, ncol0 + 128).
+__device__ __forceinline__ void gemm_epi_resid_ln_finish(const GemmEpiParams& ep, float (&rmean)[8], float (&rm2)[8],
+                                                         long long row0, int nvalid, int ncol0, int slot, int lane) {
+  // (a) the eight lanes that share a row: 16 values each -> 128
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const float mb = __shfl_xor_sync(0xffffffffu, rmean[i], o);
+      const float qb = __shfl_xor_sync(0xffffffffu, rm2[i], o);
+      ln_merge_equal(rmean[i], rm2[i], mb, qb, 8.0f * o);
+    }
+  }
+  // (b) publish (every lane of a row's group holds the same bits; the first one stores them)
+  if ((lane & 7) == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + (lane >> 3);
+      if (rr < nvalid) ep.ln_stats[(row0 + rr) * 8 + slot] = make_float2(rmean[i], rm2[i]);
+    }
+  }
+  __threadfence();
+  __syncwarp();
+  unsigned int* ctr = ep.ln_ready + (row0 >> 5);
+  if (lane == 0) red_release_gpu_add_u32(ctr, 1u);
+  // (c) wait for the eight slices of these 32 rows, merge them: 128 -> 1024
+  ln_wait_ready(ctr, 8u, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    float2 p = make_float2(0.f, 0.f);
+    if (rr < nvalid) p = __ldcg(ep.ln_stats + (row0 + rr) * 8 + (lane & 7));
+    rmean[i] = p.x;
+    rm2[i] = p.y;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const float mb = __shfl_xor_sync(0xffffffffu, rmean[i], o);
+      const float qb = __shfl_xor_sync(0xffffffffu, rm2[i], o);
+      ln_merge_equal(rmean[i], rm2[i], mb, qb, 64.0f * o);
+    }
+    rm2[i] = rsqrtf(rm2[i] * (1.0f / 1024.0f) + ep.ln_eps);  // from here on: 1 / std
+  }
+  // (d) pass 2: own 32 x 128 slice back from L2, normalise, bf16 (8 lanes x 8 B = 64 contiguous bytes per row)
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    const int n = ncol0 + c + 4 * (lane & 7);
+    float4 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + (lane >> 3);
+      x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rr < nvalid) x[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.out) + (row0 + rr) * ep.ldc + n);
+    }
+    const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + (lane >> 3);
+      const float mean = rmean[i], rstd = rm2[i];
+      const uint2 o = make_uint2(pack_bf16x2((x[i].x - mean) * rstd * g.x + b.x, (x[i].y - mean) * rstd * g.y + b.y),
+                                 pack_bf16x2((x[i].z - mean) * rstd * g.z + b.z, (x[i].w - mean) * rstd * g.w + b.w));
+      if (rr < nvalid) *reinterpret_cast<uint2*>(ep.ln_out + (row0 + rr) * ep.ld_ln + n) = o;
+    }
+  }
 }
 
 // ---- bf16-output epilogues with a row-major destination (bias / GELU / GELU') ---------------------------------------
@@ -336,6 +491,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
+  // EPI_RESID_LN: the epilogue warps carry the residual prefetch (64 registers) and the row statistics, so the control
+  // warpgroup gives its registers away (128 x 56 + 256 x 224 = 384 x 168, the CTA's pool).  ptxas sizes each side of
+  // this branch by the setmaxnreg it starts with, hence the nesting.
+  if (warp < 4) {
+  if constexpr (MODE == EPI_RESID_LN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
     int stage = 0;
@@ -401,8 +561,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
+    if constexpr (MODE == EPI_RESID_LN) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     constexpr int kColsPerWarp = BLOCK_N / (GEMM_EPI_WARPS / 4);
     const int col0 = ((warp - 4) >> 2) * kColsPerWarp;
@@ -431,6 +593,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           gemm_epi_f32_chunk<MODE>(ep, v, pr, stg, row0, nvalid, n0 + c, lane);
           pr = pn;
         }
+      } else if constexpr (MODE == EPI_RESID_LN) {
+        static_assert(MODE != EPI_RESID_LN || BLOCK_N == 256, "the LayerNorm exchange assumes eight 128-column slices per row");
+        float* stg = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 1024;
+        EpiRows pr, pn;
+        float rmean[8], rm2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rmean[i] = 0.f; rm2[i] = 0.f; }
+        gemm_epi_f32_prefetch<EPI_RESID_F32>(ep, pr, row0, nvalid, n0 + col0, lane);
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        int ci = 0;
+#pragma unroll 1
+        for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          if (c + 32 < col0 + kColsPerWarp) gemm_epi_f32_prefetch<EPI_RESID_F32>(ep, pn, row0, nvalid, n0 + c + 32, lane);
+          tmem_ld_wait();
+          gemm_epi_resid_ln_chunk(ep, v, pr, stg, row0, nvalid, n0 + c, lane, ci, rmean, rm2);
+          pr = pn;
+          ++ci;
+        }
+        // the accumulator is drained: the MMA warp gets the buffer back BEFORE this warp waits for the other CTAs
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtas == 2) mbar_arrive_cluster(&tmem_empty[as], 0);
+          else mbar_arrive(&tmem_empty[as]);
+        }
+        if (nvalid > 0)  // (warp-uniform; a 32-row group past the end of the range has no counter and no rows)
+          gemm_epi_resid_ln_finish(ep, rmean, rm2, row0, nvalid, n0 + col0, (n0 >> 8) * 2 + ((warp - 4) >> 2), lane);
       } else if constexpr (MODE == EPI_BF16 || MODE == EPI_BF16_GELU || MODE == EPI_DGELU) {
         uint32_t* stg = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 1024;
         mbar_wait(&tmem_full[as], aphase);
@@ -490,11 +682,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (lane < nvalid) gemm_epilogue_chunk<MODE>(ep, v, m, n0 + c);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kCtas == 2) mbar_arrive_cluster(&tmem_empty[as], 0);  // the leader's barrier counts both CTAs
-        else mbar_arrive(&tmem_empty[as]);
+      if constexpr (MODE != EPI_RESID_LN) {  // (that mode released its buffer before its cross-CTA wait)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtas == 2) mbar_arrive_cluster(&tmem_empty[as], 0);  // the leader's barrier counts both CTAs
+          else mbar_arrive(&tmem_empty[as]);
+        }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }

@@ -285,6 +285,21 @@ int bseg_gemm_set_cta_pairs(int on);
  * 1 (default) lets a GEMM whose 256-wide tiles would leave most SMs idle run on 128 x 128 one-CTA tiles instead;
  * 0 always uses the 256-wide tiles.  Results are bit-identical.  Returns the previous setting; < 0 only queries. */
 int bseg_gemm_set_small_tiles(int on);
+/* Residual + LayerNorm fusion: 1 (default) lets the two residual GEMMs of every encoder layer (attention projection,
+ * HF:modeling_seggpt.py:225,420-432; MLP lin2, :356,433-441) also write the LayerNorm that reads their rows next
+ * (norm2 of the layer, :433 / norm1 of the next layer, :420), so the fp32 residual stream is not read back from HBM by a
+ * separate LayerNorm launch; 0 runs bseg_layernorm1024's kernel after every residual GEMM as in round 1.  The
+ * statistics are merged in a different (fixed) order, so the bf16 LayerNorm output can differ from the unfused path
+ * in the last bit.  Returns the previous setting; < 0 only queries. */
+int bseg_gemm_set_fused_ln(int on);
+/* One residual GEMM with the fused LayerNorm, for tests and probes:
+ *   h[M,1024] (fp32, in place) += A[M,K] * W[1024,K]^T + bias ;  ln_out[M,1024] (bf16) = LayerNorm(h) * gamma + beta.
+ * scratch: bseg_gemm_resid_ln_scratch_bytes(M) bytes of device memory (row statistics + arrival counters; zeroed by
+ * the call). */
+size_t bseg_gemm_resid_ln_scratch_bytes(long long M);
+int bseg_gemm_bf16_resid_ln(const void* A, long long lda, const void* W, long long M, int K, const float* bias,
+                            float* h, const float* gamma, const float* beta, void* ln_out, float eps, void* scratch,
+                            void* stream);
 
 /* D = A[M,K] * W[N,K]^T (+bias); A, W bf16; out fp32 (out_is_bf16 == 0) or bf16; gelu applies to bf16 output. */
 int bseg_gemm_bf16(const void* A, long long lda, const void* W, long long M, int N, int K, const float* bias,

@@ -136,3 +136,64 @@ def test_gemm_small_launch_tiles_bit_identical(dev, M, N, K):
     assert e <= 2e-3 * s_
     assert torch.equal(wide, small)
     assert torch.equal(wide_bf, small_bf)
+
+
+def run_resid_ln(A, W, bias, h, gamma, beta, eps=1e-6):
+    """h (fp32, updated in place) += A W^T + bias; returns the bf16 LayerNorm of the updated rows."""
+    M, K = A.shape
+    L = _lib.lib()
+    ln = torch.empty((M, 1024), dtype=torch.bfloat16, device=A.device)
+    scratch = torch.empty(int(L.bseg_gemm_resid_ln_scratch_bytes(M)), dtype=torch.uint8, device=A.device)
+    scratch.fill_(0xA5)  # the call zeroes what it needs
+    _lib.check(L.bseg_gemm_bf16_resid_ln(_lib.ptr(A), A.stride(0), _lib.ptr(W), M, K, _lib.ptr(bias), _lib.ptr(h),
+                                         _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(ln), eps, _lib.ptr(scratch),
+                                         _lib.stream_ptr()), "bseg_gemm_bf16_resid_ln")
+    torch.cuda.synchronize()
+    return ln
+
+
+@pytest.mark.parametrize("M,K,pairs", [(1568, 1024, 1), (1568, 4096, 1), (1568 * 2 * 8, 1024, 1), (1568 * 7, 4096, 1),
+                                       (1568 * 3, 1024, 0), (1568 * 64, 1024, 1)])
+def test_gemm_residual_layernorm_epilogue(dev, M, K, pairs):
+    """EPI_RESID_LN (HF:modeling_seggpt.py:420-441: residual add, then the LayerNorm that reads the stream next): the
+    fp32 stream must equal the plain residual epilogue BIT FOR BIT (same accumulators, same adds), and the fused bf16
+    LayerNorm output must match (a) an fp64 LayerNorm of that stream to bf16 rounding and (b) the stand-alone
+    layernorm1024 kernel to one bf16 ulp (the statistics are merged in a different order).  Rows carry a large common
+    offset (|mean| = 30 std) so that an E[x^2] - mean^2 formulation would fail."""
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    A = torch.randn((M, K), generator=g).to(dev).to(torch.bfloat16)
+    W = (torch.randn((1024, K), generator=g) / K ** 0.5).to(dev).to(torch.bfloat16)
+    bias = torch.randn((1024,), generator=g).to(dev)
+    gamma = (1.0 + 0.2 * torch.randn((1024,), generator=g)).to(dev)
+    beta = (0.1 * torch.randn((1024,), generator=g)).to(dev)
+    h0 = (torch.randn((M, 1024), generator=g) + 30.0 * torch.randn((M, 1), generator=g)).to(dev)
+    L = _lib.lib()
+    prev = L.bseg_gemm_set_cta_pairs(pairs)
+    try:
+        h = h0.clone()
+        ln = run_resid_ln(A, W, bias, h, gamma, beta)
+        h2 = h0.clone()
+        ln2 = run_resid_ln(A, W, bias, h2, gamma, beta)
+    finally:
+        L.bseg_gemm_set_cta_pairs(prev)
+    assert torch.equal(h, h2) and torch.equal(ln, ln2)  # deterministic, whichever CTA finishes first
+    want_h = run_gemm(A, W, bias) + h0  # (acc + bias) + residual: the epilogue's own order of fp32 additions
+    assert torch.equal(h, want_h)
+    e, s = report(h, A.float() @ W.float().t() + bias + h0, f"resid_ln stream {M}x{K}")
+    assert e <= 2e-3 * s
+    sep = torch.empty((M, 1024), dtype=torch.bfloat16, device=dev)
+    _lib.check(L.bseg_layernorm1024(_lib.ptr(h), 1024, _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(sep), 1024, M, 1e-6,
+                                    _lib.stream_ptr()), "bseg_layernorm1024")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(h.double(), (1024,), gamma.double(), beta.double(), 1e-6)
+    err = (ln.double() - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-6  # half a bf16 ulp is 2^-9 relative; allow one
+    bad = (err > tol).float().mean().item()
+    diff_sep = (ln.float() - sep.float()).abs()
+    ulp = sep.float().abs() * 2.0 ** -7 + 1e-30
+    print(f"[resid_ln {M}x{K} pairs={pairs}] vs fp64 LN: max|err|={err.max().item():.3e} beyond 1 ulp: {bad:.2e}; "
+          f"differs from the stand-alone kernel in {(diff_sep > 0).float().mean().item():.2e} of the elements, "
+          f"max {(diff_sep / ulp).max().item():.2f} ulp")
+    assert bad == 0.0
+    assert (diff_sep <= ulp).all()
+    assert (diff_sep > 0).float().mean().item() < 2e-2
