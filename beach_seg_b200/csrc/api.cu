@@ -312,14 +312,12 @@ int bseg_create(const bseg_weights* w, bseg_handle** out, void* stream_) {
 // ---- workspace layout (all offsets 1024-aligned) ----
 namespace {
 struct WsLayout {
-  size_t h, xn, att, q, k, vt, mlp, inter, dec, ln_stats, ln_ready, total;
+  size_t h, xn, att, q, k, vt, mlp, inter, dec, ln_stats, total;
 };
-// Exchange buffers of the residual+LayerNorm GEMM epilogue (EPI_RESID_LN): eight (mean, M2) partials per row, and one
-// arrival counter per 32 rows for each of the (at most) 2 * kMaxLayers fused launches of a forward pass.
-constexpr int kMaxLayers = 64;
-size_t ln_stats_bytes(size_t rows) { return rows * 8 * sizeof(float2); }
-size_t ln_ready_stride(size_t rows) { return (rows + 31) / 32; }  // counters per launch
-size_t ln_ready_bytes(size_t rows) { return 2 * kMaxLayers * ln_ready_stride(rows) * sizeof(unsigned int); }
+// Exchange buffer of the residual+LayerNorm GEMM epilogue (EPI_RESID_LN): eight tagged 64-bit (mean, M2) partials per
+// row; every fused launch of a forward pass uses its own tag (launch index, < 255), the buffer is set to 0xFF bytes
+// ("never written") at the start of the pass.
+size_t ln_stats_bytes(size_t rows) { return rows * 8 * sizeof(unsigned long long); }
 WsLayout ws_layout(int B, int T = kT) {
   WsLayout L;
   const size_t rows2 = 2ull * B * T, rows1 = 1ull * B * T;
@@ -339,7 +337,6 @@ WsLayout ws_layout(int B, int T = kT) {
   L.inter = carve(rows1 * 4096 * 2);
   L.dec = carve(rows1 * kDecN * 2);
   L.ln_stats = carve(ln_stats_bytes(rows2));
-  L.ln_ready = carve(ln_ready_bytes(rows2));
   L.total = off;
   return L;
 }
@@ -353,7 +350,7 @@ struct TrainLayer {
 };
 struct TrainLayout {
   // forward transients
-  size_t xn, mlp, inter, ln_stats, ln_ready;
+  size_t xn, mlp, inter, ln_stats;
   // saved
   size_t h_emb, dec;
   std::vector<TrainLayer> layers;
@@ -374,7 +371,6 @@ TrainLayout train_layout(const bseg_handle* h, int B) {
   L.mlp = carve(rows2 * kMlp * 2);
   L.inter = carve(rows1 * 4096 * 2);
   L.ln_stats = carve(ln_stats_bytes(rows2));
-  L.ln_ready = carve(ln_ready_bytes(rows2));
   L.h_emb = carve(rows2 * kD * 4);
   L.dec = carve(rows1 * kDecN * 2);
   L.layers.resize(h->num_layers);
@@ -412,8 +408,7 @@ TrainLayout train_layout(const bseg_handle* h, int B) {
 struct FwdBufs {
   float* h_emb;                    // embeddings output == input of layer 0
   __nv_bfloat16 *xn, *mlp, *inter, *dec;
-  float2* ln_stats = nullptr;          // EPI_RESID_LN exchange (see ws_layout)
-  unsigned int* ln_ready = nullptr;
+  unsigned long long* ln_stats = nullptr;  // EPI_RESID_LN exchange (see ws_layout)
   struct PerLayer {
     float *h_mid, *h_out;
     __nv_bfloat16 *q, *k, *vt, *att, *z;
@@ -442,13 +437,15 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
   }
 
   // ---- encoder (modeling_seggpt.py:453-501) ----
-  // Fused residual + LayerNorm (gemm_set_fused_ln, default on): the proj GEMM also emits norm2 of its rows and the lin2
-  // GEMM emits the NEXT layer's norm1 (when the stream is not merged / ensembled in between), so 46 of the 52
-  // layernorm1024 launches of a 24-layer forward and their fp32 re-read of the residual stream disappear.
-  const bool fused_ln = gemm_set_fused_ln(-1) != 0 && fb.ln_stats != nullptr && h->num_layers <= kMaxLayers;
-  const size_t ready_stride = ln_ready_stride(2ull * B * kT);
+  // Fused residual + LayerNorm (gemm_set_fused_ln): the lin2 GEMM (K = 4096: ~32000 MMA cycles per tile hide the longer
+  // epilogue) also emits the NEXT layer's norm1 when the stream is not merged / ensembled in between (level >= 1, the
+  // default: 22 of the 52 layernorm1024 launches of a 24-layer forward and their fp32 re-read of the residual stream
+  // disappear); at level 2 the proj GEMM (K = 1024) also emits norm2 of its rows -- measured slower than the separate
+  // launch (its epilogue is the bottleneck already), kept as a switch.
+  const bool fused_ln = gemm_set_fused_ln(-1) != 0 && fb.ln_stats != nullptr && 2 * h->num_layers < 255;
+  const bool fused_ln_proj = fused_ln && gemm_set_fused_ln(-1) >= 2;
   if (fused_ln) {
-    cudaError_t ce = cudaMemsetAsync(fb.ln_ready, 0, ln_ready_bytes(2ull * B * kT), stream);
+    cudaError_t ce = cudaMemsetAsync(fb.ln_stats, 0xFF, ln_stats_bytes(2ull * B * kT), stream);
     if (ce != cudaSuccess) {
       set_error("bseg_forward: memset failed: %s", cudaGetErrorString(ce));
       return -static_cast<int>(ce);
@@ -457,7 +454,7 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
   auto fuse_ln = [&](GemmEpiParams& ep, const float* gamma, const float* beta, int launch_idx) {
     ep.ln_gamma = gamma; ep.ln_beta = beta; ep.ln_out = fb.xn; ep.ld_ln = kD; ep.ln_eps = h->eps;
     ep.ln_stats = fb.ln_stats;
-    ep.ln_ready = fb.ln_ready + static_cast<size_t>(launch_idx) * ready_stride;
+    ep.ln_tag = static_cast<unsigned int>(launch_idx);
   };
   float* h_in = fb.h_emb;
   bool ln1_done = false;  // norm1 of this layer was written by the previous layer's lin2 epilogue
@@ -486,10 +483,10 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
     if (!ens) {
       GemmEpiParams ep;
       ep.out = pl.h_mid; ep.ldc = kD; ep.bias = lp.proj_b; ep.resid = h_in; ep.ldr = kD;
-      if (fused_ln) fuse_ln(ep, lp.ln2_w, lp.ln2_b, 2 * i);
-      if ((rc = launch_gemm(fused_ln ? EPI_RESID_LN : EPI_RESID_F32, pl.att, kD, lp.proj_w, M, kD, kD, ep, stream)))
+      if (fused_ln_proj) fuse_ln(ep, lp.ln2_w, lp.ln2_b, 2 * i);
+      if ((rc = launch_gemm(fused_ln_proj ? EPI_RESID_LN : EPI_RESID_F32, pl.att, kD, lp.proj_w, M, kD, kD, ep, stream)))
         return rc;
-      ln2_done = fused_ln;
+      ln2_done = fused_ln_proj;
     } else {
       BSEG_REQUIRE(pl.h_mid == h_in, "feature ensemble is an inference-only path");
       float* tmp = reinterpret_cast<float*>(fb.mlp);
@@ -568,8 +565,7 @@ FwdBufs train_bufs(bseg_handle* h, const TrainLayout& L, uint8_t* ws) {
   auto fp = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
   fb.h_emb = fp(L.h_emb);
   fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
-  fb.ln_stats = reinterpret_cast<float2*>(ws + L.ln_stats);
-  fb.ln_ready = reinterpret_cast<unsigned int*>(ws + L.ln_ready);
+  fb.ln_stats = reinterpret_cast<unsigned long long*>(ws + L.ln_stats);
   fb.layers.resize(h->num_layers);
   for (int i = 0; i < h->num_layers; ++i) {
     const TrainLayer& t = L.layers[i];
@@ -598,8 +594,7 @@ static int forward_eager(bool query_half_only, bseg_handle* h, const float* pixe
   FwdBufs fb;
   fb.h_emb = reinterpret_cast<float*>(ws + L.h);
   fb.xn = bf(L.xn); fb.mlp = bf(L.mlp); fb.inter = bf(L.inter); fb.dec = bf(L.dec);
-  fb.ln_stats = reinterpret_cast<float2*>(ws + L.ln_stats);
-  fb.ln_ready = reinterpret_cast<unsigned int*>(ws + L.ln_ready);
+  fb.ln_stats = reinterpret_cast<unsigned long long*>(ws + L.ln_stats);
   fb.layers.assign(h->num_layers, {fb.h_emb, fb.h_emb, bf(L.q), bf(L.k), bf(L.vt), bf(L.att), nullptr, nullptr});
   return forward_impl(h, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, ensemble_prompts, fb,
                       pred_masks, stream, query_half_only);
@@ -1136,22 +1131,20 @@ int bseg_gemm_set_fused_ln(int on) { return gemm_set_fused_ln(on); }
 
 size_t bseg_gemm_resid_ln_scratch_bytes(long long M) {
   if (M <= 0) return 0;
-  return align_up(ln_stats_bytes(static_cast<size_t>(M)), 1024) + ln_ready_stride(static_cast<size_t>(M)) * sizeof(unsigned int);
+  return ln_stats_bytes(static_cast<size_t>(M));
 }
 int bseg_gemm_bf16_resid_ln(const void* A, long long lda, const void* W, long long M, int K, const float* bias,
                             float* hres, const float* gamma, const float* beta, void* ln_out, float eps, void* scratch,
                             void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BSEG_REQUIRE(A && W && hres && gamma && beta && ln_out && scratch && M > 0, "bseg_gemm_bf16_resid_ln: bad argument");
-  uint8_t* sc = static_cast<uint8_t*>(scratch);
-  const size_t off = align_up(ln_stats_bytes(static_cast<size_t>(M)), 1024);
-  BSEG_CHECK_CUDA(cudaMemsetAsync(sc + off, 0, ln_ready_stride(static_cast<size_t>(M)) * sizeof(unsigned int), stream));
+  BSEG_CHECK_CUDA(cudaMemsetAsync(scratch, 0xFF, ln_stats_bytes(static_cast<size_t>(M)), stream));
   GemmEpiParams ep;
   ep.out = hres; ep.ldc = 1024; ep.bias = bias; ep.resid = hres; ep.ldr = 1024;
   ep.ln_gamma = gamma; ep.ln_beta = beta; ep.ln_out = static_cast<__nv_bfloat16*>(ln_out); ep.ld_ln = 1024;
   ep.ln_eps = eps;
-  ep.ln_stats = reinterpret_cast<float2*>(sc);
-  ep.ln_ready = reinterpret_cast<unsigned int*>(sc + off);
+  ep.ln_stats = static_cast<unsigned long long*>(scratch);
+  ep.ln_tag = 0;
   return launch_gemm(EPI_RESID_LN, static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), M,
                      1024, K, ep, stream);
 }

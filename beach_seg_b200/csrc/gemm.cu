@@ -21,10 +21,10 @@ int gemm_set_small_tiles(int on) {
   if (on >= 0) g_small_tiles = on != 0;
   return prev;
 }
-static int g_fused_ln = 1;  // residual GEMMs also emit the LayerNorm that follows (EPI_RESID_LN)
-int gemm_set_fused_ln(int on) {
+static int g_fused_ln = 0;  // 0: off (default), 1: lin2 also emits the next norm1 (EPI_RESID_LN), 2: proj emits norm2 as well
+int gemm_set_fused_ln(int level) {
   const int prev = g_fused_ln;
-  if (on >= 0) g_fused_ln = on != 0;
+  if (level >= 0) g_fused_ln = level > 2 ? 2 : level;
   return prev;
 }
 int gemm_set_cta_pairs(int on) {
@@ -170,9 +170,9 @@ int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv
     // residual + LayerNorm: the four N tiles of a row block exchange row statistics, eight 128-column slices per row
     BSEG_REQUIRE(N == 1024 && gr.nbatch == 1 && gr.row_begin == 0,
                  "gemm: the residual+LayerNorm epilogue needs N == 1024 and one contiguous row range");
-    BSEG_REQUIRE(ep.ln_gamma && ep.ln_beta && ep.ln_out && ep.ln_stats && ep.ln_ready && ep.resid && ep.out,
+    BSEG_REQUIRE(ep.ln_gamma && ep.ln_beta && ep.ln_out && ep.ln_stats && ep.ln_tag < 255 && ep.resid && ep.out,
                  "gemm: residual+LayerNorm epilogue with a null pointer");
-    BSEG_REQUIRE(ep.ld_ln % 4 == 0 && ep.ldc % 4 == 0 && ep.ldr % 4 == 0, "gemm: residual+LayerNorm leading dims");
+    BSEG_REQUIRE(ep.ld_ln == 1024 && ep.ldc == 1024 && ep.ldr == 1024, "gemm: residual+LayerNorm operands must be dense [M,1024]");
     if (pairs) return launch_gemm_pair_t<256, EPI_RESID_LN>(A, lda, W, gr, N, K, ep, stream);
     return launch_gemm_t<256, EPI_RESID_LN>(A, lda, W, gr, N, K, ep, stream);
   }

@@ -50,8 +50,10 @@ struct GemmEpiParams {
   __nv_bfloat16* ln_out = nullptr;
   long long ld_ln = 0;
   float ln_eps = 1e-6f;
-  float2* ln_stats = nullptr;     // [M][8] (mean, M2) of the eight 128-column slices of a row
-  unsigned int* ln_ready = nullptr;  // [ceil(M / 32)] arrival counters, ZERO before the launch (8 arrivals per 32 rows)
+  // [M][8] 64-bit entries {mean, M2 with the launch tag in its low 8 mantissa bits} of the eight 128-column slices of a
+  // row.  Consecutive launches on the same buffer must use different tags (0..254); 0xFF bytes = never written.
+  unsigned long long* ln_stats = nullptr;
+  unsigned int ln_tag = 0;
 };
 
 // Which rows of A (== rows of the output) a launch covers: `nbatch` entries of `rows_per_batch` rows each, of which
@@ -141,11 +143,14 @@ __device__ __forceinline__ void gemm_epi_f32_chunk(const GemmEpiParams& ep, cons
 
 // ---- EPI_RESID_LN: residual epilogue + LayerNorm of the finished row ---------------------------------------------
 // A 256-column tile sees a quarter of a row, so the row statistics are exchanged between the four CTAs (pairs) that own
-// the N tiles of the same rows: every epilogue warp publishes (mean, M2) of its 32 rows x 128 columns, bumps the
-// arrival counter of its 32-row group (release), hands its TMEM buffer back to the MMA warp, waits for the eight
-// arrivals of the group (acquire; the other seven warps belong to CTAs that are resident by construction: the kernel is
-// persistent with at most one wave of CTAs), merges the eight partials and normalises ITS OWN 32 x 128 slice, which it
-// wrote microseconds ago and now reads back from L2 with the same thread <-> element mapping.
+// the N tiles of the same rows, through L2: every epilogue warp publishes (mean, M2) of its 32 rows x 128 columns as ONE
+// 64-bit relaxed store per row whose low 8 bits carry the launch's tag, and a reader polls the eight entries of a row
+// until all carry the tag.  A 64-bit scalar access is single-copy atomic, so no fence, no counter and no ordering with
+// any other access is needed (a first version with arrival counters + release/acquire ran 3x slower: each fence waits
+// for the warp's ~100 outstanding residual loads and stores).  The peers are resident by construction (persistent kernel,
+// at most one wave of CTAs), and a warp publishes its tile BEFORE it waits for anybody, so there is no cyclic wait.
+// The warp then normalises ITS OWN 32 x 128 slice, which it wrote a tile ago and reads back from L2 with the same
+// thread <-> element mapping.
 // Statistics are carried as (mean, M2 = sum of squared deviations) and merged pairwise between equal counts (Chan et
 // al.): no E[x^2] - mean^2 cancellation, and the merge is bitwise symmetric, so every warp that merges the same eight
 // partials in the same tree gets the same bits (one row is normalised consistently by four different CTAs).
@@ -154,58 +159,63 @@ __device__ __forceinline__ void ln_merge_equal(float& mean, float& m2, float mea
   m2 = __fmaf_rn(d * d, half_count, m2 + m2_b);
   mean = 0.5f * (mean + mean_b);
 }
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_gpu_add_u32(unsigned int* p, unsigned int v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// lane 0 of the warp spins (with the same kind of watchdog as mbar_wait), the warp re-converges behind it
-__device__ __forceinline__ void ln_wait_ready(const unsigned int* ctr, unsigned int target, int lane) {
-  if (lane == 0) {
-    long long t0 = 0;
-    uint32_t spins = 0;
-    while (ld_acquire_gpu_u32(ctr) < target) {
-      __nanosleep(40);
-      if ((++spins & 63u) == 0u) {
-        const long long now = clock64();
-        if (t0 == 0) t0 = now;
-        if (now - t0 > 4000000000LL) {
-          printf("bseg: LayerNorm statistics watchdog block=%d thread=%d counter=%u target=%u\n", blockIdx.x,
-                 threadIdx.x, ld_acquire_gpu_u32(ctr), target);
-          __trap();
-        }
-      }
-    }
-  }
-  __syncwarp();
-  __threadfence();
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // pass 1 for one 32 x 32 chunk: gemm_epi_f32_chunk<EPI_RESID_F32> + running statistics of rows (i*4 + lane/8) over
 // this thread's four columns per chunk.  `ci` = number of chunks already merged (the running side holds 4*ci values).
-__device__ __forceinline__ void gemm_epi_resid_ln_chunk(const GemmEpiParams& ep, const float (&v)[32], const EpiRows& pr,
-                                                        float* stg, long long row0, int nvalid, int n, int lane, int ci,
-                                                        float (&rmean)[8], float (&rm2)[8]) {
+// All three row-major operands of this mode (residual in, stream out, LayerNorm out) have leading dimension 1024 (checked
+// by the launcher), so every access is `thread base + compile-time offset`.
+constexpr int kLnLd = 1024;
+// -DBSEG_LN_TRACE: per-phase clock64 sums of the epilogue loop of a few warps, printed at kernel end (tools/ln_trace.py)
+#ifdef BSEG_LN_TRACE
+#define LN_T(k) do { const long long t_ = clock64(); ln_t[k] += t_ - ln_last; ln_last = t_; } while (0)
+#else
+#define LN_T(k) do { } while (0)
+#endif
+__device__ __forceinline__ void gemm_epi_resid_ln_prefetch(const float* resid_thread /*row0 + lane/8, n + 4*(lane%8)*/,
+                                                           EpiRows& pr, int nvalid, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i * 4 + (lane >> 3) < nvalid) pr.r[i] = *reinterpret_cast<const float4*>(resid_thread + i * 4 * kLnLd);
+}
+__device__ __forceinline__ void sts128_f32(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128_f32(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+// stg_w / stg_r: shared-window byte addresses of this thread's row in the per-warp 32 x 32 transposing tile
+// (stg + lane * 128) and of its read-back position (stg + (lane / 8) * 128); the 16-byte chunk index is XORed with row % 8.
+__device__ __forceinline__ void gemm_epi_resid_ln_chunk(const float* bias_thread /*bias + n + 4*(lane%8), or null*/,
+                                                        float* out_thread /*row0 + lane/8, n + 4*(lane%8)*/,
+                                                        const float (&v)[32], const EpiRows& pr, uint32_t stg_w,
+                                                        uint32_t stg_r, int nvalid, int lane, int ci, float (&rmean)[8],
+                                                        float (&rm2)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    sts128_f32(stg_w + (((j ^ lane) & 7) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4 * (lane & 7)));
+  if (bias_thread != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias_thread));
   // merging 4 new values into 4*ci: mean += delta / (ci + 1), M2 += M2_new + delta^2 * 4 ci / (ci + 1)
   const float w_mean = ci == 0 ? 1.0f : (ci == 1 ? 0.5f : (ci == 2 ? (1.0f / 3.0f) : 0.25f));
   const float w_m2 = ci == 0 ? 0.0f : (ci == 1 ? 2.0f : (ci == 2 ? (8.0f / 3.0f) : 3.0f));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
+    // row rr = i * 4 + lane / 8: rr % 8 = (i % 2) * 4 + lane / 8 (lane / 8 < 4)
     const int rr = i * 4 + (lane >> 3);
-    const long long m = row0 + rr;
-    float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+    float4 o = lds128_f32(stg_r + i * 4 * 128 + ((((lane & 7) ^ rr) & 7) << 4));
     o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
     o.x += pr.r[i].x; o.y += pr.r[i].y; o.z += pr.r[i].z; o.w += pr.r[i].w;
-    if (rr < nvalid) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + m * ep.ldc + n + 4 * (lane & 7)) = o;
+    if (rr < nvalid) *reinterpret_cast<float4*>(out_thread + i * 4 * kLnLd) = o;
     const float m4 = 0.25f * ((o.x + o.y) + (o.z + o.w));
     const float da = o.x - m4, db = o.y - m4, dc = o.z - m4, dd = o.w - m4;
     const float q4 = (da * da + db * db) + (dc * dc + dd * dd);
@@ -215,11 +225,10 @@ __device__ __forceinline__ void gemm_epi_resid_ln_chunk(const GemmEpiParams& ep,
   }
   __syncwarp();
 }
-// Everything after the last chunk of pass 1 (the caller has already released its TMEM buffer): publish, wait, merge,
-// normalise.  `slot` = 2 * (N tile) + (column half of the warp); the warp covers columns [ncol0, ncol0 + 128).
-__device__ __forceinline__ void gemm_epi_resid_ln_finish(const GemmEpiParams& ep, float (&rmean)[8], float (&rm2)[8],
-                                                         long long row0, int nvalid, int ncol0, int slot, int lane) {
-  // (a) the eight lanes that share a row: 16 values each -> 128
+// After the last chunk of pass 1: merge the eight lanes that share a row (16 values each -> 128) and publish the warp's
+// 32 x (mean, M2 | tag).  `slot` = 2 * (N tile) + (column half of the warp).
+__device__ __forceinline__ void gemm_epi_resid_ln_publish(const GemmEpiParams& ep, float (&rmean)[8], float (&rm2)[8],
+                                                          long long row0, int nvalid, int slot, int lane) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -229,57 +238,113 @@ __device__ __forceinline__ void gemm_epi_resid_ln_finish(const GemmEpiParams& ep
       ln_merge_equal(rmean[i], rm2[i], mb, qb, 8.0f * o);
     }
   }
-  // (b) publish (every lane of a row's group holds the same bits; the first one stores them)
-  if ((lane & 7) == 0) {
+  if ((lane & 7) == 0) {  // every lane of a row's group holds the same bits; the first one stores them
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rr = i * 4 + (lane >> 3);
-      if (rr < nvalid) ep.ln_stats[(row0 + rr) * 8 + slot] = make_float2(rmean[i], rm2[i]);
+      const unsigned long long e = (static_cast<unsigned long long>((__float_as_uint(rm2[i]) & 0xffffff00u) | ep.ln_tag) << 32) |
+                                   __float_as_uint(rmean[i]);
+      if (rr < nvalid) st_relaxed_gpu_u64(ep.ln_stats + (row0 + rr) * 8 + slot, e);
     }
   }
-  __threadfence();
-  __syncwarp();
-  unsigned int* ctr = ep.ln_ready + (row0 >> 5);
-  if (lane == 0) red_release_gpu_add_u32(ctr, 1u);
-  // (c) wait for the eight slices of these 32 rows, merge them: 128 -> 1024
-  ln_wait_ready(ctr, 8u, lane);
+}
+// The LayerNorm of a tile happens one tile later (the peers published long ago, so the entries normally carry the tag
+// on the first look).  _issue starts the loads of the first half (64 columns) of the warp's own 32 x 128 slice of the
+// fp32 stream, which the same thread wrote a tile ago and which now sits in L2; _finish, called after the next tile's
+// pass 1, fetches and merges the eight statistics entries per row (128 -> 1024 columns), normalises the first half,
+// fetches and normalises the second half (register budget: the next tile's residual prefetch is in flight as well).  8 lanes x 8 B = 64 contiguous bytes of bf16 per row.
+struct LnPending {
+  float4 x[16];  // columns 32 j + 4 (lane % 8) .. + 3 of rows i * 4 + lane / 8, j = 0, 1
+};
+__device__ __forceinline__ void gemm_epi_resid_ln_load_half(const float* xin, float4 (&x)[16], int nvalid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[j * 8 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i * 4 + (lane >> 3) < nvalid) x[j * 8 + i] = *reinterpret_cast<const float4*>(xin + i * 4 * kLnLd + 32 * j);
+    }
+}
+__device__ __forceinline__ void gemm_epi_resid_ln_load_stats(const unsigned long long* mine, unsigned long long (&e)[8],
+                                                             unsigned int tag, int nvalid, int lane) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int rr = i * 4 + (lane >> 3);
-    float2 p = make_float2(0.f, 0.f);
-    if (rr < nvalid) p = __ldcg(ep.ln_stats + (row0 + rr) * 8 + (lane & 7));
-    rmean[i] = p.x;
-    rm2[i] = p.y;
+    e[i] = static_cast<unsigned long long>(tag) << 32;  // rows past the range: "ready", zeros
+    if (i * 4 + (lane >> 3) < nvalid) e[i] = ld_relaxed_gpu_u64(mine + i * 4 * 8);
+  }
+}
+__device__ __forceinline__ void gemm_epi_resid_ln_issue(const GemmEpiParams& ep, LnPending& p, long long row0, int nvalid,
+                                                        int ncol0, int lane) {
+  const size_t toff = static_cast<size_t>(row0 + (lane >> 3)) * kLnLd + ncol0 + 4 * (lane & 7);
+  gemm_epi_resid_ln_load_half(reinterpret_cast<const float*>(ep.out) + toff, p.x, nvalid, lane);
+}
+__device__ __forceinline__ void gemm_epi_resid_ln_store_half(const float4 (&x)[16], const float (&mean)[8],
+                                                             const float (&rstd)[8], const float* gam, const float* bet,
+                                                             __nv_bfloat16* yout, int nvalid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gam + 32 * j));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bet + 32 * j));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 xv = x[j * 8 + i];
+      const uint2 o = make_uint2(pack_bf16x2((xv.x - mean[i]) * rstd[i] * g.x + b.x, (xv.y - mean[i]) * rstd[i] * g.y + b.y),
+                                 pack_bf16x2((xv.z - mean[i]) * rstd[i] * g.z + b.z, (xv.w - mean[i]) * rstd[i] * g.w + b.w));
+      if (i * 4 + (lane >> 3) < nvalid) *reinterpret_cast<uint2*>(yout + i * 4 * kLnLd + 32 * j) = o;
+    }
+  }
+}
+__device__ __forceinline__ void gemm_epi_resid_ln_finish(const GemmEpiParams& ep, LnPending& p, long long row0, int nvalid,
+                                                         int ncol0, int lane) {
+  float mean[8], rstd[8];
+  {
+    const unsigned long long* mine = ep.ln_stats + (row0 + (lane >> 3)) * 8 + (lane & 7);
+    unsigned long long e[8];  // statistics entry (slot lane % 8) of rows i * 4 + lane / 8
+    long long t0 = 0;
+    uint32_t spins = 0;
+    for (;;) {
+      gemm_epi_resid_ln_load_stats(mine, e, ep.ln_tag, nvalid, lane);
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ok = ok && ((static_cast<uint32_t>(e[i] >> 32) & 0xffu) == ep.ln_tag);
+      if (__all_sync(0xffffffffu, ok)) break;
+      __nanosleep(64);
+      if ((++spins & 63u) == 0u) {  // same kind of watchdog as mbar_wait: a protocol bug traps instead of hanging the box
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000LL) {
+          if (lane == 0)
+            printf("bseg: LayerNorm statistics watchdog block=%d thread=%d row0=%lld tag=%u\n", blockIdx.x, threadIdx.x,
+                   row0, ep.ln_tag);
+          __trap();
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = __uint_as_float(static_cast<uint32_t>(e[i]));
+      rstd[i] = __uint_as_float(static_cast<uint32_t>(e[i] >> 32) & 0xffffff00u);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
-      const float mb = __shfl_xor_sync(0xffffffffu, rmean[i], o);
-      const float qb = __shfl_xor_sync(0xffffffffu, rm2[i], o);
-      ln_merge_equal(rmean[i], rm2[i], mb, qb, 64.0f * o);
+      const float mb = __shfl_xor_sync(0xffffffffu, mean[i], o);
+      const float qb = __shfl_xor_sync(0xffffffffu, rstd[i], o);
+      ln_merge_equal(mean[i], rstd[i], mb, qb, 64.0f * o);
     }
-    rm2[i] = rsqrtf(rm2[i] * (1.0f / 1024.0f) + ep.ln_eps);  // from here on: 1 / std
+    rstd[i] = rsqrtf(rstd[i] * (1.0f / 1024.0f) + ep.ln_eps);
   }
-  // (d) pass 2: own 32 x 128 slice back from L2, normalise, bf16 (8 lanes x 8 B = 64 contiguous bytes per row)
-#pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
-    const int n = ncol0 + c + 4 * (lane & 7);
-    float4 x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 4 + (lane >> 3);
-      x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rr < nvalid) x[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.out) + (row0 + rr) * ep.ldc + n);
-    }
-    const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 4 + (lane >> 3);
-      const float mean = rmean[i], rstd = rm2[i];
-      const uint2 o = make_uint2(pack_bf16x2((x[i].x - mean) * rstd * g.x + b.x, (x[i].y - mean) * rstd * g.y + b.y),
-                                 pack_bf16x2((x[i].z - mean) * rstd * g.z + b.z, (x[i].w - mean) * rstd * g.w + b.w));
-      if (rr < nvalid) *reinterpret_cast<uint2*>(ep.ln_out + (row0 + rr) * ep.ld_ln + n) = o;
-    }
-  }
+  const size_t toff = static_cast<size_t>(row0 + (lane >> 3)) * kLnLd + ncol0 + 4 * (lane & 7);
+  const float* xin = reinterpret_cast<const float*>(ep.out) + toff;
+  __nv_bfloat16* yout = ep.ln_out + toff;
+  const float* gam = ep.ln_gamma + ncol0 + 4 * (lane & 7);
+  const float* bet = ep.ln_beta + ncol0 + 4 * (lane & 7);
+  gemm_epi_resid_ln_store_half(p.x, mean, rstd, gam, bet, yout, nvalid, lane);
+  asm volatile("" ::: "memory");  // (the second half reuses the first half's registers: do not hoist its loads)
+  gemm_epi_resid_ln_load_half(xin + 64, p.x, nvalid, lane);
+  gemm_epi_resid_ln_store_half(p.x, mean, rstd, gam + 64, bet + 64, yout + 64, nvalid, lane);
 }
 
 // ---- bf16-output epilogues with a row-major destination (bias / GELU / GELU') ---------------------------------------
@@ -491,7 +556,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
-  // EPI_RESID_LN: the epilogue warps carry the residual prefetch (64 registers) and the row statistics, so the control
+  // EPI_RESID_LN: the epilogue warps carry the residual prefetch, the LayerNorm loads and the row statistics, so the control
   // warpgroup gives its registers away (128 x 56 + 256 x 224 = 384 x 168, the CTA's pool).  ptxas sizes each side of
   // this branch by the setmaxnreg it starts with, hence the nesting.
   if (warp < 4) {
@@ -570,6 +635,106 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int col0 = ((warp - 4) >> 2) * kColsPerWarp;
     int as = 0;
     uint32_t aphase = 0;
+    if constexpr (MODE == EPI_RESID_LN) {
+      // Software-pipelined over the warp's tiles, so that every L2 / HBM round trip of the epilogue overlaps other work:
+      //   top of tile i : issue the loads for the LayerNorm of tile i-1 (its eight statistics entries per row and the
+      //                   first half of the warp's own slice of the fp32 stream, written a tile ago, now in L2)
+      //   pass 1 of i   : accumulator + bias + residual -> fp32 stream, running row statistics; the residual chunks are
+      //                   fetched two chunks ahead (chunks 0, 1 of tile i were issued at the end of tile i-1)
+      //   then          : TMEM buffer back to the MMA warp, publish the statistics of tile i, issue the residual loads of
+      //                   tile i+1's first two chunks, LayerNorm of tile i-1 (second half of the slice fetched here).
+      // No warp waits for another CTA before it has published everything it owes, so there is no cyclic wait.
+      static_assert(MODE != EPI_RESID_LN || (BLOCK_N == 256 && kColsPerWarp == 128),
+                    "the LayerNorm exchange assumes eight 128-column slices per row");
+      const uint32_t stg_s = smem_u32(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 4096;
+      const uint32_t stg_w = stg_s + lane * 128, stg_r = stg_s + (lane >> 3) * 128;
+      // N == 1024 and one contiguous row range (checked by the launcher): tile -> (row block, N tile) by shifts
+      const int warp_row = cta_rank * GEMM_BLOCK_M + q * 32;
+      const size_t lane_off = static_cast<size_t>(lane >> 3) * kLnLd + col0 + 4 * (lane & 7);
+      EpiRows pr[2];
+      long long tile = tile_first;
+      long long row0 = 0, row0_p = 0;
+      int nvalid = 0, n0 = 0, nvalid_p = 0, n0_p = 0;
+      if (tile < num_tiles) {
+        row0 = (tile >> 2) * kTileM + warp_row;
+        nvalid = gr.rows - static_cast<int>(row0);
+        n0 = static_cast<int>(tile & 3) * BLOCK_N;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+          gemm_epi_resid_ln_prefetch(ep.resid + static_cast<size_t>(row0) * kLnLd + n0 + lane_off + 32 * ci, pr[ci], nvalid, lane);
+      }
+#ifdef BSEG_LN_TRACE
+      long long ln_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ln_last = clock64();
+      int ln_tiles = 0;
+#endif
+      while (tile < num_tiles) {
+        // ---- loads for the LayerNorm of the previous tile (consumed after this tile's pass 1) ----
+        LnPending pend;
+        if (nvalid_p > 0) gemm_epi_resid_ln_issue(ep, pend, row0_p, nvalid_p, n0_p + col0, lane);
+        LN_T(7);
+        float rmean[8], rm2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rmean[i] = 0.f; rm2[i] = 0.f; }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + col0;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        LN_T(0);
+        const float* resid_thread = ep.resid + static_cast<size_t>(row0) * kLnLd + n0 + lane_off;
+        float* out_thread = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row0) * kLnLd + n0 + lane_off;
+        const float* bias_thread = ep.bias != nullptr ? ep.bias + n0 + col0 + 4 * (lane & 7) : nullptr;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          float v[32];
+          tmem_ld32(taddr + 32 * ci, v);
+          tmem_ld_wait();
+          gemm_epi_resid_ln_chunk(bias_thread != nullptr ? bias_thread + 32 * ci : nullptr, out_thread + 32 * ci, v, pr[ci & 1],
+                                  stg_w, stg_r, nvalid, lane, ci, rmean, rm2);
+          if (ci < 2) gemm_epi_resid_ln_prefetch(resid_thread + 32 * (ci + 2), pr[ci & 1], nvalid, lane);
+        }
+        LN_T(1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtas == 2) mbar_arrive_cluster(&tmem_empty[as], 0);
+          else mbar_arrive(&tmem_empty[as]);
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        // (nvalid is warp-uniform; a 32-row group past the end of the row range publishes and normalises nothing)
+        if (nvalid > 0) gemm_epi_resid_ln_publish(ep, rmean, rm2, row0, nvalid, (n0 >> 8) * 2 + ((warp - 4) >> 2), lane);
+        LN_T(2);
+        const long long row0_c = row0;
+        const int nvalid_c = nvalid, n0_c = n0;
+        tile += tile_step;
+        if (tile < num_tiles) {
+          row0 = (tile >> 2) * kTileM + warp_row;
+          nvalid = gr.rows - static_cast<int>(row0);
+          n0 = static_cast<int>(tile & 3) * BLOCK_N;
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci)
+            gemm_epi_resid_ln_prefetch(ep.resid + static_cast<size_t>(row0) * kLnLd + n0 + lane_off + 32 * ci, pr[ci], nvalid, lane);
+        }
+        LN_T(3);
+        if (nvalid_p > 0) {
+          gemm_epi_resid_ln_finish(ep, pend, row0_p, nvalid_p, n0_p + col0, lane);
+#ifdef BSEG_LN_TRACE
+          ++ln_tiles;
+#endif
+        }
+        LN_T(5);
+        row0_p = row0_c; nvalid_p = nvalid_c; n0_p = n0_c;
+      }
+      if (nvalid_p > 0) {
+        LnPending pend;
+        gemm_epi_resid_ln_issue(ep, pend, row0_p, nvalid_p, n0_p + col0, lane);
+        gemm_epi_resid_ln_finish(ep, pend, row0_p, nvalid_p, n0_p + col0, lane);
+      }
+#ifdef BSEG_LN_TRACE
+      if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && (warp == 4 || warp == 9) && ln_tiles > 0)
+        printf("LNTRACE block %d warp %d tiles %d | per tile: wait_acc %lld pass1 %lld release+publish %lld prefetch %lld "
+               "layernorm %lld issue %lld\n", blockIdx.x, warp, ln_tiles, ln_t[0] / ln_tiles, ln_t[1] / ln_tiles,
+               ln_t[2] / ln_tiles, ln_t[3] / ln_tiles, ln_t[5] / ln_tiles, ln_t[7] / ln_tiles);
+#endif
+    } else
     for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
       const long long mt = tile / num_n_tiles;
       const int local0 = gr.row_begin + static_cast<int>(mt % tiles_per_batch) * kTileM + cta_rank * GEMM_BLOCK_M + q * 32;
@@ -593,36 +758,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           gemm_epi_f32_chunk<MODE>(ep, v, pr, stg, row0, nvalid, n0 + c, lane);
           pr = pn;
         }
-      } else if constexpr (MODE == EPI_RESID_LN) {
-        static_assert(MODE != EPI_RESID_LN || BLOCK_N == 256, "the LayerNorm exchange assumes eight 128-column slices per row");
-        float* stg = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 1024;
-        EpiRows pr, pn;
-        float rmean[8], rm2[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { rmean[i] = 0.f; rm2[i] = 0.f; }
-        gemm_epi_f32_prefetch<EPI_RESID_F32>(ep, pr, row0, nvalid, n0 + col0, lane);
-        mbar_wait(&tmem_full[as], aphase);
-        tc_fence_after();
-        int ci = 0;
-#pragma unroll 1
-        for (int c = col0; c < col0 + kColsPerWarp; c += 32) {
-          float v[32];
-          tmem_ld32(taddr + c, v);
-          if (c + 32 < col0 + kColsPerWarp) gemm_epi_f32_prefetch<EPI_RESID_F32>(ep, pn, row0, nvalid, n0 + c + 32, lane);
-          tmem_ld_wait();
-          gemm_epi_resid_ln_chunk(ep, v, pr, stg, row0, nvalid, n0 + c, lane, ci, rmean, rm2);
-          pr = pn;
-          ++ci;
-        }
-        // the accumulator is drained: the MMA warp gets the buffer back BEFORE this warp waits for the other CTAs
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (kCtas == 2) mbar_arrive_cluster(&tmem_empty[as], 0);
-          else mbar_arrive(&tmem_empty[as]);
-        }
-        if (nvalid > 0)  // (warp-uniform; a 32-row group past the end of the range has no counter and no rows)
-          gemm_epi_resid_ln_finish(ep, rmean, rm2, row0, nvalid, n0 + col0, (n0 >> 8) * 2 + ((warp - 4) >> 2), lane);
       } else if constexpr (MODE == EPI_BF16 || MODE == EPI_BF16_GELU || MODE == EPI_DGELU) {
         uint32_t* stg = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kStageBytes + 256) + (warp - 4) * 1024;
         mbar_wait(&tmem_full[as], aphase);
@@ -682,7 +817,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (lane < nvalid) gemm_epilogue_chunk<MODE>(ep, v, m, n0 + c);
         }
       }
-      if constexpr (MODE != EPI_RESID_LN) {  // (that mode released its buffer before its cross-CTA wait)
+      if constexpr (MODE != EPI_RESID_LN) {  // (that mode runs its own loop above)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {

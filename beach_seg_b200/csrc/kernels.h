@@ -18,8 +18,8 @@ int launch_gemm_rows(int mode, const __nv_bfloat16* A, long long lda, const __nv
 int gemm_set_cta_pairs(int on);
 // 128 x 128 one-CTA tiles for launches too small to fill the SMs with 256-wide tiles (default on; < 0 queries)
 int gemm_set_small_tiles(int on);
-// the residual GEMMs (proj, lin2) of the encoder also emit the LayerNorm that follows them (default on; < 0 queries)
-int gemm_set_fused_ln(int on);
+// residual + LayerNorm fusion level: 0 off, 1 (default) lin2 emits the next layer's norm1, 2 proj emits norm2 too; < 0 queries
+int gemm_set_fused_ln(int level);
 
 // attention.cu : fused softmax(q k^T * scale + decomposed rel-pos bias) v, one CTA per (seq, head, 128-query tile)
 //   q, k : [nseq, heads, T, 64] bf16     vt : [nseq, heads, 64, T] bf16

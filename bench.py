@@ -681,7 +681,7 @@ def main():
     L.bseg_profile_enable(0)
     gemm_modes = {}
     names = {0: "bf16", 1: "lin1_gelu", 2: "proj_f32(ensemble)", 3: "proj_resid", 4: "qkv", 5: "patch_embed",
-             6: "dec_embed_pixshuf", 11: "lin2_resid", 14: "dec_embed_pixshuf"}
+             6: "dec_embed_pixshuf", 11: "lin2_resid", 14: "dec_embed_pixshuf", 12: "proj_resid_ln", 13: "lin2_resid_ln"}
     for i in range(16):
         if gms[i] > 0:
             gemm_modes[names.get(i, str(i))] = {"ms_per_step": gms[i] / args.steps,
@@ -719,6 +719,19 @@ def main():
         ms_v = timed(step_device, args.steps)
         gemm_variants[vname + "_tiles_per_s"] = world * TILES_PER_STEP * args.steps / (ms_v * 1e-3)
     L.bseg_gemm_set_cta_pairs(cur)
+    # ---- A/B of the residual + LayerNorm fusion (EPI_RESID_LN) on the same step, interleaved twice so that the
+    # power-capped clock drifts hit both sides alike ----
+    cur = L.bseg_gemm_set_fused_ln(-1)
+    ab = {0: [], 1: [], 2: []}
+    for _ in range(2):
+        for v in (0, 1, 2):
+            L.bseg_gemm_set_fused_ln(v)
+            step_device()
+            ab[v].append(world * TILES_PER_STEP * args.steps / (timed(step_device, args.steps) * 1e-3))
+    L.bseg_gemm_set_fused_ln(cur)
+    gemm_variants["fused_residual_layernorm"] = {"default_level": int(cur), "off_tiles_per_s": sum(ab[0]) / 2,
+                                                 "lin2_tiles_per_s": sum(ab[1]) / 2,
+                                                 "lin2_and_proj_tiles_per_s": sum(ab[2]) / 2}
 
     # ---- the other kernels against their own bounds (same profiled pass; per-step times) ----
     other = {}

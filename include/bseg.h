@@ -285,16 +285,17 @@ int bseg_gemm_set_cta_pairs(int on);
  * 1 (default) lets a GEMM whose 256-wide tiles would leave most SMs idle run on 128 x 128 one-CTA tiles instead;
  * 0 always uses the 256-wide tiles.  Results are bit-identical.  Returns the previous setting; < 0 only queries. */
 int bseg_gemm_set_small_tiles(int on);
-/* Residual + LayerNorm fusion: 1 (default) lets the two residual GEMMs of every encoder layer (attention projection,
- * HF:modeling_seggpt.py:225,420-432; MLP lin2, :356,433-441) also write the LayerNorm that reads their rows next
- * (norm2 of the layer, :433 / norm1 of the next layer, :420), so the fp32 residual stream is not read back from HBM by a
- * separate LayerNorm launch; 0 runs bseg_layernorm1024's kernel after every residual GEMM as in round 1.  The
- * statistics are merged in a different (fixed) order, so the bf16 LayerNorm output can differ from the unfused path
- * in the last bit.  Returns the previous setting; < 0 only queries. */
-int bseg_gemm_set_fused_ln(int on);
+/* Residual + LayerNorm fusion level.  1 (default): the MLP's lin2 GEMM of every encoder layer (HF:modeling_seggpt.py:356,
+ * 433-441) also writes the LayerNorm that reads its rows next (norm1 of the next layer, :420), so the fp32 residual
+ * stream is not read back from HBM by a separate LayerNorm launch; 2: the attention projection (:225,420-432) also
+ * writes norm2 of the layer (:433) (slower than the separate launch on B200: that GEMM's epilogue is its bottleneck);
+ * 0: bseg_layernorm1024's kernel after every residual GEMM as in round 1.  The row statistics are merged in a different
+ * (fixed) order, so the bf16 LayerNorm output can differ from the unfused path in the last bit.  Returns the previous
+ * level; < 0 only queries. */
+int bseg_gemm_set_fused_ln(int level);
 /* One residual GEMM with the fused LayerNorm, for tests and probes:
  *   h[M,1024] (fp32, in place) += A[M,K] * W[1024,K]^T + bias ;  ln_out[M,1024] (bf16) = LayerNorm(h) * gamma + beta.
- * scratch: bseg_gemm_resid_ln_scratch_bytes(M) bytes of device memory (row statistics + arrival counters; zeroed by
+ * scratch: bseg_gemm_resid_ln_scratch_bytes(M) bytes of device memory (tagged row statistics; initialised by
  * the call). */
 size_t bseg_gemm_resid_ln_scratch_bytes(long long M);
 int bseg_gemm_bf16_resid_ln(const void* A, long long lda, const void* W, long long M, int K, const float* bias,

@@ -187,10 +187,11 @@ def test_gemm_residual_layernorm_epilogue(dev, M, K, pairs):
     torch.cuda.synchronize()
     ref = torch.nn.functional.layer_norm(h.double(), (1024,), gamma.double(), beta.double(), 1e-6)
     err = (ln.double() - ref).abs()
-    tol = ref.abs() * 2.0 ** -8 + 1e-6  # half a bf16 ulp is 2^-9 relative; allow one
+    # half a bf16 ulp is 2^-9 relative (allow one); the absolute floor is fp32 rounding of x - mean at |x| ~ 100 std
+    tol = ref.abs() * 2.0 ** -8 + 3e-4
     bad = (err > tol).float().mean().item()
     diff_sep = (ln.float() - sep.float()).abs()
-    ulp = sep.float().abs() * 2.0 ** -7 + 1e-30
+    ulp = sep.float().abs() * 2.0 ** -7 + 3e-4
     print(f"[resid_ln {M}x{K} pairs={pairs}] vs fp64 LN: max|err|={err.max().item():.3e} beyond 1 ulp: {bad:.2e}; "
           f"differs from the stand-alone kernel in {(diff_sep > 0).float().mean().item():.2e} of the elements, "
           f"max {(diff_sep / ulp).max().item():.2f} ulp")
