@@ -61,6 +61,9 @@ SIGNATURES = {
     "bseg_train_workspace_bytes": (_sz, [_vp, _i]),
     "bseg_forward_train": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp]),
     "bseg_backward_to_prompt": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
+    "bseg_train_workspace_bytes_f32": (_sz, [_vp, _i]),
+    "bseg_forward_train_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp]),
+    "bseg_backward_to_prompt_f32": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
     "bseg_attention_fwd_lse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "bseg_attention_bwd_scratch_bytes": (_sz, [_i]),
     "bseg_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),

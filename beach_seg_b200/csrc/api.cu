@@ -768,6 +768,36 @@ int bseg_forward_f32(bseg_handle* h, const float* pixel_values, const float* pro
                           ensemble_prompts, workspace, pred_masks, static_cast<cudaStream_t>(stream_));
 }
 
+size_t bseg_train_workspace_bytes_f32(const bseg_handle* h, int batch) {
+  if (h == nullptr || batch <= 0 || h->f32_arena == nullptr) return 0;
+  return f32_train_workspace_bytes(h->f32, batch);
+}
+
+int bseg_forward_train_f32(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                           const float* prompt_masks, int batch, int embedding_type, void* workspace,
+                           size_t workspace_bytes, float* pred_masks, void* stream_) {
+  int rc = check_forward_args(h, batch, embedding_type, workspace, "bseg_forward_train_f32");
+  if (rc) return rc;
+  BSEG_REQUIRE(h->f32_arena != nullptr, "bseg_forward_train_f32: call bseg_enable_fp32 first");
+  const size_t need = f32_train_workspace_bytes(h->f32, batch);
+  BSEG_REQUIRE(workspace_bytes >= need, "bseg_forward_train_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
+  return forward_f32_train_impl(h->f32, pixel_values, prompt_pixel_values, prompt_masks, batch, embedding_type, workspace,
+                                pred_masks, static_cast<cudaStream_t>(stream_));
+}
+
+int bseg_backward_to_prompt_f32(bseg_handle* h, const float* d_pred_masks, int batch, void* workspace,
+                                size_t workspace_bytes, float* d_prompt_pixel_values, void* stream_) {
+  int rc = check_forward_args(h, batch, 0, workspace, "bseg_backward_to_prompt_f32");
+  if (rc) return rc;
+  BSEG_REQUIRE(h->f32_arena != nullptr, "bseg_backward_to_prompt_f32: call bseg_enable_fp32 first");
+  BSEG_REQUIRE(d_pred_masks != nullptr && d_prompt_pixel_values != nullptr, "bseg_backward_to_prompt_f32: null argument");
+  const size_t need = f32_train_workspace_bytes(h->f32, batch);
+  BSEG_REQUIRE(workspace_bytes >= need, "bseg_backward_to_prompt_f32: workspace too small (%zu < %zu)", workspace_bytes,
+               need);
+  return backward_f32_impl(h->f32, d_pred_masks, batch, workspace, d_prompt_pixel_values,
+                           static_cast<cudaStream_t>(stream_));
+}
+
 // ---- training: transposed weight packs, forward that keeps what the backward needs, backward to the prompt ----
 int bseg_train_prepare(bseg_handle* h, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

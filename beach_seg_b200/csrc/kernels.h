@@ -150,6 +150,13 @@ size_t f32_workspace_bytes(int B);
 int forward_f32_impl(const F32Weights& w, const float* pixel_values, const float* prompt_pixel_values,
                      const float* prompt_masks, int B, int embedding_type, int P, void* workspace, float* pred_masks,
                      cudaStream_t stream);
+// fp32 train step: forward that keeps its activations in `workspace`, and the backward to the prompt pixels
+size_t f32_train_workspace_bytes(const F32Weights& w, int B);
+int forward_f32_train_impl(const F32Weights& w, const float* pixel_values, const float* prompt_pixel_values,
+                           const float* prompt_masks, int B, int embedding_type, void* workspace, float* pred_masks,
+                           cudaStream_t stream);
+int backward_f32_impl(const F32Weights& w, const float* d_pred_masks, int B, void* workspace, float* d_prompt,
+                      cudaStream_t stream);
 int launch_merge_mosaic(const float* data, const uint8_t* yesdata, int N, int C, int Hs, int Ws, float* mean,
                         uint8_t* nodata, cudaStream_t stream);
 

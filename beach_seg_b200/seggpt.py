@@ -51,12 +51,13 @@ class _PromptGradFn(torch.autograd.Function):
         B = pixel_values.shape[0]
         pred = torch.empty((B, 3, 2 * IMG, IMG), dtype=torch.float32, device=model.device)
         ws, base, nbytes = model._train_workspace(B)
+        L = _lib.lib()
+        fwd, name = ((L.bseg_forward_train_f32, "bseg_forward_train_f32") if model.precision == "fp32"
+                     else (L.bseg_forward_train, "bseg_forward_train"))
         with torch.cuda.device(model.device):
-            _lib.check(_lib.lib().bseg_forward_train(model._handle, _lib.ptr(pixel_values),
-                                                     _lib.ptr(prompt_pixel_values), _lib.ptr(prompt_masks), B,
-                                                     0 if embedding_type == "instance" else 1, C.c_void_p(base),
-                                                     C.c_size_t(nbytes), _lib.ptr(pred), _lib.stream_ptr()),
-                       "bseg_forward_train")
+            _lib.check(fwd(model._handle, _lib.ptr(pixel_values), _lib.ptr(prompt_pixel_values),
+                           _lib.ptr(prompt_masks), B, 0 if embedding_type == "instance" else 1, C.c_void_p(base),
+                           C.c_size_t(nbytes), _lib.ptr(pred), _lib.stream_ptr()), name)
         ctx.model, ctx.batch = model, B
         model._train_token += 1
         ctx.token = model._train_token
@@ -74,10 +75,12 @@ class _PromptGradFn(torch.autograd.Function):
                                       "the reference's SegGptLoss (src/model.py:48-57)")
         d_prompt = torch.empty((B, 3, IMG, IMG), dtype=torch.float32, device=model.device)
         ws, base, nbytes = model._train_workspace(B)
+        L = _lib.lib()
+        bwd, name = ((L.bseg_backward_to_prompt_f32, "bseg_backward_to_prompt_f32") if model.precision == "fp32"
+                     else (L.bseg_backward_to_prompt, "bseg_backward_to_prompt"))
         with torch.cuda.device(model.device):
-            _lib.check(_lib.lib().bseg_backward_to_prompt(model._handle, _lib.ptr(d_pred), B, C.c_void_p(base),
-                                                          C.c_size_t(nbytes), _lib.ptr(d_prompt), _lib.stream_ptr()),
-                       "bseg_backward_to_prompt")
+            _lib.check(bwd(model._handle, _lib.ptr(d_pred), B, C.c_void_p(base), C.c_size_t(nbytes), _lib.ptr(d_prompt),
+                           _lib.stream_ptr()), name)
         return d_prompt, None, None, None, None
 
 
@@ -206,11 +209,14 @@ class SegGptB200(torch.nn.Module):
         """(tensor, 256B-aligned base address, usable bytes) of the training workspace for `batch` samples; the first
         call also packs the transposed weight copies the dgrad GEMMs need."""
         L = _lib.lib()
-        if not self._train_ready:
-            with torch.cuda.device(self._device):
-                _lib.check(L.bseg_train_prepare(self._handle, _lib.stream_ptr()), "bseg_train_prepare")
-            self._train_ready = True
-        need = int(L.bseg_train_workspace_bytes(self._handle, batch))
+        if self.precision == "fp32":  # (the accuracy mode differentiates with the weights as stored: nothing to pack)
+            need = int(L.bseg_train_workspace_bytes_f32(self._handle, batch))
+        else:
+            if not self._train_ready:
+                with torch.cuda.device(self._device):
+                    _lib.check(L.bseg_train_prepare(self._handle, _lib.stream_ptr()), "bseg_train_prepare")
+                self._train_ready = True
+            need = int(L.bseg_train_workspace_bytes(self._handle, batch))
         if self._train_ws is None or self._train_ws.numel() < need + 256:
             self._train_ws = None
             self._train_ws = torch.empty(need + 256, dtype=torch.uint8, device=self._device)
@@ -265,8 +271,6 @@ class SegGptB200(torch.nn.Module):
         def prep(t):
             return t.detach().to(device=self._device, dtype=torch.float32).contiguous()
 
-        if want_grad and self.precision == "fp32":
-            raise NotImplementedError("the fp32 accuracy mode is inference-only; train with precision='bf16'")
         if want_grad and S != IMG:
             raise NotImplementedError("the native-resolution mode is inference-only; the train step runs at 448")
         if want_grad:

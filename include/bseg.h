@@ -115,6 +115,17 @@ size_t bseg_workspace_bytes_f32(const bseg_handle* h, int batch);
 int bseg_forward_f32(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
                      const float* prompt_masks, int batch, int embedding_type, int ensemble_prompts, void* workspace,
                      size_t workspace_bytes, float* pred_masks, void* stream);
+/* The train step in the accuracy mode (autograd of HF:modeling_seggpt.py under src/model.py:233-269, what
+ * bseg_forward_train / bseg_backward_to_prompt compute on the tensor cores): same arguments and the same contract
+ * (d_pred_masks zero for image rows < 448; gradient w.r.t. prompt_pixel_values only), every operand, accumulator and
+ * saved activation IEEE fp32, no atomics (bit-reproducible).  Workspace: bseg_train_workspace_bytes_f32 (about 1.6 GB
+ * per sample at 24 layers; 0 before bseg_enable_fp32).  For checking the bf16 train step, not for training at scale. */
+size_t bseg_train_workspace_bytes_f32(const bseg_handle* h, int batch);
+int bseg_forward_train_f32(bseg_handle* h, const float* pixel_values, const float* prompt_pixel_values,
+                           const float* prompt_masks, int batch, int embedding_type, void* workspace,
+                           size_t workspace_bytes, float* pred_masks, void* stream);
+int bseg_backward_to_prompt_f32(bseg_handle* h, const float* d_pred_masks, int batch, void* workspace,
+                                size_t workspace_bytes, float* d_prompt_pixel_values, void* stream);
 
 /* ---- train step (src/model.py:233-269 + Lightning's loss.backward()): the reference differentiates the frozen HF
  * module w.r.t. prompt_pixel_values only (all backbone weights have requires_grad=False, src/util/ml_util.py:9-10).
