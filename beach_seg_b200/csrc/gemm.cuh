@@ -50,8 +50,9 @@ struct GemmEpiParams {
   __nv_bfloat16* ln_out = nullptr;
   long long ld_ln = 0;
   float ln_eps = 1e-6f;
-  // [M][8] 64-bit entries {mean, M2 with the launch tag in its low 8 mantissa bits} of the eight 128-column slices of a
-  // row.  Consecutive launches on the same buffer must use different tags (0..254); 0xFF bytes = never written.
+  // [M][8] 64-bit entries {mean, M2} of the eight 128-column slices of a row; the low 4 mantissa bits of each value hold
+  // a nibble of the launch tag.  Consecutive launches on the same buffer must use different tags (0..254); 0xFF bytes =
+  // never written.
   unsigned long long* ln_stats = nullptr;
   unsigned int ln_tag = 0;
 };
@@ -144,7 +145,7 @@ __device__ __forceinline__ void gemm_epi_f32_chunk(const GemmEpiParams& ep, cons
 // ---- EPI_RESID_LN: residual epilogue + LayerNorm of the finished row ---------------------------------------------
 // A 256-column tile sees a quarter of a row, so the row statistics are exchanged between the four CTAs (pairs) that own
 // the N tiles of the same rows, through L2: every epilogue warp publishes (mean, M2) of its 32 rows x 128 columns as ONE
-// 64-bit relaxed store per row whose low 8 bits carry the launch's tag, and a reader polls the eight entries of a row
+// 64-bit relaxed store per row which carries the launch's 8-bit tag in its lowest mantissa bits, and a reader polls the eight entries of a row
 // until all carry the tag.  A 64-bit scalar access is single-copy atomic, so no fence, no counter and no ordering with
 // any other access is needed (a first version with arrival counters + release/acquire ran 3x slower: each fence waits
 // for the warp's ~100 outstanding residual loads and stores).  The peers are resident by construction (persistent kernel,
@@ -242,8 +243,10 @@ __device__ __forceinline__ void gemm_epi_resid_ln_publish(const GemmEpiParams& e
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rr = i * 4 + (lane >> 3);
-      const unsigned long long e = (static_cast<unsigned long long>((__float_as_uint(rm2[i]) & 0xffffff00u) | ep.ln_tag) << 32) |
-                                   __float_as_uint(rmean[i]);
+      // the 8-bit tag replaces the low 4 mantissa bits of each value (relative error 2^-20: ~1e-3 of a bf16 ulp)
+      const unsigned long long e =
+          (static_cast<unsigned long long>((__float_as_uint(rm2[i]) & 0xfffffff0u) | (ep.ln_tag & 15u)) << 32) |
+          ((__float_as_uint(rmean[i]) & 0xfffffff0u) | (ep.ln_tag >> 4));
       if (rr < nvalid) st_relaxed_gpu_u64(ep.ln_stats + (row0 + rr) * 8 + slot, e);
     }
   }
@@ -269,7 +272,7 @@ __device__ __forceinline__ void gemm_epi_resid_ln_load_stats(const unsigned long
                                                              unsigned int tag, int nvalid, int lane) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    e[i] = static_cast<unsigned long long>(tag) << 32;  // rows past the range: "ready", zeros
+    e[i] = (static_cast<unsigned long long>(tag & 15u) << 32) | (tag >> 4);  // rows past the range: "ready", zeros
     if (i * 4 + (lane >> 3) < nvalid) e[i] = ld_relaxed_gpu_u64(mine + i * 4 * 8);
   }
 }
@@ -306,7 +309,8 @@ __device__ __forceinline__ void gemm_epi_resid_ln_finish(const GemmEpiParams& ep
       gemm_epi_resid_ln_load_stats(mine, e, ep.ln_tag, nvalid, lane);
       bool ok = true;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ok = ok && ((static_cast<uint32_t>(e[i] >> 32) & 0xffu) == ep.ln_tag);
+      for (int i = 0; i < 8; ++i)
+        ok = ok && ((((static_cast<uint32_t>(e[i]) & 15u) << 4) | (static_cast<uint32_t>(e[i] >> 32) & 15u)) == ep.ln_tag);
       if (__all_sync(0xffffffffu, ok)) break;
       __nanosleep(64);
       if ((++spins & 63u) == 0u) {  // same kind of watchdog as mbar_wait: a protocol bug traps instead of hanging the box
@@ -322,8 +326,8 @@ __device__ __forceinline__ void gemm_epi_resid_ln_finish(const GemmEpiParams& ep
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      mean[i] = __uint_as_float(static_cast<uint32_t>(e[i]));
-      rstd[i] = __uint_as_float(static_cast<uint32_t>(e[i] >> 32) & 0xffffff00u);
+      mean[i] = __uint_as_float(static_cast<uint32_t>(e[i]) & 0xfffffff0u);
+      rstd[i] = __uint_as_float(static_cast<uint32_t>(e[i] >> 32) & 0xfffffff0u);
     }
   }
 #pragma unroll

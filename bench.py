@@ -826,7 +826,33 @@ def main():
                      "class_map_disagreements": int((c32 != c16).sum().item()), "class_map_pixels": int(c32.numel()),
                      "note": "fp32 mode = every operand/accumulator IEEE fp32 on the CUDA cores; its own deviation from "
                              "the HF fp32 CPU forward is 2e-6 rel-L2 (tests/test_gpu_fp32_mode.py)"}
-        del model32, p32, p16
+        # the same comparison for the train step's gradient (bseg_forward_train_f32 + bseg_backward_to_prompt_f32 against
+        # the tensor-core path), 2 tiles, d(pred) = the reference loss's gradient on the bf16 prediction
+        ng = 2
+        labels = ops.colorize_norm(prompt_cls[ng:2 * ng], palette[0][ng:2 * ng])
+        yes = torch.ones((ng, 448, 448), dtype=torch.bool, device=dev)
+        kwg = dict(pixel_values=tiles[:ng], prompt_masks=pcol[:ng], embedding_type="instance")
+        grads, t_step = {}, {}
+        d_pred = None
+        for name, m in (("bf16", model), ("fp32", model32)):
+            ppx = prompt_images[:ng].clone().requires_grad_(True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pred = m(prompt_pixel_values=ppx, **kwg).pred_masks
+            if d_pred is None:
+                _, d_pred = ops.smooth_l1_loss(pred.detach(), labels, yes, 0.01, per_sample=True, want_grad=True)
+            pred.backward(d_pred)
+            e1.record()
+            torch.cuda.synchronize()
+            grads[name], t_step[name] = ppx.grad, e0.elapsed_time(e1)
+        fp32_mode["train_step"] = {
+            "tiles": ng, "fp32_ms": t_step["fp32"],
+            "bf16_vs_fp32_prompt_grad_rel_l2": ((grads["bf16"] - grads["fp32"]).norm() / grads["fp32"].norm()).item(),
+            "cosine": torch.nn.functional.cosine_similarity(grads["bf16"].flatten(), grads["fp32"].flatten(), dim=0).item(),
+            "note": "the fp32 train step is within 5e-6 rel-L2 of torch autograd through the HF module "
+                    "(tests/test_gpu_fp32_mode.py)"}
+        del model32, p32, p16, grads
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
