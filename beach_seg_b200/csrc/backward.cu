@@ -61,7 +61,7 @@ int launch_transpose_bf16(const __nv_bfloat16* src, __nv_bfloat16* dst, int R, i
 // Rows: `nbatch` groups of `rows_per_batch`, rows [row_begin, row_begin + rows) of each (the decoder only sends
 // gradient into the query half).
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 layernorm1024_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long lddy,
                          const float* __restrict__ gamma, const float* dh_in, float* dh_out,
                          __nv_bfloat16* __restrict__ dh_bf16, long long rows_per_batch, int nbatch, int row_begin,
@@ -74,14 +74,21 @@ layernorm1024_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
     const long long row = (it / rows) * rows_per_batch + row_begin + (it % rows);
     const float4* xr = reinterpret_cast<const float4*>(x + row * 1024);
     const float4* gr = reinterpret_cast<const float4*>(dy + row * lddy);
-    float4 v[8], g[8];
+    float4 v[8], g[8], r[8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       v[i] = xr[lane + 32 * i];
       g[i] = gr[lane + 32 * i];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
+    // the residual gradient is only needed at the very end: request it now, so that all three input streams of the
+    // row are in flight together (it used to be fetched after the four warp reductions: 0.74 of the HBM rate)
+    if (dh_in != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = reinterpret_cast<const float4*>(dh_in + row * 1024)[lane + 32 * i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) * (1.0f / 1024.0f);
     float ss = 0.f;
 #pragma unroll
@@ -107,10 +114,7 @@ layernorm1024_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
       o.y = rstd * (g[i].y - m1 - v[i].y * m2);
       o.z = rstd * (g[i].z - m1 - v[i].z * m2);
       o.w = rstd * (g[i].w - m1 - v[i].w * m2);
-      if (dh_in != nullptr) {
-        const float4 r = reinterpret_cast<const float4*>(dh_in + row * 1024)[lane + 32 * i];
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+      if (dh_in != nullptr) { o.x += r[i].x; o.y += r[i].y; o.z += r[i].z; o.w += r[i].w; }
       reinterpret_cast<float4*>(dh_out + row * 1024)[lane + 32 * i] = o;
       if (dh_bf16 != nullptr)
         reinterpret_cast<uint2*>(dh_bf16 + row * 1024)[lane + 32 * i] =

@@ -554,6 +554,52 @@ __global__ void vote_accumulate_vec4_kernel(uint32_t* __restrict__ counter, int 
     }
   }
 }
+// Same, eight pixels per thread (crop % 8 == 0): one 8-byte load of class ids and two independent 16-byte
+// read-modify-writes in flight per thread (the four-pixel kernel reached 0.56 of the HBM rate on 41 us launches).
+__device__ __forceinline__ void vote_rmw4(uint4& v, uint32_t c4) {
+  uint32_t pv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t c = (c4 >> (8 * j)) & 0xFFu;
+    if (c <= 3) {
+      const uint32_t byte = ((pv[j] >> (8 * c)) + 1u) & 0xFFu;
+      pv[j] = (pv[j] & ~(0xFFu << (8 * c))) | (byte << (8 * c));
+    }
+  }
+  v = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+}
+__global__ void vote_accumulate_vec8_kernel(uint32_t* __restrict__ counter, int Hs, int Ws,
+                                            const uint8_t* __restrict__ cls, int n_tiles, int crop,
+                                            const int* __restrict__ boxes) {
+  const int cw = crop >> 3;
+  const long long per = (long long)crop * cw;
+  const long long total = per * n_tiles;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = static_cast<int>(i / per);
+    const int sy = static_cast<int>((i % per) / cw);
+    const int sx = static_cast<int>(i % cw) * 8;
+    const int dy = boxes[t * 4 + 1] + sy, dx = boxes[t * 4 + 0] + sx;
+    if (dy < 0 || dy >= Hs || dx + 7 < 0 || dx >= Ws) continue;
+    const uint2 c8 = *reinterpret_cast<const uint2*>(cls + ((long long)t * crop + sy) * crop + sx);
+    uint32_t* w = counter + (long long)dy * Ws + dx;
+    if (dx >= 0 && dx + 7 < Ws && (dx & 3) == 0) {
+      uint4 v0 = *reinterpret_cast<uint4*>(w), v1 = *reinterpret_cast<uint4*>(w + 4);
+      vote_rmw4(v0, c8.x);
+      vote_rmw4(v1, c8.y);
+      *reinterpret_cast<uint4*>(w) = v0;
+      *reinterpret_cast<uint4*>(w + 4) = v1;
+    } else {
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t c = ((j < 4 ? c8.x : c8.y) >> (8 * (j & 3))) & 0xFFu;
+        if (dx + j < 0 || dx + j >= Ws || c > 3) continue;
+        const uint32_t old = w[j];
+        const uint32_t byte = ((old >> (8 * c)) + 1u) & 0xFFu;
+        w[j] = (old & ~(0xFFu << (8 * c))) | (byte << (8 * c));
+      }
+    }
+  }
+}
 int launch_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls, int n_tiles, int crop,
                            const int* boxes, int use_atomics, cudaStream_t stream) {
   const long long total = (long long)crop * crop * n_tiles;
@@ -561,7 +607,10 @@ int launch_vote_accumulate(uint32_t* counter, int Hs, int Ws, const uint8_t* cls
   ProfScope prof(CAT_VOTE, 0, static_cast<double>(total) * 9, stream);
   const bool vec = !use_atomics && (crop % 4 == 0) && (Ws % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(counter) % 16 == 0) && (reinterpret_cast<uintptr_t>(cls) % 4 == 0);
-  if (vec)
+  if (vec && crop % 8 == 0 && reinterpret_cast<uintptr_t>(cls) % 8 == 0)
+    vote_accumulate_vec8_kernel<<<blocks_for(total / 8, 256), 256, 0, stream>>>(counter, Hs, Ws, cls, n_tiles, crop,
+                                                                               boxes);
+  else if (vec)
     vote_accumulate_vec4_kernel<<<blocks_for(total / 4, 256), 256, 0, stream>>>(counter, Hs, Ws, cls, n_tiles, crop,
                                                                                boxes);
   else
