@@ -528,7 +528,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-tiles", type=int, default=2)
+    ap.add_argument("--cpu-tiles", type=int, default=6)
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg (BASELINE configs[3])")
     ap.add_argument("--train-steps", type=int, default=3)
     ap.add_argument("--no-fast-path", action="store_true", help="skip the query-half-only decoder leg")
