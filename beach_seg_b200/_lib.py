@@ -99,6 +99,7 @@ SIGNATURES = {
     "bseg_gemm_set_cta_pairs": (_i, [_i]),
     "bseg_gemm_set_small_tiles": (_i, [_i]),
     "bseg_gemm_set_fused_ln": (_i, [_i]),
+    "bseg_set_pdl": (_i, [_i]),
     "bseg_gemm_resid_ln_scratch_bytes": (C.c_size_t, [_ll]),
     "bseg_gemm_bf16_resid_ln": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
     "bseg_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp]),

@@ -421,6 +421,7 @@ int forward_impl(bseg_handle* h, const float* pixel_values, const float* prompt_
                  const float* prompt_masks, int B, int embedding_type, int P, const FwdBufs& fb, float* pred_masks,
                  cudaStream_t stream, bool query_half_only = false) {
   int rc;
+  const PdlScope pdl_scope(B <= kPdlMaxBatch);  // programmatic dependent launch for small forwards (host_utils.h)
   const int kT = h->T;  // tokens of the stacked image (shadows the 448-path constant: 1568, or 2048 for native 512-px tiles)
   // ---- embeddings: patchify + GEMM (modeling_seggpt.py:713-737, 163-206) ----
   __nv_bfloat16* a_patch = fb.mlp;
@@ -619,7 +620,7 @@ static int forward_entry(bool query_half_only, bseg_handle* h, const float* pixe
       cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
     return eager();  // (per-launch event timing and a caller's own capture both need the plain launch sequence)
   const bseg_handle::GraphKey key{pixel_values, prompt_pixel_values, prompt_masks, workspace, pred_masks, batch,
-                                  embedding_type, ensemble_prompts, query_half_only ? 1 : 0, gemm_set_cta_pairs(-1) | (gemm_set_small_tiles(-1) << 1) | (gemm_set_fused_ln(-1) << 2)};
+                                  embedding_type, ensemble_prompts, query_half_only ? 1 : 0, gemm_set_cta_pairs(-1) | (gemm_set_small_tiles(-1) << 1) | (gemm_set_fused_ln(-1) << 2) | (pdl_set(-1) << 4)};
   for (auto it = h->graphs.begin(); it != h->graphs.end(); ++it) {
     if (!(it->key == key)) continue;
     h->graphs.splice(h->graphs.begin(), h->graphs, it);  // most recently used first
@@ -1158,6 +1159,7 @@ int bseg_loss_smoothl1_fwd_bwd(const float* pred, const float* labels, const uin
 int bseg_gemm_set_cta_pairs(int on) { return gemm_set_cta_pairs(on); }
 int bseg_gemm_set_small_tiles(int on) { return gemm_set_small_tiles(on); }
 int bseg_gemm_set_fused_ln(int on) { return gemm_set_fused_ln(on); }
+int bseg_set_pdl(int on) { return pdl_set(on); }
 
 size_t bseg_gemm_resid_ln_scratch_bytes(long long M) {
   if (M <= 0) return 0;

@@ -189,6 +189,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                      const __grid_constant__ CUtensorMap tmap_vt, const __grid_constant__ CUtensorMap tmap_rel,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, int heads) {
   using namespace attn;
+  pdl_launch_dependents();
   constexpr int kQTile = Cfg::kQTile, kGridW = Cfg::kGridW, kGridH = Cfg::kGridH, kRows = Cfg::kRowsPerKB;
   constexpr int kKB = Cfg::kKB, kT = Cfg::kT, kNumKB = Cfg::kNumKB, kStages = Cfg::kStages;
   constexpr int kRelH = Cfg::kRelH, kRelW = Cfg::kRelW, kRelRows = Cfg::kRelRows;
@@ -278,6 +279,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  pdl_wait();  // (barriers, TMEM and the one-hot operands above were set up under the tail of the QKV GEMM)
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kRegsControl));
@@ -644,8 +646,7 @@ static int launch_attention_t(const __nv_bfloat16* q, const __nv_bfloat16* k, co
   ProfScope prof(CAT_ATTENTION,
                  static_cast<double>(nseq) * heads * (4.0 * kT * kT * 64 + 2.0 * kT * (Cfg::kGridH + Cfg::kGridW) * 64),
                  static_cast<double>(nseq) * heads * kT * 64 * 2 * 4, stream);
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, tr, out, lse_out, heads);
-  BSEG_CHECK_CUDA(cudaGetLastError());
+  BSEG_CHECK_CUDA(launch_pdl(kern, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tq, tk, tv, tr, out, lse_out, heads));
   count_launch();
   return 0;
 }

@@ -36,6 +36,15 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining.  pdl_launch_dependents() lets the NEXT kernel's CTAs be
+// scheduled as soon as every CTA of this grid has started (they then sit in their own pdl_wait()); pdl_wait() blocks
+// until the predecessor grid has completed and its memory operations are visible.  Both are no-ops for a normal launch.
+// Rule of this library: every kernel that is ever launched with the attribute calls pdl_wait() before it touches global
+// memory other than its parameters, so a chain of such kernels stays transitively ordered.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

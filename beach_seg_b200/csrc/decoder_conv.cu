@@ -55,6 +55,7 @@ template <int MODE>
 __global__ void __launch_bounds__(dconv::kThreads, 1)
 decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const dconv::Params prm) {
+  pdl_launch_dependents();
   using namespace dconv;
   const int B = prm.B, H = prm.H, W = prm.W;
   const float eps = prm.eps;
@@ -104,6 +105,7 @@ decoder_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  pdl_wait();  // (the prologue above may run under the tail of the previous kernel)
 
   if (warp == 0) {
     {
@@ -342,8 +344,7 @@ int launch_decoder_conv_t(const __nv_bfloat16* x_nhwc, int rows_in, const __nv_b
   const long long tiles = static_cast<long long>(prm.B) * (prm.H / kTileH - prm.ty_begin) * (prm.W / kTileW);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   ProfScope prof(CAT_DECODER_HEAD, flop, bytes, stream);
-  kern<<<grid, kThreads, kSmemBytes, stream>>>(tx, tw, prm);
-  BSEG_CHECK_CUDA(cudaGetLastError());
+  BSEG_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), kSmemBytes, stream, tx, tw, prm));
   count_launch();
   return 0;
 }

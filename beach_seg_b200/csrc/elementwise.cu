@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(256)
 layernorm1024_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long ldo, long long M,
                      float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -83,8 +85,8 @@ int launch_layernorm1024(const float* x, long long ldx, const float* gamma, cons
                          long long ldo, long long M, float eps, cudaStream_t stream) {
   BSEG_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "layernorm: leading dims must be multiples of 4");
   ProfScope prof(CAT_LAYERNORM, 0, static_cast<double>(M) * 1024 * 6, stream);
-  layernorm1024_kernel<<<blocks_for(M, 8, 148 * 8), 256, 0, stream>>>(x, ldx, gamma, beta, out, ldo, M, eps);
-  BSEG_CHECK_CUDA(cudaGetLastError());
+  BSEG_CHECK_CUDA(launch_pdl(layernorm1024_kernel, dim3(blocks_for(M, 8, 148 * 8)), dim3(256), 0, stream, x, ldx, gamma, beta,
+                             out, ldo, M, eps));
   count_launch();
   return 0;
 }
@@ -100,6 +102,8 @@ int launch_layernorm1024(const float* x, long long ldx, const float* gamma, cons
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ px, const float* __restrict__ prompt_px,
                 const float* __restrict__ prompt_mask, __nv_bfloat16* __restrict__ A, int B, int img) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one thread = 8 consecutive pixels of one image row of one channel; img = 448 (56 x 28 tokens) or 512 (64 x 32)
   const int gw = img >> 4, w8 = img >> 3, T = 2 * gw * gw;
   const long long total = 2LL * B * 3 * (2 * img) * w8;  // (stream, b, c, y, x8)
@@ -134,8 +138,8 @@ int launch_patchify(const float* px, const float* prompt_px, const float* prompt
                     __nv_bfloat16* A, int B, int img, cudaStream_t stream) {
   const long long total = 2LL * B * 3 * (2 * img) * (img / 8);
   ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(total) * 8 * 6, stream);
-  patchify_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, prompt_px, prompt_mask, A, B, img);
-  BSEG_CHECK_CUDA(cudaGetLastError());
+  BSEG_CHECK_CUDA(launch_pdl(patchify_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, stream, px, prompt_px, prompt_mask,
+                             A, B, img));
   count_launch();
   return 0;
 }
@@ -144,6 +148,8 @@ int launch_patchify(const float* px, const float* prompt_px, const float* prompt
 // two-stream merge after layer `merge_index`: h[:B] = (h[:B] + h[B:]) * 0.5   (modeling_seggpt.py:476-479)
 // ----------------------------------------------------------------------------------------------
 __global__ void merge_streams_kernel(float4* __restrict__ h, long long n4_half) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4_half;
        i += (long long)gridDim.x * blockDim.x) {
     float4 a = h[i];
@@ -155,8 +161,8 @@ __global__ void merge_streams_kernel(float4* __restrict__ h, long long n4_half) 
 int launch_merge_streams(float* h, long long n_half, cudaStream_t stream) {
   BSEG_REQUIRE(n_half % 4 == 0, "merge_streams: size must be a multiple of 4");
   ProfScope prof(CAT_ELEMENTWISE, 0, static_cast<double>(n_half) * 12, stream);
-  merge_streams_kernel<<<blocks_for(n_half / 4, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(h), n_half / 4);
-  BSEG_CHECK_CUDA(cudaGetLastError());
+  BSEG_CHECK_CUDA(launch_pdl(merge_streams_kernel, dim3(blocks_for(n_half / 4, 256)), dim3(256), 0, stream,
+                             reinterpret_cast<float4*>(h), n_half / 4));
   count_launch();
   return 0;
 }

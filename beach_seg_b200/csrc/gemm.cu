@@ -63,11 +63,13 @@ static int launch_gemm_pair_t(const __nv_bfloat16* A, long long lda, const __nv_
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // (the kernel calls pdl_wait() after its prologue)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent kernel: launch exactly as many pairs as can be co-resident (normally one per TPC = SMs / 2)
@@ -85,6 +87,7 @@ static int launch_gemm_pair_t(const __nv_bfloat16* A, long long lda, const __nv_
   ProfScope prof(CAT_GEMM, 2.0 * static_cast<double>(M) * N * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream,
                  MODE == EPI_RESID_LN ? (K > 2048 ? 13 : 12) : MODE + (K > 2048 ? 8 : 0));
+  cfg.numAttrs = pdl_active() ? 2 : 1;
   BSEG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, gr, N, K, ep));
   count_launch();
   return 0;
@@ -118,8 +121,7 @@ static int launch_gemm_t(const __nv_bfloat16* A, long long lda, const __nv_bfloa
   ProfScope prof(CAT_GEMM, 2.0 * static_cast<double>(M) * N * K,
                  2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N), stream,
                  MODE == EPI_RESID_LN ? (K > 2048 ? 13 : 12) : MODE + (K > 2048 ? 8 : 0));
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, gr, N, K, ep);
-  BSEG_CHECK_CUDA(cudaGetLastError());
+  BSEG_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, stream, ta, tb, gr, N, K, ep));
   count_launch();
   return 0;
 }

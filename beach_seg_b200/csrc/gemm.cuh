@@ -524,6 +524,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   // launched as clusters of kCtas CTAs: rank 0 is the leader (MMA issuer, owner of the full / tmem_empty barriers)
   const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
@@ -559,6 +560,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  // everything above (barriers, TMEM, tensor-map prefetch) may run under the tail of the previous kernel in the stream
+  pdl_wait();
 
   // EPI_RESID_LN: the epilogue warps carry the residual prefetch, the LayerNorm loads and the row statistics, so the control
   // warpgroup gives its registers away (128 x 56 + 256 x 224 = 384 x 168, the CTA's pool).  ptxas sizes each side of

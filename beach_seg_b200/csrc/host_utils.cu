@@ -78,6 +78,16 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return 0;
 }
 
+static std::atomic<int> g_pdl{1};
+int pdl_set(int on) {
+  const int prev = g_pdl.load(std::memory_order_relaxed);
+  if (on >= 0) g_pdl.store(on != 0, std::memory_order_relaxed);
+  return prev;
+}
+static thread_local bool t_pdl_scope = false;
+bool pdl_active() { return t_pdl_scope && g_pdl.load(std::memory_order_relaxed) != 0; }
+PdlScope::PdlScope(bool on) : prev_(t_pdl_scope) { t_pdl_scope = on; }
+PdlScope::~PdlScope() { t_pdl_scope = prev_; }
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }

@@ -156,3 +156,38 @@ def test_fused_residual_layernorm_levels(dev, small_model):
                 assert torch.equal(one[0], got[2])
     finally:
         L.bseg_gemm_set_fused_ln(prev)
+
+
+def test_programmatic_dependent_launch_is_invisible(dev, small_model):
+    """bseg_set_pdl: launching the forward-path kernels with programmatic stream serialization (each calls
+    griddepcontrol.wait after its prologue) must not change a single bit -- eager, graph-captured and replayed, batch 1
+    and a ragged multi-launch batch -- and the training forward / backward must be unaffected as well."""
+    L = _lib.lib()
+    prev = L.bseg_set_pdl(0)
+    try:
+        outs = {}
+        for on in (0, 1):
+            L.bseg_set_pdl(on)
+            res = []
+            for batch in (1, 5):
+                px, ppx, pm = synth.model_inputs(batch=batch, seed=40 + batch)
+                args = dict(pixel_values=px.to(dev), prompt_pixel_values=ppx.to(dev), prompt_masks=pm.to(dev))
+                with torch.no_grad():
+                    a = small_model(**args).pred_masks.clone()
+                    b = small_model(**args).pred_masks.clone()   # capture
+                    c = small_model(**args).pred_masks.clone()   # replay
+                assert torch.equal(a, b) and torch.equal(a, c)
+                res.append(a)
+            px, ppx, pm = synth.model_inputs(batch=2, seed=50)
+            p = ppx.to(dev).requires_grad_(True)
+            out = small_model(pixel_values=px.to(dev), prompt_pixel_values=p, prompt_masks=pm.to(dev))
+            d = torch.zeros_like(out.pred_masks)
+            d[:, :, 448:] = torch.randn(d[:, :, 448:].shape, generator=torch.Generator().manual_seed(3)).to(dev)
+            out.pred_masks.backward(d)
+            torch.cuda.synchronize()
+            res += [out.pred_masks.detach().clone(), p.grad.clone()]
+            outs[on] = res
+        for x, y in zip(outs[0], outs[1]):
+            assert torch.equal(x, y)
+    finally:
+        L.bseg_set_pdl(prev)
