@@ -515,6 +515,15 @@ def latency_leg(args, dev, model, predictor, scene, nodata, stats, boxes, prompt
         floor = max(0.741e9 / (peaks["hbm"] * 1e9), B * FWD_FLOP_PER_TILE / (peaks["tensor"] * 1e12)) * 1e3
         out[f"batch{B}"] = {"ms_per_launch": ms / reps, "ms_per_tile": ms / reps / B, "host_enqueue_ms": host_ms,
                             "floor_ms_per_launch": floor, "frac_of_floor": floor / (ms / reps)}
+        if B == 1:  # the same launch without programmatic dependent launch (bseg_set_pdl; on for <= 2 tiles by default)
+            from beach_seg_b200 import _lib
+            L = _lib.lib()
+            prev = L.bseg_set_pdl(0)
+            for _ in range(3):
+                step()
+            ms0, _ = timed(step, reps, want_ranks=True)
+            L.bseg_set_pdl(prev)
+            out["batch1"]["ms_per_launch_without_pdl"] = ms0 / reps
     return out
 
 
