@@ -723,7 +723,9 @@ def main():
                 "frac": gemm_tflops / peaks["tensor"], "peak_source": peaks["source"] + " bf16_tflops_sustained",
                 "traffic": None, "avg_launch_ms": pms[g] / max(pl[g], 1),
                 "flop_per_launch": pw[g] / max(pl[g], 1)}
-    tfile = ROOT / "profiles" / "r01_gemm_traffic.json"
+    tfile = ROOT / "profiles" / "r02_gemm_traffic.json"  # (latest capture; r01_gemm_traffic.json: 2.344 GB per launch)
+    if not tfile.exists():
+        tfile = ROOT / "profiles" / "r01_gemm_traffic.json"
     if tfile.exists():  # DRAM bytes per launch from the committed `ncu --set full` capture of the layer GEMMs
         t = json.loads(tfile.read_text())
         roofline["traffic"] = t["per_launch_avg_dram_bytes"]
